@@ -1,0 +1,286 @@
+"""ORACLE (test infrastructure, not product code) -- Python front end.
+
+* builds ``oracle/_build/liboracle_chain.so`` from ``oracle/chain.cpp`` (our C++
+  restatement) and, when ``/root/reference`` is present, ``oracle/_ref/libmtrng.so``
+  from the reference's own ``src/mtrng/random.cc`` (compiled where it lies, never
+  copied);
+* ``OracleChain``: one CPU Markov chain driven through the same call sequence as
+  ``CtHybSolver.solve`` (cthyb_solver.py:316-400);
+* ``normalise``: the post-processing of ``ctqmc_measure`` (CTQMC.F90:8663-8771)
+  and the density-matrix estimators (CTQMC.F90:2842-3060, 3163-3179).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import atomic as oatomic
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "liboracle_chain.so")
+MTLIB = os.path.join(HERE, "_ref", "libmtrng.so")
+REF_RANDOM_CC = "/root/reference/src/mtrng/random.cc"
+
+
+def build(force: bool = False):
+    """Compile the oracle (and the reference RNG when its source is reachable)."""
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    src = os.path.join(HERE, "chain.cpp")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O3", "-march=x86-64-v2", "-std=c++17", "-shared", "-fPIC",
+                               "-o", LIB, src, "-ldl"])
+    if os.path.exists(REF_RANDOM_CC) and (force or not os.path.exists(MTLIB)):
+        os.makedirs(os.path.dirname(MTLIB), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++11", "-shared", "-fPIC", "-o", MTLIB, REF_RANDOM_CC])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        L.orc_create.restype = C.c_void_p
+        L.orc_grnd.restype = C.c_double
+        L.orc_trace_of.restype = C.c_double
+        L.orc_log_count.restype = C.c_longlong
+        L.orc_rng_counter.restype = C.c_ulonglong
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class OracleChain:
+    LOGW = 20
+
+    def __init__(self, problem, rng="philox", seed=43890, chain=0, **qmc_over):
+        """problem: w2dynamics_b200.problems.Problem (inputs only -- no engine code)."""
+        L = lib()
+        from w2dynamics_b200.problems import QMC_DEFAULTS
+        q = dict(QMC_DEFAULTS)
+        q.update(problem.qmc)
+        q.update(qmc_over)
+        self.q = q
+        self.problem = problem
+        nb = problem.nbands
+        self.nb, self.nf = nb, 2 * nb
+        at = oatomic.build_atomic(nb, problem.quantum_numbers, problem.u_matrix, problem.muimp,
+                                  q["EPSBLOCK"], q["EPSEVEC"])
+        self.at = at
+        tb = oatomic.pack_tables(at)
+        self._keep = tb
+        first_state = np.array([int(b[0]) for b in at.block_states], dtype=np.int32)
+        state2sst = at.states2sst.astype(np.int32)
+        ftd = np.ascontiguousarray(np.stack([problem.ftau[b, s, b, s, :] for b in range(nb) for s in range(2)]))
+        self.nftau = ftd.shape[1]
+        self.ntau, self.nleg, self.maxhisto = int(q["Ntau"]), int(q["NLegMax"]), int(q["MaxHisto"])
+        self.beta = float(problem.beta)
+        self.h = C.c_void_p(L.orc_create(
+            C.c_int(at.nsst), C.c_int(nb), _p(tb["dim"], C.c_int), _p(tb["offset"], C.c_int),
+            _p(tb["connect"], C.c_int), _p(tb["op_off"], C.c_longlong), _p(tb["opdata"], C.c_double),
+            C.c_longlong(tb["opdata"].size), _p(tb["evals"], C.c_double), C.c_double(at.egs),
+            _p(first_state, C.c_int), _p(state2sst, C.c_int), _p(ftd, C.c_double), C.c_int(self.nftau),
+            C.c_double(self.beta), C.c_int(self.ntau), C.c_int(self.nleg), C.c_int(self.maxhisto),
+            C.c_int(int(q["NCorr"])), C.c_double(q["PercentageGlobalMove"]),
+            C.c_double(q["PercentageTauShiftMove"]), C.c_double(q["Percentage4OperatorMove"]),
+            C.c_double(q["PercentageOuterMove"]), C.c_double(q["TaudiffMax"]),
+            C.c_int(int("Szt" in problem.quantum_numbers)), C.c_int(int(q["MeasDensityMatrix"]))))
+        kind = 0 if rng == "mt" else 1
+        rc = L.orc_init_rnd(self.h, C.c_int(kind), C.c_uint(seed), C.c_uint(chain), MTLIB.encode())
+        if rc != 0:
+            raise RuntimeError("oracle RNG init failed (%d); libmtrng.so missing?" % rc)
+        L.orc_init_trace(self.h)
+        if q["TaudiffMax"] > 0:
+            L.orc_set_taudiffmax(self.h, C.c_double(q["TaudiffMax"]))
+        self._log = None
+
+    def __del__(self):
+        try:
+            lib().orc_destroy(self.h)
+        except Exception:
+            pass
+
+    # --- driver calls (names mirror the mctqmc surface)
+    def set_taudiffmax(self, t):
+        lib().orc_set_taudiffmax(self.h, C.c_double(t))
+
+    def warmup(self, n):
+        lib().orc_warmup(self.h, C.c_longlong(n))
+
+    def measure(self, nmeas, reset=True):
+        lib().orc_measure(self.h, C.c_longlong(nmeas), C.c_int(int(reset)))
+
+    def measure_once(self):
+        lib().orc_measure_once(self.h)
+
+    def init_counters(self):
+        lib().orc_init_counters(self.h)
+
+    def steps(self, n, log=False):
+        L = lib()
+        if log:
+            buf = np.zeros((n, self.LOGW))
+            L.orc_set_log(self.h, _p(buf, C.c_double), C.c_longlong(n))
+            L.orc_steps(self.h, C.c_longlong(n))
+            cnt = L.orc_log_count(self.h)
+            L.orc_set_log(self.h, None, C.c_longlong(0))
+            return buf[:cnt]
+        L.orc_steps(self.h, C.c_longlong(n))
+        return None
+
+    @property
+    def error(self):
+        return lib().orc_error(self.h)
+
+    # --- state
+    def config(self):
+        L = lib()
+        n = L.orc_noper(self.h)
+        taus = np.zeros(n)
+        orbs = np.zeros(n, dtype=np.int32)
+        spins = np.zeros(n, dtype=np.int32)
+        cas = np.zeros(n, dtype=np.int32)
+        if n:
+            L.orc_get_config(self.h, _p(taus, C.c_double), _p(orbs, C.c_int), _p(spins, C.c_int), _p(cas, C.c_int))
+        return dict(taus=taus, orbs=orbs, spins=spins, cas=cas, outer_sst=L.orc_outer_sst(self.h),
+                    window_position=L.orc_window_position(self.h))
+
+    def set_config(self, taus, orbs, spins, cas, outer_sst):
+        taus = np.ascontiguousarray(taus, dtype=np.float64)
+        orbs = np.ascontiguousarray(orbs, dtype=np.int32)
+        spins = np.ascontiguousarray(spins, dtype=np.int32)
+        cas = np.ascontiguousarray(cas, dtype=np.int32)
+        lib().orc_set_config(self.h, C.c_int(len(taus)), _p(taus, C.c_double), _p(orbs, C.c_int),
+                             _p(spins, C.c_int), _p(cas, C.c_int), C.c_int(outer_sst))
+
+    def scalars(self):
+        out = np.zeros(8)
+        lib().orc_get_scalars(self.h, _p(out, C.c_double))
+        return dict(trace_log=out[0], trace_sign=out[1], det_log=out[2], det_sign=out[3], cfgsign=out[4],
+                    meas_sign=out[5], cnt_meas=int(out[6]), cnt_steps=int(out[7]))
+
+    def counters(self):
+        out = np.zeros(11)
+        lib().orc_get_counters(self.h, _p(out, C.c_double))
+        names = ["TryAdd", "TryRem", "TryGlob", "TryShift", "AccAdd", "AccRem", "AccGlob", "AccShift",
+                 "AccQNAdd", "AccQNRem", "AccQNGlob"]
+        return dict(zip(names, out))
+
+    def kf(self):
+        return np.array([lib().orc_kf(self.h, C.c_int(f)) for f in range(self.nf)])
+
+    def minv(self, f, scratch=False):
+        k = int(self.kf()[f])
+        out = np.zeros((k, k), order="F")
+        if k:
+            (lib().orc_scratch_minv if scratch else lib().orc_get_minv)(self.h, C.c_int(f), _p(out, C.c_double))
+        return out
+
+    def scratch_det(self):
+        a, b = C.c_double(), C.c_double()
+        lib().orc_scratch_det(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def trace_of(self, outer_sst):
+        sg = C.c_double()
+        lg = lib().orc_trace_of(self.h, C.c_int(outer_sst), C.byref(sg))
+        return lg, sg.value
+
+    def npairs(self):
+        return lib().orc_npairs(self.h)
+
+    # --- accumulators
+    def raw(self):
+        at = self.at
+        nf, ns = self.nf, at.nstates
+        r = dict(gtau=np.zeros((nf, self.ntau)), gleg=np.zeros((nf, self.nleg)),
+                 histo=np.zeros((nf, self.maxhisto + 1)), dens=np.zeros((ns, ns)),
+                 outer_hist=np.zeros(at.nsst), sign_hist=np.zeros(at.nsst), contrib_sst=np.zeros(at.nsst),
+                 outerstate_hist=np.zeros(ns), signstate_hist=np.zeros(ns), contrib_state=np.zeros(ns),
+                 accpair=np.zeros((nf, self.ntau), dtype=np.int64))
+        lib().orc_get_accum(self.h, *[_p(r[k], C.c_double) for k in
+                                      ("gtau", "gleg", "histo", "dens", "outer_hist", "sign_hist", "contrib_sst",
+                                       "outerstate_hist", "signstate_hist", "contrib_state")],
+                            _p(r["accpair"], C.c_longlong))
+        r.update(self.scalars())
+        r.update(self.counters())
+        return r
+
+    def results(self):
+        return normalise(self.raw(), self.at, self.beta)
+
+
+def density_estimators(dm_eb, at):
+    """occ / rho1 from the (normalised) eigenbasis density matrix, then EB -> occupation
+    basis (CTQMC.F90:2884-2942, 3020-3060, 3163-3179).  rho2 is left to the product tests
+    (it is checked against the same formula there)."""
+    nb = at.nbands
+    occ = np.zeros((nb, 2, nb, 2))
+    rho1 = np.zeros((2 * nb, 2 * nb))
+    blocks = [dm_eb[o:o + d, o:o + d] for o, d in zip(at.offset, at.dim)]
+
+    def op(k, b, s, ca):
+        return at.psis_eb.get((k, b, s, ca))
+    for b1 in range(nb):
+        for s1 in range(2):
+            for b2 in range(nb):
+                for s2 in range(2):
+                    for k in range(at.nsst):
+                        n1 = at.connect[k, b1, s1, 1]
+                        n2 = at.connect[k, b2, s2, 1]
+                        if n1 >= 0 and n2 >= 0:
+                            # Tr[rho c2^+ c2 c1^+ c1] restricted to block k
+                            t = blocks[k] @ op(n2, b2, s2, 1) @ op(k, b2, s2, 2) @ op(n1, b1, s1, 1) @ op(k, b1, s1, 2)
+                            occ[b1, s1, b2, s2] += np.trace(t)
+                        if n1 >= 0 and at.connect[n1, b2, s2, 0] == k:
+                            t = blocks[k] @ op(n1, b2, s2, 1) @ op(k, b1, s1, 2)
+                            rho1[2 * b2 + s2, 2 * b1 + s1] += np.trace(t)
+    dm_occ = dm_eb.copy()
+    for k in range(at.nsst):
+        o, d = at.offset[k], at.dim[k]
+        dm_occ[o:o + d, o:o + d] = at.evec[k] @ blocks[k] @ at.evec[k].T
+    return occ, rho1, dm_occ
+
+
+def normalise(raw, at, beta):
+    """ctqmc_measure post-processing (CTQMC.F90:8663-8771)."""
+    n = raw["cnt_meas"]
+    nb = at.nbands
+    ntau = raw["gtau"].shape[1]
+    nleg = raw["gleg"].shape[1]
+    mean_sign = raw["meas_sign"] / n
+    zs = -1.0 / (n * mean_sign)
+    out = {"sign": mean_sign}
+    out["gtau"] = (-(raw["gtau"] / n) / (-mean_sign) * ntau / beta ** 2).reshape(nb, 2, ntau)
+    leg = raw["gleg"] * np.sqrt(2.0 * np.arange(nleg) + 1.0)[None, :] / beta
+    out["gleg"] = (-leg * zs).reshape(nb, 2, nleg)
+    out["hist"] = (raw["histo"] / n).reshape(nb, 2, -1)
+    dm = raw["dens"] * zs
+    occ, rho1, dm_occ = density_estimators(dm, at)
+    out["occ"], out["rho1"], out["densitymatrix"] = occ, rho1, dm_occ
+    out["densitymatrix_eb"] = dm
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out["sign-sst"] = raw["sign_hist"] / raw["outer_hist"]
+        out["sign-state"] = raw["signstate_hist"] / raw["outerstate_hist"]
+    out["hist-sst"] = raw["outer_hist"] / n
+    out["hist-state"] = raw["outerstate_hist"] / n
+    out["contrib-sst"] = raw["contrib_sst"] / n
+    out["contrib-state"] = raw["contrib_state"] / n
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out["accept-ins"] = raw["AccAdd"] / raw["TryAdd"]
+        out["accept-rem"] = raw["AccRem"] / raw["TryRem"]
+        out["accept-glob"] = raw["AccGlob"] / raw["TryGlob"]
+        out["accept-shift"] = raw["AccShift"] / raw["TryShift"]
+    out["accept-pair-tau"] = raw["accpair"].reshape(nb, 2, ntau)
+    return out
