@@ -1,0 +1,351 @@
+// C ABI of the engine (see include/w2b_cthyb.h) -- a process-wide singleton like the reference's
+// Fortran module (CTQMC.F90 module variables; cthyb_solver.py:96-98).
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/w2b_cthyb.h"
+#include "engine.hpp"
+#include "params.hpp"
+#include "postproc.hpp"
+
+namespace {
+
+using namespace w2b;
+
+struct Solver {
+    Params par;
+    bool have_par = false;
+    int seed = 0;
+    std::unique_ptr<Engine> eng;
+    EngineOptions opt;
+    long long nmeas_override = -1;
+    int device = -1;
+    // derived
+    double beta = 0; int nb = 0; long long nmeas = 0; int ncorr = 100;
+    double cfg_taudiffmax = -1;
+    std::vector<int> dens_off;
+    ResultSet res; bool have_res = false;
+    std::vector<std::vector<double>> bin_gtau, bin_gleg, bin_occ; std::vector<double> bin_sign;
+    double time_warmup = 0, time_sim = 0, time_sim_steps = 0;
+    std::string err;
+};
+Solver S;
+
+int fail(const std::string& m) { S.err = m; return 1; }
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+template <class F> int guarded(F f) {
+    try { f(); return 0; } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+void require_engine() { if (!S.eng) throw std::runtime_error("solver not initialised (call w2b_init_solver)"); }
+
+void check_supported(const Params& p) {
+    auto zero_i = [&](const char* k) { if (p.has(k) && p.integer(k) != 0) throw std::runtime_error(std::string(k) + " != 0 is outside the implemented hot path"); };
+    auto zero_r = [&](const char* k) { if (p.has(k) && p.real(k) != 0.0) throw std::runtime_error(std::string(k) + " != 0 is outside the implemented hot path"); };
+    zero_i("segment"); zero_i("offdiag"); zero_i("statesampling"); zero_i("Uw"); zero_i("Phonon"); zero_i("NSymMove");
+    zero_i("MeasGiw"); zero_i("MeasG2iw"); zero_i("MeasSusz"); zero_i("MeasExpResDensityMatrix"); zero_i("FourPnt");
+    zero_i("MeasSsquare"); zero_i("MeasGtauDetRat"); zero_i("flavourchange_moves"); zero_i("Gtau_mean_step"); zero_i("Gtau_mid_step"); zero_i("sign_step");
+    zero_r("PercentageOuterMove"); zero_r("Percentage4OperatorMove");
+    if (p.has("Eigenbasis") && p.integer("Eigenbasis") == 0) throw std::runtime_error("You requested Krylov, but this no longer supported.");
+    if (p.has("EnableOuterTruncation") && p.str("EnableOuterTruncation") == "YES") throw std::runtime_error("EnableOuterTruncation is outside the implemented hot path");
+    if (p.has("AccumGtau") && p.integer("AccumGtau") != 1) throw std::runtime_error("only AccumGtau = 1 (mean accumulator) is implemented");
+}
+
+void finalize_results() {
+    require_engine();
+    Engine& E = *S.eng;
+    std::vector<double> acc; std::vector<unsigned long long> accpair;
+    E.download_accum(acc, accpair);
+    const int nbins = E.R.nbins; const long long st = E.accum_doubles;
+    std::vector<double> tot(st, 0.0);
+    for (int b = 0; b < nbins; ++b) for (long long i = 0; i < st; ++i) tot[i] += acc[(size_t)b * st + i];
+    if (tot[E.A.o_cnt] <= 0.0) throw std::runtime_error("No measurements");
+    S.res = ResultSet();
+    normalise_slab(E.at, E.A, E.R, S.beta, tot.data(), S.dens_off, true, S.res);
+    // per-bin samples (for error bars across chain groups)
+    S.bin_gtau.clear(); S.bin_gleg.clear(); S.bin_occ.clear(); S.bin_sign.clear();
+    for (int b = 0; b < nbins; ++b) {
+        const double* slab = acc.data() + (size_t)b * st;
+        if (slab[E.A.o_cnt] <= 0.0) continue;
+        ResultSet r; normalise_slab(E.at, E.A, E.R, S.beta, slab, S.dens_off, false, r);
+        S.bin_gtau.push_back(r.arr["gtau"]); S.bin_gleg.push_back(r.arr["gleg"]); S.bin_occ.push_back(r.arr["occ"]);
+        S.bin_sign.push_back(r.scal["mean_sign"]);
+    }
+    // move statistics (CTQMC.F90:8680-8695)
+    std::vector<unsigned long long> cnt; E.get_counters(cnt);
+    auto ratio = [](unsigned long long a, unsigned long long b) { return b ? (double)a / (double)b : std::numeric_limits<double>::quiet_NaN(); };
+    std::vector<double> accadd(16, 0.0), accrem(16, 0.0);
+    accadd[0] = ratio(cnt[C_ACCADD], cnt[C_TRYADD]); accrem[0] = ratio(cnt[C_ACCREM], cnt[C_TRYREM]);
+    S.res.arr["accadd"] = accadd; S.res.arr["accrem"] = accrem;
+    S.res.scal["accglob"] = ratio(cnt[C_ACCGLOB], cnt[C_TRYGLOB]); S.res.scal["accshift"] = ratio(cnt[C_ACCSHIFT], cnt[C_TRYSHIFT]);
+    S.res.scal["accadd4"] = std::numeric_limits<double>::quiet_NaN(); S.res.scal["accrem4"] = std::numeric_limits<double>::quiet_NaN();
+    S.res.scal["accflavc"] = std::numeric_limits<double>::quiet_NaN();
+    S.res.scal["steps"] = (double)cnt[C_STEPS];
+    std::vector<double> ap(accpair.size());
+    const int nf = E.T.nf, nbd = E.T.nb, ntau = E.R.ntau;
+    for (int b = 0; b < nbd; ++b) for (int s = 0; s < 2; ++s) for (int t = 0; t < ntau; ++t) ap[b + (size_t)nbd * (s + 2 * t)] = (double)accpair[(size_t)(2 * b + s) * ntau + t];
+    S.res.arr["accpair"] = ap;
+    // static tables Python also reads (CTQMC.F90:8053-8066)
+    const AtomicTables& at = E.at;
+    std::vector<double> sss(at.nstates), ene(at.nstates), occm((size_t)at.nstates * nbd * 2);
+    for (int k = 0; k < at.nsst; ++k) for (int i = 0; i < at.dim[k]; ++i) {
+        int idx = at.offset[k] + i; sss[idx] = k; ene[idx] = at.evals[idx];
+        int st_ = at.block_states[k][i];
+        for (int b = 0; b < nbd; ++b) for (int s = 0; s < 2; ++s) occm[idx + (size_t)at.nstates * (b + (size_t)nbd * s)] = (st_ >> (b + s * nbd)) & 1;
+    }
+    S.res.arr["statessuperstates"] = sss; S.res.arr["eigenstatesenergies"] = ene; S.res.arr["occbasismapping"] = occm;
+    S.res.arr["gtau_full"] = std::vector<double>((size_t)nf * nf * ntau, 0.0);
+    S.res.arr["gleg_full"] = std::vector<double>((size_t)nf * nf * E.R.nlegmax, 0.0);
+    S.res.arr["rhisto"] = std::vector<double>(100, 0.0);
+    S.res.arr["lhisto"] = std::vector<double>(100, std::numeric_limits<double>::quiet_NaN());   // 0/0 in the reference (CTQMC.F90:8698)
+    S.have_res = true;
+}
+
+void run_blocks(long long nmeas, bool timing) {
+    Engine& E = *S.eng;
+#if W2B_DEVICE
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float steps_ms = 0.f;
+#endif
+    for (long long i = 0; i < nmeas; ++i) {
+#if W2B_DEVICE
+        if (timing) cudaEventRecord(e0);
+#endif
+        E.sweep(S.ncorr);
+#if W2B_DEVICE
+        if (timing) cudaEventRecord(e1);
+#endif
+        E.measure();
+#if W2B_DEVICE
+        if (timing) { cudaEventSynchronize(e1); float ms = 0; cudaEventElapsedTime(&ms, e0, e1); steps_ms += ms; }
+#endif
+    }
+    E.sync();
+#if W2B_DEVICE
+    if (timing) S.time_sim_steps += steps_ms * 1e-3;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+#endif
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* w2b_last_error(void) { return S.err.c_str(); }
+
+int w2b_init_rnd(int nseed) { S.seed = nseed; return 0; }
+
+int w2b_init_paras(const char* parastr, size_t len) {
+    return guarded([&] { S.par.parse(std::string(parastr, len)); S.have_par = true; check_supported(S.par); });
+}
+
+int w2b_set_option(const char* key, double value) {
+    std::string k(key);
+    if (k == "nchains") S.opt.nchains = (int)value;
+    else if (k == "nbins") S.opt.nbins = (int)value;
+    else if (k == "kcap") S.opt.kcap = (int)value;
+    else if (k == "ops_cap") S.opt.ops_cap = (int)value;
+    else if (k == "chain_base") S.opt.chain_base = (unsigned)value;
+    else if (k == "device") S.device = (int)value;
+    else if (k == "nmeas_override") S.nmeas_override = (long long)value;
+    else return fail("unknown option " + k);
+    return 0;
+}
+
+int w2b_init_solver(const double* u_matrix, const double* ftau_full, const double* muimp_full, const double* screening,
+                    int iter_no, int nftau, int nbands) {
+    (void)screening; (void)iter_no;
+    return guarded([&] {
+        if (!S.have_par) throw std::runtime_error("init_paras must be called before init_solver");
+        const Params& p = S.par;
+#if W2B_DEVICE
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("no CUDA device available: the B200 engine has no CPU fallback");
+        if (S.device >= 0) W2B_CUDA_CHECK(cudaSetDevice(S.device));
+#endif
+        S.nb = (int)p.integer("Nd");
+        if (S.nb != nbands) throw std::runtime_error("Nd in the parameter string does not match the array extents");
+        S.beta = p.real("beta");
+        S.nmeas = S.nmeas_override >= 0 ? S.nmeas_override : p.integer("Nmeas");
+        S.ncorr = (int)p.integer("NCorr");
+        S.cfg_taudiffmax = p.real("TaudiffMax");
+        const int nb = S.nb, nf = 2 * nb;
+        AtomicTables at = build_atomic(nb, p.str("QuantumNumbers"), u_matrix, muimp_full, p.real("EPSBLOCK"), p.real("EPSEVEC"));
+        // diagonal hybridisation (CTQMC.F90:7950-7955): Ftau(b,s,:) = Ftau_full(b,s,b,s,:)
+        std::vector<double> fd((size_t)nf * nftau);
+        for (int b = 0; b < nb; ++b) for (int s = 0; s < 2; ++s) for (int t = 0; t < nftau; ++t)
+            fd[(size_t)(2 * b + s) * nftau + t] = ftau_full[b + (size_t)nb * (s + 2 * (b + (size_t)nb * (s + 2 * (size_t)t)))];
+        Run R{};
+        R.pglob = p.real("PercentageGlobalMove"); R.pshift = p.real("PercentageTauShiftMove");
+        R.p4op = p.real_or("Percentage4OperatorMove", 0.0); R.pouter = p.real_or("PercentageOuterMove", 0.0);
+        R.ntau = (int)p.integer("Ntau"); R.nlegmax = (int)p.integer("NLegMax"); R.maxhisto = (int)p.integer("MaxHisto");
+        R.has_szt = p.str("QuantumNumbers").find("Szt") != std::string::npos;
+        R.meas_dm = p.integer("MeasDensityMatrix") != 0;
+        R.nbins = std::max(1, std::min(S.opt.nbins, S.opt.nchains));
+        R.seed = (unsigned)S.seed; R.chain_base = S.opt.chain_base;
+        // init_window with the configured TaudiffMax, NSlide fixed here (CTQMC.F90:8068-8069)
+        if (S.cfg_taudiffmax > 0.0) { R.taudiff_max = S.cfg_taudiffmax; R.num_windows = std::max((int)std::floor(S.beta / S.cfg_taudiffmax) - 1, 1); }
+        else { R.taudiff_max = S.beta; R.num_windows = 1; }
+        R.nslide = std::max(2 * nb, (int)std::floor((double)S.ncorr / (double)R.num_windows));
+        S.eng.reset(new Engine());
+        S.opt.seed = (unsigned)S.seed;
+        S.eng->setup(at, fd, nftau, S.beta, R, S.opt);
+        S.dens_off.assign(at.nsst, 0);
+        for (int k = 0; k < at.nsst; ++k) S.dens_off[k] = at.offset[k];      // 1x1 blocks: one entry per state
+        S.have_res = false; S.time_warmup = S.time_sim = S.time_sim_steps = 0;
+        S.eng->sync();
+    });
+}
+
+int w2b_set_taudiffmax(double t) { return guarded([&] { require_engine(); S.eng->set_taudiffmax(t); }); }
+int w2b_init_counters(void) { return guarded([&] { require_engine(); S.eng->reset_counters(); }); }
+
+int w2b_ctqmc_warmup(long long nwarmups) {
+    return guarded([&] {
+        require_engine();
+        double t0 = now();
+        S.eng->reset_counters();
+        const long long chunk = 1000;
+        for (long long done = 0; done < nwarmups; done += chunk) S.eng->sweep(std::min(chunk, nwarmups - done));
+        S.eng->sync();
+        S.time_warmup = now() - t0;
+    });
+}
+
+int w2b_sample(long long nmeas, int reset) {
+    return guarded([&] {
+        require_engine();
+        double t0 = now();
+        if (reset) S.eng->zero_accum();
+        S.eng->reset_counters();
+        run_blocks(nmeas, true);
+        S.time_sim += now() - t0;
+    });
+}
+int w2b_finalize(void) { return guarded([&] { finalize_results(); }); }
+
+int w2b_ctqmc_measure(int isector, int icomponent) {
+    if (isector != 1) return fail("only the partition-function sector (isector = 1) is implemented");
+    (void)icomponent;
+    int rc = w2b_sample(S.nmeas, 1);
+    if (rc) return rc;
+    return w2b_finalize();
+}
+
+int w2b_ctqmc_calibrate(int, int, int, int, int) { return fail("ctqmc_calibrate is not implemented yet: set TaudiffMax > 0"); }
+
+int w2b_block(long long nsweep, int do_measure) {
+    return guarded([&] { require_engine(); S.eng->sweep(nsweep); if (do_measure) S.eng->measure(); });
+}
+int w2b_sync(void) { return guarded([&] { require_engine(); S.eng->sync(); }); }
+
+int w2b_accum_device(void** p, size_t* n) {
+    return guarded([&] { require_engine(); *p = (void*)S.eng->A.base; *n = (size_t)S.eng->R.nbins * S.eng->accum_doubles; });
+}
+
+int w2b_dest_ctqmc(void) { S.eng.reset(); S.have_res = false; return 0; }
+int w2b_dest_paras(void) { S.par.clear(); S.have_par = false; return 0; }
+
+// ---------------------------------------------------------------- configurations
+int w2b_get_mc_config_scalars(int chain, int* noper, int* outer_sst, int* outer_state) {
+    return guarded([&] {
+        require_engine();
+        std::vector<int> ih; std::vector<double> dh; S.eng->get_header(chain, ih, dh);
+        *noper = ih[IH_NOPS]; *outer_sst = ih[IH_OUTER]; *outer_state = 1;
+    });
+}
+int w2b_get_mc_config(int chain, int n, double* taus, int* orbs, int* spins, int* cas, int* hashybs, int* outer_sst, int* outer_state) {
+    return guarded([&] {
+        require_engine();
+        std::vector<double> tau; std::vector<unsigned char> code; std::vector<short> sst;
+        S.eng->get_ops(chain, tau, code, sst);
+        if ((int)tau.size() != n) throw std::runtime_error("get_mc_config: size mismatch");
+        for (int i = 0; i < n; ++i) { int f = code[i] >> 1; taus[i] = tau[i]; orbs[i] = f / 2 + 1; spins[i] = f % 2 + 1; cas[i] = (code[i] & 1) + 1; hashybs[i] = -1; }
+        std::vector<int> ih; std::vector<double> dh; S.eng->get_header(chain, ih, dh);
+        *outer_sst = ih[IH_OUTER]; *outer_state = 1;
+    });
+}
+int w2b_set_mc_config(int chain, int n, const double* taus, const int* orbs, const int* spins, const int* cas, const int* hashybs, int outer_sst, int outer_state) {
+    (void)outer_state;
+    return guarded([&] {
+        require_engine();
+        std::vector<unsigned char> code(n);
+        for (int i = 0; i < n; ++i) {
+            if (hashybs && hashybs[i] == 0) throw std::runtime_error("worm operators are outside the implemented hot path");
+            code[i] = (unsigned char)((((orbs[i] - 1) * 2 + (spins[i] - 1)) << 1) | (cas[i] - 1));
+            if (i && !(taus[i] > taus[i - 1])) throw std::runtime_error("set_mc_config: operators must be in ascending tau");
+        }
+        S.eng->set_ops(chain, n, taus, code.data(), outer_sst);
+    });
+}
+int w2b_set_empty_mc_config(int chain, int outer_sst, int outer_state) { return w2b_set_mc_config(chain, 0, nullptr, nullptr, nullptr, nullptr, nullptr, outer_sst, outer_state); }
+
+// ---------------------------------------------------------------- results
+int w2b_get_array(const char* name, double* out, size_t cap, size_t* n) {
+    return guarded([&] {
+        std::string k(name);
+        const std::vector<double>* src = nullptr; std::vector<double> tmp;
+        auto bins = [&](const std::vector<std::vector<double>>& b) { tmp.clear(); for (auto& v : b) tmp.insert(tmp.end(), v.begin(), v.end()); src = &tmp; };
+        if (!S.have_res) throw std::runtime_error("no results: call ctqmc_measure first");
+        if (k == "gtau_bins") bins(S.bin_gtau);
+        else if (k == "gleg_bins") bins(S.bin_gleg);
+        else if (k == "occ_bins") bins(S.bin_occ);
+        else if (k == "sign_bins") { tmp = S.bin_sign; src = &tmp; }
+        else { auto it = S.res.arr.find(k); if (it == S.res.arr.end()) throw std::runtime_error("unknown result array " + k); src = &it->second; }
+        *n = src->size();
+        if (out) std::memcpy(out, src->data(), std::min(cap, src->size()) * sizeof(double));
+    });
+}
+
+int w2b_get_scalar(const char* name, double* out) {
+    return guarded([&] {
+        std::string k(name);
+        if (k == "time_warmup") { *out = S.time_warmup; return; }
+        if (k == "time_sim") { *out = S.time_sim; return; }
+        if (k == "time_sim_steps") { *out = S.time_sim_steps; return; }
+        if (k == "aborted") { *out = 0; return; }
+        if (S.eng) {
+            Engine& E = *S.eng;
+            if (k == "nchains") { *out = E.C.nchains; return; }
+            if (k == "nbins") { *out = E.R.nbins; return; }
+            if (k == "nsst") { *out = E.at.nsst; return; }
+            if (k == "nstates") { *out = E.at.nstates; return; }
+            if (k == "nstatesmax") { *out = E.at.dmax; return; }
+            if (k == "kcap") { *out = E.C.kcap; return; }
+            if (k == "ops_cap") { *out = E.C.ops_cap; return; }
+            if (k == "num_windows") { *out = E.R.num_windows; return; }
+            if (k == "nslide") { *out = E.R.nslide; return; }
+            if (k == "egs") { *out = E.at.egs; return; }
+            if (k == "gpu_launches") { *out = (double)E.launches; return; }
+            if (k == "max_k" || k == "max_ops" || k == "error_flags") { int mk, mo; int e = E.error_flags(&mk, &mo); *out = k == "max_k" ? mk : k == "max_ops" ? mo : e; return; }
+        }
+        if (S.have_res) { auto it = S.res.scal.find(k); if (it != S.res.scal.end()) { *out = it->second; return; } }
+        throw std::runtime_error("unknown scalar " + k);
+    });
+}
+
+// ---------------------------------------------------------------- replay / parity hooks
+int w2b_debug_steps(int chain, long long nsteps, double* log) {
+    return guarded([&] { require_engine(); S.eng->sweep(nsteps, chain, log); S.eng->sync(); });
+}
+int w2b_debug_chain_scalars(int chain, double* out) {
+    return guarded([&] {
+        require_engine();
+        std::vector<int> ih; std::vector<double> dh; S.eng->get_header(chain, ih, dh);
+        out[0] = dh[DH_TRLOG]; out[1] = dh[DH_TRSIGN]; out[2] = dh[DH_DETLOG]; out[3] = dh[DH_DETSIGN]; out[4] = dh[DH_CFGSIGN];
+        out[5] = ih[IH_NOPS]; out[6] = ih[IH_OUTER]; out[7] = ih[IH_ERR];
+    });
+}
+int w2b_debug_minv(int chain, int orbital, int spin, double* out, size_t cap, int* k) {
+    return guarded([&] {
+        require_engine();
+        std::vector<double> m; S.eng->get_minv(chain, (orbital - 1) * 2 + (spin - 1), m, *k);
+        if (out) std::memcpy(out, m.data(), std::min(cap, m.size()) * sizeof(double));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,336 @@
+// Host driver of the chain population: device memory layout, kernel launches, accumulator traffic.
+//
+// Memory layout in HBM (chain-major, every per-chain array contiguous so a warp's accesses coalesce):
+//   op_tau  [chain][ops_cap] f64   op_code [chain][ops_cap] u8   op_sst [chain][ops_cap] i16
+//   tau_c / tau_a [chain][nf][kcap] f64     (time-ordered creator / annihilator times per flavour)
+//   M       [chain][nf+1][kcap][ld] f64     (inverse hybridisation matrices + one spare for out-of-place updates)
+//   ih/dh   [chain][IH_STRIDE] i32 / [DH_STRIDE] f64   (scalar chain state), rng counters, move counters
+//   accumulators [bin][stride] f64          (bin = global chain id mod nbins; reduced with one allreduce per block)
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "atomic.hpp"
+#include "engine_core.hpp"
+
+#if W2B_DEVICE
+#include <cuda_runtime.h>
+#define W2B_CUDA_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); } while (0)
+#endif
+
+namespace w2b {
+
+// ---------------------------------------------------------------- raw memory helpers (device or host-emulation)
+template <class T_> T_* dev_alloc(size_t n) {
+    if (n == 0) n = 1;
+#if W2B_DEVICE
+    void* p = nullptr; W2B_CUDA_CHECK(cudaMalloc(&p, n * sizeof(T_))); W2B_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T_))); return (T_*)p;
+#else
+    return (T_*)std::calloc(n, sizeof(T_));
+#endif
+}
+template <class T_> void dev_free(T_*& p) {
+    if (!p) return;
+#if W2B_DEVICE
+    cudaFree((void*)p);
+#else
+    std::free((void*)p);
+#endif
+    p = nullptr;
+}
+template <class T_> void h2d(T_* d, const T_* h, size_t n) {
+    if (!n) return;
+#if W2B_DEVICE
+    W2B_CUDA_CHECK(cudaMemcpy((void*)d, h, n * sizeof(T_), cudaMemcpyHostToDevice));
+#else
+    std::memcpy((void*)d, h, n * sizeof(T_));
+#endif
+}
+template <class T_> void d2h(T_* h, const T_* d, size_t n) {
+    if (!n) return;
+#if W2B_DEVICE
+    W2B_CUDA_CHECK(cudaMemcpy(h, d, n * sizeof(T_), cudaMemcpyDeviceToHost));
+#else
+    std::memcpy(h, d, n * sizeof(T_));
+#endif
+}
+template <class T_> void dev_zero(T_* d, size_t n) {
+    if (!n) return;
+#if W2B_DEVICE
+    W2B_CUDA_CHECK(cudaMemset((void*)d, 0, n * sizeof(T_)));
+#else
+    std::memset((void*)d, 0, n * sizeof(T_));
+#endif
+}
+template <class T_> T_* dev_upload(const std::vector<T_>& v) { T_* d = dev_alloc<T_>(v.size()); h2d(d, v.data(), v.size()); return d; }
+
+// ---------------------------------------------------------------- kernels
+constexpr int WARPS_PER_CTA = 4;
+
+#if W2B_DEVICE
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_init(Tables T, Run R, Chains C) {
+    int chain = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (chain < C.nchains) init_chain(T, R, C, chain);
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_sweep(Tables T, Run R, Chains C, Accum A, long long nsteps, int wdoubles,
+                                                              int log_chain, double* logbuf) {
+    extern __shared__ double smem[];
+    int warp = threadIdx.x >> 5;
+    int chain = blockIdx.x * WARPS_PER_CTA + warp;
+    if (chain >= C.nchains) return;
+    double* ws = smem + (size_t)warp * wdoubles;
+    int* is = (int*)(ws + 3 * C.kcap);
+    sweep_chain(T, R, C, A, chain, nsteps, ws, is, chain == log_chain ? logbuf : nullptr);
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_measure(Tables T, Run R, Chains C, Accum A) {
+    int chain = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (chain < C.nchains) measure_chain(T, R, C, A, chain);
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R, Chains C, int wdoubles, int only_chain) {
+    extern __shared__ double smem[];
+    int warp = threadIdx.x >> 5;
+    int chain = blockIdx.x * WARPS_PER_CTA + warp;
+    if (chain >= C.nchains || (only_chain >= 0 && chain != only_chain)) return;
+    double* ws = smem + (size_t)warp * wdoubles;
+    int* is = (int*)(ws + 3 * C.kcap);
+    rebuild_chain(T, R, C, chain, ws, is);
+}
+#endif
+
+struct EngineOptions {
+    int nchains = 1024, nbins = 16, kcap = 0, ops_cap = 0;
+    unsigned seed = 0, chain_base = 0;
+};
+
+class Engine {
+public:
+    AtomicTables at;
+    Tables T{};
+    Run R{};
+    Chains C{};
+    Accum A{};
+    EngineOptions opt;
+    long long accum_doubles = 0;       // per bin
+    int wdoubles = 0;                  // per-warp scratch in doubles
+    long long launches = 0;            // kernels launched (bench accounting)
+    std::vector<void*> owned;
+
+    ~Engine() { release(); }
+
+    void release() {
+        for (void* p : owned) {
+#if W2B_DEVICE
+            cudaFree(p);
+#else
+            std::free(p);
+#endif
+        }
+        owned.clear();
+    }
+    template <class T_> T_* keep(T_* p) { owned.push_back((void*)p); return p; }
+
+    // ftau_diag: [nf][nftau] with flavour f = 2*band+spin
+    void setup(const AtomicTables& tables, const std::vector<double>& ftau_diag, int nftau, double beta, const Run& run,
+               const EngineOptions& options) {
+        release();
+        at = tables; opt = options; R = run;
+        if (at.nf > NF_MAX) throw std::runtime_error("too many flavours for this build (NF_MAX)");
+        if (at.dmax > 1) throw std::runtime_error("blocks larger than 1x1 are not supported by the scalar-trace engine yet");
+        const int nf = at.nf, nsst = at.nsst;
+        T.nb = at.nb; T.nf = nf; T.nsst = nsst; T.nops = at.nops; T.dmax = at.dmax; T.nftau = nftau; T.nstates = at.nstates;
+        T.beta = beta; T.egs = at.egs;
+        std::vector<short> conn(at.connect.begin(), at.connect.end());
+        std::vector<double> e0(nsst), elem((size_t)nsst * at.nops, 0.0), ew(nsst), el(nsst);
+        double wsum_ = 0;
+        for (int k = 0; k < nsst; ++k) {
+            e0[k] = at.evals[at.offset[k]];
+            for (int c = 0; c < at.nops; ++c) if (at.op_off[(size_t)k * at.nops + c] >= 0) elem[(size_t)k * at.nops + c] = at.opdata[at.op_off[(size_t)k * at.nops + c]];
+            // empty trace of outer superstate k: sum_j exp(-(E_j - Egs) beta)   (Trace.F90:647-655)
+            double w = 0; for (int j = 0; j < at.dim[k]; ++j) w += std::exp(-(at.evals[at.offset[k] + j] - at.egs) * beta);
+            ew[k] = w; el[k] = std::log(w); wsum_ += w;
+        }
+        for (double& w : ew) w /= wsum_;
+        T.connect = keep(dev_upload(conn)); T.e0 = keep(dev_upload(e0)); T.elem = keep(dev_upload(elem));
+        T.ftau = keep(dev_upload(ftau_diag));
+        T.first_state = keep(dev_upload(at.first_state)); T.state2sst = keep(dev_upload(at.state2sst));
+        T.dim = keep(dev_upload(at.dim)); T.offset = keep(dev_upload(at.offset));
+        T.empty_w = keep(dev_upload(ew)); T.empty_log = keep(dev_upload(el));
+        T.op_off = keep(dev_upload(at.op_off)); T.opdata = keep(dev_upload(at.opdata)); T.evals = keep(dev_upload(at.evals));
+
+        // capacities
+        int kcap = opt.kcap;
+        if (kcap <= 0) { double kd = 0.45 * beta; kcap = (int)(kd + 6.0 * std::sqrt(kd) + 16.0); }
+        kcap = ((kcap + 15) / 16) * 16;
+        int ops_cap = opt.ops_cap > 0 ? opt.ops_cap : 2 * nf * kcap;
+        if (ops_cap > 2 * nf * kcap) ops_cap = 2 * nf * kcap;
+        ops_cap = ((ops_cap + 31) / 32) * 32;
+        const int nc = opt.nchains;
+        C.nchains = nc; C.ops_cap = ops_cap; C.kcap = kcap; C.ld = kcap;
+        C.op_tau = keep(dev_alloc<double>((size_t)nc * ops_cap)); C.op_code = keep(dev_alloc<unsigned char>((size_t)nc * ops_cap));
+        C.op_sst = keep(dev_alloc<short>((size_t)nc * ops_cap));
+        C.sc_tau = keep(dev_alloc<double>((size_t)nc * ops_cap)); C.sc_code = keep(dev_alloc<unsigned char>((size_t)nc * ops_cap));
+        C.sc_sst = keep(dev_alloc<short>((size_t)nc * ops_cap));
+        C.tau_c = keep(dev_alloc<double>((size_t)nc * nf * kcap)); C.tau_a = keep(dev_alloc<double>((size_t)nc * nf * kcap));
+        C.sc_tc = keep(dev_alloc<double>((size_t)nc * nf * kcap)); C.sc_ta = keep(dev_alloc<double>((size_t)nc * nf * kcap));
+        C.M = keep(dev_alloc<double>((size_t)nc * (nf + 1) * kcap * kcap));
+        C.ih = keep(dev_alloc<int>((size_t)nc * IH_STRIDE)); C.dh = keep(dev_alloc<double>((size_t)nc * DH_STRIDE));
+        C.rng_ctr = keep(dev_alloc<unsigned long long>(nc)); C.counters = keep(dev_alloc<unsigned long long>((size_t)nc * C_NCNT));
+        int wints = kcap + 32 + nsst;
+        wdoubles = 3 * kcap + (wints + 1) / 2;
+
+        // accumulators
+        int o = 0;
+        A.o_gtau = o; o += nf * R.ntau; A.o_gleg = o; o += nf * R.nlegmax; A.o_histo = o; o += nf * (R.maxhisto + 1);
+        A.ndens = at.nstates; A.o_dens = o; o += A.ndens;
+        A.o_outer = o; o += nsst; A.o_signsst = o; o += nsst; A.o_contribsst = o; o += nsst;
+        A.o_outerst = o; o += at.nstates; A.o_signst = o; o += at.nstates; A.o_contribst = o; o += at.nstates;
+        A.o_sign = o; o += 1; A.o_cnt = o; o += 1;
+        accum_doubles = o; A.stride = o;
+        A.base = keep(dev_alloc<double>((size_t)R.nbins * o));
+        A.accpair = keep(dev_alloc<unsigned long long>((size_t)nf * R.ntau));
+        init_chains();
+    }
+
+    size_t smem_bytes() const { return (size_t)WARPS_PER_CTA * wdoubles * sizeof(double); }
+    int grid() const { return (C.nchains + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+
+    void sync() {
+#if W2B_DEVICE
+        W2B_CUDA_CHECK(cudaDeviceSynchronize());
+#endif
+    }
+
+    void init_chains() {
+#if W2B_DEVICE
+        k_init<<<grid(), WARPS_PER_CTA * 32>>>(T, R, C); ++launches;
+        W2B_CUDA_CHECK(cudaGetLastError());
+#else
+        for (int c = 0; c < C.nchains; ++c) init_chain(T, R, C, c);
+#endif
+    }
+
+    void set_taudiffmax(double tdm) {          // set_taudiffmax -> init_window (CTQMC.F90:8180, Trace.F90:1608-1648)
+        if (tdm > 0.0) { R.taudiff_max = tdm; R.num_windows = std::max((int)std::floor(T.beta / tdm) - 1, 1); }
+        else { R.taudiff_max = T.beta; R.num_windows = 1; }
+        // window_position = 0, NPairs invalid for every chain
+        std::vector<int> ih((size_t)C.nchains * IH_STRIDE);
+        d2h(ih.data(), C.ih, ih.size());
+        for (int c = 0; c < C.nchains; ++c) { ih[(size_t)c * IH_STRIDE + IH_WPOS] = 0; ih[(size_t)c * IH_STRIDE + IH_NPAIRS] = -1; }
+        h2d(C.ih, ih.data(), ih.size());
+    }
+
+    void reset_counters() {                    // init_counters CTQMC.F90:847-899
+        dev_zero(C.counters, (size_t)C.nchains * C_NCNT);
+        dev_zero(A.accpair, (size_t)T.nf * R.ntau);
+    }
+    void zero_accum() { dev_zero(A.base, (size_t)R.nbins * accum_doubles); }
+
+    // advance every chain by nsteps moves; optionally record the replay log of one chain
+    void sweep(long long nsteps, int log_chain = -1, double* log_host = nullptr) {
+        double* dlog = nullptr;
+        if (log_chain >= 0) dlog = dev_alloc<double>((size_t)nsteps * LOGW);
+#if W2B_DEVICE
+        size_t sm = smem_bytes();
+        static size_t configured = 0;
+        if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+        k_sweep<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, A, nsteps, wdoubles, log_chain, dlog); ++launches;
+        W2B_CUDA_CHECK(cudaGetLastError());
+#else
+        std::vector<double> ws(wdoubles + 8);
+        for (int c = 0; c < C.nchains; ++c)
+            sweep_chain(T, R, C, A, c, nsteps, ws.data(), (int*)(ws.data() + 3 * C.kcap), c == log_chain ? dlog : nullptr);
+#endif
+        if (log_chain >= 0) { sync(); d2h(log_host, dlog, (size_t)nsteps * LOGW); dev_free(dlog); }
+    }
+
+    void measure() {
+#if W2B_DEVICE
+        k_measure<<<grid(), WARPS_PER_CTA * 32>>>(T, R, C, A); ++launches;
+        W2B_CUDA_CHECK(cudaGetLastError());
+#else
+        for (int c = 0; c < C.nchains; ++c) measure_chain(T, R, C, A, c);
+#endif
+    }
+
+    void rebuild(int only_chain = -1) {
+#if W2B_DEVICE
+        size_t sm = smem_bytes();
+        static size_t configured = 0;
+        if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+        k_rebuild<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, wdoubles, only_chain); ++launches;
+        W2B_CUDA_CHECK(cudaGetLastError());
+#else
+        std::vector<double> ws(wdoubles + 8);
+        for (int c = 0; c < C.nchains; ++c) if (only_chain < 0 || c == only_chain) rebuild_chain(T, R, C, c, ws.data(), (int*)(ws.data() + 3 * C.kcap));
+#endif
+    }
+
+    // ------------------------------------------------------------ host access to chain state
+    void get_header(int chain, std::vector<int>& ih, std::vector<double>& dh) {
+        ih.resize(IH_STRIDE); dh.resize(DH_STRIDE);
+        sync();
+        d2h(ih.data(), C.ih + (size_t)chain * IH_STRIDE, IH_STRIDE);
+        d2h(dh.data(), C.dh + (size_t)chain * DH_STRIDE, DH_STRIDE);
+    }
+    void get_ops(int chain, std::vector<double>& tau, std::vector<unsigned char>& code, std::vector<short>& sst) {
+        std::vector<int> ih; std::vector<double> dh; get_header(chain, ih, dh);
+        int n = ih[IH_NOPS];
+        tau.resize(n); code.resize(n); sst.resize(n);
+        d2h(tau.data(), C.op_tau + (size_t)chain * C.ops_cap, n);
+        d2h(code.data(), C.op_code + (size_t)chain * C.ops_cap, n);
+        d2h(sst.data(), C.op_sst + (size_t)chain * C.ops_cap, n);
+    }
+    void get_minv(int chain, int f, std::vector<double>& out, int& k) {
+        std::vector<int> ih; std::vector<double> dh; get_header(chain, ih, dh);
+        k = ih[IH_KF + f];
+        std::vector<double> buf((size_t)C.kcap * C.ld);
+        d2h(buf.data(), C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld), buf.size());
+        out.assign((size_t)k * k, 0.0);                // column-major (creator, annihilator) like the reference
+        for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) out[i + (size_t)j * k] = buf[(size_t)i * C.ld + j];
+    }
+    void set_ops(int chain, int n, const double* tau, const unsigned char* code, int outer_sst) {
+        if (n > C.ops_cap) throw std::runtime_error("configuration exceeds operator capacity");
+        sync();
+        std::vector<int> ih(IH_STRIDE);
+        d2h(ih.data(), C.ih + (size_t)chain * IH_STRIDE, IH_STRIDE);
+        ih[IH_NOPS] = n; ih[IH_OUTER] = outer_sst; ih[IH_ERR] = 0;
+        h2d(C.ih + (size_t)chain * IH_STRIDE, ih.data(), IH_STRIDE);
+        h2d(C.op_tau + (size_t)chain * C.ops_cap, tau, n);
+        h2d(C.op_code + (size_t)chain * C.ops_cap, code, n);
+        rebuild(chain);
+    }
+    void get_counters(std::vector<unsigned long long>& out) {   // summed over chains
+        sync();
+        std::vector<unsigned long long> all((size_t)C.nchains * C_NCNT);
+        d2h(all.data(), C.counters, all.size());
+        out.assign(C_NCNT, 0ull);
+        for (int c = 0; c < C.nchains; ++c) for (int i = 0; i < C_NCNT; ++i) out[i] += all[(size_t)c * C_NCNT + i];
+    }
+    int error_flags(int* max_k = nullptr, int* max_ops = nullptr) {
+        sync();
+        std::vector<int> ih((size_t)C.nchains * IH_STRIDE);
+        d2h(ih.data(), C.ih, ih.size());
+        int e = 0, mk = 0, mo = 0;
+        for (int c = 0; c < C.nchains; ++c) {
+            e |= ih[(size_t)c * IH_STRIDE + IH_ERR];
+            mo = std::max(mo, ih[(size_t)c * IH_STRIDE + IH_NOPS]);
+            for (int f = 0; f < T.nf; ++f) mk = std::max(mk, ih[(size_t)c * IH_STRIDE + IH_KF + f]);
+        }
+        if (max_k) *max_k = mk;
+        if (max_ops) *max_ops = mo;
+        return e;
+    }
+    void download_accum(std::vector<double>& out, std::vector<unsigned long long>& accpair) {
+        sync();
+        out.resize((size_t)R.nbins * accum_doubles);
+        d2h(out.data(), A.base, out.size());
+        accpair.resize((size_t)T.nf * R.ntau);
+        d2h(accpair.data(), A.accpair, accpair.size());
+    }
+};
+
+}  // namespace w2b

@@ -1,0 +1,994 @@
+// CT-HYB chain engine: one warp advances one Markov chain.
+//
+// This file holds the per-chain logic of the hot path; it is compiled
+//  * by nvcc for sm_100a (32 lanes per chain, kernels in engine.cu), and
+//  * by g++ with W2B_HOST_EMU (1 lane) into a test-only library for CPU logic tests.
+//
+// Reference semantics restated here (files under /root/reference/src/ctqmc_fortran):
+//   scheduler + window shift        CTQMC.F90:8213-8258, 8428-8533 ; Trace.F90:1608-1751
+//   StepAdd / StepRem               CTQMC.F90:3353-3612, 3892-4150
+//   pair_OperAdd / process_OperAdd  Trace.F90:3657-3698, 4275-4462   (FPos = rank among same flavour & type)
+//   gen_OperRemove / NPairs         Trace.F90:4851-4950, 1770-1935
+//   check_sst_sequence              Trace.F90:1243-1302
+//   get_LogDetRatPairAdd/Rem        Trace.F90:2775-2832, 2937-2963 ; MatrixUpdate.F90:392-482
+//   get_Trace_EB (scalar blocks)    Trace.F90:5556-5727
+//   get_Sign                        Trace.F90:3479-3618
+//   StepGlob / StepShiftTau         CTQMC.F90:4433-4835 ; Trace.F90:1103-1433, 2126-2188, 2279-2457
+//   measurements                    CTQMC.F90:2252-2440, 3088-3151, 3264-3350
+//
+// B200-first representation (NOT the reference's linked lists / per-move heap churn):
+//   * operators: one time-sorted packed array per chain (tau f64, code u8 = flavour*2+type, sst i16 = superstate
+//     after the operator); FPos, NPairs, window membership are index arithmetic / lane-parallel counts;
+//   * inverse hybridisation matrices M_f: chain-major, row-major [creator][annihilator] with leading dimension ld,
+//     updated out-of-place into one spare buffer per chain (rank-1 insert / remove with the row/column shift fused
+//     into the same pass), reduced with warp shuffles;
+//   * local trace for 1x1 blocks: the ratio is evaluated only over the changed sub-string (exact, not cached);
+//   * counter-based RNG (Philox4x32-10) consumed in the reference's draw order.
+#pragma once
+#include "warp.hpp"
+
+namespace w2b {
+
+constexpr int LOGW = 20;      // doubles per replay-log record (same layout as oracle/chain.cpp)
+constexpr int NF_MAX = 14;
+enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_NCNT };
+enum { IH_NOPS = 0, IH_OUTER, IH_WPOS, IH_NPAIRS, IH_PERM, IH_PALT, IH_ERR, IH_PAD, IH_KF = 8, IH_MSLOT = IH_KF + NF_MAX, IH_STRIDE = IH_MSLOT + NF_MAX + 2 };
+enum { DH_DETLOG = 0, DH_DETSIGN, DH_TRLOG, DH_TRSIGN, DH_CFGSIGN, DH_STRIDE = 8 };
+enum { ERR_CAPACITY = 1, ERR_DETRAT_SMALL = 2, ERR_PAIR_LOGIC = 4, ERR_GLOBAL_QN = 8, ERR_SINGULAR = 16 };
+
+// static tables (device pointers), identical for all chains
+struct Tables {
+    int nb, nf, nsst, nops, dmax, nftau, nstates;
+    double beta, egs;
+    const short* connect;        // [nsst*nops]
+    const double* e0;            // [nsst] lowest eigenvalue of each block
+    const double* elem;          // [nsst*nops] operator element for 1x1 blocks (0 where not connected)
+    const double* ftau;          // [nf][nftau] diagonal hybridisation, flavour f = 2*band+spin
+    const int* first_state;      // [nsst]
+    const int* state2sst;        // [nstates]
+    const int* dim;              // [nsst]
+    const int* offset;           // [nsst]
+    const double* empty_w;       // [nsst] normalised empty-trace weights (init_Trace / StepChangeOuter)
+    const double* empty_log;     // [nsst] log of the empty trace of each outer superstate
+    const long long* op_off;     // matrix path
+    const double* opdata;
+    const double* evals;
+};
+
+struct Run {
+    double taudiff_max, pglob, pshift, p4op, pouter;
+    int num_windows, nslide, ntau, nlegmax, maxhisto, has_szt, nbins, meas_dm;
+    unsigned seed, chain_base;
+};
+
+struct Chains {
+    int nchains, ops_cap, kcap, ld;
+    double* op_tau; unsigned char* op_code; short* op_sst;
+    double* tau_c; double* tau_a;
+    double* M;
+    int* ih; double* dh;
+    unsigned long long* rng_ctr; unsigned long long* counters;
+    double* sc_tau; unsigned char* sc_code; short* sc_sst;     // per-chain scratch (global / tau-shift moves)
+    double* sc_tc; double* sc_ta;                              // [chain][nf][kcap]
+};
+
+// accumulators (device), one slab per bin; offsets in doubles
+struct Accum {
+    double* base; long long stride;
+    int o_gtau, o_gleg, o_histo, o_dens, o_outer, o_signsst, o_contribsst, o_outerst, o_signst, o_contribst, o_sign, o_cnt;
+    unsigned long long* accpair;     // [nf][ntau]
+    int ndens;
+};
+
+struct Ctx {
+    double* tau; unsigned char* code; short* sst; double* tc; double* ta; double* Mbase; int* ih; double* dh;
+    unsigned long long* cnt;
+    double* sc_tau; unsigned char* sc_code; short* sc_sst; double* sc_tc; double* sc_ta;
+    double* wQ; double* wR; double* wV; int* wI;
+    int n, outer, wpos, npairs, perm, palt, err;
+    double det_log, det_sign, tr_log, tr_sign, cfgsign, wmin, wmax;
+    Philox rng;
+    int lane;
+    double* log;           // replay record for the current step (or nullptr)
+};
+
+W2B_HD double sgn1(double x) { return (x < 0.0 || (x == 0.0 && 1.0 / x < 0.0)) ? -1.0 : 1.0; }
+W2B_HD int conn(const Tables& T, int sst, int opc) { return (int)ldg(&T.connect[sst * T.nops + opc]); }
+
+// get_HybrF Trace.F90:1014-1033
+W2B_HD double hybrF(const Tables& T, double tau, int f) {
+    double sig = 1.0;
+    if (tau < 0.0) { tau += T.beta; sig = -1.0; }
+    double n = tau / T.beta * (double)(T.nftau - 1);
+    int i = (int)n;
+    const double* p = T.ftau + (size_t)f * T.nftau + i;
+    double a = ldg(p), b = ldg(p + 1);
+    return sig * (a + (n - (double)i) * (b - a));
+}
+
+W2B_HD void set_window_edges(const Tables& T, const Run& R, Ctx& x) {   // set_window Trace.F90:1697-1699
+    if (R.num_windows > 1) {
+        x.wmin = ((double)x.wpos / (double)(R.num_windows + 1)) * T.beta;
+        x.wmax = ((double)(x.wpos + 2) / (double)(R.num_windows + 1)) * T.beta;
+    } else { x.wmin = 0.0; x.wmax = T.beta; }
+}
+
+W2B_HD double* Mbuf(const Chains& C, Ctx& x, int f) { return x.Mbase + (size_t)x.ih[IH_MSLOT + f] * ((size_t)C.kcap * C.ld); }
+
+// number of sorted entries < t ; eq is set when an entry equals t
+W2B_HD int count_lt(const double* a, int n, double t, bool& eq) {
+    int c = 0; bool e = false;
+    for (int i = lane_id(); i < n; i += W2B_WARP) { double v = a[i]; c += (v < t); e |= (v == t); }
+    eq = wany(e);
+    return wsum(c);
+}
+W2B_HD int count_lt(const double* a, int n, double t) { bool e; return count_lt(a, n, t, e); }
+W2B_HD int count_le(const double* a, int n, double t) {
+    int c = 0;
+    for (int i = lane_id(); i < n; i += W2B_WARP) c += (a[i] <= t);
+    return wsum(c);
+}
+
+// array shifts by whole-warp chunks (read chunk, sync, write)
+template <class T_> W2B_HD void shift_up(T_* a, int from, int n, int by) {       // [from,n) -> [from+by, n+by)
+    for (int top = n; top > from; top -= W2B_WARP) {
+        int idx = top - 1 - lane_id();
+        T_ v = T_(); bool act = idx >= from;
+        if (act) v = a[idx];
+        wsync();
+        if (act) a[idx + by] = v;
+        wsync();
+    }
+}
+template <class T_> W2B_HD void shift_down(T_* a, int from, int n, int by) {     // [from+by, n) -> [from, n-by)
+    for (int base = from; base < n - by; base += W2B_WARP) {
+        int idx = base + lane_id();
+        T_ v = T_(); bool act = idx < n - by;
+        if (act) v = a[idx + by];
+        wsync();
+        if (act) a[idx] = v;
+        wsync();
+    }
+}
+
+// Serial superstate walk over `m` existing operators starting at list index i0 (codes from `code`), starting from
+// superstate `cur`; stores the superstate after each operator into out[i0out + j].  Returns the final superstate
+// (-1 if annihilated on the way).
+W2B_HD int walk_store(const Tables& T, const unsigned char* code, int i0, int m, int cur, short* out, int i0out) {
+    for (int base = 0; base < m; base += W2B_WARP) {
+        int j = base + lane_id(); bool act = j < m;
+        int cj = act ? (int)code[i0 + j] : 0;
+        int cnt = m - base < W2B_WARP ? m - base : W2B_WARP;
+        int mine = -1;
+        for (int q = 0; q < cnt; ++q) {
+            int cq = wbcast(cj, q);
+            cur = cur >= 0 ? conn(T, cur, cq) : -1;
+            if (lane_id() == q) mine = cur;
+        }
+        if (act) out[i0out + j] = (short)mine;
+    }
+    wsync();
+    return cur;
+}
+
+// Re-evaluate `m` existing operators [i0, i0+m) from new superstate `cur` while the old superstates are read from
+// x.sst; accumulates the change of the scalar local trace (Trace.F90:5595-5642 restricted to the changed sub-string).
+// On entry: old_before = old superstate before operator i0, tl = time of the left end of the first interval.
+// On exit:  cur / old_after = new / old superstate after the last walked operator, tl = its time (unchanged if m == 0),
+//           nother = number of walked operators whose flavour differs from f.
+W2B_HD void walk_delta(const Tables& T, const Ctx& x, int i0, int m, int f, int& cur, int& old_after, double& tl,
+                       double& dlog, double& dsign, int& nother) {
+    double acc = 0.0; int neg = 0, oth = 0;
+    int old_before0 = old_after; double tl0 = tl;
+    for (int base = 0; base < m; base += W2B_WARP) {
+        int j = base + lane_id(); bool act = j < m;
+        int cj = act ? (int)x.code[i0 + j] : 0;
+        int cnt = m - base < W2B_WARP ? m - base : W2B_WARP;
+        int nb4 = -1;
+        for (int q = 0; q < cnt; ++q) {
+            int cq = wbcast(cj, q);
+            if (lane_id() == q) nb4 = cur;
+            cur = cur >= 0 ? conn(T, cur, cq) : -1;
+        }
+        if (act && nb4 >= 0) {
+            double tj = x.tau[i0 + j];
+            int ob = (j == 0) ? old_before0 : (int)x.sst[i0 + j - 1];
+            double tp = (j == 0) ? tl0 : x.tau[i0 + j - 1];
+            acc += -(ldg(&T.e0[nb4]) - ldg(&T.e0[ob])) * (tj - tp);
+            double en = ldg(&T.elem[nb4 * T.nops + cj]), eo = ldg(&T.elem[ob * T.nops + cj]);
+            if (en != 0.0) { acc += log(fabs(en)) - log(fabs(eo)); neg += (en < 0.0) != (eo < 0.0); }
+            oth += ((cj >> 1) != f);
+        }
+    }
+    if (m > 0) { old_after = (int)x.sst[i0 + m - 1]; tl = x.tau[i0 + m - 1]; }
+    dlog += wsum(acc);
+    if (wsum(neg) & 1) dsign = -dsign;
+    nother = wsum(oth);
+}
+
+// pairs (Trace.F90:1794-1814): earlier >= wmin, later <= wmax, !(later > earlier + taudiff_max)
+W2B_HD bool pairable(const Run& R, const Ctx& x, double a, double b) {
+    double e = a < b ? a : b, l = a < b ? b : a;
+    return e >= x.wmin && l <= x.wmax && !(l > e + R.taudiff_max);
+}
+W2B_HD int pairs_with(const Run& R, const Ctx& x, const double* opp, int k, double t) {
+    int c = 0;
+    for (int i = lane_id(); i < k; i += W2B_WARP) c += pairable(R, x, opp[i], t);
+    return wsum(c);
+}
+W2B_HD int count_pairs_full(const Tables& T, const Run& R, const Chains& C, const Ctx& x) {
+    int c = 0;
+    for (int f = 0; f < T.nf; ++f) {
+        int k = x.ih[IH_KF + f];
+        const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+        for (int i = lane_id(); i < k; i += W2B_WARP) {
+            double t = tc[i];
+            if (t < x.wmin || t > x.wmax) continue;
+            for (int a = 0; a < k; ++a) c += pairable(R, x, ta[a], t);
+        }
+    }
+    return wsum(c);
+}
+
+// number of creators sitting at an even position of the flavour's time-ordered list (get_permaltca, Trace.F90:3554-3588)
+W2B_HD int palt_flavour(const Chains& C, const Ctx& x, int f) {
+    int k = x.ih[IH_KF + f];
+    const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+    int c = 0;
+    for (int i = lane_id(); i < k; i += W2B_WARP) {
+        double t = tc[i]; int pos = i;
+        for (int a = 0; a < k; ++a) pos += (ta[a] < t);
+        c += ((pos & 1) == 0);
+    }
+    return wsum(c) & 1;
+}
+// inversion parity of the flavour sequence in time order (== get_BlockSign, Trace.F90:3594-3618)
+W2B_HD int perm_full(const unsigned char* code, int n) {
+    int c = 0;
+    for (int i = lane_id(); i < n; i += W2B_WARP) {
+        int fi = code[i] >> 1;
+        for (int j = i + 1; j < n; ++j) c += ((code[j] >> 1) < fi);
+    }
+    return wsum(c) & 1;
+}
+W2B_HD void update_cfgsign(const Tables& T, Ctx& x) {
+    int pal = 0;
+    for (int f = 0; f < T.nf; ++f) pal ^= (x.palt >> f) & 1;
+    if ((x.n / 2) & 1) pal ^= 1;
+    double s = x.tr_sign * x.det_sign * ((x.perm & 1) ? -1.0 : 1.0) * (pal ? -1.0 : 1.0);
+    x.cfgsign = -s;                                         // CTQMC.F90:3574
+}
+
+// ------------------------------------------------------------------ determinant ratio + rank-1 updates
+// S - R^T M Q (MatrixUpdate.F90:392-407); leaves Q, R, V = R^T M in the warp scratch for the update
+W2B_HDN double det_ratio_add(const Tables& T, const Chains& C, Ctx& x, int f, double tau_c, double tau_a) {
+    int k = x.ih[IH_KF + f];
+    const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+    for (int j = x.lane; j < k; j += W2B_WARP) {
+        x.wQ[j] = hybrF(T, ta[j] - tau_c, f);              // Q_j = F(tau_a_j - tau_c,new)
+        x.wR[j] = hybrF(T, tau_a - tc[j], f);              // R_i = F(tau_a,new - tau_c_i)
+    }
+    wsync();
+    const double* M = Mbuf(C, x, f);
+    const int ld = C.ld;
+    double part = 0.0;
+    for (int j = x.lane; j < k; j += W2B_WARP) {
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        int i = 0;
+        for (; i + 3 < k; i += 4) {
+            a0 += x.wR[i] * M[(size_t)i * ld + j];
+            a1 += x.wR[i + 1] * M[(size_t)(i + 1) * ld + j];
+            a2 += x.wR[i + 2] * M[(size_t)(i + 2) * ld + j];
+            a3 += x.wR[i + 3] * M[(size_t)(i + 3) * ld + j];
+        }
+        for (; i < k; ++i) a0 += x.wR[i] * M[(size_t)i * ld + j];
+        double v = (a0 + a1) + (a2 + a3);
+        x.wV[j] = v;
+        part += v * x.wQ[j];
+    }
+    double S = hybrF(T, tau_a - tau_c, f) - wsum(part);
+    wsync();
+    return S;
+}
+
+// get_MatAdd MatrixUpdate.F90:410-442, fused with the row/column shift, written into the spare buffer
+W2B_HDN void mat_add(const Chains& C, Ctx& x, int f, int nf, int p1, int p2, double S) {
+    int k = x.ih[IH_KF + f];
+    const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, nf);
+    const int ld = C.ld; const double inv = 1.0 / S;
+    for (int in = 0; in <= k; ++in) {
+        if (in == p1) {
+            for (int jn = x.lane; jn <= k; jn += W2B_WARP)
+                dst[(size_t)in * ld + jn] = (jn == p2) ? inv : -x.wV[jn - (jn > p2)] * inv;
+        } else {
+            int i = in - (in > p1);
+            double part = 0.0;
+            for (int j = x.lane; j < k; j += W2B_WARP) part += src[(size_t)i * ld + j] * x.wQ[j];
+            double u = wsum(part);
+            for (int jn = x.lane; jn <= k; jn += W2B_WARP) {
+                if (jn == p2) dst[(size_t)in * ld + jn] = -u * inv;
+                else { int j = jn - (jn > p2); dst[(size_t)in * ld + jn] = src[(size_t)i * ld + j] + u * x.wV[j] * inv; }
+            }
+        }
+    }
+    wsync();
+    if (x.lane == 0) { int t = x.ih[IH_MSLOT + f]; x.ih[IH_MSLOT + f] = x.ih[IH_MSLOT + nf]; x.ih[IH_MSLOT + nf] = t; x.ih[IH_KF + f] = k + 1; }
+    wsync();
+}
+
+// get_MatRem MatrixUpdate.F90:455-482
+W2B_HDN void mat_rem(const Chains& C, Ctx& x, int f, int nf, int p1, int p2) {
+    int k = x.ih[IH_KF + f];
+    const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, nf);
+    const int ld = C.ld;
+    for (int j = x.lane; j < k; j += W2B_WARP) { x.wV[j] = src[(size_t)p1 * ld + j]; x.wQ[j] = src[(size_t)j * ld + p2]; }
+    wsync();
+    const double ipiv = 1.0 / src[(size_t)p1 * ld + p2];
+    for (int i = 0; i < k - 1; ++i) {
+        int io = i + (i >= p1);
+        double c = x.wQ[io];
+        for (int j = x.lane; j < k - 1; j += W2B_WARP) {
+            int jo = j + (j >= p2);
+            dst[(size_t)i * ld + j] = src[(size_t)io * ld + jo] - c * x.wV[jo] * ipiv;
+        }
+    }
+    wsync();
+    if (x.lane == 0) { int t = x.ih[IH_MSLOT + f]; x.ih[IH_MSLOT + f] = x.ih[IH_MSLOT + nf]; x.ih[IH_MSLOT + nf] = t; x.ih[IH_KF + f] = k - 1; }
+    wsync();
+}
+
+// ------------------------------------------------------------------ logging helpers
+W2B_HD void log_begin(Ctx& x, int type) {
+    if (x.log && x.lane == 0) { for (int i = 0; i < LOGW; ++i) x.log[i] = 0.0; x.log[0] = type; x.log[4] = -1; }
+}
+W2B_HD void log_set(Ctx& x, int i, double v) { if (x.log && x.lane == 0) x.log[i] = v; }
+W2B_HD void log_end(Ctx& x, int status) {
+    if (x.log && x.lane == 0) { x.log[1] = status; x.log[12] = x.n; x.log[13] = x.outer; x.log[15] = x.cfgsign; }
+}
+W2B_HD void bump(Ctx& x, int c) { if (x.lane == 0) x.cnt[c] += 1ull; }
+
+// ------------------------------------------------------------------ StepAdd (CTQMC.F90:3353-3612, change_outer = false)
+W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x) {
+    log_begin(x, 1);
+    bump(x, C_TRYADD);
+    const double W = x.wmax - x.wmin;
+    const double tau_a = x.wmin + W * x.rng.next();                    // pair_OperAdd Trace.F90:3672-3695
+    const int b = x.rng.randint(1, T.nb) - 1;
+    const int s = x.rng.randint(1, 2) - 1;
+    const double tmin = fmax(tau_a - R.taudiff_max, x.wmin);
+    const double w2 = fmin(tau_a + R.taudiff_max, x.wmax) - tmin;
+    const double tau_c = tmin + w2 * x.rng.next();
+    const double taudiff_factor = W * w2;
+    const int f = b * 2 + s;
+    const bool a_first = tau_a < tau_c;
+    const double t1 = a_first ? tau_a : tau_c, t2 = a_first ? tau_c : tau_a;
+    const int code1 = f * 2 + (a_first ? 1 : 0), code2 = f * 2 + (a_first ? 0 : 1);
+    log_set(x, 4, f); log_set(x, 2, t1); log_set(x, 3, t2);
+    bool eq1, eq2;
+    const int i1 = count_lt(x.tau, x.n, t1, eq1), i2 = count_lt(x.tau, x.n, t2, eq2);
+    if (eq1 || eq2 || tau_a == tau_c) { bump(x, C_QNADD); log_end(x, 2); return; }     // process_OperAdd: equal times
+    const int k = x.ih[IH_KF + f];
+    const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+    const int p1 = count_lt(tc, k, tau_c), p2 = count_lt(ta, k, tau_a);              // FPos-1 (creator row, annihilator column)
+    log_set(x, 5, p1 + 1); log_set(x, 6, p2 + 1);
+    // quantum-number check of the changed sub-string + scalar trace ratio
+    const int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
+    double dlog = 0.0, dsign = 1.0;
+    int cur = conn(T, begin_sst, code1), old_after = begin_sst, nother = 0;
+    double tl = t1;
+    if (cur >= 0) {
+        double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog += log(fabs(e)); if (e < 0) dsign = -dsign;
+        walk_delta(T, x, i1, i2 - i1, f, cur, old_after, tl, dlog, dsign, nother);
+    }
+    int new_end = -1;
+    if (cur >= 0) {
+        dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
+        double e = ldg(&T.elem[cur * T.nops + code2]);
+        new_end = conn(T, cur, code2);
+        if (new_end >= 0) { dlog += log(fabs(e)); if (e < 0) dsign = -dsign; }
+    }
+    if (new_end < 0 || new_end != old_after) { bump(x, C_QNADD); log_end(x, 2); return; }
+    // determinant ratio
+    const double S = det_ratio_add(T, C, x, f, tau_c, tau_a);
+    const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
+    const double dr_log = log(fabs(S)), dr_sign = sgn1(S) * sig;
+    const double rand = x.rng.next();
+    // NPairs after insertion (CTQMC.F90:3510-3515)
+    if (x.npairs < 0) x.npairs = count_pairs_full(T, R, C, x);
+    const int np_new = x.npairs + pairs_with(R, x, ta, k, tau_c) + pairs_with(R, x, tc, k, tau_a) + (pairable(R, x, tau_a, tau_c) ? 1 : 0);
+    const double prob = fabs(taudiff_factor * (double)(2 * T.nb) / (double)np_new * exp(dlog + dr_log));
+    log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, dlog); log_set(x, 10, dsign); log_set(x, 11, prob);
+    log_set(x, 14, np_new); log_set(x, 17, rand);
+    if (!(rand < prob)) { log_end(x, 0); return; }
+    if (k + 1 > C.kcap || x.n + 2 > C.ops_cap) { x.err |= ERR_CAPACITY; log_end(x, 0); return; }
+    // ---- accept
+    mat_add(C, x, f, T.nf, p1, p2, S);
+    shift_up(x.tc + (size_t)f * C.kcap, p1, k, 1); shift_up(x.ta + (size_t)f * C.kcap, p2, k, 1);
+    if (x.lane == 0) { x.tc[(size_t)f * C.kcap + p1] = tau_c; x.ta[(size_t)f * C.kcap + p2] = tau_a; }
+    shift_up(x.tau, i2, x.n, 2); shift_up(x.code, i2, x.n, 2); shift_up(x.sst, i2, x.n, 2);
+    shift_up(x.tau, i1, i2, 1); shift_up(x.code, i1, i2, 1); shift_up(x.sst, i1, i2, 1);
+    if (x.lane == 0) { x.tau[i1] = t1; x.code[i1] = (unsigned char)code1; x.tau[i2 + 1] = t2; x.code[i2 + 1] = (unsigned char)code2; }
+    wsync();
+    x.n += 2;
+    walk_store(T, x.code, i1, i2 - i1 + 2, begin_sst, x.sst, i1);
+    x.det_log += dr_log; x.det_sign *= dr_sign; x.tr_log += dlog; x.tr_sign *= dsign;
+    x.perm ^= (nother & 1);
+    x.palt = (x.palt & ~(1 << f)) | (palt_flavour(C, x, f) << f);
+    x.npairs = np_new;
+    update_cfgsign(T, x);
+    bump(x, C_ACCADD);
+    if (x.lane == 0) {
+        int bin = (int)floor((t2 - t1) / T.beta * (double)R.ntau) + 1; if (bin > R.ntau) bin = R.ntau;
+        atomic_add(&A.accpair[(size_t)f * R.ntau + bin - 1], 1ull);
+    }
+    log_end(x, 1);
+}
+
+// ------------------------------------------------------------------ StepRem (CTQMC.F90:3892-4150, change_outer = false)
+W2B_HDN void step_rem(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x) {
+    log_begin(x, 2);
+    bump(x, C_TRYREM);
+    if (x.npairs < 0) x.npairs = count_pairs_full(T, R, C, x);        // gen_OperRemove Trace.F90:4868-4877
+    log_set(x, 14, x.npairs);
+    if (x.npairs <= 0) { bump(x, C_QNREM); log_end(x, 2); return; }
+    const int r = x.rng.randint(1, x.npairs);
+    const int ia = count_lt(x.tau, x.n, x.wmin), ib = count_le(x.tau, x.n, x.wmax);
+    // enumerate (El, mEl) in the reference's order: El over in-window operators in time order, mEl over later
+    // same-flavour operators of opposite type with tau <= wmax and tau <= tau_El + taudiff_max
+    int i1 = -1, f = 0, type1 = 0, midx = 0; double t1 = 0.0;
+    int cum = 0;
+    for (int base = ia; base < ib; base += W2B_WARP) {
+        int i = base + x.lane; bool act = i < ib;
+        int c = 0, lb = 0, fi = 0, ty = 0; double ti = 0.0;
+        if (act) {
+            int cd = x.code[i]; fi = cd >> 1; ty = cd & 1; ti = x.tau[i];
+            int k = x.ih[IH_KF + fi];
+            const double* opp = (ty == 0 ? x.ta : x.tc) + (size_t)fi * C.kcap;
+            for (int a = 0; a < k; ++a) {
+                double v = opp[a];
+                if (v <= ti) ++lb;
+                else if (v <= x.wmax && !(v > ti + R.taudiff_max)) ++c;
+                else break;
+            }
+        }
+        int incl = wscan_incl(c);
+        int total = wbcast(incl, W2B_WARP - 1);
+        if (cum + total >= r) {
+            unsigned hit = wballot(act && (cum + incl >= r));
+            int src = 0;
+#if W2B_DEVICE
+            src = __ffs(hit) - 1;
+#endif
+            int rr = r - (cum + incl - c);
+            i1 = base + src; f = wbcast(fi, src); type1 = wbcast(ty, src); t1 = wbcast(ti, src); midx = wbcast(lb + rr - 1, src);
+            break;
+        }
+        cum += total;
+    }
+    if (i1 < 0) { x.err |= ERR_PAIR_LOGIC; log_end(x, 2); return; }
+    const int k = x.ih[IH_KF + f];
+    const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+    const double t2 = (type1 == 0 ? ta : tc)[midx];
+    const int pE = count_lt(type1 == 0 ? tc : ta, k, t1);
+    const int p1 = type1 == 0 ? pE : midx, p2 = type1 == 0 ? midx : pE;
+    const double tau_an = type1 == 1 ? t1 : t2;
+    const int i2 = count_lt(x.tau, x.n, t2);
+    log_set(x, 2, t1); log_set(x, 3, t2); log_set(x, 4, f); log_set(x, 5, p1 + 1); log_set(x, 6, p2 + 1);
+    const double factor = (double)x.npairs / ((x.wmax - x.wmin) * (fmin(tau_an + R.taudiff_max, x.wmax) - fmax(tau_an - R.taudiff_max, x.wmin)));
+    // quantum numbers + scalar trace ratio of the configuration without the pair
+    const int code1 = f * 2 + type1, code2 = f * 2 + (1 - type1);
+    const int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
+    double dlog = 0.0, dsign = 1.0;
+    { double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog -= log(fabs(e)); if (e < 0) dsign = -dsign; }
+    int cur = begin_sst, old_after = (int)x.sst[i1], nother = 0;
+    double tl = t1;
+    walk_delta(T, x, i1 + 1, i2 - i1 - 1, f, cur, old_after, tl, dlog, dsign, nother);
+    const int end_sst = (int)x.sst[i2];
+    if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return; }
+    dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
+    { double e = ldg(&T.elem[old_after * T.nops + code2]); dlog -= log(fabs(e)); if (e < 0) dsign = -dsign; }
+    // determinant ratio = M(p1,p2)  (MatrixUpdate.F90:445-452)
+    const double S = Mbuf(C, x, f)[(size_t)p1 * C.ld + p2];
+    const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
+    const double dr_log = log(fabs(S)), dr_sign = sgn1(S) * sig;
+    const double prob = fabs(factor / (double)(2 * T.nb) * exp(dlog + dr_log));
+    const double rand = x.rng.next();
+    log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, dlog); log_set(x, 10, dsign); log_set(x, 11, prob); log_set(x, 17, rand);
+    if (!(rand < prob)) { log_end(x, 0); return; }
+    if (fabs(S) < 1e-12) x.err |= ERR_DETRAT_SMALL;                    // CTQMC.F90:4062 `stop`
+    // ---- accept
+    const int np_new = x.npairs - (pairs_with(R, x, type1 == 0 ? ta : tc, k, t1) + pairs_with(R, x, type1 == 0 ? tc : ta, k, t2) - (pairable(R, x, t1, t2) ? 1 : 0));
+    mat_rem(C, x, f, T.nf, p1, p2);
+    shift_down(x.tc + (size_t)f * C.kcap, p1, k, 1); shift_down(x.ta + (size_t)f * C.kcap, p2, k, 1);
+    shift_down(x.tau, i1, i2, 1); shift_down(x.code, i1, i2, 1); shift_down(x.sst, i1, i2, 1);
+    shift_down(x.tau, i2 - 1, x.n, 2); shift_down(x.code, i2 - 1, x.n, 2); shift_down(x.sst, i2 - 1, x.n, 2);
+    x.n -= 2;
+    walk_store(T, x.code, i1, i2 - i1 - 1, begin_sst, x.sst, i1);
+    x.det_log += dr_log; x.det_sign *= dr_sign; x.tr_log += dlog; x.tr_sign *= dsign;
+    x.perm ^= (nother & 1);
+    x.palt = (x.palt & ~(1 << f)) | (palt_flavour(C, x, f) << f);
+    x.npairs = np_new;
+    update_cfgsign(T, x);
+    bump(x, C_ACCREM);
+    if (x.lane == 0) {
+        int bin = (int)floor((t2 - t1) / T.beta * (double)R.ntau) + 1; if (bin > R.ntau) bin = R.ntau;
+        atomic_add(&A.accpair[(size_t)f * R.ntau + bin - 1], 1ull);
+    }
+    log_end(x, 1);
+}
+
+// ------------------------------------------------------------------ full (global) evaluations
+// scalar local trace of a whole configuration given codes/taus/ssts (get_Trace_EB_onlyscalars Trace.F90:5556-5727)
+W2B_HD void trace_full_scalar(const Tables& T, const double* tau, const unsigned char* code, const short* sst, int n, int outer,
+                              double& lg, double& sg) {
+    double acc = 0.0; int neg = 0;
+    for (int i = lane_id(); i < n; i += W2B_WARP) {
+        int before = i == 0 ? outer : (int)sst[i - 1];
+        double tp = i == 0 ? 0.0 : tau[i - 1];
+        acc += -(ldg(&T.e0[before]) - T.egs) * (tau[i] - tp);
+        double e = ldg(&T.elem[before * T.nops + code[i]]);
+        acc += log(fabs(e)); neg += (e < 0.0);
+    }
+    double tlast = n > 0 ? tau[n - 1] : 0.0;
+    lg = wsum(acc) - (ldg(&T.e0[outer]) - T.egs) * (T.beta - tlast);
+    sg = (wsum(neg) & 1) ? -1.0 : 1.0;
+}
+
+// In-place Gauss-Jordan inversion with partial pivoting of the k x k row-major matrix a (leading dimension ld);
+// returns log|det| and sign through the references; singular -> sign 0.  Uses wI[0..k) as pivot bookkeeping.
+// (stands in for DGETRF/DGETRI of get_MatLogDetFull, MatrixUpdate.F90:41-99)
+W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, bool want_inverse, double& lg, double& sg) {
+    lg = 0.0; sg = 1.0;
+    const int lane = lane_id();
+    for (int c = 0; c < k; ++c) {
+        // pivot search in column c among rows that have not been used as pivot rows (rows >= c after swapping)
+        double best = 0.0; int bi = c;
+        for (int r = c + lane; r < k; r += W2B_WARP) { double v = fabs(a[(size_t)r * ld + c]); if (v > best) { best = v; bi = r; } }
+        double bv; int p = wargmax_abs(best, bi, bv);
+        if (!(bv > 0.0)) { sg = 0.0; lg = -1.7976931348623157e308; return; }
+        if (lane == 0) wI[c] = p;
+        if (p != c) {
+            for (int j = lane; j < k; j += W2B_WARP) { double t = a[(size_t)c * ld + j]; a[(size_t)c * ld + j] = a[(size_t)p * ld + j]; a[(size_t)p * ld + j] = t; }
+            sg = -sg;
+        }
+        wsync();
+        double piv = a[(size_t)c * ld + c];
+        lg += log(fabs(piv)); if (piv < 0) sg = -sg;
+        double ipiv = 1.0 / piv;
+        wsync();
+        if (want_inverse) {
+            // Gauss-Jordan step: row c scaled, eliminated from every other row; column c becomes the inverse column
+            for (int j = lane; j < k; j += W2B_WARP) a[(size_t)c * ld + j] = (j == c) ? ipiv : a[(size_t)c * ld + j] * ipiv;
+            wsync();
+            for (int r = 0; r < k; ++r) {
+                if (r == c) continue;
+                double fct = a[(size_t)r * ld + c];
+                wsync();
+                for (int j = lane; j < k; j += W2B_WARP)
+                    a[(size_t)r * ld + j] = (j == c) ? -fct * ipiv : a[(size_t)r * ld + j] - fct * a[(size_t)c * ld + j];
+                wsync();
+            }
+        } else {
+            for (int r = c + 1; r < k; ++r) {
+                double fct = a[(size_t)r * ld + c] * ipiv;
+                for (int j = c + 1 + lane; j < k; j += W2B_WARP) a[(size_t)r * ld + j] -= fct * a[(size_t)c * ld + j];
+            }
+            wsync();
+        }
+    }
+    if (want_inverse) {
+        // undo the row swaps as column swaps in reverse order: inv(P A) = inv(A) P^T
+        for (int c = k - 1; c >= 0; --c) {
+            int p = wI[c];
+            if (p != c) for (int r = lane; r < k; r += W2B_WARP) { double t = a[(size_t)r * ld + c]; a[(size_t)r * ld + c] = a[(size_t)r * ld + p]; a[(size_t)r * ld + p] = t; }
+            wsync();
+        }
+    }
+}
+
+// Rebuild every inverse hybridisation matrix from the flavour tau arrays (get_InvFullHybr Trace.F90:2279-2333):
+// Delta(ia, ic) = F(tau_a[ia] - tau_c[ic]) ; M = Delta^{-1} is indexed (creator, annihilator).
+// Builds directly the transposed system so that the in-place inverse lands in M's [creator][annihilator] layout.
+W2B_HDN void rebuild_inverses(const Tables& T, const Chains& C, Ctx& x, const double* tcs, const double* tas, const int* kfs,
+                              bool want_inverse, double& lg, double& sg) {
+    lg = 0.0; sg = 1.0;
+    for (int f = 0; f < T.nf; ++f) {
+        int k = kfs[f];
+        if (k == 0) continue;
+        double* a = Mbuf(C, x, want_inverse ? f : T.nf);
+        const double* tc = tcs + (size_t)f * C.kcap; const double* ta = tas + (size_t)f * C.kcap;
+        // a[ia][ic] = Delta(ia, ic); its inverse inv[ic][ia] is what M stores at [creator ic][annihilator ia]
+        for (int ia = 0; ia < k; ++ia)
+            for (int ic = x.lane; ic < k; ic += W2B_WARP) a[(size_t)ia * C.ld + ic] = hybrF(T, ta[ia] - tc[ic], f);
+        wsync();
+        double l, s;
+        invert_inplace(a, k, C.ld, x.wI, want_inverse, l, s);
+        lg += l; sg *= s;
+    }
+}
+
+// ------------------------------------------------------------------ StepGlob (CTQMC.F90:4433-4554)
+W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
+    log_begin(x, 3);
+    bump(x, C_TRYGLOB);
+    if (x.n == 0) { log_end(x, 2); return; }
+    const int nf = T.nf, nb = T.nb;
+    int* gu = x.wI + C.kcap;               // gu[0] = c<->c^dag flip, gu[1..nf] = target flavour (bit index + 1)
+    const double r = x.rng.next();
+    int type;
+    if (r < 0.3) {                         // gen_SpinFlipUpdate Trace.F90:1150-1166
+        type = 3;
+        if (x.lane == 0) { gu[0] = 0; for (int i = 1; i <= nb; ++i) gu[i] = i + nb; for (int i = nb + 1; i <= nf; ++i) gu[i] = i - nb; }
+    } else if (r < 0.6) {                  // gen_CAFlip 1186-1198
+        type = 4;
+        if (x.lane == 0) { gu[0] = 1; for (int i = 1; i <= nf; ++i) gu[i] = i; }
+    } else {                               // gen_GlobalUpdate_new 1103-1123 (NSymMove = 0)
+        type = 1;
+        if (x.lane == 0) for (int i = 1; i <= nf; ++i) gu[i] = i;
+        wsync();
+        for (int j = 1; j <= nf; ++j) { int i = x.rng.randint(j, nf); if (x.lane == 0) { int t = gu[j]; gu[j] = gu[i]; gu[i] = t; } wsync(); }
+        int flip = x.rng.randint(0, 1);
+        if (x.lane == 0) gu[0] = flip;
+    }
+    wsync();
+    log_set(x, 4, type);
+    const int flip = gu[0];
+    // relabelled operator codes (globalUpdate Trace.F90:2126-2188); flavour f=2b+s <-> gu index b+nb*s+1
+    for (int i = x.lane; i < x.n; i += W2B_WARP) {
+        int cd = x.code[i], f = cd >> 1, ty = cd & 1, b = f >> 1, s = f & 1;
+        int g = gu[b + nb * s + 1] - 1;
+        int f2 = (g % nb) * 2 + g / nb;
+        x.sc_code[i] = (unsigned char)(f2 * 2 + (flip ? 1 - ty : ty));
+    }
+    wsync();
+    double factor = 0.0; int new_outer = x.outer;
+    if (type == 3 && R.has_szt) {          // perform_spinflip_check_qn Trace.F90:1306-1339
+        int st = ldg(&T.first_state[x.outer]);
+        int dn = st & ((1 << nb) - 1), up = (st >> nb) & ((1 << nb) - 1);
+        new_outer = ldg(&T.state2sst[up | (dn << nb)]);
+        int fin = walk_store(T, x.sc_code, 0, x.n, new_outer, x.sc_sst, 0);
+        factor = (fin == new_outer) ? 1.0 : 0.0;
+    } else {                               // perform_global_check_qn Trace.F90:1345-1394
+        int pold = 0, pnew = 0;
+        // each lane walks one candidate outer superstate through the old and the new sequence
+        for (int base = 0; base < T.nsst; base += W2B_WARP) {
+            int k0 = base + x.lane; bool act = k0 < T.nsst;
+            int co = act ? k0 : -1, cn = act ? k0 : -1;
+            for (int i = 0; i < x.n; ++i) {
+                int a = x.code[i], b2 = x.sc_code[i];
+                co = co >= 0 ? conn(T, co, a) : -1;
+                cn = cn >= 0 ? conn(T, cn, b2) : -1;
+            }
+            bool oko = act && co == k0, okn = act && cn == k0;
+            if (act) x.wI[C.kcap + 32 + k0] = okn ? 1 : 0;
+            pold += wsum(oko ? 1 : 0); pnew += wsum(okn ? 1 : 0);
+        }
+        wsync();
+        if (pold <= 0) { x.err |= ERR_GLOBAL_QN; log_end(x, 2); return; }
+        if (pnew > 0) {
+            factor = (double)pnew / (double)pold;
+            int kk = x.rng.randint(1, pnew);
+            for (int i = 0; i < T.nsst; ++i) if (x.wI[C.kcap + 32 + i]) { if (--kk <= 0) { new_outer = i; break; } }
+            walk_store(T, x.sc_code, 0, x.n, new_outer, x.sc_sst, 0);
+        }
+    }
+    if (factor == 0.0) { bump(x, C_QNGLOB); log_end(x, 2); return; }
+    // relabelled flavour tau arrays and orders
+    int* knew = x.wI + C.kcap + 16;
+    for (int f = 0; f < nf; ++f) {
+        int b = f >> 1, s = f & 1, g = gu[b + nb * s + 1] - 1, f2 = (g % nb) * 2 + g / nb;
+        int k = x.ih[IH_KF + f];
+        if (x.lane == 0) knew[f2] = k;
+        const double* oc = x.tc + (size_t)f * C.kcap; const double* oa = x.ta + (size_t)f * C.kcap;
+        double* nc = x.sc_tc + (size_t)f2 * C.kcap; double* na = x.sc_ta + (size_t)f2 * C.kcap;
+        for (int i = x.lane; i < k; i += W2B_WARP) { nc[i] = flip ? oa[i] : oc[i]; na[i] = flip ? oc[i] : oa[i]; }
+    }
+    wsync();
+    // determinant of the new configuration from scratch (spare buffer) and of the stored inverses (get_FullLogDet)
+    double dn_log, dn_sign, do_log = 0.0, do_sign = 1.0;
+    rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, knew, false, dn_log, dn_sign);
+    for (int f = 0; f < nf; ++f) {
+        int k = x.ih[IH_KF + f]; if (k == 0) continue;
+        const double* src = Mbuf(C, x, f); double* sp = Mbuf(C, x, nf);
+        for (int i = 0; i < k; ++i) for (int j = x.lane; j < k; j += W2B_WARP) sp[(size_t)i * C.ld + j] = src[(size_t)i * C.ld + j];
+        wsync();
+        double l, s; invert_inplace(sp, k, C.ld, x.wI, false, l, s);
+        do_log += l; do_sign *= s;
+    }
+    const double dr_log = dn_log + do_log, dr_sign = dn_sign * do_sign;
+    double tn_log, tn_sign;
+    trace_full_scalar(T, x.tau, x.sc_code, x.sc_sst, x.n, new_outer, tn_log, tn_sign);
+    const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
+    const double prob = fabs(exp(trr_log + dr_log) * factor);
+    const double rand = x.rng.next();
+    log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 17, rand);
+    if (!(rand < prob)) { log_end(x, 0); return; }
+    // ---- accept
+    for (int i = x.lane; i < x.n; i += W2B_WARP) { x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
+    for (int f = 0; f < nf; ++f) {
+        int k = knew[f];
+        for (int i = x.lane; i < k; i += W2B_WARP) { x.tc[(size_t)f * C.kcap + i] = x.sc_tc[(size_t)f * C.kcap + i]; x.ta[(size_t)f * C.kcap + i] = x.sc_ta[(size_t)f * C.kcap + i]; }
+    }
+    wsync();
+    if (x.lane == 0) for (int f = 0; f < nf; ++f) x.ih[IH_KF + f] = knew[f];
+    wsync();
+    double l2, s2;
+    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
+    x.outer = new_outer;
+    x.det_log = dn_log; x.det_sign = dn_sign; x.tr_log = tn_log; x.tr_sign = tn_sign;
+    x.perm = perm_full(x.code, x.n);
+    x.palt = 0; for (int f = 0; f < nf; ++f) x.palt |= palt_flavour(C, x, f) << f;
+    update_cfgsign(T, x);
+    bump(x, C_ACCGLOB);
+    log_end(x, 1);
+}
+
+// ------------------------------------------------------------------ StepShiftTau (CTQMC.F90:4557-4835)
+W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
+    log_begin(x, 4);
+    if (x.n == 0) {                        // StepChangeOuter CTQMC.F90:4570-4638
+        const double rand = x.rng.next();
+        double acc = 0.0; int pick = T.nsst - 1;
+        for (int i = 0; i < T.nsst; ++i) { double w = ldg(&T.empty_w[i]); acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
+        x.outer = pick; x.tr_log = ldg(&T.empty_log[pick]); x.tr_sign = 1.0;
+        update_cfgsign(T, x);
+        log_set(x, 17, rand); log_end(x, 1);
+        return;
+    }
+    const double dt = x.rng.next() * T.beta;
+    log_set(x, 2, dt);
+    if (dt == 0.0 || dt == T.beta) { log_end(x, 2); return; }
+    bump(x, C_TRYSHIFT);
+    const int n = x.n;
+    const int nwrap = count_lt(x.tau, n, dt);                     // operators passing through tau = 0
+    const int first = nwrap == n ? 0 : nwrap;
+    const int new_outer = first == 0 ? x.outer : (int)x.sst[first - 1];
+    for (int i = x.lane; i < n; i += W2B_WARP) {
+        int src = first + i; if (src >= n) src -= n;
+        double t = x.tau[src] - dt; if (t < 0.0) t += T.beta;     // modulo(tau - dt, beta)
+        x.sc_tau[i] = t; x.sc_code[i] = x.code[src]; x.sc_sst[i] = x.sst[src];
+    }
+    wsync();
+    const int wp_old = x.wpos; const double wmin_old = x.wmin, wmax_old = x.wmax;
+    const int sh = ((int)floor((dt / T.beta) * (double)(R.num_windows + 1))) % R.num_windows;
+    x.wpos = ((wp_old - sh) % R.num_windows + R.num_windows) % R.num_windows;
+    set_window_edges(T, R, x);
+    double tn_log, tn_sign;
+    trace_full_scalar(T, x.sc_tau, x.sc_code, x.sc_sst, n, new_outer, tn_log, tn_sign);
+    const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
+    const double prob = fabs(trr_sign * exp(trr_log));
+    const double rand = x.rng.next();
+    log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 17, rand);
+    if (!(rand < prob)) { x.wpos = wp_old; x.wmin = wmin_old; x.wmax = wmax_old; log_end(x, 0); return; }
+    // ---- accept: update_InvFullHybrShiftTau_diag Trace.F90:2355-2457 (cyclic roll + negation of wrapped rows/columns)
+    double detrat = 1.0;
+    for (int f = 0; f < T.nf; ++f) {
+        const int k = x.ih[IH_KF + f];
+        if (k == 0) continue;
+        double* tc = x.tc + (size_t)f * C.kcap; double* ta = x.ta + (size_t)f * C.kcap;
+        const int w1 = count_lt(tc, k, dt), w2 = count_lt(ta, k, dt);
+        if (!((w1 == 0 && w2 == 0) || (w1 == k && w2 == k))) {
+            const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, T.nf);
+            for (int i = 0; i < k; ++i) {
+                int in = i - w1; double si = 1.0; if (in < 0) { in += k; si = -1.0; }
+                for (int j = x.lane; j < k; j += W2B_WARP) {
+                    int jn = j - w2; double sj = si; if (jn < 0) { jn += k; sj = -si; }
+                    dst[(size_t)in * C.ld + jn] = sj * src[(size_t)i * C.ld + j];
+                }
+            }
+            wsync();
+            if (x.lane == 0) { int t = x.ih[IH_MSLOT + f]; x.ih[IH_MSLOT + f] = x.ih[IH_MSLOT + T.nf]; x.ih[IH_MSLOT + T.nf] = t; }
+            wsync();
+        }
+        if ((k & 1) && ((w1 + w2) & 1)) detrat = -detrat;
+        // rotate the flavour tau arrays
+        double* scc = x.sc_tc + (size_t)f * C.kcap; double* sca = x.sc_ta + (size_t)f * C.kcap;
+        for (int i = x.lane; i < k; i += W2B_WARP) {
+            int s1 = i + w1; double a1 = 0.0; if (s1 >= k) { s1 -= k; a1 = T.beta; }
+            int s2 = i + w2; double a2 = 0.0; if (s2 >= k) { s2 -= k; a2 = T.beta; }
+            double v1 = tc[s1] - dt; if (v1 < 0.0) v1 += T.beta; (void)a1;
+            double v2 = ta[s2] - dt; if (v2 < 0.0) v2 += T.beta; (void)a2;
+            scc[i] = v1; sca[i] = v2;
+        }
+        wsync();
+        for (int i = x.lane; i < k; i += W2B_WARP) { tc[i] = scc[i]; ta[i] = sca[i]; }
+        wsync();
+    }
+    for (int i = x.lane; i < n; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
+    wsync();
+    x.outer = new_outer;
+    x.tr_log = tn_log; x.tr_sign = tn_sign; x.det_sign *= detrat;
+    x.npairs = -1;
+    x.perm = perm_full(x.code, x.n);
+    x.palt = 0; for (int f = 0; f < T.nf; ++f) x.palt |= palt_flavour(C, x, f) << f;
+    update_cfgsign(T, x);
+    bump(x, C_ACCSHIFT);
+    log_end(x, 1);
+}
+
+// ------------------------------------------------------------------ one Monte-Carlo step (CTQMC.F90:8428-8533)
+W2B_HD void do_step(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, unsigned long long& attempts) {
+    const double r = x.rng.next();
+    if (r < (1.0 - R.pshift - R.pglob) / 2.0) {
+        (void)x.rng.next(); (void)x.rng.next();                   // Percentage4OperatorMove / PercentageOuterMove draws
+        step_add(T, R, C, A, x); ++attempts;
+    } else if (r <= 1.0 - R.pshift - R.pglob) {
+        (void)x.rng.next(); (void)x.rng.next();
+        step_rem(T, R, C, A, x); ++attempts;
+    } else if (r <= 1.0 - R.pshift) step_glob(T, R, C, x);
+    else step_shift(T, R, C, x);
+    if (attempts % (unsigned long long)R.nslide == 0ull) {         // shift_window Trace.F90:1652-1678
+        if (R.num_windows > 1) {
+            x.wpos += 1; if (x.wpos == R.num_windows) x.wpos = 0;
+            set_window_edges(T, R, x);
+            x.npairs = -1;
+        }
+    }
+    if (x.log && x.lane == 0) x.log[16] = x.wpos;
+}
+
+// ------------------------------------------------------------------ chain load / store
+W2B_HD void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, double* wscratch, int* iscratch) {
+    x.lane = lane_id();
+    x.tau = C.op_tau + (size_t)chain * C.ops_cap; x.code = C.op_code + (size_t)chain * C.ops_cap; x.sst = C.op_sst + (size_t)chain * C.ops_cap;
+    x.sc_tau = C.sc_tau + (size_t)chain * C.ops_cap; x.sc_code = C.sc_code + (size_t)chain * C.ops_cap; x.sc_sst = C.sc_sst + (size_t)chain * C.ops_cap;
+    x.tc = C.tau_c + (size_t)chain * T.nf * C.kcap; x.ta = C.tau_a + (size_t)chain * T.nf * C.kcap;
+    x.sc_tc = C.sc_tc + (size_t)chain * T.nf * C.kcap; x.sc_ta = C.sc_ta + (size_t)chain * T.nf * C.kcap;
+    x.Mbase = C.M + (size_t)chain * (T.nf + 1) * ((size_t)C.kcap * C.ld);
+    x.ih = C.ih + (size_t)chain * IH_STRIDE; x.dh = C.dh + (size_t)chain * DH_STRIDE;
+    x.cnt = C.counters + (size_t)chain * C_NCNT;
+    x.wQ = wscratch; x.wR = wscratch + C.kcap; x.wV = wscratch + 2 * C.kcap; x.wI = iscratch;
+    x.n = x.ih[IH_NOPS]; x.outer = x.ih[IH_OUTER]; x.wpos = x.ih[IH_WPOS]; x.npairs = x.ih[IH_NPAIRS];
+    x.perm = x.ih[IH_PERM]; x.palt = x.ih[IH_PALT]; x.err = x.ih[IH_ERR];
+    x.det_log = x.dh[DH_DETLOG]; x.det_sign = x.dh[DH_DETSIGN]; x.tr_log = x.dh[DH_TRLOG]; x.tr_sign = x.dh[DH_TRSIGN]; x.cfgsign = x.dh[DH_CFGSIGN];
+    x.rng.init(R.seed, R.chain_base + (unsigned)chain, C.rng_ctr[chain]);
+    set_window_edges(T, R, x);
+    x.log = nullptr;
+}
+W2B_HD void ctx_store(const Chains& C, int chain, Ctx& x) {
+    wsync();
+    if (x.lane == 0) {
+        x.ih[IH_NOPS] = x.n; x.ih[IH_OUTER] = x.outer; x.ih[IH_WPOS] = x.wpos; x.ih[IH_NPAIRS] = x.npairs;
+        x.ih[IH_PERM] = x.perm; x.ih[IH_PALT] = x.palt; x.ih[IH_ERR] = x.err;
+        x.dh[DH_DETLOG] = x.det_log; x.dh[DH_DETSIGN] = x.det_sign; x.dh[DH_TRLOG] = x.tr_log; x.dh[DH_TRSIGN] = x.tr_sign; x.dh[DH_CFGSIGN] = x.cfgsign;
+        C.rng_ctr[chain] = x.rng.ctr;
+    }
+    wsync();
+}
+
+// advance one chain by nsteps moves; logbuf (optional) receives LOGW doubles per move
+W2B_HD void sweep_chain(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain, long long nsteps,
+                        double* wscratch, int* iscratch, double* logbuf) {
+    Ctx x;
+    ctx_bind(T, R, C, chain, x, wscratch, iscratch);
+    unsigned long long attempts = x.cnt[C_TRYADD] + x.cnt[C_TRYREM];
+    wsync();
+    for (long long it = 0; it < nsteps; ++it) {
+        x.log = logbuf ? logbuf + (size_t)it * LOGW : nullptr;
+        do_step(T, R, C, A, x, attempts);
+        wsync();
+    }
+    if (x.lane == 0) x.cnt[C_STEPS] += (unsigned long long)nsteps;
+    ctx_store(C, chain, x);
+}
+
+// init_Trace (Trace.F90:340-701): empty configuration, outer superstate drawn with the empty-trace weights
+W2B_HD void init_chain(const Tables& T, const Run& R, const Chains& C, int chain) {
+    if (lane_id() != 0) return;
+    int* ih = C.ih + (size_t)chain * IH_STRIDE; double* dh = C.dh + (size_t)chain * DH_STRIDE;
+    Philox rng; rng.init(R.seed, R.chain_base + (unsigned)chain, 0ull);
+    const double rand = rng.next();
+    double acc = 0.0; int pick = T.nsst - 1;
+    for (int i = 0; i < T.nsst; ++i) { double w = T.empty_w[i]; acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
+    for (int i = 0; i < IH_STRIDE; ++i) ih[i] = 0;
+    ih[IH_OUTER] = pick; ih[IH_NPAIRS] = 0;
+    for (int f = 0; f <= T.nf; ++f) ih[IH_MSLOT + f] = f;
+    dh[DH_DETLOG] = 0.0; dh[DH_DETSIGN] = 1.0; dh[DH_TRLOG] = T.empty_log[pick]; dh[DH_TRSIGN] = 1.0; dh[DH_CFGSIGN] = -1.0;
+    C.rng_ctr[chain] = rng.ctr;
+    for (int i = 0; i < C_NCNT; ++i) C.counters[(size_t)chain * C_NCNT + i] = 0ull;
+}
+
+// ------------------------------------------------------------------ measurement (CTQMC.F90:8541-8581)
+constexpr int LEG_CHUNK = 20;
+W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain) {
+    const int lane = lane_id();
+    const int* ih = C.ih + (size_t)chain * IH_STRIDE; const double* dh = C.dh + (size_t)chain * DH_STRIDE;
+    const int n = ih[IH_NOPS], outer = ih[IH_OUTER];
+    const double cfgsign = dh[DH_CFGSIGN];
+    double* acc = A.base + (size_t)((R.chain_base + (unsigned)chain) % (unsigned)R.nbins) * A.stride;
+    const double* tau = C.op_tau + (size_t)chain * C.ops_cap; const short* sst = C.op_sst + (size_t)chain * C.ops_cap;
+    if (lane == 0) {
+        atomic_add(&acc[A.o_sign], cfgsign); atomic_add(&acc[A.o_cnt], 1.0);                 // MeasSign 3343
+        atomic_add(&acc[A.o_outer + outer], 1.0); atomic_add(&acc[A.o_signsst + outer], cfgsign);   // MeasOuterHistograms 3285-3339 (1x1 blocks)
+        atomic_add(&acc[A.o_contribsst + outer], exp(dh[DH_TRLOG]));
+        int off = T.offset[outer];
+        atomic_add(&acc[A.o_outerst + off], 1.0); atomic_add(&acc[A.o_signst + off], cfgsign);  // Trace.sign*parttrace.sign = 1 for a 1x1 block
+        atomic_add(&acc[A.o_contribst + off], exp(dh[DH_TRLOG]));
+        for (int f = 0; f < T.nf; ++f) {                                                       // MeasExpOrder 3264-3282
+            int k = ih[IH_KF + f]; if (k > R.maxhisto) k = R.maxhisto;
+            atomic_add(&acc[A.o_histo + f * (R.maxhisto + 1) + k], 1.0);
+        }
+    }
+    if (R.meas_dm) {                                                                          // MeasDensityMatrix_beta_half 3088-3151 (1x1 blocks)
+        int ihalf = count_le(tau, n, T.beta / 2.0);
+        if (lane == 0) {
+            int s = ihalf == 0 ? outer : (int)sst[ihalf - 1];
+            atomic_add(&acc[A.o_dens + T.offset[s]], -cfgsign);
+        }
+    }
+    // MeasGtauRem 2252-2440: all (annihilator, creator) pairs of every flavour
+    const double beta = T.beta;
+    for (int f = 0; f < T.nf; ++f) {
+        const int k = ih[IH_KF + f];
+        if (k == 0) continue;
+        const double* tc = C.tau_c + ((size_t)chain * T.nf + f) * C.kcap; const double* ta = C.tau_a + ((size_t)chain * T.nf + f) * C.kcap;
+        const double* M = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
+        for (int lbase = 0; lbase < R.nlegmax; lbase += LEG_CHUNK) {
+            double part[LEG_CHUNK];
+#pragma unroll
+            for (int q = 0; q < LEG_CHUNK; ++q) part[q] = 0.0;
+            const int lend = lbase + LEG_CHUNK < R.nlegmax ? lbase + LEG_CHUNK : R.nlegmax;
+            for (int p = lane; p < k * k; p += W2B_WARP) {
+                int ic = p / k, ia = p - ic * k;
+                double Mv = M[(size_t)ic * C.ld + ia];
+                double dtau = ta[ia] - tc[ic], xx; int idt;
+                if (dtau > 0.0) { idt = (int)(dtau / beta * (double)R.ntau) + 1; xx = 2.0 / beta * dtau - 1.0; }
+                else { idt = (int)((beta + dtau) / beta * (double)R.ntau) + 1; xx = 2.0 / beta * (beta + dtau) - 1.0; Mv = -Mv; }
+                Mv *= cfgsign;
+                if (lbase == 0) { if (idt > R.ntau) idt = R.ntau; atomic_add(&acc[A.o_gtau + f * R.ntau + idt - 1], Mv); }
+                double Plx = 0.0, Plm1 = 0.0, Pl = 0.0;
+                for (int l = 0; l < lend; ++l) {
+                    if (l == 0) Pl = 1.0; else if (l == 1) Pl = xx;
+                    else { int ll = l - 1; Pl = (2.0 * ll + 1.0) / (double)(ll + 1) * xx * Plx - (double)ll / (double)(ll + 1) * Plm1; }
+                    if (l >= lbase) part[l - lbase] += Mv * Pl;
+                    Plm1 = Plx; Plx = Pl;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < LEG_CHUNK; ++q) {
+                double s = wsum(part[q]);
+                if (lane == 0 && lbase + q < R.nlegmax) atomic_add(&acc[A.o_gleg + f * R.nlegmax + lbase + q], s);
+            }
+        }
+    }
+}
+
+// Rebuild all derived state of one chain from its operator list (set_mc_config_from_arrays, Trace.F90:6872-7000):
+// superstate sequence, flavour tau arrays, inverse matrices + determinant, trace, signs.
+W2B_HD void rebuild_chain(const Tables& T, const Run& R, const Chains& C, int chain, double* wscratch, int* iscratch) {
+    Ctx x;
+    ctx_bind(T, R, C, chain, x, wscratch, iscratch);
+    const int lane = x.lane;
+    x.wpos = 0; set_window_edges(T, R, x);
+    if (lane == 0) for (int f = 0; f <= T.nf; ++f) x.ih[IH_MSLOT + f] = f;
+    // flavour arrays
+    for (int f = 0; f < T.nf; ++f) {
+        int kc = 0, ka = 0;
+        if (lane == 0) {
+            for (int i = 0; i < x.n; ++i) {
+                int cd = x.code[i];
+                if ((cd >> 1) != f) continue;
+                if ((cd & 1) == 0) { if (kc < C.kcap) x.tc[(size_t)f * C.kcap + kc] = x.tau[i]; ++kc; }
+                else { if (ka < C.kcap) x.ta[(size_t)f * C.kcap + ka] = x.tau[i]; ++ka; }
+            }
+            if (kc != ka || kc > C.kcap) { x.err |= ERR_CAPACITY; kc = 0; }
+            x.ih[IH_KF + f] = kc;
+        }
+        wsync();
+    }
+    x.err = wbcast(x.err, 0);
+    int fin = walk_store(T, x.code, 0, x.n, x.outer, x.sst, 0);
+    if (fin != x.outer) x.err |= ERR_GLOBAL_QN;
+    double lg, sg;
+    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, lg, sg);
+    x.det_log = lg; x.det_sign = sg;
+    if (sg == 0.0) x.err |= ERR_SINGULAR;
+    if (!(x.err & ERR_GLOBAL_QN)) trace_full_scalar(T, x.tau, x.code, x.sst, x.n, x.outer, x.tr_log, x.tr_sign);
+    x.npairs = -1;
+    x.perm = perm_full(x.code, x.n);
+    x.palt = 0; for (int f = 0; f < T.nf; ++f) x.palt |= palt_flavour(C, x, f) << f;
+    update_cfgsign(T, x);
+    ctx_store(C, chain, x);
+}
+
+}  // namespace w2b
