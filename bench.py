@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the CT-HYB hot path (BASELINE.json metric: QMC moves/s for the whole box).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 engine (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on the host cores
+
+A *step* is one accumulation block of the hot path: every chain of the population advances by NCorr = 100 moves
+(one sweep kernel) and is measured once (one measurement kernel) -- the body of ctqmc_measure's iNMeas loop
+(reference CTQMC.F90:8422-8581).  A *move* is one iteration of the iNCorr loop: one proposal of any type,
+accepted or not (CTQMC.F90:8428-8434).  value = chains * NCorr * K * N / time.
+
+Timed region of `value`: chain state resident in HBM, K steps, (N > 1: plus the single all-reduce of the raw
+accumulators that ends an accumulation), CUDA events on the launching stream, max over ranks.
+`e2e`: same steps through the C ABI with HOST buffers: every step uploads the hybridisation function from pinned
+host memory (what a DMFT iteration hands to init_solver) and copies the accumulator slab back to the host.
+`roofline`: dominant kernel k_sweep, algorithmic bytes counted in-kernel per move (DESIGN.md "Roofline accounting")
+divided by the kernel's summed event time.  `cpu_baseline`: the oracle (CPU restatement of the reference algorithm;
+the Fortran reference cannot be built in this image) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C1": "C1: 1-band Hubbard, Bethe bath, half filling, U=2, beta=10 (4-state Fock space)",
+    "C2": "C2: 2-orbital density-density Kanamori, beta=50, 16-state Fock space (determinant-dominated)",
+    "C3": "C3: 3-orbital t2g full Kanamori, beta=40, 64-state Fock space, blocks d<=3",
+    "C4": "C4: 5-orbital d-shell full Slater-Coulomb, beta=20, 1024-state Fock space, 132 blocks d<=28",
+    "C5": "C5: 1-band Hubbard, beta=200 (expansion order in the hundreds)",
+}
+DEFAULT_CHAINS = {"C1": 65536, "C2": 16384, "C3": 16384, "C4": 8192, "C5": 4096}
+THERMALISE = {"C1": 2000, "C2": 6000, "C3": 6000, "C4": 6000, "C5": 40000}
+METRIC = "QMC moves/sec (box)"
+UNIT = "moves/s"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(path))
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def cpu_oracle_rate(cfg, seconds, nthreads, with_measure=True):
+    """Oracle (CPU restatement) on `nthreads` host threads, one independent chain each; returns moves/s and a note."""
+    from w2dynamics_b200 import problems
+    from oracle.oracle import OracleChain
+    from oracle import oracle as orc
+    orc.build()
+    p = problems.make_problem(cfg)
+    ncorr = int(p.qmc.get("NCorr", 100))
+    chains = [OracleChain(p, rng="philox", seed=43890, chain=1000 + i) for i in range(nthreads)]
+    therm = THERMALISE[cfg]
+
+    def run(o, fn):
+        fn(o)
+    ths = [threading.Thread(target=run, args=(o, lambda o: o.warmup(therm))) for o in chains]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    # calibrate the chunk on one chain
+    t0 = time.time(); chains[0].measure(20, reset=False); dt = max(time.time() - t0, 1e-4)
+    nmeas = max(1, int(20 * (seconds / 4.0) / dt))
+    done = [0] * nthreads
+    stop_at = time.time() + seconds
+
+    def work(i):
+        o = chains[i]
+        while time.time() < stop_at:
+            if with_measure:
+                o.measure(nmeas, reset=False)
+            else:
+                o.steps(nmeas * ncorr)
+            done[i] += nmeas * ncorr
+    t0 = time.time()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    dt = time.time() - t0
+    return sum(done) / dt, "%d independent chains x %.0f s of NCorr=%d sweeps + measurements (%d moves in total), thermalised %d moves" % (
+        nthreads, dt, ncorr, sum(done), therm)
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm for the path.  The Fortran module cannot be built in this
+    image (no Fortran compiler), so this is the oracle port on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from w2dynamics_b200 import problems
+    from oracle.oracle import OracleChain
+    from oracle import oracle as orc
+    orc.build()
+    cfg = args.config
+    nthreads = os.cpu_count() or 1
+    p = problems.make_problem(cfg)
+    ncorr = int(p.qmc.get("NCorr", 100))
+    chains = [OracleChain(p, rng="philox", seed=43890, chain=1000 + i) for i in range(nthreads)]
+    ths = [threading.Thread(target=lambda o=o: o.warmup(THERMALISE[cfg])) for o in chains]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    t0 = time.time(); chains[0].measure(20, reset=False); dt = max(time.time() - t0, 1e-4)
+    budget = 60.0 / max(1, args.steps + args.warmup)            # whole run ~ a minute
+    nmeas = max(1, int(20 * min(budget, 5.0) / dt))
+
+    def step():
+        ths = [threading.Thread(target=lambda o=o: o.measure(nmeas, reset=False)) for o in chains]
+        [t.start() for t in ths]; [t.join() for t in ths]
+    for _ in range(args.warmup):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = time.time() - t0
+    moves = nthreads * nmeas * ncorr * args.steps
+    val = moves / dt
+    sample = "%d host threads x %d steps of %d measurements x NCorr=%d moves" % (nthreads, args.steps, nmeas, ncorr)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[cfg], "ncorr": ncorr, "note": "oracle port of the reference algorithm (Fortran reference not buildable here)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_engine(args):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import __graft_entry__ as g
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from w2dynamics_b200 import problems
+    from w2dynamics_b200.CTQMC import MCTQMC
+
+    cfg = args.config
+    p = problems.make_problem(cfg)
+    ncorr = int(p.qmc.get("NCorr", 100))
+    nchains = args.chains or DEFAULT_CHAINS[cfg]
+    eng = MCTQMC()
+    eng.set_option("nchains", nchains); eng.set_option("nbins", 32); eng.set_option("device", local)
+    if world > 1:
+        eng.enable_distributed()
+    eng.init_rnd(43890)
+    eng.init_paras(p.pstring())
+    eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)
+    eng.set_taudiffmax(p.qmc["TaudiffMax"])
+    L = eng._load()
+    L.w2b_pinned_alloc.restype = C.c_void_p
+    eng.ctqmc_warmup(args.thermalise if args.thermalise >= 0 else THERMALISE[cfg])      # thermalisation, untimed
+    eng.init_counters()
+    ms = (C.c_double * 3)()
+
+    def blocks(n):
+        eng._ck(L.w2b_bench_blocks(C.c_longlong(n), C.c_longlong(ncorr), C.c_int(1), ms))
+        return ms[0], ms[1], ms[2]
+
+    def allreduce_accum():
+        if world > 1:
+            eng.allreduce_accumulators()
+
+    blocks(args.warmup)                                        # W untimed warm-up steps
+    allreduce_accum()
+    eng._ck(L.w2b_read_accum(None, C.c_size_t(0), C.byref(C.c_size_t())))
+    torch.cuda.synchronize()
+    bytes0, launches0 = eng.scalar("cnt_alg_bytes"), eng.scalar("gpu_launches")
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t_all, t_sweep, t_meas = blocks(args.steps)                # K timed steps (CUDA events inside, on the launching stream)
+    allreduce_accum()                                          # N > 1: the single all-reduce that ends an accumulation
+    e1.record()
+    torch.cuda.synchronize()
+    elapsed_ms = max(e0.elapsed_time(e1), t_all)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    bytes1, launches1 = eng.scalar("cnt_alg_bytes"), eng.scalar("gpu_launches")
+    mean_k = eng.scalar("mean_order")
+    moves = float(nchains) * ncorr * args.steps * world
+    value = moves / (elapsed_ms * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, every step
+    nacc = C.c_size_t()
+    eng._ck(L.w2b_read_accum(None, C.c_size_t(0), C.byref(nacc)))
+    nft = p.ftau.size
+    h_ft = L.w2b_pinned_alloc(C.c_size_t(nft * 8)); h_acc = L.w2b_pinned_alloc(C.c_size_t(nacc.value * 8))
+    C.memmove(h_ft, np.asfortranarray(p.ftau).ctypes.data, nft * 8)
+    dp = C.POINTER(C.c_double)
+
+    def e2e_step():
+        eng._ck(L.w2b_upload_ftau(C.cast(h_ft, dp), C.c_int(p.ftau.shape[-1])))
+        eng._ck(L.w2b_block(C.c_longlong(ncorr), C.c_int(1)))
+        eng._ck(L.w2b_read_accum(C.cast(h_acc, dp), C.c_size_t(nacc.value), C.byref(nacc)))
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = moves / (e2e_ms * 1e-3)
+    err = int(eng.scalar("error_flags"))
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = bytes1 - bytes0
+        achieved = alg_bytes / (t_sweep * 1e-3) / 1e9 if t_sweep > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg)
+        except Exception:
+            pass
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            nthreads = os.cpu_count() or 1
+            v, sample = cpu_oracle_rate(cfg, args.cpu_seconds, nthreads)
+            cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample}
+        state_gb = nchains * (2 * p.nbands + 1) * eng.scalar("kcap") ** 2 * 8 / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[cfg], "chains_per_gpu": nchains, "ncorr": ncorr, "moves_per_step": nchains * ncorr * world,
+                       "mean_order_per_flavour": mean_k, "parallelism": "chains sharded over %d GPU(s), no data-path collective; one all-reduce of the accumulators per accumulation" % world,
+                       "l2": "inverse-matrix state %.1f GB per GPU > 126 MB L2 (inputs larger than L2, no flush needed)" % state_gb,
+                       "error_flags": err},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(nft * 8), "d2h_bytes_per_step": int(nacc.value * 8),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches1 - launches0),
+            "kernel_ms": {"k_sweep": t_sweep / args.steps, "k_measure": t_meas / args.steps},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "k_sweep", "algorithmic_bytes_per_launch": alg_bytes / args.steps, "launch_ms": t_sweep / args.steps,
+                         "peak_source": peak_src},
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    eng.dest_ctqmc()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=os.environ.get("W2B_BENCH_CONFIG", "C2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default per config)")
+    ap.add_argument("--thermalise", type=int, default=-1, help="untimed thermalisation moves per chain")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,16 @@ int w2b_finalize(void);
 /* one accumulation block: `nsweep` moves per chain followed by one measurement (bench / profiling hook) */
 int w2b_block(long long nsweep, int do_measure);
 int w2b_sync(void);
+/* bench hook: nblocks x (nsweep moves per chain [+ measurement]) timed with CUDA events on the launching stream;
+ * ms[0] = whole region, ms[1] = sum over sweep kernels, ms[2] = sum over measurement kernels */
+int w2b_bench_blocks(long long nblocks, long long nsweep, int do_measure, double* ms);
+/* end-to-end hooks: replace the hybridisation function from HOST memory (layout of init_solver's ftau_full,
+ * CTQMC.F90:7950-7955) and copy the raw accumulator slab (nbins x stride doubles) to HOST memory */
+int w2b_upload_ftau(const double* ftau_full, int nftau);
+int w2b_read_accum(double* out, size_t cap, size_t* n);
+/* page-locked host buffers for the two calls above */
+void* w2b_pinned_alloc(size_t bytes);
+void w2b_pinned_free(void* p);
 
 /* ---- replay / parity hooks ---- */
 /* advance all chains by nsteps moves and record chain `chain`'s per-move records (20 doubles each):

@@ -1,0 +1,142 @@
+"""CPU logic tests of the chain engine: the kernel source (w2dynamics_b200/csrc/engine_core.hpp) compiled with
+W2B_HOST_EMU (one lane per chain, g++) is replayed move by move against the oracle.  This checks the *logic* the
+CUDA build shares; the CUDA build itself is checked by the `gpu` tests through the product C ABI.  The host-emulation
+library is test infrastructure only: the product module loads the CUDA library and nothing else."""
+import numpy as np
+import pytest
+
+import _hostemu
+from oracle.oracle import OracleChain
+from w2dynamics_b200 import problems
+
+INTS = [0, 1, 4, 5, 6, 8, 10, 12, 13, 14, 15, 16]     # move, status, flavour, FPos, signs, n_ops, outer sst, NPairs, cfgsign, window
+TOL = 1e-10                                            # north_star: per-move det / trace ratios within 1e-10 relative
+
+
+def make(p, nchains=4, nbins=2, seed=43890):
+    eng = _hostemu.make()
+    eng.set_option("nchains", nchains)
+    eng.set_option("nbins", nbins)
+    eng.init_rnd(seed)
+    eng.init_paras(p.pstring())
+    eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)
+    eng.set_taudiffmax(p.qmc["TaudiffMax"])
+    eng.init_counters()
+    return eng
+
+
+def assert_replay(log, ref):
+    bad = np.nonzero((log[:, INTS] != ref[:, INTS]).any(1))[0]
+    assert bad.size == 0, "integer state differs first at move %d: %s vs %s" % (bad[0], log[bad[0]], ref[bad[0]])
+    for col in (7, 9):      # log|det ratio|, log|trace ratio|  (absolute error of a log == relative error of the ratio)
+        assert np.abs(log[:, col] - ref[:, col]).max() < TOL
+    assert np.array_equal(log[:, [2, 3, 17]], ref[:, [2, 3, 17]])         # proposed times and accept draw: same RNG stream
+
+
+@pytest.mark.parametrize("cfg,nsteps,chain", [("C1", 20000, 0), ("C2", 20000, 3), ("C5", 6000, 1)])
+def test_replay_parity(built, cfg, nsteps, chain):
+    p = problems.make_problem(cfg, nftau=2001)
+    eng = make(p)
+    log = eng.debug_steps(chain, nsteps)
+    orc = OracleChain(p, rng="philox", seed=43890, chain=chain)
+    orc.init_counters()
+    ref = orc.steps(nsteps, log=True)
+    assert_replay(log, ref)
+    assert set(np.unique(log[:, 0])) == {1.0, 2.0, 3.0, 4.0}             # all four move types were exercised
+    # chain state after the replay: trace, determinant, sign, inverse matrices
+    s, o = eng.debug_chain_scalars(chain), orc.scalars()
+    assert s["error"] == 0 and orc.error == 0
+    assert abs(s["trace_log"] - o["trace_log"]) < 1e-8 and abs(s["det_log"] - o["det_log"]) < 1e-8
+    assert (s["trace_sign"], s["det_sign"], s["cfgsign"]) == (o["trace_sign"], o["det_sign"], o["cfgsign"])
+    for f in range(2 * p.nbands):
+        a, b = eng.debug_minv(chain, f // 2 + 1, f % 2 + 1), orc.minv(f)
+        assert a.shape == b.shape
+        if a.size:
+            assert np.abs(a - b).max() < 1e-9 * max(1.0, np.abs(b).max())
+    eng.dest_ctqmc()
+
+
+def test_config_roundtrip_and_measurement(built):
+    """get_mc_config -> oracle.set_config gives the same derived state; one measurement of the same
+    configuration adds the same numbers to the accumulators (MeasGtauRem, histograms, sign, density matrix)."""
+    p = problems.make_problem("C2", nftau=2001, Ntau=200, NLegMax=30)
+    eng = make(p, nchains=1, nbins=1)
+    eng.ctqmc_warmup(6000)
+    n, osst, _ = eng.get_mc_config_scalars(0)
+    taus, orbs, spins, cas, hyb, osst2, _ = eng.get_mc_config(n, 0)
+    assert osst == osst2 and np.all(np.diff(taus) > 0) and np.all(hyb == -1)
+    orc = OracleChain(p, seed=1, Ntau=200, NLegMax=30)
+    orc.set_config(taus, orbs, spins, cas, osst)
+    s, o = eng.debug_chain_scalars(0), orc.scalars()
+    assert abs(s["trace_log"] - o["trace_log"]) < 1e-9 and abs(s["det_log"] - o["det_log"]) < 1e-8
+    assert s["cfgsign"] == o["cfgsign"]
+    # set_mc_config on the engine side reproduces its own state from scratch (LU inverse)
+    before = [eng.debug_minv(0, f // 2 + 1, f % 2 + 1) for f in range(4)]
+    eng.set_mc_config(n, taus, orbs, spins, cas, hyb, osst, 1, chain=0)
+    s2 = eng.debug_chain_scalars(0)
+    assert abs(s2["det_log"] - s["det_log"]) < 1e-8 and s2["cfgsign"] == s["cfgsign"] and s2["error"] == 0
+    for f in range(4):
+        a = eng.debug_minv(0, f // 2 + 1, f % 2 + 1)
+        assert np.abs(a - before[f]).max() < 1e-8 * max(1.0, np.abs(a).max())
+    # one measurement each
+    eng.block(0, True)
+    eng._ck(eng._load().w2b_finalize())
+    orc.measure(0, reset=True)
+    orc.measure_once()
+    r = orc.results()
+    assert np.abs(eng.gtau - r["gtau"]).max() < 1e-9 * max(1.0, np.abs(r["gtau"]).max())
+    assert np.abs(eng.gleg - r["gleg"]).max() < 1e-9 * max(1.0, np.abs(r["gleg"]).max())
+    assert np.array_equal(eng.histo, r["hist"])
+    assert eng.mean_sign == r["sign"]
+    assert np.abs(eng.occ - r["occ"]).max() < 1e-12
+    assert np.abs(eng.rho1 - r["rho1"]).max() < 1e-12
+    eng.dest_ctqmc()
+
+
+def test_statistical_agreement_c1(built):
+    """Engine population vs oracle chain on C1: G(tau), occupation, <k>, sign agree within Monte-Carlo error bars;
+    particle-hole symmetry pins the exact values (occ = 0.5, G(tau) = G(beta - tau), sign = 1)."""
+    p = problems.make_problem("C1", nftau=2001, Nmeas=300, Ntau=100, NLegMax=20)
+    eng = make(p, nchains=32, nbins=8)
+    eng.ctqmc_warmup(3000)
+    eng.ctqmc_measure(1, 1)
+    orc = OracleChain(p, seed=1234, Ntau=100, NLegMax=20)
+    orc.warmup(20000)
+    orc.measure(9600)
+    r = orc.results()
+    bins = eng.bins("gtau")
+    assert bins.shape[0] == 8
+    err = bins.std(0, ddof=1) / np.sqrt(bins.shape[0])
+    g = eng.gtau
+    # literal restatement of cfgsign = -get_Sign (CTQMC.F90:3574; TTrace default -1, Trace.F90:129): a sign-problem-free
+    # run reports mean_sign = -1 and every estimator divides it out (CTQMC.F90:8697, 8730)
+    assert eng.mean_sign == -1.0 and r["sign"] == -1.0
+    assert abs(eng.occ[0, 0, 0, 0] - 0.5) < 0.02 and abs(eng.occ[0, 1, 0, 1] - 0.5) < 0.02
+    z = (g - r["gtau"]) / np.sqrt(err ** 2 + err.mean() ** 2 + 1e-12)
+    assert np.abs(z).mean() < 2.0 and np.abs(z).max() < 6.0
+    assert np.abs(g[0, 0] - g[0, 0, ::-1]).mean() < 4 * err.mean() + 1e-3
+    k_eng = (eng.histo * np.arange(eng.histo.shape[2])[None, None, :]).sum(2)
+    k_orc = (r["hist"] * np.arange(r["hist"].shape[2])[None, None, :]).sum(2)
+    assert np.abs(k_eng - k_orc).max() < 0.15
+    eng.dest_ctqmc()
+
+
+def test_parameter_string_semantics(built):
+    """Parameters.F90 quirks: prefix match on the first hit, commas -> blanks, scientific-notation integers;
+    unsupported sectors fail loudly instead of silently running something else."""
+    p = problems.make_problem("C1", nftau=101)
+    eng = _hostemu.make()
+    eng.init_rnd(1)
+    with pytest.raises(RuntimeError):
+        eng.init_paras(p.pstring(segment=1))
+    with pytest.raises(RuntimeError):
+        eng.init_paras(p.pstring(offdiag=1))
+    eng.init_paras(p.pstring(Nmeas="1e2", NCorr=10))
+    eng.set_option("nchains", 2)
+    eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)
+    with pytest.raises(RuntimeError):
+        eng.ctqmc_measure(2, 1)                     # worm sectors are outside the path
+    eng.ctqmc_measure(1, 1)
+    assert eng.scalar("cnt_steps") == 2 * 100 * 10
+    eng.dest_ctqmc()
+    eng.dest_paras()

@@ -1,0 +1,133 @@
+"""GPU parity tests proper: the CUDA engine, called through the C ABI (include/w2b_cthyb.h) via the mctqmc shim,
+against the CPU oracle on the same seeded inputs.
+  * deterministic replay: integer state bit-exact, per-move determinant / trace ratios within 1e-10 (north_star);
+  * chain state after the replay (inverse matrices) against the oracle's from-scratch LU;
+  * one measurement of an identical configuration adds identical numbers to the accumulators;
+  * statistical agreement of G(tau), occupations, <k>, sign within Monte-Carlo error bars;
+  * size-independent properties at BASELINE sizes (particle-hole symmetry, M * Delta = 1 via LU rebuild)."""
+import numpy as np
+import pytest
+
+from oracle.oracle import OracleChain
+from w2dynamics_b200 import problems
+
+pytestmark = pytest.mark.gpu
+INTS = [0, 1, 4, 5, 6, 8, 10, 12, 13, 14, 15, 16]
+TOL = 1e-10
+
+
+def replay(eng, p, chain, nsteps):
+    log = eng.debug_steps(chain, nsteps)
+    orc = OracleChain(p, rng="philox", seed=43890, chain=chain)
+    orc.init_counters()
+    ref = orc.steps(nsteps, log=True)
+    bad = np.nonzero((log[:, INTS] != ref[:, INTS]).any(1))[0]
+    assert bad.size == 0, "integer state differs first at move %d:\n%s\n%s" % (bad[0], log[bad[0]], ref[bad[0]])
+    assert np.abs(log[:, 7] - ref[:, 7]).max() < TOL, "determinant ratio"
+    assert np.abs(log[:, 9] - ref[:, 9]).max() < TOL, "trace ratio"
+    assert np.array_equal(log[:, [2, 3, 17]], ref[:, [2, 3, 17]])
+    return log, orc
+
+
+@pytest.mark.parametrize("cfg,nsteps,chain", [("C1", 30000, 0), ("C2", 30000, 37), ("C5", 10000, 5)])
+def test_replay_parity(cuda_engine_factory, cfg, nsteps, chain):
+    p = problems.make_problem(cfg)
+    eng = cuda_engine_factory(p, nchains=64, nbins=4)
+    log, orc = replay(eng, p, chain, nsteps)
+    assert set(np.unique(log[:, 0])) == {1.0, 2.0, 3.0, 4.0}
+    s, o = eng.debug_chain_scalars(chain), orc.scalars()
+    assert s["error"] == 0 and orc.error == 0
+    assert abs(s["trace_log"] - o["trace_log"]) < 1e-8 and abs(s["det_log"] - o["det_log"]) < 1e-8
+    assert (s["trace_sign"], s["det_sign"], s["cfgsign"]) == (o["trace_sign"], o["det_sign"], o["cfgsign"])
+    for f in range(2 * p.nbands):
+        a, b, c = eng.debug_minv(chain, f // 2 + 1, f % 2 + 1), orc.minv(f), orc.minv(f, scratch=True)
+        assert a.shape == b.shape
+        if a.size:
+            assert np.abs(a - b).max() < 1e-9 * max(1.0, np.abs(b).max())
+            assert np.abs(a - c).max() < 1e-7 * max(1.0, np.abs(c).max())      # fast updates vs from-scratch LU
+    assert eng.scalar("error_flags") == 0
+    eng.dest_ctqmc()
+
+
+def test_measurement_parity(cuda_engine_factory):
+    p = problems.make_problem("C2", Ntau=200, NLegMax=40)
+    eng = cuda_engine_factory(p, nchains=1, nbins=1)
+    eng.ctqmc_warmup(8000)
+    n, osst, _ = eng.get_mc_config_scalars(0)
+    taus, orbs, spins, cas, hyb, _, _ = eng.get_mc_config(n, 0)
+    orc = OracleChain(p, seed=1, Ntau=200, NLegMax=40)
+    orc.set_config(taus, orbs, spins, cas, osst)
+    eng.block(0, True)
+    eng._ck(eng._load().w2b_finalize())
+    orc.measure(0, reset=True)
+    orc.measure_once()
+    r = orc.results()
+    assert np.abs(eng.gtau - r["gtau"]).max() < 1e-9 * max(1.0, np.abs(r["gtau"]).max())
+    assert np.abs(eng.gleg - r["gleg"]).max() < 1e-9 * max(1.0, np.abs(r["gleg"]).max())
+    assert np.array_equal(eng.histo, r["hist"]) and eng.mean_sign == r["sign"]
+    assert np.abs(eng.occ - r["occ"]).max() < 1e-12 and np.abs(eng.rho1 - r["rho1"]).max() < 1e-12
+    # set_mc_config: LU rebuild on the device reproduces the fast-updated state
+    s = eng.debug_chain_scalars(0)
+    eng.set_mc_config(n, taus, orbs, spins, cas, hyb, osst, 1, chain=0)
+    s2 = eng.debug_chain_scalars(0)
+    assert abs(s2["det_log"] - s["det_log"]) < 1e-8 and s2["cfgsign"] == s["cfgsign"] and s2["error"] == 0
+    eng.dest_ctqmc()
+
+
+def test_statistical_agreement(cuda_engine_factory):
+    """C1 at BASELINE parameters: 2048 chains on the GPU vs one long oracle chain."""
+    p = problems.make_problem("C1", Nmeas=200)
+    eng = cuda_engine_factory(p, nchains=2048, nbins=32)
+    eng.ctqmc_warmup(5000)
+    eng.ctqmc_measure(1, 1)
+    assert eng.scalar("error_flags") == 0
+    orc = OracleChain(p, seed=99)
+    orc.warmup(50000)
+    orc.measure(20000)
+    r = orc.results()
+    bins = eng.bins("gtau")
+    err = bins.std(0, ddof=1) / np.sqrt(bins.shape[0])
+    g = eng.gtau
+    gc, rc, ec = g.reshape(1, 2, 50, 20).mean(3), r["gtau"].reshape(1, 2, 50, 20).mean(3), err.reshape(1, 2, 50, 20).mean(3)
+    # the oracle's own error is ~ sqrt(2048*200/20000) = 4.5x the engine's; allow for it
+    z = (gc - rc) / (5.0 * ec + 1e-4)
+    assert np.abs(z).max() < 5.0, np.abs(z).max()
+    assert eng.mean_sign == r["sign"] == -1.0
+    assert abs(eng.occ[0, 0, 0, 0] - 0.5) < 5e-3 and abs(eng.occ[0, 1, 0, 1] - 0.5) < 5e-3   # half filling (exact by symmetry)
+    assert abs(eng.occ[0, 0, 0, 1] - r["occ"][0, 0, 0, 1]) < 0.02                             # double occupancy
+    assert np.abs(gc[0, 0] - gc[0, 0, ::-1]).max() < 10 * ec.max() + 1e-3                     # G(tau) = G(beta - tau)
+    k_eng = (eng.histo * np.arange(eng.histo.shape[2])[None, None, :]).sum(2)
+    k_orc = (r["hist"] * np.arange(r["hist"].shape[2])[None, None, :]).sum(2)
+    assert np.abs(k_eng - k_orc).max() < 0.1
+    eng.dest_ctqmc()
+
+
+@pytest.mark.parametrize("cfg,nchains", [("C2", 4096), ("C5", 1024)])
+def test_full_size_properties(cuda_engine_factory, cfg, nchains):
+    """BASELINE sizes: no error flags, and for a sample of chains the fast-updated inverse equals the device LU rebuild
+    (idempotence of set_mc_config), det/sign unchanged; particle-hole symmetry of the occupations."""
+    p = problems.make_problem(cfg, Nmeas=20)
+    eng = cuda_engine_factory(p, nchains=nchains, nbins=32)
+    eng.ctqmc_warmup(20000 if cfg == "C2" else 60000)
+    assert eng.scalar("error_flags") == 0
+    for chain in (0, nchains // 2, nchains - 1):
+        s = eng.debug_chain_scalars(chain)
+        n, osst, _ = eng.get_mc_config_scalars(chain)
+        cfgarr = eng.get_mc_config(n, chain)
+        before = [eng.debug_minv(chain, f // 2 + 1, f % 2 + 1) for f in range(2 * p.nbands)]
+        eng.set_mc_config(n, *cfgarr[:5], osst, 1, chain=chain)
+        s2 = eng.debug_chain_scalars(chain)
+        assert s2["error"] == 0 and s2["cfgsign"] == s["cfgsign"]
+        assert abs(s2["det_log"] - s["det_log"]) < 1e-7 * max(1.0, abs(s["det_log"]))
+        assert abs(s2["trace_log"] - s["trace_log"]) < 1e-8 * max(1.0, abs(s["trace_log"]))
+        for f, b in enumerate(before):
+            a = eng.debug_minv(chain, f // 2 + 1, f % 2 + 1)
+            if a.size:
+                assert np.abs(a - b).max() < 1e-6 * max(1.0, np.abs(a).max())
+    eng.ctqmc_measure(1, 1)
+    occ = eng.occ
+    for b in range(p.nbands):
+        for s_ in range(2):
+            assert abs(occ[b, s_, b, s_] - 0.5) < 0.02
+    assert abs(eng.mean_sign) == 1.0 and np.all(np.isfinite(eng.gtau))
+    eng.dest_ctqmc()

@@ -243,6 +243,77 @@ int w2b_block(long long nsweep, int do_measure) {
 }
 int w2b_sync(void) { return guarded([&] { require_engine(); S.eng->sync(); }); }
 
+// bench hook: nblocks x (sweep of nsweep moves per chain [+ one measurement]) timed with CUDA events on the
+// launching stream.  ms[0] = whole region, ms[1] = sum of the sweep kernels, ms[2] = sum of the measurement kernels.
+int w2b_bench_blocks(long long nblocks, long long nsweep, int do_measure, double* ms) {
+    return guarded([&] {
+        require_engine();
+        Engine& E = *S.eng;
+        ms[0] = ms[1] = ms[2] = 0.0;
+#if W2B_DEVICE
+        std::vector<cudaEvent_t> ev((size_t)nblocks * 2 + 1);
+        for (auto& e : ev) W2B_CUDA_CHECK(cudaEventCreate(&e));
+        E.sync();
+        W2B_CUDA_CHECK(cudaEventRecord(ev[0]));
+        for (long long i = 0; i < nblocks; ++i) {
+            E.sweep(nsweep);
+            W2B_CUDA_CHECK(cudaEventRecord(ev[2 * i + 1]));
+            if (do_measure) E.measure();
+            W2B_CUDA_CHECK(cudaEventRecord(ev[2 * i + 2]));
+        }
+        W2B_CUDA_CHECK(cudaEventSynchronize(ev[2 * nblocks]));
+        float t = 0;
+        W2B_CUDA_CHECK(cudaEventElapsedTime(&t, ev[0], ev[2 * nblocks])); ms[0] = t;
+        for (long long i = 0; i < nblocks; ++i) {
+            W2B_CUDA_CHECK(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1])); ms[1] += t;
+            W2B_CUDA_CHECK(cudaEventElapsedTime(&t, ev[2 * i + 1], ev[2 * i + 2])); ms[2] += t;
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+#else
+        double t0 = now();
+        for (long long i = 0; i < nblocks; ++i) { double a = now(); E.sweep(nsweep); double b = now(); if (do_measure) E.measure(); double c = now(); ms[1] += (b - a) * 1e3; ms[2] += (c - b) * 1e3; }
+        ms[0] = (now() - t0) * 1e3;
+#endif
+    });
+}
+
+// end-to-end hooks: new hybridisation function from host memory (what a DMFT iteration hands to init_solver,
+// CTQMC.F90:7950-7955) and the raw accumulator slab back to host memory.
+int w2b_upload_ftau(const double* ftau_full, int nftau) {
+    return guarded([&] {
+        require_engine();
+        Engine& E = *S.eng;
+        if (nftau != E.T.nftau) throw std::runtime_error("w2b_upload_ftau: Nftau differs from init_solver");
+        const int nb = E.T.nb, nf = E.T.nf;
+        std::vector<double>& fd = E.ftau_stage; fd.resize((size_t)nf * nftau);
+        for (int b = 0; b < nb; ++b) for (int s = 0; s < 2; ++s) for (int t = 0; t < nftau; ++t)
+            fd[(size_t)(2 * b + s) * nftau + t] = ftau_full[b + (size_t)nb * (s + 2 * (b + (size_t)nb * (s + 2 * (size_t)t)))];
+        h2d(const_cast<double*>(E.T.ftau), fd.data(), fd.size());
+    });
+}
+int w2b_read_accum(double* out, size_t cap, size_t* n) {
+    return guarded([&] {
+        require_engine();
+        Engine& E = *S.eng;
+        *n = (size_t)E.R.nbins * E.accum_doubles;
+        if (out) d2h(out, E.A.base, std::min(cap, *n));
+    });
+}
+void* w2b_pinned_alloc(size_t bytes) {
+#if W2B_DEVICE
+    void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr; return p;
+#else
+    return std::malloc(bytes);
+#endif
+}
+void w2b_pinned_free(void* p) {
+#if W2B_DEVICE
+    cudaFreeHost(p);
+#else
+    std::free(p);
+#endif
+}
+
 int w2b_accum_device(void** p, size_t* n) {
     return guarded([&] { require_engine(); *p = (void*)S.eng->A.base; *n = (size_t)S.eng->R.nbins * S.eng->accum_doubles; });
 }
@@ -321,6 +392,13 @@ int w2b_get_scalar(const char* name, double* out) {
             if (k == "nslide") { *out = E.R.nslide; return; }
             if (k == "egs") { *out = E.at.egs; return; }
             if (k == "gpu_launches") { *out = (double)E.launches; return; }
+            if (k.rfind("cnt_", 0) == 0) {
+                static const char* names[C_NCNT] = {"try_add", "try_rem", "try_glob", "try_shift", "acc_add", "acc_rem", "acc_glob", "acc_shift",
+                                                    "qn_add", "qn_rem", "qn_glob", "steps", "alg_bytes"};
+                std::vector<unsigned long long> cnt; E.get_counters(cnt);
+                for (int i = 0; i < C_NCNT; ++i) if (k.substr(4) == names[i]) { *out = (double)cnt[i]; return; }
+            }
+            if (k == "mean_order") { *out = E.mean_order(); return; }
             if (k == "max_k" || k == "max_ops" || k == "error_flags") { int mk, mo; int e = E.error_flags(&mk, &mo); *out = k == "max_k" ? mk : k == "max_ops" ? mo : e; return; }
         }
         if (S.have_res) { auto it = S.res.scal.find(k); if (it != S.res.scal.end()) { *out = it->second; return; } }

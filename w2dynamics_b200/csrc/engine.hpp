@@ -118,6 +118,7 @@ public:
     int wdoubles = 0;                  // per-warp scratch in doubles
     long long launches = 0;            // kernels launched (bench accounting)
     std::vector<void*> owned;
+    std::vector<double> ftau_stage;    // host staging of the diagonal hybridisation (w2b_upload_ftau)
 
     ~Engine() { release(); }
 
@@ -323,6 +324,13 @@ public:
         if (max_k) *max_k = mk;
         if (max_ops) *max_ops = mo;
         return e;
+    }
+    double mean_order() {                       // <k_f> averaged over chains and flavours
+        sync();
+        std::vector<int> ih((size_t)C.nchains * IH_STRIDE);
+        d2h(ih.data(), C.ih, ih.size());
+        double s = 0; for (int c = 0; c < C.nchains; ++c) for (int f = 0; f < T.nf; ++f) s += ih[(size_t)c * IH_STRIDE + IH_KF + f];
+        return s / ((double)C.nchains * T.nf);
     }
     void download_accum(std::vector<double>& out, std::vector<unsigned long long>& accpair) {
         sync();

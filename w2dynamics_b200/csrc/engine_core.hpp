@@ -31,7 +31,7 @@ namespace w2b {
 
 constexpr int LOGW = 20;      // doubles per replay-log record (same layout as oracle/chain.cpp)
 constexpr int NF_MAX = 14;
-enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_NCNT };
+enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_ALGBYTES, C_NCNT };
 enum { IH_NOPS = 0, IH_OUTER, IH_WPOS, IH_NPAIRS, IH_PERM, IH_PALT, IH_ERR, IH_PAD, IH_KF = 8, IH_MSLOT = IH_KF + NF_MAX, IH_STRIDE = IH_MSLOT + NF_MAX + 2 };
 enum { DH_DETLOG = 0, DH_DETSIGN, DH_TRLOG, DH_TRSIGN, DH_CFGSIGN, DH_STRIDE = 8 };
 enum { ERR_CAPACITY = 1, ERR_DETRAT_SMALL = 2, ERR_PAIR_LOGIC = 4, ERR_GLOBAL_QN = 8, ERR_SINGULAR = 16 };
@@ -346,6 +346,8 @@ W2B_HD void log_end(Ctx& x, int status) {
     if (x.log && x.lane == 0) { x.log[1] = status; x.log[12] = x.n; x.log[13] = x.outer; x.log[15] = x.cfgsign; }
 }
 W2B_HD void bump(Ctx& x, int c) { if (x.lane == 0) x.cnt[c] += 1ull; }
+// algorithmic bytes of the determinant path (definition in DESIGN.md "Roofline accounting")
+W2B_HD void bump_bytes(Ctx& x, long long b) { if (x.lane == 0) x.cnt[C_ALGBYTES] += (unsigned long long)b; }
 
 // ------------------------------------------------------------------ StepAdd (CTQMC.F90:3353-3612, change_outer = false)
 W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x) {
@@ -371,6 +373,7 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     const int p1 = count_lt(tc, k, tau_c), p2 = count_lt(ta, k, tau_a);              // FPos-1 (creator row, annihilator column)
     log_set(x, 5, p1 + 1); log_set(x, 6, p2 + 1);
+    bump_bytes(x, 64ll * k);
     // quantum-number check of the changed sub-string + scalar trace ratio
     const int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
     double dlog = 0.0, dsign = 1.0;
@@ -390,6 +393,7 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
     if (new_end < 0 || new_end != old_after) { bump(x, C_QNADD); log_end(x, 2); return; }
     // determinant ratio
     const double S = det_ratio_add(T, C, x, f, tau_c, tau_a);
+    bump_bytes(x, 8ll * k * k);
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
     const double dr_log = log(fabs(S)), dr_sign = sgn1(S) * sig;
     const double rand = x.rng.next();
@@ -402,6 +406,7 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
     if (!(rand < prob)) { log_end(x, 0); return; }
     if (k + 1 > C.kcap || x.n + 2 > C.ops_cap) { x.err |= ERR_CAPACITY; log_end(x, 0); return; }
     // ---- accept
+    bump_bytes(x, 8ll * (k * k + (k + 1) * (k + 1)));
     mat_add(C, x, f, T.nf, p1, p2, S);
     shift_up(x.tc + (size_t)f * C.kcap, p1, k, 1); shift_up(x.ta + (size_t)f * C.kcap, p2, k, 1);
     if (x.lane == 0) { x.tc[(size_t)f * C.kcap + p1] = tau_c; x.ta[(size_t)f * C.kcap + p2] = tau_a; }
@@ -469,6 +474,7 @@ W2B_HDN void step_rem(const Tables& T, const Run& R, const Chains& C, const Accu
     const int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     const double t2 = (type1 == 0 ? ta : tc)[midx];
+    bump_bytes(x, 64ll * k);
     const int pE = count_lt(type1 == 0 ? tc : ta, k, t1);
     const int p1 = type1 == 0 ? pE : midx, p2 = type1 == 0 ? midx : pE;
     const double tau_an = type1 == 1 ? t1 : t2;
@@ -498,6 +504,7 @@ W2B_HDN void step_rem(const Tables& T, const Run& R, const Chains& C, const Accu
     if (fabs(S) < 1e-12) x.err |= ERR_DETRAT_SMALL;                    // CTQMC.F90:4062 `stop`
     // ---- accept
     const int np_new = x.npairs - (pairs_with(R, x, type1 == 0 ? ta : tc, k, t1) + pairs_with(R, x, type1 == 0 ? tc : ta, k, t2) - (pairable(R, x, t1, t2) ? 1 : 0));
+    bump_bytes(x, 8ll * (k * k + (k - 1) * (k - 1)));
     mat_rem(C, x, f, T.nf, p1, p2);
     shift_down(x.tc + (size_t)f * C.kcap, p1, k, 1); shift_down(x.ta + (size_t)f * C.kcap, p2, k, 1);
     shift_down(x.tau, i1, i2, 1); shift_down(x.code, i1, i2, 1); shift_down(x.sst, i1, i2, 1);
@@ -673,6 +680,8 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
         }
     }
     if (factor == 0.0) { bump(x, C_QNGLOB); log_end(x, 2); return; }
+    long long sumk2 = 0; for (int f = 0; f < nf; ++f) sumk2 += (long long)x.ih[IH_KF + f] * x.ih[IH_KF + f];
+    bump_bytes(x, 24ll * sumk2);                  // build Delta_new (write), read the stored inverses, write their LU copy
     // relabelled flavour tau arrays and orders
     int* knew = x.wI + C.kcap + 16;
     for (int f = 0; f < nf; ++f) {
@@ -704,6 +713,7 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 17, rand);
     if (!(rand < prob)) { log_end(x, 0); return; }
     // ---- accept
+    bump_bytes(x, 8ll * sumk2);
     for (int i = x.lane; i < x.n; i += W2B_WARP) { x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
     for (int f = 0; f < nf; ++f) {
         int k = knew[f];
@@ -769,6 +779,7 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
         const int w1 = count_lt(tc, k, dt), w2 = count_lt(ta, k, dt);
         if (!((w1 == 0 && w2 == 0) || (w1 == k && w2 == k))) {
             const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, T.nf);
+            bump_bytes(x, 16ll * k * k);
             for (int i = 0; i < k; ++i) {
                 int in = i - w1; double si = 1.0; if (in < 0) { in += k; si = -1.0; }
                 for (int j = x.lane; j < k; j += W2B_WARP) {
