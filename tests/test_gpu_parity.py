@@ -11,9 +11,9 @@ import pytest
 from oracle.oracle import OracleChain
 from w2dynamics_b200 import problems
 
+from _parity import assert_replay
+
 pytestmark = pytest.mark.gpu
-INTS = [0, 1, 4, 5, 6, 8, 10, 12, 13, 14, 15, 16]
-TOL = 1e-10
 
 
 def replay(eng, p, chain, nsteps):
@@ -21,15 +21,11 @@ def replay(eng, p, chain, nsteps):
     orc = OracleChain(p, rng="philox", seed=43890, chain=chain)
     orc.init_counters()
     ref = orc.steps(nsteps, log=True)
-    bad = np.nonzero((log[:, INTS] != ref[:, INTS]).any(1))[0]
-    assert bad.size == 0, "integer state differs first at move %d:\n%s\n%s" % (bad[0], log[bad[0]], ref[bad[0]])
-    assert np.abs(log[:, 7] - ref[:, 7]).max() < TOL, "determinant ratio"
-    assert np.abs(log[:, 9] - ref[:, 9]).max() < TOL, "trace ratio"
-    assert np.array_equal(log[:, [2, 3, 17]], ref[:, [2, 3, 17]])
+    assert_replay(log, ref)
     return log, orc
 
 
-@pytest.mark.parametrize("cfg,nsteps,chain", [("C1", 30000, 0), ("C2", 30000, 37), ("C5", 10000, 5)])
+@pytest.mark.parametrize("cfg,nsteps,chain", [("C1", 30000, 0), ("C2", 30000, 37), ("C5", 10000, 5), ("C3", 30000, 11), ("C4", 30000, 63)])
 def test_replay_parity(cuda_engine_factory, cfg, nsteps, chain):
     p = problems.make_problem(cfg)
     eng = cuda_engine_factory(p, nchains=64, nbins=4)
@@ -130,4 +126,59 @@ def test_full_size_properties(cuda_engine_factory, cfg, nchains):
         for s_ in range(2):
             assert abs(occ[b, s_, b, s_] - 0.5) < 0.02
     assert abs(eng.mean_sign) == 1.0 and np.all(np.isfinite(eng.gtau))
+    eng.dest_ctqmc()
+
+
+@pytest.mark.parametrize("cfg", ["C3", "C4"])
+def test_blocked_trace_measurement(cuda_engine_factory, cfg):
+    """d > 1 blocks on the GPU: cached ket/bra trace == from-scratch oracle trace; density matrix / histograms / G(tau) of
+    identical configurations equal the oracle's."""
+    p = problems.make_problem(cfg, Ntau=100, NLegMax=20)
+    eng = cuda_engine_factory(p, nchains=1, nbins=1)
+    orc = OracleChain(p, seed=1, Ntau=100, NLegMax=20)
+    orc.measure(0, reset=True)
+    for _ in range(30):
+        eng.ctqmc_warmup(400)
+        n, osst, _ = eng.get_mc_config_scalars(0)
+        taus, orbs, spins, cas, hyb, _, _ = eng.get_mc_config(n, 0)
+        orc.set_config(taus, orbs, spins, cas, osst)
+        s, o = eng.debug_chain_scalars(0), orc.scalars()
+        assert abs(s["trace_log"] - o["trace_log"]) < 1e-9 and s["trace_sign"] == o["trace_sign"] and s["cfgsign"] == o["cfgsign"]
+        eng.block(0, True)
+        orc.measure_once()
+    eng._ck(eng._load().w2b_finalize())
+    r = orc.results()
+    for a, b in ((eng.gtau, r["gtau"]), (eng.gleg, r["gleg"]), (eng.occ, r["occ"]), (eng.rho1, r["rho1"]),
+                 (eng.densitymatrix, r["densitymatrix"]), (eng.outerstatehisto, r["hist-state"]),
+                 (eng.tracecontribstates, r["contrib-state"]), (eng.tracecontribsuperstates, r["contrib-sst"])):
+        assert np.abs(a - b).max() < 1e-9 * max(1e-3, np.abs(b).max())
+    assert np.array_equal(eng.histo, r["hist"]) and eng.mean_sign == r["sign"]
+    assert eng.scalar("error_flags") == 0
+    eng.dest_ctqmc()
+
+
+@pytest.mark.parametrize("cfg,nchains", [("C3", 2048), ("C4", 1024)])
+def test_blocked_full_size(cuda_engine_factory, cfg, nchains):
+    """BASELINE sizes of the blocked-trace configs: no error flags; cached trace == device from-scratch rebuild
+    (set_mc_config idempotence); particle-hole symmetric occupations; density matrix has unit trace."""
+    p = problems.make_problem(cfg, Nmeas=20)
+    eng = cuda_engine_factory(p, nchains=nchains, nbins=32)
+    eng.ctqmc_warmup(8000)
+    assert eng.scalar("error_flags") == 0
+    for chain in (0, nchains // 3, nchains - 1):
+        s = eng.debug_chain_scalars(chain)
+        n, osst, _ = eng.get_mc_config_scalars(chain)
+        cfgarr = eng.get_mc_config(n, chain)
+        eng.set_mc_config(n, *cfgarr[:5], osst, 1, chain=chain)
+        s2 = eng.debug_chain_scalars(chain)
+        assert s2["error"] == 0 and s2["cfgsign"] == s["cfgsign"] and s2["trace_sign"] == s["trace_sign"]
+        assert abs(s2["trace_log"] - s["trace_log"]) < 1e-9 * max(1.0, abs(s["trace_log"]))
+        assert abs(s2["det_log"] - s["det_log"]) < 1e-7 * max(1.0, abs(s["det_log"]))
+    eng.ctqmc_measure(1, 1)
+    occ = eng.occ
+    for b in range(p.nbands):
+        for s_ in range(2):
+            assert abs(occ[b, s_, b, s_] - 0.5) < 0.03
+    assert abs(np.trace(eng.densitymatrix) - 1.0) < 1e-9 and abs(eng.mean_sign) == 1.0
+    assert eng.scalar("error_flags") == 0
     eng.dest_ctqmc()

@@ -14,6 +14,7 @@ p = problems.make_problem(cfg)
 for nc in chains:
     eng = MCTQMC()
     eng.set_option("nchains", nc); eng.set_option("nbins", 32)
+    if os.environ.get("W2B_SAME_KEY"): eng.set_option("debug_same_key", 1)
     eng.init_rnd(43890); eng.init_paras(p.pstring())
     t0 = time.time()
     eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)

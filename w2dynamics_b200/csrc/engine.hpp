@@ -70,6 +70,11 @@ template <class T_> T_* dev_upload(const std::vector<T_>& v) { T_* d = dev_alloc
 
 // ---------------------------------------------------------------- kernels
 constexpr int WARPS_PER_CTA = 4;
+// per-warp work space of the blocked trace in doubles: two d x m matrices, column log scales, per-state trace parts
+#if W2B_DEVICE
+__host__ __device__
+#endif
+inline int mat_doubles(const Chains& C) { return C.dmax > 1 ? 2 * C.mstride + 3 * C.dmax : 0; }
 
 #if W2B_DEVICE
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_init(Tables T, Run R, Chains C) {
@@ -83,12 +88,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_sweep(Tables T, Run R, C
     int chain = blockIdx.x * WARPS_PER_CTA + warp;
     if (chain >= C.nchains) return;
     double* ws = smem + (size_t)warp * wdoubles;
-    int* is = (int*)(ws + 3 * C.kcap);
-    sweep_chain(T, R, C, A, chain, nsteps, ws, is, chain == log_chain ? logbuf : nullptr);
+    int* is = (int*)(ws + 3 * C.kcap + mat_doubles(C));
+    sweep_chain(T, R, C, A, chain, nsteps, ws, is, ws + 3 * C.kcap, chain == log_chain ? logbuf : nullptr);
 }
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_measure(Tables T, Run R, Chains C, Accum A) {
-    int chain = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (chain < C.nchains) measure_chain(T, R, C, A, chain);
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_measure(Tables T, Run R, Chains C, Accum A, int wdoubles) {
+    extern __shared__ double smem[];
+    int warp = threadIdx.x >> 5;
+    int chain = blockIdx.x * WARPS_PER_CTA + warp;
+    if (chain >= C.nchains) return;
+    double* ws = smem + (size_t)warp * wdoubles;
+    int* is = (int*)(ws + 3 * C.kcap + mat_doubles(C));
+    measure_chain(T, R, C, A, chain, ws, is, ws + 3 * C.kcap);
 }
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R, Chains C, int wdoubles, int only_chain) {
     extern __shared__ double smem[];
@@ -96,8 +106,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R,
     int chain = blockIdx.x * WARPS_PER_CTA + warp;
     if (chain >= C.nchains || (only_chain >= 0 && chain != only_chain)) return;
     double* ws = smem + (size_t)warp * wdoubles;
-    int* is = (int*)(ws + 3 * C.kcap);
-    rebuild_chain(T, R, C, chain, ws, is);
+    int* is = (int*)(ws + 3 * C.kcap + mat_doubles(C));
+    rebuild_chain(T, R, C, chain, ws, is, ws + 3 * C.kcap);
 }
 #endif
 
@@ -118,6 +128,7 @@ public:
     int wdoubles = 0;                  // per-warp scratch in doubles
     long long launches = 0;            // kernels launched (bench accounting)
     std::vector<void*> owned;
+    std::vector<int> dens_off;         // per block: offset of its d x d slab in the density accumulator
     std::vector<double> ftau_stage;    // host staging of the diagonal hybridisation (w2b_upload_ftau)
 
     ~Engine() { release(); }
@@ -140,7 +151,6 @@ public:
         release();
         at = tables; opt = options; R = run;
         if (at.nf > NF_MAX) throw std::runtime_error("too many flavours for this build (NF_MAX)");
-        if (at.dmax > 1) throw std::runtime_error("blocks larger than 1x1 are not supported by the scalar-trace engine yet");
         const int nf = at.nf, nsst = at.nsst;
         T.nb = at.nb; T.nf = nf; T.nsst = nsst; T.nops = at.nops; T.dmax = at.dmax; T.nftau = nftau; T.nstates = at.nstates;
         T.beta = beta; T.egs = at.egs;
@@ -159,6 +169,10 @@ public:
         T.ftau = keep(dev_upload(ftau_diag));
         T.first_state = keep(dev_upload(at.first_state)); T.state2sst = keep(dev_upload(at.state2sst));
         T.dim = keep(dev_upload(at.dim)); T.offset = keep(dev_upload(at.offset));
+        std::vector<int> doff(nsst); int dsum = 0;
+        for (int k = 0; k < nsst; ++k) { doff[k] = dsum; dsum += at.dim[k] * at.dim[k]; }
+        dens_off = doff;
+        T.dens_off = keep(dev_upload(doff));
         T.empty_w = keep(dev_upload(ew)); T.empty_log = keep(dev_upload(el));
         T.op_off = keep(dev_upload(at.op_off)); T.opdata = keep(dev_upload(at.opdata)); T.evals = keep(dev_upload(at.evals));
 
@@ -166,9 +180,14 @@ public:
         int kcap = opt.kcap;
         if (kcap <= 0) { double kd = 0.45 * beta; kcap = (int)(kd + 6.0 * std::sqrt(kd) + 16.0); }
         kcap = ((kcap + 15) / 16) * 16;
-        int ops_cap = opt.ops_cap > 0 ? opt.ops_cap : 2 * nf * kcap;
+        int ops_cap = opt.ops_cap;
+        if (ops_cap <= 0) {                      // 2 * (<n_pairs> + 8 sigma + 32); blocked traces keep one cache slot per operator
+            double np = nf * 0.45 * beta; ops_cap = (int)(2.0 * (np + 8.0 * std::sqrt(np) + 32.0));
+            if (at.dmax > 1 && ops_cap > 256) ops_cap = 256;
+        }
         if (ops_cap > 2 * nf * kcap) ops_cap = 2 * nf * kcap;
         ops_cap = ((ops_cap + 31) / 32) * 32;
+        if (ops_cap > 4096) throw std::runtime_error("ops_cap > 4096 not supported (16-bit cache slot ids)");
         const int nc = opt.nchains;
         C.nchains = nc; C.ops_cap = ops_cap; C.kcap = kcap; C.ld = kcap;
         C.op_tau = keep(dev_alloc<double>((size_t)nc * ops_cap)); C.op_code = keep(dev_alloc<unsigned char>((size_t)nc * ops_cap));
@@ -180,13 +199,20 @@ public:
         C.M = keep(dev_alloc<double>((size_t)nc * (nf + 1) * kcap * kcap));
         C.ih = keep(dev_alloc<int>((size_t)nc * IH_STRIDE)); C.dh = keep(dev_alloc<double>((size_t)nc * DH_STRIDE));
         C.rng_ctr = keep(dev_alloc<unsigned long long>(nc)); C.counters = keep(dev_alloc<unsigned long long>((size_t)nc * C_NCNT));
+        C.dmax = at.dmax; C.mstride = at.dmax > 1 ? at.dmax * at.dmax : 0;
+        if (at.dmax > 1) {
+            C.op_slot = keep(dev_alloc<unsigned short>((size_t)nc * ops_cap)); C.free_slot = keep(dev_alloc<unsigned short>((size_t)nc * ops_cap));
+            C.ket = keep(dev_alloc<double>((size_t)nc * ops_cap * C.mstride)); C.bra = keep(dev_alloc<double>((size_t)nc * ops_cap * C.mstride));
+            C.ketlg = keep(dev_alloc<double>((size_t)nc * ops_cap * C.dmax)); C.bralg = keep(dev_alloc<double>((size_t)nc * ops_cap * C.dmax));
+            C.pt = keep(dev_alloc<double>((size_t)nc * 2 * C.dmax));
+        }
         int wints = kcap + 32 + nsst;
-        wdoubles = 3 * kcap + (wints + 1) / 2;
+        wdoubles = 3 * kcap + mat_doubles(C) + (wints + 1) / 2;
 
         // accumulators
         int o = 0;
         A.o_gtau = o; o += nf * R.ntau; A.o_gleg = o; o += nf * R.nlegmax; A.o_histo = o; o += nf * (R.maxhisto + 1);
-        A.ndens = at.nstates; A.o_dens = o; o += A.ndens;
+        A.ndens = dsum; A.o_dens = o; o += A.ndens;
         A.o_outer = o; o += nsst; A.o_signsst = o; o += nsst; A.o_contribsst = o; o += nsst;
         A.o_outerst = o; o += at.nstates; A.o_signst = o; o += at.nstates; A.o_contribst = o; o += at.nstates;
         A.o_sign = o; o += 1; A.o_cnt = o; o += 1;
@@ -243,17 +269,21 @@ public:
 #else
         std::vector<double> ws(wdoubles + 8);
         for (int c = 0; c < C.nchains; ++c)
-            sweep_chain(T, R, C, A, c, nsteps, ws.data(), (int*)(ws.data() + 3 * C.kcap), c == log_chain ? dlog : nullptr);
+            sweep_chain(T, R, C, A, c, nsteps, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C)), ws.data() + 3 * C.kcap, c == log_chain ? dlog : nullptr);
 #endif
         if (log_chain >= 0) { sync(); d2h(log_host, dlog, (size_t)nsteps * LOGW); dev_free(dlog); }
     }
 
     void measure() {
 #if W2B_DEVICE
-        k_measure<<<grid(), WARPS_PER_CTA * 32>>>(T, R, C, A); ++launches;
+        size_t sm = smem_bytes();
+        static size_t configured = 0;
+        if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_measure, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+        k_measure<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, A, wdoubles); ++launches;
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
-        for (int c = 0; c < C.nchains; ++c) measure_chain(T, R, C, A, c);
+        std::vector<double> ws(wdoubles + 8);
+        for (int c = 0; c < C.nchains; ++c) measure_chain(T, R, C, A, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C)), ws.data() + 3 * C.kcap);
 #endif
     }
 
@@ -266,7 +296,7 @@ public:
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
         std::vector<double> ws(wdoubles + 8);
-        for (int c = 0; c < C.nchains; ++c) if (only_chain < 0 || c == only_chain) rebuild_chain(T, R, C, c, ws.data(), (int*)(ws.data() + 3 * C.kcap));
+        for (int c = 0; c < C.nchains; ++c) if (only_chain < 0 || c == only_chain) rebuild_chain(T, R, C, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C)), ws.data() + 3 * C.kcap);
 #endif
     }
 

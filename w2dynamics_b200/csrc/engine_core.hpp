@@ -26,13 +26,14 @@
 //   * counter-based RNG (Philox4x32-10) consumed in the reference's draw order.
 #pragma once
 #include "warp.hpp"
+#include "trace_matrix.hpp"
 
 namespace w2b {
 
 constexpr int LOGW = 20;      // doubles per replay-log record (same layout as oracle/chain.cpp)
 constexpr int NF_MAX = 14;
 enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_ALGBYTES, C_NCNT };
-enum { IH_NOPS = 0, IH_OUTER, IH_WPOS, IH_NPAIRS, IH_PERM, IH_PALT, IH_ERR, IH_PAD, IH_KF = 8, IH_MSLOT = IH_KF + NF_MAX, IH_STRIDE = IH_MSLOT + NF_MAX + 2 };
+enum { IH_NOPS = 0, IH_OUTER, IH_WPOS, IH_NPAIRS, IH_PERM, IH_PALT, IH_ERR, IH_KV, IH_KF = 8, IH_MSLOT = IH_KF + NF_MAX, IH_BV = IH_MSLOT + NF_MAX + 1, IH_NFREE, IH_STRIDE };
 enum { DH_DETLOG = 0, DH_DETSIGN, DH_TRLOG, DH_TRSIGN, DH_CFGSIGN, DH_STRIDE = 8 };
 enum { ERR_CAPACITY = 1, ERR_DETRAT_SMALL = 2, ERR_PAIR_LOGIC = 4, ERR_GLOBAL_QN = 8, ERR_SINGULAR = 16 };
 
@@ -48,6 +49,7 @@ struct Tables {
     const int* state2sst;        // [nstates]
     const int* dim;              // [nsst]
     const int* offset;           // [nsst]
+    const int* dens_off;         // [nsst] offset of the block's d x d slab inside the density-matrix accumulator
     const double* empty_w;       // [nsst] normalised empty-trace weights (init_Trace / StepChangeOuter)
     const double* empty_log;     // [nsst] log of the empty trace of each outer superstate
     const long long* op_off;     // matrix path
@@ -59,6 +61,7 @@ struct Run {
     double taudiff_max, pglob, pshift, p4op, pouter;
     int num_windows, nslide, ntau, nlegmax, maxhisto, has_szt, nbins, meas_dm;
     unsigned seed, chain_base;
+    int same_key;                // diagnostics only: every chain uses chain 0's RNG key (identical control flow across warps)
 };
 
 struct Chains {
@@ -70,6 +73,12 @@ struct Chains {
     unsigned long long* rng_ctr; unsigned long long* counters;
     double* sc_tau; unsigned char* sc_code; short* sc_sst;     // per-chain scratch (global / tau-shift moves)
     double* sc_tc; double* sc_ta;                              // [chain][nf][kcap]
+    // blocked-trace caches (dmax > 1 only): slot ids per operator, free-slot stack, ket / bra matrices + column log scales
+    unsigned short* op_slot; unsigned short* free_slot;        // [chain][ops_cap]
+    double* ket; double* bra;                                  // [chain][ops_cap][mstride]   (compact d x m, column-major)
+    double* ketlg; double* bralg;                              // [chain][ops_cap][dmax]
+    double* pt;                                                // [chain][2*dmax] (log, sign) of every outer state's trace contribution
+    int mstride, dmax;
 };
 
 // accumulators (device), one slab per bin; offsets in doubles
@@ -85,6 +94,9 @@ struct Ctx {
     unsigned long long* cnt;
     double* sc_tau; unsigned char* sc_code; short* sc_sst; double* sc_tc; double* sc_ta;
     double* wQ; double* wR; double* wV; int* wI;
+    unsigned short* slot; unsigned short* freel; double* ket; double* bra; double* ketlg; double* bralg; double* pt;
+    double* mX; double* mY; double* mlg; double* mpt;      // per-warp work space of the blocked trace
+    int kv, bv, nfree;
     int n, outer, wpos, npairs, perm, palt, err;
     double det_log, det_sign, tr_log, tr_sign, cfgsign, wmin, wmax;
     Philox rng;
@@ -259,6 +271,131 @@ W2B_HD void update_cfgsign(const Tables& T, Ctx& x) {
     x.cfgsign = -s;                                         // CTQMC.F90:3574
 }
 
+// ------------------------------------------------------------------ blocked local trace (dmax > 1): cache frontiers
+// (design notes in trace_matrix.hpp; reference get_Trace_EB Trace.F90:5354-6033, update_trace_EB 6109-6209)
+W2B_HD int sst_before(const Ctx& x, int i) { return i == 0 ? x.outer : (int)x.sst[i - 1]; }
+W2B_HD double* ket_slot(const Chains& C, const Ctx& x, int i) { return x.ket + (size_t)x.slot[i] * C.mstride; }
+W2B_HD double* bra_slot(const Chains& C, const Ctx& x, int i) { return x.bra + (size_t)x.slot[i] * C.mstride; }
+
+// all cache slots back to "operator i owns slot i", nothing valid
+W2B_HD void slots_reset(const Chains& C, Ctx& x) {
+    for (int i = x.lane; i < C.ops_cap; i += W2B_WARP) { x.slot[i] = (unsigned short)i; x.freel[i] = (unsigned short)(C.ops_cap - 1 - i); }
+    x.nfree = C.ops_cap - x.n; x.kv = 0; x.bv = x.n;
+    wsync();
+}
+
+// make KET_i valid for all i <= upto
+W2B_HDN void extend_kets(const Tables& T, const Chains& C, Ctx& x, int upto) {
+    if (x.kv > upto) return;
+    const int m = ldg(&T.dim[x.outer]);
+    int i = x.kv, sst; double tprev;
+    double* X = x.mX; double* Y = x.mY;
+    if (i == 0) { mat_identity(X, x.mlg, m); sst = x.outer; tprev = 0.0; }
+    else {
+        sst = (int)x.sst[i - 1]; tprev = x.tau[i - 1];
+        mat_copy(X, ket_slot(C, x, i - 1), ldg(&T.dim[sst]) * m);
+        mat_copy(x.mlg, x.ketlg + (size_t)x.slot[i - 1] * C.dmax, m);
+        wsync();
+    }
+    for (; i <= upto; ++i) {
+        sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, Y, x.mlg, m);
+        mat_copy(ket_slot(C, x, i), Y, ldg(&T.dim[sst]) * m);
+        mat_copy(x.ketlg + (size_t)x.slot[i] * C.dmax, x.mlg, m);
+        tprev = x.tau[i];
+        double* t = X; X = Y; Y = t;
+    }
+    wsync();
+    x.kv = upto + 1;
+}
+
+// make BRA_i valid for all i >= downto
+W2B_HDN void extend_bras(const Tables& T, const Chains& C, Ctx& x, int downto) {
+    if (x.bv <= downto) return;
+    const int m = ldg(&T.dim[x.outer]);
+    int i = x.bv; double tnext;
+    double* X = x.mX; double* Y = x.mY;
+    if (i == x.n) { mat_identity(X, x.mlg, m); tnext = T.beta; }
+    else {
+        tnext = x.tau[i];
+        mat_copy(X, bra_slot(C, x, i), ldg(&T.dim[sst_before(x, i)]) * m);
+        mat_copy(x.mlg, x.bralg + (size_t)x.slot[i] * C.dmax, m);
+        wsync();
+    }
+    for (i = x.bv - 1; i >= downto; --i) {          // BRA_i = O_i^T P(tau_{i+1} - tau_i) BRA_{i+1}
+        const int sb = mat_apply(T, (int)x.sst[i], (int)x.code[i] ^ 1, tnext - x.tau[i], X, Y, x.mlg, m);
+        mat_copy(bra_slot(C, x, i), Y, ldg(&T.dim[sb]) * m);
+        mat_copy(x.bralg + (size_t)x.slot[i] * C.dmax, x.mlg, m);
+        tnext = x.tau[i];
+        double* t = X; X = Y; Y = t;
+    }
+    wsync();
+    x.bv = downto;
+}
+
+// Trace of the configuration that keeps operators [0, s) and [e, n) and has, in between: optional new operator A,
+// the old operators [lo, hi), optional new operator B.  Parts of every outer state go to x.mpt.
+W2B_HDN void seg_trace(const Tables& T, const Chains& C, Ctx& x, int s, int e, bool hasA, double tA, int codeA, int lo, int hi,
+                       bool hasB, double tB, int codeB, double& tlog, double& tsign) {
+    extend_kets(T, C, x, s - 1);
+    extend_bras(T, C, x, e);
+    const int m = ldg(&T.dim[x.outer]);
+    double* X = x.mX; double* Y = x.mY;
+    int sst; double tprev;
+    if (s == 0) { mat_identity(X, x.mlg, m); sst = x.outer; tprev = 0.0; }
+    else {
+        sst = (int)x.sst[s - 1]; tprev = x.tau[s - 1];
+        mat_copy(X, ket_slot(C, x, s - 1), ldg(&T.dim[sst]) * m);
+        mat_copy(x.mlg, x.ketlg + (size_t)x.slot[s - 1] * C.dmax, m);
+        wsync();
+    }
+    if (hasA) { sst = mat_apply(T, sst, codeA, tA - tprev, X, Y, x.mlg, m); tprev = tA; double* t = X; X = Y; Y = t; }
+    for (int i = lo; i < hi; ++i) {
+        sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, Y, x.mlg, m); tprev = x.tau[i];
+        double* t = X; X = Y; Y = t;
+    }
+    if (hasB) { sst = mat_apply(T, sst, codeB, tB - tprev, X, Y, x.mlg, m); tprev = tB; double* t = X; X = Y; Y = t; }
+    if (e == x.n) mat_close(T, sst, T.beta - tprev, X, x.mlg, (const double*)nullptr, (const double*)nullptr, m, x.mpt, tlog, tsign);
+    else mat_close(T, sst, x.tau[e] - tprev, X, x.mlg, bra_slot(C, x, e), x.bralg + (size_t)x.slot[e] * C.dmax, m, x.mpt, tlog, tsign);
+}
+
+// from-scratch trace of an arbitrary sequence (global moves, tau shifts, set_mc_config); no caches touched
+W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsigned char* code, int n, int outer, double& tlog, double& tsign) {
+    const int m = ldg(&T.dim[outer]);
+    double* X = x.mX; double* Y = x.mY;
+    mat_identity(X, x.mlg, m);
+    int sst = outer; double tprev = 0.0;
+    for (int i = 0; i < n; ++i) {
+        sst = mat_apply(T, sst, (int)code[i], tau[i] - tprev, X, Y, x.mlg, m); tprev = tau[i];
+        double* t = X; X = Y; Y = t;
+    }
+    mat_close(T, sst, T.beta - tprev, X, x.mlg, (const double*)nullptr, (const double*)nullptr, m, x.mpt, tlog, tsign);
+}
+// trace contributions of the outer states of an empty configuration: exp(-(E_j - Egs) beta)
+W2B_HD void empty_parts(const Tables& T, Ctx& x, int outer) {
+    const int m = ldg(&T.dim[outer]);
+    const double* ev = T.evals + ldg(&T.offset[outer]);
+    for (int j = x.lane; j < m; j += W2B_WARP) { x.pt[2 * j] = -(ldg(&ev[j]) - T.egs) * T.beta; x.pt[2 * j + 1] = 1.0; }
+    wsync();
+}
+W2B_HD void commit_parts(const Tables& T, Ctx& x) {
+    const int m = ldg(&T.dim[x.outer]);
+    for (int j = x.lane; j < 2 * m; j += W2B_WARP) x.pt[j] = x.mpt[j];
+}
+
+// integer superstate walk over the old operators [i0, i0+mcount) starting from `cur`; counts operators of another flavour
+W2B_HD int walk_check(const Tables& T, const Ctx& x, int i0, int mcount, int f, int cur, int& nother) {
+    int oth = 0;
+    for (int base = 0; base < mcount; base += W2B_WARP) {
+        int j = base + lane_id(); bool act = j < mcount;
+        int cj = act ? (int)x.code[i0 + j] : 0;
+        int cnt = mcount - base < W2B_WARP ? mcount - base : W2B_WARP;
+        for (int q = 0; q < cnt; ++q) { int cq = wbcast(cj, q); cur = cur >= 0 ? conn(T, cur, cq) : -1; }
+        if (act) oth += ((cj >> 1) != f);
+    }
+    nother = wsum(oth);
+    return cur;
+}
+
 // ------------------------------------------------------------------ determinant ratio + rank-1 updates
 // S - R^T M Q (MatrixUpdate.F90:392-407); leaves Q, R, V = R^T M in the warp scratch for the update
 W2B_HDN double det_ratio_add(const Tables& T, const Chains& C, Ctx& x, int f, double tau_c, double tau_a) {
@@ -354,13 +491,13 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
     log_begin(x, 1);
     bump(x, C_TRYADD);
     const double W = x.wmax - x.wmin;
-    const double tau_a = x.wmin + W * x.rng.next();                    // pair_OperAdd Trace.F90:3672-3695
+    const double tau_a = add_rn(x.wmin, mul_rn(W, x.rng.next()));                    // pair_OperAdd Trace.F90:3672-3695
     const int b = x.rng.randint(1, T.nb) - 1;
     const int s = x.rng.randint(1, 2) - 1;
     const double tmin = fmax(tau_a - R.taudiff_max, x.wmin);
     const double w2 = fmin(tau_a + R.taudiff_max, x.wmax) - tmin;
-    const double tau_c = tmin + w2 * x.rng.next();
-    const double taudiff_factor = W * w2;
+    const double tau_c = add_rn(tmin, mul_rn(w2, x.rng.next()));
+    const double taudiff_factor = mul_rn(W, w2);
     const int f = b * 2 + s;
     const bool a_first = tau_a < tau_c;
     const double t1 = a_first ? tau_a : tau_c, t2 = a_first ? tau_c : tau_a;
@@ -376,24 +513,36 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
     bump_bytes(x, 64ll * k);
     // quantum-number check of the changed sub-string + scalar trace ratio
     const int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
+    const bool blocked = T.dmax > 1;
     double dlog = 0.0, dsign = 1.0;
     int cur = conn(T, begin_sst, code1), old_after = begin_sst, nother = 0;
     double tl = t1;
-    if (cur >= 0) {
-        double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog += log(fabs(e)); if (e < 0) dsign = -dsign;
-        walk_delta(T, x, i1, i2 - i1, f, cur, old_after, tl, dlog, dsign, nother);
-    }
     int new_end = -1;
-    if (cur >= 0) {
-        dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
-        double e = ldg(&T.elem[cur * T.nops + code2]);
-        new_end = conn(T, cur, code2);
-        if (new_end >= 0) { dlog += log(fabs(e)); if (e < 0) dsign = -dsign; }
+    if (!blocked) {
+        if (cur >= 0) {
+            double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog += log(fabs(e)); if (e < 0) dsign = -dsign;
+            walk_delta(T, x, i1, i2 - i1, f, cur, old_after, tl, dlog, dsign, nother);
+        }
+        if (cur >= 0) {
+            dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
+            double e = ldg(&T.elem[cur * T.nops + code2]);
+            new_end = conn(T, cur, code2);
+            if (new_end >= 0) { dlog += log(fabs(e)); if (e < 0) dsign = -dsign; }
+        }
+    } else {
+        if (cur >= 0) cur = walk_check(T, x, i1, i2 - i1, f, cur, nother);
+        if (i2 > i1) old_after = (int)x.sst[i2 - 1];
+        if (cur >= 0) new_end = conn(T, cur, code2);
     }
     if (new_end < 0 || new_end != old_after) { bump(x, C_QNADD); log_end(x, 2); return; }
     // determinant ratio
     const double S = det_ratio_add(T, C, x, f, tau_c, tau_a);
     bump_bytes(x, 8ll * k * k);
+    double tn_log = 0.0, tn_sign = 1.0;
+    if (blocked) {                                                     // get_trace_EB of the proposed configuration
+        seg_trace(T, C, x, i1, i2, true, t1, code1, i1, i2, true, t2, code2, tn_log, tn_sign);
+        dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
+    }
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
     const double dr_log = log(fabs(S)), dr_sign = sgn1(S) * sig;
     const double rand = x.rng.next();
@@ -413,10 +562,17 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
     shift_up(x.tau, i2, x.n, 2); shift_up(x.code, i2, x.n, 2); shift_up(x.sst, i2, x.n, 2);
     shift_up(x.tau, i1, i2, 1); shift_up(x.code, i1, i2, 1); shift_up(x.sst, i1, i2, 1);
     if (x.lane == 0) { x.tau[i1] = t1; x.code[i1] = (unsigned char)code1; x.tau[i2 + 1] = t2; x.code[i2 + 1] = (unsigned char)code2; }
+    if (blocked) {                                                     // two fresh cache slots; kets valid below i1, bras from i2+2 on
+        shift_up(x.slot, i2, x.n, 2); shift_up(x.slot, i1, i2, 1);
+        if (x.lane == 0) { x.slot[i1] = x.freel[x.nfree - 1]; x.slot[i2 + 1] = x.freel[x.nfree - 2]; }
+        x.nfree -= 2; x.kv = i1; x.bv = i2 + 2;
+        commit_parts(T, x);
+    }
     wsync();
     x.n += 2;
     walk_store(T, x.code, i1, i2 - i1 + 2, begin_sst, x.sst, i1);
-    x.det_log += dr_log; x.det_sign *= dr_sign; x.tr_log += dlog; x.tr_sign *= dsign;
+    x.det_log += dr_log; x.det_sign *= dr_sign;
+    if (blocked) { x.tr_log = tn_log; x.tr_sign = tn_sign; } else { x.tr_log += dlog; x.tr_sign *= dsign; }
     x.perm ^= (nother & 1);
     x.palt = (x.palt & ~(1 << f)) | (palt_flavour(C, x, f) << f);
     x.npairs = np_new;
@@ -484,15 +640,23 @@ W2B_HDN void step_rem(const Tables& T, const Run& R, const Chains& C, const Accu
     // quantum numbers + scalar trace ratio of the configuration without the pair
     const int code1 = f * 2 + type1, code2 = f * 2 + (1 - type1);
     const int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
-    double dlog = 0.0, dsign = 1.0;
-    { double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog -= log(fabs(e)); if (e < 0) dsign = -dsign; }
+    const bool blocked = T.dmax > 1;
+    double dlog = 0.0, dsign = 1.0, tn_log = 0.0, tn_sign = 1.0;
     int cur = begin_sst, old_after = (int)x.sst[i1], nother = 0;
     double tl = t1;
-    walk_delta(T, x, i1 + 1, i2 - i1 - 1, f, cur, old_after, tl, dlog, dsign, nother);
     const int end_sst = (int)x.sst[i2];
-    if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return; }
-    dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
-    { double e = ldg(&T.elem[old_after * T.nops + code2]); dlog -= log(fabs(e)); if (e < 0) dsign = -dsign; }
+    if (!blocked) {
+        { double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog -= log(fabs(e)); if (e < 0) dsign = -dsign; }
+        walk_delta(T, x, i1 + 1, i2 - i1 - 1, f, cur, old_after, tl, dlog, dsign, nother);
+        if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return; }
+        dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
+        { double e = ldg(&T.elem[old_after * T.nops + code2]); dlog -= log(fabs(e)); if (e < 0) dsign = -dsign; }
+    } else {
+        cur = walk_check(T, x, i1 + 1, i2 - i1 - 1, f, cur, nother);
+        if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return; }
+        seg_trace(T, C, x, i1, i2 + 1, false, 0.0, 0, i1 + 1, i2, false, 0.0, 0, tn_log, tn_sign);
+        dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
+    }
     // determinant ratio = M(p1,p2)  (MatrixUpdate.F90:445-452)
     const double S = Mbuf(C, x, f)[(size_t)p1 * C.ld + p2];
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
@@ -507,11 +671,19 @@ W2B_HDN void step_rem(const Tables& T, const Run& R, const Chains& C, const Accu
     bump_bytes(x, 8ll * (k * k + (k - 1) * (k - 1)));
     mat_rem(C, x, f, T.nf, p1, p2);
     shift_down(x.tc + (size_t)f * C.kcap, p1, k, 1); shift_down(x.ta + (size_t)f * C.kcap, p2, k, 1);
+    if (blocked) {                                                     // give the two cache slots back; kets valid below i1, bras from i2-1 on
+        if (x.lane == 0) { x.freel[x.nfree] = x.slot[i1]; x.freel[x.nfree + 1] = x.slot[i2]; }
+        wsync();
+        shift_down(x.slot, i1, i2, 1); shift_down(x.slot, i2 - 1, x.n, 2);
+        x.nfree += 2; x.kv = i1; x.bv = i2 - 1;
+        commit_parts(T, x);
+    }
     shift_down(x.tau, i1, i2, 1); shift_down(x.code, i1, i2, 1); shift_down(x.sst, i1, i2, 1);
     shift_down(x.tau, i2 - 1, x.n, 2); shift_down(x.code, i2 - 1, x.n, 2); shift_down(x.sst, i2 - 1, x.n, 2);
     x.n -= 2;
     walk_store(T, x.code, i1, i2 - i1 - 1, begin_sst, x.sst, i1);
-    x.det_log += dr_log; x.det_sign *= dr_sign; x.tr_log += dlog; x.tr_sign *= dsign;
+    x.det_log += dr_log; x.det_sign *= dr_sign;
+    if (blocked) { x.tr_log = tn_log; x.tr_sign = tn_sign; } else { x.tr_log += dlog; x.tr_sign *= dsign; }
     x.perm ^= (nother & 1);
     x.palt = (x.palt & ~(1 << f)) | (palt_flavour(C, x, f) << f);
     x.npairs = np_new;
@@ -706,7 +878,8 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
     }
     const double dr_log = dn_log + do_log, dr_sign = dn_sign * do_sign;
     double tn_log, tn_sign;
-    trace_full_scalar(T, x.tau, x.sc_code, x.sc_sst, x.n, new_outer, tn_log, tn_sign);
+    if (T.dmax > 1) full_trace(T, x, x.tau, x.sc_code, x.n, new_outer, tn_log, tn_sign);
+    else trace_full_scalar(T, x.tau, x.sc_code, x.sc_sst, x.n, new_outer, tn_log, tn_sign);
     const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
     const double prob = fabs(exp(trr_log + dr_log) * factor);
     const double rand = x.rng.next();
@@ -726,6 +899,7 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
     rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
     x.outer = new_outer;
     x.det_log = dn_log; x.det_sign = dn_sign; x.tr_log = tn_log; x.tr_sign = tn_sign;
+    if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); }
     x.perm = perm_full(x.code, x.n);
     x.palt = 0; for (int f = 0; f < nf; ++f) x.palt |= palt_flavour(C, x, f) << f;
     update_cfgsign(T, x);
@@ -741,6 +915,7 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
         double acc = 0.0; int pick = T.nsst - 1;
         for (int i = 0; i < T.nsst; ++i) { double w = ldg(&T.empty_w[i]); acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
         x.outer = pick; x.tr_log = ldg(&T.empty_log[pick]); x.tr_sign = 1.0;
+        if (T.dmax > 1) empty_parts(T, x, pick);
         update_cfgsign(T, x);
         log_set(x, 17, rand); log_end(x, 1);
         return;
@@ -764,7 +939,8 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
     x.wpos = ((wp_old - sh) % R.num_windows + R.num_windows) % R.num_windows;
     set_window_edges(T, R, x);
     double tn_log, tn_sign;
-    trace_full_scalar(T, x.sc_tau, x.sc_code, x.sc_sst, n, new_outer, tn_log, tn_sign);
+    if (T.dmax > 1) full_trace(T, x, x.sc_tau, x.sc_code, n, new_outer, tn_log, tn_sign);
+    else trace_full_scalar(T, x.sc_tau, x.sc_code, x.sc_sst, n, new_outer, tn_log, tn_sign);
     const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
     const double prob = fabs(trr_sign * exp(trr_log));
     const double rand = x.rng.next();
@@ -809,6 +985,7 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
     wsync();
     x.outer = new_outer;
     x.tr_log = tn_log; x.tr_sign = tn_sign; x.det_sign *= detrat;
+    if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); }
     x.npairs = -1;
     x.perm = perm_full(x.code, x.n);
     x.palt = 0; for (int f = 0; f < T.nf; ++f) x.palt |= palt_flavour(C, x, f) << f;
@@ -839,7 +1016,7 @@ W2B_HD void do_step(const Tables& T, const Run& R, const Chains& C, const Accum&
 }
 
 // ------------------------------------------------------------------ chain load / store
-W2B_HD void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, double* wscratch, int* iscratch) {
+W2B_HD void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, double* wscratch, int* iscratch, double* mscratch) {
     x.lane = lane_id();
     x.tau = C.op_tau + (size_t)chain * C.ops_cap; x.code = C.op_code + (size_t)chain * C.ops_cap; x.sst = C.op_sst + (size_t)chain * C.ops_cap;
     x.sc_tau = C.sc_tau + (size_t)chain * C.ops_cap; x.sc_code = C.sc_code + (size_t)chain * C.ops_cap; x.sc_sst = C.sc_sst + (size_t)chain * C.ops_cap;
@@ -849,10 +1026,18 @@ W2B_HD void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, 
     x.ih = C.ih + (size_t)chain * IH_STRIDE; x.dh = C.dh + (size_t)chain * DH_STRIDE;
     x.cnt = C.counters + (size_t)chain * C_NCNT;
     x.wQ = wscratch; x.wR = wscratch + C.kcap; x.wV = wscratch + 2 * C.kcap; x.wI = iscratch;
+    if (C.dmax > 1) {
+        x.slot = C.op_slot + (size_t)chain * C.ops_cap; x.freel = C.free_slot + (size_t)chain * C.ops_cap;
+        x.ket = C.ket + (size_t)chain * C.ops_cap * C.mstride; x.bra = C.bra + (size_t)chain * C.ops_cap * C.mstride;
+        x.ketlg = C.ketlg + (size_t)chain * C.ops_cap * C.dmax; x.bralg = C.bralg + (size_t)chain * C.ops_cap * C.dmax;
+        x.pt = C.pt + (size_t)chain * 2 * C.dmax;
+        x.mX = mscratch; x.mY = mscratch + C.mstride; x.mlg = mscratch + 2 * C.mstride; x.mpt = x.mlg + C.dmax;
+        x.kv = x.ih[IH_KV]; x.bv = x.ih[IH_BV]; x.nfree = x.ih[IH_NFREE];
+    }
     x.n = x.ih[IH_NOPS]; x.outer = x.ih[IH_OUTER]; x.wpos = x.ih[IH_WPOS]; x.npairs = x.ih[IH_NPAIRS];
     x.perm = x.ih[IH_PERM]; x.palt = x.ih[IH_PALT]; x.err = x.ih[IH_ERR];
     x.det_log = x.dh[DH_DETLOG]; x.det_sign = x.dh[DH_DETSIGN]; x.tr_log = x.dh[DH_TRLOG]; x.tr_sign = x.dh[DH_TRSIGN]; x.cfgsign = x.dh[DH_CFGSIGN];
-    x.rng.init(R.seed, R.chain_base + (unsigned)chain, C.rng_ctr[chain]);
+    x.rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, C.rng_ctr[chain]);
     set_window_edges(T, R, x);
     x.log = nullptr;
 }
@@ -861,6 +1046,7 @@ W2B_HD void ctx_store(const Chains& C, int chain, Ctx& x) {
     if (x.lane == 0) {
         x.ih[IH_NOPS] = x.n; x.ih[IH_OUTER] = x.outer; x.ih[IH_WPOS] = x.wpos; x.ih[IH_NPAIRS] = x.npairs;
         x.ih[IH_PERM] = x.perm; x.ih[IH_PALT] = x.palt; x.ih[IH_ERR] = x.err;
+        if (C.dmax > 1) { x.ih[IH_KV] = x.kv; x.ih[IH_BV] = x.bv; x.ih[IH_NFREE] = x.nfree; }
         x.dh[DH_DETLOG] = x.det_log; x.dh[DH_DETSIGN] = x.det_sign; x.dh[DH_TRLOG] = x.tr_log; x.dh[DH_TRSIGN] = x.tr_sign; x.dh[DH_CFGSIGN] = x.cfgsign;
         C.rng_ctr[chain] = x.rng.ctr;
     }
@@ -869,9 +1055,9 @@ W2B_HD void ctx_store(const Chains& C, int chain, Ctx& x) {
 
 // advance one chain by nsteps moves; logbuf (optional) receives LOGW doubles per move
 W2B_HD void sweep_chain(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain, long long nsteps,
-                        double* wscratch, int* iscratch, double* logbuf) {
+                        double* wscratch, int* iscratch, double* mscratch, double* logbuf) {
     Ctx x;
-    ctx_bind(T, R, C, chain, x, wscratch, iscratch);
+    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
     unsigned long long attempts = x.cnt[C_TRYADD] + x.cnt[C_TRYREM];
     wsync();
     for (long long it = 0; it < nsteps; ++it) {
@@ -887,7 +1073,7 @@ W2B_HD void sweep_chain(const Tables& T, const Run& R, const Chains& C, const Ac
 W2B_HD void init_chain(const Tables& T, const Run& R, const Chains& C, int chain) {
     if (lane_id() != 0) return;
     int* ih = C.ih + (size_t)chain * IH_STRIDE; double* dh = C.dh + (size_t)chain * DH_STRIDE;
-    Philox rng; rng.init(R.seed, R.chain_base + (unsigned)chain, 0ull);
+    Philox rng; rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, 0ull);
     const double rand = rng.next();
     double acc = 0.0; int pick = T.nsst - 1;
     for (int i = 0; i < T.nsst; ++i) { double w = T.empty_w[i]; acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
@@ -897,11 +1083,72 @@ W2B_HD void init_chain(const Tables& T, const Run& R, const Chains& C, int chain
     dh[DH_DETLOG] = 0.0; dh[DH_DETSIGN] = 1.0; dh[DH_TRLOG] = T.empty_log[pick]; dh[DH_TRSIGN] = 1.0; dh[DH_CFGSIGN] = -1.0;
     C.rng_ctr[chain] = rng.ctr;
     for (int i = 0; i < C_NCNT; ++i) C.counters[(size_t)chain * C_NCNT + i] = 0ull;
+    if (C.dmax > 1) {
+        ih[IH_KV] = 0; ih[IH_BV] = 0; ih[IH_NFREE] = C.ops_cap;
+        for (int i = 0; i < C.ops_cap; ++i) { C.op_slot[(size_t)chain * C.ops_cap + i] = (unsigned short)i; C.free_slot[(size_t)chain * C.ops_cap + i] = (unsigned short)(C.ops_cap - 1 - i); }
+        const double* ev = T.evals + T.offset[pick];
+        for (int j = 0; j < T.dim[pick]; ++j) { C.pt[(size_t)chain * 2 * C.dmax + 2 * j] = -(ev[j] - T.egs) * T.beta; C.pt[(size_t)chain * 2 * C.dmax + 2 * j + 1] = 1.0; }
+    }
 }
 
 // ------------------------------------------------------------------ measurement (CTQMC.F90:8541-8581)
 constexpr int LEG_CHUNK = 20;
-W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain) {
+// blocked-trace part of one measurement: per-state histograms (MeasOuterHistograms CTQMC.F90:3285-3339) and the density
+// matrix at beta/2 (update_b2_states_eb Trace.F90:6213-6469 + MeasDensityMatrix_beta_half CTQMC.F90:3088-3151)
+W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, double* acc) {
+    const int m = ldg(&T.dim[x.outer]), off = ldg(&T.offset[x.outer]);
+    double csum = 0.0;
+    for (int j = x.lane; j < m; j += W2B_WARP) {
+        const double e = x.pt[2 * j + 1] != 0.0 ? exp(x.pt[2 * j]) : 0.0;
+        atomic_add(&acc[A.o_outerst + off + j], 1.0);
+        atomic_add(&acc[A.o_signst + off + j], x.tr_sign * x.pt[2 * j + 1] * x.cfgsign);
+        atomic_add(&acc[A.o_contribst + off + j], e);
+        csum += e;
+    }
+    csum = wsum(csum);
+    if (x.lane == 0) atomic_add(&acc[A.o_contribsst + x.outer], csum);
+    if (!R.meas_dm) return;
+    if (x.n == 0) {
+        const int doff = ldg(&T.dens_off[x.outer]);
+        for (int j = x.lane; j < m; j += W2B_WARP)
+            atomic_add(&acc[A.o_dens + doff + j + j * m], -x.cfgsign * x.pt[2 * j + 1] * x.tr_sign * exp(x.pt[2 * j] - x.tr_log));
+        return;
+    }
+    const double bh = T.beta / 2.0;
+    const int ih = count_le(x.tau, x.n, bh);                 // operators with tau <= beta/2 belong to the ket
+    extend_kets(T, C, x, ih - 1);
+    extend_bras(T, C, x, ih);
+    const int sst = ih == 0 ? x.outer : (int)x.sst[ih - 1];
+    const int d = ldg(&T.dim[sst]);
+    const double* ev = T.evals + ldg(&T.offset[sst]);
+    const double e0 = ldg(&ev[0]);
+    const double tauR = ih == 0 ? 0.0 : x.tau[ih - 1], tauL = ih == x.n ? T.beta : x.tau[ih];
+    double* K = x.mX; double* B = x.mY; double* klg = x.mlg; double* blg = x.mpt; double* fac = x.mpt + C.dmax;
+    if (ih == 0) mat_identity(K, klg, m);
+    else { mat_copy(K, ket_slot(C, x, ih - 1), d * m); mat_copy(klg, x.ketlg + (size_t)x.slot[ih - 1] * C.dmax, m); }
+    if (ih == x.n) mat_identity(B, blg, m);
+    else { mat_copy(B, bra_slot(C, x, ih), d * m); mat_copy(blg, x.bralg + (size_t)x.slot[ih] * C.dmax, m); }
+    wsync();
+    for (int e = x.lane; e < d * m; e += W2B_WARP) {
+        const int c = e % d; const double de = ldg(&ev[c]) - e0;
+        K[e] *= exp(-de * (bh - tauR)); B[e] *= exp(-de * (tauL - bh));
+    }
+    for (int j = x.lane; j < m; j += W2B_WARP) {
+        const double kl = klg[j] - (e0 - T.egs) * (bh - tauR), bl = blg[j] - (e0 - T.egs) * (tauL - bh);
+        fac[j] = x.tr_sign * (-x.cfgsign) * exp(kl + bl - x.tr_log);      // 1 / trval(Trace / TLogTr(kl + bl, -cfgsign))
+    }
+    wsync();
+    const int doff = ldg(&T.dens_off[sst]);
+    for (int e = x.lane; e < d * d; e += W2B_WARP) {
+        const int a = e % d, c = e / d;
+        double v = 0.0;
+        for (int j = 0; j < m; ++j) v += B[a + (size_t)j * d] * K[c + (size_t)j * d] * fac[j];
+        atomic_add(&acc[A.o_dens + doff + a + c * d], v);
+    }
+    wsync();
+}
+
+W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain, double* wscratch, int* iscratch, double* mscratch) {
     const int lane = lane_id();
     const int* ih = C.ih + (size_t)chain * IH_STRIDE; const double* dh = C.dh + (size_t)chain * DH_STRIDE;
     const int n = ih[IH_NOPS], outer = ih[IH_OUTER];
@@ -910,17 +1157,25 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
     const double* tau = C.op_tau + (size_t)chain * C.ops_cap; const short* sst = C.op_sst + (size_t)chain * C.ops_cap;
     if (lane == 0) {
         atomic_add(&acc[A.o_sign], cfgsign); atomic_add(&acc[A.o_cnt], 1.0);                 // MeasSign 3343
-        atomic_add(&acc[A.o_outer + outer], 1.0); atomic_add(&acc[A.o_signsst + outer], cfgsign);   // MeasOuterHistograms 3285-3339 (1x1 blocks)
-        atomic_add(&acc[A.o_contribsst + outer], exp(dh[DH_TRLOG]));
-        int off = T.offset[outer];
-        atomic_add(&acc[A.o_outerst + off], 1.0); atomic_add(&acc[A.o_signst + off], cfgsign);  // Trace.sign*parttrace.sign = 1 for a 1x1 block
-        atomic_add(&acc[A.o_contribst + off], exp(dh[DH_TRLOG]));
+        atomic_add(&acc[A.o_outer + outer], 1.0); atomic_add(&acc[A.o_signsst + outer], cfgsign);   // MeasOuterHistograms 3285-3339
+        if (T.dmax == 1) {
+            atomic_add(&acc[A.o_contribsst + outer], exp(dh[DH_TRLOG]));
+            int off = T.offset[outer];
+            atomic_add(&acc[A.o_outerst + off], 1.0); atomic_add(&acc[A.o_signst + off], cfgsign);  // Trace.sign*parttrace.sign = 1 for a 1x1 block
+            atomic_add(&acc[A.o_contribst + off], exp(dh[DH_TRLOG]));
+        }
         for (int f = 0; f < T.nf; ++f) {                                                       // MeasExpOrder 3264-3282
             int k = ih[IH_KF + f]; if (k > R.maxhisto) k = R.maxhisto;
             atomic_add(&acc[A.o_histo + f * (R.maxhisto + 1) + k], 1.0);
         }
     }
-    if (R.meas_dm) {                                                                          // MeasDensityMatrix_beta_half 3088-3151 (1x1 blocks)
+    if (T.dmax > 1) {
+        Ctx x;
+        ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+        wsync();
+        measure_blocked(T, R, C, A, x, acc);
+        ctx_store(C, chain, x);
+    } else if (R.meas_dm) {                                                                   // MeasDensityMatrix_beta_half 3088-3151 (1x1 blocks)
         int ihalf = count_le(tau, n, T.beta / 2.0);
         if (lane == 0) {
             int s = ihalf == 0 ? outer : (int)sst[ihalf - 1];
@@ -966,9 +1221,9 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
 
 // Rebuild all derived state of one chain from its operator list (set_mc_config_from_arrays, Trace.F90:6872-7000):
 // superstate sequence, flavour tau arrays, inverse matrices + determinant, trace, signs.
-W2B_HD void rebuild_chain(const Tables& T, const Run& R, const Chains& C, int chain, double* wscratch, int* iscratch) {
+W2B_HD void rebuild_chain(const Tables& T, const Run& R, const Chains& C, int chain, double* wscratch, int* iscratch, double* mscratch) {
     Ctx x;
-    ctx_bind(T, R, C, chain, x, wscratch, iscratch);
+    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
     const int lane = x.lane;
     x.wpos = 0; set_window_edges(T, R, x);
     if (lane == 0) for (int f = 0; f <= T.nf; ++f) x.ih[IH_MSLOT + f] = f;
@@ -994,7 +1249,13 @@ W2B_HD void rebuild_chain(const Tables& T, const Run& R, const Chains& C, int ch
     rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, lg, sg);
     x.det_log = lg; x.det_sign = sg;
     if (sg == 0.0) x.err |= ERR_SINGULAR;
-    if (!(x.err & ERR_GLOBAL_QN)) trace_full_scalar(T, x.tau, x.code, x.sst, x.n, x.outer, x.tr_log, x.tr_sign);
+    if (!(x.err & ERR_GLOBAL_QN)) {
+        if (T.dmax > 1) {
+            if (x.n > 0) { full_trace(T, x, x.tau, x.code, x.n, x.outer, x.tr_log, x.tr_sign); commit_parts(T, x); }
+            else { x.tr_log = T.empty_log[x.outer]; x.tr_sign = 1.0; empty_parts(T, x, x.outer); }
+            slots_reset(C, x);
+        } else trace_full_scalar(T, x.tau, x.code, x.sst, x.n, x.outer, x.tr_log, x.tr_sign);
+    }
     x.npairs = -1;
     x.perm = perm_full(x.code, x.n);
     x.palt = 0; for (int f = 0; f < T.nf; ++f) x.palt |= palt_flavour(C, x, f) << f;

@@ -86,6 +86,7 @@ W2B_HD void atomic_add(unsigned long long* p, unsigned long long v) { atomicAdd(
 W2B_HD double ldg(const double* p) { return __ldg(p); }
 W2B_HD int ldg(const int* p) { return __ldg(p); }
 W2B_HD short ldg(const short* p) { return __ldg(p); }
+W2B_HD long long ldg(const long long* p) { return __ldg(p); }
 #else
 W2B_HD int lane_id() { return 0; }
 W2B_HD void wsync() {}
@@ -106,6 +107,17 @@ W2B_HD void atomic_add(unsigned long long* p, unsigned long long v) { *p += v; }
 W2B_HD double ldg(const double* p) { return *p; }
 W2B_HD int ldg(const int* p) { return *p; }
 W2B_HD short ldg(const short* p) { return *p; }
+W2B_HD long long ldg(const long long* p) { return *p; }
+#endif
+
+// Unfused multiply / add: proposal times must be bit-identical to a CPU evaluation of the reference formulas
+// (nvcc would contract a*b+c into one FMA; times feed exact comparisons and integer bookkeeping).
+#if W2B_DEVICE
+W2B_HD double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+W2B_HD double add_rn(double a, double b) { return __dadd_rn(a, b); }
+#else
+W2B_HD double mul_rn(double a, double b) { return a * b; }
+W2B_HD double add_rn(double a, double b) { return a + b; }
 #endif
 
 // ---------------------------------------------------------------- counter-based RNG
