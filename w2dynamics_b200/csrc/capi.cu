@@ -151,6 +151,8 @@ int w2b_set_option(const char* key, double value) {
     else if (k == "kcap") S.opt.kcap = (int)value;
     else if (k == "ops_cap") S.opt.ops_cap = (int)value;
     else if (k == "chain_base") S.opt.chain_base = (unsigned)value;
+    else if (k == "cta_warps") S.opt.cta_warps = (int)value;
+    else if (k == "batch_chains") S.opt.batch_chains = (int)value;
     else if (k == "device") S.device = (int)value;
     else if (k == "nmeas_override") S.nmeas_override = (long long)value;
     else if (k == "debug_same_key") S.same_key = (int)value;
@@ -393,6 +395,10 @@ int w2b_get_scalar(const char* name, double* out) {
             if (k == "nslide") { *out = E.R.nslide; return; }
             if (k == "egs") { *out = E.at.egs; return; }
             if (k == "gpu_launches") { *out = (double)E.launches; return; }
+            if (k == "cta_warps") { *out = E.sw_warps; return; }
+            if (k == "batch_chains") { *out = E.sw_ncb; return; }
+            if (k == "sweep_grid") { *out = E.sw_grid; return; }
+            if (k == "sweep_smem") { *out = (double)E.sw_smem; return; }
             if (k.rfind("cnt_", 0) == 0) {
                 static const char* names[C_NCNT] = {"try_add", "try_rem", "try_glob", "try_shift", "acc_add", "acc_rem", "acc_glob", "acc_shift",
                                                     "qn_add", "qn_rem", "qn_glob", "steps", "alg_bytes"};

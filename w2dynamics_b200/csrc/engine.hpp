@@ -70,6 +70,7 @@ template <class T_> T_* dev_upload(const std::vector<T_>& v) { T_* d = dev_alloc
 
 // ---------------------------------------------------------------- kernels
 constexpr int WARPS_PER_CTA = 4;
+constexpr int MAX_CTA_THREADS = 512;
 // per-warp work space of the blocked trace in doubles: two d x m matrices, column log scales, per-state trace parts
 #if W2B_DEVICE
 __host__ __device__
@@ -81,15 +82,42 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_init(Tables T, Run R, Ch
     int chain = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (chain < C.nchains) init_chain(T, R, C, chain);
 }
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_sweep(Tables T, Run R, Chains C, Accum A, long long nsteps, int wdoubles,
-                                                              int log_chain, double* logbuf) {
+// bytes of the CTA-shared scheduler arrays for a batch of ncb chains (after the per-warp scratch)
+#endif
+#if W2B_DEVICE
+#define W2B_HOSTDEV __host__ __device__
+#else
+#define W2B_HOSTDEV
+#endif
+W2B_HOSTDEV inline size_t sched_bytes(int ncb) { return (size_t)ncb * (sizeof(Prop) + sizeof(int) + 5 * sizeof(short) + 2) + 64; }
+W2B_HOSTDEV inline void sched_carve(CtaShared& S, char* base, int ncb) {
+    S.prop = (Prop*)base; base += (size_t)ncb * sizeof(Prop);
+    S.left = (int*)base; base += (size_t)ncb * sizeof(int);
+    S.lA = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.lR = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.lA2 = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.lR2 = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.lG = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.parked = (unsigned char*)base; base += ncb;
+    S.kind = (unsigned char*)base;
+}
+#if W2B_DEVICE
+// persistent sweep kernel: every CTA serves batches of ncb chains (batch b -> chains [b*ncb, (b+1)*ncb))
+__global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T, Run R, Chains C, Accum A, long long nsteps, int wdoubles, int ncb, int nbatch,
+                                                             int log_chain, double* logbuf) {
     extern __shared__ double smem[];
-    int warp = threadIdx.x >> 5;
-    int chain = blockIdx.x * WARPS_PER_CTA + warp;
-    if (chain >= C.nchains) return;
+    __shared__ CtaShared S;
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5;
     double* ws = smem + (size_t)warp * wdoubles;
     int* is = (int*)(ws + 3 * C.kcap + mat_doubles(C));
-    sweep_chain(T, R, C, A, chain, nsteps, ws, is, ws + 3 * C.kcap, chain == log_chain ? logbuf : nullptr);
+    if (threadIdx.x == 0) { CtaShared tmp; sched_carve(tmp, (char*)(smem + (size_t)W * wdoubles), ncb);
+        S.prop = tmp.prop; S.left = tmp.left; S.lA = tmp.lA; S.lR = tmp.lR; S.lA2 = tmp.lA2; S.lR2 = tmp.lR2; S.lG = tmp.lG; S.parked = tmp.parked; S.kind = tmp.kind; }
+    __syncthreads();
+    for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+        const int lo = b * ncb, nloc = min(ncb, C.nchains - lo);
+        cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws, is, ws + 3 * C.kcap, log_chain, logbuf);
+        __syncthreads();
+    }
 }
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_measure(Tables T, Run R, Chains C, Accum A, int wdoubles) {
     extern __shared__ double smem[];
@@ -113,6 +141,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R,
 
 struct EngineOptions {
     int nchains = 1024, nbins = 16, kcap = 0, ops_cap = 0;
+    int cta_warps = 0, batch_chains = 0;      // sweep kernel geometry (0 = automatic)
     unsigned seed = 0, chain_base = 0;
 };
 
@@ -256,20 +285,54 @@ public:
     }
     void zero_accum() { dev_zero(A.base, (size_t)R.nbins * accum_doubles); }
 
+    // sweep-kernel geometry: W warps per CTA, batches of ncb chains, persistent grid
+    int sw_warps = 1, sw_ncb = 1, sw_nbatch = 1, sw_grid = 1; size_t sw_smem = 0; bool sw_ready = false;
+    void plan_sweep() {
+        const int nc = C.nchains;
+#if W2B_DEVICE
+        int dev = 0, nsm = 1, smem_max = 48 * 1024;
+        W2B_CUDA_CHECK(cudaGetDevice(&dev));
+        W2B_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        W2B_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        int W = opt.cta_warps > 0 ? opt.cta_warps : 8;
+        const size_t per_warp = (size_t)wdoubles * sizeof(double);
+        while (W > 1 && W * per_warp + sched_bytes(4 * W) > (size_t)smem_max - 1024) --W;
+        if (W > MAX_CTA_THREADS / 32) W = MAX_CTA_THREADS / 32;
+        int target = opt.batch_chains > 0 ? opt.batch_chains : 4 * W;
+        size_t sm = W * per_warp + sched_bytes(target);
+        W2B_CUDA_CHECK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min((size_t)smem_max, sm + 4096)));
+        int occ = 1;
+        W2B_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, W * 32, sm));
+        if (occ < 1) occ = 1;
+        const int slots = nsm * occ;
+        int rounds = (nc + slots * target - 1) / (slots * target);
+        int ncb = (nc + slots * rounds - 1) / (slots * rounds);
+        if (ncb < 1) ncb = 1;
+        if (ncb > target) ncb = target;
+        sw_warps = W; sw_ncb = ncb; sw_nbatch = (nc + ncb - 1) / ncb; sw_grid = std::min(sw_nbatch, slots);
+        sw_smem = W * per_warp + sched_bytes(ncb);
+#else
+        sw_warps = 1; sw_ncb = opt.batch_chains > 0 ? opt.batch_chains : 4; sw_nbatch = (nc + sw_ncb - 1) / sw_ncb; sw_grid = 1;
+#endif
+        sw_ready = true;
+    }
+
     // advance every chain by nsteps moves; optionally record the replay log of one chain
     void sweep(long long nsteps, int log_chain = -1, double* log_host = nullptr) {
+        if (!sw_ready) plan_sweep();
         double* dlog = nullptr;
         if (log_chain >= 0) dlog = dev_alloc<double>((size_t)nsteps * LOGW);
 #if W2B_DEVICE
-        size_t sm = smem_bytes();
-        static size_t configured = 0;
-        if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
-        k_sweep<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, A, nsteps, wdoubles, log_chain, dlog); ++launches;
+        k_sweep<<<sw_grid, sw_warps * 32, sw_smem>>>(T, R, C, A, nsteps, wdoubles, sw_ncb, sw_nbatch, log_chain, dlog); ++launches;
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
         std::vector<double> ws(wdoubles + 8);
-        for (int c = 0; c < C.nchains; ++c)
-            sweep_chain(T, R, C, A, c, nsteps, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C)), ws.data() + 3 * C.kcap, c == log_chain ? dlog : nullptr);
+        std::vector<char> sb(sched_bytes(sw_ncb));
+        CtaShared S{}; sched_carve(S, sb.data(), sw_ncb);
+        for (int b = 0; b < sw_nbatch; ++b) {
+            const int lo = b * sw_ncb, nloc = std::min(sw_ncb, C.nchains - lo);
+            cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C)), ws.data() + 3 * C.kcap, log_chain, dlog);
+        }
 #endif
         if (log_chain >= 0) { sync(); d2h(log_host, dlog, (size_t)nsteps * LOGW); dev_free(dlog); }
     }

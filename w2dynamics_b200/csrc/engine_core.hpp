@@ -108,7 +108,7 @@ W2B_HD double sgn1(double x) { return (x < 0.0 || (x == 0.0 && 1.0 / x < 0.0)) ?
 W2B_HD int conn(const Tables& T, int sst, int opc) { return (int)ldg(&T.connect[sst * T.nops + opc]); }
 
 // get_HybrF Trace.F90:1014-1033
-W2B_HD double hybrF(const Tables& T, double tau, int f) {
+W2B_HDN double hybrF(const Tables& T, double tau, int f) {
     double sig = 1.0;
     if (tau < 0.0) { tau += T.beta; sig = -1.0; }
     double n = tau / T.beta * (double)(T.nftau - 1);
@@ -128,21 +128,21 @@ W2B_HD void set_window_edges(const Tables& T, const Run& R, Ctx& x) {   // set_w
 W2B_HD double* Mbuf(const Chains& C, Ctx& x, int f) { return x.Mbase + (size_t)x.ih[IH_MSLOT + f] * ((size_t)C.kcap * C.ld); }
 
 // number of sorted entries < t ; eq is set when an entry equals t
-W2B_HD int count_lt(const double* a, int n, double t, bool& eq) {
+W2B_HDN int count_lt(const double* a, int n, double t, bool& eq) {
     int c = 0; bool e = false;
     for (int i = lane_id(); i < n; i += W2B_WARP) { double v = a[i]; c += (v < t); e |= (v == t); }
     eq = wany(e);
     return wsum(c);
 }
 W2B_HD int count_lt(const double* a, int n, double t) { bool e; return count_lt(a, n, t, e); }
-W2B_HD int count_le(const double* a, int n, double t) {
+W2B_HDN int count_le(const double* a, int n, double t) {
     int c = 0;
     for (int i = lane_id(); i < n; i += W2B_WARP) c += (a[i] <= t);
     return wsum(c);
 }
 
 // array shifts by whole-warp chunks (read chunk, sync, write)
-template <class T_> W2B_HD void shift_up(T_* a, int from, int n, int by) {       // [from,n) -> [from+by, n+by)
+template <class T_> W2B_HDN void shift_up(T_* a, int from, int n, int by) {       // [from,n) -> [from+by, n+by)
     for (int top = n; top > from; top -= W2B_WARP) {
         int idx = top - 1 - lane_id();
         T_ v = T_(); bool act = idx >= from;
@@ -152,7 +152,7 @@ template <class T_> W2B_HD void shift_up(T_* a, int from, int n, int by) {      
         wsync();
     }
 }
-template <class T_> W2B_HD void shift_down(T_* a, int from, int n, int by) {     // [from+by, n) -> [from, n-by)
+template <class T_> W2B_HDN void shift_down(T_* a, int from, int n, int by) {     // [from+by, n) -> [from, n-by)
     for (int base = from; base < n - by; base += W2B_WARP) {
         int idx = base + lane_id();
         T_ v = T_(); bool act = idx < n - by;
@@ -166,7 +166,7 @@ template <class T_> W2B_HD void shift_down(T_* a, int from, int n, int by) {    
 // Serial superstate walk over `m` existing operators starting at list index i0 (codes from `code`), starting from
 // superstate `cur`; stores the superstate after each operator into out[i0out + j].  Returns the final superstate
 // (-1 if annihilated on the way).
-W2B_HD int walk_store(const Tables& T, const unsigned char* code, int i0, int m, int cur, short* out, int i0out) {
+W2B_HDN int walk_store(const Tables& T, const unsigned char* code, int i0, int m, int cur, short* out, int i0out) {
     for (int base = 0; base < m; base += W2B_WARP) {
         int j = base + lane_id(); bool act = j < m;
         int cj = act ? (int)code[i0 + j] : 0;
@@ -188,7 +188,7 @@ W2B_HD int walk_store(const Tables& T, const unsigned char* code, int i0, int m,
 // On entry: old_before = old superstate before operator i0, tl = time of the left end of the first interval.
 // On exit:  cur / old_after = new / old superstate after the last walked operator, tl = its time (unchanged if m == 0),
 //           nother = number of walked operators whose flavour differs from f.
-W2B_HD void walk_delta(const Tables& T, const Ctx& x, int i0, int m, int f, int& cur, int& old_after, double& tl,
+W2B_HDN void walk_delta(const Tables& T, const Ctx& x, int i0, int m, int f, int& cur, int& old_after, double& tl,
                        double& dlog, double& dsign, int& nother) {
     double acc = 0.0; int neg = 0, oth = 0;
     int old_before0 = old_after; double tl0 = tl;
@@ -208,7 +208,7 @@ W2B_HD void walk_delta(const Tables& T, const Ctx& x, int i0, int m, int f, int&
             double tp = (j == 0) ? tl0 : x.tau[i0 + j - 1];
             acc += -(ldg(&T.e0[nb4]) - ldg(&T.e0[ob])) * (tj - tp);
             double en = ldg(&T.elem[nb4 * T.nops + cj]), eo = ldg(&T.elem[ob * T.nops + cj]);
-            if (en != 0.0) { acc += log(fabs(en)) - log(fabs(eo)); neg += (en < 0.0) != (eo < 0.0); }
+            if (en != 0.0) { acc += w_log(fabs(en)) - w_log(fabs(eo)); neg += (en < 0.0) != (eo < 0.0); }
             oth += ((cj >> 1) != f);
         }
     }
@@ -223,12 +223,12 @@ W2B_HD bool pairable(const Run& R, const Ctx& x, double a, double b) {
     double e = a < b ? a : b, l = a < b ? b : a;
     return e >= x.wmin && l <= x.wmax && !(l > e + R.taudiff_max);
 }
-W2B_HD int pairs_with(const Run& R, const Ctx& x, const double* opp, int k, double t) {
+W2B_HDN int pairs_with(const Run& R, const Ctx& x, const double* opp, int k, double t) {
     int c = 0;
     for (int i = lane_id(); i < k; i += W2B_WARP) c += pairable(R, x, opp[i], t);
     return wsum(c);
 }
-W2B_HD int count_pairs_full(const Tables& T, const Run& R, const Chains& C, const Ctx& x) {
+W2B_HDN int count_pairs_full(const Tables& T, const Run& R, const Chains& C, const Ctx& x) {
     int c = 0;
     for (int f = 0; f < T.nf; ++f) {
         int k = x.ih[IH_KF + f];
@@ -243,7 +243,7 @@ W2B_HD int count_pairs_full(const Tables& T, const Run& R, const Chains& C, cons
 }
 
 // number of creators sitting at an even position of the flavour's time-ordered list (get_permaltca, Trace.F90:3554-3588)
-W2B_HD int palt_flavour(const Chains& C, const Ctx& x, int f) {
+W2B_HDN int palt_flavour(const Chains& C, const Ctx& x, int f) {
     int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     int c = 0;
@@ -255,7 +255,7 @@ W2B_HD int palt_flavour(const Chains& C, const Ctx& x, int f) {
     return wsum(c) & 1;
 }
 // inversion parity of the flavour sequence in time order (== get_BlockSign, Trace.F90:3594-3618)
-W2B_HD int perm_full(const unsigned char* code, int n) {
+W2B_HDN int perm_full(const unsigned char* code, int n) {
     int c = 0;
     for (int i = lane_id(); i < n; i += W2B_WARP) {
         int fi = code[i] >> 1;
@@ -263,7 +263,7 @@ W2B_HD int perm_full(const unsigned char* code, int n) {
     }
     return wsum(c) & 1;
 }
-W2B_HD void update_cfgsign(const Tables& T, Ctx& x) {
+W2B_HDN void update_cfgsign(const Tables& T, Ctx& x) {
     int pal = 0;
     for (int f = 0; f < T.nf; ++f) pal ^= (x.palt >> f) & 1;
     if ((x.n / 2) & 1) pal ^= 1;
@@ -370,20 +370,20 @@ W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsign
     }
     mat_close(T, sst, T.beta - tprev, X, x.mlg, (const double*)nullptr, (const double*)nullptr, m, x.mpt, tlog, tsign);
 }
-// trace contributions of the outer states of an empty configuration: exp(-(E_j - Egs) beta)
+// trace contributions of the outer states of an empty configuration: w_exp(-(E_j - Egs) beta)
 W2B_HD void empty_parts(const Tables& T, Ctx& x, int outer) {
     const int m = ldg(&T.dim[outer]);
     const double* ev = T.evals + ldg(&T.offset[outer]);
     for (int j = x.lane; j < m; j += W2B_WARP) { x.pt[2 * j] = -(ldg(&ev[j]) - T.egs) * T.beta; x.pt[2 * j + 1] = 1.0; }
     wsync();
 }
-W2B_HD void commit_parts(const Tables& T, Ctx& x) {
+W2B_HDN void commit_parts(const Tables& T, Ctx& x) {
     const int m = ldg(&T.dim[x.outer]);
     for (int j = x.lane; j < 2 * m; j += W2B_WARP) x.pt[j] = x.mpt[j];
 }
 
 // integer superstate walk over the old operators [i0, i0+mcount) starting from `cur`; counts operators of another flavour
-W2B_HD int walk_check(const Tables& T, const Ctx& x, int i0, int mcount, int f, int cur, int& nother) {
+W2B_HDN int walk_check(const Tables& T, const Ctx& x, int i0, int mcount, int f, int cur, int& nother) {
     int oth = 0;
     for (int base = 0; base < mcount; base += W2B_WARP) {
         int j = base + lane_id(); bool act = j < mcount;
@@ -486,8 +486,17 @@ W2B_HD void bump(Ctx& x, int c) { if (x.lane == 0) x.cnt[c] += 1ull; }
 // algorithmic bytes of the determinant path (definition in DESIGN.md "Roofline accounting")
 W2B_HD void bump_bytes(Ctx& x, long long b) { if (x.lane == 0) x.cnt[C_ALGBYTES] += (unsigned long long)b; }
 
-// ------------------------------------------------------------------ StepAdd (CTQMC.F90:3353-3612, change_outer = false)
-W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x) {
+// ------------------------------------------------------------------ pair insertion / removal, split into two phases
+// The CTA-level scheduler (cta_sweep below) runs all chains of a CTA through the SAME phase at the same time so that the
+// warps of an SM share instruction-cache lines:  propose (RNG draws, positions, quantum-number walk, scalar trace ratio)
+// -> decide (determinant ratio, blocked trace, Metropolis draw, rank-1 update).  The proposal travels in a Prop record.
+struct Prop {
+    double t1, t2, tau_a, tau_c, factor, dlog, dsign;
+    int f, i1, i2, p1, p2, begin_sst, nother, type1;
+};
+
+// StepAdd part 1 (CTQMC.F90:3353-3469): pair_OperAdd, process_OperAdd, check_sst_sequence.  Returns false on an early exit.
+W2B_HDN bool add_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x, Prop& P) {
     log_begin(x, 1);
     bump(x, C_TRYADD);
     const double W = x.wmax - x.wmin;
@@ -497,7 +506,6 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
     const double tmin = fmax(tau_a - R.taudiff_max, x.wmin);
     const double w2 = fmin(tau_a + R.taudiff_max, x.wmax) - tmin;
     const double tau_c = add_rn(tmin, mul_rn(w2, x.rng.next()));
-    const double taudiff_factor = mul_rn(W, w2);
     const int f = b * 2 + s;
     const bool a_first = tau_a < tau_c;
     const double t1 = a_first ? tau_a : tau_c, t2 = a_first ? tau_c : tau_a;
@@ -505,37 +513,52 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
     log_set(x, 4, f); log_set(x, 2, t1); log_set(x, 3, t2);
     bool eq1, eq2;
     const int i1 = count_lt(x.tau, x.n, t1, eq1), i2 = count_lt(x.tau, x.n, t2, eq2);
-    if (eq1 || eq2 || tau_a == tau_c) { bump(x, C_QNADD); log_end(x, 2); return; }     // process_OperAdd: equal times
+    if (eq1 || eq2 || tau_a == tau_c) { bump(x, C_QNADD); log_end(x, 2); return false; }     // process_OperAdd: equal times
     const int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     const int p1 = count_lt(tc, k, tau_c), p2 = count_lt(ta, k, tau_a);              // FPos-1 (creator row, annihilator column)
     log_set(x, 5, p1 + 1); log_set(x, 6, p2 + 1);
     bump_bytes(x, 64ll * k);
-    // quantum-number check of the changed sub-string + scalar trace ratio
+    // quantum-number check of the changed sub-string (+ scalar trace ratio when every block is 1x1)
     const int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
-    const bool blocked = T.dmax > 1;
     double dlog = 0.0, dsign = 1.0;
     int cur = conn(T, begin_sst, code1), old_after = begin_sst, nother = 0;
     double tl = t1;
     int new_end = -1;
-    if (!blocked) {
+    if (T.dmax == 1) {
         if (cur >= 0) {
-            double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog += log(fabs(e)); if (e < 0) dsign = -dsign;
+            double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog += w_log(fabs(e)); if (e < 0) dsign = -dsign;
             walk_delta(T, x, i1, i2 - i1, f, cur, old_after, tl, dlog, dsign, nother);
         }
         if (cur >= 0) {
             dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
             double e = ldg(&T.elem[cur * T.nops + code2]);
             new_end = conn(T, cur, code2);
-            if (new_end >= 0) { dlog += log(fabs(e)); if (e < 0) dsign = -dsign; }
+            if (new_end >= 0) { dlog += w_log(fabs(e)); if (e < 0) dsign = -dsign; }
         }
     } else {
         if (cur >= 0) cur = walk_check(T, x, i1, i2 - i1, f, cur, nother);
         if (i2 > i1) old_after = (int)x.sst[i2 - 1];
         if (cur >= 0) new_end = conn(T, cur, code2);
     }
-    if (new_end < 0 || new_end != old_after) { bump(x, C_QNADD); log_end(x, 2); return; }
-    // determinant ratio
+    if (new_end < 0 || new_end != old_after) { bump(x, C_QNADD); log_end(x, 2); return false; }
+    if (x.lane == 0) {
+        P.t1 = t1; P.t2 = t2; P.tau_a = tau_a; P.tau_c = tau_c; P.factor = mul_rn(W, w2); P.dlog = dlog; P.dsign = dsign;
+        P.f = f; P.i1 = i1; P.i2 = i2; P.p1 = p1; P.p2 = p2; P.begin_sst = begin_sst; P.nother = nother; P.type1 = a_first ? 1 : 0;
+    }
+    wsync();
+    return true;
+}
+
+// StepAdd part 2 (CTQMC.F90:3470-3612): determinant ratio, local trace, Metropolis, get_MatAdd + list insertion
+W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, const Prop& P) {
+    const int f = P.f, i1 = P.i1, i2 = P.i2, p1 = P.p1, p2 = P.p2, begin_sst = P.begin_sst, nother = P.nother;
+    const double t1 = P.t1, t2 = P.t2, tau_a = P.tau_a, tau_c = P.tau_c;
+    const int code1 = f * 2 + P.type1, code2 = f * 2 + (1 - P.type1);
+    const bool blocked = T.dmax > 1;
+    const int k = x.ih[IH_KF + f];
+    const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+    double dlog = P.dlog, dsign = P.dsign;
     const double S = det_ratio_add(T, C, x, f, tau_c, tau_a);
     bump_bytes(x, 8ll * k * k);
     double tn_log = 0.0, tn_sign = 1.0;
@@ -544,12 +567,12 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
-    const double dr_log = log(fabs(S)), dr_sign = sgn1(S) * sig;
+    const double dr_log = w_log(fabs(S)), dr_sign = sgn1(S) * sig;
     const double rand = x.rng.next();
     // NPairs after insertion (CTQMC.F90:3510-3515)
     if (x.npairs < 0) x.npairs = count_pairs_full(T, R, C, x);
     const int np_new = x.npairs + pairs_with(R, x, ta, k, tau_c) + pairs_with(R, x, tc, k, tau_a) + (pairable(R, x, tau_a, tau_c) ? 1 : 0);
-    const double prob = fabs(taudiff_factor * (double)(2 * T.nb) / (double)np_new * exp(dlog + dr_log));
+    const double prob = fabs(P.factor * (double)(2 * T.nb) / (double)np_new * w_exp(dlog + dr_log));
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, dlog); log_set(x, 10, dsign); log_set(x, 11, prob);
     log_set(x, 14, np_new); log_set(x, 17, rand);
     if (!(rand < prob)) { log_end(x, 0); return; }
@@ -585,13 +608,13 @@ W2B_HDN void step_add(const Tables& T, const Run& R, const Chains& C, const Accu
     log_end(x, 1);
 }
 
-// ------------------------------------------------------------------ StepRem (CTQMC.F90:3892-4150, change_outer = false)
-W2B_HDN void step_rem(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x) {
+// StepRem part 1 (CTQMC.F90:3892-3977): gen_OperRemove (pair choice in the reference's enumeration order), quantum numbers
+W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x, Prop& P) {
     log_begin(x, 2);
     bump(x, C_TRYREM);
     if (x.npairs < 0) x.npairs = count_pairs_full(T, R, C, x);        // gen_OperRemove Trace.F90:4868-4877
     log_set(x, 14, x.npairs);
-    if (x.npairs <= 0) { bump(x, C_QNREM); log_end(x, 2); return; }
+    if (x.npairs <= 0) { bump(x, C_QNREM); log_end(x, 2); return false; }
     const int r = x.rng.randint(1, x.npairs);
     const int ia = count_lt(x.tau, x.n, x.wmin), ib = count_le(x.tau, x.n, x.wmax);
     // enumerate (El, mEl) in the reference's order: El over in-window operators in time order, mEl over later
@@ -626,7 +649,7 @@ W2B_HDN void step_rem(const Tables& T, const Run& R, const Chains& C, const Accu
         }
         cum += total;
     }
-    if (i1 < 0) { x.err |= ERR_PAIR_LOGIC; log_end(x, 2); return; }
+    if (i1 < 0) { x.err |= ERR_PAIR_LOGIC; log_end(x, 2); return false; }
     const int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     const double t2 = (type1 == 0 ? ta : tc)[midx];
@@ -637,31 +660,48 @@ W2B_HDN void step_rem(const Tables& T, const Run& R, const Chains& C, const Accu
     const int i2 = count_lt(x.tau, x.n, t2);
     log_set(x, 2, t1); log_set(x, 3, t2); log_set(x, 4, f); log_set(x, 5, p1 + 1); log_set(x, 6, p2 + 1);
     const double factor = (double)x.npairs / ((x.wmax - x.wmin) * (fmin(tau_an + R.taudiff_max, x.wmax) - fmax(tau_an - R.taudiff_max, x.wmin)));
-    // quantum numbers + scalar trace ratio of the configuration without the pair
+    // quantum numbers (+ scalar trace ratio) of the configuration without the pair
     const int code1 = f * 2 + type1, code2 = f * 2 + (1 - type1);
     const int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
-    const bool blocked = T.dmax > 1;
-    double dlog = 0.0, dsign = 1.0, tn_log = 0.0, tn_sign = 1.0;
+    double dlog = 0.0, dsign = 1.0;
     int cur = begin_sst, old_after = (int)x.sst[i1], nother = 0;
     double tl = t1;
     const int end_sst = (int)x.sst[i2];
-    if (!blocked) {
-        { double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog -= log(fabs(e)); if (e < 0) dsign = -dsign; }
+    if (T.dmax == 1) {
+        { double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog -= w_log(fabs(e)); if (e < 0) dsign = -dsign; }
         walk_delta(T, x, i1 + 1, i2 - i1 - 1, f, cur, old_after, tl, dlog, dsign, nother);
-        if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return; }
+        if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return false; }
         dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
-        { double e = ldg(&T.elem[old_after * T.nops + code2]); dlog -= log(fabs(e)); if (e < 0) dsign = -dsign; }
+        { double e = ldg(&T.elem[old_after * T.nops + code2]); dlog -= w_log(fabs(e)); if (e < 0) dsign = -dsign; }
     } else {
         cur = walk_check(T, x, i1 + 1, i2 - i1 - 1, f, cur, nother);
-        if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return; }
+        if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return false; }
+    }
+    if (x.lane == 0) {
+        P.t1 = t1; P.t2 = t2; P.tau_a = 0.0; P.tau_c = 0.0; P.factor = factor; P.dlog = dlog; P.dsign = dsign;
+        P.f = f; P.i1 = i1; P.i2 = i2; P.p1 = p1; P.p2 = p2; P.begin_sst = begin_sst; P.nother = nother; P.type1 = type1;
+    }
+    wsync();
+    return true;
+}
+
+// StepRem part 2 (CTQMC.F90:3978-4150): ratio = M(p1,p2), local trace, Metropolis, get_MatRem + list removal
+W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, const Prop& P) {
+    const int f = P.f, i1 = P.i1, i2 = P.i2, p1 = P.p1, p2 = P.p2, begin_sst = P.begin_sst, nother = P.nother, type1 = P.type1;
+    const double t1 = P.t1, t2 = P.t2;
+    const bool blocked = T.dmax > 1;
+    const int k = x.ih[IH_KF + f];
+    const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+    double dlog = P.dlog, dsign = P.dsign, tn_log = 0.0, tn_sign = 1.0;
+    if (blocked) {
         seg_trace(T, C, x, i1, i2 + 1, false, 0.0, 0, i1 + 1, i2, false, 0.0, 0, tn_log, tn_sign);
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
     // determinant ratio = M(p1,p2)  (MatrixUpdate.F90:445-452)
     const double S = Mbuf(C, x, f)[(size_t)p1 * C.ld + p2];
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
-    const double dr_log = log(fabs(S)), dr_sign = sgn1(S) * sig;
-    const double prob = fabs(factor / (double)(2 * T.nb) * exp(dlog + dr_log));
+    const double dr_log = w_log(fabs(S)), dr_sign = sgn1(S) * sig;
+    const double prob = fabs(P.factor / (double)(2 * T.nb) * w_exp(dlog + dr_log));
     const double rand = x.rng.next();
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, dlog); log_set(x, 10, dsign); log_set(x, 11, prob); log_set(x, 17, rand);
     if (!(rand < prob)) { log_end(x, 0); return; }
@@ -698,7 +738,7 @@ W2B_HDN void step_rem(const Tables& T, const Run& R, const Chains& C, const Accu
 
 // ------------------------------------------------------------------ full (global) evaluations
 // scalar local trace of a whole configuration given codes/taus/ssts (get_Trace_EB_onlyscalars Trace.F90:5556-5727)
-W2B_HD void trace_full_scalar(const Tables& T, const double* tau, const unsigned char* code, const short* sst, int n, int outer,
+W2B_HDN void trace_full_scalar(const Tables& T, const double* tau, const unsigned char* code, const short* sst, int n, int outer,
                               double& lg, double& sg) {
     double acc = 0.0; int neg = 0;
     for (int i = lane_id(); i < n; i += W2B_WARP) {
@@ -706,7 +746,7 @@ W2B_HD void trace_full_scalar(const Tables& T, const double* tau, const unsigned
         double tp = i == 0 ? 0.0 : tau[i - 1];
         acc += -(ldg(&T.e0[before]) - T.egs) * (tau[i] - tp);
         double e = ldg(&T.elem[before * T.nops + code[i]]);
-        acc += log(fabs(e)); neg += (e < 0.0);
+        acc += w_log(fabs(e)); neg += (e < 0.0);
     }
     double tlast = n > 0 ? tau[n - 1] : 0.0;
     lg = wsum(acc) - (ldg(&T.e0[outer]) - T.egs) * (T.beta - tlast);
@@ -732,7 +772,7 @@ W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, bool want_inverse
         }
         wsync();
         double piv = a[(size_t)c * ld + c];
-        lg += log(fabs(piv)); if (piv < 0) sg = -sg;
+        lg += w_log(fabs(piv)); if (piv < 0) sg = -sg;
         double ipiv = 1.0 / piv;
         wsync();
         if (want_inverse) {
@@ -881,7 +921,7 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
     if (T.dmax > 1) full_trace(T, x, x.tau, x.sc_code, x.n, new_outer, tn_log, tn_sign);
     else trace_full_scalar(T, x.tau, x.sc_code, x.sc_sst, x.n, new_outer, tn_log, tn_sign);
     const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
-    const double prob = fabs(exp(trr_log + dr_log) * factor);
+    const double prob = fabs(w_exp(trr_log + dr_log) * factor);
     const double rand = x.rng.next();
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 17, rand);
     if (!(rand < prob)) { log_end(x, 0); return; }
@@ -942,7 +982,7 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
     if (T.dmax > 1) full_trace(T, x, x.sc_tau, x.sc_code, n, new_outer, tn_log, tn_sign);
     else trace_full_scalar(T, x.sc_tau, x.sc_code, x.sc_sst, n, new_outer, tn_log, tn_sign);
     const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
-    const double prob = fabs(trr_sign * exp(trr_log));
+    const double prob = fabs(trr_sign * w_exp(trr_log));
     const double rand = x.rng.next();
     log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 17, rand);
     if (!(rand < prob)) { x.wpos = wp_old; x.wmin = wmin_old; x.wmax = wmax_old; log_end(x, 0); return; }
@@ -994,29 +1034,8 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
     log_end(x, 1);
 }
 
-// ------------------------------------------------------------------ one Monte-Carlo step (CTQMC.F90:8428-8533)
-W2B_HD void do_step(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, unsigned long long& attempts) {
-    const double r = x.rng.next();
-    if (r < (1.0 - R.pshift - R.pglob) / 2.0) {
-        (void)x.rng.next(); (void)x.rng.next();                   // Percentage4OperatorMove / PercentageOuterMove draws
-        step_add(T, R, C, A, x); ++attempts;
-    } else if (r <= 1.0 - R.pshift - R.pglob) {
-        (void)x.rng.next(); (void)x.rng.next();
-        step_rem(T, R, C, A, x); ++attempts;
-    } else if (r <= 1.0 - R.pshift) step_glob(T, R, C, x);
-    else step_shift(T, R, C, x);
-    if (attempts % (unsigned long long)R.nslide == 0ull) {         // shift_window Trace.F90:1652-1678
-        if (R.num_windows > 1) {
-            x.wpos += 1; if (x.wpos == R.num_windows) x.wpos = 0;
-            set_window_edges(T, R, x);
-            x.npairs = -1;
-        }
-    }
-    if (x.log && x.lane == 0) x.log[16] = x.wpos;
-}
-
 // ------------------------------------------------------------------ chain load / store
-W2B_HD void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, double* wscratch, int* iscratch, double* mscratch) {
+W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, double* wscratch, int* iscratch, double* mscratch) {
     x.lane = lane_id();
     x.tau = C.op_tau + (size_t)chain * C.ops_cap; x.code = C.op_code + (size_t)chain * C.ops_cap; x.sst = C.op_sst + (size_t)chain * C.ops_cap;
     x.sc_tau = C.sc_tau + (size_t)chain * C.ops_cap; x.sc_code = C.sc_code + (size_t)chain * C.ops_cap; x.sc_sst = C.sc_sst + (size_t)chain * C.ops_cap;
@@ -1041,7 +1060,7 @@ W2B_HD void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, 
     set_window_edges(T, R, x);
     x.log = nullptr;
 }
-W2B_HD void ctx_store(const Chains& C, int chain, Ctx& x) {
+W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
     if (x.lane == 0) {
         x.ih[IH_NOPS] = x.n; x.ih[IH_OUTER] = x.outer; x.ih[IH_WPOS] = x.wpos; x.ih[IH_NPAIRS] = x.npairs;
@@ -1053,20 +1072,122 @@ W2B_HD void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
 }
 
-// advance one chain by nsteps moves; logbuf (optional) receives LOGW doubles per move
-W2B_HD void sweep_chain(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain, long long nsteps,
-                        double* wscratch, int* iscratch, double* mscratch, double* logbuf) {
-    Ctx x;
-    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-    unsigned long long attempts = x.cnt[C_TRYADD] + x.cnt[C_TRYREM];
+// ------------------------------------------------------------------ phase scheduler of one CTA (CTQMC.F90:8213-8258, 8428-8533)
+// One CTA advances a batch of `nloc` chains by `nsteps` moves each.  Chains are independent Markov chains, so the order
+// in which *different* chains execute their moves is free; the scheduler uses that freedom to keep all warps of the CTA in
+// the same phase of the algorithm (shared instruction-cache lines, no cross-warp code divergence):
+//   round := schedule (every runnable chain draws its move type, reference thresholds CTQMC.F90:8437-8488)
+//            -> propose (all insertions, then all removals; warps take chains from a shared-memory work list)
+//            -> decide  (determinant ratio, trace, Metropolis, rank-1 update for the proposals that survived)
+//   Global moves and tau-shifts (1 % of the moves, 10-100x the cost) park their chain; parked chains are served together
+//   in a `rare` phase once a warp-load of them has accumulated (or nothing else is runnable).
+// Within a chain the sequence of moves and RNG draws is exactly the reference's.
+struct CtaShared {
+    int nA, nR, nA2, nR2, nG, cA, cR, cA2, cR2, cG;
+    int* left; unsigned char* parked; unsigned char* kind;
+    short* lA; short* lR; short* lA2; short* lR2; short* lG;
+    Prop* prop;
+};
+
+W2B_HDN void finish_move(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, CtaShared& S, int c) {
     wsync();
-    for (long long it = 0; it < nsteps; ++it) {
-        x.log = logbuf ? logbuf + (size_t)it * LOGW : nullptr;
-        do_step(T, R, C, A, x, attempts);
-        wsync();
+    const unsigned long long attempts = x.cnt[C_TRYADD] + x.cnt[C_TRYREM];
+    if (attempts % (unsigned long long)R.nslide == 0ull) {         // shift_window Trace.F90:1652-1678 (checked after EVERY move)
+        if (R.num_windows > 1) {
+            x.wpos += 1; if (x.wpos == R.num_windows) x.wpos = 0;
+            set_window_edges(T, R, x);
+            x.npairs = -1;
+        }
     }
-    if (x.lane == 0) x.cnt[C_STEPS] += (unsigned long long)nsteps;
+    if (x.lane == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; S.left[c] -= 1; }
     ctx_store(C, chain, x);
+}
+
+W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain_lo, int nloc, long long nsteps,
+                      CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf) {
+    const int w = cta_warp(), W = cta_nwarps(), lane = lane_id();
+    for (int c = cta_tid(); c < nloc; c += cta_nthreads()) { S.left[c] = (int)nsteps; S.parked[c] = 0; }
+    if (cta_tid() == 0) { S.nG = 0; S.cG = 0; }
+    cta_sync();
+    const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
+    for (;;) {
+        if (cta_tid() == 0) { S.nA = S.nR = S.nA2 = S.nR2 = 0; S.cA = S.cR = S.cA2 = S.cR2 = 0; }
+        cta_sync();
+        // ---- schedule: move type of every runnable chain (+ the two draws the reference spends on 4-operator / outer moves)
+        for (int c = w; c < nloc; c += W) {
+            if (S.left[c] <= 0 || S.parked[c]) continue;
+            const int chain = chain_lo + c;
+            Philox rng; rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, C.rng_ctr[chain]);
+            const double r = rng.next();
+            int kind;
+            if (r < thr_add) { (void)rng.next(); (void)rng.next(); kind = 1; }
+            else if (r <= thr_rem) { (void)rng.next(); (void)rng.next(); kind = 2; }
+            else kind = r <= thr_glob ? 3 : 4;
+            if (lane == 0) {
+                C.rng_ctr[chain] = rng.ctr; S.kind[c] = (unsigned char)kind;
+                if (kind == 1) S.lA[wgrab_one(&S.nA)] = (short)c;
+                else if (kind == 2) S.lR[wgrab_one(&S.nR)] = (short)c;
+                else { S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
+            }
+        }
+        cta_sync();
+        const int na = S.nA, nr = S.nR;
+        bool rare = false;
+        if (na + nr == 0) {
+            if (S.nG == 0) break;
+            rare = true;
+        } else {
+            // ---- propose
+            for (int i = wgrab(&S.cA); i < na; i = wgrab(&S.cA)) {
+                const int c = S.lA[i], chain = chain_lo + c;
+                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                if (add_propose(T, R, C, x, S.prop[c])) { ctx_store(C, chain, x); if (lane == 0) S.lA2[wgrab_one(&S.nA2)] = (short)c; }
+                else finish_move(T, R, C, chain, x, S, c);
+            }
+            for (int i = wgrab(&S.cR); i < nr; i = wgrab(&S.cR)) {
+                const int c = S.lR[i], chain = chain_lo + c;
+                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                if (rem_propose(T, R, C, x, S.prop[c])) { ctx_store(C, chain, x); if (lane == 0) S.lR2[wgrab_one(&S.nR2)] = (short)c; }
+                else finish_move(T, R, C, chain, x, S, c);
+            }
+            cta_sync();
+            // ---- decide
+            const int na2 = S.nA2, nr2 = S.nR2;
+            for (int i = wgrab(&S.cA2); i < na2; i = wgrab(&S.cA2)) {
+                const int c = S.lA2[i], chain = chain_lo + c;
+                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                add_decide(T, R, C, A, x, S.prop[c]);
+                finish_move(T, R, C, chain, x, S, c);
+            }
+            for (int i = wgrab(&S.cR2); i < nr2; i = wgrab(&S.cR2)) {
+                const int c = S.lR2[i], chain = chain_lo + c;
+                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                rem_decide(T, R, C, A, x, S.prop[c]);
+                finish_move(T, R, C, chain, x, S, c);
+            }
+            cta_sync();
+            rare = S.nG >= W || (S.nG > 0 && na + nr < W);
+        }
+        if (rare) {
+            // ---- rare phase: global moves and tau shifts of all parked chains
+            const int ng = S.nG;
+            for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {
+                const int c = S.lG[i], chain = chain_lo + c;
+                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                if (S.kind[c] == 3) step_glob(T, R, C, x); else step_shift(T, R, C, x);
+                finish_move(T, R, C, chain, x, S, c);
+                if (lane == 0) S.parked[c] = 0;
+            }
+            cta_sync();
+            if (cta_tid() == 0) { S.nG = 0; S.cG = 0; }
+            cta_sync();
+        }
+    }
 }
 
 // init_Trace (Trace.F90:340-701): empty configuration, outer superstate drawn with the empty-trace weights
@@ -1099,7 +1220,7 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     const int m = ldg(&T.dim[x.outer]), off = ldg(&T.offset[x.outer]);
     double csum = 0.0;
     for (int j = x.lane; j < m; j += W2B_WARP) {
-        const double e = x.pt[2 * j + 1] != 0.0 ? exp(x.pt[2 * j]) : 0.0;
+        const double e = x.pt[2 * j + 1] != 0.0 ? w_exp(x.pt[2 * j]) : 0.0;
         atomic_add(&acc[A.o_outerst + off + j], 1.0);
         atomic_add(&acc[A.o_signst + off + j], x.tr_sign * x.pt[2 * j + 1] * x.cfgsign);
         atomic_add(&acc[A.o_contribst + off + j], e);
@@ -1111,7 +1232,7 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     if (x.n == 0) {
         const int doff = ldg(&T.dens_off[x.outer]);
         for (int j = x.lane; j < m; j += W2B_WARP)
-            atomic_add(&acc[A.o_dens + doff + j + j * m], -x.cfgsign * x.pt[2 * j + 1] * x.tr_sign * exp(x.pt[2 * j] - x.tr_log));
+            atomic_add(&acc[A.o_dens + doff + j + j * m], -x.cfgsign * x.pt[2 * j + 1] * x.tr_sign * w_exp(x.pt[2 * j] - x.tr_log));
         return;
     }
     const double bh = T.beta / 2.0;
@@ -1131,11 +1252,11 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     wsync();
     for (int e = x.lane; e < d * m; e += W2B_WARP) {
         const int c = e % d; const double de = ldg(&ev[c]) - e0;
-        K[e] *= exp(-de * (bh - tauR)); B[e] *= exp(-de * (tauL - bh));
+        K[e] *= w_exp(-de * (bh - tauR)); B[e] *= w_exp(-de * (tauL - bh));
     }
     for (int j = x.lane; j < m; j += W2B_WARP) {
         const double kl = klg[j] - (e0 - T.egs) * (bh - tauR), bl = blg[j] - (e0 - T.egs) * (tauL - bh);
-        fac[j] = x.tr_sign * (-x.cfgsign) * exp(kl + bl - x.tr_log);      // 1 / trval(Trace / TLogTr(kl + bl, -cfgsign))
+        fac[j] = x.tr_sign * (-x.cfgsign) * w_exp(kl + bl - x.tr_log);      // 1 / trval(Trace / TLogTr(kl + bl, -cfgsign))
     }
     wsync();
     const int doff = ldg(&T.dens_off[sst]);
@@ -1159,10 +1280,10 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
         atomic_add(&acc[A.o_sign], cfgsign); atomic_add(&acc[A.o_cnt], 1.0);                 // MeasSign 3343
         atomic_add(&acc[A.o_outer + outer], 1.0); atomic_add(&acc[A.o_signsst + outer], cfgsign);   // MeasOuterHistograms 3285-3339
         if (T.dmax == 1) {
-            atomic_add(&acc[A.o_contribsst + outer], exp(dh[DH_TRLOG]));
+            atomic_add(&acc[A.o_contribsst + outer], w_exp(dh[DH_TRLOG]));
             int off = T.offset[outer];
             atomic_add(&acc[A.o_outerst + off], 1.0); atomic_add(&acc[A.o_signst + off], cfgsign);  // Trace.sign*parttrace.sign = 1 for a 1x1 block
-            atomic_add(&acc[A.o_contribst + off], exp(dh[DH_TRLOG]));
+            atomic_add(&acc[A.o_contribst + off], w_exp(dh[DH_TRLOG]));
         }
         for (int f = 0; f < T.nf; ++f) {                                                       // MeasExpOrder 3264-3282
             int k = ih[IH_KF + f]; if (k > R.maxhisto) k = R.maxhisto;

@@ -27,25 +27,25 @@ struct Ctx;
 constexpr double NEG_HUGE = -1.7976931348623157e308;
 
 // X = I_m, log scales 0
-W2B_HD void mat_identity(double* X, double* lg, int m) {
+W2B_HDN void mat_identity(double* X, double* lg, int m) {
     for (int e = lane_id(); e < m * m; e += W2B_WARP) X[e] = (e / m == e % m) ? 1.0 : 0.0;
     for (int j = lane_id(); j < m; j += W2B_WARP) lg[j] = 0.0;
     wsync();
 }
-W2B_HD void mat_copy(double* dst, const double* src, int cnt) {
+W2B_HDN void mat_copy(double* dst, const double* src, int cnt) {
     for (int e = lane_id(); e < cnt; e += W2B_WARP) dst[e] = src[e];
 }
 
-// Y(d_out x m) = O(d_out x d_in) * diag(exp(-(E_c - E_0) dt)) * X(d_in x m); every column is renormalised by its
-// largest element and lg[j] += -(E_0 - Egs) dt + log(max)   (Trace.F90:5802-5822 / split_log 5341-5348).
+// Y(d_out x m) = O(d_out x d_in) * diag(w_exp(-(E_c - E_0) dt)) * X(d_in x m); every column is renormalised by its
+// largest element and lg[j] += -(E_0 - Egs) dt + w_log(max)   (Trace.F90:5802-5822 / split_log 5341-5348).
 // X is overwritten by the propagated input.  Returns the target superstate.
 template <class TablesT>
-W2B_HD int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* X, double* Y, double* lg, int m) {
+W2B_HDN int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* X, double* Y, double* lg, int m) {
     const int d_in = ldg(&T.dim[sst_in]);
     const double* ev = T.evals + ldg(&T.offset[sst_in]);
     const double e0 = ldg(&ev[0]);
     if (d_in > 1) {
-        for (int e = lane_id(); e < d_in * m; e += W2B_WARP) { int c = e % d_in; if (c) X[e] *= exp(-(ldg(&ev[c]) - e0) * dt); }
+        for (int e = lane_id(); e < d_in * m; e += W2B_WARP) { int c = e % d_in; if (c) X[e] *= w_exp(-(ldg(&ev[c]) - e0) * dt); }
         wsync();
     }
     const int sst_out = (int)ldg(&T.connect[sst_in * T.nops + opc]);
@@ -55,6 +55,7 @@ W2B_HD int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* X
         const int r = e % d_out, j = e / d_out;
         const double* xc = X + (size_t)j * d_in;
         double acc = 0.0;
+#pragma unroll 2
         for (int c = 0; c < d_in; ++c) acc += ldg(&O[r + (size_t)c * d_out]) * xc[c];
         Y[e] = acc;
     }
@@ -63,37 +64,44 @@ W2B_HD int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* X
     for (int j = lane_id(); j < m; j += W2B_WARP) {
         double* yc = Y + (size_t)j * d_out;
         double mx = 0.0;
+#pragma unroll 1
         for (int r = 0; r < d_out; ++r) mx = fmax(mx, fabs(yc[r]));
-        if (mx > 0.0) { const double inv = 1.0 / mx; for (int r = 0; r < d_out; ++r) yc[r] *= inv; lg[j] += shift + log(mx); }
+        if (mx > 0.0) { const double inv = 1.0 / mx;
+#pragma unroll 1
+            for (int r = 0; r < d_out; ++r) yc[r] *= inv; lg[j] += shift + w_log(mx); }
     }
     wsync();
     return sst_out;
 }
 
 // Close ket K (block sst, d x m, scales klg) with bra B (same block; nullptr = unit vectors e_j at tau = beta) across a
-// propagation of length dt:  tr_j = sum_c B[c,j] exp(-(E_c-E_0) dt) K[c,j].  pt receives (log, sign) per outer state,
+// propagation of length dt:  tr_j = sum_c B[c,j] w_exp(-(E_c-E_0) dt) K[c,j].  pt receives (log, sign) per outer state,
 // (tlog, tsign) the signed log-sum (addLogTr, Trace.F90:298-309).
 template <class TablesT>
-W2B_HD void mat_close(const TablesT& T, int sst, double dt, const double* K, const double* klg, const double* B, const double* blg,
+W2B_HDN void mat_close(const TablesT& T, int sst, double dt, const double* K, const double* klg, const double* B, const double* blg,
                       int m, double* pt, double& tlog, double& tsign) {
     const int d = ldg(&T.dim[sst]);
     const double* ev = T.evals + ldg(&T.offset[sst]);
     const double e0 = ldg(&ev[0]);
     for (int j = lane_id(); j < m; j += W2B_WARP) {
         double s;
-        if (B) { s = 0.0; for (int c = 0; c < d; ++c) s += B[c + (size_t)j * d] * exp(-(ldg(&ev[c]) - e0) * dt) * K[c + (size_t)j * d]; }
-        else s = exp(-(ldg(&ev[j]) - e0) * dt) * K[j + (size_t)j * d];
-        if (s != 0.0) { pt[2 * j] = klg[j] + (B ? blg[j] : 0.0) - (e0 - T.egs) * dt + log(fabs(s)); pt[2 * j + 1] = s < 0.0 ? -1.0 : 1.0; }
+        if (B) { s = 0.0;
+#pragma unroll 1
+            for (int c = 0; c < d; ++c) s += B[c + (size_t)j * d] * w_exp(-(ldg(&ev[c]) - e0) * dt) * K[c + (size_t)j * d]; }
+        else s = w_exp(-(ldg(&ev[j]) - e0) * dt) * K[j + (size_t)j * d];
+        if (s != 0.0) { pt[2 * j] = klg[j] + (B ? blg[j] : 0.0) - (e0 - T.egs) * dt + w_log(fabs(s)); pt[2 * j + 1] = s < 0.0 ? -1.0 : 1.0; }
         else { pt[2 * j] = NEG_HUGE; pt[2 * j + 1] = 0.0; }
     }
     wsync();
     double mx = NEG_HUGE;
+#pragma unroll 1
     for (int j = 0; j < m; ++j) if (pt[2 * j + 1] != 0.0) mx = fmax(mx, pt[2 * j]);
     if (mx == NEG_HUGE) { tlog = NEG_HUGE; tsign = 0.0; return; }
     double sum = 0.0;
-    for (int j = 0; j < m; ++j) if (pt[2 * j + 1] != 0.0) sum += pt[2 * j + 1] * exp(pt[2 * j] - mx);
+#pragma unroll 1
+    for (int j = 0; j < m; ++j) if (pt[2 * j + 1] != 0.0) sum += pt[2 * j + 1] * w_exp(pt[2 * j] - mx);
     if (sum == 0.0) { tlog = NEG_HUGE; tsign = 0.0; return; }
-    tlog = mx + log(fabs(sum)); tsign = sum < 0.0 ? -1.0 : 1.0;
+    tlog = mx + w_log(fabs(sum)); tsign = sum < 0.0 ? -1.0 : 1.0;
 }
 
 }  // namespace w2b

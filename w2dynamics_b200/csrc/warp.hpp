@@ -83,6 +83,16 @@ W2B_HD int wargmax_abs(double x, int idx, double& best) {
 }
 W2B_HD void atomic_add(double* p, double v) { atomicAdd(p, v); }
 W2B_HD void atomic_add(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+// CTA-level primitives of the phase scheduler
+W2B_HD void cta_sync() { __syncthreads(); }
+W2B_HD int cta_warp() { return threadIdx.x >> 5; }
+W2B_HD int cta_nwarps() { return blockDim.x >> 5; }
+W2B_HD int cta_tid() { return threadIdx.x; }
+W2B_HD int cta_nthreads() { return blockDim.x; }
+// lane 0 takes the next ticket of a shared-memory counter, all lanes get it
+W2B_HD int wgrab(int* ctr) { int v = 0; if ((threadIdx.x & 31) == 0) v = atomicAdd(ctr, 1); return __shfl_sync(W2B_FULL, v, 0); }
+// single-thread ticket (caller is one lane)
+W2B_HD int wgrab_one(int* ctr) { return atomicAdd(ctr, 1); }
 W2B_HD double ldg(const double* p) { return __ldg(p); }
 W2B_HD int ldg(const int* p) { return __ldg(p); }
 W2B_HD short ldg(const short* p) { return __ldg(p); }
@@ -104,11 +114,24 @@ W2B_HD int wscan_incl(int x) { return x; }
 W2B_HD int wargmax_abs(double x, int idx, double& best) { best = std::fabs(x); return idx; }
 W2B_HD void atomic_add(double* p, double v) { *p += v; }
 W2B_HD void atomic_add(unsigned long long* p, unsigned long long v) { *p += v; }
+W2B_HD void cta_sync() {}
+W2B_HD int cta_warp() { return 0; }
+W2B_HD int cta_nwarps() { return 1; }
+W2B_HD int cta_tid() { return 0; }
+W2B_HD int cta_nthreads() { return 1; }
+W2B_HD int wgrab(int* ctr) { return (*ctr)++; }
+W2B_HD int wgrab_one(int* ctr) { return (*ctr)++; }
 W2B_HD double ldg(const double* p) { return *p; }
 W2B_HD int ldg(const int* p) { return *p; }
 W2B_HD short ldg(const short* p) { return *p; }
 W2B_HD long long ldg(const long long* p) { return *p; }
 #endif
+
+// Out-of-line math: log / exp expand to ~50-100 SASS instructions each; one shared copy keeps the hot path inside the
+// 32 KB L1.5 instruction cache (warps of different chains sit at different program counters).
+W2B_HDN double w_log(double x) { return log(x); }
+W2B_HDN double w_exp(double x) { return exp(x); }
+W2B_HDN double wsumd(double x) { return wsum(x); }
 
 // Unfused multiply / add: proposal times must be bit-identical to a CPU evaluation of the reference formulas
 // (nvcc would contract a*b+c into one FMA; times feed exact comparisons and integer bookkeeping).
@@ -129,7 +152,7 @@ struct Philox {
     uint32_t buf[4];
     uint64_t have;
     W2B_HD void init(uint32_t seed, uint32_t chain, uint64_t counter) { k0 = seed; k1 = chain; ctr = counter; have = ~0ull; }
-    W2B_HD void block(uint64_t blk) {
+    W2B_HDN void block(uint64_t blk) {
         uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = 0, c3 = 0, a = k0, b = k1;
         const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
