@@ -179,6 +179,7 @@ def test_blocked_full_size(cuda_engine_factory, cfg, nchains):
     for b in range(p.nbands):
         for s_ in range(2):
             assert abs(occ[b, s_, b, s_] - 0.5) < 0.03
-    assert abs(np.trace(eng.densitymatrix) - 1.0) < 1e-9 and abs(eng.mean_sign) == 1.0
+    # full Coulomb (C4) has a mild sign problem (oracle: <sign> = -0.993 +- 0.004); Kanamori at half filling has none
+    assert abs(np.trace(eng.densitymatrix) - 1.0) < 1e-9 and (abs(eng.mean_sign) == 1.0 if cfg == "C3" else 0.97 < -eng.mean_sign <= 1.0)
     assert eng.scalar("error_flags") == 0
     eng.dest_ctqmc()

@@ -24,6 +24,7 @@ struct Solver {
     long long nmeas_override = -1;
     int device = -1;
     int same_key = 0;
+    int prefetch = 1;
     // derived
     double beta = 0; int nb = 0; long long nmeas = 0; int ncorr = 100;
     double cfg_taudiffmax = -1;
@@ -156,6 +157,7 @@ int w2b_set_option(const char* key, double value) {
     else if (k == "device") S.device = (int)value;
     else if (k == "nmeas_override") S.nmeas_override = (long long)value;
     else if (k == "debug_same_key") S.same_key = (int)value;
+    else if (k == "prefetch") S.prefetch = (int)value;
     else return fail("unknown option " + k);
     return 0;
 }
@@ -190,7 +192,7 @@ int w2b_init_solver(const double* u_matrix, const double* ftau_full, const doubl
         R.has_szt = p.str("QuantumNumbers").find("Szt") != std::string::npos;
         R.meas_dm = p.integer("MeasDensityMatrix") != 0;
         R.nbins = std::max(1, std::min(S.opt.nbins, S.opt.nchains));
-        R.seed = (unsigned)S.seed; R.chain_base = S.opt.chain_base; R.same_key = S.same_key;
+        R.seed = (unsigned)S.seed; R.chain_base = S.opt.chain_base; R.same_key = S.same_key; R.prefetch = S.prefetch;
         // init_window with the configured TaudiffMax, NSlide fixed here (CTQMC.F90:8068-8069)
         if (S.cfg_taudiffmax > 0.0) { R.taudiff_max = S.cfg_taudiffmax; R.num_windows = std::max((int)std::floor(S.beta / S.cfg_taudiffmax) - 1, 1); }
         else { R.taudiff_max = S.beta; R.num_windows = 1; }

@@ -70,7 +70,7 @@ template <class T_> T_* dev_upload(const std::vector<T_>& v) { T_* d = dev_alloc
 
 // ---------------------------------------------------------------- kernels
 constexpr int WARPS_PER_CTA = 4;
-constexpr int MAX_CTA_THREADS = 512;
+constexpr int MAX_CTA_THREADS = 1024;
 // per-warp work space of the blocked trace in doubles: two d x m matrices, column log scales, per-state trace parts
 #if W2B_DEVICE
 __host__ __device__
@@ -294,11 +294,11 @@ public:
         W2B_CUDA_CHECK(cudaGetDevice(&dev));
         W2B_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
         W2B_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        int W = opt.cta_warps > 0 ? opt.cta_warps : 8;
+        int W = opt.cta_warps > 0 ? opt.cta_warps : 16;
         const size_t per_warp = (size_t)wdoubles * sizeof(double);
-        while (W > 1 && W * per_warp + sched_bytes(4 * W) > (size_t)smem_max - 1024) --W;
+        while (W > 1 && W * per_warp + sched_bytes(8 * W) > (size_t)smem_max - 1024) --W;
         if (W > MAX_CTA_THREADS / 32) W = MAX_CTA_THREADS / 32;
-        int target = opt.batch_chains > 0 ? opt.batch_chains : 4 * W;
+        int target = opt.batch_chains > 0 ? opt.batch_chains : 8 * W;
         size_t sm = W * per_warp + sched_bytes(target);
         W2B_CUDA_CHECK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min((size_t)smem_max, sm + 4096)));
         int occ = 1;

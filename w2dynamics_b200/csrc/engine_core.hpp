@@ -61,6 +61,7 @@ struct Run {
     double taudiff_max, pglob, pshift, p4op, pouter;
     int num_windows, nslide, ntau, nlegmax, maxhisto, has_szt, nbins, meas_dm;
     unsigned seed, chain_base;
+    int prefetch;                // software prefetch of the next work item's records (0 = off)
     int same_key;                // diagnostics only: every chain uses chain 0's RNG key (identical control flow across warps)
 };
 
@@ -1089,10 +1090,37 @@ struct CtaShared {
     Prop* prop;
 };
 
-W2B_HDN void finish_move(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, CtaShared& S, int c) {
+// Pull the hot records of the chain a warp will work on next into L1 while it is still busy with the current one:
+// every lane prefetches one 128-byte line (operator times / superstates / codes, scalar state, counters, the first line
+// of each flavour's creator / annihilator times).  For a decide-phase item also the rows of the touched flavour's M.
+W2B_HD void prefetch_chain(const Tables& T, const Chains& C, int chain) {
+#if W2B_DEVICE
+    const int l = lane_id();
+    const char* p = nullptr;
+    if (l < 8) p = (const char*)(C.op_tau + (size_t)chain * C.ops_cap) + l * 128;
+    else if (l < 10) p = (const char*)(C.op_sst + (size_t)chain * C.ops_cap) + (l - 8) * 128;
+    else if (l == 10) p = (const char*)(C.op_code + (size_t)chain * C.ops_cap);
+    else if (l < 13) p = (const char*)(C.ih + (size_t)chain * IH_STRIDE) + (l - 11) * 128;
+    else if (l == 13) p = (const char*)(C.dh + (size_t)chain * DH_STRIDE);
+    else if (l == 14) p = (const char*)(C.counters + (size_t)chain * C_NCNT);
+    else if (l - 15 < 2 * T.nf) { const int f = (l - 15) >> 1; p = (const char*)(((l - 15) & 1 ? C.tau_a : C.tau_c) + ((size_t)chain * T.nf + f) * C.kcap); }
+    if (p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+W2B_HD void prefetch_minv(const Tables& T, const Chains& C, int chain, int f) {
+#if W2B_DEVICE
+    const int* ih = C.ih + (size_t)chain * IH_STRIDE;
+    const int k = ih[IH_KF + f];
+    const char* m = (const char*)(C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld));
+    for (int r = lane_id(); r < k; r += W2B_WARP) asm volatile("prefetch.global.L1 [%0];" ::"l"(m + (size_t)r * C.ld * 8));
+#endif
+}
+
+// bookkeeping after every move: window shift (checked after EVERY move, CTQMC.F90:8255/8531), step counter, quota
+W2B_HDN void post_move(const Tables& T, const Run& R, Ctx& x, CtaShared& S, int c) {
     wsync();
     const unsigned long long attempts = x.cnt[C_TRYADD] + x.cnt[C_TRYREM];
-    if (attempts % (unsigned long long)R.nslide == 0ull) {         // shift_window Trace.F90:1652-1678 (checked after EVERY move)
+    if (attempts % (unsigned long long)R.nslide == 0ull) {         // shift_window Trace.F90:1652-1678
         if (R.num_windows > 1) {
             x.wpos += 1; if (x.wpos == R.num_windows) x.wpos = 0;
             set_window_edges(T, R, x);
@@ -1100,77 +1128,76 @@ W2B_HDN void finish_move(const Tables& T, const Run& R, const Chains& C, int cha
         }
     }
     if (x.lane == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; S.left[c] -= 1; }
-    ctx_store(C, chain, x);
+    wsync();
 }
+
+constexpr int PROPOSE_RUN = 6;      // consecutive moves one chain may take inside a propose phase while they exit early
 
 W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain_lo, int nloc, long long nsteps,
                       CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf) {
-    const int w = cta_warp(), W = cta_nwarps(), lane = lane_id();
+    const int W = cta_nwarps(), lane = lane_id();
     for (int c = cta_tid(); c < nloc; c += cta_nthreads()) { S.left[c] = (int)nsteps; S.parked[c] = 0; }
     if (cta_tid() == 0) { S.nG = 0; S.cG = 0; }
     cta_sync();
     const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
     for (;;) {
-        if (cta_tid() == 0) { S.nA = S.nR = S.nA2 = S.nR2 = 0; S.cA = S.cR = S.cA2 = S.cR2 = 0; }
+        if (cta_tid() == 0) { S.nA = 0; S.nA2 = S.nR2 = 0; S.cA = S.cA2 = S.cR2 = 0; }
         cta_sync();
-        // ---- schedule: move type of every runnable chain (+ the two draws the reference spends on 4-operator / outer moves)
-        for (int c = w; c < nloc; c += W) {
+        // ---- propose phase: every runnable chain draws move types (reference thresholds CTQMC.F90:8437-8488, plus the two
+        //      draws spent on 4-operator / outer moves) and proposes until one proposal survives the quantum-number check
+        for (int c = wgrab(&S.cA), cnext; c < nloc; c = cnext) {
+            cnext = wgrab(&S.cA);
             if (S.left[c] <= 0 || S.parked[c]) continue;
+            if (R.prefetch && cnext < nloc) prefetch_chain(T, C, chain_lo + cnext);
             const int chain = chain_lo + c;
-            Philox rng; rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, C.rng_ctr[chain]);
-            const double r = rng.next();
-            int kind;
-            if (r < thr_add) { (void)rng.next(); (void)rng.next(); kind = 1; }
-            else if (r <= thr_rem) { (void)rng.next(); (void)rng.next(); kind = 2; }
-            else kind = r <= thr_glob ? 3 : 4;
-            if (lane == 0) {
-                C.rng_ctr[chain] = rng.ctr; S.kind[c] = (unsigned char)kind;
-                if (kind == 1) S.lA[wgrab_one(&S.nA)] = (short)c;
-                else if (kind == 2) S.lR[wgrab_one(&S.nR)] = (short)c;
-                else { S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
+            Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+            if (lane == 0) wgrab_one(&S.nA);                              // S.nA counts the chains that were runnable this round
+            for (int run = 0; run < PROPOSE_RUN && S.left[c] > 0; ++run) {
+                const double r = x.rng.next();
+                if (!(r <= thr_rem)) {                                    // global move / tau shift: park for the rare phase
+                    if (lane == 0) { S.kind[c] = (unsigned char)(r <= thr_glob ? 3 : 4); S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
+                    break;
+                }
+                (void)x.rng.next(); (void)x.rng.next();
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                bool go;
+                if (r < thr_add) { go = add_propose(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lA2[wgrab_one(&S.nA2)] = (short)c; }
+                else { go = rem_propose(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lR2[wgrab_one(&S.nR2)] = (short)c; }
+                if (go) break;
+                post_move(T, R, x, S, c);
             }
+            ctx_store(C, chain, x);
         }
         cta_sync();
-        const int na = S.nA, nr = S.nR;
-        bool rare = false;
-        if (na + nr == 0) {
-            if (S.nG == 0) break;
+        bool rare;
+        if (S.nA == 0) {
+            if (S.nG == 0) break;                                         // every chain has used its quota
             rare = true;
         } else {
-            // ---- propose
-            for (int i = wgrab(&S.cA); i < na; i = wgrab(&S.cA)) {
-                const int c = S.lA[i], chain = chain_lo + c;
-                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                if (add_propose(T, R, C, x, S.prop[c])) { ctx_store(C, chain, x); if (lane == 0) S.lA2[wgrab_one(&S.nA2)] = (short)c; }
-                else finish_move(T, R, C, chain, x, S, c);
-            }
-            for (int i = wgrab(&S.cR); i < nr; i = wgrab(&S.cR)) {
-                const int c = S.lR[i], chain = chain_lo + c;
-                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                if (rem_propose(T, R, C, x, S.prop[c])) { ctx_store(C, chain, x); if (lane == 0) S.lR2[wgrab_one(&S.nR2)] = (short)c; }
-                else finish_move(T, R, C, chain, x, S, c);
-            }
-            cta_sync();
-            // ---- decide
+            // ---- decide phase: determinant ratio, trace, Metropolis, rank-1 update
             const int na2 = S.nA2, nr2 = S.nR2;
-            for (int i = wgrab(&S.cA2); i < na2; i = wgrab(&S.cA2)) {
+            for (int i = wgrab(&S.cA2), inext; i < na2; i = inext) {
+                inext = wgrab(&S.cA2);
+                if (R.prefetch && inext < na2) { const int cn = S.lA2[inext]; prefetch_chain(T, C, chain_lo + cn); prefetch_minv(T, C, chain_lo + cn, S.prop[cn].f); }
                 const int c = S.lA2[i], chain = chain_lo + c;
                 Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
                 add_decide(T, R, C, A, x, S.prop[c]);
-                finish_move(T, R, C, chain, x, S, c);
+                post_move(T, R, x, S, c);
+                ctx_store(C, chain, x);
             }
-            for (int i = wgrab(&S.cR2); i < nr2; i = wgrab(&S.cR2)) {
+            for (int i = wgrab(&S.cR2), inext; i < nr2; i = inext) {
+                inext = wgrab(&S.cR2);
+                if (R.prefetch && inext < nr2) prefetch_chain(T, C, chain_lo + S.lR2[inext]);
                 const int c = S.lR2[i], chain = chain_lo + c;
                 Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
                 rem_decide(T, R, C, A, x, S.prop[c]);
-                finish_move(T, R, C, chain, x, S, c);
+                post_move(T, R, x, S, c);
+                ctx_store(C, chain, x);
             }
             cta_sync();
-            rare = S.nG >= W || (S.nG > 0 && na + nr < W);
+            rare = S.nG >= W || (S.nG > 0 && S.nA < W);
         }
         if (rare) {
             // ---- rare phase: global moves and tau shifts of all parked chains
@@ -1180,7 +1207,8 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                 Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
                 if (S.kind[c] == 3) step_glob(T, R, C, x); else step_shift(T, R, C, x);
-                finish_move(T, R, C, chain, x, S, c);
+                post_move(T, R, x, S, c);
+                ctx_store(C, chain, x);
                 if (lane == 0) S.parked[c] = 0;
             }
             cta_sync();
