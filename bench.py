@@ -36,7 +36,7 @@ WORKLOADS = {
     "C4": "C4: 5-orbital d-shell full Slater-Coulomb, beta=20, 1024-state Fock space, 132 blocks d<=28",
     "C5": "C5: 1-band Hubbard, beta=200 (expansion order in the hundreds)",
 }
-DEFAULT_CHAINS = {"C1": 65536, "C2": 16384, "C3": 16384, "C4": 8192, "C5": 4096}
+DEFAULT_CHAINS = {"C1": 65536, "C2": 16384, "C3": 16384, "C4": 8192, "C5": 4096}      # per GPU
 THERMALISE = {"C1": 2000, "C2": 6000, "C3": 6000, "C4": 6000, "C5": 40000}
 METRIC = "QMC moves/sec (box)"
 UNIT = "moves/s"
@@ -204,6 +204,10 @@ def run_engine(args):
     nchains = args.chains or DEFAULT_CHAINS[cfg]
     eng = MCTQMC()
     eng.set_option("nchains", nchains); eng.set_option("nbins", 32); eng.set_option("device", local)
+    if os.environ.get("W2B_CTA_WARPS"):
+        eng.set_option("cta_warps", int(os.environ["W2B_CTA_WARPS"]))
+    if os.environ.get("W2B_BATCH_CHAINS"):
+        eng.set_option("batch_chains", int(os.environ["W2B_BATCH_CHAINS"]))
     if world > 1:
         eng.enable_distributed()
     eng.init_rnd(43890)
@@ -328,7 +332,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default=os.environ.get("W2B_BENCH_CONFIG", "C2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--config", default=os.environ.get("W2B_BENCH_CONFIG", "C4"), choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default per config)")
     ap.add_argument("--thermalise", type=int, default=-1, help="untimed thermalisation moves per chain")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

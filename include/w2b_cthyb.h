@@ -39,7 +39,8 @@ int w2b_init_counters(void);
 int w2b_ctqmc_warmup(long long nwarmups);
 /* ctqmc_measure(isector, icomponent)   CTQMC.F90:8355 ; only the Z sector (1,1) is implemented */
 int w2b_ctqmc_measure(int isector, int icomponent);
-/* ctqmc_calibrate(...)                 CTQMC.F90:8088 ; not implemented yet -> returns an error (use TaudiffMax > 0) */
+/* ctqmc_calibrate(list, phase1pairnum, phase2taugrid, phase2pairnum, nprogress)   CTQMC.F90:8088-8178 ;
+ * outputs through w2b_get_array: "accpairtau" (phase 1) and "accpair" (Nb,2,phase2taugrid; phase 2) */
 int w2b_ctqmc_calibrate(int list, int phase1pairnum, int phase2taugrid, int phase2pairnum, int nprogress);
 /* dest_ctqmc(), dest_paras()           CTQMC.F90:901, 9420 */
 int w2b_dest_ctqmc(void);

@@ -1,0 +1,134 @@
+"""Drop-in boundary test: the reference's OWN, unmodified solver plugin `w2dyn.dmft.cthyb_solver.CtHybSolver`
+(imported from /root/reference) drives the engine through the `mctqmc` surface -- only the module behind
+`from w2dyn.auxiliaries.CTQMC import mctqmc` (cthyb_solver.py:21) is swapped.  mpi4py is absent in this image, so a
+single-rank stub communicator stands in for it.  Runs only where /root/reference exists (this container); uses the
+host-emulation build of the kernel logic on CPU, the CUDA library when a GPU is visible."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "w2dyn")), reason="reference checkout not present")
+
+
+class _Comm:
+    def Get_rank(self): return 0
+    def Get_size(self): return 1
+    def Barrier(self): pass
+    def bcast(self, x, root=0): return x
+    def Allreduce(self, sendbuf, recvbuf, op=None): pass
+    def allgather(self, x): return [x]
+
+
+def _qmc_defaults():
+    """[QMC] section of the reference's configspec with its defaults (configobj is absent here, so a tiny parser)."""
+    import re
+    out, on = {}, False
+    for line in open(os.path.join(REF, "w2dyn", "auxiliaries", "configspec")):
+        line = line.split("#")[0].strip()
+        if line.startswith("["):
+            on = line == "[QMC]"
+            continue
+        m = re.match(r"^(\w+)\s*=\s*(\w+)\((.*)\)$", line)
+        if not (on and m):
+            continue
+        key, typ, args = m.groups()
+        d = re.search(r"default\s*=\s*('[^']*'|\"[^\"]*\"|[^,)]*)", args)
+        val = d.group(1).strip() if d else "None"
+        if val == "None":
+            out[key] = None
+        elif typ == "integer":
+            out[key] = int(val)
+        elif typ == "float":
+            out[key] = float(val)
+        elif typ == "boolean":
+            out[key] = val.strip("'\"") in ("True", "true", "1")
+        else:
+            out[key] = val.strip("'\"")
+    return out
+
+
+def _install_stubs(engine):
+    mpi4py = types.ModuleType("mpi4py")
+    MPI = types.ModuleType("mpi4py.MPI")
+    MPI.IN_PLACE, MPI.SUM, MPI.COMM_WORLD = object(), object(), _Comm()
+    mpi4py.MPI = MPI
+    sys.modules.setdefault("mpi4py", mpi4py)
+    sys.modules.setdefault("mpi4py.MPI", MPI)
+    shim = types.ModuleType("w2dyn.auxiliaries.CTQMC")
+    shim.mctqmc = engine
+    sys.modules["w2dyn.auxiliaries.CTQMC"] = shim
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+
+@pytest.mark.parametrize("taudiffmax", ["fixed", "calibrate"])
+def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
+    import torch
+    from w2dynamics_b200 import problems
+    if torch.cuda.is_available():
+        from w2dynamics_b200.CTQMC import MCTQMC
+        eng = MCTQMC()
+    else:
+        import _hostemu
+        eng = _hostemu.make()
+    eng.set_option("nchains", 16)
+    eng.set_option("nbins", 4)
+    _install_stubs(eng)
+    import w2dyn.dmft.cthyb_solver as cs
+    import w2dyn.dmft.impurity as imp
+    import w2dyn.dmft.interaction as inter
+    import w2dyn.auxiliaries.transform as tf
+
+    p = problems.make_problem("C1", nftau=501)
+    nb, beta, niw = 1, p.beta, 200
+    qmc = _qmc_defaults()                              # every [QMC] key of the reference, at its default
+    assert qmc["NCorr"] == 100 and qmc["Nftau"] == 5000 and "real_ham_tolerance" in qmc
+    qmc.update(Nwarmups=2000, Nmeas=150, NCorr=50, Ntau=200, NLegMax=40, NLegOrder=40, Niw=niw, Nftau=501,
+               TaudiffMax=p.qmc["TaudiffMax"] if taudiffmax == "fixed" else -1.0)   # -1 (the default): ctqmc_calibrate path
+    config = {"QMC": qmc, "General": {"FTType": "legendre", "beta": beta}, "Atoms": {"1": {"Nd": nb}}}
+    iw = tf.matfreq(beta, "fermi", niw)
+    tau = np.linspace(0, beta, 501)
+    fiw, ftau = tf.hybr_from_sites(p.eps_bath, p.v_bath[:, None], iw, tau, beta)       # (nb, nb, niw), (nb, nb, ntau)
+    fiw5 = np.zeros((niw, nb, 2, nb, 2), complex)
+    ftau5 = np.zeros((501, nb, 2, nb, 2))
+    for s in range(2):
+        fiw5[:, 0, s, 0, s] = fiw[0, 0]
+        ftau5[:, 0, s, 0, s] = ftau[0, 0].real
+    muimp = np.zeros((nb, 2, nb, 2))
+    for s in range(2):
+        muimp[0, s, 0, s] = p.mu                       # lattice convention; the plugin negates it (cthyb_solver.py:255)
+    g0inv = np.zeros_like(fiw5)
+    for s in range(2):
+        g0inv[:, 0, s, 0, s] = 1j * iw + p.mu - fiw[0, 0]
+    interaction = inter.Density(nb, 2.0, 0.0, 0.0)
+    interaction.quantum_numbers = ("auto",) + interaction.auto_quantum_numbers        # as config.interaction_from_cfg does (config.py:272)
+    problem = imp.ImpurityProblem(beta, g0inv, fiw5, np.zeros((2, nb, 2, nb, 2)), ftau5, muimp, interaction)
+
+    solver = cs.CtHybSolver(config, 43890, 0, 0, 0, interactive=False, mpi_comm=_Comm())
+    solver_tdm = []
+    orig = eng.set_taudiffmax
+    eng.set_taudiffmax = lambda t: (solver_tdm.append(float(t)), orig(t))[1]
+    solver.set_problem(problem)
+    mc_cfg = []
+    result = solver.solve(0, mc_cfg)
+    if taudiffmax == "calibrate":       # calibrate_taudiff_max (cthyb_solver.py:899-944) ran both phases and set a window
+        assert 0.0 < solver_tdm[0] <= beta
+
+    giw = result.giw.mean()
+    assert giw.shape == (niw, nb, 2, nb, 2) and np.all(np.isfinite(giw))
+    occ = result.other["occ"].mean()
+    assert abs(occ[0, 0, 0, 0] - 0.5) < 0.06 and abs(occ[0, 1, 0, 1] - 0.5) < 0.06       # half filling
+    assert float(result.other["sign"].mean()) == -1.0
+    gtau = result.other["gtau"].mean()
+    assert gtau.shape == (nb, 2, 200) and gtau.min() > 0
+    # G(iw) from the Legendre coefficients: particle-hole symmetric problem -> purely imaginary, negative imaginary part
+    g = giw[niw // 2:niw // 2 + 10, 0, 0, 0, 0]
+    assert np.all(g.imag < 0) and np.abs(g.real).max() < 0.08
+    # ReuseMCConfig hook: the plugin fetched the configuration through get_mc_config
+    assert len(mc_cfg) == 1 and mc_cfg[0].taus.shape == mc_cfg[0].orbs.shape
+    for k in ("w2dyn.auxiliaries.CTQMC", "w2dyn.dmft.cthyb_solver"):
+        sys.modules.pop(k, None)

@@ -20,6 +20,7 @@ for nc in chains:
         if cw: eng.set_option("cta_warps", cw)
         if bc: eng.set_option("batch_chains", bc)
         if os.environ.get("W2B_SAME_KEY"): eng.set_option("debug_same_key", 1)
+        if os.environ.get("W2B_PRUN"): eng.set_option("propose_run", int(os.environ["W2B_PRUN"]))
         if os.environ.get("W2B_PREFETCH"): eng.set_option("prefetch", int(os.environ["W2B_PREFETCH"]))
         eng.init_rnd(43890); eng.init_paras(p.pstring())
         t0 = time.time()

@@ -267,6 +267,11 @@ class MCTQMC:
     def __getattr__(self, name):
         if name.startswith("_"):
             raise AttributeError(name)
+        if name == "accpairtau":
+            return self.array("accpairtau")
+        if name == "accpair" and int(self.scalar("naccpair")) != self._get_dims()["ntau"]:
+            # calibration phase 2 (cthyb_solver.py:914-921): AccPair(Nb, 2, phase2taugrid)
+            return np.asfortranarray(np.rint(self.array("accpair", (self._nb, 2, int(self.scalar("naccpair"))))).astype(np.int64))
         if name in MCTQMC._ARRAYS:
             if name not in self._cache:
                 a = self.array(name, MCTQMC._ARRAYS[name](self._get_dims()))
@@ -275,8 +280,8 @@ class MCTQMC:
                 self._cache[name] = a
             return self._cache[name]
         if name in MCTQMC._SCALARS:
-            v = self.scalar(name)
-            return int(v) if name == "aborted" else v
+            v = self.scalar(name)       # f2py hands module scalars back as 0-d arrays (the caller does `.copy()`, solver.py:1028)
+            return np.int32(v) if name == "aborted" else np.float64(v)
         raise AttributeError(name)
 
     # ------------------------------------------------------------------ parity / bench hooks

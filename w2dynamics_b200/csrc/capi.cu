@@ -25,6 +25,7 @@ struct Solver {
     int device = -1;
     int same_key = 0;
     int prefetch = 1;
+    int propose_run = 4;
     // derived
     double beta = 0; int nb = 0; long long nmeas = 0; int ncorr = 100;
     double cfg_taudiffmax = -1;
@@ -32,6 +33,7 @@ struct Solver {
     ResultSet res; bool have_res = false;
     std::vector<std::vector<double>> bin_gtau, bin_gleg, bin_occ; std::vector<double> bin_sign;
     double time_warmup = 0, time_sim = 0, time_sim_steps = 0;
+    std::vector<double> accpairtau, calib_accpair;     // ctqmc_calibrate outputs
     std::string err;
 };
 Solver S;
@@ -158,6 +160,7 @@ int w2b_set_option(const char* key, double value) {
     else if (k == "nmeas_override") S.nmeas_override = (long long)value;
     else if (k == "debug_same_key") S.same_key = (int)value;
     else if (k == "prefetch") S.prefetch = (int)value;
+    else if (k == "propose_run") S.propose_run = (int)value;
     else return fail("unknown option " + k);
     return 0;
 }
@@ -192,7 +195,7 @@ int w2b_init_solver(const double* u_matrix, const double* ftau_full, const doubl
         R.has_szt = p.str("QuantumNumbers").find("Szt") != std::string::npos;
         R.meas_dm = p.integer("MeasDensityMatrix") != 0;
         R.nbins = std::max(1, std::min(S.opt.nbins, S.opt.nchains));
-        R.seed = (unsigned)S.seed; R.chain_base = S.opt.chain_base; R.same_key = S.same_key; R.prefetch = S.prefetch;
+        R.seed = (unsigned)S.seed; R.chain_base = S.opt.chain_base; R.same_key = S.same_key; R.prefetch = S.prefetch; R.propose_run = S.propose_run > 0 ? S.propose_run : 1;
         // init_window with the configured TaudiffMax, NSlide fixed here (CTQMC.F90:8068-8069)
         if (S.cfg_taudiffmax > 0.0) { R.taudiff_max = S.cfg_taudiffmax; R.num_windows = std::max((int)std::floor(S.beta / S.cfg_taudiffmax) - 1, 1); }
         else { R.taudiff_max = S.beta; R.num_windows = 1; }
@@ -213,6 +216,8 @@ int w2b_ctqmc_warmup(long long nwarmups) {
     return guarded([&] {
         require_engine();
         double t0 = now();
+        S.eng->set_accpair_binning(S.eng->R.ntau, S.beta);              // NAccPair = NGtau, AccPairMax = beta (CTQMC.F90:8203-8204)
+        S.calib_accpair.clear();
         S.eng->reset_counters();
         const long long chunk = 1000;
         for (long long done = 0; done < nwarmups; done += chunk) S.eng->sweep(std::min(chunk, nwarmups - done));
@@ -226,6 +231,8 @@ int w2b_sample(long long nmeas, int reset) {
         require_engine();
         double t0 = now();
         if (reset) S.eng->zero_accum();
+        S.eng->set_accpair_binning(S.eng->R.ntau, S.beta);              // CTQMC.F90:8391-8392
+        S.calib_accpair.clear();
         S.eng->reset_counters();
         run_blocks(nmeas, true);
         S.time_sim += now() - t0;
@@ -241,7 +248,62 @@ int w2b_ctqmc_measure(int isector, int icomponent) {
     return w2b_finalize();
 }
 
-int w2b_ctqmc_calibrate(int, int, int, int, int) { return fail("ctqmc_calibrate is not implemented yet: set TaudiffMax > 0"); }
+// ctqmc_calibrate (CTQMC.F90:8088-8178), driven by CtHybSolver.calibrate_taudiff_max (cthyb_solver.py:899-921).
+// Phase 1 (list): run until phase1pairnum pair moves were accepted; `accpairtau` = their tau distances.  The whole chain
+//   population contributes; the list is reconstructed from the population's histogram (resolution beta / Ntau), which is
+//   all the caller uses (its 99.5 % quantile).
+// Phase 2: histogram of accepted pair distances on [0, taudiff_max] with phase2taugrid bins, until every flavour holds
+//   phase2pairnum entries; the caller fits an exponential.  As in the reference the window is never shifted here.
+int w2b_ctqmc_calibrate(int list, int phase1pairnum, int phase2taugrid, int phase2pairnum, int nprogress) {
+    (void)nprogress;
+    return guarded([&] {
+        require_engine();
+        Engine& E = *S.eng;
+        const int nf = E.T.nf;
+        E.R.freeze_window = 1;
+        std::vector<unsigned long long> ap;
+        auto flavour_sums = [&](std::vector<unsigned long long>& sums) {
+            E.get_accpair(ap); sums.assign(nf, 0ull);
+            for (int f = 0; f < nf; ++f) for (int b = 0; b < E.R.naccpair; ++b) sums[f] += ap[(size_t)f * E.R.naccpair + b];
+        };
+        std::vector<unsigned long long> sums;
+        try {
+            if (list) {
+                E.set_accpair_binning(E.R.ntau, S.beta);
+                unsigned long long tot = 0;
+                for (int it = 0; it < 100000 && tot < (unsigned long long)phase1pairnum; ++it) {
+                    E.sweep(50); flavour_sums(sums); tot = 0; for (auto v : sums) tot += v;
+                    if (it == 99999) throw std::runtime_error("ctqmc_calibrate phase 1: no pair moves are being accepted");
+                }
+                // phase1pairnum evenly spaced quantiles of the pooled histogram
+                std::vector<double> hist(E.R.naccpair, 0.0); double total = 0;
+                for (int f = 0; f < nf; ++f) for (int b = 0; b < E.R.naccpair; ++b) { hist[b] += (double)ap[(size_t)f * E.R.naccpair + b]; total += (double)ap[(size_t)f * E.R.naccpair + b]; }
+                S.accpairtau.assign(phase1pairnum, 0.0);
+                int b = 0; double cum = hist[0];
+                for (int j = 0; j < phase1pairnum; ++j) {
+                    const double target = ((double)j + 0.5) / (double)phase1pairnum * total;
+                    while (cum < target && b + 1 < E.R.naccpair) { ++b; cum += hist[b]; }
+                    S.accpairtau[j] = ((double)b + 1.0) * S.beta / (double)E.R.naccpair;      // upper bin edge (conservative)
+                }
+            } else {
+                E.set_accpair_binning(phase2taugrid, E.R.taudiff_max);
+                for (int it = 0;; ++it) {
+                    E.sweep(50); flavour_sums(sums);
+                    bool done = true; for (auto v : sums) if (v < (unsigned long long)phase2pairnum) done = false;
+                    if (done) break;
+                    if (it == 99999) throw std::runtime_error("ctqmc_calibrate phase 2: a flavour accepts no pair moves");
+                }
+                std::vector<double> out((size_t)nf * phase2taugrid);
+                const int nbd = E.T.nb;
+                for (int bb = 0; bb < nbd; ++bb) for (int s = 0; s < 2; ++s) for (int t = 0; t < phase2taugrid; ++t)
+                    out[bb + (size_t)nbd * (s + 2 * t)] = (double)ap[(size_t)(2 * bb + s) * phase2taugrid + t];
+                S.calib_accpair = out;
+            }
+        } catch (...) { E.R.freeze_window = 0; throw; }
+        E.R.freeze_window = 0;
+        E.sync();
+    });
+}
 
 int w2b_block(long long nsweep, int do_measure) {
     return guarded([&] { require_engine(); S.eng->sweep(nsweep); if (do_measure) S.eng->measure(); });
@@ -366,6 +428,8 @@ int w2b_get_array(const char* name, double* out, size_t cap, size_t* n) {
         std::string k(name);
         const std::vector<double>* src = nullptr; std::vector<double> tmp;
         auto bins = [&](const std::vector<std::vector<double>>& b) { tmp.clear(); for (auto& v : b) tmp.insert(tmp.end(), v.begin(), v.end()); src = &tmp; };
+        if (k == "accpairtau") { src = &S.accpairtau; *n = src->size(); if (out) std::memcpy(out, src->data(), std::min(cap, src->size()) * sizeof(double)); return; }
+        if (k == "accpair" && !S.calib_accpair.empty()) { src = &S.calib_accpair; *n = src->size(); if (out) std::memcpy(out, src->data(), std::min(cap, src->size()) * sizeof(double)); return; }
         if (!S.have_res) throw std::runtime_error("no results: call ctqmc_measure first");
         if (k == "gtau_bins") bins(S.bin_gtau);
         else if (k == "gleg_bins") bins(S.bin_gleg);
@@ -395,6 +459,8 @@ int w2b_get_scalar(const char* name, double* out) {
             if (k == "ops_cap") { *out = E.C.ops_cap; return; }
             if (k == "num_windows") { *out = E.R.num_windows; return; }
             if (k == "nslide") { *out = E.R.nslide; return; }
+            if (k == "naccpair") { *out = E.R.naccpair; return; }
+            if (k == "taudiff_max") { *out = E.R.taudiff_max; return; }
             if (k == "egs") { *out = E.at.egs; return; }
             if (k == "gpu_launches") { *out = (double)E.launches; return; }
             if (k == "cta_warps") { *out = E.sw_warps; return; }

@@ -156,6 +156,7 @@ public:
     long long accum_doubles = 0;       // per bin
     int wdoubles = 0;                  // per-warp scratch in doubles
     long long launches = 0;            // kernels launched (bench accounting)
+    int accpair_cap = 0;
     std::vector<void*> owned;
     std::vector<int> dens_off;         // per block: offset of its d x d slab in the density accumulator
     std::vector<double> ftau_stage;    // host staging of the diagonal hybridisation (w2b_upload_ftau)
@@ -247,7 +248,9 @@ public:
         A.o_sign = o; o += 1; A.o_cnt = o; o += 1;
         accum_doubles = o; A.stride = o;
         A.base = keep(dev_alloc<double>((size_t)R.nbins * o));
-        A.accpair = keep(dev_alloc<unsigned long long>((size_t)nf * R.ntau));
+        accpair_cap = std::max(R.ntau, 1024);
+        A.accpair = keep(dev_alloc<unsigned long long>((size_t)nf * accpair_cap));
+        R.naccpair = R.ntau; R.accpair_max = beta; R.freeze_window = 0;
         init_chains();
     }
 
@@ -281,8 +284,13 @@ public:
 
     void reset_counters() {                    // init_counters CTQMC.F90:847-899
         dev_zero(C.counters, (size_t)C.nchains * C_NCNT);
-        dev_zero(A.accpair, (size_t)T.nf * R.ntau);
+        dev_zero(A.accpair, (size_t)T.nf * accpair_cap);
     }
+    void set_accpair_binning(int n, double range) {
+        if (n > accpair_cap) throw std::runtime_error("accepted-pair histogram: too many bins");
+        R.naccpair = n; R.accpair_max = range; dev_zero(A.accpair, (size_t)T.nf * accpair_cap);
+    }
+    void get_accpair(std::vector<unsigned long long>& out) { sync(); out.resize((size_t)T.nf * R.naccpair); d2h(out.data(), A.accpair, out.size()); }
     void zero_accum() { dev_zero(A.base, (size_t)R.nbins * accum_doubles); }
 
     // sweep-kernel geometry: W warps per CTA, batches of ncb chains, persistent grid
@@ -294,7 +302,7 @@ public:
         W2B_CUDA_CHECK(cudaGetDevice(&dev));
         W2B_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
         W2B_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        int W = opt.cta_warps > 0 ? opt.cta_warps : 16;
+        int W = opt.cta_warps > 0 ? opt.cta_warps : 32;
         const size_t per_warp = (size_t)wdoubles * sizeof(double);
         while (W > 1 && W * per_warp + sched_bytes(8 * W) > (size_t)smem_max - 1024) --W;
         if (W > MAX_CTA_THREADS / 32) W = MAX_CTA_THREADS / 32;
@@ -429,7 +437,7 @@ public:
         sync();
         out.resize((size_t)R.nbins * accum_doubles);
         d2h(out.data(), A.base, out.size());
-        accpair.resize((size_t)T.nf * R.ntau);
+        accpair.resize((size_t)T.nf * R.naccpair);
         d2h(accpair.data(), A.accpair, accpair.size());
     }
 };

@@ -61,6 +61,9 @@ struct Run {
     double taudiff_max, pglob, pshift, p4op, pouter;
     int num_windows, nslide, ntau, nlegmax, maxhisto, has_szt, nbins, meas_dm;
     unsigned seed, chain_base;
+    int naccpair; double accpair_max;   // accepted-pair-distance histogram: bins / range (Ntau, beta; calibration phase 2: grid, taudiff_max)
+    int freeze_window;           // ctqmc_calibrate never shifts the window (CTQMC.F90:8118-8175 has no shift_window call)
+    int propose_run;             // consecutive early-exit moves one chain may take inside one propose phase
     int prefetch;                // software prefetch of the next work item's records (0 = off)
     int same_key;                // diagnostics only: every chain uses chain 0's RNG key (identical control flow across warps)
 };
@@ -603,8 +606,8 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     update_cfgsign(T, x);
     bump(x, C_ACCADD);
     if (x.lane == 0) {
-        int bin = (int)floor((t2 - t1) / T.beta * (double)R.ntau) + 1; if (bin > R.ntau) bin = R.ntau;
-        atomic_add(&A.accpair[(size_t)f * R.ntau + bin - 1], 1ull);
+        int bin = (int)floor((t2 - t1) / R.accpair_max * (double)R.naccpair) + 1; if (bin > R.naccpair) bin = R.naccpair;   // CTQMC.F90:3579-3582
+        atomic_add(&A.accpair[(size_t)f * R.naccpair + bin - 1], 1ull);
     }
     log_end(x, 1);
 }
@@ -731,8 +734,8 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     update_cfgsign(T, x);
     bump(x, C_ACCREM);
     if (x.lane == 0) {
-        int bin = (int)floor((t2 - t1) / T.beta * (double)R.ntau) + 1; if (bin > R.ntau) bin = R.ntau;
-        atomic_add(&A.accpair[(size_t)f * R.ntau + bin - 1], 1ull);
+        int bin = (int)floor((t2 - t1) / R.accpair_max * (double)R.naccpair) + 1; if (bin > R.naccpair) bin = R.naccpair;   // CTQMC.F90:3579-3582
+        atomic_add(&A.accpair[(size_t)f * R.naccpair + bin - 1], 1ull);
     }
     log_end(x, 1);
 }
@@ -1120,7 +1123,7 @@ W2B_HD void prefetch_minv(const Tables& T, const Chains& C, int chain, int f) {
 W2B_HDN void post_move(const Tables& T, const Run& R, Ctx& x, CtaShared& S, int c) {
     wsync();
     const unsigned long long attempts = x.cnt[C_TRYADD] + x.cnt[C_TRYREM];
-    if (attempts % (unsigned long long)R.nslide == 0ull) {         // shift_window Trace.F90:1652-1678
+    if (!R.freeze_window && attempts % (unsigned long long)R.nslide == 0ull) {         // shift_window Trace.F90:1652-1678
         if (R.num_windows > 1) {
             x.wpos += 1; if (x.wpos == R.num_windows) x.wpos = 0;
             set_window_edges(T, R, x);
@@ -1131,7 +1134,6 @@ W2B_HDN void post_move(const Tables& T, const Run& R, Ctx& x, CtaShared& S, int 
     wsync();
 }
 
-constexpr int PROPOSE_RUN = 6;      // consecutive moves one chain may take inside a propose phase while they exit early
 
 W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain_lo, int nloc, long long nsteps,
                       CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf) {
@@ -1152,7 +1154,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
             const int chain = chain_lo + c;
             Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
             if (lane == 0) wgrab_one(&S.nA);                              // S.nA counts the chains that were runnable this round
-            for (int run = 0; run < PROPOSE_RUN && S.left[c] > 0; ++run) {
+            for (int run = 0; run < R.propose_run && S.left[c] > 0; ++run) {
                 const double r = x.rng.next();
                 if (!(r <= thr_rem)) {                                    // global move / tau shift: park for the rare phase
                     if (lane == 0) { S.kind[c] = (unsigned char)(r <= thr_glob ? 3 : 4); S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
@@ -1169,8 +1171,9 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
             ctx_store(C, chain, x);
         }
         cta_sync();
+        const int nrun = S.nA;             // read before thread 0 may reset it at the top of the next round
         bool rare;
-        if (S.nA == 0) {
+        if (nrun == 0) {
             if (S.nG == 0) break;                                         // every chain has used its quota
             rare = true;
         } else {
@@ -1197,7 +1200,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                 ctx_store(C, chain, x);
             }
             cta_sync();
-            rare = S.nG >= W || (S.nG > 0 && S.nA < W);
+            rare = S.nG >= W || (S.nG > 0 && nrun < W);
         }
         if (rare) {
             // ---- rare phase: global moves and tau shifts of all parked chains
