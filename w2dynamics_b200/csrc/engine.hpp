@@ -75,7 +75,7 @@ constexpr int MAX_CTA_THREADS = 1024;
 #if W2B_DEVICE
 __host__ __device__
 #endif
-inline int mat_doubles(const Chains& C) { return C.dmax > 1 ? 2 * C.mstride + 3 * C.dmax : 0; }
+inline int mat_doubles(const Chains& C) { return C.dmax > 1 ? 2 * C.mstride + 4 * C.dmax : 0; }
 
 #if W2B_DEVICE
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_init(Tables T, Run R, Chains C) {
@@ -195,7 +195,9 @@ public:
             ew[k] = w; el[k] = std::log(w); wsum_ += w;
         }
         for (double& w : ew) w /= wsum_;
-        T.connect = keep(dev_upload(conn)); T.e0 = keep(dev_upload(e0)); T.elem = keep(dev_upload(elem));
+        std::vector<double> lelem(elem.size(), 0.0);
+        for (size_t i = 0; i < elem.size(); ++i) if (elem[i] != 0.0) lelem[i] = std::log(std::fabs(elem[i]));
+        T.connect = keep(dev_upload(conn)); T.e0 = keep(dev_upload(e0)); T.elem = keep(dev_upload(elem)); T.lelem = keep(dev_upload(lelem));
         T.ftau = keep(dev_upload(ftau_diag));
         T.first_state = keep(dev_upload(at.first_state)); T.state2sst = keep(dev_upload(at.state2sst));
         T.dim = keep(dev_upload(at.dim)); T.offset = keep(dev_upload(at.offset));

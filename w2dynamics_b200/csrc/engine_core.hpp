@@ -44,6 +44,7 @@ struct Tables {
     const short* connect;        // [nsst*nops]
     const double* e0;            // [nsst] lowest eigenvalue of each block
     const double* elem;          // [nsst*nops] operator element for 1x1 blocks (0 where not connected)
+    const double* lelem;         // [nsst*nops] log|element| (0 where not connected)
     const double* ftau;          // [nf][nftau] diagonal hybridisation, flavour f = 2*band+spin
     const int* first_state;      // [nsst]
     const int* state2sst;        // [nstates]
@@ -99,7 +100,7 @@ struct Ctx {
     double* sc_tau; unsigned char* sc_code; short* sc_sst; double* sc_tc; double* sc_ta;
     double* wQ; double* wR; double* wV; int* wI;
     unsigned short* slot; unsigned short* freel; double* ket; double* bra; double* ketlg; double* bralg; double* pt;
-    double* mX; double* mY; double* mlg; double* mpt;      // per-warp work space of the blocked trace
+    double* mX; double* mY; double* mlg; double* mpt; double* mpw;   // per-warp work space of the blocked trace
     int kv, bv, nfree;
     int n, outer, wpos, npairs, perm, palt, err;
     double det_log, det_sign, tr_log, tr_sign, cfgsign, wmin, wmax;
@@ -139,6 +140,14 @@ W2B_HDN int count_lt(const double* a, int n, double t, bool& eq) {
     return wsum(c);
 }
 W2B_HD int count_lt(const double* a, int n, double t) { bool e; return count_lt(a, n, t, e); }
+// both insertion positions in one pass over the operator times (t1 < t2); eq: some entry equals t1 or t2
+W2B_HDN void count_lt2(const double* a, int n, double t1, double t2, int& c1, int& c2, bool& eq) {
+    int x1 = 0, x2 = 0; bool e = false;
+    for (int i = lane_id(); i < n; i += W2B_WARP) { double v = a[i]; x1 += (v < t1); x2 += (v < t2); e |= (v == t1) | (v == t2); }
+    eq = wany(e);
+    const int packed = wsum(x1 | (x2 << 16));                 // n <= 4096 operators: both counts fit 16 bits
+    c1 = packed & 0xffff; c2 = packed >> 16;
+}
 W2B_HDN int count_le(const double* a, int n, double t) {
     int c = 0;
     for (int i = lane_id(); i < n; i += W2B_WARP) c += (a[i] <= t);
@@ -212,7 +221,7 @@ W2B_HDN void walk_delta(const Tables& T, const Ctx& x, int i0, int m, int f, int
             double tp = (j == 0) ? tl0 : x.tau[i0 + j - 1];
             acc += -(ldg(&T.e0[nb4]) - ldg(&T.e0[ob])) * (tj - tp);
             double en = ldg(&T.elem[nb4 * T.nops + cj]), eo = ldg(&T.elem[ob * T.nops + cj]);
-            if (en != 0.0) { acc += w_log(fabs(en)) - w_log(fabs(eo)); neg += (en < 0.0) != (eo < 0.0); }
+            if (en != 0.0) { acc += ldg(&T.lelem[nb4 * T.nops + cj]) - ldg(&T.lelem[ob * T.nops + cj]); neg += (en < 0.0) != (eo < 0.0); }
             oth += ((cj >> 1) != f);
         }
     }
@@ -302,7 +311,7 @@ W2B_HDN void extend_kets(const Tables& T, const Chains& C, Ctx& x, int upto) {
         wsync();
     }
     for (; i <= upto; ++i) {
-        sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, Y, x.mlg, m);
+        sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, Y, x.mlg, x.mpw, m);
         mat_copy(ket_slot(C, x, i), Y, ldg(&T.dim[sst]) * m);
         mat_copy(x.ketlg + (size_t)x.slot[i] * C.dmax, x.mlg, m);
         tprev = x.tau[i];
@@ -326,7 +335,7 @@ W2B_HDN void extend_bras(const Tables& T, const Chains& C, Ctx& x, int downto) {
         wsync();
     }
     for (i = x.bv - 1; i >= downto; --i) {          // BRA_i = O_i^T P(tau_{i+1} - tau_i) BRA_{i+1}
-        const int sb = mat_apply(T, (int)x.sst[i], (int)x.code[i] ^ 1, tnext - x.tau[i], X, Y, x.mlg, m);
+        const int sb = mat_apply(T, (int)x.sst[i], (int)x.code[i] ^ 1, tnext - x.tau[i], X, Y, x.mlg, x.mpw, m);
         mat_copy(bra_slot(C, x, i), Y, ldg(&T.dim[sb]) * m);
         mat_copy(x.bralg + (size_t)x.slot[i] * C.dmax, x.mlg, m);
         tnext = x.tau[i];
@@ -352,14 +361,14 @@ W2B_HDN void seg_trace(const Tables& T, const Chains& C, Ctx& x, int s, int e, b
         mat_copy(x.mlg, x.ketlg + (size_t)x.slot[s - 1] * C.dmax, m);
         wsync();
     }
-    if (hasA) { sst = mat_apply(T, sst, codeA, tA - tprev, X, Y, x.mlg, m); tprev = tA; double* t = X; X = Y; Y = t; }
+    if (hasA) { sst = mat_apply(T, sst, codeA, tA - tprev, X, Y, x.mlg, x.mpw, m); tprev = tA; double* t = X; X = Y; Y = t; }
     for (int i = lo; i < hi; ++i) {
-        sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, Y, x.mlg, m); tprev = x.tau[i];
+        sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, Y, x.mlg, x.mpw, m); tprev = x.tau[i];
         double* t = X; X = Y; Y = t;
     }
-    if (hasB) { sst = mat_apply(T, sst, codeB, tB - tprev, X, Y, x.mlg, m); tprev = tB; double* t = X; X = Y; Y = t; }
-    if (e == x.n) mat_close(T, sst, T.beta - tprev, X, x.mlg, (const double*)nullptr, (const double*)nullptr, m, x.mpt, tlog, tsign);
-    else mat_close(T, sst, x.tau[e] - tprev, X, x.mlg, bra_slot(C, x, e), x.bralg + (size_t)x.slot[e] * C.dmax, m, x.mpt, tlog, tsign);
+    if (hasB) { sst = mat_apply(T, sst, codeB, tB - tprev, X, Y, x.mlg, x.mpw, m); tprev = tB; double* t = X; X = Y; Y = t; }
+    if (e == x.n) mat_close(T, sst, T.beta - tprev, X, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
+    else mat_close(T, sst, x.tau[e] - tprev, X, x.mlg, bra_slot(C, x, e), x.bralg + (size_t)x.slot[e] * C.dmax, x.mpw, m, x.mpt, tlog, tsign);
 }
 
 // from-scratch trace of an arbitrary sequence (global moves, tau shifts, set_mc_config); no caches touched
@@ -369,10 +378,10 @@ W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsign
     mat_identity(X, x.mlg, m);
     int sst = outer; double tprev = 0.0;
     for (int i = 0; i < n; ++i) {
-        sst = mat_apply(T, sst, (int)code[i], tau[i] - tprev, X, Y, x.mlg, m); tprev = tau[i];
+        sst = mat_apply(T, sst, (int)code[i], tau[i] - tprev, X, Y, x.mlg, x.mpw, m); tprev = tau[i];
         double* t = X; X = Y; Y = t;
     }
-    mat_close(T, sst, T.beta - tprev, X, x.mlg, (const double*)nullptr, (const double*)nullptr, m, x.mpt, tlog, tsign);
+    mat_close(T, sst, T.beta - tprev, X, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
 }
 // trace contributions of the outer states of an empty configuration: w_exp(-(E_j - Egs) beta)
 W2B_HD void empty_parts(const Tables& T, Ctx& x, int outer) {
@@ -515,9 +524,9 @@ W2B_HDN bool add_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     const double t1 = a_first ? tau_a : tau_c, t2 = a_first ? tau_c : tau_a;
     const int code1 = f * 2 + (a_first ? 1 : 0), code2 = f * 2 + (a_first ? 0 : 1);
     log_set(x, 4, f); log_set(x, 2, t1); log_set(x, 3, t2);
-    bool eq1, eq2;
-    const int i1 = count_lt(x.tau, x.n, t1, eq1), i2 = count_lt(x.tau, x.n, t2, eq2);
-    if (eq1 || eq2 || tau_a == tau_c) { bump(x, C_QNADD); log_end(x, 2); return false; }     // process_OperAdd: equal times
+    bool eq12; int i1, i2;
+    count_lt2(x.tau, x.n, t1, t2, i1, i2, eq12);
+    if (eq12 || tau_a == tau_c) { bump(x, C_QNADD); log_end(x, 2); return false; }     // process_OperAdd: equal times
     const int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     const int p1 = count_lt(tc, k, tau_c), p2 = count_lt(ta, k, tau_a);              // FPos-1 (creator row, annihilator column)
@@ -531,14 +540,14 @@ W2B_HDN bool add_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     int new_end = -1;
     if (T.dmax == 1) {
         if (cur >= 0) {
-            double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog += w_log(fabs(e)); if (e < 0) dsign = -dsign;
+            double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog += ldg(&T.lelem[begin_sst * T.nops + code1]); if (e < 0) dsign = -dsign;
             walk_delta(T, x, i1, i2 - i1, f, cur, old_after, tl, dlog, dsign, nother);
         }
         if (cur >= 0) {
             dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
             double e = ldg(&T.elem[cur * T.nops + code2]);
             new_end = conn(T, cur, code2);
-            if (new_end >= 0) { dlog += w_log(fabs(e)); if (e < 0) dsign = -dsign; }
+            if (new_end >= 0) { dlog += ldg(&T.lelem[cur * T.nops + code2]); if (e < 0) dsign = -dsign; }
         }
     } else {
         if (cur >= 0) cur = walk_check(T, x, i1, i2 - i1, f, cur, nother);
@@ -672,11 +681,11 @@ W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     double tl = t1;
     const int end_sst = (int)x.sst[i2];
     if (T.dmax == 1) {
-        { double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog -= w_log(fabs(e)); if (e < 0) dsign = -dsign; }
+        { double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog -= ldg(&T.lelem[begin_sst * T.nops + code1]); if (e < 0) dsign = -dsign; }
         walk_delta(T, x, i1 + 1, i2 - i1 - 1, f, cur, old_after, tl, dlog, dsign, nother);
         if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return false; }
         dlog += -(ldg(&T.e0[cur]) - ldg(&T.e0[old_after])) * (t2 - tl);
-        { double e = ldg(&T.elem[old_after * T.nops + code2]); dlog -= w_log(fabs(e)); if (e < 0) dsign = -dsign; }
+        { double e = ldg(&T.elem[old_after * T.nops + code2]); dlog -= ldg(&T.lelem[old_after * T.nops + code2]); if (e < 0) dsign = -dsign; }
     } else {
         cur = walk_check(T, x, i1 + 1, i2 - i1 - 1, f, cur, nother);
         if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return false; }
@@ -750,7 +759,7 @@ W2B_HDN void trace_full_scalar(const Tables& T, const double* tau, const unsigne
         double tp = i == 0 ? 0.0 : tau[i - 1];
         acc += -(ldg(&T.e0[before]) - T.egs) * (tau[i] - tp);
         double e = ldg(&T.elem[before * T.nops + code[i]]);
-        acc += w_log(fabs(e)); neg += (e < 0.0);
+        acc += ldg(&T.lelem[before * T.nops + code[i]]); neg += (e < 0.0);
     }
     double tlast = n > 0 ? tau[n - 1] : 0.0;
     lg = wsum(acc) - (ldg(&T.e0[outer]) - T.egs) * (T.beta - tlast);
@@ -897,7 +906,7 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
     }
     if (factor == 0.0) { bump(x, C_QNGLOB); log_end(x, 2); return; }
     long long sumk2 = 0; for (int f = 0; f < nf; ++f) sumk2 += (long long)x.ih[IH_KF + f] * x.ih[IH_KF + f];
-    bump_bytes(x, 24ll * sumk2);                  // build Delta_new (write), read the stored inverses, write their LU copy
+    bump_bytes(x, 8ll * sumk2);                   // build Delta_new (write)
     // relabelled flavour tau arrays and orders
     int* knew = x.wI + C.kcap + 16;
     for (int f = 0; f < nf; ++f) {
@@ -909,18 +918,12 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
         for (int i = x.lane; i < k; i += W2B_WARP) { nc[i] = flip ? oa[i] : oc[i]; na[i] = flip ? oc[i] : oa[i]; }
     }
     wsync();
-    // determinant of the new configuration from scratch (spare buffer) and of the stored inverses (get_FullLogDet)
-    double dn_log, dn_sign, do_log = 0.0, do_sign = 1.0;
+    // determinant of the new configuration from scratch (LU in the spare buffer).  The reference obtains the old determinant
+    // from an LU of the stored inverses (get_FullLogDet, Trace.F90:2665-2685); the tracked Det is the same number up to the
+    // rounding of the fast updates (pinned by the from-scratch tests), so the second LU is not repeated here.
+    double dn_log, dn_sign;
     rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, knew, false, dn_log, dn_sign);
-    for (int f = 0; f < nf; ++f) {
-        int k = x.ih[IH_KF + f]; if (k == 0) continue;
-        const double* src = Mbuf(C, x, f); double* sp = Mbuf(C, x, nf);
-        for (int i = 0; i < k; ++i) for (int j = x.lane; j < k; j += W2B_WARP) sp[(size_t)i * C.ld + j] = src[(size_t)i * C.ld + j];
-        wsync();
-        double l, s; invert_inplace(sp, k, C.ld, x.wI, false, l, s);
-        do_log += l; do_sign *= s;
-    }
-    const double dr_log = dn_log + do_log, dr_sign = dn_sign * do_sign;
+    const double dr_log = dn_log - x.det_log, dr_sign = dn_sign * x.det_sign;
     double tn_log, tn_sign;
     if (T.dmax > 1) full_trace(T, x, x.tau, x.sc_code, x.n, new_outer, tn_log, tn_sign);
     else trace_full_scalar(T, x.tau, x.sc_code, x.sc_sst, x.n, new_outer, tn_log, tn_sign);
@@ -1054,7 +1057,7 @@ W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain,
         x.ket = C.ket + (size_t)chain * C.ops_cap * C.mstride; x.bra = C.bra + (size_t)chain * C.ops_cap * C.mstride;
         x.ketlg = C.ketlg + (size_t)chain * C.ops_cap * C.dmax; x.bralg = C.bralg + (size_t)chain * C.ops_cap * C.dmax;
         x.pt = C.pt + (size_t)chain * 2 * C.dmax;
-        x.mX = mscratch; x.mY = mscratch + C.mstride; x.mlg = mscratch + 2 * C.mstride; x.mpt = x.mlg + C.dmax;
+        x.mX = mscratch; x.mY = mscratch + C.mstride; x.mlg = mscratch + 2 * C.mstride; x.mpt = x.mlg + C.dmax; x.mpw = x.mpt + 2 * C.dmax;
         x.kv = x.ih[IH_KV]; x.bv = x.ih[IH_BV]; x.nfree = x.ih[IH_NFREE];
     }
     x.n = x.ih[IH_NOPS]; x.outer = x.ih[IH_OUTER]; x.wpos = x.ih[IH_WPOS]; x.npairs = x.ih[IH_NPAIRS];
@@ -1087,7 +1090,7 @@ W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
 //   in a `rare` phase once a warp-load of them has accumulated (or nothing else is runnable).
 // Within a chain the sequence of moves and RNG draws is exactly the reference's.
 struct CtaShared {
-    int nA, nR, nA2, nR2, nG, cA, cR, cA2, cR2, cG;
+    int nA, nR, nA2, nR2, nG, cA, cR, cA2, cR2, cG, cA2h, cR2h;
     int* left; unsigned char* parked; unsigned char* kind;
     short* lA; short* lR; short* lA2; short* lR2; short* lG;
     Prop* prop;
@@ -1143,7 +1146,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
     cta_sync();
     const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
     for (;;) {
-        if (cta_tid() == 0) { S.nA = 0; S.nA2 = S.nR2 = 0; S.cA = S.cA2 = S.cR2 = 0; }
+        if (cta_tid() == 0) { S.nA = 0; S.nA2 = S.nR2 = 0; S.cA = S.cA2 = S.cR2 = S.cA2h = S.cR2h = 0; }
         cta_sync();
         // ---- propose phase: every runnable chain draws move types (reference thresholds CTQMC.F90:8437-8488, plus the two
         //      draws spent on 4-operator / outer moves) and proposes until one proposal survives the quantum-number check
@@ -1160,7 +1163,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                     if (lane == 0) { S.kind[c] = (unsigned char)(r <= thr_glob ? 3 : 4); S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
                     break;
                 }
-                (void)x.rng.next(); (void)x.rng.next();
+                x.rng.skip(2);                                            // Percentage4OperatorMove / PercentageOuterMove draws (both 0)
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
                 bool go;
                 if (r < thr_add) { go = add_propose(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lA2[wgrab_one(&S.nA2)] = (short)c; }
@@ -1179,25 +1182,28 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
         } else {
             // ---- decide phase: determinant ratio, trace, Metropolis, rank-1 update
             const int na2 = S.nA2, nr2 = S.nR2;
-            for (int i = wgrab(&S.cA2), inext; i < na2; i = inext) {
-                inext = wgrab(&S.cA2);
-                if (R.prefetch && inext < na2) { const int cn = S.lA2[inext]; prefetch_chain(T, C, chain_lo + cn); prefetch_minv(T, C, chain_lo + cn, S.prop[cn].f); }
-                const int c = S.lA2[i], chain = chain_lo + c;
-                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                add_decide(T, R, C, A, x, S.prop[c]);
-                post_move(T, R, x, S, c);
-                ctx_store(C, chain, x);
-            }
-            for (int i = wgrab(&S.cR2), inext; i < nr2; i = inext) {
-                inext = wgrab(&S.cR2);
-                if (R.prefetch && inext < nr2) prefetch_chain(T, C, chain_lo + S.lR2[inext]);
-                const int c = S.lR2[i], chain = chain_lo + c;
-                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                rem_decide(T, R, C, A, x, S.prop[c]);
-                post_move(T, R, x, S, c);
-                ctx_store(C, chain, x);
+            // blocked traces: chains whose outer block is larger than 1x1 cost 10-100x more -> serve them first (longest
+            // processing time first keeps the tail of the phase short); pass 0 = heavy, pass 1 = the rest
+            for (int pass = (T.dmax > 1 ? 0 : 1); pass < 2; ++pass) {
+                int* curA = pass == 0 ? &S.cA2h : &S.cA2; int* curR = pass == 0 ? &S.cR2h : &S.cR2;
+                for (int i = wgrab(curA); i < na2; i = wgrab(curA)) {
+                    const int c = S.lA2[i], chain = chain_lo + c;
+                    if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
+                    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                    if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                    add_decide(T, R, C, A, x, S.prop[c]);
+                    post_move(T, R, x, S, c);
+                    ctx_store(C, chain, x);
+                }
+                for (int i = wgrab(curR); i < nr2; i = wgrab(curR)) {
+                    const int c = S.lR2[i], chain = chain_lo + c;
+                    if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
+                    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                    if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                    rem_decide(T, R, C, A, x, S.prop[c]);
+                    post_move(T, R, x, S, c);
+                    ctx_store(C, chain, x);
+                }
             }
             cta_sync();
             rare = S.nG >= W || (S.nG > 0 && nrun < W);
@@ -1244,7 +1250,7 @@ W2B_HD void init_chain(const Tables& T, const Run& R, const Chains& C, int chain
 }
 
 // ------------------------------------------------------------------ measurement (CTQMC.F90:8541-8581)
-constexpr int LEG_CHUNK = 20;
+constexpr int LEG_CHUNK = 25;
 // blocked-trace part of one measurement: per-state histograms (MeasOuterHistograms CTQMC.F90:3285-3339) and the density
 // matrix at beta/2 (update_b2_states_eb Trace.F90:6213-6469 + MeasDensityMatrix_beta_half CTQMC.F90:3088-3151)
 W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, double* acc) {
@@ -1342,10 +1348,9 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
         const double* tc = C.tau_c + ((size_t)chain * T.nf + f) * C.kcap; const double* ta = C.tau_a + ((size_t)chain * T.nf + f) * C.kcap;
         const double* M = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
         for (int lbase = 0; lbase < R.nlegmax; lbase += LEG_CHUNK) {
-            double part[LEG_CHUNK];
+            double part[LEG_CHUNK];                       // statically indexed below -> registers
 #pragma unroll
             for (int q = 0; q < LEG_CHUNK; ++q) part[q] = 0.0;
-            const int lend = lbase + LEG_CHUNK < R.nlegmax ? lbase + LEG_CHUNK : R.nlegmax;
             for (int p = lane; p < k * k; p += W2B_WARP) {
                 int ic = p / k, ia = p - ic * k;
                 double Mv = M[(size_t)ic * C.ld + ia];
@@ -1354,11 +1359,20 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
                 else { idt = (int)((beta + dtau) / beta * (double)R.ntau) + 1; xx = 2.0 / beta * (beta + dtau) - 1.0; Mv = -Mv; }
                 Mv *= cfgsign;
                 if (lbase == 0) { if (idt > R.ntau) idt = R.ntau; atomic_add(&acc[A.o_gtau + f * R.ntau + idt - 1], Mv); }
+                // three-term recurrence (CTQMC.F90:2407-2420): advance to l = lbase, then accumulate LEG_CHUNK terms
                 double Plx = 0.0, Plm1 = 0.0, Pl = 0.0;
-                for (int l = 0; l < lend; ++l) {
+#pragma unroll 1
+                for (int l = 0; l < lbase; ++l) {
                     if (l == 0) Pl = 1.0; else if (l == 1) Pl = xx;
                     else { int ll = l - 1; Pl = (2.0 * ll + 1.0) / (double)(ll + 1) * xx * Plx - (double)ll / (double)(ll + 1) * Plm1; }
-                    if (l >= lbase) part[l - lbase] += Mv * Pl;
+                    Plm1 = Plx; Plx = Pl;
+                }
+#pragma unroll
+                for (int q = 0; q < LEG_CHUNK; ++q) {
+                    const int l = lbase + q;
+                    if (l == 0) Pl = 1.0; else if (l == 1) Pl = xx;
+                    else { int ll = l - 1; Pl = (2.0 * ll + 1.0) / (double)(ll + 1) * xx * Plx - (double)ll / (double)(ll + 1) * Plm1; }
+                    part[q] += Mv * Pl;
                     Plm1 = Plx; Plx = Pl;
                 }
             }

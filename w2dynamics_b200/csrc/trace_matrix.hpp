@@ -36,63 +36,96 @@ W2B_HDN void mat_copy(double* dst, const double* src, int cnt) {
     for (int e = lane_id(); e < cnt; e += W2B_WARP) dst[e] = src[e];
 }
 
-// Y(d_out x m) = O(d_out x d_in) * diag(w_exp(-(E_c - E_0) dt)) * X(d_in x m); every column is renormalised by its
-// largest element and lg[j] += -(E_0 - Egs) dt + w_log(max)   (Trace.F90:5802-5822 / split_log 5341-5348).
-// X is overwritten by the propagated input.  Returns the target superstate.
+// Y(d_out x m) = O(d_out x d_in) * diag(exp(-(E_c - E_0) dt)) * X(d_in x m); every column is renormalised by a power
+// of two near its largest element and lg[j] += -(E_0 - Egs) dt + e ln2   (the reference divides by the largest element and
+// adds its log, Trace.F90:5802-5822 / split_log 5341-5348; a power of two is exact and needs no log()).
+// `pw` is warp scratch for the d_in propagation factors.  X is overwritten by the propagated input.  Returns the target block.
+constexpr double LN2 = 0.6931471805599453094;
+W2B_HD double renorm_pow2(double mx, double& lgadd) {          // returns the scale 2^-e, e = exponent of mx
+    int e;
+#if W2B_DEVICE
+    e = ilogb(mx);
+    lgadd = (double)e * LN2;
+    return scalbn(1.0, -e);
+#else
+    e = std::ilogb(mx);
+    lgadd = (double)e * LN2;
+    return std::scalbn(1.0, -e);
+#endif
+}
+
 template <class TablesT>
-W2B_HDN int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* X, double* Y, double* lg, int m) {
+W2B_HDN int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* X, double* Y, double* lg, double* pw, int m) {
     const int d_in = ldg(&T.dim[sst_in]);
     const double* ev = T.evals + ldg(&T.offset[sst_in]);
     const double e0 = ldg(&ev[0]);
-    if (d_in > 1) {
-        for (int e = lane_id(); e < d_in * m; e += W2B_WARP) { int c = e % d_in; if (c) X[e] *= w_exp(-(ldg(&ev[c]) - e0) * dt); }
-        wsync();
-    }
     const int sst_out = (int)ldg(&T.connect[sst_in * T.nops + opc]);
     const int d_out = ldg(&T.dim[sst_out]);
     const double* O = T.opdata + ldg(&T.op_off[(size_t)sst_in * T.nops + opc]);
+    const double shift = -(e0 - T.egs) * dt;
+    if (d_in == 1 && d_out == 1) {                               // scalar link of the chain: one multiply per outer state
+        const double o = ldg(&O[0]);
+        for (int j = lane_id(); j < m; j += W2B_WARP) {
+            const double y = o * X[j];
+            if (y != 0.0) { double la; const double sc = renorm_pow2(fabs(y), la); Y[j] = y * sc; lg[j] += shift + la; }
+            else Y[j] = 0.0;
+        }
+        wsync();
+        return sst_out;
+    }
+    if (d_in > 1) {
+        for (int c = lane_id(); c < d_in; c += W2B_WARP) pw[c] = c ? w_exp(-(ldg(&ev[c]) - e0) * dt) : 1.0;
+        wsync();
+    }
     for (int e = lane_id(); e < d_out * m; e += W2B_WARP) {
-        const int r = e % d_out, j = e / d_out;
+        const int j = e / d_out, r = e - j * d_out;
         const double* xc = X + (size_t)j * d_in;
         double acc = 0.0;
+        if (d_in > 1) {
 #pragma unroll 2
-        for (int c = 0; c < d_in; ++c) acc += ldg(&O[r + (size_t)c * d_out]) * xc[c];
+            for (int c = 0; c < d_in; ++c) acc += ldg(&O[r + (size_t)c * d_out]) * (pw[c] * xc[c]);
+        } else acc = ldg(&O[r]) * xc[0];
         Y[e] = acc;
     }
     wsync();
-    const double shift = -(e0 - T.egs) * dt;
     for (int j = lane_id(); j < m; j += W2B_WARP) {
         double* yc = Y + (size_t)j * d_out;
         double mx = 0.0;
 #pragma unroll 1
         for (int r = 0; r < d_out; ++r) mx = fmax(mx, fabs(yc[r]));
-        if (mx > 0.0) { const double inv = 1.0 / mx;
+        if (mx > 0.0) {
+            double la; const double sc = renorm_pow2(mx, la);
 #pragma unroll 1
-            for (int r = 0; r < d_out; ++r) yc[r] *= inv; lg[j] += shift + w_log(mx); }
+            for (int r = 0; r < d_out; ++r) yc[r] *= sc;
+            lg[j] += shift + la;
+        }
     }
     wsync();
     return sst_out;
 }
 
 // Close ket K (block sst, d x m, scales klg) with bra B (same block; nullptr = unit vectors e_j at tau = beta) across a
-// propagation of length dt:  tr_j = sum_c B[c,j] w_exp(-(E_c-E_0) dt) K[c,j].  pt receives (log, sign) per outer state,
+// propagation of length dt:  tr_j = sum_c B[c,j] exp(-(E_c-E_0) dt) K[c,j].  pt receives (log, sign) per outer state,
 // (tlog, tsign) the signed log-sum (addLogTr, Trace.F90:298-309).
 template <class TablesT>
 W2B_HDN void mat_close(const TablesT& T, int sst, double dt, const double* K, const double* klg, const double* B, const double* blg,
-                      int m, double* pt, double& tlog, double& tsign) {
+                      double* pw, int m, double* pt, double& tlog, double& tsign) {
     const int d = ldg(&T.dim[sst]);
     const double* ev = T.evals + ldg(&T.offset[sst]);
     const double e0 = ldg(&ev[0]);
+    for (int c = lane_id(); c < d; c += W2B_WARP) pw[c] = c ? w_exp(-(ldg(&ev[c]) - e0) * dt) : 1.0;
+    wsync();
     for (int j = lane_id(); j < m; j += W2B_WARP) {
         double s;
         if (B) { s = 0.0;
 #pragma unroll 1
-            for (int c = 0; c < d; ++c) s += B[c + (size_t)j * d] * w_exp(-(ldg(&ev[c]) - e0) * dt) * K[c + (size_t)j * d]; }
-        else s = w_exp(-(ldg(&ev[j]) - e0) * dt) * K[j + (size_t)j * d];
+            for (int c = 0; c < d; ++c) s += B[c + (size_t)j * d] * pw[c] * K[c + (size_t)j * d]; }
+        else s = pw[j] * K[j + (size_t)j * d];
         if (s != 0.0) { pt[2 * j] = klg[j] + (B ? blg[j] : 0.0) - (e0 - T.egs) * dt + w_log(fabs(s)); pt[2 * j + 1] = s < 0.0 ? -1.0 : 1.0; }
         else { pt[2 * j] = NEG_HUGE; pt[2 * j + 1] = 0.0; }
     }
     wsync();
+    if (m == 1) { tlog = pt[0]; tsign = pt[1]; return; }
     double mx = NEG_HUGE;
 #pragma unroll 1
     for (int j = 0; j < m; ++j) if (pt[2 * j + 1] != 0.0) mx = fmax(mx, pt[2 * j]);

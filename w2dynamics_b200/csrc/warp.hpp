@@ -171,6 +171,7 @@ struct Philox {
         ++ctr;
         return ((double)(x >> 5) * 67108864.0 + (double)(y >> 6)) / 9007199254740992.0;
     }
+    W2B_HD void skip(int n) { ctr += (uint64_t)n; }       // draws whose value is never used (counter-based: free)
     W2B_HD int randint(int lo, int hi) {
         int r = lo + (int)(next() * (double)(hi - lo + 1));
         return r > hi ? hi : r;
