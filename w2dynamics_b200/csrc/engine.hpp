@@ -75,7 +75,7 @@ constexpr int MAX_CTA_THREADS = 1024;
 #if W2B_DEVICE
 __host__ __device__
 #endif
-inline int mat_doubles(const Chains& C) { return C.dmax > 1 ? 2 * C.mstride + 4 * C.dmax : 0; }
+inline int mat_doubles(const Chains& C, bool second) { return C.dmax > 1 ? C.xdoubles + 4 * C.dmax + (second ? C.mstride : 0) : 0; }
 
 #if W2B_DEVICE
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_init(Tables T, Run R, Chains C) {
@@ -103,13 +103,13 @@ W2B_HOSTDEV inline void sched_carve(CtaShared& S, char* base, int ncb) {
 }
 #if W2B_DEVICE
 // persistent sweep kernel: every CTA serves batches of ncb chains (batch b -> chains [b*ncb, (b+1)*ncb))
-__global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T, Run R, Chains C, Accum A, long long nsteps, int wdoubles, int ncb, int nbatch,
+__global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T, Run R, Chains C, Accum A, long long nsteps, int wdoubles, int mdoubles, int ncb, int nbatch,
                                                              int log_chain, double* logbuf) {
     extern __shared__ double smem[];
     __shared__ CtaShared S;
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5;
     double* ws = smem + (size_t)warp * wdoubles;
-    int* is = (int*)(ws + 3 * C.kcap + mat_doubles(C));
+    int* is = (int*)(ws + 3 * C.kcap + mdoubles);
     if (threadIdx.x == 0) { CtaShared tmp; sched_carve(tmp, (char*)(smem + (size_t)W * wdoubles), ncb);
         S.prop = tmp.prop; S.left = tmp.left; S.lA = tmp.lA; S.lR = tmp.lR; S.lA2 = tmp.lA2; S.lR2 = tmp.lR2; S.lG = tmp.lG; S.parked = tmp.parked; S.kind = tmp.kind; }
     __syncthreads();
@@ -119,22 +119,22 @@ __global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T, Run R, C
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_measure(Tables T, Run R, Chains C, Accum A, int wdoubles) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_measure(Tables T, Run R, Chains C, Accum A, int wdoubles, int mdoubles) {
     extern __shared__ double smem[];
     int warp = threadIdx.x >> 5;
     int chain = blockIdx.x * WARPS_PER_CTA + warp;
     if (chain >= C.nchains) return;
     double* ws = smem + (size_t)warp * wdoubles;
-    int* is = (int*)(ws + 3 * C.kcap + mat_doubles(C));
+    int* is = (int*)(ws + 3 * C.kcap + mdoubles);
     measure_chain(T, R, C, A, chain, ws, is, ws + 3 * C.kcap);
 }
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R, Chains C, int wdoubles, int only_chain) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R, Chains C, int wdoubles, int mdoubles, int only_chain) {
     extern __shared__ double smem[];
     int warp = threadIdx.x >> 5;
     int chain = blockIdx.x * WARPS_PER_CTA + warp;
     if (chain >= C.nchains || (only_chain >= 0 && chain != only_chain)) return;
     double* ws = smem + (size_t)warp * wdoubles;
-    int* is = (int*)(ws + 3 * C.kcap + mat_doubles(C));
+    int* is = (int*)(ws + 3 * C.kcap + mdoubles);
     rebuild_chain(T, R, C, chain, ws, is, ws + 3 * C.kcap);
 }
 #endif
@@ -154,7 +154,7 @@ public:
     Accum A{};
     EngineOptions opt;
     long long accum_doubles = 0;       // per bin
-    int wdoubles = 0;                  // per-warp scratch in doubles
+    int wdoubles = 0, wdoubles_sweep = 0;   // per-warp scratch in doubles (measurement kernel: second work matrix; sweep kernel: one)
     long long launches = 0;            // kernels launched (bench accounting)
     int accpair_cap = 0;
     std::vector<void*> owned;
@@ -232,6 +232,8 @@ public:
         C.ih = keep(dev_alloc<int>((size_t)nc * IH_STRIDE)); C.dh = keep(dev_alloc<double>((size_t)nc * DH_STRIDE));
         C.rng_ctr = keep(dev_alloc<unsigned long long>(nc)); C.counters = keep(dev_alloc<unsigned long long>((size_t)nc * C_NCNT));
         C.dmax = at.dmax; C.mstride = at.dmax > 1 ? at.dmax * at.dmax : 0;
+        if (at.dmax > MAT_DMAX) throw std::runtime_error("quantum-number blocks larger than 32 are not supported by the tensor trace path (add quantum numbers)");
+        C.ldx = mat_ld(at.dmax); C.xdoubles = at.dmax > 1 ? C.ldx * at.dmax : 0;
         if (at.dmax > 1) {
             C.op_slot = keep(dev_alloc<unsigned short>((size_t)nc * ops_cap)); C.free_slot = keep(dev_alloc<unsigned short>((size_t)nc * ops_cap));
             C.ket = keep(dev_alloc<double>((size_t)nc * ops_cap * C.mstride)); C.bra = keep(dev_alloc<double>((size_t)nc * ops_cap * C.mstride));
@@ -239,7 +241,8 @@ public:
             C.pt = keep(dev_alloc<double>((size_t)nc * 2 * C.dmax));
         }
         int wints = kcap + 32 + nsst;
-        wdoubles = 3 * kcap + mat_doubles(C) + (wints + 1) / 2;
+        wdoubles = 3 * kcap + mat_doubles(C, true) + (wints + 1) / 2;
+        wdoubles_sweep = 3 * kcap + mat_doubles(C, false) + (wints + 1) / 2;
 
         // accumulators
         int o = 0;
@@ -305,7 +308,7 @@ public:
         W2B_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
         W2B_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         int W = opt.cta_warps > 0 ? opt.cta_warps : 32;
-        const size_t per_warp = (size_t)wdoubles * sizeof(double);
+        const size_t per_warp = (size_t)wdoubles_sweep * sizeof(double);
         while (W > 1 && W * per_warp + sched_bytes(8 * W) > (size_t)smem_max - 1024) --W;
         if (W > MAX_CTA_THREADS / 32) W = MAX_CTA_THREADS / 32;
         int target = opt.batch_chains > 0 ? opt.batch_chains : 8 * W;
@@ -333,7 +336,7 @@ public:
         double* dlog = nullptr;
         if (log_chain >= 0) dlog = dev_alloc<double>((size_t)nsteps * LOGW);
 #if W2B_DEVICE
-        k_sweep<<<sw_grid, sw_warps * 32, sw_smem>>>(T, R, C, A, nsteps, wdoubles, sw_ncb, sw_nbatch, log_chain, dlog); ++launches;
+        k_sweep<<<sw_grid, sw_warps * 32, sw_smem>>>(T, R, C, A, nsteps, wdoubles_sweep, mat_doubles(C, false), sw_ncb, sw_nbatch, log_chain, dlog); ++launches;
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
         std::vector<double> ws(wdoubles + 8);
@@ -341,7 +344,7 @@ public:
         CtaShared S{}; sched_carve(S, sb.data(), sw_ncb);
         for (int b = 0; b < sw_nbatch; ++b) {
             const int lo = b * sw_ncb, nloc = std::min(sw_ncb, C.nchains - lo);
-            cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C)), ws.data() + 3 * C.kcap, log_chain, dlog);
+            cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, log_chain, dlog);
         }
 #endif
         if (log_chain >= 0) { sync(); d2h(log_host, dlog, (size_t)nsteps * LOGW); dev_free(dlog); }
@@ -352,11 +355,11 @@ public:
         size_t sm = smem_bytes();
         static size_t configured = 0;
         if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_measure, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
-        k_measure<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, A, wdoubles); ++launches;
+        k_measure<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, A, wdoubles, mat_doubles(C, true)); ++launches;
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
         std::vector<double> ws(wdoubles + 8);
-        for (int c = 0; c < C.nchains; ++c) measure_chain(T, R, C, A, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C)), ws.data() + 3 * C.kcap);
+        for (int c = 0; c < C.nchains; ++c) measure_chain(T, R, C, A, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);
 #endif
     }
 
@@ -365,11 +368,11 @@ public:
         size_t sm = smem_bytes();
         static size_t configured = 0;
         if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
-        k_rebuild<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, wdoubles, only_chain); ++launches;
+        k_rebuild<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, wdoubles, mat_doubles(C, true), only_chain); ++launches;
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
         std::vector<double> ws(wdoubles + 8);
-        for (int c = 0; c < C.nchains; ++c) if (only_chain < 0 || c == only_chain) rebuild_chain(T, R, C, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C)), ws.data() + 3 * C.kcap);
+        for (int c = 0; c < C.nchains; ++c) if (only_chain < 0 || c == only_chain) rebuild_chain(T, R, C, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);
 #endif
     }
 

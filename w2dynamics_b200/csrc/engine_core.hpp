@@ -84,6 +84,7 @@ struct Chains {
     double* ketlg; double* bralg;                              // [chain][ops_cap][dmax]
     double* pt;                                                // [chain][2*dmax] (log, sign) of every outer state's trace contribution
     int mstride, dmax;
+    int ldx, xdoubles;                                         // work matrix: leading dimension (4 mod 16) and size ldx * dmax
 };
 
 // accumulators (device), one slab per bin; offsets in doubles
@@ -100,7 +101,8 @@ struct Ctx {
     double* sc_tau; unsigned char* sc_code; short* sc_sst; double* sc_tc; double* sc_ta;
     double* wQ; double* wR; double* wV; int* wI;
     unsigned short* slot; unsigned short* freel; double* ket; double* bra; double* ketlg; double* bralg; double* pt;
-    double* mX; double* mY; double* mlg; double* mpt; double* mpw;   // per-warp work space of the blocked trace
+    double* mX; double* mY; double* mlg; double* mpt; double* mpw;   // per-warp work space of the blocked trace (mY: measurement kernel only)
+    int ldx;
     int kv, bv, nfree;
     int n, outer, wpos, npairs, perm, palt, err;
     double det_log, det_sign, tr_log, tr_sign, cfgsign, wmin, wmax;
@@ -297,49 +299,52 @@ W2B_HD void slots_reset(const Chains& C, Ctx& x) {
     wsync();
 }
 
-// make KET_i valid for all i <= upto
-W2B_HDN void extend_kets(const Tables& T, const Chains& C, Ctx& x, int upto) {
-    if (x.kv > upto) return;
-    const int m = ldg(&T.dim[x.outer]);
+// make KET_i valid for all i <= upto; returns true when the work matrix holds KET_upto (with its scales in x.mlg) on exit
+W2B_HDN bool extend_kets(const Tables& T, const Chains& C, Ctx& x, int upto) {
+    if (x.kv > upto) return false;
+    const int m = ldg(&T.dim[x.outer]), ld = x.ldx;
     int i = x.kv, sst; double tprev;
-    double* X = x.mX; double* Y = x.mY;
-    if (i == 0) { mat_identity(X, x.mlg, m); sst = x.outer; tprev = 0.0; }
+    double* X = x.mX;
+    if (i == 0) { mat_identity(X, ld, x.mlg, m); sst = x.outer; tprev = 0.0; }
     else {
         sst = (int)x.sst[i - 1]; tprev = x.tau[i - 1];
-        mat_copy(X, ket_slot(C, x, i - 1), ldg(&T.dim[sst]) * m);
+        const int d = ldg(&T.dim[sst]);
+        mat_move(X, ld, ket_slot(C, x, i - 1), d, d, m);
         mat_copy(x.mlg, x.ketlg + (size_t)x.slot[i - 1] * C.dmax, m);
         wsync();
     }
     for (; i <= upto; ++i) {
-        sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, Y, x.mlg, x.mpw, m);
-        mat_copy(ket_slot(C, x, i), Y, ldg(&T.dim[sst]) * m);
+        sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, ld, x.mlg, x.mpw, m);
+        const int d = ldg(&T.dim[sst]);
+        mat_move(ket_slot(C, x, i), d, X, ld, d, m);
         mat_copy(x.ketlg + (size_t)x.slot[i] * C.dmax, x.mlg, m);
         tprev = x.tau[i];
-        double* t = X; X = Y; Y = t;
     }
     wsync();
     x.kv = upto + 1;
+    return true;
 }
 
 // make BRA_i valid for all i >= downto
 W2B_HDN void extend_bras(const Tables& T, const Chains& C, Ctx& x, int downto) {
     if (x.bv <= downto) return;
-    const int m = ldg(&T.dim[x.outer]);
+    const int m = ldg(&T.dim[x.outer]), ld = x.ldx;
     int i = x.bv; double tnext;
-    double* X = x.mX; double* Y = x.mY;
-    if (i == x.n) { mat_identity(X, x.mlg, m); tnext = T.beta; }
+    double* X = x.mX;
+    if (i == x.n) { mat_identity(X, ld, x.mlg, m); tnext = T.beta; }
     else {
         tnext = x.tau[i];
-        mat_copy(X, bra_slot(C, x, i), ldg(&T.dim[sst_before(x, i)]) * m);
+        const int d = ldg(&T.dim[sst_before(x, i)]);
+        mat_move(X, ld, bra_slot(C, x, i), d, d, m);
         mat_copy(x.mlg, x.bralg + (size_t)x.slot[i] * C.dmax, m);
         wsync();
     }
     for (i = x.bv - 1; i >= downto; --i) {          // BRA_i = O_i^T P(tau_{i+1} - tau_i) BRA_{i+1}
-        const int sb = mat_apply(T, (int)x.sst[i], (int)x.code[i] ^ 1, tnext - x.tau[i], X, Y, x.mlg, x.mpw, m);
-        mat_copy(bra_slot(C, x, i), Y, ldg(&T.dim[sb]) * m);
+        const int sb = mat_apply(T, (int)x.sst[i], (int)x.code[i] ^ 1, tnext - x.tau[i], X, ld, x.mlg, x.mpw, m);
+        const int d = ldg(&T.dim[sb]);
+        mat_move(bra_slot(C, x, i), d, X, ld, d, m);
         mat_copy(x.bralg + (size_t)x.slot[i] * C.dmax, x.mlg, m);
         tnext = x.tau[i];
-        double* t = X; X = Y; Y = t;
     }
     wsync();
     x.bv = downto;
@@ -349,39 +354,36 @@ W2B_HDN void extend_bras(const Tables& T, const Chains& C, Ctx& x, int downto) {
 // the old operators [lo, hi), optional new operator B.  Parts of every outer state go to x.mpt.
 W2B_HDN void seg_trace(const Tables& T, const Chains& C, Ctx& x, int s, int e, bool hasA, double tA, int codeA, int lo, int hi,
                        bool hasB, double tB, int codeB, double& tlog, double& tsign) {
-    extend_kets(T, C, x, s - 1);
     extend_bras(T, C, x, e);
-    const int m = ldg(&T.dim[x.outer]);
-    double* X = x.mX; double* Y = x.mY;
+    const bool have = extend_kets(T, C, x, s - 1);          // bras first: the ket frontier may leave KET_{s-1} in the work matrix
+    const int m = ldg(&T.dim[x.outer]), ld = x.ldx;
+    double* X = x.mX;
     int sst; double tprev;
-    if (s == 0) { mat_identity(X, x.mlg, m); sst = x.outer; tprev = 0.0; }
+    if (s == 0) { mat_identity(X, ld, x.mlg, m); sst = x.outer; tprev = 0.0; }
     else {
         sst = (int)x.sst[s - 1]; tprev = x.tau[s - 1];
-        mat_copy(X, ket_slot(C, x, s - 1), ldg(&T.dim[sst]) * m);
-        mat_copy(x.mlg, x.ketlg + (size_t)x.slot[s - 1] * C.dmax, m);
-        wsync();
+        if (!have) {
+            const int d = ldg(&T.dim[sst]);
+            mat_move(X, ld, ket_slot(C, x, s - 1), d, d, m);
+            mat_copy(x.mlg, x.ketlg + (size_t)x.slot[s - 1] * C.dmax, m);
+            wsync();
+        }
     }
-    if (hasA) { sst = mat_apply(T, sst, codeA, tA - tprev, X, Y, x.mlg, x.mpw, m); tprev = tA; double* t = X; X = Y; Y = t; }
-    for (int i = lo; i < hi; ++i) {
-        sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, Y, x.mlg, x.mpw, m); tprev = x.tau[i];
-        double* t = X; X = Y; Y = t;
-    }
-    if (hasB) { sst = mat_apply(T, sst, codeB, tB - tprev, X, Y, x.mlg, x.mpw, m); tprev = tB; double* t = X; X = Y; Y = t; }
-    if (e == x.n) mat_close(T, sst, T.beta - tprev, X, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
-    else mat_close(T, sst, x.tau[e] - tprev, X, x.mlg, bra_slot(C, x, e), x.bralg + (size_t)x.slot[e] * C.dmax, x.mpw, m, x.mpt, tlog, tsign);
+    if (hasA) { sst = mat_apply(T, sst, codeA, tA - tprev, X, ld, x.mlg, x.mpw, m); tprev = tA; }
+    for (int i = lo; i < hi; ++i) { sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, ld, x.mlg, x.mpw, m); tprev = x.tau[i]; }
+    if (hasB) { sst = mat_apply(T, sst, codeB, tB - tprev, X, ld, x.mlg, x.mpw, m); tprev = tB; }
+    if (e == x.n) mat_close(T, sst, T.beta - tprev, X, ld, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
+    else mat_close(T, sst, x.tau[e] - tprev, X, ld, x.mlg, bra_slot(C, x, e), x.bralg + (size_t)x.slot[e] * C.dmax, x.mpw, m, x.mpt, tlog, tsign);
 }
 
 // from-scratch trace of an arbitrary sequence (global moves, tau shifts, set_mc_config); no caches touched
 W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsigned char* code, int n, int outer, double& tlog, double& tsign) {
-    const int m = ldg(&T.dim[outer]);
-    double* X = x.mX; double* Y = x.mY;
-    mat_identity(X, x.mlg, m);
+    const int m = ldg(&T.dim[outer]), ld = x.ldx;
+    double* X = x.mX;
+    mat_identity(X, ld, x.mlg, m);
     int sst = outer; double tprev = 0.0;
-    for (int i = 0; i < n; ++i) {
-        sst = mat_apply(T, sst, (int)code[i], tau[i] - tprev, X, Y, x.mlg, x.mpw, m); tprev = tau[i];
-        double* t = X; X = Y; Y = t;
-    }
-    mat_close(T, sst, T.beta - tprev, X, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
+    for (int i = 0; i < n; ++i) { sst = mat_apply(T, sst, (int)code[i], tau[i] - tprev, X, ld, x.mlg, x.mpw, m); tprev = tau[i]; }
+    mat_close(T, sst, T.beta - tprev, X, ld, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
 }
 // trace contributions of the outer states of an empty configuration: w_exp(-(E_j - Egs) beta)
 W2B_HD void empty_parts(const Tables& T, Ctx& x, int outer) {
@@ -1057,7 +1059,7 @@ W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain,
         x.ket = C.ket + (size_t)chain * C.ops_cap * C.mstride; x.bra = C.bra + (size_t)chain * C.ops_cap * C.mstride;
         x.ketlg = C.ketlg + (size_t)chain * C.ops_cap * C.dmax; x.bralg = C.bralg + (size_t)chain * C.ops_cap * C.dmax;
         x.pt = C.pt + (size_t)chain * 2 * C.dmax;
-        x.mX = mscratch; x.mY = mscratch + C.mstride; x.mlg = mscratch + 2 * C.mstride; x.mpt = x.mlg + C.dmax; x.mpw = x.mpt + 2 * C.dmax;
+        x.ldx = C.ldx; x.mX = mscratch; x.mlg = mscratch + C.xdoubles; x.mpt = x.mlg + C.dmax; x.mpw = x.mpt + 2 * C.dmax; x.mY = x.mpw + C.dmax;
         x.kv = x.ih[IH_KV]; x.bv = x.ih[IH_BV]; x.nfree = x.ih[IH_NFREE];
     }
     x.n = x.ih[IH_NOPS]; x.outer = x.ih[IH_OUTER]; x.wpos = x.ih[IH_WPOS]; x.npairs = x.ih[IH_NPAIRS];
@@ -1282,9 +1284,9 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     const double e0 = ldg(&ev[0]);
     const double tauR = ih == 0 ? 0.0 : x.tau[ih - 1], tauL = ih == x.n ? T.beta : x.tau[ih];
     double* K = x.mX; double* B = x.mY; double* klg = x.mlg; double* blg = x.mpt; double* fac = x.mpt + C.dmax;
-    if (ih == 0) mat_identity(K, klg, m);
+    if (ih == 0) mat_identity(K, m, klg, m);
     else { mat_copy(K, ket_slot(C, x, ih - 1), d * m); mat_copy(klg, x.ketlg + (size_t)x.slot[ih - 1] * C.dmax, m); }
-    if (ih == x.n) mat_identity(B, blg, m);
+    if (ih == x.n) mat_identity(B, m, blg, m);
     else { mat_copy(B, bra_slot(C, x, ih), d * m); mat_copy(blg, x.bralg + (size_t)x.slot[ih] * C.dmax, m); }
     wsync();
     for (int e = x.lane; e < d * m; e += W2B_WARP) {

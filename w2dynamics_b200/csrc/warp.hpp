@@ -42,6 +42,11 @@ W2B_HD int wsum(int x) {
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(W2B_FULL, x, o);
     return x;
 }
+W2B_HD double wmaxd(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(W2B_FULL, x, o));
+    return x;
+}
 W2B_HD int wmax(int x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(W2B_FULL, x, o));
@@ -102,6 +107,7 @@ W2B_HD int lane_id() { return 0; }
 W2B_HD void wsync() {}
 W2B_HD double wsum(double x) { return x; }
 W2B_HD int wsum(int x) { return x; }
+W2B_HD double wmaxd(double x) { return x; }
 W2B_HD int wmax(int x) { return x; }
 W2B_HD int wmin(int x) { return x; }
 W2B_HD int wxor(int x) { return x; }
