@@ -467,6 +467,7 @@ int w2b_get_scalar(const char* name, double* out) {
             if (k == "batch_chains") { *out = E.sw_ncb; return; }
             if (k == "sweep_grid") { *out = E.sw_grid; return; }
             if (k == "sweep_smem") { *out = (double)E.sw_smem; return; }
+            if (k == "rounds") { *out = (double)E.rounds; return; }
             if (k.rfind("cnt_", 0) == 0) {
                 static const char* names[C_NCNT] = {"try_add", "try_rem", "try_glob", "try_shift", "acc_add", "acc_rem", "acc_glob", "acc_shift",
                                                     "qn_add", "qn_rem", "qn_glob", "steps", "alg_bytes"};

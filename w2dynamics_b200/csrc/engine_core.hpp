@@ -53,6 +53,7 @@ struct Tables {
     const int* dens_off;         // [nsst] offset of the block's d x d slab inside the density-matrix accumulator
     const double* empty_w;       // [nsst] normalised empty-trace weights (init_Trace / StepChangeOuter)
     const double* empty_log;     // [nsst] log of the empty trace of each outer superstate
+    const OpDesc* desc;          // [nsst*nops] packed operator records of the blocked trace
     const long long* op_off;     // matrix path
     const double* opdata;
     const double* evals;
@@ -69,6 +70,18 @@ struct Run {
     int same_key;                // diagnostics only: every chain uses chain 0's RNG key (identical control flow across warps)
 };
 
+// a proposal that survived the quantum-number check travels from the propose kernel to the decide kernel in this record
+struct Prop {
+    double t1, t2, tau_a, tau_c, factor, dlog, dsign;
+    int f, i1, i2, p1, p2, begin_sst, nother, type1;
+};
+
+// round scheduler counters (device memory, two sets used in alternation by consecutive rounds)
+enum { SC_NRARE = 0, SC_NQ0, SC_NQ1, SC_NQ2, SC_TICKET, SC_NRUN, SC_MAXLEFT, SC_TTICKET, SC_NT0, SC_NT1, SC_NT2, SC_STRIDE = 16 };
+constexpr int Q_REM = 1 << 30;       // decide-queue entry = chain id | Q_REM for a removal
+constexpr int Q_NTSHIFT = 26;         // trace-queue entry: + column tile << Q_NTSHIFT
+constexpr int Q_IDMASK = (1 << 26) - 1;
+
 struct Chains {
     int nchains, ops_cap, kcap, ld;
     double* op_tau; unsigned char* op_code; short* op_sst;
@@ -84,6 +97,11 @@ struct Chains {
     double* ketlg; double* bralg;                              // [chain][ops_cap][dmax]
     double* pt;                                                // [chain][2*dmax] (log, sign) of every outer state's trace contribution
     int mstride, dmax;
+    // round scheduler: moves left in the current sweep, rare-move flags, proposals, work queues, counters
+    int* left; unsigned char* parked; unsigned char* kind; Prop* prop;
+    int* q_rare; int* q_dec0; int* q_dec1; int* q_dec2; int* sched;
+    double* ptc;                                               // trace kernel results: per-outer-state parts (log, sign) of the proposed configuration [chain][2*dmax]
+    int* q_tr0; int* q_tr1; int* q_tr2;                        // trace jobs (chain | column tile | removal flag) by number of steps: long, medium, short
     int ldx, xdoubles;                                         // work matrix: leading dimension (4 mod 16) and size ldx * dmax
 };
 
@@ -104,6 +122,7 @@ struct Ctx {
     double* mX; double* mY; double* mlg; double* mpt; double* mpw;   // per-warp work space of the blocked trace (mY: measurement kernel only)
     int ldx;
     int kv, bv, nfree;
+    const double* pre;     // trace of the proposed configuration computed by the trace kernel (or nullptr)
     int n, outer, wpos, npairs, perm, palt, err;
     double det_log, det_sign, tr_log, tr_sign, cfgsign, wmin, wmax;
     Philox rng;
@@ -385,6 +404,111 @@ W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsign
     for (int i = 0; i < n; ++i) { sst = mat_apply(T, sst, (int)code[i], tau[i] - tprev, X, ld, x.mlg, x.mpw, m); tprev = tau[i]; }
     mat_close(T, sst, T.beta - tprev, X, ld, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
 }
+// ------------------------------------------------------------------ trace kernel (blocked traces, pair moves)
+// One job = 8 columns (outer states) of the local trace of one proposed pair insertion / removal.  Columns never mix
+// (KET_i[:, j] = O_i P ... O_1 P e_j), so an outer block of dimension m splits into ceil(m/8) independent jobs -- four times
+// the parallelism for the 28-wide blocks, a 2.3 kB work matrix per warp, and one DMMA column tile held in registers.
+// A job extends the bra frontier down to the end of the changed sub-string, the ket frontier up to its start, multiplies
+// through the sub-string and closes.  The three phases run as ONE loop over "steps" (operator, propagation time, input
+// block, cache slot to fill) whose records are prepared 32 at a time, one per lane, and broadcast by shuffles: the
+// operator product is the only code in the loop and the per-step global-memory latency is paid once per 32 steps.
+// Writes the per-outer-state parts (log, sign) of the proposed configuration to C.ptc; the decide kernel sums them and
+// moves the frontiers (kv = max(kv, s), bv = min(bv, e)).
+W2B_HD void load_tile(const Tables& T, const Chains& C, double* X, double* lg, const double* slot_mat, const double* slot_lg, int sst, int j0, int mw) {
+    if (slot_mat) {
+        const int d = ldg(&T.dim[sst]);
+        mat_move(X, C.ldx, slot_mat + j0 * d, d, d, mw);
+        for (int j = lane_id(); j < mw; j += W2B_WARP) lg[j] = slot_lg[j0 + j];
+    } else {                                                    // identity: columns j0 .. j0+mw-1 of I_m (m = dim of sst)
+        const int m = ldg(&T.dim[sst]);
+        for (int j = 0; j < mw; ++j) for (int r = lane_id(); r < m; r += W2B_WARP) X[r + j * C.ldx] = (r == j0 + j) ? 1.0 : 0.0;
+        for (int j = lane_id(); j < mw; j += W2B_WARP) lg[j] = 0.0;
+    }
+    wsync();
+}
+W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, double* lg, double* pw) {
+    const int lane = lane_id();
+    const int chain = entry & Q_IDMASK, nt = (entry >> Q_NTSHIFT) & 3;
+    const bool rem = (entry & Q_REM) != 0;
+    const int* ih = C.ih + (size_t)chain * IH_STRIDE;
+    const double* tau = C.op_tau + (size_t)chain * C.ops_cap; const unsigned char* code = C.op_code + (size_t)chain * C.ops_cap;
+    const short* sst = C.op_sst + (size_t)chain * C.ops_cap; const unsigned short* slot = C.op_slot + (size_t)chain * C.ops_cap;
+    double* ket = C.ket + (size_t)chain * C.ops_cap * C.mstride; double* bra = C.bra + (size_t)chain * C.ops_cap * C.mstride;
+    double* ketlg = C.ketlg + (size_t)chain * C.ops_cap * C.dmax; double* bralg = C.bralg + (size_t)chain * C.ops_cap * C.dmax;
+    const int n = ih[IH_NOPS], outer = ih[IH_OUTER], kv = ih[IH_KV], bv = ih[IH_BV];
+    const Prop& P = C.prop[chain];
+    const int i1 = P.i1, i2 = P.i2;
+    const int s = i1, e = rem ? i2 + 1 : i2, lo = rem ? i1 + 1 : i1, hi = i2, nA = rem ? 0 : 1;
+    const double tA = P.t1, tB = P.t2;
+    const int codeA = P.f * 2 + P.type1, codeB = P.f * 2 + (1 - P.type1);
+    const int m = ldg(&T.dim[outer]), ld = C.ldx;
+    const int j0 = nt * 8, mw = m - j0 < 8 ? m - j0 : 8;        // this job's columns
+    const int nb = bv > e ? bv - e : 0, nk = kv <= s - 1 ? s - kv : 0, ns = nA + (hi - lo) + nA;
+    const int total = nb + nk + ns;
+    int cur = -1;                        // block of the work matrix (rows)
+    int r_opc = 0, r_sst = 0, r_slot = 0; double r_dt = 0.0;
+    for (int j = 0; j < total; ++j) {
+        if ((j & (W2B_WARP - 1)) == 0) {                       // next 32 step records, one per lane
+            const int q = j + lane;
+            r_opc = 0; r_sst = -1; r_slot = -1; r_dt = 0.0;
+            if (q < nb) {                                       // bra step: BRA_i = O_i^T P(tau_{i+1} - tau_i) BRA_{i+1}
+                const int i = bv - 1 - q;
+                r_opc = (int)code[i] ^ 1; r_sst = (int)sst[i]; r_slot = (int)slot[i] | (2 << 16);
+                r_dt = (i + 1 == n ? T.beta : tau[i + 1]) - tau[i];
+            } else if (q < nb + nk) {                           // ket step: KET_i = O_i P(tau_i - tau_{i-1}) KET_{i-1}
+                const int i = kv + (q - nb);
+                r_opc = (int)code[i]; r_sst = i == 0 ? outer : (int)sst[i - 1]; r_slot = (int)slot[i] | (1 << 16);
+                r_dt = tau[i] - (i == 0 ? 0.0 : tau[i - 1]);
+            } else if (q < total) {                             // sub-string step: [A] old operators [lo, hi) [B]
+                const int u = q - nb - nk;
+                double t, tp;
+                if (u < nA) { r_opc = codeA; t = tA; tp = s == 0 ? 0.0 : tau[s - 1]; }
+                else if (u - nA < hi - lo) { const int i = lo + u - nA; r_opc = (int)code[i]; t = tau[i]; tp = u == 0 ? (s == 0 ? 0.0 : tau[s - 1]) : (u - nA == 0 ? tA : tau[i - 1]); }
+                else { r_opc = codeB; t = tB; tp = hi > lo ? tau[hi - 1] : tA; }
+                r_dt = t - tp;
+            }
+        }
+        const int src = j & (W2B_WARP - 1);
+        const int opc = wbcast(r_opc, src), sin = wbcast(r_sst, src), sl = wbcast(r_slot, src);
+        const double dt = wbcast(r_dt, src);
+        // phase starts: load the frontier tile (or identity columns) into the work matrix
+        if (j == 0 && nb > 0) {
+            if (bv == n) load_tile(T, C, X, lg, nullptr, nullptr, outer, j0, mw);
+            else load_tile(T, C, X, lg, bra + (size_t)slot[bv] * C.mstride, bralg + (size_t)slot[bv] * C.dmax, (int)sst[bv - 1], j0, mw);
+        } else if (j == nb && nk > 0) {
+            cur = kv == 0 ? outer : (int)sst[kv - 1];
+            if (kv == 0) load_tile(T, C, X, lg, nullptr, nullptr, outer, j0, mw);
+            else load_tile(T, C, X, lg, ket + (size_t)slot[kv - 1] * C.mstride, ketlg + (size_t)slot[kv - 1] * C.dmax, cur, j0, mw);
+        } else if (j == nb + nk && nk == 0) {
+            cur = s == 0 ? outer : (int)sst[s - 1];
+            if (s == 0) load_tile(T, C, X, lg, nullptr, nullptr, outer, j0, mw);
+            else load_tile(T, C, X, lg, ket + (size_t)slot[s - 1] * C.mstride, ketlg + (size_t)slot[s - 1] * C.dmax, cur, j0, mw);
+        }
+        const int in = sin >= 0 ? sin : cur;
+        cur = mat_apply_inl<1>(T, in, opc, dt, X, ld, lg, pw, mw);
+        if (sl >= 0) {                                          // fill this job's columns of the operator's cache slot
+            const int d = ldg(&T.dim[cur]);
+            double* dst = ((sl >> 16) == 1 ? ket : bra) + (size_t)(sl & 0xffff) * C.mstride + j0 * d;
+            double* dlg = ((sl >> 16) == 1 ? ketlg : bralg) + (size_t)(sl & 0xffff) * C.dmax + j0;
+            mat_move(dst, d, X, ld, d, mw);
+            for (int jj = lane; jj < mw; jj += W2B_WARP) dlg[jj] = lg[jj];
+            wsync();
+        }
+    }
+    if (ns == 0 && nk == 0) {                                   // nothing applied after the ket frontier: work matrix = KET_{s-1}
+        cur = s == 0 ? outer : (int)sst[s - 1];
+        if (s == 0) load_tile(T, C, X, lg, nullptr, nullptr, outer, j0, mw);
+        else load_tile(T, C, X, lg, ket + (size_t)slot[s - 1] * C.mstride, ketlg + (size_t)slot[s - 1] * C.dmax, cur, j0, mw);
+    }
+    const double tlast = ns > 0 ? (nA ? tB : tau[hi - 1]) : (s == 0 ? 0.0 : tau[s - 1]);
+    double* pt = C.ptc + (size_t)chain * 2 * C.dmax + 2 * j0;
+    if (e == n) mat_close_parts(T, cur, T.beta - tlast, X, ld, lg, (const double*)nullptr, (const double*)nullptr, pw, mw, j0, pt);
+    else {
+        const int d = ldg(&T.dim[cur]);
+        mat_close_parts(T, cur, tau[e] - tlast, X, ld, lg, bra + (size_t)slot[e] * C.mstride + j0 * d, bralg + (size_t)slot[e] * C.dmax + j0, pw, mw, j0, pt);
+    }
+}
+
 // trace contributions of the outer states of an empty configuration: w_exp(-(E_j - Egs) beta)
 W2B_HD void empty_parts(const Tables& T, Ctx& x, int outer) {
     const int m = ldg(&T.dim[outer]);
@@ -505,10 +629,6 @@ W2B_HD void bump_bytes(Ctx& x, long long b) { if (x.lane == 0) x.cnt[C_ALGBYTES]
 // The CTA-level scheduler (cta_sweep below) runs all chains of a CTA through the SAME phase at the same time so that the
 // warps of an SM share instruction-cache lines:  propose (RNG draws, positions, quantum-number walk, scalar trace ratio)
 // -> decide (determinant ratio, blocked trace, Metropolis draw, rank-1 update).  The proposal travels in a Prop record.
-struct Prop {
-    double t1, t2, tau_a, tau_c, factor, dlog, dsign;
-    int f, i1, i2, p1, p2, begin_sst, nother, type1;
-};
 
 // StepAdd part 1 (CTQMC.F90:3353-3469): pair_OperAdd, process_OperAdd, check_sst_sequence.  Returns false on an early exit.
 W2B_HDN bool add_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x, Prop& P) {
@@ -578,7 +698,8 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     bump_bytes(x, 8ll * k * k);
     double tn_log = 0.0, tn_sign = 1.0;
     if (blocked) {                                                     // get_trace_EB of the proposed configuration
-        seg_trace(T, C, x, i1, i2, true, t1, code1, i1, i2, true, t2, code2, tn_log, tn_sign);
+        if (x.pre) { parts_sum(x.mpt, ldg(&T.dim[x.outer]), tn_log, tn_sign); if (x.kv < i1) x.kv = i1; if (x.bv > i2) x.bv = i2; }
+        else seg_trace(T, C, x, i1, i2, true, t1, code1, i1, i2, true, t2, code2, tn_log, tn_sign);
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
@@ -709,7 +830,8 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     double dlog = P.dlog, dsign = P.dsign, tn_log = 0.0, tn_sign = 1.0;
     if (blocked) {
-        seg_trace(T, C, x, i1, i2 + 1, false, 0.0, 0, i1 + 1, i2, false, 0.0, 0, tn_log, tn_sign);
+        if (x.pre) { parts_sum(x.mpt, ldg(&T.dim[x.outer]), tn_log, tn_sign); if (x.kv < i1) x.kv = i1; if (x.bv > i2 + 1) x.bv = i2 + 1; }
+        else seg_trace(T, C, x, i1, i2 + 1, false, 0.0, 0, i1 + 1, i2, false, 0.0, 0, tn_log, tn_sign);
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
     // determinant ratio = M(p1,p2)  (MatrixUpdate.F90:445-452)
@@ -1067,7 +1189,7 @@ W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain,
     x.det_log = x.dh[DH_DETLOG]; x.det_sign = x.dh[DH_DETSIGN]; x.tr_log = x.dh[DH_TRLOG]; x.tr_sign = x.dh[DH_TRSIGN]; x.cfgsign = x.dh[DH_CFGSIGN];
     x.rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, C.rng_ctr[chain]);
     set_window_edges(T, R, x);
-    x.log = nullptr;
+    x.log = nullptr; x.pre = nullptr;
 }
 W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
@@ -1081,51 +1203,8 @@ W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
 }
 
-// ------------------------------------------------------------------ phase scheduler of one CTA (CTQMC.F90:8213-8258, 8428-8533)
-// One CTA advances a batch of `nloc` chains by `nsteps` moves each.  Chains are independent Markov chains, so the order
-// in which *different* chains execute their moves is free; the scheduler uses that freedom to keep all warps of the CTA in
-// the same phase of the algorithm (shared instruction-cache lines, no cross-warp code divergence):
-//   round := schedule (every runnable chain draws its move type, reference thresholds CTQMC.F90:8437-8488)
-//            -> propose (all insertions, then all removals; warps take chains from a shared-memory work list)
-//            -> decide  (determinant ratio, trace, Metropolis, rank-1 update for the proposals that survived)
-//   Global moves and tau-shifts (1 % of the moves, 10-100x the cost) park their chain; parked chains are served together
-//   in a `rare` phase once a warp-load of them has accumulated (or nothing else is runnable).
-// Within a chain the sequence of moves and RNG draws is exactly the reference's.
-struct CtaShared {
-    int nA, nR, nA2, nR2, nG, cA, cR, cA2, cR2, cG, cA2h, cR2h;
-    int* left; unsigned char* parked; unsigned char* kind;
-    short* lA; short* lR; short* lA2; short* lR2; short* lG;
-    Prop* prop;
-};
-
-// Pull the hot records of the chain a warp will work on next into L1 while it is still busy with the current one:
-// every lane prefetches one 128-byte line (operator times / superstates / codes, scalar state, counters, the first line
-// of each flavour's creator / annihilator times).  For a decide-phase item also the rows of the touched flavour's M.
-W2B_HD void prefetch_chain(const Tables& T, const Chains& C, int chain) {
-#if W2B_DEVICE
-    const int l = lane_id();
-    const char* p = nullptr;
-    if (l < 8) p = (const char*)(C.op_tau + (size_t)chain * C.ops_cap) + l * 128;
-    else if (l < 10) p = (const char*)(C.op_sst + (size_t)chain * C.ops_cap) + (l - 8) * 128;
-    else if (l == 10) p = (const char*)(C.op_code + (size_t)chain * C.ops_cap);
-    else if (l < 13) p = (const char*)(C.ih + (size_t)chain * IH_STRIDE) + (l - 11) * 128;
-    else if (l == 13) p = (const char*)(C.dh + (size_t)chain * DH_STRIDE);
-    else if (l == 14) p = (const char*)(C.counters + (size_t)chain * C_NCNT);
-    else if (l - 15 < 2 * T.nf) { const int f = (l - 15) >> 1; p = (const char*)(((l - 15) & 1 ? C.tau_a : C.tau_c) + ((size_t)chain * T.nf + f) * C.kcap); }
-    if (p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
-W2B_HD void prefetch_minv(const Tables& T, const Chains& C, int chain, int f) {
-#if W2B_DEVICE
-    const int* ih = C.ih + (size_t)chain * IH_STRIDE;
-    const int k = ih[IH_KF + f];
-    const char* m = (const char*)(C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld));
-    for (int r = lane_id(); r < k; r += W2B_WARP) asm volatile("prefetch.global.L1 [%0];" ::"l"(m + (size_t)r * C.ld * 8));
-#endif
-}
-
 // bookkeeping after every move: window shift (checked after EVERY move, CTQMC.F90:8255/8531), step counter, quota
-W2B_HDN void post_move(const Tables& T, const Run& R, Ctx& x, CtaShared& S, int c) {
+W2B_HDN void post_move(const Tables& T, const Run& R, const Chains& C, Ctx& x, int chain) {
     wsync();
     const unsigned long long attempts = x.cnt[C_TRYADD] + x.cnt[C_TRYREM];
     if (!R.freeze_window && attempts % (unsigned long long)R.nslide == 0ull) {         // shift_window Trace.F90:1652-1678
@@ -1135,98 +1214,90 @@ W2B_HDN void post_move(const Tables& T, const Run& R, Ctx& x, CtaShared& S, int 
             x.npairs = -1;
         }
     }
-    if (x.lane == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; S.left[c] -= 1; }
+    if (x.lane == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; C.left[chain] -= 1; }
     wsync();
 }
 
-
-W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain_lo, int nloc, long long nsteps,
-                      CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf) {
-    const int W = cta_nwarps(), lane = lane_id();
-    for (int c = cta_tid(); c < nloc; c += cta_nthreads()) { S.left[c] = (int)nsteps; S.parked[c] = 0; }
-    if (cta_tid() == 0) { S.nG = 0; S.cG = 0; }
-    cta_sync();
+// ------------------------------------------------------------------ round scheduler (CTQMC.F90:8213-8258, 8428-8533)
+// Chains are independent Markov chains, so the order in which *different* chains execute their moves is free.  A sweep of
+// `nsteps` moves per chain runs as rounds of two kernels over the whole population:
+//   k_propose : every runnable chain draws move types (reference thresholds CTQMC.F90:8437-8488) and proposes until one
+//               proposal survives the quantum-number check (at most R.propose_run moves); survivors are queued for the
+//               decide kernel, global moves / tau shifts for its rare queue.  No shared memory, full occupancy.
+//   k_decide  : determinant ratio, blocked trace on the tensor pipe, Metropolis, rank-1 update.  Warps take tickets from
+//               one global counter, longest jobs first: rare moves, then outer blocks >= 16, > 1, == 1.
+// Each kernel is small enough for the instruction cache and sized for its own register / shared-memory needs.
+// Within a chain the sequence of moves and RNG draws is exactly the reference's.
+W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int chain, long long nsteps, int parity, int log_chain, double* logbuf) {
+    const int lane = lane_id();
+    int left = C.left[chain];
+    if (left <= 0 || C.parked[chain]) return;
+    int* sc = C.sched + parity * SC_STRIDE;
     const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
-    for (;;) {
-        if (cta_tid() == 0) { S.nA = 0; S.nA2 = S.nR2 = 0; S.cA = S.cA2 = S.cR2 = S.cA2h = S.cR2h = 0; }
-        cta_sync();
-        // ---- propose phase: every runnable chain draws move types (reference thresholds CTQMC.F90:8437-8488, plus the two
-        //      draws spent on 4-operator / outer moves) and proposes until one proposal survives the quantum-number check
-        for (int c = wgrab(&S.cA), cnext; c < nloc; c = cnext) {
-            cnext = wgrab(&S.cA);
-            if (S.left[c] <= 0 || S.parked[c]) continue;
-            if (R.prefetch && cnext < nloc) prefetch_chain(T, C, chain_lo + cnext);
-            const int chain = chain_lo + c;
-            Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-            if (lane == 0) wgrab_one(&S.nA);                              // S.nA counts the chains that were runnable this round
-            for (int run = 0; run < R.propose_run && S.left[c] > 0; ++run) {
-                const double r = x.rng.next();
-                if (!(r <= thr_rem)) {                                    // global move / tau shift: park for the rare phase
-                    if (lane == 0) { S.kind[c] = (unsigned char)(r <= thr_glob ? 3 : 4); S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
-                    break;
-                }
-                x.rng.skip(2);                                            // Percentage4OperatorMove / PercentageOuterMove draws (both 0)
-                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                bool go;
-                if (r < thr_add) { go = add_propose(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lA2[wgrab_one(&S.nA2)] = (short)c; }
-                else { go = rem_propose(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lR2[wgrab_one(&S.nR2)] = (short)c; }
-                if (go) break;
-                post_move(T, R, x, S, c);
-            }
-            ctx_store(C, chain, x);
+    Ctx x; ctx_bind(T, R, C, chain, x, nullptr, nullptr, nullptr);
+    if (lane == 0) { atomic_add_int(&sc[SC_NRUN], 1); atomic_max_int(&sc[SC_MAXLEFT], left); }
+    for (int run = 0; run < R.propose_run && left > 0; ++run) {
+        const double r = x.rng.next();
+        if (!(r <= thr_rem)) {                                    // global move / tau shift: rare queue
+            if (lane == 0) { C.kind[chain] = (unsigned char)(r <= thr_glob ? 3 : 4); C.parked[chain] = 1; C.q_rare[atomic_add_int(&sc[SC_NRARE], 1)] = chain; }
+            break;
         }
-        cta_sync();
-        const int nrun = S.nA;             // read before thread 0 may reset it at the top of the next round
-        bool rare;
-        if (nrun == 0) {
-            if (S.nG == 0) break;                                         // every chain has used its quota
-            rare = true;
-        } else {
-            // ---- decide phase: determinant ratio, trace, Metropolis, rank-1 update
-            const int na2 = S.nA2, nr2 = S.nR2;
-            // blocked traces: chains whose outer block is larger than 1x1 cost 10-100x more -> serve them first (longest
-            // processing time first keeps the tail of the phase short); pass 0 = heavy, pass 1 = the rest
-            for (int pass = (T.dmax > 1 ? 0 : 1); pass < 2; ++pass) {
-                int* curA = pass == 0 ? &S.cA2h : &S.cA2; int* curR = pass == 0 ? &S.cR2h : &S.cR2;
-                for (int i = wgrab(curA); i < na2; i = wgrab(curA)) {
-                    const int c = S.lA2[i], chain = chain_lo + c;
-                    if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
-                    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                    if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                    add_decide(T, R, C, A, x, S.prop[c]);
-                    post_move(T, R, x, S, c);
-                    ctx_store(C, chain, x);
-                }
-                for (int i = wgrab(curR); i < nr2; i = wgrab(curR)) {
-                    const int c = S.lR2[i], chain = chain_lo + c;
-                    if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
-                    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                    if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                    rem_decide(T, R, C, A, x, S.prop[c]);
-                    post_move(T, R, x, S, c);
-                    ctx_store(C, chain, x);
+        x.rng.skip(2);                                            // Percentage4OperatorMove / PercentageOuterMove draws (both 0)
+        if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - left) * LOGW;
+        bool go; int entry = chain;
+        if (r < thr_add) go = add_propose(T, R, C, x, C.prop[chain]);
+        else { go = rem_propose(T, R, C, x, C.prop[chain]); entry |= Q_REM; }
+        if (go) {
+            if (lane == 0) {
+                const int m = T.dmax > 1 ? ldg(&T.dim[x.outer]) : 1;
+                if (m >= 16) C.q_dec0[atomic_add_int(&sc[SC_NQ0], 1)] = entry;
+                else if (m > 1) C.q_dec1[atomic_add_int(&sc[SC_NQ1], 1)] = entry;
+                else C.q_dec2[atomic_add_int(&sc[SC_NQ2], 1)] = entry;
+                if (T.dmax > 1) {                                 // trace jobs: one per 8 outer states, queued by number of steps
+                    const Prop& P = C.prop[chain];
+                    const int rem = (entry & Q_REM) ? 1 : 0, s = P.i1, e = P.i2 + rem;
+                    const int steps = (x.bv > e ? x.bv - e : 0) + (x.kv <= s - 1 ? s - x.kv : 0) + (P.i2 - P.i1 - rem) + (rem ? 0 : 2);
+                    const int ntl = (m + 7) >> 3;
+                    int* q = steps >= 24 ? C.q_tr0 : (steps >= 8 ? C.q_tr1 : C.q_tr2);
+                    const int base = atomic_add_int(&sc[steps >= 24 ? SC_NT0 : (steps >= 8 ? SC_NT1 : SC_NT2)], ntl);
+                    for (int t = 0; t < ntl; ++t) q[base + t] = entry | (t << Q_NTSHIFT);
                 }
             }
-            cta_sync();
-            rare = S.nG >= W || (S.nG > 0 && nrun < W);
+            break;
         }
-        if (rare) {
-            // ---- rare phase: global moves and tau shifts of all parked chains
-            const int ng = S.nG;
-            for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {
-                const int c = S.lG[i], chain = chain_lo + c;
-                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                if (S.kind[c] == 3) step_glob(T, R, C, x); else step_shift(T, R, C, x);
-                post_move(T, R, x, S, c);
-                ctx_store(C, chain, x);
-                if (lane == 0) S.parked[c] = 0;
-            }
-            cta_sync();
-            if (cta_tid() == 0) { S.nG = 0; S.cG = 0; }
-            cta_sync();
-        }
+        post_move(T, R, C, x, chain);
+        --left;
     }
+    ctx_store(C, chain, x);
+}
+
+// one ticket of the trace kernel (blocked traces only): tickets run over the three trace queues, longest jobs first
+W2B_HD void phase_trace(const Tables& T, const Chains& C, int ticket, const int* sc, double* mscratch) {
+    const int n0 = sc[SC_NT0], n1 = sc[SC_NT1];
+    const int entry = ticket < n0 ? C.q_tr0[ticket] : (ticket < n0 + n1 ? C.q_tr1[ticket - n0] : C.q_tr2[ticket - n0 - n1]);
+    trace_job(T, C, entry, mscratch, mscratch + C.ldx * 8, mscratch + C.ldx * 8 + 8);
+}
+
+// one ticket of the decide kernel: tickets [0, nrare) are rare moves, then the three decide queues
+W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const Accum& A, int ticket, const int* sc, long long nsteps,
+                         int log_chain, double* logbuf, double* wscratch, int* iscratch, double* mscratch) {
+    const int lane = lane_id();
+    const int nrare = sc[SC_NRARE], n0 = sc[SC_NQ0], n1 = sc[SC_NQ1];
+    int entry; bool rare = false;
+    if (ticket < nrare) { entry = C.q_rare[ticket]; rare = true; }
+    else if (ticket < nrare + n0) entry = C.q_dec0[ticket - nrare];
+    else if (ticket < nrare + n0 + n1) entry = C.q_dec1[ticket - nrare - n0];
+    else entry = C.q_dec2[ticket - nrare - n0 - n1];
+    const int chain = entry & Q_IDMASK;
+    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+    if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - C.left[chain]) * LOGW;
+    if (!rare && T.dmax > 1) { x.pre = C.ptc + (size_t)chain * 2 * C.dmax; x.mpt = C.ptc + (size_t)chain * 2 * C.dmax; }
+    if (rare) { if (C.kind[chain] == 3) step_glob(T, R, C, x); else step_shift(T, R, C, x); }
+    else if (entry & Q_REM) rem_decide(T, R, C, A, x, C.prop[chain]);
+    else add_decide(T, R, C, A, x, C.prop[chain]);
+    post_move(T, R, C, x, chain);
+    ctx_store(C, chain, x);
+    if (rare && lane == 0) C.parked[chain] = 0;
 }
 
 // init_Trace (Trace.F90:340-701): empty configuration, outer superstate drawn with the empty-trace weights

@@ -87,17 +87,40 @@ W2B_HD void dmma884(double& d0, double& d1, double a, double b) {
 }
 #endif
 
+#if W2B_DEVICE
+// exact renormalisation of a column whose maximum is zero, subnormal or huge (rare): full reduction over the 8 lanes of the column
+W2B_HDN void renorm_slow(double mx, double& sc, double& la, bool& nonzero) {
+    mx = fmax(mx, __shfl_xor_sync(W2B_FULL, mx, 4)); mx = fmax(mx, __shfl_xor_sync(W2B_FULL, mx, 8)); mx = fmax(mx, __shfl_xor_sync(W2B_FULL, mx, 16));
+    sc = 1.0; la = 0.0; nonzero = mx > 0.0;
+    if (nonzero) sc = renorm_pow2(mx, la);
+}
+#endif
+
+// one packed record per (superstate, operator): everything an operator product needs, fetched with two 16-byte loads
+struct alignas(16) OpDesc { int sst_out, d_in, d_out, ev_off; long long op_off; double e0; };
+
 // X(d_in x m) <- O(d_out x d_in) * diag(exp(-(E_c - E_0) dt)) * X, in place; every column is renormalised by a power
 // of two near its largest element and lg[j] += -(E_0 - Egs) dt + e ln2.  `pw` is warp scratch for the d_in propagation
 // factors.  Returns the target block.
-template <class TablesT>
-W2B_HDN int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* X, int ld, double* lg, double* pw, int m) {
-    const int d_in = ldg(&T.dim[sst_in]);
-    const double* ev = T.evals + ldg(&T.offset[sst_in]);
-    const double e0 = ldg(&ev[0]);
-    const int sst_out = (int)ldg(&T.connect[sst_in * T.nops + opc]);
-    const int d_out = ldg(&T.dim[sst_out]);
-    const double* O = T.opdata + ldg(&T.op_off[(size_t)sst_in * T.nops + opc]);
+// Latency / code-size structure (the chains are latency- and instruction-fetch-bound, not throughput-bound): the
+// descriptor is one load; the k-loop is rolled (small code) and holds all <= 4 x 4 output tiles in registers, so every A
+// fragment is fetched once, one k-step ahead of its use, and X is overwritten only after the last k-step.
+template <int NTMAX, class TablesT>
+W2B_HD int mat_apply_inl(const TablesT& T, int sst_in, int opc, double dt, double* X, int ld, double* lg, double* pw, int m) {
+#if W2B_DEVICE
+    const int4* dp = (const int4*)&T.desc[sst_in * T.nops + opc];
+    const int4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
+    const int sst_out = q0.x, d_in = q0.y, d_out = q0.z;
+    const double* ev = T.evals + q0.w;
+    const double* O = T.opdata + (((long long)q1.y << 32) | (unsigned)q1.x);
+    const double e0 = __hiloint2double(q1.w, q1.z);
+#else
+    const OpDesc& D = T.desc[sst_in * T.nops + opc];
+    const int sst_out = D.sst_out, d_in = D.d_in, d_out = D.d_out;
+    const double* ev = T.evals + D.ev_off;
+    const double* O = T.opdata + D.op_off;
+    const double e0 = D.e0;
+#endif
     const double shift = -(e0 - T.egs) * dt;
     if (d_in == 1 && d_out == 1) {                               // scalar link of the chain: one multiply per outer state
         const double o = ldg(&O[0]);
@@ -109,58 +132,78 @@ W2B_HDN int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* 
         wsync();
         return sst_out;
     }
-    for (int c = lane_id(); c < d_in; c += W2B_WARP) pw[c] = c ? w_exp(-(ldg(&ev[c]) - e0) * dt) : 1.0;
-    wsync();
 #if W2B_DEVICE
     const int lane = lane_id(), g = lane >> 2, t = lane & 3;
     const int ntiles = (m + 7) >> 3, mtiles = (d_out + 7) >> 3, ksteps = (d_in + 3) >> 2;
-    for (int nt = 0; nt < ntiles; ++nt) {
-        double acc[4][2];
+    // A fragments of the first k-step are requested before the exp() of the propagation factors
+    double an[4];
+    {
+        const bool cok = t < d_in;
+        const double* ocol = O + t * d_out;
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) { acc[mt][0] = 0.0; acc[mt][1] = 0.0; }
-        const int n = nt * 8 + g;
-        const bool nok = n < m;
-        const double* xcol = X + (size_t)n * ld;
-        for (int ks = 0; ks < ksteps; ++ks) {
-            const int k = ks * 4 + t;
-            const bool kok = k < d_in;
-            const double b = (kok && nok) ? xcol[k] * pw[k] : 0.0;
-            const double* ocol = O + (size_t)k * d_out;
+        for (int mt = 0; mt < 4; ++mt) { const int r = mt * 8 + g; an[mt] = (mt < mtiles && cok && r < d_out) ? ldg(&ocol[r]) : 0.0; }
+    }
+    for (int c = lane; c < d_in; c += W2B_WARP) pw[c] = c ? w_exp(-(ldg(&ev[c]) - e0) * dt) : 1.0;
+    wsync();
+    double acc[NTMAX][4][2];                                       // [column tile][row tile][fragment half]
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
-                if (mt < mtiles) {                                 // warp-uniform
-                    const int r = mt * 8 + g;
-                    const double a = (kok && r < d_out) ? ldg(&ocol[r]) : 0.0;
-                    dmma884(acc[mt][0], acc[mt][1], a, b);
+    for (int nt = 0; nt < NTMAX; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) { acc[nt][mt][0] = 0.0; acc[nt][mt][1] = 0.0; }
+#pragma unroll 1
+    for (int ks = 0; ks < ksteps; ++ks) {
+        double ac[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) ac[mt] = an[mt];
+        if (ks + 1 < ksteps) {                                     // prefetch the next k-step's A fragments
+            const int c = (ks + 1) * 4 + t;
+            const bool cok = c < d_in;
+            const double* ocol = O + c * d_out;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) { const int r = mt * 8 + g; an[mt] = (mt < mtiles && cok && r < d_out) ? ldg(&ocol[r]) : 0.0; }
+        }
+        const int k = ks * 4 + t;
+        const bool kok = k < d_in;
+        const double pk = kok ? pw[k] : 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NTMAX; ++nt) {
+            if (nt < ntiles) {                                     // warp-uniform
+                const int n = nt * 8 + g;
+                const double b = (kok && n < m) ? X[n * ld + k] * pk : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+                    if (mt < mtiles) dmma884(acc[nt][mt][0], acc[nt][mt][1], ac[mt], b);
+            }
+        }
+    }
+    wsync();                                                       // every lane has consumed X: overwrite in place
+#pragma unroll
+    for (int nt = 0; nt < NTMAX; ++nt) {
+        if (nt < ntiles) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int col = nt * 8 + 2 * t + q;
+                double mx = 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) mx = fmax(mx, fabs(acc[nt][mt][q]));     // unused row tiles hold zeros
+                // column maximum over the 8 lanes sharing t: order-preserving compare of the high words gives the exponent
+                int hi = __double2hiint(mx);
+                hi = max(hi, __shfl_xor_sync(W2B_FULL, hi, 4)); hi = max(hi, __shfl_xor_sync(W2B_FULL, hi, 8)); hi = max(hi, __shfl_xor_sync(W2B_FULL, hi, 16));
+                const int ef = hi >> 20;
+                double sc, la; bool nonzero = true;
+                if (wany(col < m && (ef == 0 || ef > 2040))) renorm_slow(mx, sc, la, nonzero);   // zero / subnormal / huge column
+                else { const int e = ef - 1023; sc = __hiloint2double((1023 - e) << 20, 0); la = (double)e * LN2; }
+                if (col < m) {
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) { const int r = mt * 8 + g; if (mt < mtiles && r < d_out) X[col * ld + r] = acc[nt][mt][q] * sc; }
+                    if (g == 0 && nonzero) lg[col] += shift + la;
                 }
             }
         }
-        wsync();                                                   // every lane has consumed its part of this column tile
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int col = nt * 8 + 2 * t + q;
-            double mx = 0.0;
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) mx = fmax(mx, fabs(acc[mt][q]));
-            // column maximum over the 8 lanes sharing t: order-preserving compare of the high words is enough for the exponent
-            int hi = __double2hiint(mx);
-            hi = max(hi, __shfl_xor_sync(W2B_FULL, hi, 4)); hi = max(hi, __shfl_xor_sync(W2B_FULL, hi, 8)); hi = max(hi, __shfl_xor_sync(W2B_FULL, hi, 16));
-            const int ef = hi >> 20;
-            double sc = 1.0, la = 0.0; bool nonzero = true;
-            if (wany(ef == 0 || ef > 2040)) {                      // zero / subnormal / huge column somewhere: exact slow path
-                double mxx = mx;
-                mxx = fmax(mxx, __shfl_xor_sync(W2B_FULL, mxx, 4)); mxx = fmax(mxx, __shfl_xor_sync(W2B_FULL, mxx, 8)); mxx = fmax(mxx, __shfl_xor_sync(W2B_FULL, mxx, 16));
-                if (mxx > 0.0) sc = renorm_pow2(mxx, la); else nonzero = false;
-            } else { const int e = ef - 1023; sc = __hiloint2double((1023 - e) << 20, 0); la = (double)e * LN2; }
-            if (col < m) {
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) { const int r = mt * 8 + g; if (mt < mtiles && r < d_out) X[r + (size_t)col * ld] = acc[mt][q] * sc; }
-                if (g == 0 && nonzero) lg[col] += shift + la;
-            }
-        }
-        wsync();
     }
+    wsync();
 #else
+    for (int c = 0; c < d_in; ++c) pw[c] = c ? w_exp(-(ev[c] - e0) * dt) : 1.0;
     for (int j = 0; j < m; ++j) {
         double* xc = X + (size_t)j * ld;
         double y[MAT_DMAX]; double mx = 0.0;
@@ -177,29 +220,45 @@ W2B_HDN int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* 
     return sst_out;
 }
 
-// Close ket K (block sst, d x m, leading dimension ld, scales klg) with bra B (same block, compact d x m; nullptr = unit
-// vectors e_j at tau = beta) across a propagation of length dt:  tr_j = sum_c B[c,j] exp(-(E_c-E_0) dt) K[c,j].
-// pt receives (log, sign) per outer state, (tlog, tsign) the signed log-sum (addLogTr, Trace.F90:298-309).
 template <class TablesT>
-W2B_HDN void mat_close(const TablesT& T, int sst, double dt, const double* K, int ld, const double* klg, const double* B, const double* blg,
-                      double* pw, int m, double* pt, double& tlog, double& tsign) {
-    const int d = ldg(&T.dim[sst]);
-    const double* ev = T.evals + ldg(&T.offset[sst]);
-    const double e0 = ldg(&ev[0]);
+W2B_HDN int mat_apply(const TablesT& T, int sst_in, int opc, double dt, double* X, int ld, double* lg, double* pw, int m) {
+    return mat_apply_inl<4>(T, sst_in, opc, dt, X, ld, lg, pw, m);
+}
+
+// Close ket K (block sst, d x m, leading dimension ld, scales klg) with bra B (same block, compact d x m; nullptr = unit
+// vectors e_{j0+j} at tau = beta) across a propagation of length dt:  tr_j = sum_c B[c,j] exp(-(E_c-E_0) dt) K[c,j].
+// pt receives (log, sign) per outer state.  K, klg, B, blg, pt address the first of the m columns handled here; j0 is that
+// column's index inside the outer block (the trace kernel works on 8-column tiles).
+template <class TablesT>
+W2B_HD void mat_close_parts(const TablesT& T, int sst, double dt, const double* K, int ld, const double* klg, const double* B, const double* blg,
+                            double* pw, int m, int j0, double* pt) {
+#if W2B_DEVICE
+    const int4* dp = (const int4*)&T.desc[sst * T.nops];
+    const int4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
+    const int d = q0.y;
+    const double* ev = T.evals + q0.w;
+    const double e0 = __hiloint2double(q1.w, q1.z);
+#else
+    const int d = T.desc[sst * T.nops].d_in;
+    const double* ev = T.evals + T.desc[sst * T.nops].ev_off;
+    const double e0 = T.desc[sst * T.nops].e0;
+#endif
     for (int c = lane_id(); c < d; c += W2B_WARP) pw[c] = c ? w_exp(-(ldg(&ev[c]) - e0) * dt) : 1.0;
     wsync();
     for (int j = lane_id(); j < m; j += W2B_WARP) {
         double s;
         if (B) { s = 0.0;
-#pragma unroll 4
-            for (int c = 0; c < d; ++c) s += B[c + (size_t)j * d] * pw[c] * K[c + (size_t)j * ld]; }
-        else s = pw[j] * K[j + (size_t)j * ld];
+#pragma unroll 1
+            for (int c = 0; c < d; ++c) s += B[c + j * d] * pw[c] * K[c + j * ld]; }
+        else s = pw[j0 + j] * K[j0 + j + j * ld];
         if (s != 0.0) { pt[2 * j] = klg[j] + (B ? blg[j] : 0.0) - (e0 - T.egs) * dt + w_log(fabs(s)); pt[2 * j + 1] = s < 0.0 ? -1.0 : 1.0; }
         else { pt[2 * j] = NEG_HUGE; pt[2 * j + 1] = 0.0; }
     }
     wsync();
+}
+// signed log-sum of the per-outer-state parts (addLogTr, Trace.F90:298-309), lane-parallel
+W2B_HDN void parts_sum(const double* pt, int m, double& tlog, double& tsign) {
     if (m == 1) { tlog = pt[0]; tsign = pt[1]; return; }
-    // signed log-sum over the outer states, lane-parallel
     double mx = NEG_HUGE;
     for (int j = lane_id(); j < m; j += W2B_WARP) if (pt[2 * j + 1] != 0.0) mx = fmax(mx, pt[2 * j]);
     mx = wmaxd(mx);
@@ -209,6 +268,12 @@ W2B_HDN void mat_close(const TablesT& T, int sst, double dt, const double* K, in
     sum = wsumd(sum);
     if (sum == 0.0) { tlog = NEG_HUGE; tsign = 0.0; return; }
     tlog = mx + w_log(fabs(sum)); tsign = sum < 0.0 ? -1.0 : 1.0;
+}
+template <class TablesT>
+W2B_HDN void mat_close(const TablesT& T, int sst, double dt, const double* K, int ld, const double* klg, const double* B, const double* blg,
+                      double* pw, int m, double* pt, double& tlog, double& tsign) {
+    mat_close_parts(T, sst, dt, K, ld, klg, B, blg, pw, m, 0, pt);
+    parts_sum(pt, m, tlog, tsign);
 }
 
 }  // namespace w2b

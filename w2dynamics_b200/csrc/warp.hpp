@@ -88,6 +88,8 @@ W2B_HD int wargmax_abs(double x, int idx, double& best) {
 }
 W2B_HD void atomic_add(double* p, double v) { atomicAdd(p, v); }
 W2B_HD void atomic_add(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+W2B_HD int atomic_add_int(int* p, int v) { return atomicAdd(p, v); }
+W2B_HD void atomic_max_int(int* p, int v) { atomicMax(p, v); }
 // CTA-level primitives of the phase scheduler
 W2B_HD void cta_sync() { __syncthreads(); }
 W2B_HD int cta_warp() { return threadIdx.x >> 5; }
@@ -120,6 +122,8 @@ W2B_HD int wscan_incl(int x) { return x; }
 W2B_HD int wargmax_abs(double x, int idx, double& best) { best = std::fabs(x); return idx; }
 W2B_HD void atomic_add(double* p, double v) { *p += v; }
 W2B_HD void atomic_add(unsigned long long* p, unsigned long long v) { *p += v; }
+W2B_HD int atomic_add_int(int* p, int v) { int o = *p; *p += v; return o; }
+W2B_HD void atomic_max_int(int* p, int v) { if (v > *p) *p = v; }
 W2B_HD void cta_sync() {}
 W2B_HD int cta_warp() { return 0; }
 W2B_HD int cta_nwarps() { return 1; }
