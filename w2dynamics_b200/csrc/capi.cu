@@ -463,10 +463,10 @@ int w2b_get_scalar(const char* name, double* out) {
             if (k == "taudiff_max") { *out = E.R.taudiff_max; return; }
             if (k == "egs") { *out = E.at.egs; return; }
             if (k == "gpu_launches") { *out = (double)E.launches; return; }
-            if (k == "cta_warps") { *out = E.sw_warps; return; }
-            if (k == "batch_chains") { *out = E.sw_ncb; return; }
-            if (k == "sweep_grid") { *out = E.sw_grid; return; }
-            if (k == "sweep_smem") { *out = (double)E.sw_smem; return; }
+            if (k == "cta_warps") { *out = E.C.dmax == 1 ? E.ct_warps : E.sw_warps; return; }
+            if (k == "batch_chains") { *out = E.ct_ncb; return; }
+            if (k == "sweep_grid") { *out = E.C.dmax == 1 ? E.ct_grid : E.sw_grid; return; }
+            if (k == "sweep_smem") { *out = (double)(E.C.dmax == 1 ? E.ct_smem : E.sw_smem); return; }
             if (k == "rounds") { *out = (double)E.rounds; return; }
             if (k.rfind("cnt_", 0) == 0) {
                 static const char* names[C_NCNT] = {"try_add", "try_rem", "try_glob", "try_shift", "acc_add", "acc_rem", "acc_glob", "acc_shift",

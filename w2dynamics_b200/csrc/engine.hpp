@@ -88,6 +88,39 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_init(Tables T, Run R, Ch
 #else
 #define W2B_HOSTDEV
 #endif
+// ---- persistent CTA-scheduler kernel (1x1 blocks)
+W2B_HOSTDEV inline size_t sched_bytes(int ncb) { return (size_t)ncb * (sizeof(Prop) + sizeof(int) + 5 * sizeof(short) + 2) + 64; }
+W2B_HOSTDEV inline void sched_carve(CtaShared& S, char* base, int ncb) {
+    S.prop = (Prop*)base; base += (size_t)ncb * sizeof(Prop);
+    S.left = (int*)base; base += (size_t)ncb * sizeof(int);
+    S.lA = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.lR = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.lA2 = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.lR2 = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.lG = (short*)base; base += (size_t)ncb * sizeof(short);
+    S.parked = (unsigned char*)base; base += ncb;
+    S.kind = (unsigned char*)base;
+}
+#if W2B_DEVICE
+// persistent sweep kernel: every CTA serves batches of ncb chains (batch b -> chains [b*ncb, (b+1)*ncb))
+__global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T, Run R, Chains C, Accum A, long long nsteps, int wdoubles, int ncb, int nbatch,
+                                                             int log_chain, double* logbuf) {
+    extern __shared__ double smem[];
+    __shared__ CtaShared S;
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    double* ws = smem + (size_t)warp * wdoubles;
+    int* is = (int*)(ws + 3 * C.kcap);
+    if (threadIdx.x == 0) { CtaShared tmp; sched_carve(tmp, (char*)(smem + (size_t)W * wdoubles), ncb);
+        S.prop = tmp.prop; S.left = tmp.left; S.lA = tmp.lA; S.lR = tmp.lR; S.lA2 = tmp.lA2; S.lR2 = tmp.lR2; S.lG = tmp.lG; S.parked = tmp.parked; S.kind = tmp.kind; }
+    __syncthreads();
+    for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+        const int lo = b * ncb, nloc = min(ncb, C.nchains - lo);
+        cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws, is, ws + 3 * C.kcap, log_chain, logbuf);
+        __syncthreads();
+    }
+}
+#endif
+// ---- round kernels (blocked traces)
 constexpr int PROPOSE_WARPS = 8;      // warps per CTA of the propose kernel (no shared memory)
 constexpr int TRACE_WARPS = 4;        // warps per CTA of the trace kernel (one work matrix per warp in shared memory)
 constexpr int DECIDE_WARPS = 4;       // warps per CTA of the decide kernel (one work matrix per warp in shared memory)
@@ -98,7 +131,8 @@ __global__ void __launch_bounds__(256) k_sweep_begin(Chains C, long long nsteps)
     if (c < 2 * SC_STRIDE) C.sched[c] = 0;
 }
 // propose phase of one round: one warp per chain
-__global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(Tables T, Run R, Chains C, long long nsteps, int parity, int log_chain, double* logbuf) {
+__global__ void __launch_bounds__(PROPOSE_WARPS * 32, 4) k_propose(Tables T, Run R, Chains C, long long nsteps, int parity, int log_chain, double* logbuf) {
+    if (blockIdx.x == 0 && threadIdx.x < SC_STRIDE) C.sched[(parity ^ 1) * SC_STRIDE + threadIdx.x] = 0;     // counters of the next round
     const int chain = blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
     if (chain < C.nchains) phase_propose(T, R, C, chain, nsteps, parity, log_chain, logbuf);
 }
@@ -110,10 +144,19 @@ __global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_decide(Tables T, Run R
     double* ws = smem + (size_t)warp * wdoubles;
     int* is = (int*)(ws + 3 * C.kcap + mdoubles);
     int* sc = C.sched + parity * SC_STRIDE;
-    if (blockIdx.x == 0 && threadIdx.x < SC_STRIDE) C.sched[(parity ^ 1) * SC_STRIDE + threadIdx.x] = 0;     // counters of the next round
-    const int total = sc[SC_NRARE] + sc[SC_NQ0] + sc[SC_NQ1] + sc[SC_NQ2];
+    const int total = sc[SC_NRFIN] + sc[SC_NQ0] + sc[SC_NQ1] + sc[SC_NQ2];
     for (int t = wgrab(&sc[SC_TICKET]); t < total; t = wgrab(&sc[SC_TICKET]))
-        phase_decide(T, R, C, A, t, sc, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap);
+        phase_decide(T, R, C, A, t, parity, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap);
+}
+// global moves / tau shifts, on their own stream beside the round pipeline: scan the chain states, serve ST_RARE_NEW
+__global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T, Run R, Chains C, long long nsteps, int wdoubles, int mdoubles,
+                                                              int log_chain, double* logbuf) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    double* ws = smem + (size_t)warp * wdoubles;
+    int* is = (int*)(ws + 3 * C.kcap + mdoubles);
+    for (int c = blockIdx.x * DECIDE_WARPS + warp; c < C.nchains; c += gridDim.x * DECIDE_WARPS)
+        phase_rare(T, R, C, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap);
 }
 // trace phase of one round (blocked traces): operator products of every surviving proposal on the FP64 tensor pipe
 __global__ void __launch_bounds__(TRACE_WARPS * 32, 8) k_trace(Tables T, Chains C, int tdoubles, int parity) {
@@ -121,7 +164,7 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 8) k_trace(Tables T, Chains 
     double* ws = smem + (size_t)(threadIdx.x >> 5) * tdoubles;
     int* sc = C.sched + parity * SC_STRIDE;
     const int total = sc[SC_NT0] + sc[SC_NT1] + sc[SC_NT2];
-    for (int t = wgrab(&sc[SC_TTICKET]); t < total; t = wgrab(&sc[SC_TTICKET])) phase_trace(T, C, t, sc, ws);
+    for (int t = wgrab(&sc[SC_TTICKET]); t < total; t = wgrab(&sc[SC_TTICKET])) phase_trace(T, C, t, parity, ws);
 }
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_measure(Tables T, Run R, Chains C, Accum A, int wdoubles, int mdoubles) {
     extern __shared__ double smem[];
@@ -255,13 +298,13 @@ public:
             C.pt = keep(dev_alloc<double>((size_t)nc * 2 * C.dmax));
         }
         C.left = keep(dev_alloc<int>(nc)); C.parked = keep(dev_alloc<unsigned char>(nc)); C.kind = keep(dev_alloc<unsigned char>(nc));
-        C.prop = keep(dev_alloc<Prop>(nc));
-        C.q_rare = keep(dev_alloc<int>(nc)); C.q_dec0 = keep(dev_alloc<int>(nc)); C.q_dec1 = keep(dev_alloc<int>(nc)); C.q_dec2 = keep(dev_alloc<int>(nc));
+        C.prop = keep(dev_alloc<Prop>(nc)); C.rjob = keep(dev_alloc<RareJob>(nc));
+        C.q_rare = keep(dev_alloc<int>((size_t)2 * nc)); C.q_rfin = keep(dev_alloc<int>((size_t)2 * nc)); C.q_dec0 = keep(dev_alloc<int>(nc)); C.q_dec1 = keep(dev_alloc<int>(nc)); C.q_dec2 = keep(dev_alloc<int>(nc));
         C.sched = keep(dev_alloc<int>(2 * SC_STRIDE));
         C.ptc = nullptr; C.q_tr0 = C.q_tr1 = C.q_tr2 = nullptr;
         if (at.dmax > 1) {
             C.ptc = keep(dev_alloc<double>((size_t)nc * 2 * at.dmax));
-            C.q_tr0 = keep(dev_alloc<int>((size_t)nc * 4)); C.q_tr1 = keep(dev_alloc<int>((size_t)nc * 4)); C.q_tr2 = keep(dev_alloc<int>((size_t)nc * 4));
+            C.q_tr0 = keep(dev_alloc<int>((size_t)nc * 8)); C.q_tr1 = keep(dev_alloc<int>((size_t)nc * 8)); C.q_tr2 = keep(dev_alloc<int>((size_t)nc * 8));
         }
         int wints = kcap + 32 + nsst;
         wdoubles = 3 * kcap + mat_doubles(C, true) + (wints + 1) / 2;
@@ -321,10 +364,67 @@ public:
     void get_accpair(std::vector<unsigned long long>& out) { sync(); out.resize((size_t)T.nf * R.naccpair); d2h(out.data(), A.accpair, out.size()); }
     void zero_accum() { dev_zero(A.base, (size_t)R.nbins * accum_doubles); }
 
+    // ---- 1x1 blocks: persistent CTA-scheduler kernel; geometry: W warps per CTA, batches of ncb chains, persistent grid
+    int ct_warps = 1, ct_ncb = 1, ct_nbatch = 1, ct_grid = 1; size_t ct_smem = 0; bool ct_ready = false;
+    void plan_cta() {
+        const int nc = C.nchains;
+#if W2B_DEVICE
+        int dev = 0, nsm = 1, smem_max = 48 * 1024;
+        W2B_CUDA_CHECK(cudaGetDevice(&dev));
+        W2B_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        W2B_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        int W = opt.cta_warps > 0 ? opt.cta_warps : 32;
+        const size_t per_warp = (size_t)wdoubles_sweep * sizeof(double);
+        while (W > 1 && W * per_warp + sched_bytes(8 * W) > (size_t)smem_max - 1024) --W;
+        if (W > MAX_CTA_THREADS / 32) W = MAX_CTA_THREADS / 32;
+        int target = opt.batch_chains > 0 ? opt.batch_chains : 8 * W;
+        size_t sm = W * per_warp + sched_bytes(target);
+        W2B_CUDA_CHECK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min((size_t)smem_max, sm + 4096)));
+        int occ = 1;
+        W2B_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, W * 32, sm));
+        if (occ < 1) occ = 1;
+        const int slots = nsm * occ;
+        int rounds = (nc + slots * target - 1) / (slots * target);
+        int ncb = (nc + slots * rounds - 1) / (slots * rounds);
+        if (ncb < 1) ncb = 1;
+        if (ncb > target) ncb = target;
+        ct_warps = W; ct_ncb = ncb; ct_nbatch = (nc + ncb - 1) / ncb; ct_grid = std::min(ct_nbatch, slots);
+        ct_smem = W * per_warp + sched_bytes(ncb);
+#else
+        ct_warps = 1; ct_ncb = opt.batch_chains > 0 ? opt.batch_chains : 4; ct_nbatch = (nc + ct_ncb - 1) / ct_ncb; ct_grid = 1;
+#endif
+        ct_ready = true;
+    }
+
+    // advance every chain by nsteps moves; optionally record the replay log of one chain
+    void sweep_cta(long long nsteps, int log_chain, double* log_host) {
+        if (!ct_ready) plan_cta();
+        double* dlog = nullptr;
+        if (log_chain >= 0) dlog = dev_alloc<double>((size_t)nsteps * LOGW);
+#if W2B_DEVICE
+        k_sweep<<<ct_grid, ct_warps * 32, ct_smem>>>(T, R, C, A, nsteps, wdoubles_sweep, ct_ncb, ct_nbatch, log_chain, dlog); ++launches;
+        W2B_CUDA_CHECK(cudaGetLastError());
+#else
+        std::vector<double> ws(wdoubles + 8);
+        std::vector<char> sb(sched_bytes(ct_ncb));
+        CtaShared S{}; sched_carve(S, sb.data(), ct_ncb);
+        for (int b = 0; b < ct_nbatch; ++b) {
+            const int lo = b * ct_ncb, nloc = std::min(ct_ncb, C.nchains - lo);
+            cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, log_chain, dlog);
+        }
+#endif
+        if (log_chain >= 0) { sync(); d2h(log_host, dlog, (size_t)nsteps * LOGW); dev_free(dlog); }
+    }
+
+
+    // ---- blocked traces: round kernels
     // decide-kernel geometry: persistent grid of DECIDE_WARPS-warp CTAs, as many as fit per SM
     int sw_warps = DECIDE_WARPS, sw_ncb = 0, sw_nbatch = 0, sw_grid = 1; size_t sw_smem = 0; bool sw_ready = false;
     int* h_sched = nullptr;            // pinned host copy of one counter set
-    int tr_doubles = 0, tr_grid = 1; size_t tr_smem = 0;   // trace kernel: per-warp work space, grid, shared memory
+#if W2B_DEVICE
+    cudaStream_t rare_stream = nullptr; cudaEvent_t ev_prop[2] = {nullptr, nullptr}, ev_rare[2] = {nullptr, nullptr};
+#endif
+    int tr_doubles = 0, tr_grid = 1, rp_grid = 1; size_t tr_smem = 0;   // trace kernel: per-warp work space, grid, shared memory
     long long rounds = 0;              // rounds launched so far (bench accounting)
     void plan_sweep() {
 #if W2B_DEVICE
@@ -340,6 +440,12 @@ public:
         sw_grid = std::min(nsm * occ, (C.nchains + DECIDE_WARPS - 1) / DECIDE_WARPS);
         sw_warps = occ * DECIDE_WARPS;
         if (!h_sched) W2B_CUDA_CHECK(cudaMallocHost((void**)&h_sched, SC_STRIDE * sizeof(int)));
+        if (!rare_stream) {
+            W2B_CUDA_CHECK(cudaStreamCreateWithFlags(&rare_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) { W2B_CUDA_CHECK(cudaEventCreateWithFlags(&ev_prop[i], cudaEventDisableTiming)); W2B_CUDA_CHECK(cudaEventCreateWithFlags(&ev_rare[i], cudaEventDisableTiming)); }
+        }
+        W2B_CUDA_CHECK(cudaFuncSetAttribute(k_rare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem));
+        rp_grid = std::max(1, std::min(nsm, C.nchains / (8 * DECIDE_WARPS) + 1));
         if (C.dmax > 1) {
             tr_doubles = C.ldx * 8 + 8 + MAT_DMAX;
             tr_smem = (size_t)TRACE_WARPS * tr_doubles * sizeof(double);
@@ -347,6 +453,7 @@ public:
             int occt = 1;
             W2B_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occt, k_trace, TRACE_WARPS * 32, tr_smem));
             tr_grid = std::min(nsm * std::max(1, occt), (C.nchains + TRACE_WARPS - 1) / TRACE_WARPS);
+
         }
 #else
         if (!h_sched) h_sched = (int*)std::calloc(SC_STRIDE, sizeof(int));
@@ -356,8 +463,9 @@ public:
 
     // advance every chain by nsteps moves; optionally record the replay log of one chain
     void sweep(long long nsteps, int log_chain = -1, double* log_host = nullptr) {
-        if (!sw_ready) plan_sweep();
         if (nsteps <= 0) return;
+        if (C.dmax == 1) { sweep_cta(nsteps, log_chain, log_host); return; }
+        if (!sw_ready) plan_sweep();
         double* dlog = nullptr;
         if (log_chain >= 0) dlog = dev_alloc<double>((size_t)nsteps * LOGW);
         const int nc = C.nchains, prun = std::max(1, R.propose_run);
@@ -376,17 +484,24 @@ public:
                 const int parity = (int)(round & 1);
 #if W2B_DEVICE
                 k_propose<<<gp, PROPOSE_WARPS * 32>>>(T, R, C, nsteps, parity, log_chain, dlog);
+                // global moves / tau shifts drawn in this round: served on the rare stream, never waited for by the rounds
+                W2B_CUDA_CHECK(cudaEventRecord(ev_prop[parity], 0));
+                W2B_CUDA_CHECK(cudaStreamWaitEvent(rare_stream, ev_prop[parity], 0));
+                k_rare<<<rp_grid, DECIDE_WARPS * 32, sw_smem, rare_stream>>>(T, R, C, nsteps, wdoubles_sweep, md, log_chain, dlog);
+                ++launches;
                 if (C.dmax > 1) { k_trace<<<tr_grid, TRACE_WARPS * 32, tr_smem>>>(T, C, tr_doubles, parity); ++launches; }
                 k_decide<<<sw_grid, DECIDE_WARPS * 32, sw_smem>>>(T, R, C, A, nsteps, wdoubles_sweep, md, parity, log_chain, dlog);
                 launches += 2;
 #else
+                for (int i2 = 0; i2 < SC_STRIDE; ++i2) C.sched[(parity ^ 1) * SC_STRIDE + i2] = 0;
                 for (int c = 0; c < nc; ++c) phase_propose(T, R, C, c, nsteps, parity, log_chain, dlog);
                 int* sc = C.sched + parity * SC_STRIDE;
-                for (int i2 = 0; i2 < SC_STRIDE; ++i2) C.sched[(parity ^ 1) * SC_STRIDE + i2] = 0;
-                const int total = sc[SC_NRARE] + sc[SC_NQ0] + sc[SC_NQ1] + sc[SC_NQ2];
-                if (C.dmax > 1) for (int t = 0; t < sc[SC_NT0] + sc[SC_NT1] + sc[SC_NT2]; ++t) phase_trace(T, C, t, sc, ws.data() + 3 * C.kcap);
+                for (int c = 0; c < nc; ++c)
+                    phase_rare(T, R, C, c, nsteps, log_chain, dlog, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);
+                if (C.dmax > 1) for (int t = 0; t < sc[SC_NT0] + sc[SC_NT1] + sc[SC_NT2]; ++t) phase_trace(T, C, t, parity, ws.data() + 3 * C.kcap);
+                const int total = sc[SC_NRFIN] + sc[SC_NQ0] + sc[SC_NQ1] + sc[SC_NQ2];
                 for (int t = 0; t < total; ++t)
-                    phase_decide(T, R, C, A, t, sc, nsteps, log_chain, dlog, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);
+                    phase_decide(T, R, C, A, t, parity, nsteps, log_chain, dlog, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);
 #endif
             }
             rounds += chunk;
@@ -398,9 +513,12 @@ public:
 #else
             std::memcpy(h_sched, C.sched + ((round - 1) & 1) * SC_STRIDE, SC_STRIDE * sizeof(int));
 #endif
-            if (h_sched[SC_NRUN] == 0) break;
+            if (h_sched[SC_NRUN] == 0) break;                 // nothing runnable and nothing in flight on the rare stream
             chunk = std::max<long long>(1, (long long)h_sched[SC_MAXLEFT] / prun);
         }
+#if W2B_DEVICE
+        W2B_CUDA_CHECK(cudaStreamSynchronize(rare_stream));       // the last rare move may still be storing its chain record
+#endif
         if (log_chain >= 0) { sync(); d2h(log_host, dlog, (size_t)nsteps * LOGW); dev_free(dlog); }
     }
 

@@ -76,8 +76,18 @@ struct Prop {
     int f, i1, i2, p1, p2, begin_sst, nother, type1;
 };
 
+// a global move / tau shift between its two halves (prepare -> trace kernel -> finish)
+struct RareJob {
+    double dt, factor, dn_log, dn_sign;
+    int kind, new_outer, type, stored;       // kind 3 = global move, 4 = tau shift; stored: the trace kernel filled the ket caches of the new configuration
+    int knew[NF_MAX];
+};
+
 // round scheduler counters (device memory, two sets used in alternation by consecutive rounds)
-enum { SC_NRARE = 0, SC_NQ0, SC_NQ1, SC_NQ2, SC_TICKET, SC_NRUN, SC_MAXLEFT, SC_TTICKET, SC_NT0, SC_NT1, SC_NT2, SC_STRIDE = 16 };
+enum { SC_NRARE = 0, SC_NQ0, SC_NQ1, SC_NQ2, SC_TICKET, SC_NRUN, SC_MAXLEFT, SC_TTICKET, SC_NT0, SC_NT1, SC_NT2, SC_NRFIN, SC_STRIDE = 16 };
+// per-chain scheduling state (Chains::parked): global moves / tau shifts leave the round pipeline and come back through these states
+enum { ST_RUN = 0, ST_RARE_NEW = 1, ST_RARE_TRACE = 3, ST_RARE_QUEUED = 4, ST_RARE_DONE = 5 };
+constexpr int Q_RARE = 1 << 29;      // trace-queue entry of a global move / tau shift (whole sequence, no caches)
 constexpr int Q_REM = 1 << 30;       // decide-queue entry = chain id | Q_REM for a removal
 constexpr int Q_NTSHIFT = 26;         // trace-queue entry: + column tile << Q_NTSHIFT
 constexpr int Q_IDMASK = (1 << 26) - 1;
@@ -98,8 +108,8 @@ struct Chains {
     double* pt;                                                // [chain][2*dmax] (log, sign) of every outer state's trace contribution
     int mstride, dmax;
     // round scheduler: moves left in the current sweep, rare-move flags, proposals, work queues, counters
-    int* left; unsigned char* parked; unsigned char* kind; Prop* prop;
-    int* q_rare; int* q_dec0; int* q_dec1; int* q_dec2; int* sched;
+    int* left; unsigned char* parked; unsigned char* kind; Prop* prop; RareJob* rjob;
+    int* q_rare; int* q_rfin; int* q_dec0; int* q_dec1; int* q_dec2; int* sched;      // q_rare, q_rfin and the trace queues: one buffer per counter set
     double* ptc;                                               // trace kernel results: per-outer-state parts (log, sign) of the proposed configuration [chain][2*dmax]
     int* q_tr0; int* q_tr1; int* q_tr2;                        // trace jobs (chain | column tile | removal flag) by number of steps: long, medium, short
     int ldx, xdoubles;                                         // work matrix: leading dimension (4 mod 16) and size ldx * dmax
@@ -435,10 +445,20 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
     const short* sst = C.op_sst + (size_t)chain * C.ops_cap; const unsigned short* slot = C.op_slot + (size_t)chain * C.ops_cap;
     double* ket = C.ket + (size_t)chain * C.ops_cap * C.mstride; double* bra = C.bra + (size_t)chain * C.ops_cap * C.mstride;
     double* ketlg = C.ketlg + (size_t)chain * C.ops_cap * C.dmax; double* bralg = C.bralg + (size_t)chain * C.ops_cap * C.dmax;
-    const int n = ih[IH_NOPS], outer = ih[IH_OUTER], kv = ih[IH_KV], bv = ih[IH_BV];
+    const bool rare = (entry & Q_RARE) != 0;
+    const int n = ih[IH_NOPS];
+    int outer = ih[IH_OUTER], kv = ih[IH_KV], bv = ih[IH_BV];
     const Prop& P = C.prop[chain];
-    const int i1 = P.i1, i2 = P.i2;
-    const int s = i1, e = rem ? i2 + 1 : i2, lo = rem ? i1 + 1 : i1, hi = i2, nA = rem ? 0 : 1;
+    int i1 = P.i1, i2 = P.i2;
+    bool store_seg = false;
+    if (rare) {                                                   // whole (relabelled / shifted) sequence from the identity, no caches used
+        const RareJob& J = C.rjob[chain];
+        outer = J.new_outer; kv = 0; bv = n; i1 = 0; i2 = n;
+        code = C.sc_code + (size_t)chain * C.ops_cap;
+        if (J.kind == 4) tau = C.sc_tau + (size_t)chain * C.ops_cap;
+        store_seg = J.stored != 0;
+    }
+    const int s = i1, e = (rem && !rare) ? i2 + 1 : i2, lo = (rem && !rare) ? i1 + 1 : i1, hi = i2, nA = (rem || rare) ? 0 : 1;
     const double tA = P.t1, tB = P.t2;
     const int codeA = P.f * 2 + P.type1, codeB = P.f * 2 + (1 - P.type1);
     const int m = ldg(&T.dim[outer]), ld = C.ldx;
@@ -463,7 +483,10 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
                 const int u = q - nb - nk;
                 double t, tp;
                 if (u < nA) { r_opc = codeA; t = tA; tp = s == 0 ? 0.0 : tau[s - 1]; }
-                else if (u - nA < hi - lo) { const int i = lo + u - nA; r_opc = (int)code[i]; t = tau[i]; tp = u == 0 ? (s == 0 ? 0.0 : tau[s - 1]) : (u - nA == 0 ? tA : tau[i - 1]); }
+                else if (u - nA < hi - lo) {
+                    const int i = lo + u - nA; r_opc = (int)code[i]; t = tau[i]; tp = u == 0 ? (s == 0 ? 0.0 : tau[s - 1]) : (u - nA == 0 ? tA : tau[i - 1]);
+                    if (store_seg) r_slot = i | (1 << 16);      // accepted tau shifts reset the slot map to the identity: operator i <-> slot i
+                }
                 else { r_opc = codeB; t = tB; tp = hi > lo ? tau[hi - 1] : tA; }
                 r_dt = t - tp;
             }
@@ -964,10 +987,13 @@ W2B_HDN void rebuild_inverses(const Tables& T, const Chains& C, Ctx& x, const do
 }
 
 // ------------------------------------------------------------------ StepGlob (CTQMC.F90:4433-4554)
-W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
+// Split in two halves around the local trace of the proposed configuration so that blocked traces can run in the trace
+// kernel: prepare (update choice, relabelling, quantum numbers, determinant from scratch) returns true when a trace is
+// needed; finish takes (log, sign) of that trace, draws the Metropolis number and applies the update.
+W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J) {
     log_begin(x, 3);
     bump(x, C_TRYGLOB);
-    if (x.n == 0) { log_end(x, 2); return; }
+    if (x.n == 0) { log_end(x, 2); return false; }
     const int nf = T.nf, nb = T.nb;
     int* gu = x.wI + C.kcap;               // gu[0] = c<->c^dag flip, gu[1..nf] = target flavour (bit index + 1)
     const double r = x.rng.next();
@@ -1020,7 +1046,7 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
             pold += wsum(oko ? 1 : 0); pnew += wsum(okn ? 1 : 0);
         }
         wsync();
-        if (pold <= 0) { x.err |= ERR_GLOBAL_QN; log_end(x, 2); return; }
+        if (pold <= 0) { x.err |= ERR_GLOBAL_QN; log_end(x, 2); return false; }
         if (pnew > 0) {
             factor = (double)pnew / (double)pold;
             int kk = x.rng.randint(1, pnew);
@@ -1028,15 +1054,14 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
             walk_store(T, x.sc_code, 0, x.n, new_outer, x.sc_sst, 0);
         }
     }
-    if (factor == 0.0) { bump(x, C_QNGLOB); log_end(x, 2); return; }
+    if (factor == 0.0) { bump(x, C_QNGLOB); log_end(x, 2); return false; }
     long long sumk2 = 0; for (int f = 0; f < nf; ++f) sumk2 += (long long)x.ih[IH_KF + f] * x.ih[IH_KF + f];
     bump_bytes(x, 8ll * sumk2);                   // build Delta_new (write)
     // relabelled flavour tau arrays and orders
-    int* knew = x.wI + C.kcap + 16;
     for (int f = 0; f < nf; ++f) {
         int b = f >> 1, s = f & 1, g = gu[b + nb * s + 1] - 1, f2 = (g % nb) * 2 + g / nb;
         int k = x.ih[IH_KF + f];
-        if (x.lane == 0) knew[f2] = k;
+        if (x.lane == 0) J.knew[f2] = k;
         const double* oc = x.tc + (size_t)f * C.kcap; const double* oa = x.ta + (size_t)f * C.kcap;
         double* nc = x.sc_tc + (size_t)f2 * C.kcap; double* na = x.sc_ta + (size_t)f2 * C.kcap;
         for (int i = x.lane; i < k; i += W2B_WARP) { nc[i] = flip ? oa[i] : oc[i]; na[i] = flip ? oc[i] : oa[i]; }
@@ -1046,25 +1071,30 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
     // from an LU of the stored inverses (get_FullLogDet, Trace.F90:2665-2685); the tracked Det is the same number up to the
     // rounding of the fast updates (pinned by the from-scratch tests), so the second LU is not repeated here.
     double dn_log, dn_sign;
-    rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, knew, false, dn_log, dn_sign);
+    rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, J.knew, false, dn_log, dn_sign);
+    if (x.lane == 0) { J.kind = 3; J.new_outer = new_outer; J.type = type; J.factor = factor; J.dn_log = dn_log; J.dn_sign = dn_sign; J.stored = 0; }
+    wsync();
+    return true;
+}
+W2B_HDN void step_glob_finish(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, double tn_log, double tn_sign) {
+    const int nf = T.nf, new_outer = J.new_outer;
+    const double dn_log = J.dn_log, dn_sign = J.dn_sign;
     const double dr_log = dn_log - x.det_log, dr_sign = dn_sign * x.det_sign;
-    double tn_log, tn_sign;
-    if (T.dmax > 1) full_trace(T, x, x.tau, x.sc_code, x.n, new_outer, tn_log, tn_sign);
-    else trace_full_scalar(T, x.tau, x.sc_code, x.sc_sst, x.n, new_outer, tn_log, tn_sign);
     const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
-    const double prob = fabs(w_exp(trr_log + dr_log) * factor);
+    const double prob = fabs(w_exp(trr_log + dr_log) * J.factor);
     const double rand = x.rng.next();
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 17, rand);
     if (!(rand < prob)) { log_end(x, 0); return; }
     // ---- accept
+    long long sumk2 = 0; for (int f = 0; f < nf; ++f) sumk2 += (long long)x.ih[IH_KF + f] * x.ih[IH_KF + f];
     bump_bytes(x, 8ll * sumk2);
     for (int i = x.lane; i < x.n; i += W2B_WARP) { x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
     for (int f = 0; f < nf; ++f) {
-        int k = knew[f];
+        int k = J.knew[f];
         for (int i = x.lane; i < k; i += W2B_WARP) { x.tc[(size_t)f * C.kcap + i] = x.sc_tc[(size_t)f * C.kcap + i]; x.ta[(size_t)f * C.kcap + i] = x.sc_ta[(size_t)f * C.kcap + i]; }
     }
     wsync();
-    if (x.lane == 0) for (int f = 0; f < nf; ++f) x.ih[IH_KF + f] = knew[f];
+    if (x.lane == 0) for (int f = 0; f < nf; ++f) x.ih[IH_KF + f] = J.knew[f];
     wsync();
     double l2, s2;
     rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
@@ -1078,8 +1108,8 @@ W2B_HDN void step_glob(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
     log_end(x, 1);
 }
 
-// ------------------------------------------------------------------ StepShiftTau (CTQMC.F90:4557-4835)
-W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) {
+// ------------------------------------------------------------------ StepShiftTau (CTQMC.F90:4557-4835), same two halves
+W2B_HDN bool step_shift_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J) {
     log_begin(x, 4);
     if (x.n == 0) {                        // StepChangeOuter CTQMC.F90:4570-4638
         const double rand = x.rng.next();
@@ -1089,11 +1119,11 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
         if (T.dmax > 1) empty_parts(T, x, pick);
         update_cfgsign(T, x);
         log_set(x, 17, rand); log_end(x, 1);
-        return;
+        return false;
     }
     const double dt = x.rng.next() * T.beta;
     log_set(x, 2, dt);
-    if (dt == 0.0 || dt == T.beta) { log_end(x, 2); return; }
+    if (dt == 0.0 || dt == T.beta) { log_end(x, 2); return false; }
     bump(x, C_TRYSHIFT);
     const int n = x.n;
     const int nwrap = count_lt(x.tau, n, dt);                     // operators passing through tau = 0
@@ -1104,19 +1134,26 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
         double t = x.tau[src] - dt; if (t < 0.0) t += T.beta;     // modulo(tau - dt, beta)
         x.sc_tau[i] = t; x.sc_code[i] = x.code[src]; x.sc_sst[i] = x.sst[src];
     }
+    if (x.lane == 0) { J.kind = 4; J.dt = dt; J.new_outer = new_outer; J.stored = 0; }
     wsync();
+    return true;
+}
+W2B_HDN void step_shift_finish(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, double tn_log, double tn_sign) {
+    const double dt = J.dt;
+    const int n = x.n, new_outer = J.new_outer;
     const int wp_old = x.wpos; const double wmin_old = x.wmin, wmax_old = x.wmax;
     const int sh = ((int)floor((dt / T.beta) * (double)(R.num_windows + 1))) % R.num_windows;
     x.wpos = ((wp_old - sh) % R.num_windows + R.num_windows) % R.num_windows;
     set_window_edges(T, R, x);
-    double tn_log, tn_sign;
-    if (T.dmax > 1) full_trace(T, x, x.sc_tau, x.sc_code, n, new_outer, tn_log, tn_sign);
-    else trace_full_scalar(T, x.sc_tau, x.sc_code, x.sc_sst, n, new_outer, tn_log, tn_sign);
     const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
     const double prob = fabs(trr_sign * w_exp(trr_log));
     const double rand = x.rng.next();
     log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 17, rand);
-    if (!(rand < prob)) { x.wpos = wp_old; x.wmin = wmin_old; x.wmax = wmax_old; log_end(x, 0); return; }
+    if (!(rand < prob)) {
+        x.wpos = wp_old; x.wmin = wmin_old; x.wmax = wmax_old;
+        if (J.stored) slots_reset(C, x);                          // the trace kernel overwrote the caches with the rejected configuration
+        log_end(x, 0); return;
+    }
     // ---- accept: update_InvFullHybrShiftTau_diag Trace.F90:2355-2457 (cyclic roll + negation of wrapped rows/columns)
     double detrat = 1.0;
     for (int f = 0; f < T.nf; ++f) {
@@ -1142,10 +1179,10 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
         // rotate the flavour tau arrays
         double* scc = x.sc_tc + (size_t)f * C.kcap; double* sca = x.sc_ta + (size_t)f * C.kcap;
         for (int i = x.lane; i < k; i += W2B_WARP) {
-            int s1 = i + w1; double a1 = 0.0; if (s1 >= k) { s1 -= k; a1 = T.beta; }
-            int s2 = i + w2; double a2 = 0.0; if (s2 >= k) { s2 -= k; a2 = T.beta; }
-            double v1 = tc[s1] - dt; if (v1 < 0.0) v1 += T.beta; (void)a1;
-            double v2 = ta[s2] - dt; if (v2 < 0.0) v2 += T.beta; (void)a2;
+            int s1 = i + w1; if (s1 >= k) s1 -= k;
+            int s2 = i + w2; if (s2 >= k) s2 -= k;
+            double v1 = tc[s1] - dt; if (v1 < 0.0) v1 += T.beta;
+            double v2 = ta[s2] - dt; if (v2 < 0.0) v2 += T.beta;
             scc[i] = v1; sca[i] = v2;
         }
         wsync();
@@ -1156,13 +1193,23 @@ W2B_HDN void step_shift(const Tables& T, const Run& R, const Chains& C, Ctx& x) 
     wsync();
     x.outer = new_outer;
     x.tr_log = tn_log; x.tr_sign = tn_sign; x.det_sign *= detrat;
-    if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); }
+    if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); if (J.stored) x.kv = n; }   // kets of the shifted sequence are already cached
     x.npairs = -1;
     x.perm = perm_full(x.code, x.n);
     x.palt = 0; for (int f = 0; f < T.nf; ++f) x.palt |= palt_flavour(C, x, f) << f;
     update_cfgsign(T, x);
     bump(x, C_ACCSHIFT);
     log_end(x, 1);
+}
+// both halves back to back with the trace in between (1x1 blocks; host paths that do not use the trace kernel)
+W2B_HD void step_rare(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, int kind) {
+    const bool go = kind == 3 ? step_glob_prepare(T, R, C, x, J) : step_shift_prepare(T, R, C, x, J);
+    if (!go) return;
+    const double* tau = kind == 3 ? x.tau : x.sc_tau;
+    double tn_log, tn_sign;
+    if (T.dmax > 1) full_trace(T, x, tau, x.sc_code, x.n, J.new_outer, tn_log, tn_sign);
+    else trace_full_scalar(T, tau, x.sc_code, x.sc_sst, x.n, J.new_outer, tn_log, tn_sign);
+    if (kind == 3) step_glob_finish(T, R, C, x, J, tn_log, tn_sign); else step_shift_finish(T, R, C, x, J, tn_log, tn_sign);
 }
 
 // ------------------------------------------------------------------ chain load / store
@@ -1203,6 +1250,157 @@ W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
 }
 
+// ------------------------------------------------------------------ phase scheduler of one CTA (CTQMC.F90:8213-8258, 8428-8533)
+// Used for 1x1 quantum-number blocks (C1, C2, C5), where a move is short and a global move (LU of every flavour's matrix)
+// costs 100-1000 moves: one persistent kernel, no launch per round.  Blocked traces use the round kernels further down.
+// One CTA advances a batch of `nloc` chains by `nsteps` moves each.  Chains are independent Markov chains, so the order
+// in which *different* chains execute their moves is free; the scheduler uses that freedom to keep all warps of the CTA in
+// the same phase of the algorithm (shared instruction-cache lines, no cross-warp code divergence):
+//   round := schedule (every runnable chain draws its move type, reference thresholds CTQMC.F90:8437-8488)
+//            -> propose (all insertions, then all removals; warps take chains from a shared-memory work list)
+//            -> decide  (determinant ratio, trace, Metropolis, rank-1 update for the proposals that survived)
+//   Global moves and tau-shifts (1 % of the moves, 10-100x the cost) park their chain; parked chains are served together
+//   in a `rare` phase once a warp-load of them has accumulated (or nothing else is runnable).
+// Within a chain the sequence of moves and RNG draws is exactly the reference's.
+struct CtaShared {
+    int nA, nR, nA2, nR2, nG, cA, cR, cA2, cR2, cG, cA2h, cR2h;
+    int* left; unsigned char* parked; unsigned char* kind;
+    short* lA; short* lR; short* lA2; short* lR2; short* lG;
+    Prop* prop;
+};
+
+// Pull the hot records of the chain a warp will work on next into L1 while it is still busy with the current one:
+// every lane prefetches one 128-byte line (operator times / superstates / codes, scalar state, counters, the first line
+// of each flavour's creator / annihilator times).  For a decide-phase item also the rows of the touched flavour's M.
+W2B_HD void prefetch_chain(const Tables& T, const Chains& C, int chain) {
+#if W2B_DEVICE
+    const int l = lane_id();
+    const char* p = nullptr;
+    if (l < 8) p = (const char*)(C.op_tau + (size_t)chain * C.ops_cap) + l * 128;
+    else if (l < 10) p = (const char*)(C.op_sst + (size_t)chain * C.ops_cap) + (l - 8) * 128;
+    else if (l == 10) p = (const char*)(C.op_code + (size_t)chain * C.ops_cap);
+    else if (l < 13) p = (const char*)(C.ih + (size_t)chain * IH_STRIDE) + (l - 11) * 128;
+    else if (l == 13) p = (const char*)(C.dh + (size_t)chain * DH_STRIDE);
+    else if (l == 14) p = (const char*)(C.counters + (size_t)chain * C_NCNT);
+    else if (l - 15 < 2 * T.nf) { const int f = (l - 15) >> 1; p = (const char*)(((l - 15) & 1 ? C.tau_a : C.tau_c) + ((size_t)chain * T.nf + f) * C.kcap); }
+    if (p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+W2B_HD void prefetch_minv(const Tables& T, const Chains& C, int chain, int f) {
+#if W2B_DEVICE
+    const int* ih = C.ih + (size_t)chain * IH_STRIDE;
+    const int k = ih[IH_KF + f];
+    const char* m = (const char*)(C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld));
+    for (int r = lane_id(); r < k; r += W2B_WARP) asm volatile("prefetch.global.L1 [%0];" ::"l"(m + (size_t)r * C.ld * 8));
+#endif
+}
+
+// bookkeeping after every move: window shift (checked after EVERY move, CTQMC.F90:8255/8531), step counter, quota
+W2B_HDN void post_move_cta(const Tables& T, const Run& R, Ctx& x, CtaShared& S, int c) {
+    wsync();
+    const unsigned long long attempts = x.cnt[C_TRYADD] + x.cnt[C_TRYREM];
+    if (!R.freeze_window && attempts % (unsigned long long)R.nslide == 0ull) {         // shift_window Trace.F90:1652-1678
+        if (R.num_windows > 1) {
+            x.wpos += 1; if (x.wpos == R.num_windows) x.wpos = 0;
+            set_window_edges(T, R, x);
+            x.npairs = -1;
+        }
+    }
+    if (x.lane == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; S.left[c] -= 1; }
+    wsync();
+}
+
+
+W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain_lo, int nloc, long long nsteps,
+                      CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf) {
+    const int W = cta_nwarps(), lane = lane_id();
+    for (int c = cta_tid(); c < nloc; c += cta_nthreads()) { S.left[c] = (int)nsteps; S.parked[c] = 0; }
+    if (cta_tid() == 0) { S.nG = 0; S.cG = 0; }
+    cta_sync();
+    const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
+    for (;;) {
+        if (cta_tid() == 0) { S.nA = 0; S.nA2 = S.nR2 = 0; S.cA = S.cA2 = S.cR2 = S.cA2h = S.cR2h = 0; }
+        cta_sync();
+        // ---- propose phase: every runnable chain draws move types (reference thresholds CTQMC.F90:8437-8488, plus the two
+        //      draws spent on 4-operator / outer moves) and proposes until one proposal survives the quantum-number check
+        for (int c = wgrab(&S.cA), cnext; c < nloc; c = cnext) {
+            cnext = wgrab(&S.cA);
+            if (S.left[c] <= 0 || S.parked[c]) continue;
+            if (R.prefetch && cnext < nloc) prefetch_chain(T, C, chain_lo + cnext);
+            const int chain = chain_lo + c;
+            Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+            if (lane == 0) wgrab_one(&S.nA);                              // S.nA counts the chains that were runnable this round
+            for (int run = 0; run < R.propose_run && S.left[c] > 0; ++run) {
+                const double r = x.rng.next();
+                if (!(r <= thr_rem)) {                                    // global move / tau shift: park for the rare phase
+                    if (lane == 0) { S.kind[c] = (unsigned char)(r <= thr_glob ? 3 : 4); S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
+                    break;
+                }
+                x.rng.skip(2);                                            // Percentage4OperatorMove / PercentageOuterMove draws (both 0)
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                bool go;
+                if (r < thr_add) { go = add_propose(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lA2[wgrab_one(&S.nA2)] = (short)c; }
+                else { go = rem_propose(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lR2[wgrab_one(&S.nR2)] = (short)c; }
+                if (go) break;
+                post_move_cta(T, R, x, S, c);
+            }
+            ctx_store(C, chain, x);
+        }
+        cta_sync();
+        const int nrun = S.nA;             // read before thread 0 may reset it at the top of the next round
+        bool rare;
+        if (nrun == 0) {
+            if (S.nG == 0) break;                                         // every chain has used its quota
+            rare = true;
+        } else {
+            // ---- decide phase: determinant ratio, trace, Metropolis, rank-1 update
+            const int na2 = S.nA2, nr2 = S.nR2;
+            // blocked traces: chains whose outer block is larger than 1x1 cost 10-100x more -> serve them first (longest
+            // processing time first keeps the tail of the phase short); pass 0 = heavy, pass 1 = the rest
+            for (int pass = (T.dmax > 1 ? 0 : 1); pass < 2; ++pass) {
+                int* curA = pass == 0 ? &S.cA2h : &S.cA2; int* curR = pass == 0 ? &S.cR2h : &S.cR2;
+                for (int i = wgrab(curA); i < na2; i = wgrab(curA)) {
+                    const int c = S.lA2[i], chain = chain_lo + c;
+                    if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
+                    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                    if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                    add_decide(T, R, C, A, x, S.prop[c]);
+                    post_move_cta(T, R, x, S, c);
+                    ctx_store(C, chain, x);
+                }
+                for (int i = wgrab(curR); i < nr2; i = wgrab(curR)) {
+                    const int c = S.lR2[i], chain = chain_lo + c;
+                    if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
+                    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                    if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                    rem_decide(T, R, C, A, x, S.prop[c]);
+                    post_move_cta(T, R, x, S, c);
+                    ctx_store(C, chain, x);
+                }
+            }
+            cta_sync();
+            rare = S.nG >= W || (S.nG > 0 && nrun < W);
+        }
+        if (rare) {
+            // ---- rare phase: global moves and tau shifts of all parked chains
+            const int ng = S.nG;
+            for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {
+                const int c = S.lG[i], chain = chain_lo + c;
+                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                step_rare(T, R, C, x, C.rjob[chain], (int)S.kind[c]);
+                post_move_cta(T, R, x, S, c);
+                ctx_store(C, chain, x);
+                if (lane == 0) S.parked[c] = 0;
+            }
+            cta_sync();
+            if (cta_tid() == 0) { S.nG = 0; S.cG = 0; }
+            cta_sync();
+        }
+    }
+}
+
+
 // bookkeeping after every move: window shift (checked after EVERY move, CTQMC.F90:8255/8531), step counter, quota
 W2B_HDN void post_move(const Tables& T, const Run& R, const Chains& C, Ctx& x, int chain) {
     wsync();
@@ -1231,15 +1429,34 @@ W2B_HDN void post_move(const Tables& T, const Run& R, const Chains& C, Ctx& x, i
 W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int chain, long long nsteps, int parity, int log_chain, double* logbuf) {
     const int lane = lane_id();
     int left = C.left[chain];
-    if (left <= 0 || C.parked[chain]) return;
+    if (left <= 0) return;
     int* sc = C.sched + parity * SC_STRIDE;
+    const int state = vload_u8(&C.parked[chain]);
+    if (state != ST_RUN) {                                        // global move / tau shift in flight on the rare stream
+        if (lane == 0) {
+            atomic_add_int(&sc[SC_NRUN], 1); atomic_max_int(&sc[SC_MAXLEFT], left);
+            // a move completed on the rare stream re-enters with the NEXT round: its records were written while this kernel was
+            // already running and may sit stale in this SM's L1 (lines shared with neighbouring chains)
+            if (state == ST_RARE_DONE) C.parked[chain] = ST_RUN;
+            if (state == ST_RARE_TRACE) {                         // first half done: this round's trace kernel runs its jobs, the decide kernel the second half
+                const int new_outer = *(const volatile int*)&C.rjob[chain].new_outer;
+                const int ntl = (ldg(&T.dim[new_outer]) + 7) >> 3;
+                int* q_tr0 = C.q_tr0 + (size_t)parity * 4 * C.nchains;
+                const int base = atomic_add_int(&sc[SC_NT0], ntl);
+                for (int t = 0; t < ntl; ++t) q_tr0[base + t] = chain | Q_RARE | (t << Q_NTSHIFT);
+                C.q_rfin[(size_t)parity * C.nchains + atomic_add_int(&sc[SC_NRFIN], 1)] = chain;
+                C.parked[chain] = ST_RARE_QUEUED;
+            }
+        }
+        return;
+    }
     const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
     Ctx x; ctx_bind(T, R, C, chain, x, nullptr, nullptr, nullptr);
     if (lane == 0) { atomic_add_int(&sc[SC_NRUN], 1); atomic_max_int(&sc[SC_MAXLEFT], left); }
     for (int run = 0; run < R.propose_run && left > 0; ++run) {
         const double r = x.rng.next();
         if (!(r <= thr_rem)) {                                    // global move / tau shift: rare queue
-            if (lane == 0) { C.kind[chain] = (unsigned char)(r <= thr_glob ? 3 : 4); C.parked[chain] = 1; C.q_rare[atomic_add_int(&sc[SC_NRARE], 1)] = chain; }
+            if (lane == 0) { C.kind[chain] = (unsigned char)(r <= thr_glob ? 3 : 4); C.parked[chain] = ST_RARE_NEW; }
             break;
         }
         x.rng.skip(2);                                            // Percentage4OperatorMove / PercentageOuterMove draws (both 0)
@@ -1258,7 +1475,7 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
                     const int rem = (entry & Q_REM) ? 1 : 0, s = P.i1, e = P.i2 + rem;
                     const int steps = (x.bv > e ? x.bv - e : 0) + (x.kv <= s - 1 ? s - x.kv : 0) + (P.i2 - P.i1 - rem) + (rem ? 0 : 2);
                     const int ntl = (m + 7) >> 3;
-                    int* q = steps >= 24 ? C.q_tr0 : (steps >= 8 ? C.q_tr1 : C.q_tr2);
+                    int* q = (steps >= 24 ? C.q_tr0 : (steps >= 8 ? C.q_tr1 : C.q_tr2)) + (size_t)parity * 4 * C.nchains;
                     const int base = atomic_add_int(&sc[steps >= 24 ? SC_NT0 : (steps >= 8 ? SC_NT1 : SC_NT2)], ntl);
                     for (int t = 0; t < ntl; ++t) q[base + t] = entry | (t << Q_NTSHIFT);
                 }
@@ -1272,19 +1489,46 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
 }
 
 // one ticket of the trace kernel (blocked traces only): tickets run over the three trace queues, longest jobs first
-W2B_HD void phase_trace(const Tables& T, const Chains& C, int ticket, const int* sc, double* mscratch) {
+W2B_HD void phase_trace(const Tables& T, const Chains& C, int ticket, int parity, double* mscratch) {
+    const int* sc = C.sched + parity * SC_STRIDE;
+    const size_t qo = (size_t)parity * 4 * C.nchains;
     const int n0 = sc[SC_NT0], n1 = sc[SC_NT1];
-    const int entry = ticket < n0 ? C.q_tr0[ticket] : (ticket < n0 + n1 ? C.q_tr1[ticket - n0] : C.q_tr2[ticket - n0 - n1]);
+    const int entry = ticket < n0 ? C.q_tr0[qo + ticket] : (ticket < n0 + n1 ? C.q_tr1[qo + ticket - n0] : C.q_tr2[qo + ticket - n0 - n1]);
     trace_job(T, C, entry, mscratch, mscratch + C.ldx * 8, mscratch + C.ldx * 8 + 8);
 }
 
+// Global moves / tau shifts (1 % of the moves, 10-1000x the cost of a pair move) run on their own stream beside the round
+// pipeline: the rare kernel scans the chain states, takes the chains a propose kernel left in ST_RARE_NEW and runs
+//   1x1 blocks:     the whole move; the chain returns to ST_RUN;
+//   blocked traces: the first half (everything up to the local trace), then ST_RARE_TRACE: the next propose kernel queues the
+//                   trace jobs and the second half for its round (trace kernel / decide kernel).
+// The round pipeline never waits for this stream; a chain whose rare move is in flight simply sits out a few rounds.
+W2B_HD void phase_rare(const Tables& T, const Run& R, const Chains& C, int chain, long long nsteps,
+                       int log_chain, double* logbuf, double* wscratch, int* iscratch, double* mscratch) {
+    if (vload_u8(&C.parked[chain]) != ST_RARE_NEW) return;
+    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+    if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - C.left[chain]) * LOGW;
+    RareJob& J = C.rjob[chain];
+    const int kind = C.kind[chain];
+    bool pending = false;
+    if (T.dmax > 1) {
+        pending = kind == 3 ? step_glob_prepare(T, R, C, x, J) : step_shift_prepare(T, R, C, x, J);
+        if (pending && kind == 4 && x.lane == 0) J.stored = 1;    // tau shifts are accepted with probability ~1: cache the kets of the new sequence
+    } else step_rare(T, R, C, x, J, kind);
+    if (!pending) post_move(T, R, C, x, chain);
+    ctx_store(C, chain, x);
+    fence_device();
+    if (x.lane == 0) vstore_u8(&C.parked[chain], (unsigned char)(pending ? ST_RARE_TRACE : ST_RARE_DONE));
+}
+
 // one ticket of the decide kernel: tickets [0, nrare) are rare moves, then the three decide queues
-W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const Accum& A, int ticket, const int* sc, long long nsteps,
+W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const Accum& A, int ticket, int parity, long long nsteps,
                          int log_chain, double* logbuf, double* wscratch, int* iscratch, double* mscratch) {
     const int lane = lane_id();
-    const int nrare = sc[SC_NRARE], n0 = sc[SC_NQ0], n1 = sc[SC_NQ1];
+    const int* sc = C.sched + parity * SC_STRIDE;
+    const int nrare = sc[SC_NRFIN], n0 = sc[SC_NQ0], n1 = sc[SC_NQ1];
     int entry; bool rare = false;
-    if (ticket < nrare) { entry = C.q_rare[ticket]; rare = true; }
+    if (ticket < nrare) { entry = C.q_rfin[(size_t)parity * C.nchains + ticket]; rare = true; }
     else if (ticket < nrare + n0) entry = C.q_dec0[ticket - nrare];
     else if (ticket < nrare + n0 + n1) entry = C.q_dec1[ticket - nrare - n0];
     else entry = C.q_dec2[ticket - nrare - n0 - n1];
@@ -1292,12 +1536,18 @@ W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const A
     Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
     if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - C.left[chain]) * LOGW;
     if (!rare && T.dmax > 1) { x.pre = C.ptc + (size_t)chain * 2 * C.dmax; x.mpt = C.ptc + (size_t)chain * 2 * C.dmax; }
-    if (rare) { if (C.kind[chain] == 3) step_glob(T, R, C, x); else step_shift(T, R, C, x); }
+    if (rare) {                                                   // second half of a global move / tau shift: the trace kernel has left the parts in C.ptc
+        RareJob& J = C.rjob[chain];
+        double tn_log, tn_sign;
+        x.mpt = C.ptc + (size_t)chain * 2 * C.dmax;
+        parts_sum(x.mpt, ldg(&T.dim[J.new_outer]), tn_log, tn_sign);
+        if (C.kind[chain] == 3) step_glob_finish(T, R, C, x, J, tn_log, tn_sign); else step_shift_finish(T, R, C, x, J, tn_log, tn_sign);
+    }
     else if (entry & Q_REM) rem_decide(T, R, C, A, x, C.prop[chain]);
     else add_decide(T, R, C, A, x, C.prop[chain]);
     post_move(T, R, C, x, chain);
     ctx_store(C, chain, x);
-    if (rare && lane == 0) C.parked[chain] = 0;
+    if (rare && lane == 0) C.parked[chain] = ST_RUN;
 }
 
 // init_Trace (Trace.F90:340-701): empty configuration, outer superstate drawn with the empty-trace weights

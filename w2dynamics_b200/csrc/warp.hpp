@@ -89,6 +89,10 @@ W2B_HD int wargmax_abs(double x, int idx, double& best) {
 W2B_HD void atomic_add(double* p, double v) { atomicAdd(p, v); }
 W2B_HD void atomic_add(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 W2B_HD int atomic_add_int(int* p, int v) { return atomicAdd(p, v); }
+// flags exchanged between kernels that run concurrently on different streams
+W2B_HD int vload_u8(const unsigned char* p) { return (int)*(const volatile unsigned char*)p; }
+W2B_HD void vstore_u8(unsigned char* p, unsigned char v) { *(volatile unsigned char*)p = v; }
+W2B_HD void fence_device() { __threadfence(); }
 W2B_HD void atomic_max_int(int* p, int v) { atomicMax(p, v); }
 // CTA-level primitives of the phase scheduler
 W2B_HD void cta_sync() { __syncthreads(); }
@@ -123,6 +127,9 @@ W2B_HD int wargmax_abs(double x, int idx, double& best) { best = std::fabs(x); r
 W2B_HD void atomic_add(double* p, double v) { *p += v; }
 W2B_HD void atomic_add(unsigned long long* p, unsigned long long v) { *p += v; }
 W2B_HD int atomic_add_int(int* p, int v) { int o = *p; *p += v; return o; }
+W2B_HD int vload_u8(const unsigned char* p) { return (int)*p; }
+W2B_HD void vstore_u8(unsigned char* p, unsigned char v) { *p = v; }
+W2B_HD void fence_device() {}
 W2B_HD void atomic_max_int(int* p, int v) { if (v > *p) *p = v; }
 W2B_HD void cta_sync() {}
 W2B_HD int cta_warp() { return 0; }
