@@ -36,10 +36,20 @@ WORKLOADS = {
     "C4": "C4: 5-orbital d-shell full Slater-Coulomb, beta=20, 1024-state Fock space, 132 blocks d<=28",
     "C5": "C5: 1-band Hubbard, beta=200 (expansion order in the hundreds)",
 }
-DEFAULT_CHAINS = {"C1": 65536, "C2": 16384, "C3": 16384, "C4": 8192, "C5": 4096}      # per GPU
+DEFAULT_CHAINS = {"C1": 65536, "C2": 16384, "C3": 32768, "C4": 32768, "C5": 4096}      # per GPU
 THERMALISE = {"C1": 2000, "C2": 6000, "C3": 6000, "C4": 6000, "C5": 40000}
 METRIC = "QMC moves/sec (box)"
 UNIT = "moves/s"
+
+
+def fp64_peak():
+    """FP64 tensor-pipe yardstick measured on this pool's B200 (cuBLAS DGEMM 8192^3, tools/fp64_peak.py): MEASURED_PEAKS.json
+    holds no FP64 number."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_yardstick.json")))
+        return float(d["dgemm_8192_tflops"]), "measured cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r1_fp64_yardstick.json)"
+    except Exception:
+        return 37.0, "nominal B200 FP64 (no measurement file)"
 
 
 def measured_peak():
@@ -232,7 +242,12 @@ def run_engine(args):
     allreduce_accum()
     eng._ck(L.w2b_read_accum(None, C.c_size_t(0), C.byref(C.c_size_t())))
     torch.cuda.synchronize()
+    blocked = eng.scalar("blocked") > 0
     bytes0, launches0 = eng.scalar("cnt_alg_bytes"), eng.scalar("gpu_launches")
+    flops0 = eng.scalar("trace_flops") if blocked else 0.0
+    rounds0 = eng.scalar("rounds")
+    if blocked:
+        eng.set_option("time_kernels", 1)                      # CUDA events around every round kernel, on the launching stream
     sampler = ClockSampler(local) if rank == 0 else None
     if world > 1:
         dist.barrier()
@@ -250,6 +265,11 @@ def run_engine(args):
         elapsed_ms = float(t.item())
     clocks = sampler.stop() if sampler else None
     bytes1, launches1 = eng.scalar("cnt_alg_bytes"), eng.scalar("gpu_launches")
+    flops1 = eng.scalar("trace_flops") if blocked else 0.0
+    rounds1 = eng.scalar("rounds")
+    kms = {k: eng.scalar("ms_" + k) for k in ("propose", "trace", "decide")} if blocked else {}
+    if blocked:
+        eng.set_option("time_kernels", 0)
     mean_k = eng.scalar("mean_order")
     moves = float(nchains) * ncorr * args.steps * world
     value = moves / (elapsed_ms * 1e-3)
@@ -317,6 +337,19 @@ def run_engine(args):
                          "peak_source": peak_src},
             "clocks": clocks,
         }
+        if blocked:
+            # blocked traces: the sweep is rounds of k_propose / k_trace / k_decide (+ k_rare on a second stream); the dominant
+            # kernel is k_trace, bound by the FP64 tensor pipe (DMMA): algorithmic flops = 2 d_out d_in columns per operator
+            # product, counted in the kernel, over the summed CUDA-event durations of its launches in the timed region
+            nround = max(1.0, rounds1 - rounds0)
+            fpk, fsrc = fp64_peak()
+            tfl = (flops1 - flops0) / (kms["trace"] * 1e-3) / 1e12 if kms["trace"] > 0 else 0.0
+            line["kernel_ms"] = {"sweep": t_sweep / args.steps, "k_propose": kms["propose"] / args.steps, "k_trace": kms["trace"] / args.steps,
+                                 "k_decide": kms["decide"] / args.steps, "k_measure": t_meas / args.steps, "rounds_per_step": nround / args.steps}
+            line["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": fpk, "unit": "TFLOP/s", "frac": tfl / fpk, "traffic": traffic,
+                                "kernel": "k_trace", "dtype": "f64 (DMMA.8x8x4)", "algorithmic_flops_per_launch": (flops1 - flops0) / nround,
+                                "launch_ms": kms["trace"] / nround, "peak_source": fsrc,
+                                "hbm_view": {"achieved_gbs": achieved, "peak_gbs": peak, "note": "determinant-path algorithmic bytes over the whole sweep"}}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -26,7 +26,7 @@ def short(n):
     s = n.split("$")[-1] if "$" in n else n
     return subprocess.run(["c++filt", s], capture_output=True, text=True).stdout.strip().split("(")[0]
 starts = [(o, short(n)) for o, n in funcs]
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--kernel-name", "regex:" + want, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]

@@ -19,7 +19,7 @@ for line in dis.splitlines():
     mm = re.match(r"^\s+/\*([0-9a-f]{4,6})\*/", line)
     if mm and insec:
         line_of[int(mm.group(1), 16)] = where
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--kernel-name", "regex:" + want, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]

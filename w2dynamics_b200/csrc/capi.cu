@@ -25,6 +25,7 @@ struct Solver {
     int device = -1;
     int same_key = 0;
     int prefetch = 1;
+    int time_kernels = 0;
     int propose_run = 4;
     // derived
     double beta = 0; int nb = 0; long long nmeas = 0; int ncorr = 100;
@@ -160,6 +161,7 @@ int w2b_set_option(const char* key, double value) {
     else if (k == "nmeas_override") S.nmeas_override = (long long)value;
     else if (k == "debug_same_key") S.same_key = (int)value;
     else if (k == "prefetch") S.prefetch = (int)value;
+    else if (k == "time_kernels") { S.time_kernels = (int)value; if (S.eng) { S.eng->time_kernels = value != 0; S.eng->ms_propose = S.eng->ms_trace = S.eng->ms_decide = 0; } }
     else if (k == "propose_run") S.propose_run = (int)value;
     else return fail("unknown option " + k);
     return 0;
@@ -468,9 +470,14 @@ int w2b_get_scalar(const char* name, double* out) {
             if (k == "sweep_grid") { *out = E.C.dmax == 1 ? E.ct_grid : E.sw_grid; return; }
             if (k == "sweep_smem") { *out = (double)(E.C.dmax == 1 ? E.ct_smem : E.sw_smem); return; }
             if (k == "rounds") { *out = (double)E.rounds; return; }
+            if (k == "trace_flops") { *out = (double)E.trace_flops(); return; }
+            if (k == "ms_propose") { *out = E.ms_propose; return; }
+            if (k == "ms_trace") { *out = E.ms_trace; return; }
+            if (k == "ms_decide") { *out = E.ms_decide; return; }
+            if (k == "blocked") { *out = E.C.dmax > 1 ? 1.0 : 0.0; return; }
             if (k.rfind("cnt_", 0) == 0) {
                 static const char* names[C_NCNT] = {"try_add", "try_rem", "try_glob", "try_shift", "acc_add", "acc_rem", "acc_glob", "acc_shift",
-                                                    "qn_add", "qn_rem", "qn_glob", "steps", "alg_bytes"};
+                                                    "qn_add", "qn_rem", "qn_glob", "steps", "alg_bytes", "trace_flops"};
                 std::vector<unsigned long long> cnt; E.get_counters(cnt);
                 for (int i = 0; i < C_NCNT; ++i) if (k.substr(4) == names[i]) { *out = (double)cnt[i]; return; }
             }

@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T, Run R, C
 }
 #endif
 // ---- round kernels (blocked traces)
-constexpr int PROPOSE_WARPS = 8;      // warps per CTA of the propose kernel (no shared memory)
+constexpr int PROPOSE_WARPS = 8;      // warps per CTA of the propose kernel (its queue pushes are aggregated per CTA)
 constexpr int TRACE_WARPS = 4;        // warps per CTA of the trace kernel (one work matrix per warp in shared memory)
+constexpr int TICKET_BATCH = 1;       // tickets a warp takes per atomic on the round's ticket counter
 constexpr int DECIDE_WARPS = 4;       // warps per CTA of the decide kernel (one work matrix per warp in shared memory)
 #if W2B_DEVICE
 __global__ void __launch_bounds__(256) k_sweep_begin(Chains C, long long nsteps) {
@@ -130,33 +131,54 @@ __global__ void __launch_bounds__(256) k_sweep_begin(Chains C, long long nsteps)
     if (c < C.nchains) { C.left[c] = (int)nsteps; C.parked[c] = 0; }
     if (c < 2 * SC_STRIDE) C.sched[c] = 0;
 }
-// propose phase of one round: one warp per chain
-__global__ void __launch_bounds__(PROPOSE_WARPS * 32, 4) k_propose(Tables T, Run R, Chains C, long long nsteps, int parity, int log_chain, double* logbuf) {
+// propose phase of one round: one warp per chain; the CTA's results reach the round's queues with one atomic per queue
+// (the parameter structs are copied to shared memory once per CTA: passing kernel parameters by reference to out-of-line
+// functions would otherwise spill a private copy per thread to local memory)
+__global__ void __launch_bounds__(PROPOSE_WARPS * 32, 4) k_propose(Tables T_, Run R_, Chains C_, long long nsteps, int parity, int log_chain, double* logbuf) {
+    __shared__ ProposeOut outs[PROPOSE_WARPS];
+    __shared__ Ctx ctxs[PROPOSE_WARPS];
+    __shared__ Tables T; __shared__ Run R; __shared__ Chains C;
+    if (threadIdx.x == 0) { T = T_; R = R_; C = C_; }
+    __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x < SC_STRIDE) C.sched[(parity ^ 1) * SC_STRIDE + threadIdx.x] = 0;     // counters of the next round
-    const int chain = blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
-    if (chain < C.nchains) phase_propose(T, R, C, chain, nsteps, parity, log_chain, logbuf);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) outs[warp] = ProposeOut{0, 0, -1, 0, -1, 0, 0, 0};
+    __syncwarp();
+    const int chain = blockIdx.x * PROPOSE_WARPS + warp;
+    if (chain < C.nchains) phase_propose(T, R, C, chain, nsteps, parity, log_chain, logbuf, &outs[warp], ctxs[warp]);
+    __syncthreads();
+    if (warp == 0) propose_flush(C, parity, outs, PROPOSE_WARPS);
 }
 // decide phase of one round: persistent warps take tickets (rare moves first, then decide queues by outer block size)
-__global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_decide(Tables T, Run R, Chains C, Accum A, long long nsteps, int wdoubles, int mdoubles, int parity,
+__global__ void __launch_bounds__(DECIDE_WARPS * 32, 6) k_decide(Tables T_, Run R_, Chains C_, Accum A_, long long nsteps, int wdoubles, int mdoubles, int parity,
                                                               int log_chain, double* logbuf) {
     extern __shared__ double smem[];
+    __shared__ Tables T; __shared__ Run R; __shared__ Chains C; __shared__ Accum A;
+    if (threadIdx.x == 0) { T = T_; R = R_; C = C_; A = A_; }
+    __syncthreads();
     const int warp = threadIdx.x >> 5;
     double* ws = smem + (size_t)warp * wdoubles;
     int* is = (int*)(ws + 3 * C.kcap + mdoubles);
     int* sc = C.sched + parity * SC_STRIDE;
+    __shared__ Ctx ctxs[DECIDE_WARPS];
     const int total = sc[SC_NRFIN] + sc[SC_NQ0] + sc[SC_NQ1] + sc[SC_NQ2];
-    for (int t = wgrab(&sc[SC_TICKET]); t < total; t = wgrab(&sc[SC_TICKET]))
-        phase_decide(T, R, C, A, t, parity, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap);
+    for (int t0 = wgrab_n(&sc[SC_TICKET], TICKET_BATCH); t0 < total; t0 = wgrab_n(&sc[SC_TICKET], TICKET_BATCH))
+      for (int t = t0; t < t0 + TICKET_BATCH && t < total; ++t)
+        phase_decide(T, R, C, A, t, parity, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
 }
 // global moves / tau shifts, on their own stream beside the round pipeline: scan the chain states, serve ST_RARE_NEW
-__global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T, Run R, Chains C, long long nsteps, int wdoubles, int mdoubles,
+__global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T_, Run R_, Chains C_, long long nsteps, int wdoubles, int mdoubles,
                                                               int log_chain, double* logbuf) {
     extern __shared__ double smem[];
+    __shared__ Tables T; __shared__ Run R; __shared__ Chains C;
+    if (threadIdx.x == 0) { T = T_; R = R_; C = C_; }
+    __syncthreads();
     const int warp = threadIdx.x >> 5;
     double* ws = smem + (size_t)warp * wdoubles;
     int* is = (int*)(ws + 3 * C.kcap + mdoubles);
+    __shared__ Ctx ctxs[DECIDE_WARPS];
     for (int c = blockIdx.x * DECIDE_WARPS + warp; c < C.nchains; c += gridDim.x * DECIDE_WARPS)
-        phase_rare(T, R, C, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap);
+        phase_rare(T, R, C, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
 }
 // trace phase of one round (blocked traces): operator products of every surviving proposal on the FP64 tensor pipe
 __global__ void __launch_bounds__(TRACE_WARPS * 32, 8) k_trace(Tables T, Chains C, int tdoubles, int parity) {
@@ -164,7 +186,16 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 8) k_trace(Tables T, Chains 
     double* ws = smem + (size_t)(threadIdx.x >> 5) * tdoubles;
     int* sc = C.sched + parity * SC_STRIDE;
     const int total = sc[SC_NT0] + sc[SC_NT1] + sc[SC_NT2];
-    for (int t = wgrab(&sc[SC_TTICKET]); t < total; t = wgrab(&sc[SC_TTICKET])) phase_trace(T, C, t, parity, ws);
+    for (int t0 = wgrab_n(&sc[SC_TTICKET], TICKET_BATCH); t0 < total; t0 = wgrab_n(&sc[SC_TTICKET], TICKET_BATCH))
+        for (int t = t0; t < t0 + TICKET_BATCH && t < total; ++t) phase_trace(T, C, t, parity, ws);
+}
+// measurement pre-pass (blocked traces): extend every chain's cache frontiers to tau = beta/2, one job per 8 outer states
+__global__ void __launch_bounds__(TRACE_WARPS * 32, 8) k_meas_extend(Tables T, Chains C, int tdoubles) {
+    extern __shared__ double smem[];
+    double* ws = smem + (size_t)(threadIdx.x >> 5) * tdoubles;
+    const int njobs = C.nchains * 4;
+    for (int t = blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5); t < njobs; t += gridDim.x * TRACE_WARPS)
+        trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws, ws + C.ldx * 8, ws + C.ldx * 8 + 8);
 }
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_measure(Tables T, Run R, Chains C, Accum A, int wdoubles, int mdoubles) {
     extern __shared__ double smem[];
@@ -255,13 +286,24 @@ public:
         T.empty_w = keep(dev_upload(ew)); T.empty_log = keep(dev_upload(el));
         {
             std::vector<OpDesc> desc((size_t)nsst * at.nops);
+            std::vector<double> frag;
             for (int k = 0; k < nsst; ++k) for (int c = 0; c < at.nops; ++c) {
                 OpDesc& D = desc[(size_t)k * at.nops + c];
                 const int out = at.connect[(size_t)k * at.nops + c];
                 D.sst_out = out; D.d_in = at.dim[k]; D.d_out = out >= 0 ? at.dim[out] : 0; D.ev_off = at.offset[k];
-                D.op_off = out >= 0 ? at.op_off[(size_t)k * at.nops + c] : 0; D.e0 = at.evals[at.offset[k]];
+                D.op_off = out >= 0 ? (int)at.op_off[(size_t)k * at.nops + c] : 0; D.e0 = at.evals[at.offset[k]];
+                D.frag_off = (int)frag.size();
+                if (out < 0 || at.dmax == 1) continue;
+                // DMMA A-fragment order: [k-step][row-tile pair][lane][2]; lane l holds rows 8*mt + l/4, column 4*ks + l%4
+                const int din = D.d_in, dout = D.d_out, ks_n = (din + 3) / 4, np = ((dout + 7) / 8 + 1) / 2;
+                const double* O = at.opdata.data() + D.op_off;
+                for (int ks = 0; ks < ks_n; ++ks) for (int p = 0; p < np; ++p) for (int l = 0; l < 32; ++l) for (int h = 0; h < 2; ++h) {
+                    const int r = (2 * p + h) * 8 + l / 4, cc = ks * 4 + l % 4;
+                    frag.push_back((r < dout && cc < din) ? O[r + (size_t)cc * dout] : 0.0);
+                }
             }
-            T.desc = keep(dev_upload(desc));
+            if (frag.empty()) frag.push_back(0.0);
+            T.desc = keep(dev_upload(desc)); T.opfrag = keep(dev_upload(frag));
         }
         T.op_off = keep(dev_upload(at.op_off)); T.opdata = keep(dev_upload(at.opdata)); T.evals = keep(dev_upload(at.evals));
 
@@ -302,13 +344,14 @@ public:
         C.q_rare = keep(dev_alloc<int>((size_t)2 * nc)); C.q_rfin = keep(dev_alloc<int>((size_t)2 * nc)); C.q_dec0 = keep(dev_alloc<int>(nc)); C.q_dec1 = keep(dev_alloc<int>(nc)); C.q_dec2 = keep(dev_alloc<int>(nc));
         C.sched = keep(dev_alloc<int>(2 * SC_STRIDE));
         C.ptc = nullptr; C.q_tr0 = C.q_tr1 = C.q_tr2 = nullptr;
+        C.trace_flops = keep(dev_alloc<unsigned long long>(1));
         if (at.dmax > 1) {
             C.ptc = keep(dev_alloc<double>((size_t)nc * 2 * at.dmax));
             C.q_tr0 = keep(dev_alloc<int>((size_t)nc * 8)); C.q_tr1 = keep(dev_alloc<int>((size_t)nc * 8)); C.q_tr2 = keep(dev_alloc<int>((size_t)nc * 8));
         }
         int wints = kcap + 32 + nsst;
         wdoubles = 3 * kcap + mat_doubles(C, true) + (wints + 1) / 2;
-        wdoubles_sweep = 3 * kcap + mat_doubles(C, false) + (wints + 1) / 2;
+        wdoubles_sweep = 3 * kcap + (wints + 1) / 2;   // sweep kernels hold no work matrix: blocked traces run in the trace kernel
 
         // accumulators
         int o = 0;
@@ -426,6 +469,12 @@ public:
 #endif
     int tr_doubles = 0, tr_grid = 1, rp_grid = 1; size_t tr_smem = 0;   // trace kernel: per-warp work space, grid, shared memory
     long long rounds = 0;              // rounds launched so far (bench accounting)
+    bool time_kernels = false;         // bench: CUDA events around every round kernel (on the launching stream)
+    double ms_propose = 0, ms_trace = 0, ms_decide = 0;
+#if W2B_DEVICE
+    std::vector<cudaEvent_t> tev;      // 4 events per round of a chunk
+#endif
+    unsigned long long trace_flops() { std::vector<unsigned long long> c; get_counters(c); return c[C_TRFLOPS]; }
     void plan_sweep() {
 #if W2B_DEVICE
         int dev = 0, nsm = 1;
@@ -450,6 +499,7 @@ public:
             tr_doubles = C.ldx * 8 + 8 + MAT_DMAX;
             tr_smem = (size_t)TRACE_WARPS * tr_doubles * sizeof(double);
             W2B_CUDA_CHECK(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
+            W2B_CUDA_CHECK(cudaFuncSetAttribute(k_meas_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
             int occt = 1;
             W2B_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occt, k_trace, TRACE_WARPS * 32, tr_smem));
             tr_grid = std::min(nsm * std::max(1, occt), (C.nchains + TRACE_WARPS - 1) / TRACE_WARPS);
@@ -473,35 +523,45 @@ public:
 #if W2B_DEVICE
         k_sweep_begin<<<(std::max(nc, 2 * SC_STRIDE) + 255) / 256, 256>>>(C, nsteps); ++launches;
         const int gp = (nc + PROPOSE_WARPS - 1) / PROPOSE_WARPS;
-        const int md = mat_doubles(C, false);
+        const int md = 0;
 #else
         for (int c = 0; c < nc; ++c) { C.left[c] = (int)nsteps; C.parked[c] = 0; }
         for (int i = 0; i < 2 * SC_STRIDE; ++i) C.sched[i] = 0;
         std::vector<double> ws(wdoubles + 8);
 #endif
         for (;;) {
+#if W2B_DEVICE
+            if (time_kernels) {
+                if (chunk > 64) chunk = 64;
+                while (tev.size() < (size_t)chunk * 4) { cudaEvent_t e; W2B_CUDA_CHECK(cudaEventCreate(&e)); tev.push_back(e); }
+            }
+#endif
             for (long long i = 0; i < chunk; ++i, ++round) {
                 const int parity = (int)(round & 1);
 #if W2B_DEVICE
+                if (time_kernels) W2B_CUDA_CHECK(cudaEventRecord(tev[4 * i], 0));
                 k_propose<<<gp, PROPOSE_WARPS * 32>>>(T, R, C, nsteps, parity, log_chain, dlog);
+                if (time_kernels) W2B_CUDA_CHECK(cudaEventRecord(tev[4 * i + 1], 0));
                 // global moves / tau shifts drawn in this round: served on the rare stream, never waited for by the rounds
                 W2B_CUDA_CHECK(cudaEventRecord(ev_prop[parity], 0));
                 W2B_CUDA_CHECK(cudaStreamWaitEvent(rare_stream, ev_prop[parity], 0));
                 k_rare<<<rp_grid, DECIDE_WARPS * 32, sw_smem, rare_stream>>>(T, R, C, nsteps, wdoubles_sweep, md, log_chain, dlog);
                 ++launches;
                 if (C.dmax > 1) { k_trace<<<tr_grid, TRACE_WARPS * 32, tr_smem>>>(T, C, tr_doubles, parity); ++launches; }
+                if (time_kernels) W2B_CUDA_CHECK(cudaEventRecord(tev[4 * i + 2], 0));
                 k_decide<<<sw_grid, DECIDE_WARPS * 32, sw_smem>>>(T, R, C, A, nsteps, wdoubles_sweep, md, parity, log_chain, dlog);
+                if (time_kernels) W2B_CUDA_CHECK(cudaEventRecord(tev[4 * i + 3], 0));
                 launches += 2;
 #else
                 for (int i2 = 0; i2 < SC_STRIDE; ++i2) C.sched[(parity ^ 1) * SC_STRIDE + i2] = 0;
-                for (int c = 0; c < nc; ++c) phase_propose(T, R, C, c, nsteps, parity, log_chain, dlog);
+                for (int c = 0; c < nc; ++c) { ProposeOut o{0, 0, -1, 0, -1, 0, 0, 0}; Ctx x; phase_propose(T, R, C, c, nsteps, parity, log_chain, dlog, &o, x); propose_flush(C, parity, &o, 1); }
                 int* sc = C.sched + parity * SC_STRIDE;
                 for (int c = 0; c < nc; ++c)
-                    phase_rare(T, R, C, c, nsteps, log_chain, dlog, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);
+                    { Ctx x; phase_rare(T, R, C, c, nsteps, log_chain, dlog, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, x); }
                 if (C.dmax > 1) for (int t = 0; t < sc[SC_NT0] + sc[SC_NT1] + sc[SC_NT2]; ++t) phase_trace(T, C, t, parity, ws.data() + 3 * C.kcap);
                 const int total = sc[SC_NRFIN] + sc[SC_NQ0] + sc[SC_NQ1] + sc[SC_NQ2];
                 for (int t = 0; t < total; ++t)
-                    phase_decide(T, R, C, A, t, parity, nsteps, log_chain, dlog, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);
+                    { Ctx x; phase_decide(T, R, C, A, t, parity, nsteps, log_chain, dlog, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, x); }
 #endif
             }
             rounds += chunk;
@@ -510,6 +570,12 @@ public:
             W2B_CUDA_CHECK(cudaGetLastError());
             W2B_CUDA_CHECK(cudaMemcpyAsync(h_sched, C.sched + ((round - 1) & 1) * SC_STRIDE, SC_STRIDE * sizeof(int), cudaMemcpyDeviceToHost, 0));
             W2B_CUDA_CHECK(cudaStreamSynchronize(0));
+            if (time_kernels) for (long long i = 0; i < chunk; ++i) {
+                float t = 0;
+                W2B_CUDA_CHECK(cudaEventElapsedTime(&t, tev[4 * i], tev[4 * i + 1])); ms_propose += t;
+                W2B_CUDA_CHECK(cudaEventElapsedTime(&t, tev[4 * i + 1], tev[4 * i + 2])); ms_trace += t;
+                W2B_CUDA_CHECK(cudaEventElapsedTime(&t, tev[4 * i + 2], tev[4 * i + 3])); ms_decide += t;
+            }
 #else
             std::memcpy(h_sched, C.sched + ((round - 1) & 1) * SC_STRIDE, SC_STRIDE * sizeof(int));
 #endif
@@ -527,11 +593,22 @@ public:
         size_t sm = smem_bytes();
         static size_t configured = 0;
         if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_measure, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+        if (C.dmax > 1 && R.meas_dm) {
+            if (!sw_ready) plan_sweep();
+            k_meas_extend<<<tr_grid, TRACE_WARPS * 32, tr_smem>>>(T, C, tr_doubles); ++launches;
+            C.meas_pre = 1;
+        }
         k_measure<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, A, wdoubles, mat_doubles(C, true)); ++launches;
+        C.meas_pre = 0;
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
         std::vector<double> ws(wdoubles + 8);
+        if (C.dmax > 1 && R.meas_dm) {
+            for (int t = 0; t < C.nchains * 4; ++t) trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws.data(), ws.data() + C.ldx * 8, ws.data() + C.ldx * 8 + 8);
+            C.meas_pre = 1;
+        }
         for (int c = 0; c < C.nchains; ++c) measure_chain(T, R, C, A, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);
+        C.meas_pre = 0;
 #endif
     }
 

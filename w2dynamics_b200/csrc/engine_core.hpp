@@ -32,7 +32,7 @@ namespace w2b {
 
 constexpr int LOGW = 20;      // doubles per replay-log record (same layout as oracle/chain.cpp)
 constexpr int NF_MAX = 14;
-enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_ALGBYTES, C_NCNT };
+enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_ALGBYTES, C_TRFLOPS, C_NCNT };
 enum { IH_NOPS = 0, IH_OUTER, IH_WPOS, IH_NPAIRS, IH_PERM, IH_PALT, IH_ERR, IH_KV, IH_KF = 8, IH_MSLOT = IH_KF + NF_MAX, IH_BV = IH_MSLOT + NF_MAX + 1, IH_NFREE, IH_STRIDE };
 enum { DH_DETLOG = 0, DH_DETSIGN, DH_TRLOG, DH_TRSIGN, DH_CFGSIGN, DH_STRIDE = 8 };
 enum { ERR_CAPACITY = 1, ERR_DETRAT_SMALL = 2, ERR_PAIR_LOGIC = 4, ERR_GLOBAL_QN = 8, ERR_SINGULAR = 16 };
@@ -56,6 +56,7 @@ struct Tables {
     const OpDesc* desc;          // [nsst*nops] packed operator records of the blocked trace
     const long long* op_off;     // matrix path
     const double* opdata;
+    const double* opfrag;        // operator blocks in DMMA A-fragment order (OpDesc::frag_off)
     const double* evals;
 };
 
@@ -87,6 +88,7 @@ struct RareJob {
 enum { SC_NRARE = 0, SC_NQ0, SC_NQ1, SC_NQ2, SC_TICKET, SC_NRUN, SC_MAXLEFT, SC_TTICKET, SC_NT0, SC_NT1, SC_NT2, SC_NRFIN, SC_STRIDE = 16 };
 // per-chain scheduling state (Chains::parked): global moves / tau shifts leave the round pipeline and come back through these states
 enum { ST_RUN = 0, ST_RARE_NEW = 1, ST_RARE_TRACE = 3, ST_RARE_QUEUED = 4, ST_RARE_DONE = 5 };
+constexpr int Q_MEAS = 1 << 28;      // trace-queue entry of a measurement: extend both cache frontiers to tau = beta/2, no trace
 constexpr int Q_RARE = 1 << 29;      // trace-queue entry of a global move / tau shift (whole sequence, no caches)
 constexpr int Q_REM = 1 << 30;       // decide-queue entry = chain id | Q_REM for a removal
 constexpr int Q_NTSHIFT = 26;         // trace-queue entry: + column tile << Q_NTSHIFT
@@ -111,7 +113,9 @@ struct Chains {
     int* left; unsigned char* parked; unsigned char* kind; Prop* prop; RareJob* rjob;
     int* q_rare; int* q_rfin; int* q_dec0; int* q_dec1; int* q_dec2; int* sched;      // q_rare, q_rfin and the trace queues: one buffer per counter set
     double* ptc;                                               // trace kernel results: per-outer-state parts (log, sign) of the proposed configuration [chain][2*dmax]
+    unsigned long long* trace_flops;                           // algorithmic FP64 flops of the trace kernel (2 d_out d_in columns per operator product)
     int* q_tr0; int* q_tr1; int* q_tr2;                        // trace jobs (chain | column tile | removal flag) by number of steps: long, medium, short
+    int meas_pre;                                              // measurement kernel: the cache frontiers already reach beta/2 (extended by trace jobs)
     int ldx, xdoubles;                                         // work matrix: leading dimension (4 mod 16) and size ldx * dmax
 };
 
@@ -136,7 +140,6 @@ struct Ctx {
     int n, outer, wpos, npairs, perm, palt, err;
     double det_log, det_sign, tr_log, tr_sign, cfgsign, wmin, wmax;
     Philox rng;
-    int lane;
     double* log;           // replay record for the current step (or nullptr)
 };
 
@@ -323,7 +326,7 @@ W2B_HD double* bra_slot(const Chains& C, const Ctx& x, int i) { return x.bra + (
 
 // all cache slots back to "operator i owns slot i", nothing valid
 W2B_HD void slots_reset(const Chains& C, Ctx& x) {
-    for (int i = x.lane; i < C.ops_cap; i += W2B_WARP) { x.slot[i] = (unsigned short)i; x.freel[i] = (unsigned short)(C.ops_cap - 1 - i); }
+    for (int i = lane_id(); i < C.ops_cap; i += W2B_WARP) { x.slot[i] = (unsigned short)i; x.freel[i] = (unsigned short)(C.ops_cap - 1 - i); }
     x.nfree = C.ops_cap - x.n; x.kv = 0; x.bv = x.n;
     wsync();
 }
@@ -379,32 +382,6 @@ W2B_HDN void extend_bras(const Tables& T, const Chains& C, Ctx& x, int downto) {
     x.bv = downto;
 }
 
-// Trace of the configuration that keeps operators [0, s) and [e, n) and has, in between: optional new operator A,
-// the old operators [lo, hi), optional new operator B.  Parts of every outer state go to x.mpt.
-W2B_HDN void seg_trace(const Tables& T, const Chains& C, Ctx& x, int s, int e, bool hasA, double tA, int codeA, int lo, int hi,
-                       bool hasB, double tB, int codeB, double& tlog, double& tsign) {
-    extend_bras(T, C, x, e);
-    const bool have = extend_kets(T, C, x, s - 1);          // bras first: the ket frontier may leave KET_{s-1} in the work matrix
-    const int m = ldg(&T.dim[x.outer]), ld = x.ldx;
-    double* X = x.mX;
-    int sst; double tprev;
-    if (s == 0) { mat_identity(X, ld, x.mlg, m); sst = x.outer; tprev = 0.0; }
-    else {
-        sst = (int)x.sst[s - 1]; tprev = x.tau[s - 1];
-        if (!have) {
-            const int d = ldg(&T.dim[sst]);
-            mat_move(X, ld, ket_slot(C, x, s - 1), d, d, m);
-            mat_copy(x.mlg, x.ketlg + (size_t)x.slot[s - 1] * C.dmax, m);
-            wsync();
-        }
-    }
-    if (hasA) { sst = mat_apply(T, sst, codeA, tA - tprev, X, ld, x.mlg, x.mpw, m); tprev = tA; }
-    for (int i = lo; i < hi; ++i) { sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, ld, x.mlg, x.mpw, m); tprev = x.tau[i]; }
-    if (hasB) { sst = mat_apply(T, sst, codeB, tB - tprev, X, ld, x.mlg, x.mpw, m); tprev = tB; }
-    if (e == x.n) mat_close(T, sst, T.beta - tprev, X, ld, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
-    else mat_close(T, sst, x.tau[e] - tprev, X, ld, x.mlg, bra_slot(C, x, e), x.bralg + (size_t)x.slot[e] * C.dmax, x.mpw, m, x.mpt, tlog, tsign);
-}
-
 // from-scratch trace of an arbitrary sequence (global moves, tau shifts, set_mc_config); no caches touched
 W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsigned char* code, int n, int outer, double& tlog, double& tsign) {
     const int m = ldg(&T.dim[outer]), ld = x.ldx;
@@ -445,12 +422,16 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
     const short* sst = C.op_sst + (size_t)chain * C.ops_cap; const unsigned short* slot = C.op_slot + (size_t)chain * C.ops_cap;
     double* ket = C.ket + (size_t)chain * C.ops_cap * C.mstride; double* bra = C.bra + (size_t)chain * C.ops_cap * C.mstride;
     double* ketlg = C.ketlg + (size_t)chain * C.ops_cap * C.dmax; double* bralg = C.bralg + (size_t)chain * C.ops_cap * C.dmax;
-    const bool rare = (entry & Q_RARE) != 0;
+    const bool rare = (entry & Q_RARE) != 0, meas = (entry & Q_MEAS) != 0;
     const int n = ih[IH_NOPS];
     int outer = ih[IH_OUTER], kv = ih[IH_KV], bv = ih[IH_BV];
     const Prop& P = C.prop[chain];
     int i1 = P.i1, i2 = P.i2;
     bool store_seg = false;
+    if (meas) {                                                   // kets of the operators with tau <= beta/2, bras of the others (update_b2_states_eb)
+        if (n == 0 || nt * 8 >= ldg(&T.dim[outer])) return;
+        i1 = i2 = count_le(tau, n, T.beta / 2.0);
+    }
     if (rare) {                                                   // whole (relabelled / shifted) sequence from the identity, no caches used
         const RareJob& J = C.rjob[chain];
         outer = J.new_outer; kv = 0; bv = n; i1 = 0; i2 = n;
@@ -458,7 +439,7 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
         if (J.kind == 4) tau = C.sc_tau + (size_t)chain * C.ops_cap;
         store_seg = J.stored != 0;
     }
-    const int s = i1, e = (rem && !rare) ? i2 + 1 : i2, lo = (rem && !rare) ? i1 + 1 : i1, hi = i2, nA = (rem || rare) ? 0 : 1;
+    const int s = i1, e = (rem && !rare) ? i2 + 1 : i2, lo = (rem && !rare) ? i1 + 1 : i1, hi = i2, nA = (rem || rare || meas) ? 0 : 1;
     const double tA = P.t1, tB = P.t2;
     const int codeA = P.f * 2 + P.type1, codeB = P.f * 2 + (1 - P.type1);
     const int m = ldg(&T.dim[outer]), ld = C.ldx;
@@ -466,6 +447,7 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
     const int nb = bv > e ? bv - e : 0, nk = kv <= s - 1 ? s - kv : 0, ns = nA + (hi - lo) + nA;
     const int total = nb + nk + ns;
     int cur = -1;                        // block of the work matrix (rows)
+    int work = 0;                        // sum of d_out * d_in over the operator products of this job
     int r_opc = 0, r_sst = 0, r_slot = 0; double r_dt = 0.0;
     for (int j = 0; j < total; ++j) {
         if ((j & (W2B_WARP - 1)) == 0) {                       // next 32 step records, one per lane
@@ -508,16 +490,14 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
             else load_tile(T, C, X, lg, ket + (size_t)slot[s - 1] * C.mstride, ketlg + (size_t)slot[s - 1] * C.dmax, cur, j0, mw);
         }
         const int in = sin >= 0 ? sin : cur;
-        cur = mat_apply_inl<1>(T, in, opc, dt, X, ld, lg, pw, mw);
-        if (sl >= 0) {                                          // fill this job's columns of the operator's cache slot
-            const int d = ldg(&T.dim[cur]);
-            double* dst = ((sl >> 16) == 1 ? ket : bra) + (size_t)(sl & 0xffff) * C.mstride + j0 * d;
-            double* dlg = ((sl >> 16) == 1 ? ketlg : bralg) + (size_t)(sl & 0xffff) * C.dmax + j0;
-            mat_move(dst, d, X, ld, d, mw);
-            for (int jj = lane; jj < mw; jj += W2B_WARP) dlg[jj] = lg[jj];
-            wsync();
+        double* dst = nullptr; double* dlg = nullptr;
+        if (sl >= 0) {                                          // this job's columns of the operator's cache slot are filled by the product's epilogue
+            dst = ((sl >> 16) == 1 ? ket : bra) + (size_t)(sl & 0xffff) * C.mstride;
+            dlg = ((sl >> 16) == 1 ? ketlg : bralg) + (size_t)(sl & 0xffff) * C.dmax + j0;
         }
+        cur = mat_apply_inl<1>(T, in, opc, dt, X, ld, lg, pw, mw, dst, dlg, j0, &work);
     }
+    if (meas) return;
     if (ns == 0 && nk == 0) {                                   // nothing applied after the ket frontier: work matrix = KET_{s-1}
         cur = s == 0 ? outer : (int)sst[s - 1];
         if (s == 0) load_tile(T, C, X, lg, nullptr, nullptr, outer, j0, mw);
@@ -530,18 +510,19 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
         const int d = ldg(&T.dim[cur]);
         mat_close_parts(T, cur, tau[e] - tlast, X, ld, lg, bra + (size_t)slot[e] * C.mstride + j0 * d, bralg + (size_t)slot[e] * C.dmax + j0, pw, mw, j0, pt);
     }
+    if (lane == 0 && work) atomic_add(&C.counters[(size_t)chain * C_NCNT + C_TRFLOPS], 2ull * (unsigned long long)work * (unsigned long long)mw);   // per-chain counter: no hot address
 }
 
 // trace contributions of the outer states of an empty configuration: w_exp(-(E_j - Egs) beta)
 W2B_HD void empty_parts(const Tables& T, Ctx& x, int outer) {
     const int m = ldg(&T.dim[outer]);
     const double* ev = T.evals + ldg(&T.offset[outer]);
-    for (int j = x.lane; j < m; j += W2B_WARP) { x.pt[2 * j] = -(ldg(&ev[j]) - T.egs) * T.beta; x.pt[2 * j + 1] = 1.0; }
+    for (int j = lane_id(); j < m; j += W2B_WARP) { x.pt[2 * j] = -(ldg(&ev[j]) - T.egs) * T.beta; x.pt[2 * j + 1] = 1.0; }
     wsync();
 }
 W2B_HDN void commit_parts(const Tables& T, Ctx& x) {
     const int m = ldg(&T.dim[x.outer]);
-    for (int j = x.lane; j < 2 * m; j += W2B_WARP) x.pt[j] = x.mpt[j];
+    for (int j = lane_id(); j < 2 * m; j += W2B_WARP) x.pt[j] = x.mpt[j];
 }
 
 // integer superstate walk over the old operators [i0, i0+mcount) starting from `cur`; counts operators of another flavour
@@ -563,7 +544,7 @@ W2B_HDN int walk_check(const Tables& T, const Ctx& x, int i0, int mcount, int f,
 W2B_HDN double det_ratio_add(const Tables& T, const Chains& C, Ctx& x, int f, double tau_c, double tau_a) {
     int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
-    for (int j = x.lane; j < k; j += W2B_WARP) {
+    for (int j = lane_id(); j < k; j += W2B_WARP) {
         x.wQ[j] = hybrF(T, ta[j] - tau_c, f);              // Q_j = F(tau_a_j - tau_c,new)
         x.wR[j] = hybrF(T, tau_a - tc[j], f);              // R_i = F(tau_a,new - tau_c_i)
     }
@@ -571,7 +552,7 @@ W2B_HDN double det_ratio_add(const Tables& T, const Chains& C, Ctx& x, int f, do
     const double* M = Mbuf(C, x, f);
     const int ld = C.ld;
     double part = 0.0;
-    for (int j = x.lane; j < k; j += W2B_WARP) {
+    for (int j = lane_id(); j < k; j += W2B_WARP) {
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         int i = 0;
         for (; i + 3 < k; i += 4) {
@@ -597,21 +578,21 @@ W2B_HDN void mat_add(const Chains& C, Ctx& x, int f, int nf, int p1, int p2, dou
     const int ld = C.ld; const double inv = 1.0 / S;
     for (int in = 0; in <= k; ++in) {
         if (in == p1) {
-            for (int jn = x.lane; jn <= k; jn += W2B_WARP)
+            for (int jn = lane_id(); jn <= k; jn += W2B_WARP)
                 dst[(size_t)in * ld + jn] = (jn == p2) ? inv : -x.wV[jn - (jn > p2)] * inv;
         } else {
             int i = in - (in > p1);
             double part = 0.0;
-            for (int j = x.lane; j < k; j += W2B_WARP) part += src[(size_t)i * ld + j] * x.wQ[j];
+            for (int j = lane_id(); j < k; j += W2B_WARP) part += src[(size_t)i * ld + j] * x.wQ[j];
             double u = wsum(part);
-            for (int jn = x.lane; jn <= k; jn += W2B_WARP) {
+            for (int jn = lane_id(); jn <= k; jn += W2B_WARP) {
                 if (jn == p2) dst[(size_t)in * ld + jn] = -u * inv;
                 else { int j = jn - (jn > p2); dst[(size_t)in * ld + jn] = src[(size_t)i * ld + j] + u * x.wV[j] * inv; }
             }
         }
     }
     wsync();
-    if (x.lane == 0) { int t = x.ih[IH_MSLOT + f]; x.ih[IH_MSLOT + f] = x.ih[IH_MSLOT + nf]; x.ih[IH_MSLOT + nf] = t; x.ih[IH_KF + f] = k + 1; }
+    if (lane_id() == 0) { int t = x.ih[IH_MSLOT + f]; x.ih[IH_MSLOT + f] = x.ih[IH_MSLOT + nf]; x.ih[IH_MSLOT + nf] = t; x.ih[IH_KF + f] = k + 1; }
     wsync();
 }
 
@@ -620,33 +601,33 @@ W2B_HDN void mat_rem(const Chains& C, Ctx& x, int f, int nf, int p1, int p2) {
     int k = x.ih[IH_KF + f];
     const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, nf);
     const int ld = C.ld;
-    for (int j = x.lane; j < k; j += W2B_WARP) { x.wV[j] = src[(size_t)p1 * ld + j]; x.wQ[j] = src[(size_t)j * ld + p2]; }
+    for (int j = lane_id(); j < k; j += W2B_WARP) { x.wV[j] = src[(size_t)p1 * ld + j]; x.wQ[j] = src[(size_t)j * ld + p2]; }
     wsync();
     const double ipiv = 1.0 / src[(size_t)p1 * ld + p2];
     for (int i = 0; i < k - 1; ++i) {
         int io = i + (i >= p1);
         double c = x.wQ[io];
-        for (int j = x.lane; j < k - 1; j += W2B_WARP) {
+        for (int j = lane_id(); j < k - 1; j += W2B_WARP) {
             int jo = j + (j >= p2);
             dst[(size_t)i * ld + j] = src[(size_t)io * ld + jo] - c * x.wV[jo] * ipiv;
         }
     }
     wsync();
-    if (x.lane == 0) { int t = x.ih[IH_MSLOT + f]; x.ih[IH_MSLOT + f] = x.ih[IH_MSLOT + nf]; x.ih[IH_MSLOT + nf] = t; x.ih[IH_KF + f] = k - 1; }
+    if (lane_id() == 0) { int t = x.ih[IH_MSLOT + f]; x.ih[IH_MSLOT + f] = x.ih[IH_MSLOT + nf]; x.ih[IH_MSLOT + nf] = t; x.ih[IH_KF + f] = k - 1; }
     wsync();
 }
 
 // ------------------------------------------------------------------ logging helpers
 W2B_HD void log_begin(Ctx& x, int type) {
-    if (x.log && x.lane == 0) { for (int i = 0; i < LOGW; ++i) x.log[i] = 0.0; x.log[0] = type; x.log[4] = -1; }
+    if (x.log && lane_id() == 0) { for (int i = 0; i < LOGW; ++i) x.log[i] = 0.0; x.log[0] = type; x.log[4] = -1; }
 }
-W2B_HD void log_set(Ctx& x, int i, double v) { if (x.log && x.lane == 0) x.log[i] = v; }
+W2B_HD void log_set(Ctx& x, int i, double v) { if (x.log && lane_id() == 0) x.log[i] = v; }
 W2B_HD void log_end(Ctx& x, int status) {
-    if (x.log && x.lane == 0) { x.log[1] = status; x.log[12] = x.n; x.log[13] = x.outer; x.log[15] = x.cfgsign; }
+    if (x.log && lane_id() == 0) { x.log[1] = status; x.log[12] = x.n; x.log[13] = x.outer; x.log[15] = x.cfgsign; }
 }
-W2B_HD void bump(Ctx& x, int c) { if (x.lane == 0) x.cnt[c] += 1ull; }
+W2B_HD void bump(Ctx& x, int c) { if (lane_id() == 0) x.cnt[c] += 1ull; }
 // algorithmic bytes of the determinant path (definition in DESIGN.md "Roofline accounting")
-W2B_HD void bump_bytes(Ctx& x, long long b) { if (x.lane == 0) x.cnt[C_ALGBYTES] += (unsigned long long)b; }
+W2B_HD void bump_bytes(Ctx& x, long long b) { if (lane_id() == 0) x.cnt[C_ALGBYTES] += (unsigned long long)b; }
 
 // ------------------------------------------------------------------ pair insertion / removal, split into two phases
 // The CTA-level scheduler (cta_sweep below) runs all chains of a CTA through the SAME phase at the same time so that the
@@ -700,7 +681,7 @@ W2B_HDN bool add_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
         if (cur >= 0) new_end = conn(T, cur, code2);
     }
     if (new_end < 0 || new_end != old_after) { bump(x, C_QNADD); log_end(x, 2); return false; }
-    if (x.lane == 0) {
+    if (lane_id() == 0) {
         P.t1 = t1; P.t2 = t2; P.tau_a = tau_a; P.tau_c = tau_c; P.factor = mul_rn(W, w2); P.dlog = dlog; P.dsign = dsign;
         P.f = f; P.i1 = i1; P.i2 = i2; P.p1 = p1; P.p2 = p2; P.begin_sst = begin_sst; P.nother = nother; P.type1 = a_first ? 1 : 0;
     }
@@ -721,8 +702,8 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     bump_bytes(x, 8ll * k * k);
     double tn_log = 0.0, tn_sign = 1.0;
     if (blocked) {                                                     // get_trace_EB of the proposed configuration
-        if (x.pre) { parts_sum(x.mpt, ldg(&T.dim[x.outer]), tn_log, tn_sign); if (x.kv < i1) x.kv = i1; if (x.bv > i2) x.bv = i2; }
-        else seg_trace(T, C, x, i1, i2, true, t1, code1, i1, i2, true, t2, code2, tn_log, tn_sign);
+        // the trace kernel has left the per-outer-state parts of the proposed configuration in C.ptc and extended the cache frontiers
+        parts_sum(x.mpt, ldg(&T.dim[x.outer]), tn_log, tn_sign); if (x.kv < i1) x.kv = i1; if (x.bv > i2) x.bv = i2;
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
@@ -740,13 +721,13 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     bump_bytes(x, 8ll * (k * k + (k + 1) * (k + 1)));
     mat_add(C, x, f, T.nf, p1, p2, S);
     shift_up(x.tc + (size_t)f * C.kcap, p1, k, 1); shift_up(x.ta + (size_t)f * C.kcap, p2, k, 1);
-    if (x.lane == 0) { x.tc[(size_t)f * C.kcap + p1] = tau_c; x.ta[(size_t)f * C.kcap + p2] = tau_a; }
+    if (lane_id() == 0) { x.tc[(size_t)f * C.kcap + p1] = tau_c; x.ta[(size_t)f * C.kcap + p2] = tau_a; }
     shift_up(x.tau, i2, x.n, 2); shift_up(x.code, i2, x.n, 2); shift_up(x.sst, i2, x.n, 2);
     shift_up(x.tau, i1, i2, 1); shift_up(x.code, i1, i2, 1); shift_up(x.sst, i1, i2, 1);
-    if (x.lane == 0) { x.tau[i1] = t1; x.code[i1] = (unsigned char)code1; x.tau[i2 + 1] = t2; x.code[i2 + 1] = (unsigned char)code2; }
+    if (lane_id() == 0) { x.tau[i1] = t1; x.code[i1] = (unsigned char)code1; x.tau[i2 + 1] = t2; x.code[i2 + 1] = (unsigned char)code2; }
     if (blocked) {                                                     // two fresh cache slots; kets valid below i1, bras from i2+2 on
         shift_up(x.slot, i2, x.n, 2); shift_up(x.slot, i1, i2, 1);
-        if (x.lane == 0) { x.slot[i1] = x.freel[x.nfree - 1]; x.slot[i2 + 1] = x.freel[x.nfree - 2]; }
+        if (lane_id() == 0) { x.slot[i1] = x.freel[x.nfree - 1]; x.slot[i2 + 1] = x.freel[x.nfree - 2]; }
         x.nfree -= 2; x.kv = i1; x.bv = i2 + 2;
         commit_parts(T, x);
     }
@@ -760,7 +741,7 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     x.npairs = np_new;
     update_cfgsign(T, x);
     bump(x, C_ACCADD);
-    if (x.lane == 0) {
+    if (lane_id() == 0) {
         int bin = (int)floor((t2 - t1) / R.accpair_max * (double)R.naccpair) + 1; if (bin > R.naccpair) bin = R.naccpair;   // CTQMC.F90:3579-3582
         atomic_add(&A.accpair[(size_t)f * R.naccpair + bin - 1], 1ull);
     }
@@ -781,7 +762,7 @@ W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     int i1 = -1, f = 0, type1 = 0, midx = 0; double t1 = 0.0;
     int cum = 0;
     for (int base = ia; base < ib; base += W2B_WARP) {
-        int i = base + x.lane; bool act = i < ib;
+        int i = base + lane_id(); bool act = i < ib;
         int c = 0, lb = 0, fi = 0, ty = 0; double ti = 0.0;
         if (act) {
             int cd = x.code[i]; fi = cd >> 1; ty = cd & 1; ti = x.tau[i];
@@ -836,7 +817,7 @@ W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
         cur = walk_check(T, x, i1 + 1, i2 - i1 - 1, f, cur, nother);
         if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return false; }
     }
-    if (x.lane == 0) {
+    if (lane_id() == 0) {
         P.t1 = t1; P.t2 = t2; P.tau_a = 0.0; P.tau_c = 0.0; P.factor = factor; P.dlog = dlog; P.dsign = dsign;
         P.f = f; P.i1 = i1; P.i2 = i2; P.p1 = p1; P.p2 = p2; P.begin_sst = begin_sst; P.nother = nother; P.type1 = type1;
     }
@@ -853,8 +834,7 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     double dlog = P.dlog, dsign = P.dsign, tn_log = 0.0, tn_sign = 1.0;
     if (blocked) {
-        if (x.pre) { parts_sum(x.mpt, ldg(&T.dim[x.outer]), tn_log, tn_sign); if (x.kv < i1) x.kv = i1; if (x.bv > i2 + 1) x.bv = i2 + 1; }
-        else seg_trace(T, C, x, i1, i2 + 1, false, 0.0, 0, i1 + 1, i2, false, 0.0, 0, tn_log, tn_sign);
+        parts_sum(x.mpt, ldg(&T.dim[x.outer]), tn_log, tn_sign); if (x.kv < i1) x.kv = i1; if (x.bv > i2 + 1) x.bv = i2 + 1;
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
     // determinant ratio = M(p1,p2)  (MatrixUpdate.F90:445-452)
@@ -872,7 +852,7 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     mat_rem(C, x, f, T.nf, p1, p2);
     shift_down(x.tc + (size_t)f * C.kcap, p1, k, 1); shift_down(x.ta + (size_t)f * C.kcap, p2, k, 1);
     if (blocked) {                                                     // give the two cache slots back; kets valid below i1, bras from i2-1 on
-        if (x.lane == 0) { x.freel[x.nfree] = x.slot[i1]; x.freel[x.nfree + 1] = x.slot[i2]; }
+        if (lane_id() == 0) { x.freel[x.nfree] = x.slot[i1]; x.freel[x.nfree + 1] = x.slot[i2]; }
         wsync();
         shift_down(x.slot, i1, i2, 1); shift_down(x.slot, i2 - 1, x.n, 2);
         x.nfree += 2; x.kv = i1; x.bv = i2 - 1;
@@ -889,7 +869,7 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     x.npairs = np_new;
     update_cfgsign(T, x);
     bump(x, C_ACCREM);
-    if (x.lane == 0) {
+    if (lane_id() == 0) {
         int bin = (int)floor((t2 - t1) / R.accpair_max * (double)R.naccpair) + 1; if (bin > R.naccpair) bin = R.naccpair;   // CTQMC.F90:3579-3582
         atomic_add(&A.accpair[(size_t)f * R.naccpair + bin - 1], 1ull);
     }
@@ -978,7 +958,7 @@ W2B_HDN void rebuild_inverses(const Tables& T, const Chains& C, Ctx& x, const do
         const double* tc = tcs + (size_t)f * C.kcap; const double* ta = tas + (size_t)f * C.kcap;
         // a[ia][ic] = Delta(ia, ic); its inverse inv[ic][ia] is what M stores at [creator ic][annihilator ia]
         for (int ia = 0; ia < k; ++ia)
-            for (int ic = x.lane; ic < k; ic += W2B_WARP) a[(size_t)ia * C.ld + ic] = hybrF(T, ta[ia] - tc[ic], f);
+            for (int ic = lane_id(); ic < k; ic += W2B_WARP) a[(size_t)ia * C.ld + ic] = hybrF(T, ta[ia] - tc[ic], f);
         wsync();
         double l, s;
         invert_inplace(a, k, C.ld, x.wI, want_inverse, l, s);
@@ -1000,23 +980,23 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
     int type;
     if (r < 0.3) {                         // gen_SpinFlipUpdate Trace.F90:1150-1166
         type = 3;
-        if (x.lane == 0) { gu[0] = 0; for (int i = 1; i <= nb; ++i) gu[i] = i + nb; for (int i = nb + 1; i <= nf; ++i) gu[i] = i - nb; }
+        if (lane_id() == 0) { gu[0] = 0; for (int i = 1; i <= nb; ++i) gu[i] = i + nb; for (int i = nb + 1; i <= nf; ++i) gu[i] = i - nb; }
     } else if (r < 0.6) {                  // gen_CAFlip 1186-1198
         type = 4;
-        if (x.lane == 0) { gu[0] = 1; for (int i = 1; i <= nf; ++i) gu[i] = i; }
+        if (lane_id() == 0) { gu[0] = 1; for (int i = 1; i <= nf; ++i) gu[i] = i; }
     } else {                               // gen_GlobalUpdate_new 1103-1123 (NSymMove = 0)
         type = 1;
-        if (x.lane == 0) for (int i = 1; i <= nf; ++i) gu[i] = i;
+        if (lane_id() == 0) for (int i = 1; i <= nf; ++i) gu[i] = i;
         wsync();
-        for (int j = 1; j <= nf; ++j) { int i = x.rng.randint(j, nf); if (x.lane == 0) { int t = gu[j]; gu[j] = gu[i]; gu[i] = t; } wsync(); }
+        for (int j = 1; j <= nf; ++j) { int i = x.rng.randint(j, nf); if (lane_id() == 0) { int t = gu[j]; gu[j] = gu[i]; gu[i] = t; } wsync(); }
         int flip = x.rng.randint(0, 1);
-        if (x.lane == 0) gu[0] = flip;
+        if (lane_id() == 0) gu[0] = flip;
     }
     wsync();
     log_set(x, 4, type);
     const int flip = gu[0];
     // relabelled operator codes (globalUpdate Trace.F90:2126-2188); flavour f=2b+s <-> gu index b+nb*s+1
-    for (int i = x.lane; i < x.n; i += W2B_WARP) {
+    for (int i = lane_id(); i < x.n; i += W2B_WARP) {
         int cd = x.code[i], f = cd >> 1, ty = cd & 1, b = f >> 1, s = f & 1;
         int g = gu[b + nb * s + 1] - 1;
         int f2 = (g % nb) * 2 + g / nb;
@@ -1034,7 +1014,7 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
         int pold = 0, pnew = 0;
         // each lane walks one candidate outer superstate through the old and the new sequence
         for (int base = 0; base < T.nsst; base += W2B_WARP) {
-            int k0 = base + x.lane; bool act = k0 < T.nsst;
+            int k0 = base + lane_id(); bool act = k0 < T.nsst;
             int co = act ? k0 : -1, cn = act ? k0 : -1;
             for (int i = 0; i < x.n; ++i) {
                 int a = x.code[i], b2 = x.sc_code[i];
@@ -1061,10 +1041,10 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
     for (int f = 0; f < nf; ++f) {
         int b = f >> 1, s = f & 1, g = gu[b + nb * s + 1] - 1, f2 = (g % nb) * 2 + g / nb;
         int k = x.ih[IH_KF + f];
-        if (x.lane == 0) J.knew[f2] = k;
+        if (lane_id() == 0) J.knew[f2] = k;
         const double* oc = x.tc + (size_t)f * C.kcap; const double* oa = x.ta + (size_t)f * C.kcap;
         double* nc = x.sc_tc + (size_t)f2 * C.kcap; double* na = x.sc_ta + (size_t)f2 * C.kcap;
-        for (int i = x.lane; i < k; i += W2B_WARP) { nc[i] = flip ? oa[i] : oc[i]; na[i] = flip ? oc[i] : oa[i]; }
+        for (int i = lane_id(); i < k; i += W2B_WARP) { nc[i] = flip ? oa[i] : oc[i]; na[i] = flip ? oc[i] : oa[i]; }
     }
     wsync();
     // determinant of the new configuration from scratch (LU in the spare buffer).  The reference obtains the old determinant
@@ -1072,7 +1052,7 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
     // rounding of the fast updates (pinned by the from-scratch tests), so the second LU is not repeated here.
     double dn_log, dn_sign;
     rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, J.knew, false, dn_log, dn_sign);
-    if (x.lane == 0) { J.kind = 3; J.new_outer = new_outer; J.type = type; J.factor = factor; J.dn_log = dn_log; J.dn_sign = dn_sign; J.stored = 0; }
+    if (lane_id() == 0) { J.kind = 3; J.new_outer = new_outer; J.type = type; J.factor = factor; J.dn_log = dn_log; J.dn_sign = dn_sign; J.stored = 0; }
     wsync();
     return true;
 }
@@ -1088,13 +1068,13 @@ W2B_HDN void step_glob_finish(const Tables& T, const Run& R, const Chains& C, Ct
     // ---- accept
     long long sumk2 = 0; for (int f = 0; f < nf; ++f) sumk2 += (long long)x.ih[IH_KF + f] * x.ih[IH_KF + f];
     bump_bytes(x, 8ll * sumk2);
-    for (int i = x.lane; i < x.n; i += W2B_WARP) { x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
+    for (int i = lane_id(); i < x.n; i += W2B_WARP) { x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
     for (int f = 0; f < nf; ++f) {
         int k = J.knew[f];
-        for (int i = x.lane; i < k; i += W2B_WARP) { x.tc[(size_t)f * C.kcap + i] = x.sc_tc[(size_t)f * C.kcap + i]; x.ta[(size_t)f * C.kcap + i] = x.sc_ta[(size_t)f * C.kcap + i]; }
+        for (int i = lane_id(); i < k; i += W2B_WARP) { x.tc[(size_t)f * C.kcap + i] = x.sc_tc[(size_t)f * C.kcap + i]; x.ta[(size_t)f * C.kcap + i] = x.sc_ta[(size_t)f * C.kcap + i]; }
     }
     wsync();
-    if (x.lane == 0) for (int f = 0; f < nf; ++f) x.ih[IH_KF + f] = J.knew[f];
+    if (lane_id() == 0) for (int f = 0; f < nf; ++f) x.ih[IH_KF + f] = J.knew[f];
     wsync();
     double l2, s2;
     rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
@@ -1129,12 +1109,12 @@ W2B_HDN bool step_shift_prepare(const Tables& T, const Run& R, const Chains& C, 
     const int nwrap = count_lt(x.tau, n, dt);                     // operators passing through tau = 0
     const int first = nwrap == n ? 0 : nwrap;
     const int new_outer = first == 0 ? x.outer : (int)x.sst[first - 1];
-    for (int i = x.lane; i < n; i += W2B_WARP) {
+    for (int i = lane_id(); i < n; i += W2B_WARP) {
         int src = first + i; if (src >= n) src -= n;
         double t = x.tau[src] - dt; if (t < 0.0) t += T.beta;     // modulo(tau - dt, beta)
         x.sc_tau[i] = t; x.sc_code[i] = x.code[src]; x.sc_sst[i] = x.sst[src];
     }
-    if (x.lane == 0) { J.kind = 4; J.dt = dt; J.new_outer = new_outer; J.stored = 0; }
+    if (lane_id() == 0) { J.kind = 4; J.dt = dt; J.new_outer = new_outer; J.stored = 0; }
     wsync();
     return true;
 }
@@ -1166,19 +1146,19 @@ W2B_HDN void step_shift_finish(const Tables& T, const Run& R, const Chains& C, C
             bump_bytes(x, 16ll * k * k);
             for (int i = 0; i < k; ++i) {
                 int in = i - w1; double si = 1.0; if (in < 0) { in += k; si = -1.0; }
-                for (int j = x.lane; j < k; j += W2B_WARP) {
+                for (int j = lane_id(); j < k; j += W2B_WARP) {
                     int jn = j - w2; double sj = si; if (jn < 0) { jn += k; sj = -si; }
                     dst[(size_t)in * C.ld + jn] = sj * src[(size_t)i * C.ld + j];
                 }
             }
             wsync();
-            if (x.lane == 0) { int t = x.ih[IH_MSLOT + f]; x.ih[IH_MSLOT + f] = x.ih[IH_MSLOT + T.nf]; x.ih[IH_MSLOT + T.nf] = t; }
+            if (lane_id() == 0) { int t = x.ih[IH_MSLOT + f]; x.ih[IH_MSLOT + f] = x.ih[IH_MSLOT + T.nf]; x.ih[IH_MSLOT + T.nf] = t; }
             wsync();
         }
         if ((k & 1) && ((w1 + w2) & 1)) detrat = -detrat;
         // rotate the flavour tau arrays
         double* scc = x.sc_tc + (size_t)f * C.kcap; double* sca = x.sc_ta + (size_t)f * C.kcap;
-        for (int i = x.lane; i < k; i += W2B_WARP) {
+        for (int i = lane_id(); i < k; i += W2B_WARP) {
             int s1 = i + w1; if (s1 >= k) s1 -= k;
             int s2 = i + w2; if (s2 >= k) s2 -= k;
             double v1 = tc[s1] - dt; if (v1 < 0.0) v1 += T.beta;
@@ -1186,10 +1166,10 @@ W2B_HDN void step_shift_finish(const Tables& T, const Run& R, const Chains& C, C
             scc[i] = v1; sca[i] = v2;
         }
         wsync();
-        for (int i = x.lane; i < k; i += W2B_WARP) { tc[i] = scc[i]; ta[i] = sca[i]; }
+        for (int i = lane_id(); i < k; i += W2B_WARP) { tc[i] = scc[i]; ta[i] = sca[i]; }
         wsync();
     }
-    for (int i = x.lane; i < n; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
+    for (int i = lane_id(); i < n; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
     wsync();
     x.outer = new_outer;
     x.tr_log = tn_log; x.tr_sign = tn_sign; x.det_sign *= detrat;
@@ -1214,7 +1194,6 @@ W2B_HD void step_rare(const Tables& T, const Run& R, const Chains& C, Ctx& x, Ra
 
 // ------------------------------------------------------------------ chain load / store
 W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, double* wscratch, int* iscratch, double* mscratch) {
-    x.lane = lane_id();
     x.tau = C.op_tau + (size_t)chain * C.ops_cap; x.code = C.op_code + (size_t)chain * C.ops_cap; x.sst = C.op_sst + (size_t)chain * C.ops_cap;
     x.sc_tau = C.sc_tau + (size_t)chain * C.ops_cap; x.sc_code = C.sc_code + (size_t)chain * C.ops_cap; x.sc_sst = C.sc_sst + (size_t)chain * C.ops_cap;
     x.tc = C.tau_c + (size_t)chain * T.nf * C.kcap; x.ta = C.tau_a + (size_t)chain * T.nf * C.kcap;
@@ -1240,7 +1219,7 @@ W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain,
 }
 W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
-    if (x.lane == 0) {
+    if (lane_id() == 0) {
         x.ih[IH_NOPS] = x.n; x.ih[IH_OUTER] = x.outer; x.ih[IH_WPOS] = x.wpos; x.ih[IH_NPAIRS] = x.npairs;
         x.ih[IH_PERM] = x.perm; x.ih[IH_PALT] = x.palt; x.ih[IH_ERR] = x.err;
         if (C.dmax > 1) { x.ih[IH_KV] = x.kv; x.ih[IH_BV] = x.bv; x.ih[IH_NFREE] = x.nfree; }
@@ -1306,7 +1285,7 @@ W2B_HDN void post_move_cta(const Tables& T, const Run& R, Ctx& x, CtaShared& S, 
             x.npairs = -1;
         }
     }
-    if (x.lane == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; S.left[c] -= 1; }
+    if (lane_id() == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; S.left[c] -= 1; }
     wsync();
 }
 
@@ -1401,6 +1380,35 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
 }
 
 
+// Pull the records one chain's move will touch into the cache hierarchy with one burst of prefetches (one 128-byte line per
+// lane and instruction) before the first dependent access: with tens of thousands of chains the population is far larger than
+// L2 and every first touch is a DRAM round trip; unprefetched, a move pays dozens of them one after the other.
+W2B_HD void prefetch_line(const void* p) {
+#if W2B_DEVICE
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+W2B_HD void prefetch_chain(const Tables& T, const Chains& C, int chain, int n_hint) {
+#if W2B_DEVICE
+    const int l = lane_id();
+    const int nl = (n_hint + 15) >> 4;                            // lines of operator times in use (16 per line)
+    const char* p = nullptr;
+    if (l < 8) { if (l < nl || l == 0) p = (const char*)(C.op_tau + (size_t)chain * C.ops_cap) + l * 128; }
+    else if (l < 10) { if ((l - 8) * 64 < n_hint || l == 8) p = (const char*)(C.op_sst + (size_t)chain * C.ops_cap) + (l - 8) * 128; }
+    else if (l == 10) p = (const char*)(C.op_code + (size_t)chain * C.ops_cap);
+    else if (l == 11) p = (const char*)(C.op_code + (size_t)chain * C.ops_cap) + 128;
+    else if (l < 14) p = (const char*)(C.ih + (size_t)chain * IH_STRIDE) + (l - 12) * 128;
+    else if (l == 14) p = (const char*)(C.dh + (size_t)chain * DH_STRIDE);
+    else if (l == 15) p = (const char*)(C.counters + (size_t)chain * C_NCNT);
+    else if (l == 16) p = (const char*)(C.rng_ctr + chain);
+    else if (l == 17) p = (const char*)(C.prop + chain);
+    else if (l == 18) p = (const char*)(C.prop + chain) + 128 - 8;
+    else if (l < 21 && C.dmax > 1) p = (const char*)(C.op_slot + (size_t)chain * C.ops_cap) + (l - 19) * 128;
+    if (p) prefetch_line(p);
+    for (int q = l; q < 2 * T.nf; q += W2B_WARP)                  // first line of every flavour's creator / annihilator times
+        prefetch_line((const char*)(((q & 1) ? C.tau_a : C.tau_c) + ((size_t)chain * T.nf + (q >> 1)) * C.kcap));
+#endif
+}
 // bookkeeping after every move: window shift (checked after EVERY move, CTQMC.F90:8255/8531), step counter, quota
 W2B_HDN void post_move(const Tables& T, const Run& R, const Chains& C, Ctx& x, int chain) {
     wsync();
@@ -1412,7 +1420,7 @@ W2B_HDN void post_move(const Tables& T, const Run& R, const Chains& C, Ctx& x, i
             x.npairs = -1;
         }
     }
-    if (x.lane == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; C.left[chain] -= 1; }
+    if (lane_id() == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; C.left[chain] -= 1; }
     wsync();
 }
 
@@ -1426,36 +1434,38 @@ W2B_HDN void post_move(const Tables& T, const Run& R, const Chains& C, Ctx& x, i
 //               one global counter, longest jobs first: rare moves, then outer blocks >= 16, > 1, == 1.
 // Each kernel is small enough for the instruction cache and sized for its own register / shared-memory needs.
 // Within a chain the sequence of moves and RNG draws is exactly the reference's.
-W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int chain, long long nsteps, int parity, int log_chain, double* logbuf) {
+// what one chain's propose phase hands to the round's queues; collected per CTA and flushed with one atomic per queue
+// (tens of thousands of chains pushing one by one serialise on the counters' L2 atomics)
+struct ProposeOut { int run, left, dq, entry, tq, tentry, ntl, rfin; };      // dq / tq: decide / trace queue (0..2, -1 = none)
+
+// `x` is the warp's chain context: the kernels keep ONE copy per warp in shared memory (every lane holds the same values;
+// a per-thread copy lives in local memory, 32x replicated, and its write-back was 1.1 GB of DRAM traffic per propose launch)
+W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int chain, long long nsteps, int parity, int log_chain, double* logbuf,
+                          ProposeOut* out, Ctx& x) {
     const int lane = lane_id();
     int left = C.left[chain];
     if (left <= 0) return;
-    int* sc = C.sched + parity * SC_STRIDE;
+    if (lane == 0) { out->run = 1; out->left = left; }
     const int state = vload_u8(&C.parked[chain]);
     if (state != ST_RUN) {                                        // global move / tau shift in flight on the rare stream
         if (lane == 0) {
-            atomic_add_int(&sc[SC_NRUN], 1); atomic_max_int(&sc[SC_MAXLEFT], left);
             // a move completed on the rare stream re-enters with the NEXT round: its records were written while this kernel was
             // already running and may sit stale in this SM's L1 (lines shared with neighbouring chains)
             if (state == ST_RARE_DONE) C.parked[chain] = ST_RUN;
             if (state == ST_RARE_TRACE) {                         // first half done: this round's trace kernel runs its jobs, the decide kernel the second half
                 const int new_outer = *(const volatile int*)&C.rjob[chain].new_outer;
-                const int ntl = (ldg(&T.dim[new_outer]) + 7) >> 3;
-                int* q_tr0 = C.q_tr0 + (size_t)parity * 4 * C.nchains;
-                const int base = atomic_add_int(&sc[SC_NT0], ntl);
-                for (int t = 0; t < ntl; ++t) q_tr0[base + t] = chain | Q_RARE | (t << Q_NTSHIFT);
-                C.q_rfin[(size_t)parity * C.nchains + atomic_add_int(&sc[SC_NRFIN], 1)] = chain;
+                out->tq = 0; out->tentry = chain | Q_RARE; out->ntl = (ldg(&T.dim[new_outer]) + 7) >> 3; out->rfin = 1;
                 C.parked[chain] = ST_RARE_QUEUED;
             }
         }
         return;
     }
     const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
-    Ctx x; ctx_bind(T, R, C, chain, x, nullptr, nullptr, nullptr);
-    if (lane == 0) { atomic_add_int(&sc[SC_NRUN], 1); atomic_max_int(&sc[SC_MAXLEFT], left); }
+    if (R.prefetch) prefetch_chain(T, C, chain, 128);
+    ctx_bind(T, R, C, chain, x, nullptr, nullptr, nullptr);
     for (int run = 0; run < R.propose_run && left > 0; ++run) {
         const double r = x.rng.next();
-        if (!(r <= thr_rem)) {                                    // global move / tau shift: rare queue
+        if (!(r <= thr_rem)) {                                    // global move / tau shift: rare stream
             if (lane == 0) { C.kind[chain] = (unsigned char)(r <= thr_glob ? 3 : 4); C.parked[chain] = ST_RARE_NEW; }
             break;
         }
@@ -1467,17 +1477,12 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
         if (go) {
             if (lane == 0) {
                 const int m = T.dmax > 1 ? ldg(&T.dim[x.outer]) : 1;
-                if (m >= 16) C.q_dec0[atomic_add_int(&sc[SC_NQ0], 1)] = entry;
-                else if (m > 1) C.q_dec1[atomic_add_int(&sc[SC_NQ1], 1)] = entry;
-                else C.q_dec2[atomic_add_int(&sc[SC_NQ2], 1)] = entry;
+                out->dq = (entry & Q_REM) ? 1 : 0; out->entry = entry;   // insertions and removals in separate queues: neighbouring warps of the decide kernel run the same code
                 if (T.dmax > 1) {                                 // trace jobs: one per 8 outer states, queued by number of steps
                     const Prop& P = C.prop[chain];
                     const int rem = (entry & Q_REM) ? 1 : 0, s = P.i1, e = P.i2 + rem;
                     const int steps = (x.bv > e ? x.bv - e : 0) + (x.kv <= s - 1 ? s - x.kv : 0) + (P.i2 - P.i1 - rem) + (rem ? 0 : 2);
-                    const int ntl = (m + 7) >> 3;
-                    int* q = (steps >= 24 ? C.q_tr0 : (steps >= 8 ? C.q_tr1 : C.q_tr2)) + (size_t)parity * 4 * C.nchains;
-                    const int base = atomic_add_int(&sc[steps >= 24 ? SC_NT0 : (steps >= 8 ? SC_NT1 : SC_NT2)], ntl);
-                    for (int t = 0; t < ntl; ++t) q[base + t] = entry | (t << Q_NTSHIFT);
+                    out->tq = steps >= 24 ? 0 : (steps >= 8 ? 1 : 2); out->tentry = entry; out->ntl = (m + 7) >> 3;
                 }
             }
             break;
@@ -1486,6 +1491,43 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
         --left;
     }
     ctx_store(C, chain, x);
+}
+// one warp appends the `count` results of a CTA to the round's queues
+W2B_HD void propose_flush(const Chains& C, int parity, const ProposeOut* outs, int count) {
+    int* sc = C.sched + parity * SC_STRIDE;
+    const int lane = lane_id();
+    for (int base = 0; base < count; base += W2B_WARP) {
+        const int i = base + lane;
+        ProposeOut o = {0, 0, -1, 0, -1, 0, 0, 0};
+        if (i < count) o = outs[i];
+        const int nrun = wsum(o.run), ml = wmax(o.run ? o.left : 0);
+        if (lane == 0 && nrun) { atomic_add_int(&sc[SC_NRUN], nrun); atomic_max_int(&sc[SC_MAXLEFT], ml); }
+        for (int c = 0; c < 3; ++c) {
+            {   // decide queue c
+                const int mine = o.dq == c ? 1 : 0, incl = wscan_incl(mine), tot = wbcast(incl, W2B_WARP - 1);
+                if (tot) {
+                    int b = 0; if (lane == 0) b = atomic_add_int(&sc[SC_NQ0 + c], tot);
+                    b = wbcast(b, 0);
+                    if (mine) (c == 0 ? C.q_dec0 : (c == 1 ? C.q_dec1 : C.q_dec2))[b + incl - 1] = o.entry;
+                }
+            }
+            {   // trace queue c: ntl consecutive entries per chain
+                const int cnt = o.tq == c ? o.ntl : 0, incl = wscan_incl(cnt), tot = wbcast(incl, W2B_WARP - 1);
+                if (tot) {
+                    int b = 0; if (lane == 0) b = atomic_add_int(&sc[SC_NT0 + c], tot);
+                    b = wbcast(b, 0);
+                    int* q = (c == 0 ? C.q_tr0 : (c == 1 ? C.q_tr1 : C.q_tr2)) + (size_t)parity * 4 * C.nchains;
+                    for (int t = 0; t < cnt; ++t) q[b + incl - cnt + t] = o.tentry | (t << Q_NTSHIFT);
+                }
+            }
+        }
+        const int mine = o.rfin ? 1 : 0, incl = wscan_incl(mine), tot = wbcast(incl, W2B_WARP - 1);
+        if (tot) {
+            int b = 0; if (lane == 0) b = atomic_add_int(&sc[SC_NRFIN], tot);
+            b = wbcast(b, 0);
+            if (mine) C.q_rfin[(size_t)parity * C.nchains + b + incl - 1] = o.tentry & Q_IDMASK;
+        }
+    }
 }
 
 // one ticket of the trace kernel (blocked traces only): tickets run over the three trace queues, longest jobs first
@@ -1504,26 +1546,26 @@ W2B_HD void phase_trace(const Tables& T, const Chains& C, int ticket, int parity
 //                   trace jobs and the second half for its round (trace kernel / decide kernel).
 // The round pipeline never waits for this stream; a chain whose rare move is in flight simply sits out a few rounds.
 W2B_HD void phase_rare(const Tables& T, const Run& R, const Chains& C, int chain, long long nsteps,
-                       int log_chain, double* logbuf, double* wscratch, int* iscratch, double* mscratch) {
+                       int log_chain, double* logbuf, double* wscratch, int* iscratch, double* mscratch, Ctx& x) {
     if (vload_u8(&C.parked[chain]) != ST_RARE_NEW) return;
-    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
     if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - C.left[chain]) * LOGW;
     RareJob& J = C.rjob[chain];
     const int kind = C.kind[chain];
     bool pending = false;
     if (T.dmax > 1) {
         pending = kind == 3 ? step_glob_prepare(T, R, C, x, J) : step_shift_prepare(T, R, C, x, J);
-        if (pending && kind == 4 && x.lane == 0) J.stored = 1;    // tau shifts are accepted with probability ~1: cache the kets of the new sequence
+        if (pending && kind == 4 && lane_id() == 0) J.stored = 1;    // tau shifts are accepted with probability ~1: cache the kets of the new sequence
     } else step_rare(T, R, C, x, J, kind);
     if (!pending) post_move(T, R, C, x, chain);
     ctx_store(C, chain, x);
     fence_device();
-    if (x.lane == 0) vstore_u8(&C.parked[chain], (unsigned char)(pending ? ST_RARE_TRACE : ST_RARE_DONE));
+    if (lane_id() == 0) vstore_u8(&C.parked[chain], (unsigned char)(pending ? ST_RARE_TRACE : ST_RARE_DONE));
 }
 
 // one ticket of the decide kernel: tickets [0, nrare) are rare moves, then the three decide queues
 W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const Accum& A, int ticket, int parity, long long nsteps,
-                         int log_chain, double* logbuf, double* wscratch, int* iscratch, double* mscratch) {
+                         int log_chain, double* logbuf, double* wscratch, int* iscratch, double* mscratch, Ctx& x) {
     const int lane = lane_id();
     const int* sc = C.sched + parity * SC_STRIDE;
     const int nrare = sc[SC_NRFIN], n0 = sc[SC_NQ0], n1 = sc[SC_NQ1];
@@ -1533,7 +1575,8 @@ W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const A
     else if (ticket < nrare + n0 + n1) entry = C.q_dec1[ticket - nrare - n0];
     else entry = C.q_dec2[ticket - nrare - n0 - n1];
     const int chain = entry & Q_IDMASK;
-    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+    if (R.prefetch) { prefetch_chain(T, C, chain, 128); if (!rare) prefetch_minv(T, C, chain, C.prop[chain].f); }
+    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
     if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - C.left[chain]) * LOGW;
     if (!rare && T.dmax > 1) { x.pre = C.ptc + (size_t)chain * 2 * C.dmax; x.mpt = C.ptc + (size_t)chain * 2 * C.dmax; }
     if (rare) {                                                   // second half of a global move / tau shift: the trace kernel has left the parts in C.ptc
@@ -1579,7 +1622,7 @@ constexpr int LEG_CHUNK = 25;
 W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, double* acc) {
     const int m = ldg(&T.dim[x.outer]), off = ldg(&T.offset[x.outer]);
     double csum = 0.0;
-    for (int j = x.lane; j < m; j += W2B_WARP) {
+    for (int j = lane_id(); j < m; j += W2B_WARP) {
         const double e = x.pt[2 * j + 1] != 0.0 ? w_exp(x.pt[2 * j]) : 0.0;
         atomic_add(&acc[A.o_outerst + off + j], 1.0);
         atomic_add(&acc[A.o_signst + off + j], x.tr_sign * x.pt[2 * j + 1] * x.cfgsign);
@@ -1587,16 +1630,17 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
         csum += e;
     }
     csum = wsum(csum);
-    if (x.lane == 0) atomic_add(&acc[A.o_contribsst + x.outer], csum);
+    if (lane_id() == 0) atomic_add(&acc[A.o_contribsst + x.outer], csum);
     if (!R.meas_dm) return;
     if (x.n == 0) {
         const int doff = ldg(&T.dens_off[x.outer]);
-        for (int j = x.lane; j < m; j += W2B_WARP)
+        for (int j = lane_id(); j < m; j += W2B_WARP)
             atomic_add(&acc[A.o_dens + doff + j + j * m], -x.cfgsign * x.pt[2 * j + 1] * x.tr_sign * w_exp(x.pt[2 * j] - x.tr_log));
         return;
     }
     const double bh = T.beta / 2.0;
     const int ih = count_le(x.tau, x.n, bh);                 // operators with tau <= beta/2 belong to the ket
+    if (C.meas_pre) { if (x.kv < ih) x.kv = ih; if (x.bv > ih) x.bv = ih; }     // extended by the trace jobs of Engine::measure
     extend_kets(T, C, x, ih - 1);
     extend_bras(T, C, x, ih);
     const int sst = ih == 0 ? x.outer : (int)x.sst[ih - 1];
@@ -1610,17 +1654,17 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     if (ih == x.n) mat_identity(B, m, blg, m);
     else { mat_copy(B, bra_slot(C, x, ih), d * m); mat_copy(blg, x.bralg + (size_t)x.slot[ih] * C.dmax, m); }
     wsync();
-    for (int e = x.lane; e < d * m; e += W2B_WARP) {
+    for (int e = lane_id(); e < d * m; e += W2B_WARP) {
         const int c = e % d; const double de = ldg(&ev[c]) - e0;
         K[e] *= w_exp(-de * (bh - tauR)); B[e] *= w_exp(-de * (tauL - bh));
     }
-    for (int j = x.lane; j < m; j += W2B_WARP) {
+    for (int j = lane_id(); j < m; j += W2B_WARP) {
         const double kl = klg[j] - (e0 - T.egs) * (bh - tauR), bl = blg[j] - (e0 - T.egs) * (tauL - bh);
         fac[j] = x.tr_sign * (-x.cfgsign) * w_exp(kl + bl - x.tr_log);      // 1 / trval(Trace / TLogTr(kl + bl, -cfgsign))
     }
     wsync();
     const int doff = ldg(&T.dens_off[sst]);
-    for (int e = x.lane; e < d * d; e += W2B_WARP) {
+    for (int e = lane_id(); e < d * d; e += W2B_WARP) {
         const int a = e % d, c = e / d;
         double v = 0.0;
         for (int j = 0; j < m; ++j) v += B[a + (size_t)j * d] * K[c + (size_t)j * d] * fac[j];
@@ -1713,7 +1757,7 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
 W2B_HD void rebuild_chain(const Tables& T, const Run& R, const Chains& C, int chain, double* wscratch, int* iscratch, double* mscratch) {
     Ctx x;
     ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-    const int lane = x.lane;
+    const int lane = lane_id();
     x.wpos = 0; set_window_edges(T, R, x);
     if (lane == 0) for (int f = 0; f <= T.nf; ++f) x.ih[IH_MSLOT + f] = f;
     // flavour arrays

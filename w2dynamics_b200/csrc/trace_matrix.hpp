@@ -97,7 +97,9 @@ W2B_HDN void renorm_slow(double mx, double& sc, double& la, bool& nonzero) {
 #endif
 
 // one packed record per (superstate, operator): everything an operator product needs, fetched with two 16-byte loads
-struct alignas(16) OpDesc { int sst_out, d_in, d_out, ev_off; long long op_off; double e0; };
+// op_off: the block as a compact column-major d_out x d_in matrix; frag_off: the same block zero-padded and laid out in DMMA
+// A-fragment order [k-step][row-tile pair][lane][2] (Tables::opfrag), one coalesced 16-byte load per lane and tile pair
+struct alignas(16) OpDesc { int sst_out, d_in, d_out, ev_off; int op_off, frag_off; double e0; };
 
 // X(d_in x m) <- O(d_out x d_in) * diag(exp(-(E_c - E_0) dt)) * X, in place; every column is renormalised by a power
 // of two near its largest element and lg[j] += -(E_0 - Egs) dt + e ln2.  `pw` is warp scratch for the d_in propagation
@@ -105,14 +107,17 @@ struct alignas(16) OpDesc { int sst_out, d_in, d_out, ev_off; long long op_off; 
 // Latency / code-size structure (the chains are latency- and instruction-fetch-bound, not throughput-bound): the
 // descriptor is one load; the k-loop is rolled (small code) and holds all <= 4 x 4 output tiles in registers, so every A
 // fragment is fetched once, one k-step ahead of its use, and X is overwritten only after the last k-step.
+// slot / slot_lg (optional): the renormalised result and its log scales are also written to this cache slot (compact d_out x m)
 template <int NTMAX, class TablesT>
-W2B_HD int mat_apply_inl(const TablesT& T, int sst_in, int opc, double dt, double* X, int ld, double* lg, double* pw, int m) {
+W2B_HD int mat_apply_inl(const TablesT& T, int sst_in, int opc, double dt, double* X, int ld, double* lg, double* pw, int m,
+                         double* slot = nullptr, double* slot_lg = nullptr, int slot_cols = 0, int* work = nullptr) {
 #if W2B_DEVICE
     const int4* dp = (const int4*)&T.desc[sst_in * T.nops + opc];
     const int4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
     const int sst_out = q0.x, d_in = q0.y, d_out = q0.z;
     const double* ev = T.evals + q0.w;
-    const double* O = T.opdata + (((long long)q1.y << 32) | (unsigned)q1.x);
+    const double* O = T.opdata + q1.x;
+    const double2* F = (const double2*)(T.opfrag + q1.y);
     const double e0 = __hiloint2double(q1.w, q1.z);
 #else
     const OpDesc& D = T.desc[sst_in * T.nops + opc];
@@ -122,12 +127,16 @@ W2B_HD int mat_apply_inl(const TablesT& T, int sst_in, int opc, double dt, doubl
     const double e0 = D.e0;
 #endif
     const double shift = -(e0 - T.egs) * dt;
+    if (slot) slot += slot_cols * d_out;                          // first of this call's columns inside the cache slot
+    if (work) *work += d_in * d_out;
     if (d_in == 1 && d_out == 1) {                               // scalar link of the chain: one multiply per outer state
         const double o = ldg(&O[0]);
         for (int j = lane_id(); j < m; j += W2B_WARP) {
             const double y = o * X[(size_t)j * ld];
-            if (y != 0.0) { double la; const double sc = renorm_pow2(fabs(y), la); X[(size_t)j * ld] = y * sc; lg[j] += shift + la; }
-            else X[(size_t)j * ld] = 0.0;
+            double v = 0.0;
+            if (y != 0.0) { double la; const double sc = renorm_pow2(fabs(y), la); v = y * sc; lg[j] += shift + la; }
+            X[(size_t)j * ld] = v;
+            if (slot) { slot[j] = v; slot_lg[j] = lg[j]; }
         }
         wsync();
         return sst_out;
@@ -136,13 +145,10 @@ W2B_HD int mat_apply_inl(const TablesT& T, int sst_in, int opc, double dt, doubl
     const int lane = lane_id(), g = lane >> 2, t = lane & 3;
     const int ntiles = (m + 7) >> 3, mtiles = (d_out + 7) >> 3, ksteps = (d_in + 3) >> 2;
     // A fragments of the first k-step are requested before the exp() of the propagation factors
+    const int npair = (mtiles + 1) >> 1;
     double an[4];
-    {
-        const bool cok = t < d_in;
-        const double* ocol = O + t * d_out;
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) { const int r = mt * 8 + g; an[mt] = (mt < mtiles && cok && r < d_out) ? ldg(&ocol[r]) : 0.0; }
-    }
+    { const double2 v = __ldg(F + lane); an[0] = v.x; an[1] = v.y; }
+    if (npair > 1) { const double2 v = __ldg(F + 32 + lane); an[2] = v.x; an[3] = v.y; } else { an[2] = 0.0; an[3] = 0.0; }
     for (int c = lane; c < d_in; c += W2B_WARP) pw[c] = c ? w_exp(-(ldg(&ev[c]) - e0) * dt) : 1.0;
     wsync();
     double acc[NTMAX][4][2];                                       // [column tile][row tile][fragment half]
@@ -156,11 +162,9 @@ W2B_HD int mat_apply_inl(const TablesT& T, int sst_in, int opc, double dt, doubl
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) ac[mt] = an[mt];
         if (ks + 1 < ksteps) {                                     // prefetch the next k-step's A fragments
-            const int c = (ks + 1) * 4 + t;
-            const bool cok = c < d_in;
-            const double* ocol = O + c * d_out;
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) { const int r = mt * 8 + g; an[mt] = (mt < mtiles && cok && r < d_out) ? ldg(&ocol[r]) : 0.0; }
+            const double2* f = F + ((ks + 1) * npair) * 32 + lane;
+            { const double2 v = __ldg(f); an[0] = v.x; an[1] = v.y; }
+            if (npair > 1) { const double2 v = __ldg(f + 32); an[2] = v.x; an[3] = v.y; }
         }
         const int k = ks * 4 + t;
         const bool kok = k < d_in;
@@ -195,8 +199,11 @@ W2B_HD int mat_apply_inl(const TablesT& T, int sst_in, int opc, double dt, doubl
                 else { const int e = ef - 1023; sc = __hiloint2double((1023 - e) << 20, 0); la = (double)e * LN2; }
                 if (col < m) {
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) { const int r = mt * 8 + g; if (mt < mtiles && r < d_out) X[col * ld + r] = acc[nt][mt][q] * sc; }
-                    if (g == 0 && nonzero) lg[col] += shift + la;
+                    for (int mt = 0; mt < 4; ++mt) {
+                        const int r = mt * 8 + g;
+                        if (mt < mtiles && r < d_out) { const double v = acc[nt][mt][q] * sc; X[col * ld + r] = v; if (slot) slot[col * d_out + r] = v; }
+                    }
+                    if (g == 0) { double l = lg[col]; if (nonzero) { l += shift + la; lg[col] = l; } if (slot) slot_lg[col] = l; }
                 }
             }
         }
@@ -214,7 +221,8 @@ W2B_HD int mat_apply_inl(const TablesT& T, int sst_in, int opc, double dt, doubl
         }
         double sc = 1.0, la = 0.0;
         if (mx > 0.0) { sc = renorm_pow2(mx, la); lg[j] += shift + la; }
-        for (int r = 0; r < d_out; ++r) xc[r] = y[r] * sc;
+        for (int r = 0; r < d_out; ++r) { xc[r] = y[r] * sc; if (slot) slot[(size_t)j * d_out + r] = xc[r]; }
+        if (slot) slot_lg[j] = lg[j];
     }
 #endif
     return sst_out;

@@ -102,6 +102,7 @@ W2B_HD int cta_tid() { return threadIdx.x; }
 W2B_HD int cta_nthreads() { return blockDim.x; }
 // lane 0 takes the next ticket of a shared-memory counter, all lanes get it
 W2B_HD int wgrab(int* ctr) { int v = 0; if ((threadIdx.x & 31) == 0) v = atomicAdd(ctr, 1); return __shfl_sync(W2B_FULL, v, 0); }
+W2B_HD int wgrab_n(int* ctr, int n) { int v = 0; if ((threadIdx.x & 31) == 0) v = atomicAdd(ctr, n); return __shfl_sync(W2B_FULL, v, 0); }
 // single-thread ticket (caller is one lane)
 W2B_HD int wgrab_one(int* ctr) { return atomicAdd(ctr, 1); }
 W2B_HD double ldg(const double* p) { return __ldg(p); }
@@ -137,6 +138,7 @@ W2B_HD int cta_nwarps() { return 1; }
 W2B_HD int cta_tid() { return 0; }
 W2B_HD int cta_nthreads() { return 1; }
 W2B_HD int wgrab(int* ctr) { return (*ctr)++; }
+W2B_HD int wgrab_n(int* ctr, int n) { int v = *ctr; *ctr += n; return v; }
 W2B_HD int wgrab_one(int* ctr) { return (*ctr)++; }
 W2B_HD double ldg(const double* p) { return *p; }
 W2B_HD int ldg(const int* p) { return *p; }
