@@ -197,14 +197,27 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 8) k_meas_extend(Tables T, C
     for (int t = blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5); t < njobs; t += gridDim.x * TRACE_WARPS)
         trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws, ws + C.ldx * 8, ws + C.ldx * 8 + 8);
 }
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_measure(Tables T, Run R, Chains C, Accum A, int wdoubles, int mdoubles) {
+// measurement: grid = nbins x nsub CTAs; CTA (bin, sub) serves every nsub-th chain of its bin and keeps the Legendre
+// accumulator of the bin in shared memory (one flush per CTA instead of nf * NLegMax same-address atomics per chain)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_measure(Tables T_, Run R_, Chains C_, Accum A_, int wdoubles, int mdoubles, int nsub) {
     extern __shared__ double smem[];
-    int warp = threadIdx.x >> 5;
-    int chain = blockIdx.x * WARPS_PER_CTA + warp;
-    if (chain >= C.nchains) return;
+    __shared__ Tables T; __shared__ Run R; __shared__ Chains C; __shared__ Accum A;
+    if (threadIdx.x == 0) { T = T_; R = R_; C = C_; A = A_; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
     double* ws = smem + (size_t)warp * wdoubles;
     int* is = (int*)(ws + 3 * C.kcap + mdoubles);
-    measure_chain(T, R, C, A, chain, ws, is, ws + 3 * C.kcap);
+    double* gleg_sh = smem + (size_t)WARPS_PER_CTA * wdoubles;
+    const int nleg = T.nf * R.nlegmax;
+    for (int i = threadIdx.x; i < nleg; i += blockDim.x) gleg_sh[i] = 0.0;
+    __syncthreads();
+    const int bin = blockIdx.x % R.nbins, sub = blockIdx.x / R.nbins;
+    const int c0 = (int)(((unsigned)bin + (unsigned)R.nbins - R.chain_base % (unsigned)R.nbins) % (unsigned)R.nbins);   // first chain of this bin
+    for (int chain = c0 + R.nbins * (sub * WARPS_PER_CTA + warp); chain < C.nchains; chain += R.nbins * nsub * WARPS_PER_CTA)
+        measure_chain(T, R, C, A, chain, ws, is, ws + 3 * C.kcap, gleg_sh);
+    __syncthreads();
+    double* acc = A.base + (size_t)bin * A.stride + A.o_gleg;
+    for (int i = threadIdx.x; i < nleg; i += blockDim.x) { const double v = gleg_sh[i]; if (v != 0.0) atomicAdd(&acc[i], v); }
 }
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R, Chains C, int wdoubles, int mdoubles, int only_chain) {
     extern __shared__ double smem[];
@@ -304,6 +317,11 @@ public:
             }
             if (frag.empty()) frag.push_back(0.0);
             T.desc = keep(dev_upload(desc)); T.opfrag = keep(dev_upload(frag));
+        }
+        {
+            std::vector<double> la(std::max(R.nlegmax, 2), 0.0), lb(std::max(R.nlegmax, 2), 0.0);
+            for (int l = 2; l < R.nlegmax; ++l) { const int ll = l - 1; la[l] = (2.0 * ll + 1.0) / (double)(ll + 1); lb[l] = (double)ll / (double)(ll + 1); }
+            T.leg_a = keep(dev_upload(la)); T.leg_b = keep(dev_upload(lb));
         }
         T.op_off = keep(dev_upload(at.op_off)); T.opdata = keep(dev_upload(at.opdata)); T.evals = keep(dev_upload(at.evals));
 
@@ -590,15 +608,20 @@ public:
 
     void measure() {
 #if W2B_DEVICE
-        size_t sm = smem_bytes();
+        size_t sm = smem_bytes() + (size_t)T.nf * R.nlegmax * sizeof(double);
         static size_t configured = 0;
         if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_measure, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+        int dev = 0, nsm = 1;
+        W2B_CUDA_CHECK(cudaGetDevice(&dev));
+        W2B_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        const int per_bin = (C.nchains + R.nbins - 1) / R.nbins;                     // chains of one bin
+        const int nsub = std::max(1, std::min((nsm * 8 + R.nbins - 1) / R.nbins, (per_bin + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
         if (C.dmax > 1 && R.meas_dm) {
             if (!sw_ready) plan_sweep();
             k_meas_extend<<<tr_grid, TRACE_WARPS * 32, tr_smem>>>(T, C, tr_doubles); ++launches;
             C.meas_pre = 1;
         }
-        k_measure<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, A, wdoubles, mat_doubles(C, true)); ++launches;
+        k_measure<<<R.nbins * nsub, WARPS_PER_CTA * 32, sm>>>(T, R, C, A, wdoubles, mat_doubles(C, true), nsub); ++launches;
         C.meas_pre = 0;
         W2B_CUDA_CHECK(cudaGetLastError());
 #else

@@ -53,6 +53,7 @@ struct Tables {
     const int* dens_off;         // [nsst] offset of the block's d x d slab inside the density-matrix accumulator
     const double* empty_w;       // [nsst] normalised empty-trace weights (init_Trace / StepChangeOuter)
     const double* empty_log;     // [nsst] log of the empty trace of each outer superstate
+    const double* leg_a; const double* leg_b;   // Legendre recurrence coefficients (2l-1)/l and (l-1)/l, [NLegMax]
     const OpDesc* desc;          // [nsst*nops] packed operator records of the blocked trace
     const long long* op_off;     // matrix path
     const double* opdata;
@@ -1673,7 +1674,10 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     wsync();
 }
 
-W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain, double* wscratch, int* iscratch, double* mscratch) {
+// gleg_sh (optional): the CTA's shared-memory accumulator of the Legendre coefficients [nf][nlegmax] (all chains of a CTA
+// belong to one bin); it is flushed to the bin's slab once per CTA instead of nf * NLegMax global atomics per chain
+W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain, double* wscratch, int* iscratch, double* mscratch,
+                          double* gleg_sh = nullptr) {
     const int lane = lane_id();
     const int* ih = C.ih + (size_t)chain * IH_STRIDE; const double* dh = C.dh + (size_t)chain * DH_STRIDE;
     const int n = ih[IH_NOPS], outer = ih[IH_OUTER];
@@ -1709,6 +1713,45 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
     }
     // MeasGtauRem 2252-2440: all (annihilator, creator) pairs of every flavour
     const double beta = T.beta;
+    if (gleg_sh) {
+        // GPU mapping: one lane per (flavour, creator, annihilator) pair over ALL flavours at once (a 5-orbital chain has ~7
+        // pairs per flavour: a lane-per-pair loop inside one flavour leaves 3/4 of the warp idle); each lane runs the whole
+        // three-term recurrence (CTQMC.F90:2407-2420, coefficients tabulated) and adds into the CTA's shared accumulator --
+        // warp-reduced first when the whole warp works on one flavour (large orders)
+        int offs[NF_MAX + 1]; offs[0] = 0;
+        for (int f = 0; f < T.nf; ++f) offs[f + 1] = offs[f] + ih[IH_KF + f] * ih[IH_KF + f];
+        const int total = offs[T.nf];
+        for (int base = 0; base < total; base += W2B_WARP) {
+            const int p = base + lane; const bool act = p < total;
+            int f = 0;
+            if (act) while (p >= offs[f + 1]) ++f;
+            double Mv = 0.0, xx = 0.0;
+            if (act) {
+                const int k = ih[IH_KF + f], loc = p - offs[f], ic = loc / k, ia = loc - ic * k;
+                const double* tc = C.tau_c + ((size_t)chain * T.nf + f) * C.kcap; const double* ta = C.tau_a + ((size_t)chain * T.nf + f) * C.kcap;
+                const double* M = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
+                Mv = M[(size_t)ic * C.ld + ia];
+                const double dtau = ta[ia] - tc[ic]; int idt;
+                if (dtau > 0.0) { idt = (int)(dtau / beta * (double)R.ntau) + 1; xx = 2.0 / beta * dtau - 1.0; }
+                else { idt = (int)((beta + dtau) / beta * (double)R.ntau) + 1; xx = 2.0 / beta * (beta + dtau) - 1.0; Mv = -Mv; }
+                Mv *= cfgsign;
+                if (idt > R.ntau) idt = R.ntau;
+                atomic_add(&acc[A.o_gtau + f * R.ntau + idt - 1], Mv);
+            }
+            const bool uniform = wmin(act ? f : 1 << 20) == wmax(act ? f : -1) && base + W2B_WARP <= total;
+            double* g = gleg_sh + f * R.nlegmax;
+            double Plx = 0.0, Plm1 = 0.0, Pl = 0.0;
+#pragma unroll 1
+            for (int l = 0; l < R.nlegmax; ++l) {
+                if (l == 0) Pl = 1.0; else if (l == 1) Pl = xx;
+                else Pl = ldg(&T.leg_a[l]) * xx * Plx - ldg(&T.leg_b[l]) * Plm1;
+                Plm1 = Plx; Plx = Pl;
+                if (uniform) { const double sum = wsum(Mv * Pl); if (lane == 0) atomic_add(&g[l], sum); }
+                else if (act) atomic_add(&g[l], Mv * Pl);
+            }
+        }
+        return;
+    }
     for (int f = 0; f < T.nf; ++f) {
         const int k = ih[IH_KF + f];
         if (k == 0) continue;
@@ -1746,7 +1789,7 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
 #pragma unroll
             for (int q = 0; q < LEG_CHUNK; ++q) {
                 double s = wsum(part[q]);
-                if (lane == 0 && lbase + q < R.nlegmax) atomic_add(&acc[A.o_gleg + f * R.nlegmax + lbase + q], s);
+                if (lane == 0 && lbase + q < R.nlegmax) atomic_add(gleg_sh ? &gleg_sh[f * R.nlegmax + lbase + q] : &acc[A.o_gleg + f * R.nlegmax + lbase + q], s);
             }
         }
     }
