@@ -103,10 +103,15 @@ W2B_HOSTDEV inline void sched_carve(CtaShared& S, char* base, int ncb) {
 }
 #if W2B_DEVICE
 // persistent sweep kernel: every CTA serves batches of ncb chains (batch b -> chains [b*ncb, (b+1)*ncb))
-__global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T, Run R, Chains C, Accum A, long long nsteps, int wdoubles, int ncb, int nbatch,
+__global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T_, Run R_, Chains C_, Accum A_, long long nsteps, int wdoubles, int ncb, int nbatch,
                                                              int log_chain, double* logbuf) {
     extern __shared__ double smem[];
     __shared__ CtaShared S;
+    // one chain context per warp and one copy of the parameter structs per CTA in shared memory (not one per thread in local memory)
+    __shared__ Ctx ctxs[MAX_CTA_THREADS / 32];
+    __shared__ Tables T; __shared__ Run R; __shared__ Chains C; __shared__ Accum A;
+    if (threadIdx.x == 0) { T = T_; R = R_; C = C_; A = A_; }
+    __syncthreads();
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5;
     double* ws = smem + (size_t)warp * wdoubles;
     int* is = (int*)(ws + 3 * C.kcap);
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T, Run R, C
     __syncthreads();
     for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
         const int lo = b * ncb, nloc = min(ncb, C.nchains - lo);
-        cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws, is, ws + 3 * C.kcap, log_chain, logbuf);
+        cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws, is, ws + 3 * C.kcap, log_chain, logbuf, ctxs[warp]);
         __syncthreads();
     }
 }
@@ -207,17 +212,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_measure(Tables T_, Ru
     const int warp = threadIdx.x >> 5;
     double* ws = smem + (size_t)warp * wdoubles;
     int* is = (int*)(ws + 3 * C.kcap + mdoubles);
-    double* gleg_sh = smem + (size_t)WARPS_PER_CTA * wdoubles;
+    double* gleg_sh = smem + (size_t)WARPS_PER_CTA * wdoubles;       // one accumulator per warp
     const int nleg = T.nf * R.nlegmax;
-    for (int i = threadIdx.x; i < nleg; i += blockDim.x) gleg_sh[i] = 0.0;
+    for (int i = threadIdx.x; i < nleg * WARPS_PER_CTA; i += blockDim.x) gleg_sh[i] = 0.0;
     __syncthreads();
     const int bin = blockIdx.x % R.nbins, sub = blockIdx.x / R.nbins;
     const int c0 = (int)(((unsigned)bin + (unsigned)R.nbins - R.chain_base % (unsigned)R.nbins) % (unsigned)R.nbins);   // first chain of this bin
     for (int chain = c0 + R.nbins * (sub * WARPS_PER_CTA + warp); chain < C.nchains; chain += R.nbins * nsub * WARPS_PER_CTA)
-        measure_chain(T, R, C, A, chain, ws, is, ws + 3 * C.kcap, gleg_sh);
+        measure_chain(T, R, C, A, chain, ws, is, ws + 3 * C.kcap, gleg_sh + (size_t)warp * nleg);
     __syncthreads();
     double* acc = A.base + (size_t)bin * A.stride + A.o_gleg;
-    for (int i = threadIdx.x; i < nleg; i += blockDim.x) { const double v = gleg_sh[i]; if (v != 0.0) atomicAdd(&acc[i], v); }
+    for (int i = threadIdx.x; i < nleg; i += blockDim.x) {
+        double v = 0.0;
+        for (int w = 0; w < WARPS_PER_CTA; ++w) v += gleg_sh[(size_t)w * nleg + i];
+        if (v != 0.0) atomicAdd(&acc[i], v);
+    }
 }
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R, Chains C, int wdoubles, int mdoubles, int only_chain) {
     extern __shared__ double smem[];
@@ -434,6 +443,8 @@ public:
         W2B_CUDA_CHECK(cudaGetDevice(&dev));
         W2B_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
         W2B_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cudaFuncAttributes fa; W2B_CUDA_CHECK(cudaFuncGetAttributes(&fa, k_sweep));
+        smem_max -= (int)fa.sharedSizeBytes;                 // static shared memory of the kernel (contexts, parameter copies)
         int W = opt.cta_warps > 0 ? opt.cta_warps : 32;
         const size_t per_warp = (size_t)wdoubles_sweep * sizeof(double);
         while (W > 1 && W * per_warp + sched_bytes(8 * W) > (size_t)smem_max - 1024) --W;
@@ -471,7 +482,7 @@ public:
         CtaShared S{}; sched_carve(S, sb.data(), ct_ncb);
         for (int b = 0; b < ct_nbatch; ++b) {
             const int lo = b * ct_ncb, nloc = std::min(ct_ncb, C.nchains - lo);
-            cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, log_chain, dlog);
+            { Ctx x; cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, log_chain, dlog, x); }
         }
 #endif
         if (log_chain >= 0) { sync(); d2h(log_host, dlog, (size_t)nsteps * LOGW); dev_free(dlog); }
@@ -608,7 +619,7 @@ public:
 
     void measure() {
 #if W2B_DEVICE
-        size_t sm = smem_bytes() + (size_t)T.nf * R.nlegmax * sizeof(double);
+        size_t sm = smem_bytes() + (size_t)WARPS_PER_CTA * T.nf * R.nlegmax * sizeof(double);
         static size_t configured = 0;
         if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_measure, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
         int dev = 0, nsm = 1;

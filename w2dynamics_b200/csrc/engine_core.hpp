@@ -1292,7 +1292,7 @@ W2B_HDN void post_move_cta(const Tables& T, const Run& R, Ctx& x, CtaShared& S, 
 
 
 W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain_lo, int nloc, long long nsteps,
-                      CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf) {
+                      CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf, Ctx& x) {
     const int W = cta_nwarps(), lane = lane_id();
     for (int c = cta_tid(); c < nloc; c += cta_nthreads()) { S.left[c] = (int)nsteps; S.parked[c] = 0; }
     if (cta_tid() == 0) { S.nG = 0; S.cG = 0; }
@@ -1308,7 +1308,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
             if (S.left[c] <= 0 || S.parked[c]) continue;
             if (R.prefetch && cnext < nloc) prefetch_chain(T, C, chain_lo + cnext);
             const int chain = chain_lo + c;
-            Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+            ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
             if (lane == 0) wgrab_one(&S.nA);                              // S.nA counts the chains that were runnable this round
             for (int run = 0; run < R.propose_run && S.left[c] > 0; ++run) {
                 const double r = x.rng.next();
@@ -1342,7 +1342,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                 for (int i = wgrab(curA); i < na2; i = wgrab(curA)) {
                     const int c = S.lA2[i], chain = chain_lo + c;
                     if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
-                    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                     if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
                     add_decide(T, R, C, A, x, S.prop[c]);
                     post_move_cta(T, R, x, S, c);
@@ -1351,7 +1351,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                 for (int i = wgrab(curR); i < nr2; i = wgrab(curR)) {
                     const int c = S.lR2[i], chain = chain_lo + c;
                     if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
-                    Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                     if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
                     rem_decide(T, R, C, A, x, S.prop[c]);
                     post_move_cta(T, R, x, S, c);
@@ -1366,7 +1366,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
             const int ng = S.nG;
             for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {
                 const int c = S.lG[i], chain = chain_lo + c;
-                Ctx x; ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
                 step_rare(T, R, C, x, C.rjob[chain], (int)S.kind[c]);
                 post_move_cta(T, R, x, S, c);
@@ -1674,8 +1674,8 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     wsync();
 }
 
-// gleg_sh (optional): the CTA's shared-memory accumulator of the Legendre coefficients [nf][nlegmax] (all chains of a CTA
-// belong to one bin); it is flushed to the bin's slab once per CTA instead of nf * NLegMax global atomics per chain
+// gleg_sh (optional): the warp's private shared-memory accumulator of the Legendre coefficients [nf][nlegmax] (all chains of a
+// CTA belong to one bin); the CTA flushes its warps' accumulators to the bin's slab once, instead of nf * NLegMax global atomics per chain
 W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain, double* wscratch, int* iscratch, double* mscratch,
                           double* gleg_sh = nullptr) {
     const int lane = lane_id();
@@ -1738,7 +1738,10 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
                 if (idt > R.ntau) idt = R.ntau;
                 atomic_add(&acc[A.o_gtau + f * R.ntau + idt - 1], Mv);
             }
-            const bool uniform = wmin(act ? f : 1 << 20) == wmax(act ? f : -1) && base + W2B_WARP <= total;
+            // lanes of one flavour are contiguous: segmented shuffle reduction, the first lane of each segment adds into the
+            // warp's private accumulator (no atomics: shared-memory fp64 atomics are compare-and-swap loops)
+            const int seg_first = act ? (offs[f] > base ? offs[f] - base : 0) : lane;
+            const int seg_last = act ? (offs[f + 1] - 1 - base < W2B_WARP - 1 ? offs[f + 1] - 1 - base : W2B_WARP - 1) : lane;
             double* g = gleg_sh + f * R.nlegmax;
             double Plx = 0.0, Plm1 = 0.0, Pl = 0.0;
 #pragma unroll 1
@@ -1746,9 +1749,14 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
                 if (l == 0) Pl = 1.0; else if (l == 1) Pl = xx;
                 else Pl = ldg(&T.leg_a[l]) * xx * Plx - ldg(&T.leg_b[l]) * Plm1;
                 Plm1 = Plx; Plx = Pl;
-                if (uniform) { const double sum = wsum(Mv * Pl); if (lane == 0) atomic_add(&g[l], sum); }
-                else if (act) atomic_add(&g[l], Mv * Pl);
+                double v = Mv * Pl;
+#if W2B_DEVICE
+#pragma unroll
+                for (int o = 1; o < W2B_WARP; o <<= 1) { const double t = __shfl_down_sync(W2B_FULL, v, o); if (lane + o <= seg_last) v += t; }
+#endif
+                if (act && lane == seg_first) g[l] += v;
             }
+            wsync();
         }
         return;
     }
