@@ -159,3 +159,18 @@ def test_blocked_trace_measurement(built, cfg):
     assert np.array_equal(eng.histo, r["hist"]) and eng.mean_sign == r["sign"]
     assert abs(np.trace(eng.densitymatrix) - 1.0) < 1e-9
     eng.dest_ctqmc()
+
+
+@pytest.mark.parametrize("cfg,nsteps", [("C2", 4000), ("C4", 3000)])
+def test_chain_independent_of_population(built, cfg, nsteps):
+    """Scheduler invariance: a chain's move sequence (integer state, ratios, RNG draws) does not depend on how many other
+    chains share the device -- work queues, rounds, rare-move hand-over and ticket order all change with the population, the
+    per-chain Markov chain must not.  (1x1 blocks: CTA phase scheduler; blocked traces: propose / trace / decide rounds.)"""
+    p = problems.make_problem(cfg, nftau=2001)
+    logs = []
+    for nchains in (2, 7):
+        eng = make(p, nchains=nchains)
+        logs.append(eng.debug_steps(1, nsteps))
+        assert eng.scalar("error_flags") == 0
+        eng.dest_ctqmc()
+    assert np.array_equal(logs[0], logs[1])

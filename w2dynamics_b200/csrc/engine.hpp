@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(PROPOSE_WARPS * 32, 4) k_propose(Tables T_, Ru
     if (warp == 0) propose_flush(C, parity, outs, PROPOSE_WARPS);
 }
 // decide phase of one round: persistent warps take tickets (rare moves first, then decide queues by outer block size)
-__global__ void __launch_bounds__(DECIDE_WARPS * 32, 6) k_decide(Tables T_, Run R_, Chains C_, Accum A_, long long nsteps, int wdoubles, int mdoubles, int parity,
+__global__ void __launch_bounds__(DECIDE_WARPS * 32, 8) k_decide(Tables T_, Run R_, Chains C_, Accum A_, long long nsteps, int wdoubles, int mdoubles, int parity,
                                                               int log_chain, double* logbuf) {
     extern __shared__ double smem[];
     __shared__ Tables T; __shared__ Run R; __shared__ Chains C; __shared__ Accum A;
@@ -368,10 +368,9 @@ public:
         }
         C.left = keep(dev_alloc<int>(nc)); C.parked = keep(dev_alloc<unsigned char>(nc)); C.kind = keep(dev_alloc<unsigned char>(nc));
         C.prop = keep(dev_alloc<Prop>(nc)); C.rjob = keep(dev_alloc<RareJob>(nc));
-        C.q_rare = keep(dev_alloc<int>((size_t)2 * nc)); C.q_rfin = keep(dev_alloc<int>((size_t)2 * nc)); C.q_dec0 = keep(dev_alloc<int>(nc)); C.q_dec1 = keep(dev_alloc<int>(nc)); C.q_dec2 = keep(dev_alloc<int>(nc));
+        C.q_rfin = keep(dev_alloc<int>((size_t)2 * nc)); C.q_dec0 = keep(dev_alloc<int>(nc)); C.q_dec1 = keep(dev_alloc<int>(nc)); C.q_dec2 = keep(dev_alloc<int>(nc));
         C.sched = keep(dev_alloc<int>(2 * SC_STRIDE));
         C.ptc = nullptr; C.q_tr0 = C.q_tr1 = C.q_tr2 = nullptr;
-        C.trace_flops = keep(dev_alloc<unsigned long long>(1));
         if (at.dmax > 1) {
             C.ptc = keep(dev_alloc<double>((size_t)nc * 2 * at.dmax));
             C.q_tr0 = keep(dev_alloc<int>((size_t)nc * 8)); C.q_tr1 = keep(dev_alloc<int>((size_t)nc * 8)); C.q_tr2 = keep(dev_alloc<int>((size_t)nc * 8));

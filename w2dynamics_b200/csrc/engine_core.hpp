@@ -86,7 +86,7 @@ struct RareJob {
 };
 
 // round scheduler counters (device memory, two sets used in alternation by consecutive rounds)
-enum { SC_NRARE = 0, SC_NQ0, SC_NQ1, SC_NQ2, SC_TICKET, SC_NRUN, SC_MAXLEFT, SC_TTICKET, SC_NT0, SC_NT1, SC_NT2, SC_NRFIN, SC_STRIDE = 16 };
+enum { SC_NQ0 = 0, SC_NQ1, SC_NQ2, SC_TICKET, SC_NRUN, SC_MAXLEFT, SC_TTICKET, SC_NT0, SC_NT1, SC_NT2, SC_NRFIN, SC_STRIDE = 16 };
 // per-chain scheduling state (Chains::parked): global moves / tau shifts leave the round pipeline and come back through these states
 enum { ST_RUN = 0, ST_RARE_NEW = 1, ST_RARE_TRACE = 3, ST_RARE_QUEUED = 4, ST_RARE_DONE = 5 };
 constexpr int Q_MEAS = 1 << 28;      // trace-queue entry of a measurement: extend both cache frontiers to tau = beta/2, no trace
@@ -112,9 +112,8 @@ struct Chains {
     int mstride, dmax;
     // round scheduler: moves left in the current sweep, rare-move flags, proposals, work queues, counters
     int* left; unsigned char* parked; unsigned char* kind; Prop* prop; RareJob* rjob;
-    int* q_rare; int* q_rfin; int* q_dec0; int* q_dec1; int* q_dec2; int* sched;      // q_rare, q_rfin and the trace queues: one buffer per counter set
+    int* q_rfin; int* q_dec0; int* q_dec1; int* q_dec2; int* sched;      // q_rare, q_rfin and the trace queues: one buffer per counter set
     double* ptc;                                               // trace kernel results: per-outer-state parts (log, sign) of the proposed configuration [chain][2*dmax]
-    unsigned long long* trace_flops;                           // algorithmic FP64 flops of the trace kernel (2 d_out d_in columns per operator product)
     int* q_tr0; int* q_tr1; int* q_tr2;                        // trace jobs (chain | column tile | removal flag) by number of steps: long, medium, short
     int meas_pre;                                              // measurement kernel: the cache frontiers already reach beta/2 (extended by trace jobs)
     int ldx, xdoubles;                                         // work matrix: leading dimension (4 mod 16) and size ldx * dmax
@@ -137,7 +136,6 @@ struct Ctx {
     double* mX; double* mY; double* mlg; double* mpt; double* mpw;   // per-warp work space of the blocked trace (mY: measurement kernel only)
     int ldx;
     int kv, bv, nfree;
-    const double* pre;     // trace of the proposed configuration computed by the trace kernel (or nullptr)
     int n, outer, wpos, npairs, perm, palt, err;
     double det_log, det_sign, tr_log, tr_sign, cfgsign, wmin, wmax;
     Philox rng;
@@ -1216,7 +1214,7 @@ W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain,
     x.det_log = x.dh[DH_DETLOG]; x.det_sign = x.dh[DH_DETSIGN]; x.tr_log = x.dh[DH_TRLOG]; x.tr_sign = x.dh[DH_TRSIGN]; x.cfgsign = x.dh[DH_CFGSIGN];
     x.rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, C.rng_ctr[chain]);
     set_window_edges(T, R, x);
-    x.log = nullptr; x.pre = nullptr;
+    x.log = nullptr;
 }
 W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
@@ -1579,7 +1577,7 @@ W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const A
     if (R.prefetch) { prefetch_chain(T, C, chain, 128); if (!rare) prefetch_minv(T, C, chain, C.prop[chain].f); }
     ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
     if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - C.left[chain]) * LOGW;
-    if (!rare && T.dmax > 1) { x.pre = C.ptc + (size_t)chain * 2 * C.dmax; x.mpt = C.ptc + (size_t)chain * 2 * C.dmax; }
+    if (T.dmax > 1) x.mpt = C.ptc + (size_t)chain * 2 * C.dmax;      // parts of the proposed configuration, left by the trace kernel
     if (rare) {                                                   // second half of a global move / tau shift: the trace kernel has left the parts in C.ptc
         RareJob& J = C.rjob[chain];
         double tn_log, tn_sign;
