@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_sweep_begin(Chains C, long long nsteps)
 // propose phase of one round: one warp per chain; the CTA's results reach the round's queues with one atomic per queue
 // (the parameter structs are copied to shared memory once per CTA: passing kernel parameters by reference to out-of-line
 // functions would otherwise spill a private copy per thread to local memory)
-__global__ void __launch_bounds__(PROPOSE_WARPS * 32, 4) k_propose(Tables T_, Run R_, Chains C_, long long nsteps, int parity, int log_chain, double* logbuf) {
+__global__ void __launch_bounds__(PROPOSE_WARPS * 32, 5) k_propose(Tables T_, Run R_, Chains C_, long long nsteps, int parity, int log_chain, double* logbuf) {
     __shared__ ProposeOut outs[PROPOSE_WARPS];
     __shared__ Ctx ctxs[PROPOSE_WARPS];
     __shared__ Tables T; __shared__ Run R; __shared__ Chains C;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T_, Run R_
         phase_rare(T, R, C, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
 }
 // trace phase of one round (blocked traces): operator products of every surviving proposal on the FP64 tensor pipe
-__global__ void __launch_bounds__(TRACE_WARPS * 32, 8) k_trace(Tables T, Chains C, int tdoubles, int parity) {
+__global__ void __launch_bounds__(TRACE_WARPS * 32, TRACE_NT == 1 ? 8 : 6) k_trace(Tables T, Chains C, int tdoubles, int parity) {
     extern __shared__ double smem[];
     double* ws = smem + (size_t)(threadIdx.x >> 5) * tdoubles;
     int* sc = C.sched + parity * SC_STRIDE;
@@ -195,12 +195,12 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 8) k_trace(Tables T, Chains 
         for (int t = t0; t < t0 + TICKET_BATCH && t < total; ++t) phase_trace(T, C, t, parity, ws);
 }
 // measurement pre-pass (blocked traces): extend every chain's cache frontiers to tau = beta/2, one job per 8 outer states
-__global__ void __launch_bounds__(TRACE_WARPS * 32, 8) k_meas_extend(Tables T, Chains C, int tdoubles) {
+__global__ void __launch_bounds__(TRACE_WARPS * 32, TRACE_NT == 1 ? 8 : 6) k_meas_extend(Tables T, Chains C, int tdoubles) {
     extern __shared__ double smem[];
     double* ws = smem + (size_t)(threadIdx.x >> 5) * tdoubles;
     const int njobs = C.nchains * 4;
     for (int t = blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5); t < njobs; t += gridDim.x * TRACE_WARPS)
-        trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws, ws + C.ldx * 8, ws + C.ldx * 8 + 8);
+        trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws, ws + C.ldx * TRACE_COLS, ws + C.ldx * TRACE_COLS + TRACE_COLS);
 }
 // measurement: grid = nbins x nsub CTAs; CTA (bin, sub) serves every nsub-th chain of its bin and keeps the Legendre
 // accumulator of the bin in shared memory (one flush per CTA instead of nf * NLegMax same-address atomics per chain)
@@ -524,7 +524,7 @@ public:
         W2B_CUDA_CHECK(cudaFuncSetAttribute(k_rare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem));
         rp_grid = std::max(1, std::min(nsm, C.nchains / (8 * DECIDE_WARPS) + 1));
         if (C.dmax > 1) {
-            tr_doubles = C.ldx * 8 + 8 + MAT_DMAX;
+            tr_doubles = C.ldx * TRACE_COLS + TRACE_COLS + MAT_DMAX;
             tr_smem = (size_t)TRACE_WARPS * tr_doubles * sizeof(double);
             W2B_CUDA_CHECK(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
             W2B_CUDA_CHECK(cudaFuncSetAttribute(k_meas_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
@@ -637,7 +637,7 @@ public:
 #else
         std::vector<double> ws(wdoubles + 8);
         if (C.dmax > 1 && R.meas_dm) {
-            for (int t = 0; t < C.nchains * 4; ++t) trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws.data(), ws.data() + C.ldx * 8, ws.data() + C.ldx * 8 + 8);
+            for (int t = 0; t < C.nchains * 4; ++t) trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws.data(), ws.data() + C.ldx * TRACE_COLS, ws.data() + C.ldx * TRACE_COLS + TRACE_COLS);
             C.meas_pre = 1;
         }
         for (int c = 0; c < C.nchains; ++c) measure_chain(T, R, C, A, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);

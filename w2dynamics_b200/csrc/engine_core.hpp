@@ -92,6 +92,11 @@ enum { ST_RUN = 0, ST_RARE_NEW = 1, ST_RARE_TRACE = 3, ST_RARE_QUEUED = 4, ST_RA
 constexpr int Q_MEAS = 1 << 28;      // trace-queue entry of a measurement: extend both cache frontiers to tau = beta/2, no trace
 constexpr int Q_RARE = 1 << 29;      // trace-queue entry of a global move / tau shift (whole sequence, no caches)
 constexpr int Q_REM = 1 << 30;       // decide-queue entry = chain id | Q_REM for a removal
+#ifndef W2B_TRACE_NT
+#define W2B_TRACE_NT 1
+#endif
+constexpr int TRACE_NT = W2B_TRACE_NT;   // DMMA column tiles per trace job
+constexpr int TRACE_COLS = 8 * TRACE_NT; // outer states (columns) per trace job
 constexpr int Q_NTSHIFT = 26;         // trace-queue entry: + column tile << Q_NTSHIFT
 constexpr int Q_IDMASK = (1 << 26) - 1;
 
@@ -428,7 +433,7 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
     int i1 = P.i1, i2 = P.i2;
     bool store_seg = false;
     if (meas) {                                                   // kets of the operators with tau <= beta/2, bras of the others (update_b2_states_eb)
-        if (n == 0 || nt * 8 >= ldg(&T.dim[outer])) return;
+        if (n == 0 || nt * TRACE_COLS >= ldg(&T.dim[outer])) return;
         i1 = i2 = count_le(tau, n, T.beta / 2.0);
     }
     if (rare) {                                                   // whole (relabelled / shifted) sequence from the identity, no caches used
@@ -442,7 +447,7 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
     const double tA = P.t1, tB = P.t2;
     const int codeA = P.f * 2 + P.type1, codeB = P.f * 2 + (1 - P.type1);
     const int m = ldg(&T.dim[outer]), ld = C.ldx;
-    const int j0 = nt * 8, mw = m - j0 < 8 ? m - j0 : 8;        // this job's columns
+    const int j0 = nt * TRACE_COLS, mw = m - j0 < TRACE_COLS ? m - j0 : TRACE_COLS;        // this job's columns
     const int nb = bv > e ? bv - e : 0, nk = kv <= s - 1 ? s - kv : 0, ns = nA + (hi - lo) + nA;
     const int total = nb + nk + ns;
     int cur = -1;                        // block of the work matrix (rows)
@@ -494,7 +499,7 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
             dst = ((sl >> 16) == 1 ? ket : bra) + (size_t)(sl & 0xffff) * C.mstride;
             dlg = ((sl >> 16) == 1 ? ketlg : bralg) + (size_t)(sl & 0xffff) * C.dmax + j0;
         }
-        cur = mat_apply_inl<1>(T, in, opc, dt, X, ld, lg, pw, mw, dst, dlg, j0, &work);
+        cur = mat_apply_inl<TRACE_NT>(T, in, opc, dt, X, ld, lg, pw, mw, dst, dlg, j0, &work);
     }
     if (meas) return;
     if (ns == 0 && nk == 0) {                                   // nothing applied after the ket frontier: work matrix = KET_{s-1}
@@ -1453,7 +1458,7 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
             if (state == ST_RARE_DONE) C.parked[chain] = ST_RUN;
             if (state == ST_RARE_TRACE) {                         // first half done: this round's trace kernel runs its jobs, the decide kernel the second half
                 const int new_outer = *(const volatile int*)&C.rjob[chain].new_outer;
-                out->tq = 0; out->tentry = chain | Q_RARE; out->ntl = (ldg(&T.dim[new_outer]) + 7) >> 3; out->rfin = 1;
+                out->tq = 0; out->tentry = chain | Q_RARE; out->ntl = (ldg(&T.dim[new_outer]) + TRACE_COLS - 1) / TRACE_COLS; out->rfin = 1;
                 C.parked[chain] = ST_RARE_QUEUED;
             }
         }
@@ -1481,7 +1486,7 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
                     const Prop& P = C.prop[chain];
                     const int rem = (entry & Q_REM) ? 1 : 0, s = P.i1, e = P.i2 + rem;
                     const int steps = (x.bv > e ? x.bv - e : 0) + (x.kv <= s - 1 ? s - x.kv : 0) + (P.i2 - P.i1 - rem) + (rem ? 0 : 2);
-                    out->tq = steps >= 24 ? 0 : (steps >= 8 ? 1 : 2); out->tentry = entry; out->ntl = (m + 7) >> 3;
+                    out->tq = steps >= 24 ? 0 : (steps >= 8 ? 1 : 2); out->tentry = entry; out->ntl = (m + TRACE_COLS - 1) / TRACE_COLS;
                 }
             }
             break;
@@ -1535,7 +1540,7 @@ W2B_HD void phase_trace(const Tables& T, const Chains& C, int ticket, int parity
     const size_t qo = (size_t)parity * 4 * C.nchains;
     const int n0 = sc[SC_NT0], n1 = sc[SC_NT1];
     const int entry = ticket < n0 ? C.q_tr0[qo + ticket] : (ticket < n0 + n1 ? C.q_tr1[qo + ticket - n0] : C.q_tr2[qo + ticket - n0 - n1]);
-    trace_job(T, C, entry, mscratch, mscratch + C.ldx * 8, mscratch + C.ldx * 8 + 8);
+    trace_job(T, C, entry, mscratch, mscratch + C.ldx * TRACE_COLS, mscratch + C.ldx * TRACE_COLS + TRACE_COLS);
 }
 
 // Global moves / tau shifts (1 % of the moves, 10-1000x the cost of a pair move) run on their own stream beside the round
