@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, TRACE_NT == 1 ? 8 : 6) k_mea
 }
 // measurement: grid = nbins x nsub CTAs; CTA (bin, sub) serves every nsub-th chain of its bin and keeps the Legendre
 // accumulator of the bin in shared memory (one flush per CTA instead of nf * NLegMax same-address atomics per chain)
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_measure(Tables T_, Run R_, Chains C_, Accum A_, int wdoubles, int mdoubles, int nsub) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) k_measure(Tables T_, Run R_, Chains C_, Accum A_, int wdoubles, int mdoubles, int nsub) {
     extern __shared__ double smem[];
     __shared__ Tables T; __shared__ Run R; __shared__ Chains C; __shared__ Accum A;
     if (threadIdx.x == 0) { T = T_; R = R_; C = C_; A = A_; }

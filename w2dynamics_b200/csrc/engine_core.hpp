@@ -900,7 +900,11 @@ W2B_HDN void trace_full_scalar(const Tables& T, const double* tau, const unsigne
 // In-place Gauss-Jordan inversion with partial pivoting of the k x k row-major matrix a (leading dimension ld);
 // returns log|det| and sign through the references; singular -> sign 0.  Uses wI[0..k) as pivot bookkeeping.
 // (stands in for DGETRF/DGETRI of get_MatLogDetFull, MatrixUpdate.F90:41-99)
-W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, bool want_inverse, double& lg, double& sg) {
+// colv / rowv: two warp-scratch vectors of k doubles.  Per pivot the elimination factors (column c) and the scaled pivot row
+// are staged there once; the k row updates that follow are then independent of each other (a lane only touches its own
+// columns), so their loads and stores pipeline instead of paying one global-memory round trip and two warp barriers per row
+// (a 100 x 100 inverse took 5-10 ms on one warp that way and dominated the beta = 200 workload).
+W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, double* colv, double* rowv, bool want_inverse, double& lg, double& sg) {
     lg = 0.0; sg = 1.0;
     const int lane = lane_id();
     for (int c = 0; c < k; ++c) {
@@ -921,20 +925,23 @@ W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, bool want_inverse
         wsync();
         if (want_inverse) {
             // Gauss-Jordan step: row c scaled, eliminated from every other row; column c becomes the inverse column
-            for (int j = lane; j < k; j += W2B_WARP) a[(size_t)c * ld + j] = (j == c) ? ipiv : a[(size_t)c * ld + j] * ipiv;
+            for (int j = lane; j < k; j += W2B_WARP) { const double v = (j == c) ? ipiv : a[(size_t)c * ld + j] * ipiv; a[(size_t)c * ld + j] = v; rowv[j] = v; }
+            for (int r = lane; r < k; r += W2B_WARP) colv[r] = a[(size_t)r * ld + c];
             wsync();
             for (int r = 0; r < k; ++r) {
                 if (r == c) continue;
-                double fct = a[(size_t)r * ld + c];
-                wsync();
+                const double fct = colv[r];
                 for (int j = lane; j < k; j += W2B_WARP)
-                    a[(size_t)r * ld + j] = (j == c) ? -fct * ipiv : a[(size_t)r * ld + j] - fct * a[(size_t)c * ld + j];
-                wsync();
+                    a[(size_t)r * ld + j] = (j == c) ? -fct * ipiv : a[(size_t)r * ld + j] - fct * rowv[j];
             }
+            wsync();
         } else {
+            for (int j = c + 1 + lane; j < k; j += W2B_WARP) rowv[j] = a[(size_t)c * ld + j];
+            for (int r = c + 1 + lane; r < k; r += W2B_WARP) colv[r] = a[(size_t)r * ld + c] * ipiv;
+            wsync();
             for (int r = c + 1; r < k; ++r) {
-                double fct = a[(size_t)r * ld + c] * ipiv;
-                for (int j = c + 1 + lane; j < k; j += W2B_WARP) a[(size_t)r * ld + j] -= fct * a[(size_t)c * ld + j];
+                const double fct = colv[r];
+                for (int j = c + 1 + lane; j < k; j += W2B_WARP) a[(size_t)r * ld + j] -= fct * rowv[j];
             }
             wsync();
         }
@@ -965,7 +972,7 @@ W2B_HDN void rebuild_inverses(const Tables& T, const Chains& C, Ctx& x, const do
             for (int ic = lane_id(); ic < k; ic += W2B_WARP) a[(size_t)ia * C.ld + ic] = hybrF(T, ta[ia] - tc[ic], f);
         wsync();
         double l, s;
-        invert_inplace(a, k, C.ld, x.wI, want_inverse, l, s);
+        invert_inplace(a, k, C.ld, x.wI, x.wQ, x.wR, want_inverse, l, s);
         lg += l; sg *= s;
     }
 }
@@ -1621,6 +1628,7 @@ W2B_HD void init_chain(const Tables& T, const Run& R, const Chains& C, int chain
 
 // ------------------------------------------------------------------ measurement (CTQMC.F90:8541-8581)
 constexpr int LEG_CHUNK = 25;
+constexpr int LEG_CHUNK_BIG = 50;
 // blocked-trace part of one measurement: per-state histograms (MeasOuterHistograms CTQMC.F90:3285-3339) and the density
 // matrix at beta/2 (update_b2_states_eb Trace.F90:6213-6469 + MeasDensityMatrix_beta_half CTQMC.F90:3088-3151)
 W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, double* acc) {
@@ -1721,8 +1729,55 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
         // pairs per flavour: a lane-per-pair loop inside one flavour leaves 3/4 of the warp idle); each lane runs the whole
         // three-term recurrence (CTQMC.F90:2407-2420, coefficients tabulated) and adds into the CTA's shared accumulator --
         // warp-reduced first when the whole warp works on one flavour (large orders)
+        // flavours with more than one warp-load of pairs: all lanes work on the same flavour anyway -- keep 50 partial sums per
+        // lane in registers over all pairs and reduce once per l (two passes over the pairs, the second restarts the recurrence)
+        for (int f = 0; f < T.nf; ++f) {
+            const int k = ih[IH_KF + f];
+            if (k * k <= W2B_WARP) continue;
+            const double* tc = C.tau_c + ((size_t)chain * T.nf + f) * C.kcap; const double* ta = C.tau_a + ((size_t)chain * T.nf + f) * C.kcap;
+            const double* M = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
+            double* g = gleg_sh + f * R.nlegmax;
+            for (int lbase = 0; lbase < R.nlegmax; lbase += LEG_CHUNK_BIG) {
+                double part[LEG_CHUNK_BIG];
+#pragma unroll
+                for (int q = 0; q < LEG_CHUNK_BIG; ++q) part[q] = 0.0;
+                for (int p = lane; p < k * k; p += W2B_WARP) {
+                    const int ic = p / k, ia = p - ic * k;
+                    double Mv = M[(size_t)ic * C.ld + ia];
+                    const double dtau = ta[ia] - tc[ic]; double xx; int idt;
+                    if (dtau > 0.0) { idt = (int)(dtau / beta * (double)R.ntau) + 1; xx = 2.0 / beta * dtau - 1.0; }
+                    else { idt = (int)((beta + dtau) / beta * (double)R.ntau) + 1; xx = 2.0 / beta * (beta + dtau) - 1.0; Mv = -Mv; }
+                    Mv *= cfgsign;
+                    if (lbase == 0) { if (idt > R.ntau) idt = R.ntau; atomic_add(&acc[A.o_gtau + f * R.ntau + idt - 1], Mv); }
+                    double Plx = 0.0, Plm1 = 0.0, Pl = 0.0;
+#pragma unroll 1
+                    for (int l = 0; l < lbase; ++l) {
+                        if (l == 0) Pl = 1.0; else if (l == 1) Pl = xx;
+                        else Pl = ldg(&T.leg_a[l]) * xx * Plx - ldg(&T.leg_b[l]) * Plm1;
+                        Plm1 = Plx; Plx = Pl;
+                    }
+#pragma unroll
+                    for (int q = 0; q < LEG_CHUNK_BIG; ++q) {
+                        const int l = lbase + q;
+                        if (l < R.nlegmax) {
+                            if (l == 0) Pl = 1.0; else if (l == 1) Pl = xx;
+                            else Pl = ldg(&T.leg_a[l]) * xx * Plx - ldg(&T.leg_b[l]) * Plm1;
+                            part[q] += Mv * Pl;
+                            Plm1 = Plx; Plx = Pl;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < LEG_CHUNK_BIG; ++q) {
+                    const double sum = wsum(part[q]);
+                    if (lane == 0 && lbase + q < R.nlegmax) g[lbase + q] += sum;
+                }
+            }
+            wsync();
+        }
+        // small flavours: one lane per pair across all of them
         int offs[NF_MAX + 1]; offs[0] = 0;
-        for (int f = 0; f < T.nf; ++f) offs[f + 1] = offs[f] + ih[IH_KF + f] * ih[IH_KF + f];
+        for (int f = 0; f < T.nf; ++f) { const int k2 = ih[IH_KF + f] * ih[IH_KF + f]; offs[f + 1] = offs[f] + (k2 <= W2B_WARP ? k2 : 0); }
         const int total = offs[T.nf];
         for (int base = 0; base < total; base += W2B_WARP) {
             const int p = base + lane; const bool act = p < total;
