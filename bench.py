@@ -216,6 +216,8 @@ def run_engine(args):
     eng.set_option("nchains", nchains); eng.set_option("nbins", 32); eng.set_option("device", local)
     if os.environ.get("W2B_CTA_WARPS"):
         eng.set_option("cta_warps", int(os.environ["W2B_CTA_WARPS"]))
+    if os.environ.get("W2B_SCHEDULER"):
+        eng.set_option("scheduler", int(os.environ["W2B_SCHEDULER"]))
     if os.environ.get("W2B_BATCH_CHAINS"):
         eng.set_option("batch_chains", int(os.environ["W2B_BATCH_CHAINS"]))
     if world > 1:
@@ -242,7 +244,7 @@ def run_engine(args):
     allreduce_accum()
     eng._ck(L.w2b_read_accum(None, C.c_size_t(0), C.byref(C.c_size_t())))
     torch.cuda.synchronize()
-    blocked = eng.scalar("blocked") > 0
+    blocked = eng.scalar("blocked") > 0 or os.environ.get("W2B_SCHEDULER") == "2"
     bytes0, launches0 = eng.scalar("cnt_alg_bytes"), eng.scalar("gpu_launches")
     flops0 = eng.scalar("trace_flops") if blocked else 0.0
     rounds0 = eng.scalar("rounds")

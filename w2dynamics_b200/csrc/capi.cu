@@ -157,6 +157,7 @@ int w2b_set_option(const char* key, double value) {
     else if (k == "chain_base") S.opt.chain_base = (unsigned)value;
     else if (k == "cta_warps") S.opt.cta_warps = (int)value;
     else if (k == "batch_chains") S.opt.batch_chains = (int)value;
+    else if (k == "scheduler") S.opt.scheduler = (int)value;
     else if (k == "device") S.device = (int)value;
     else if (k == "nmeas_override") S.nmeas_override = (long long)value;
     else if (k == "debug_same_key") S.same_key = (int)value;

@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R,
 struct EngineOptions {
     int nchains = 1024, nbins = 16, kcap = 0, ops_cap = 0;
     int cta_warps = 0, batch_chains = 0;      // sweep kernel geometry (0 = automatic)
+    int scheduler = 0;                        // 1x1 blocks: 0 / 1 = persistent CTA-scheduler kernel, 2 = round kernels (blocked traces always use rounds)
     unsigned seed = 0, chain_base = 0;
 };
 
@@ -542,7 +543,7 @@ public:
     // advance every chain by nsteps moves; optionally record the replay log of one chain
     void sweep(long long nsteps, int log_chain = -1, double* log_host = nullptr) {
         if (nsteps <= 0) return;
-        if (C.dmax == 1) { sweep_cta(nsteps, log_chain, log_host); return; }
+        if (C.dmax == 1 && opt.scheduler != 2) { sweep_cta(nsteps, log_chain, log_host); return; }
         if (!sw_ready) plan_sweep();
         double* dlog = nullptr;
         if (log_chain >= 0) dlog = dev_alloc<double>((size_t)nsteps * LOGW);

@@ -405,7 +405,7 @@ W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsign
 // operator product is the only code in the loop and the per-step global-memory latency is paid once per 32 steps.
 // Writes the per-outer-state parts (log, sign) of the proposed configuration to C.ptc; the decide kernel sums them and
 // moves the frontiers (kv = max(kv, s), bv = min(bv, e)).
-W2B_HD void load_tile(const Tables& T, const Chains& C, double* X, double* lg, const double* slot_mat, const double* slot_lg, int sst, int j0, int mw) {
+W2B_HDN void load_tile(const Tables& T, const Chains& C, double* X, double* lg, const double* slot_mat, const double* slot_lg, int sst, int j0, int mw) {
     if (slot_mat) {
         const int d = ldg(&T.dim[sst]);
         mat_move(X, C.ldx, slot_mat + j0 * d, d, d, mw);
@@ -509,11 +509,12 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
     }
     const double tlast = ns > 0 ? (nA ? tB : tau[hi - 1]) : (s == 0 ? 0.0 : tau[s - 1]);
     double* pt = C.ptc + (size_t)chain * 2 * C.dmax + 2 * j0;
-    if (e == n) mat_close_parts(T, cur, T.beta - tlast, X, ld, lg, (const double*)nullptr, (const double*)nullptr, pw, mw, j0, pt);
-    else {
+    const double* B = nullptr; const double* blg = nullptr; double tend = T.beta;         // e == n: unit bras at tau = beta
+    if (e != n) {
         const int d = ldg(&T.dim[cur]);
-        mat_close_parts(T, cur, tau[e] - tlast, X, ld, lg, bra + (size_t)slot[e] * C.mstride + j0 * d, bralg + (size_t)slot[e] * C.dmax + j0, pw, mw, j0, pt);
+        B = bra + (size_t)slot[e] * C.mstride + j0 * d; blg = bralg + (size_t)slot[e] * C.dmax + j0; tend = tau[e];
     }
+    mat_close_parts(T, cur, tend - tlast, X, ld, lg, B, blg, pw, mw, j0, pt);
     if (lane == 0 && work) atomic_add(&C.counters[(size_t)chain * C_NCNT + C_TRFLOPS], 2ull * (unsigned long long)work * (unsigned long long)mw);   // per-chain counter: no hot address
 }
 
