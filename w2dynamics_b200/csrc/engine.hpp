@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T_, Run R_,
 }
 #endif
 // ---- round kernels (blocked traces)
-constexpr int PROPOSE_WARPS = 8;      // warps per CTA of the propose kernel (its queue pushes are aggregated per CTA)
+constexpr int PROPOSE_WARPS = 2;      // warps per CTA of the propose kernel (its queue pushes are aggregated per CTA)
 constexpr int TRACE_WARPS = 4;        // warps per CTA of the trace kernel (one work matrix per warp in shared memory)
 constexpr int TICKET_BATCH = 1;       // tickets a warp takes per atomic on the round's ticket counter
 constexpr int DECIDE_WARPS = 4;       // warps per CTA of the decide kernel (one work matrix per warp in shared memory)
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_sweep_begin(Chains C, long long nsteps)
 // propose phase of one round: one warp per chain; the CTA's results reach the round's queues with one atomic per queue
 // (the parameter structs are copied to shared memory once per CTA: passing kernel parameters by reference to out-of-line
 // functions would otherwise spill a private copy per thread to local memory)
-__global__ void __launch_bounds__(PROPOSE_WARPS * 32, 5) k_propose(Tables T_, Run R_, Chains C_, long long nsteps, int parity, int log_chain, double* logbuf) {
+__global__ void __launch_bounds__(PROPOSE_WARPS * 32, 20) k_propose(Tables T_, Run R_, Chains C_, long long nsteps, int parity, int log_chain, double* logbuf) {
     __shared__ ProposeOut outs[PROPOSE_WARPS];
     __shared__ Ctx ctxs[PROPOSE_WARPS];
     __shared__ Tables T; __shared__ Run R; __shared__ Chains C;
