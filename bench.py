@@ -36,8 +36,10 @@ WORKLOADS = {
     "C4": "C4: 5-orbital d-shell full Slater-Coulomb, beta=20, 1024-state Fock space, 132 blocks d<=28",
     "C5": "C5: 1-band Hubbard, beta=200 (expansion order in the hundreds)",
 }
-DEFAULT_CHAINS = {"C1": 65536, "C2": 16384, "C3": 32768, "C4": 32768, "C5": 4096}      # per GPU
-THERMALISE = {"C1": 2000, "C2": 6000, "C3": 6000, "C4": 6000, "C5": 40000}
+DEFAULT_CHAINS = {"C1": 65536, "C2": 65536, "C3": 32768, "C4": 32768, "C5": 32768}     # per GPU
+# (C5: the CTA scheduler serves global moves a warp-load at a time -- with 28 chains per CTA (4096 chains) 91 % of the warp
+#  samples waited at the CTA barrier for single global moves; 222 chains per CTA keep all warps busy: 2.2 -> 7.9 M moves/s)
+THERMALISE = {"C1": 2000, "C2": 6000, "C3": 6000, "C4": 6000, "C5": 8000}
 METRIC = "QMC moves/sec (box)"
 UNIT = "moves/s"
 

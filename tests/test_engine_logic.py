@@ -174,3 +174,20 @@ def test_chain_independent_of_population(built, cfg, nsteps):
         assert eng.scalar("error_flags") == 0
         eng.dest_ctqmc()
     assert np.array_equal(logs[0], logs[1])
+
+
+@pytest.mark.parametrize("cfg,nsteps,chain", [("C2", 12000, 3), ("C5", 3000, 1)])
+def test_round_scheduler_on_scalar_blocks(built, cfg, nsteps, chain):
+    """The round kernels (propose / decide + rare stream) are the default for blocked traces only, but they are a complete
+    scheduler: with 1x1 blocks the rare stream runs whole global moves / tau shifts.  Same replay parity against the oracle."""
+    p = problems.make_problem(cfg, nftau=2001)
+    eng = _hostemu.make()
+    eng.set_option("nchains", 4); eng.set_option("nbins", 2); eng.set_option("scheduler", 2)
+    eng.init_rnd(43890); eng.init_paras(p.pstring()); eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)
+    eng.set_taudiffmax(p.qmc["TaudiffMax"]); eng.init_counters()
+    log = eng.debug_steps(chain, nsteps)
+    orc = OracleChain(p, rng="philox", seed=43890, chain=chain)
+    orc.init_counters()
+    assert_replay(log, orc.steps(nsteps, log=True))
+    assert eng.scalar("rounds") > 0 and eng.scalar("error_flags") == 0
+    eng.dest_ctqmc()
