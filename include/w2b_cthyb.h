@@ -66,7 +66,9 @@ int w2b_get_array(const char* name, double* out, size_t cap, size_t* n);
 int w2b_get_scalar(const char* name, double* out);
 
 /* ---- engine controls without a reference counterpart ---- */
-/* keys: nchains nbins kcap ops_cap chain_base device nmeas_override ; must be set before w2b_init_solver */
+/* keys: nchains nbins kcap ops_cap chain_base device nmeas_override propose_run scheduler (1x1 blocks: 0/1 = persistent CTA
+ * scheduler kernel, 2 = round kernels) ; must be set before w2b_init_solver.  time_kernels (0/1: CUDA events around the round
+ * kernels, read back through w2b_get_scalar ms_propose / ms_trace / ms_decide) may be switched at any time. */
 int w2b_set_option(const char* key, double value);
 /* split form of ctqmc_measure for multi-GPU runs: sample, all-reduce the raw accumulators yourself
  * (device pointer, count in doubles; one NCCL allreduce(sum) over all ranks), then finalize. */

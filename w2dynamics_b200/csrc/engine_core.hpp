@@ -1,7 +1,7 @@
 // CT-HYB chain engine: one warp advances one Markov chain.
 //
 // This file holds the per-chain logic of the hot path; it is compiled
-//  * by nvcc for sm_100a (32 lanes per chain, kernels in engine.cu), and
+//  * by nvcc for sm_100a (32 lanes per chain, kernels in engine.hpp), and
 //  * by g++ with W2B_HOST_EMU (1 lane) into a test-only library for CPU logic tests.
 //
 // Reference semantics restated here (files under /root/reference/src/ctqmc_fortran):
@@ -23,6 +23,10 @@
 //     updated out-of-place into one spare buffer per chain (rank-1 insert / remove with the row/column shift fused
 //     into the same pass), reduced with warp shuffles;
 //   * local trace for 1x1 blocks: the ratio is evaluated only over the changed sub-string (exact, not cached);
+//   * local trace for larger blocks: cached ket / bra partial products, evaluated as 8-column jobs on the FP64 tensor
+//     pipe by a kernel of its own (trace_job below, trace_matrix.hpp);
+//   * two schedulers over the chain population: a persistent CTA phase scheduler (1x1 blocks) and rounds of
+//     propose / trace / decide kernels with global moves on a second stream (blocked traces);
 //   * counter-based RNG (Philox4x32-10) consumed in the reference's draw order.
 #pragma once
 #include "warp.hpp"
