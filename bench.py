@@ -321,6 +321,27 @@ def run_engine(args):
     e2e_val = moves / (e2e_ms * 1e-3)
     err = int(eng.scalar("error_flags"))
 
+    # ---- wall time to a fixed G(tau) error (second half of BASELINE.json's metric): sample K fresh accumulation
+    # blocks, SEM of G(beta/2) over the chain-group bins, T * (eps / eps*)^2 with eps* = 1e-3 |G(beta/2)|
+    tte = None
+    try:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng._ck(L.w2b_sample(C.c_longlong(args.steps), C.c_int(1)))
+        allreduce_accum()
+        torch.cuda.synchronize()
+        t_sample = time.perf_counter() - t0
+        eng._ck(L.w2b_finalize())
+        gb = eng.bins("gtau")                                   # [bins, band, spin, tau]
+        mid = gb.shape[-1] // 2
+        gm = np.abs(gb.mean(0)[..., mid]).mean()
+        sem = (gb.std(0, ddof=1)[..., mid] / np.sqrt(gb.shape[0])).mean()
+        if gm > 0 and sem > 0:
+            tte = {"seconds_to_1e-3_relative": t_sample * (sem / (1e-3 * gm)) ** 2, "sample_seconds": t_sample, "sem_g_beta_half": float(sem),
+                   "g_beta_half": float(gm), "bins": int(gb.shape[0]), "moves": moves}
+    except Exception as exc:                                    # diagnostic only: never lose the throughput line
+        tte = {"error": str(exc)[:200]}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         alg_bytes = bytes1 - bytes0
@@ -366,6 +387,8 @@ def run_engine(args):
                                 "kernel": "k_trace", "dtype": "f64 (DMMA.8x8x4)", "algorithmic_flops_per_launch": (flops1 - flops0) / nround,
                                 "launch_ms": kms["trace"] / nround, "peak_source": fsrc,
                                 "hbm_view": {"achieved_gbs": achieved, "peak_gbs": peak, "note": "determinant-path algorithmic bytes over the whole sweep"}}
+        if tte:
+            line["time_to_error"] = tte
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

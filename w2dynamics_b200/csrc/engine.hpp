@@ -273,6 +273,7 @@ public:
 #endif
         }
         owned.clear();
+        release_host();
     }
     template <class T_> T_* keep(T_* p) { owned.push_back((void*)p); return p; }
 
@@ -504,6 +505,19 @@ public:
     std::vector<cudaEvent_t> tev;      // 4 events per round of a chunk
 #endif
     unsigned long long trace_flops() { std::vector<unsigned long long> c; get_counters(c); return c[C_TRFLOPS]; }
+    // streams, events and pinned staging of the round scheduler
+    void release_host() {
+#if W2B_DEVICE
+        if (rare_stream) { cudaStreamDestroy(rare_stream); rare_stream = nullptr; }
+        for (int i = 0; i < 2; ++i) { if (ev_prop[i]) cudaEventDestroy(ev_prop[i]); if (ev_rare[i]) cudaEventDestroy(ev_rare[i]); ev_prop[i] = ev_rare[i] = nullptr; }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        tev.clear();
+        if (h_sched) { cudaFreeHost(h_sched); h_sched = nullptr; }
+#else
+        if (h_sched) { std::free(h_sched); h_sched = nullptr; }
+#endif
+        sw_ready = false; ct_ready = false;
+    }
     void plan_sweep() {
 #if W2B_DEVICE
         int dev = 0, nsm = 1;
