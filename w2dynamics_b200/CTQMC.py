@@ -135,7 +135,11 @@ class MCTQMC:
         nb, nftau = ft.shape[0], ft.shape[4]
         if u.shape != (2 * nb,) * 4 or mu.shape != (nb, 2, nb, 2) or ft.shape[:4] != (nb, 2, nb, 2):
             raise ValueError("init_solver: inconsistent array extents")
-        opts = dict(self._options)
+        # the library is a process-wide singleton like the reference's module: every engine states ALL its options, so that
+        # nothing set through another MCTQMC object lingers
+        opts = {"kcap": 0, "ops_cap": 0, "cta_warps": 0, "batch_chains": 0, "scheduler": 0, "chain_base": 0, "propose_run": 4,
+                "prefetch": 1, "debug_same_key": 0, "time_kernels": 0}
+        opts.update(self._options)
         opts.setdefault("nchains", self._nchains)
         opts.setdefault("nbins", self._nbins)
         if self._dist is not None:

@@ -69,6 +69,20 @@ void finalize_results() {
     std::vector<double> tot(st, 0.0);
     for (int b = 0; b < nbins; ++b) for (long long i = 0; i < st; ++i) tot[i] += acc[(size_t)b * st + i];
     if (tot[E.A.o_cnt] <= 0.0) throw std::runtime_error("No measurements");
+    // where the reference `stop`s (CTQMC.F90:4062 small determinant ratio; array bounds it never checks) a chain raises a flag;
+    // results of a population with a flagged chain are not handed out
+    {
+        int mk = 0, mo = 0; const int e = E.error_flags(&mk, &mo);
+        if (e) {
+            std::string m = "chain error flags:";
+            if (e & ERR_CAPACITY) m += " operator / matrix capacity exceeded (max order " + std::to_string(mk) + " of kcap " + std::to_string(E.C.kcap) + ", max operators " + std::to_string(mo) + " of ops_cap " + std::to_string(E.C.ops_cap) + "; raise the kcap / ops_cap options);";
+            if (e & ERR_DETRAT_SMALL) m += " accepted removal with |determinant ratio| < 1e-12 (CTQMC.F90:4062);";
+            if (e & ERR_PAIR_LOGIC) m += " pair enumeration inconsistent;";
+            if (e & ERR_GLOBAL_QN) m += " no outer superstate compatible with the configuration;";
+            if (e & ERR_SINGULAR) m += " singular hybridisation matrix;";
+            throw std::runtime_error(m);
+        }
+    }
     S.res = ResultSet();
     normalise_slab(E.at, E.A, E.R, S.beta, tot.data(), S.dens_off, true, S.res);
     // per-bin samples (for error bars across chain groups)
