@@ -206,3 +206,69 @@ def test_capacity_overflow_is_loud(built):
     with pytest.raises(RuntimeError, match="capacity"):
         eng.ctqmc_measure(1, 1)
     eng.dest_ctqmc()
+
+
+def _autocorracc(series, nlevels):
+    """numpy restatement of autocorracc_add / autocorracc_blocks (Accumulators.F90:285-361) for series[n, comp]."""
+    ncomp = series.shape[1]
+    spill, mean, sq = (np.zeros((nlevels, ncomp)) for _ in range(3))
+    for n0, val in enumerate(series):
+        n, lvl, v = n0, 0, val
+        while True:
+            spill[lvl] += v
+            incr1 = v - mean[lvl]; mean[lvl] += incr1 / (n + 1)
+            sq[lvl] += incr1 * (v - mean[lvl])
+            if not (n & 1) or lvl == nlevels - 1:
+                break
+            n //= 2
+            v = spill[lvl] / 2; spill[lvl] = 0
+            lvl += 1
+    out, n = np.zeros((nlevels, ncomp)), series.shape[0]
+    for lvl in range(nlevels):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out[lvl] = sq[lvl] / (n - 1) if n > 1 else sq[lvl] / 0.0
+        n //= 2
+    return out, mean[0]
+
+
+def test_autocorrelation_accumulator(built):
+    """AccumGtau = 2: logarithmic-binning variance of G(tau) per level.  The engine keeps one series per
+    chain-group bin (group mean of the per-measurement contributions) and reports the single-chain equivalent
+    (group variance x chains per bin, averaged over bins); checked against a numpy restatement of the reference accumulator
+    fed with the very same per-measurement accumulator increments."""
+    import ctypes as C
+    nmeas, nbins, nchains, ntau = 21, 2, 6, 40
+
+    def engine(accum):
+        p = problems.make_problem("C1", nftau=2001, Nmeas=nmeas, Ntau=ntau, NLegMax=10, AccumGtau=accum)
+        eng = make(p, nchains=nchains, nbins=nbins)
+        eng.ctqmc_warmup(1500)
+        return eng, p
+    eng, p = engine(2)
+    eng.ctqmc_measure(1, 1)
+    blocks = eng.gtau_blocks
+    nlev = blocks.shape[-1]
+    assert nlev == 4 and blocks.shape[:3] == (1, 2, ntau)                 # ilog2(21) = 4 levels
+    gtau_a = eng.gtau.copy()
+    eng.dest_ctqmc()
+    # the same Markov chains, one accumulation block at a time
+    eng, p = engine(1)
+    eng.init_counters()
+    L = eng._load()
+    n = C.c_size_t()
+    eng._ck(L.w2b_read_accum(None, C.c_size_t(0), C.byref(n)))
+    ncomp, series, prev = 2 * ntau, [], np.zeros((nbins, 2 * ntau))
+    for _ in range(nmeas):
+        eng.block(int(p.qmc.get("NCorr", 100)), True)
+        buf = np.zeros(n.value)
+        eng._ck(L.w2b_read_accum(buf.ctypes.data_as(C.POINTER(C.c_double)), C.c_size_t(n.value), C.byref(n)))
+        cur = buf.reshape(nbins, -1)[:, :ncomp]                            # G(tau) accumulators lead every bin's slab: [flavour][tau]
+        series.append((cur - prev) / (nchains / nbins)); prev = cur.copy()
+    series = np.array(series)                                              # [n, bin, comp]
+    ref = sum((nchains / nbins) * _autocorracc(series[:, b], nlev)[0] for b in range(nbins)) / nbins
+    ref = ref.reshape(nlev, 2, ntau)                                       # [level][spin (one band)][tau]
+    for lvl in range(nlev):
+        assert np.allclose(blocks[0, :, :, lvl], ref[lvl], rtol=1e-12, atol=1e-300), lvl
+    eng._ck(L.w2b_finalize())
+    assert np.array_equal(eng.gtau, gtau_a)                                # the mean is unaffected by the accumulator choice
+    eng.dest_ctqmc()

@@ -198,3 +198,41 @@ def test_chain_independent_of_population(cuda_engine_factory, cfg, nsteps):
         assert eng.scalar("error_flags") == 0
         eng.dest_ctqmc()
     assert np.array_equal(logs[0], logs[1])
+
+
+def test_autocorrelation_accumulator(cuda_engine_factory):
+    """AccumGtau = 2 on the GPU (k_autocorr_add): same check as the host-build test -- the logarithmic-binning variances equal a
+    numpy restatement of the reference accumulator fed with the per-measurement accumulator increments of the same chains."""
+    import ctypes as C
+    from test_engine_logic import _autocorracc
+    nmeas, nbins, nchains, ntau = 37, 4, 64, 40
+
+    def engine(accum):
+        p = problems.make_problem("C1", Nmeas=nmeas, Ntau=ntau, NLegMax=10, AccumGtau=accum)
+        eng = cuda_engine_factory(p, nchains=nchains, nbins=nbins)
+        eng.ctqmc_warmup(1500)
+        return eng, p
+    eng, p = engine(2)
+    eng.ctqmc_measure(1, 1)
+    blocks = eng.gtau_blocks
+    nlev = blocks.shape[-1]
+    assert nlev == 5                                                       # ilog2(37)
+    eng.dest_ctqmc()
+    eng, p = engine(1)
+    eng.init_counters()
+    L = eng._load()
+    n = C.c_size_t()
+    eng._ck(L.w2b_read_accum(None, C.c_size_t(0), C.byref(n)))
+    ncomp, series, prev = 2 * ntau, [], np.zeros((nbins, 2 * ntau))
+    for _ in range(nmeas):
+        eng.block(int(p.qmc.get("NCorr", 100)), True)
+        buf = np.zeros(n.value)
+        eng._ck(L.w2b_read_accum(buf.ctypes.data_as(C.POINTER(C.c_double)), C.c_size_t(n.value), C.byref(n)))
+        cur = buf.reshape(nbins, -1)[:, :ncomp]
+        series.append((cur - prev) / (nchains / nbins)); prev = cur.copy()
+    series = np.array(series)
+    ref = (sum((nchains / nbins) * _autocorracc(series[:, b], nlev)[0] for b in range(nbins)) / nbins).reshape(nlev, 2, ntau)
+    for lvl in range(nlev):
+        # G(tau) accumulators are filled by atomics: the summation order inside a bin differs between the two runs
+        assert np.allclose(blocks[0, :, :, lvl], ref[lvl], rtol=1e-8, atol=1e-12), lvl
+    eng.dest_ctqmc()

@@ -45,6 +45,7 @@ class MCTQMC:
         # name: shape builder (d = dims dict) -- extents of the reference's module arrays
         "gtau": lambda d: (d["nb"], 2, d["ntau"]),
         "gtau_full": lambda d: (d["nb"], 2, d["nb"], 2, d["ntau"]),
+        "gtau_blocks": lambda d: (d["nb"], 2, d["ntau"], -1),                     # AccumGtau = 2 only; last axis = binning levels
         "gleg": lambda d: (d["nb"], 2, d["nleg"]),
         "gleg_full": lambda d: (d["nb"], 2, d["nb"], 2, d["nleg"]),
         "occ": lambda d: (d["nb"], 2, d["nb"], 2),

@@ -57,7 +57,7 @@ void check_supported(const Params& p) {
     zero_r("PercentageOuterMove"); zero_r("Percentage4OperatorMove");
     if (p.has("Eigenbasis") && p.integer("Eigenbasis") == 0) throw std::runtime_error("You requested Krylov, but this no longer supported.");
     if (p.has("EnableOuterTruncation") && p.str("EnableOuterTruncation") == "YES") throw std::runtime_error("EnableOuterTruncation is outside the implemented hot path");
-    if (p.has("AccumGtau") && p.integer("AccumGtau") != 1) throw std::runtime_error("only AccumGtau = 1 (mean accumulator) is implemented");
+    if (p.has("AccumGtau") && p.integer("AccumGtau") != 1 && p.integer("AccumGtau") != 2) throw std::runtime_error("AccumGtau must be 1 (mean) or 2 (mean + autocorrelation blocks)");
 }
 
 void finalize_results() {
@@ -104,6 +104,15 @@ void finalize_results() {
     S.res.scal["accadd4"] = std::numeric_limits<double>::quiet_NaN(); S.res.scal["accrem4"] = std::numeric_limits<double>::quiet_NaN();
     S.res.scal["accflavc"] = std::numeric_limits<double>::quiet_NaN();
     S.res.scal["steps"] = (double)cnt[C_STEPS];
+    if (E.ac_levels) {                                                       // gtau_blocks(NBands, 2, NGtau, levels), raw as in the reference (CTQMC.F90:8733-8739)
+        std::vector<double> blk; E.autocorr_blocks(blk);
+        const int nb = E.at.nb, nf = E.at.nf, ntau = E.R.ntau;
+        std::vector<double> gb((size_t)nf * ntau * E.ac_levels);
+        for (int l = 0; l < E.ac_levels; ++l) for (int b = 0; b < nb; ++b) for (int s2 = 0; s2 < 2; ++s2) for (int t = 0; t < ntau; ++t)
+            gb[(b + (size_t)nb * s2) + (size_t)nf * t + (size_t)nf * ntau * l] = blk[(size_t)l * nf * ntau + (size_t)(2 * b + s2) * ntau + t];
+        S.res.arr["gtau_blocks"] = gb;
+        S.res.scal["gtau_levels"] = (double)E.ac_levels;
+    }
     std::vector<double> ap(accpair.size());
     const int nf = E.T.nf, nbd = E.T.nb, ntau = E.R.ntau;
     for (int b = 0; b < nbd; ++b) for (int s = 0; s < 2; ++s) for (int t = 0; t < ntau; ++t) ap[b + (size_t)nbd * (s + 2 * t)] = (double)accpair[(size_t)(2 * b + s) * ntau + t];
@@ -139,6 +148,7 @@ void run_blocks(long long nmeas, bool timing) {
         if (timing) cudaEventRecord(e1);
 #endif
         E.measure();
+        E.autocorr_add();
 #if W2B_DEVICE
         if (timing) { cudaEventSynchronize(e1); float ms = 0; cudaEventElapsedTime(&ms, e0, e1); steps_ms += ms; }
 #endif
@@ -221,6 +231,10 @@ int w2b_init_solver(const double* u_matrix, const double* ftau_full, const doubl
         S.opt.seed = (unsigned)S.seed;
         S.eng->setup(at, fd, nftau, S.beta, R, S.opt);
         S.dens_off = S.eng->dens_off;                                        // block k: d x d column-major slab
+        if (p.has("AccumGtau") && p.integer("AccumGtau") == 2) {             // autocorracc_create(ncomp, ilog2(NMeas))  CTQMC.F90:497-499
+            long long v = S.nmeas, lv = -1; while (v > 0) { ++lv; v /= 2; }   // ilog2, Accumulators.F90:89-101
+            S.eng->autocorr_setup((int)std::max<long long>(lv, 1));
+        }
         S.have_res = false; S.time_warmup = S.time_sim = S.time_sim_steps = 0;
         S.eng->sync();
     });
@@ -323,7 +337,7 @@ int w2b_ctqmc_calibrate(int list, int phase1pairnum, int phase2taugrid, int phas
 }
 
 int w2b_block(long long nsweep, int do_measure) {
-    return guarded([&] { require_engine(); S.eng->sweep(nsweep); if (do_measure) S.eng->measure(); });
+    return guarded([&] { require_engine(); S.eng->sweep(nsweep); if (do_measure) { S.eng->measure(); S.eng->autocorr_add(); } });
 }
 int w2b_sync(void) { return guarded([&] { require_engine(); S.eng->sync(); }); }
 

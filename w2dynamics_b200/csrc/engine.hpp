@@ -194,6 +194,17 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, TRACE_NT == 1 ? 8 : 6) k_tra
     for (int t0 = wgrab_n(&sc[SC_TTICKET], TICKET_BATCH); t0 < total; t0 = wgrab_n(&sc[SC_TTICKET], TICKET_BATCH))
         for (int t = t0; t < t0 + TICKET_BATCH && t < total; ++t) phase_trace(T, C, t, parity, ws);
 }
+// autocorrelation accumulator: one thread per (bin, component)
+__global__ void __launch_bounds__(256) k_autocorr_add(const double* acc, long long stride, int o_gtau, int ncomp, int nbins, int nlevels, long long n,
+                                                     const double* inv_group, double* prev, double* dat) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nbins * ncomp) return;
+    const int bin = (int)(i / ncomp), comp = (int)(i % ncomp);
+    const double now = acc[(size_t)bin * stride + o_gtau + comp];
+    const double val = (now - prev[i]) * inv_group[bin];
+    prev[i] = now;
+    autocorr_add_one(val, n, nlevels, dat + (size_t)bin * nlevels * 3 * ncomp, ncomp, comp);
+}
 // measurement pre-pass (blocked traces): extend every chain's cache frontiers to tau = beta/2, one job per 8 outer states
 __global__ void __launch_bounds__(TRACE_WARPS * 32, TRACE_NT == 1 ? 8 : 6) k_meas_extend(Tables T, Chains C, int tdoubles) {
     extern __shared__ double smem[];
@@ -433,7 +444,68 @@ public:
         R.naccpair = n; R.accpair_max = range; dev_zero(A.accpair, (size_t)T.nf * accpair_cap);
     }
     void get_accpair(std::vector<unsigned long long>& out) { sync(); out.resize((size_t)T.nf * R.naccpair); d2h(out.data(), A.accpair, out.size()); }
-    void zero_accum() { dev_zero(A.base, (size_t)R.nbins * accum_doubles); }
+    void zero_accum() { dev_zero(A.base, (size_t)R.nbins * accum_doubles); autocorr_reset(); }
+
+    // ---- autocorrelation accumulator of G(tau) (AccumGtau = 2, Accumulators.F90:214-364), one series per chain-group bin
+    int ac_levels = 0; long long ac_n = 0;
+    double* ac_prev = nullptr; double* ac_dat = nullptr; double* ac_invg = nullptr;     // [bin][comp], [bin][level][3][comp], [bin]
+    std::vector<double> ac_group;                                                       // chains per bin
+    void autocorr_setup(int nlevels) {
+        ac_levels = std::max(nlevels, 1);
+        const size_t ncomp = (size_t)T.nf * R.ntau;
+        ac_prev = keep(dev_alloc<double>((size_t)R.nbins * ncomp));
+        ac_dat = keep(dev_alloc<double>((size_t)R.nbins * ac_levels * 3 * ncomp));
+        ac_group.assign(R.nbins, 0.0);
+        for (int c = 0; c < C.nchains; ++c) ac_group[(R.chain_base + (unsigned)c) % (unsigned)R.nbins] += 1.0;
+        std::vector<double> inv(R.nbins);
+        for (int b = 0; b < R.nbins; ++b) inv[b] = ac_group[b] > 0 ? 1.0 / ac_group[b] : 0.0;
+        ac_invg = keep(dev_upload(inv));
+        ac_n = 0;
+    }
+    void autocorr_reset() {
+        if (!ac_levels) return;
+        const size_t ncomp = (size_t)T.nf * R.ntau;
+        dev_zero(ac_prev, (size_t)R.nbins * ncomp); dev_zero(ac_dat, (size_t)R.nbins * ac_levels * 3 * ncomp);
+        ac_n = 0;
+    }
+    void autocorr_add() {                       // call after every measurement
+        if (!ac_levels) return;
+        const int ncomp = T.nf * R.ntau;
+#if W2B_DEVICE
+        const long long tot = (long long)R.nbins * ncomp;
+        k_autocorr_add<<<(unsigned)((tot + 255) / 256), 256>>>(A.base, A.stride, A.o_gtau, ncomp, R.nbins, ac_levels, ac_n, ac_invg, ac_prev, ac_dat); ++launches;
+        W2B_CUDA_CHECK(cudaGetLastError());
+#else
+        for (int b = 0; b < R.nbins; ++b) for (int comp = 0; comp < ncomp; ++comp) {
+            const size_t i = (size_t)b * ncomp + comp;
+            const double nowv = A.base[(size_t)b * A.stride + A.o_gtau + comp];
+            const double val = (nowv - ac_prev[i]) * ac_invg[b];
+            ac_prev[i] = nowv;
+            autocorr_add_one(val, ac_n, ac_levels, ac_dat + (size_t)b * ac_levels * 3 * ncomp, ncomp, comp);
+        }
+#endif
+        ++ac_n;
+    }
+    // autocorracc_blocks (Accumulators.F90:343-361): variance of the level-l bin means, here of a single chain's series
+    // (group-mean variance x chains per bin, chains being independent), averaged over the bins; [level][comp]
+    void autocorr_blocks(std::vector<double>& out) {
+        const size_t ncomp = (size_t)T.nf * R.ntau;
+        out.assign((size_t)ac_levels * ncomp, 0.0);
+        if (!ac_levels) return;
+        sync();
+        std::vector<double> dat((size_t)R.nbins * ac_levels * 3 * ncomp);
+        d2h(dat.data(), ac_dat, dat.size());
+        int used = 0; for (int b = 0; b < R.nbins; ++b) used += ac_group[b] > 0;
+        long long n = ac_n;
+        for (int l = 0; l < ac_levels; ++l) {
+            for (int b = 0; b < R.nbins; ++b) {
+                if (!(ac_group[b] > 0)) continue;
+                const double* sq = dat.data() + ((size_t)b * ac_levels + l) * 3 * ncomp + 2 * ncomp;
+                for (size_t c = 0; c < ncomp; ++c) out[(size_t)l * ncomp + c] += (n > 1 ? sq[c] / (double)(n - 1) : sq[c] / 0.0) * ac_group[b] / used;
+            }
+            n /= 2;
+        }
+    }
 
     // ---- 1x1 blocks: persistent CTA-scheduler kernel; geometry: W warps per CTA, batches of ncb chains, persistent grid
     int ct_warps = 1, ct_ncb = 1, ct_nbatch = 1, ct_grid = 1; size_t ct_smem = 0; bool ct_ready = false;

@@ -1609,6 +1609,30 @@ W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const A
     if (rare && lane == 0) C.parked[chain] = ST_RUN;
 }
 
+// ------------------------------------------------------------------ autocorrelation accumulator of G(tau) (AccumGtau = 2)
+// Restates autocorracc_add (Accumulators.F90:285-330; logarithmic binning with Welford updates, arXiv:1810.05079 Sec. III.D)
+// for one component of one chain-group bin.  The series element of measurement n is the bin's accumulator increment divided
+// by its number of chains (the group mean of what the reference's single chain puts into `buffer`).
+// dat: [level][3][ncomp] of this bin (spill, mean, sqdiff).
+W2B_HD void autocorr_add_one(double val, long long n, int nlevels, double* dat, int ncomp, int comp) {
+    int lvl = 0;
+    double* sp = dat + comp; double* mn = dat + ncomp + comp; double* sq = dat + 2 * ncomp + comp;
+    {
+        *sp += val;
+        const double incr1 = val - *mn; *mn += incr1 / (double)(n + 1);
+        const double incr2 = val - *mn; *sq += incr1 * incr2;
+    }
+    while (n & 1) {                      // the lowest bits are all ones: roll the finished bin over to the next level
+        if (lvl == nlevels - 1) break;
+        n /= 2; ++lvl;
+        const double v = *sp / 2.0; *sp = 0.0;
+        sp += (size_t)3 * ncomp; mn += (size_t)3 * ncomp; sq += (size_t)3 * ncomp;
+        *sp += v;
+        const double incr1 = v - *mn; *mn += incr1 / (double)(n + 1);
+        const double incr2 = v - *mn; *sq += incr1 * incr2;
+    }
+}
+
 // init_Trace (Trace.F90:340-701): empty configuration, outer superstate drawn with the empty-trace weights
 W2B_HD void init_chain(const Tables& T, const Run& R, const Chains& C, int chain) {
     if (lane_id() != 0) return;
