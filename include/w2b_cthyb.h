@@ -59,6 +59,7 @@ int w2b_set_empty_mc_config(int chain, int outer_sst, int outer_state);
  * total element count in *n.  Names: gtau gtau_full gleg gleg_full occ histo rhisto lhisto statessuperstates
  * eigenstatesenergies occbasismapping outersuperstatehisto outerstatehisto signhistosuperstates signhistostates
  * tracecontribsuperstates tracecontribstates accadd accrem accpair densitymatrix rho1 rho2 ;
+ * gtau_blocks (Nb,2,Ntau,levels) when AccumGtau = 2 (autocorracc, Accumulators.F90:214-364; CTQMC.F90:8733-8739) ;
  * additionally per-bin samples gtau_bins gleg_bins occ_bins sign_bins (leading extents as the quantity, last = bin). */
 int w2b_get_array(const char* name, double* out, size_t cap, size_t* n);
 /* scalars: mean_sign accglob accshift accadd4 accrem4 accflavc time_warmup time_sim time_sim_steps aborted
