@@ -1396,35 +1396,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
 }
 
 
-// Pull the records one chain's move will touch into the cache hierarchy with one burst of prefetches (one 128-byte line per
-// lane and instruction) before the first dependent access: with tens of thousands of chains the population is far larger than
-// L2 and every first touch is a DRAM round trip; unprefetched, a move pays dozens of them one after the other.
-W2B_HD void prefetch_line(const void* p) {
-#if W2B_DEVICE
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
-W2B_HD void prefetch_chain(const Tables& T, const Chains& C, int chain, int n_hint) {
-#if W2B_DEVICE
-    const int l = lane_id();
-    const int nl = (n_hint + 15) >> 4;                            // lines of operator times in use (16 per line)
-    const char* p = nullptr;
-    if (l < 8) { if (l < nl || l == 0) p = (const char*)(C.op_tau + (size_t)chain * C.ops_cap) + l * 128; }
-    else if (l < 10) { if ((l - 8) * 64 < n_hint || l == 8) p = (const char*)(C.op_sst + (size_t)chain * C.ops_cap) + (l - 8) * 128; }
-    else if (l == 10) p = (const char*)(C.op_code + (size_t)chain * C.ops_cap);
-    else if (l == 11) p = (const char*)(C.op_code + (size_t)chain * C.ops_cap) + 128;
-    else if (l < 14) p = (const char*)(C.ih + (size_t)chain * IH_STRIDE) + (l - 12) * 128;
-    else if (l == 14) p = (const char*)(C.dh + (size_t)chain * DH_STRIDE);
-    else if (l == 15) p = (const char*)(C.counters + (size_t)chain * C_NCNT);
-    else if (l == 16) p = (const char*)(C.rng_ctr + chain);
-    else if (l == 17) p = (const char*)(C.prop + chain);
-    else if (l == 18) p = (const char*)(C.prop + chain) + 128 - 8;
-    else if (l < 21 && C.dmax > 1) p = (const char*)(C.op_slot + (size_t)chain * C.ops_cap) + (l - 19) * 128;
-    if (p) prefetch_line(p);
-    for (int q = l; q < 2 * T.nf; q += W2B_WARP)                  // first line of every flavour's creator / annihilator times
-        prefetch_line((const char*)(((q & 1) ? C.tau_a : C.tau_c) + ((size_t)chain * T.nf + (q >> 1)) * C.kcap));
-#endif
-}
+// (L2 prefetch bursts of a chain's records at the start of a round item were measured: no effect, 1 % slower.)
 // bookkeeping after every move: window shift (checked after EVERY move, CTQMC.F90:8255/8531), step counter, quota
 W2B_HDN void post_move(const Tables& T, const Run& R, const Chains& C, Ctx& x, int chain) {
     wsync();
@@ -1477,7 +1449,6 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
         return;
     }
     const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
-    if (R.prefetch) prefetch_chain(T, C, chain, 128);
     ctx_bind(T, R, C, chain, x, nullptr, nullptr, nullptr);
     for (int run = 0; run < R.propose_run && left > 0; ++run) {
         const double r = x.rng.next();
@@ -1591,7 +1562,6 @@ W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const A
     else if (ticket < nrare + n0 + n1) entry = C.q_dec1[ticket - nrare - n0];
     else entry = C.q_dec2[ticket - nrare - n0 - n1];
     const int chain = entry & Q_IDMASK;
-    if (R.prefetch) { prefetch_chain(T, C, chain, 128); if (!rare) prefetch_minv(T, C, chain, C.prop[chain].f); }
     ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
     if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - C.left[chain]) * LOGW;
     if (T.dmax > 1) x.mpt = C.ptc + (size_t)chain * 2 * C.dmax;      // parts of the proposed configuration, left by the trace kernel
