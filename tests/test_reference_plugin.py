@@ -88,7 +88,8 @@ def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
     qmc = _qmc_defaults()                              # every [QMC] key of the reference, at its default
     assert qmc["NCorr"] == 100 and qmc["Nftau"] == 5000 and "real_ham_tolerance" in qmc
     qmc.update(Nwarmups=2000, Nmeas=150, NCorr=50, Ntau=200, NLegMax=40, NLegOrder=40, Niw=niw, Nftau=501,
-               TaudiffMax=p.qmc["TaudiffMax"] if taudiffmax == "fixed" else -1.0)   # -1 (the default): ctqmc_calibrate path
+               TaudiffMax=p.qmc["TaudiffMax"] if taudiffmax == "fixed" else -1.0,   # -1 (the default): ctqmc_calibrate path
+               AccumGtau=2 if taudiffmax == "fixed" else 1)                           # 2: autocorrelation accumulator -> "gtau-blocks"
     config = {"QMC": qmc, "General": {"FTType": "legendre", "beta": beta}, "Atoms": {"1": {"Nd": nb}}}
     iw = tf.matfreq(beta, "fermi", niw)
     tau = np.linspace(0, beta, 501)
@@ -128,6 +129,12 @@ def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
     # G(iw) from the Legendre coefficients: particle-hole symmetric problem -> purely imaginary, negative imaginary part
     g = giw[niw // 2:niw // 2 + 10, 0, 0, 0, 0]
     assert np.all(g.imag < 0) and np.abs(g.real).max() < 0.08
+    if taudiffmax == "fixed":           # cthyb_solver.py:1024-1026 reads ctqmc.gtau_blocks; ilog2(150) = 7 binning levels
+        blocks = result.other["gtau-blocks"].mean()
+        assert blocks.shape == (nb, 2, 200, 7) and np.all(blocks[..., 0] >= 0) and np.all(np.isfinite(blocks[..., :5]))
+        import w2dyn.auxiliaries.postprocessing as pp
+        tauint = pp.gtau_tauint(blocks)                  # the reference's own logarithmic-binning analysis accepts it
+        assert tauint.shape == (nb, 2, 200)
     # ReuseMCConfig hook: the plugin fetched the configuration through get_mc_config
     assert len(mc_cfg) == 1 and mc_cfg[0].taus.shape == mc_cfg[0].orbs.shape
     for k in ("w2dyn.auxiliaries.CTQMC", "w2dyn.dmft.cthyb_solver"):
