@@ -272,3 +272,42 @@ def test_autocorrelation_accumulator(built):
     eng._ck(L.w2b_finalize())
     assert np.array_equal(eng.gtau, gtau_a)                                # the mean is unaffected by the accumulator choice
     eng.dest_ctqmc()
+
+
+def test_operator_list_invariants_under_stress(built):
+    """Counterpart of the reference's testsuite/ctqmc.tests/3-operator-list-stress-test.F90 (75 000 insert / remove / shift
+    steps at beta / taudiff_max = 10, three orbitals; it walks the doubly linked operator list and asserts time ordering,
+    per-flavour sub-list consistency and the pre-window counts).  The engine keeps packed time-sorted arrays instead of lists;
+    the same invariants are checked on what it hands back: strictly increasing times inside (0, beta), as many creators as
+    annihilators per flavour and both equal to the order of that flavour's inverse matrix, a superstate sequence that closes
+    (the oracle rebuilds the configuration from scratch without error and finds the same trace, determinant and sign), and
+    M * Delta = 1 for the from-scratch hybridisation matrix of the stored time order."""
+    p = problems.make_problem("C3", nftau=2001)                      # beta 40, taudiff_max 4: 9 windows, window shifts every 16 attempts
+    eng = make(p, nchains=2)
+    orc = OracleChain(p, seed=1)
+    seen_orders = set()
+    for _ in range(30):
+        eng.ctqmc_warmup(2500)
+        for chain in range(2):
+            n, osst, _ = eng.get_mc_config_scalars(chain)
+            taus, orbs, spins, cas, hyb, osst2, _ = eng.get_mc_config(n, chain)
+            assert osst == osst2 and n % 2 == 0
+            assert np.all(np.diff(taus) > 0) and (n == 0 or (taus[0] > 0 and taus[-1] < p.beta))
+            for b in range(p.nbands):
+                for sp in range(2):
+                    sel = (orbs == b + 1) & (spins == sp + 1)
+                    kc, ka = int((cas[sel] == 1).sum()), int((cas[sel] == 2).sum())
+                    m = eng.debug_minv(chain, b + 1, sp + 1)
+                    assert kc == ka == m.shape[0]
+                    seen_orders.add(kc)
+            orc.set_config(taus, orbs, spins, cas, osst)
+            s, o = eng.debug_chain_scalars(chain), orc.scalars()
+            assert orc.error == 0 and s["error"] == 0
+            assert abs(s["trace_log"] - o["trace_log"]) < 1e-8 and abs(s["det_log"] - o["det_log"]) < 1e-7
+            assert (s["trace_sign"], s["det_sign"], s["cfgsign"]) == (o["trace_sign"], o["det_sign"], o["cfgsign"])
+            for f in range(2 * p.nbands):
+                a, c = eng.debug_minv(chain, f // 2 + 1, f % 2 + 1), orc.minv(f, scratch=True)
+                if a.size:
+                    assert np.abs(a - c).max() < 1e-6 * max(1.0, np.abs(c).max())
+    assert len(seen_orders) > 5 and eng.scalar("cnt_acc_shift") > 0 and eng.scalar("cnt_acc_glob") >= 0
+    eng.dest_ctqmc()
