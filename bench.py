@@ -178,7 +178,7 @@ def run_reference(args):
     cfg = args.config
     nthreads = os.cpu_count() or 1
     pop = OraclePopulation(cfg, nthreads)
-    slice_s = min(60.0 / max(1, args.steps + args.warmup), 10.0)     # one step = one slice; whole run ~ a minute
+    slice_s = args.slice_seconds if args.slice_seconds > 0 else min(60.0 / max(1, args.steps + args.warmup), 10.0)     # one step = one slice; whole run ~ a minute
     for _ in range(args.warmup):
         pop.run(slice_s)
     pop.reset()
@@ -409,6 +409,7 @@ def main():
     ap.add_argument("--thermalise", type=int, default=-1, help="untimed thermalisation moves per chain")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--slice-seconds", type=float, default=0.0, help="reference arm: wall time of one step (default: sized for a one-minute run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
