@@ -114,7 +114,9 @@ class OraclePopulation:
     moves (one chain per MPI rank, Nmeas x NCorr moves each; moves/s = ranks x moves / mean(time-sampling)).
     Chains differ ~30x in cost per move on C4 (outer block of 1 vs 28 states), so each host thread owns several chains, times
     each one on its own for a slice, and the figure is  threads x chains / sum_i(seconds per move of chain i)  -- the
-    equal-moves throughput of the population, not a time-weighted average that favours the cheap chains."""
+    equal-moves throughput of the population, not a time-weighted average that favours the cheap chains.
+    The chains run the oracle's windowed trace evaluation (cached edge states outside the sliding window, oracle/chain.cpp
+    `trace_windowed`): the reference's cost structure rather than the checker's from-scratch trace."""
 
     def __init__(self, cfg, nthreads, chains_per_thread=4):
         from w2dynamics_b200 import problems
@@ -124,7 +126,7 @@ class OraclePopulation:
         self.p = problems.make_problem(cfg)
         self.ncorr = int(self.p.qmc.get("NCorr", 100))
         self.nthreads, self.cpt, self.therm = nthreads, chains_per_thread, THERMALISE[cfg]
-        self.chains = [OracleChain(self.p, rng="philox", seed=43890, chain=1000 + i) for i in range(nthreads * chains_per_thread)]
+        self.chains = [OracleChain(self.p, rng="philox", seed=43890, chain=1000 + i, fast_trace=True) for i in range(nthreads * chains_per_thread)]
         self._threads(lambda t: [self.chains[t * self.cpt + j].warmup(self.therm) for j in range(self.cpt)])
         self.reset()
 
@@ -193,7 +195,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[cfg], "ncorr": ncorr, "note": "oracle port of the reference algorithm (Fortran reference not buildable here); the port re-evaluates the local trace of the changed window without the reference's state/cache pointers"},
+        "config": {"workload": WORKLOADS[cfg], "ncorr": ncorr, "note": "oracle port of the reference algorithm (Fortran reference not buildable here); the port keeps cached edge states outside the sliding window and re-evaluates the window per proposal (the reference's cost structure; its per-operator caches inside the window are not restated)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

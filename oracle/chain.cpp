@@ -151,6 +151,7 @@ struct Chain {
         }
     }
     void init_window(double tdm) {
+        ec.valid = false;
         window_position = 0;
         if (tdm > 0.0) {
             taudiff_max = tdm;
@@ -162,6 +163,7 @@ struct Chain {
         }
     }
     void shift_window() {                         // Trace.F90:1652-1678
+        ec.valid = false;
         if (num_windows > 1) {
             window_position += 1;
             if (window_position == num_windows) window_position = 0;
@@ -260,6 +262,125 @@ struct Chain {
             if (pt.sign != 0.0) tot = (tot.sign == 0.0) ? pt : ladd(tot, pt);
         }
         return tot;
+    }
+
+    // ---------------------------------------------------------- windowed evaluation (opt-in; CPU baseline only)
+    // The reference does not recompute the whole trace per proposal: operators outside the sliding window keep cached
+    // states (TOper%state / %cache, update_trace_EB Trace.F90:6109-6209) and only the window is re-evaluated.  This mode
+    // mirrors that cost structure for the timed CPU baseline: the ket chain of the operators left of the window and the bra
+    // chain of the operators right of it are cached per outer state and rebuilt when the window moves or a global move /
+    // tau shift is accepted; a pair move (always inside the window) multiplies through the window only.  Same products as
+    // trace_full in a different association order; the checker keeps using trace_full (fast_trace = false).
+    bool fast_trace = false;
+    struct EdgeCache {
+        bool valid = false; int wpos = -1, outer = -1, nL = 0, nR = 0, sstL = 0, sstR = 0; double tauL = 0, tauR = 0;
+        std::vector<double> KL, lgL, BR, lgR;
+    } ec;
+    void build_edges(const std::vector<Op>& o, int outer) {
+        const int n = (int)o.size(), m = T.dim[outer], dm = T.dmax;
+        int nL = 0; while (nL < n && o[nL].tau < tauwin_min) ++nL;
+        int kR = n; while (kR > nL && o[kR - 1].tau > tauwin_max) --kR;
+        ec.nL = nL; ec.nR = n - kR; ec.wpos = window_position; ec.outer = outer; ec.valid = true;
+        ec.KL.assign((size_t)m * dm, 0.0); ec.lgL.assign(m, 0.0); ec.BR.assign((size_t)m * dm, 0.0); ec.lgR.assign(m, 0.0);
+        std::vector<double> kt(dm), ktp(dm);
+        // kets of the operators left of the window (same arithmetic as trace_full)
+        int sstL = outer; double tauL = 0;
+        for (int j = 0; j < m; ++j) {
+            int sst = outer, ns_sst = m; double lg = 0, tauR_ = 0;
+            std::fill(kt.begin(), kt.end(), 0.0); kt[j] = 1.0;
+            for (int i = 0; i < nL; ++i) {
+                const Op& e = o[i];
+                int ns = T.conn(sst, e.b, e.s, e.ca), nn = T.dim[ns];
+                const double* ev = &T.evals[T.offset[sst]];
+                const double* A = T.op(sst, e.b, e.s, e.ca);
+                if (ns_sst > 1) {
+                    for (int c = 0; c < ns_sst; ++c) ktp[c] = std::exp(-(ev[c] - ev[0]) * (e.tau - tauR_)) * kt[c];
+                    lg += -(ev[0] - T.egs) * (e.tau - tauR_);
+                    split_log(ktp.data(), ns_sst, lg);
+                    for (int r = 0; r < nn; ++r) kt[r] = 0.0;
+                    for (int c = 0; c < ns_sst; ++c) { double x = ktp[c]; const double* col = A + (size_t)c * nn; for (int r = 0; r < nn; ++r) kt[r] += col[r] * x; }
+                    split_log(kt.data(), nn, lg);
+                } else {
+                    lg += -(ev[0] - T.egs) * (e.tau - tauR_);
+                    double x = kt[0];
+                    for (int r = 0; r < nn; ++r) kt[r] = x * A[r];
+                }
+                tauR_ = e.tau; sst = ns; ns_sst = nn;
+            }
+            for (int c = 0; c < ns_sst; ++c) ec.KL[(size_t)j * dm + c] = kt[c];
+            ec.lgL[j] = lg; sstL = sst; tauL = tauR_;
+        }
+        ec.sstL = sstL; ec.tauL = tauL;
+        // bras of the operators right of the window: b_j = e_j^T P O_n P ... O_kR, a vector in the block before operator kR
+        std::vector<int> after; sst_sequence(o, outer, after);
+        ec.sstR = kR == n ? outer : (kR == 0 ? outer : after[kR - 1]);
+        ec.tauR = kR == n ? beta : o[kR].tau;
+        for (int j = 0; j < m; ++j) {
+            std::fill(kt.begin(), kt.end(), 0.0); kt[j] = 1.0;
+            double lg = 0, tnext = beta; int sst = outer, ns_sst = m;          // block the bra lives in (after operator i)
+            for (int i = n - 1; i >= kR; --i) {
+                const Op& e = o[i];
+                const int before = i == 0 ? outer : after[i - 1], nb_ = T.dim[before];
+                const double* ev = &T.evals[T.offset[sst]];
+                const double* A = T.op(before, e.b, e.s, e.ca);                 // (ns_sst x nb_) column-major
+                for (int c = 0; c < ns_sst; ++c) ktp[c] = std::exp(-(ev[c] - ev[0]) * (tnext - e.tau)) * kt[c];
+                lg += -(ev[0] - T.egs) * (tnext - e.tau);
+                split_log(ktp.data(), ns_sst, lg);
+                for (int c = 0; c < nb_; ++c) { const double* col = A + (size_t)c * ns_sst; double acc = 0; for (int r = 0; r < ns_sst; ++r) acc += col[r] * ktp[r]; kt[c] = acc; }
+                split_log(kt.data(), nb_, lg);
+                tnext = e.tau; sst = before; ns_sst = nb_;
+            }
+            for (int c = 0; c < ns_sst; ++c) ec.BR[(size_t)j * dm + c] = kt[c];
+            ec.lgR[j] = lg;
+        }
+    }
+    LogVal trace_windowed(const std::vector<Op>& o, int outer, std::vector<LogVal>* parts) {
+        if (!ec.valid || ec.wpos != window_position || ec.outer != outer) build_edges(o, outer);
+        const int n = (int)o.size(), m = T.dim[outer], dm = T.dmax;
+        LogVal tot{-HUGE_D, 0.0};
+        if (parts) parts->assign(m, LogVal{-HUGE_D, 0.0});
+        std::vector<double> kt(dm), ktp(dm);
+        const int lo = ec.nL, hi = n - ec.nR;
+        for (int j = 0; j < m; ++j) {
+            int sst = ec.sstL, ns_sst = T.dim[ec.sstL]; double lg = ec.lgL[j], tauR_ = ec.tauL;
+            for (int c = 0; c < ns_sst; ++c) kt[c] = ec.KL[(size_t)j * dm + c];
+            bool dead = false;
+            for (int i = lo; i < hi; ++i) {
+                const Op& e = o[i];
+                int ns = T.conn(sst, e.b, e.s, e.ca);
+                if (ns < 0) { dead = true; break; }
+                int nn = T.dim[ns];
+                const double* ev = &T.evals[T.offset[sst]];
+                const double* A = T.op(sst, e.b, e.s, e.ca);
+                if (ns_sst > 1) {
+                    for (int c = 0; c < ns_sst; ++c) ktp[c] = std::exp(-(ev[c] - ev[0]) * (e.tau - tauR_)) * kt[c];
+                    lg += -(ev[0] - T.egs) * (e.tau - tauR_);
+                    split_log(ktp.data(), ns_sst, lg);
+                    for (int r = 0; r < nn; ++r) kt[r] = 0.0;
+                    for (int c = 0; c < ns_sst; ++c) { double x = ktp[c]; const double* col = A + (size_t)c * nn; for (int r = 0; r < nn; ++r) kt[r] += col[r] * x; }
+                    split_log(kt.data(), nn, lg);
+                } else {
+                    lg += -(ev[0] - T.egs) * (e.tau - tauR_);
+                    double x = kt[0];
+                    for (int r = 0; r < nn; ++r) kt[r] = x * A[r];
+                }
+                tauR_ = e.tau; sst = ns; ns_sst = nn;
+            }
+            if (dead || sst != ec.sstR) continue;
+            const double* ev = &T.evals[T.offset[sst]];
+            double bl = -(ev[0] - T.egs) * (ec.tauR - tauR_), braket = 0.0;
+            for (int c = 0; c < ns_sst; ++c) braket += ec.BR[(size_t)j * dm + c] * std::exp(-(ev[c] - ev[0]) * (ec.tauR - tauR_)) * kt[c];
+            LogVal pt{lg + bl + ec.lgR[j] + std::log(std::fabs(braket)), sgn(braket)};
+            if (braket == 0.0) pt = LogVal{-HUGE_D, 0.0};
+            if (parts) (*parts)[j] = pt;
+            if (pt.sign != 0.0) tot = (tot.sign == 0.0) ? pt : ladd(tot, pt);
+        }
+        return tot;
+    }
+    // trace of a pair-move proposal (operators changed inside the window only)
+    LogVal trace_pair(const std::vector<Op>& o, int outer, std::vector<LogVal>* parts) {
+        if (fast_trace && T.dmax > 1 && num_windows > 1) return trace_windowed(o, outer, parts);
+        return trace_full(o, outer, parts);
     }
 
     // ---------------------------------------------------------- signs: Trace.F90:3479-3618
@@ -417,7 +538,7 @@ struct Chain {
         LogVal DetRat{std::log(std::fabs(S)), sgn(S) * sig};
         LogVal DetNew = lmul(DetRat, Det);
         std::vector<LogVal> parts;
-        LogVal TraceNew = trace_full(nw, outer_sst, &parts);
+        LogVal TraceNew = trace_pair(nw, outer_sst, &parts);
         double rand = grnd();
         int NPairs = count_pairs(nw);
         LogVal trr = ldiv(TraceNew, Trace);
@@ -494,7 +615,7 @@ struct Chain {
         LogVal DetRat{std::log(std::fabs(S)), sgn(S) * sig};
         LogVal DetNew = lmul(DetRat, Det);
         std::vector<LogVal> parts;
-        LogVal TraceNew = trace_full(nw, outer_sst, &parts);
+        LogVal TraceNew = trace_pair(nw, outer_sst, &parts);
         LogVal trr = ldiv(TraceNew, Trace);
         double prob = std::fabs(factor / (double)(2 * nb) * std::exp(trr.log + DetRat.log));
         double rand = grnd();
@@ -578,7 +699,7 @@ struct Chain {
         rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[17] = rand;
         if (rand < prob) {
             ops.swap(nw); M.swap(Mn); kf = kn; outer_sst = new_outer;
-            Det = DetNew; Trace = TraceNew; parttrace = parts;
+            Det = DetNew; Trace = TraceNew; parttrace = parts; ec.valid = false;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccGlob += 1; log_end(1);
         } else log_end(0);
@@ -592,7 +713,7 @@ struct Chain {
         double rand = grnd(), acc = 0; int pick = T.nsst - 1;
         for (int i = 0; i < T.nsst; ++i) { acc += w[i]; pick = i; if (acc >= rand && w[i] != 0.0) break; }
         outer_sst = pick;
-        Trace = trace_full(ops, outer_sst, &parttrace);
+        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false;
         cfgsign = -get_sign(ops, Trace, Det);
         rec[17] = rand;
     }
@@ -644,7 +765,7 @@ struct Chain {
                 if ((k % 2) != 0 && ((w1 + w2) % 2) != 0) detrat = -detrat;
             }
             ops.swap(nw); outer_sst = new_outer;
-            Trace = TraceNew; parttrace = parts; Det.sign *= detrat;
+            Trace = TraceNew; parttrace = parts; Det.sign *= detrat; ec.valid = false;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccShift += 1; log_end(1);
         } else {
@@ -767,7 +888,7 @@ struct Chain {
         double rand = grnd(), acc = 0; int pick = T.nsst - 1;
         for (int i = 0; i < T.nsst; ++i) { acc += w[i]; pick = i; if (acc >= rand && w[i] != 0.0) break; }
         outer_sst = pick;
-        Trace = trace_full(ops, outer_sst, &parttrace);
+        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false;
         cfgsign = -1.0;                              // TTrace default (Trace.F90:129), first computed on the first accepted move
     }
     void set_config(int n, const double* taus, const int* orbs, const int* spins, const int* cas, int osst) {
@@ -775,7 +896,7 @@ struct Chain {
         ops.clear();
         for (int i = 0; i < n; ++i) ops.push_back(Op{taus[i], orbs[i] - 1, spins[i] - 1, cas[i]});
         outer_sst = osst; window_position = 0; set_window_edges();
-        Trace = trace_full(ops, outer_sst, &parttrace);
+        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false;
         Det = build_inverse_all(ops, M, kf);
         cfgsign = -get_sign(ops, Trace, Det);
     }
@@ -853,6 +974,7 @@ unsigned long long orc_rng_counter(void* h) { return ((Chain*)h)->ph.ctr; }
 
 void orc_init_trace(void* h) { ((Chain*)h)->init_trace(); }
 void orc_set_taudiffmax(void* h, double t) { ((Chain*)h)->init_window(t); }
+void orc_set_fast_trace(void* h, int on) { Chain* c = (Chain*)h; c->fast_trace = on != 0; c->ec.valid = false; }
 void orc_init_counters(void* h) { ((Chain*)h)->reset_counters(); }
 void orc_set_log(void* h, double* buf, long long cap) { Chain* c = (Chain*)h; c->logp = buf; c->log_cap = cap; c->log_n = 0; }
 long long orc_log_count(void* h) { return ((Chain*)h)->log_n; }

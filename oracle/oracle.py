@@ -64,8 +64,10 @@ def _p(a, t):
 class OracleChain:
     LOGW = 20
 
-    def __init__(self, problem, rng="philox", seed=43890, chain=0, **qmc_over):
-        """problem: w2dynamics_b200.problems.Problem (inputs only -- no engine code)."""
+    def __init__(self, problem, rng="philox", seed=43890, chain=0, fast_trace=False, **qmc_over):
+        """problem: w2dynamics_b200.problems.Problem (inputs only -- no engine code).
+        fast_trace: windowed local-trace evaluation with cached edge states (the reference's cost structure); used by the timed
+        CPU baseline only -- the checker keeps the from-scratch trace."""
         L = lib()
         from w2dynamics_b200.problems import QMC_DEFAULTS
         q = dict(QMC_DEFAULTS)
@@ -103,6 +105,8 @@ class OracleChain:
         L.orc_init_trace(self.h)
         if q["TaudiffMax"] > 0:
             L.orc_set_taudiffmax(self.h, C.c_double(q["TaudiffMax"]))
+        if fast_trace:
+            L.orc_set_fast_trace(self.h, C.c_int(1))
         self._log = None
 
     def __del__(self):
