@@ -4,9 +4,11 @@
 // (segment=0, offdiag=0, statesampling=0, PercentageOuterMove=0).  Each function
 // cites the reference lines (relative to /root/reference/src/ctqmc_fortran) it
 // follows.  Representation differs from the reference on purpose (time-sorted
-// arrays instead of linked lists, no ket/bra caches: the local trace is always
-// recomputed from tau=0 to beta, which is mathematically identical to the cached
-// evaluation of Trace.F90:5354-6033); the *semantics* -- RNG draw order, proposal
+// arrays instead of linked lists, no ket/bra caches: as a checker the local trace is
+// always recomputed from tau=0 to beta, which is mathematically identical to the cached
+// evaluation of Trace.F90:5354-6033; an opt-in windowed evaluation with cached edge
+// states reproduces the reference's cost structure for the timed CPU baseline only);
+// the *semantics* -- RNG draw order, proposal
 // probabilities, FPos/NPairs/window bookkeeping, signs, measurement formulas --
 // are restated verbatim.
 //
