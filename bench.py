@@ -338,9 +338,12 @@ def run_engine(args):
         mid = gb.shape[-1] // 2
         gm = np.abs(gb.mean(0)[..., mid]).mean()
         sem = (gb.std(0, ddof=1)[..., mid] / np.sqrt(gb.shape[0])).mean()
+        gm_all = np.abs(gb.mean(0)).mean()                      # the same over all tau bins (G(beta/2) is exponentially small for an insulator)
+        sem_all = (gb.std(0, ddof=1) / np.sqrt(gb.shape[0])).mean()
         if gm > 0 and sem > 0:
             tte = {"seconds_to_1e-3_relative": t_sample * (sem / (1e-3 * gm)) ** 2, "sample_seconds": t_sample, "sem_g_beta_half": float(sem),
-                   "g_beta_half": float(gm), "bins": int(gb.shape[0]), "moves": moves}
+                   "g_beta_half": float(gm), "seconds_to_1e-3_relative_tau_average": t_sample * (sem_all / (1e-3 * gm_all)) ** 2,
+                   "sem_g_tau_average": float(sem_all), "g_tau_average": float(gm_all), "bins": int(gb.shape[0]), "moves": moves}
     except Exception as exc:                                    # diagnostic only: never lose the throughput line
         tte = {"error": str(exc)[:200]}
 
