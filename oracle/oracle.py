@@ -221,14 +221,48 @@ class OracleChain:
         r.update(self.counters())
         return r
 
-    def results(self):
-        return normalise(self.raw(), self.at, self.beta)
+    def results(self, want_rho2=False):
+        return normalise(self.raw(), self.at, self.beta, want_rho2)
+
+
+def rho2_estimator(dm_eb, at):
+    """Meas_rho2_from_Densitymatrix (CTQMC.F90:2945-3017), loop for loop:
+    rho2(f4, f3, f2, f1) = sum_k Tr[rho_k  c4^+(n3 -> k)  c3^+(n2 -> n3)  c2(n1 -> n2)  c1(k -> n1)],  f = 2 b + s."""
+    nb, nf = at.nbands, 2 * at.nbands
+    rho2 = np.zeros((nf,) * 4)
+    blocks = [dm_eb[o:o + d, o:o + d] for o, d in zip(at.offset, at.dim)]
+    for b1 in range(nb):
+        for s1 in range(2):
+            for k in range(at.nsst):
+                n1 = at.connect[k, b1, s1, 1]                      # Connect(ib1, is1, 2)
+                if n1 < 0:
+                    continue
+                c1 = at.psis_eb[(k, b1, s1, 2)]
+                for b2 in range(nb):
+                    for s2 in range(2):
+                        n2 = at.connect[n1, b2, s2, 1]             # Connect(ib2, is2, 2)
+                        if n2 < 0:
+                            continue
+                        c21 = at.psis_eb[(n1, b2, s2, 2)] @ c1
+                        for b3 in range(nb):
+                            for s3 in range(2):
+                                n3 = at.connect[n2, b3, s3, 0]     # Connect(ib3, is3, 1)
+                                if n3 < 0:
+                                    continue
+                                c321 = at.psis_eb[(n2, b3, s3, 1)] @ c21
+                                for b4 in range(nb):
+                                    for s4 in range(2):
+                                        if at.connect[n3, b4, s4, 0] != k:
+                                            continue
+                                        t = blocks[k] @ at.psis_eb[(n3, b4, s4, 1)] @ c321
+                                        rho2[2 * b4 + s4, 2 * b3 + s3, 2 * b2 + s2, 2 * b1 + s1] += np.trace(t)
+    return rho2
 
 
 def density_estimators(dm_eb, at):
     """occ / rho1 from the (normalised) eigenbasis density matrix, then EB -> occupation
-    basis (CTQMC.F90:2884-2942, 3020-3060, 3163-3179).  rho2 is left to the product tests
-    (it is checked against the same formula there)."""
+    basis (CTQMC.F90:2884-2942, 3020-3060, 3163-3179); rho2: rho2_estimator above (on request, it is a
+    four-deep flavour loop)."""
     nb = at.nbands
     occ = np.zeros((nb, 2, nb, 2))
     rho1 = np.zeros((2 * nb, 2 * nb))
@@ -257,7 +291,7 @@ def density_estimators(dm_eb, at):
     return occ, rho1, dm_occ
 
 
-def normalise(raw, at, beta):
+def normalise(raw, at, beta, want_rho2=False):
     """ctqmc_measure post-processing (CTQMC.F90:8663-8771)."""
     n = raw["cnt_meas"]
     nb = at.nbands
@@ -274,6 +308,8 @@ def normalise(raw, at, beta):
     occ, rho1, dm_occ = density_estimators(dm, at)
     out["occ"], out["rho1"], out["densitymatrix"] = occ, rho1, dm_occ
     out["densitymatrix_eb"] = dm
+    if want_rho2:
+        out["rho2"] = rho2_estimator(dm, at)
     with np.errstate(divide="ignore", invalid="ignore"):
         out["sign-sst"] = raw["sign_hist"] / raw["outer_hist"]
         out["sign-state"] = raw["signstate_hist"] / raw["outerstate_hist"]

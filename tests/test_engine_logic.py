@@ -74,13 +74,14 @@ def test_config_roundtrip_and_measurement(built):
     eng._ck(eng._load().w2b_finalize())
     orc.measure(0, reset=True)
     orc.measure_once()
-    r = orc.results()
+    r = orc.results(want_rho2=True)
     assert np.abs(eng.gtau - r["gtau"]).max() < 1e-9 * max(1.0, np.abs(r["gtau"]).max())
     assert np.abs(eng.gleg - r["gleg"]).max() < 1e-9 * max(1.0, np.abs(r["gleg"]).max())
     assert np.array_equal(eng.histo, r["hist"])
     assert eng.mean_sign == r["sign"]
     assert np.abs(eng.occ - r["occ"]).max() < 1e-12
     assert np.abs(eng.rho1 - r["rho1"]).max() < 1e-12
+    assert np.abs(eng.rho2 - r["rho2"]).max() < 1e-12                                       # Meas_rho2_from_Densitymatrix CTQMC.F90:2945-3017
     eng.dest_ctqmc()
 
 
@@ -151,8 +152,9 @@ def test_blocked_trace_measurement(built, cfg):
         eng.block(0, True)
         orc.measure_once()
     eng._ck(eng._load().w2b_finalize())
-    r = orc.results()
-    for a, b in ((eng.gtau, r["gtau"]), (eng.gleg, r["gleg"]), (eng.occ, r["occ"]), (eng.rho1, r["rho1"]),
+    r = orc.results(want_rho2=True)
+    assert np.abs(r["rho2"]).max() > 0.1
+    for a, b in ((eng.gtau, r["gtau"]), (eng.gleg, r["gleg"]), (eng.occ, r["occ"]), (eng.rho1, r["rho1"]), (eng.rho2, r["rho2"]),
                  (eng.densitymatrix, r["densitymatrix"]), (eng.outerstatehisto, r["hist-state"]),
                  (eng.tracecontribstates, r["contrib-state"]), (eng.tracecontribsuperstates, r["contrib-sst"])):
         assert np.abs(a - b).max() < 1e-9 * max(1e-3, np.abs(b).max())

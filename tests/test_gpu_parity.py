@@ -57,11 +57,12 @@ def test_measurement_parity(cuda_engine_factory):
     eng._ck(eng._load().w2b_finalize())
     orc.measure(0, reset=True)
     orc.measure_once()
-    r = orc.results()
+    r = orc.results(want_rho2=True)
     assert np.abs(eng.gtau - r["gtau"]).max() < 1e-9 * max(1.0, np.abs(r["gtau"]).max())
     assert np.abs(eng.gleg - r["gleg"]).max() < 1e-9 * max(1.0, np.abs(r["gleg"]).max())
     assert np.array_equal(eng.histo, r["hist"]) and eng.mean_sign == r["sign"]
     assert np.abs(eng.occ - r["occ"]).max() < 1e-12 and np.abs(eng.rho1 - r["rho1"]).max() < 1e-12
+    assert np.abs(eng.rho2 - r["rho2"]).max() < 1e-12                                       # Meas_rho2_from_Densitymatrix CTQMC.F90:2945-3017
     # set_mc_config: LU rebuild on the device reproduces the fast-updated state
     s = eng.debug_chain_scalars(0)
     eng.set_mc_config(n, taus, orbs, spins, cas, hyb, osst, 1, chain=0)
@@ -147,8 +148,9 @@ def test_blocked_trace_measurement(cuda_engine_factory, cfg):
         eng.block(0, True)
         orc.measure_once()
     eng._ck(eng._load().w2b_finalize())
-    r = orc.results()
-    for a, b in ((eng.gtau, r["gtau"]), (eng.gleg, r["gleg"]), (eng.occ, r["occ"]), (eng.rho1, r["rho1"]),
+    r = orc.results(want_rho2=True)
+    assert np.abs(r["rho2"]).max() > 0.1
+    for a, b in ((eng.gtau, r["gtau"]), (eng.gleg, r["gleg"]), (eng.occ, r["occ"]), (eng.rho1, r["rho1"]), (eng.rho2, r["rho2"]),
                  (eng.densitymatrix, r["densitymatrix"]), (eng.outerstatehisto, r["hist-state"]),
                  (eng.tracecontribstates, r["contrib-state"]), (eng.tracecontribsuperstates, r["contrib-sst"])):
         assert np.abs(a - b).max() < 1e-9 * max(1e-3, np.abs(b).max())

@@ -65,10 +65,8 @@ def _install_stubs(engine):
         sys.path.insert(0, REF)
 
 
-@pytest.mark.parametrize("taudiffmax", ["fixed", "calibrate"])
-def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
+def _engine():
     import torch
-    from w2dynamics_b200 import problems
     if torch.cuda.is_available():
         from w2dynamics_b200.CTQMC import MCTQMC
         eng = MCTQMC()
@@ -77,19 +75,80 @@ def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
         eng = _hostemu.make()
     eng.set_option("nchains", 16)
     eng.set_option("nbins", 4)
+    return eng
+
+
+def _c1_inputs(taudiffmax):
+    """C1 problem in the plugin's input conventions + the [QMC] section."""
+    from w2dynamics_b200 import problems
+    p = problems.make_problem("C1", nftau=501)
+    niw = 200
+    qmc = _qmc_defaults()                              # every [QMC] key of the reference, at its default
+    assert qmc["NCorr"] == 100 and qmc["Nftau"] == 5000 and "real_ham_tolerance" in qmc
+    qmc.update(Nwarmups=2000, Nmeas=150, NCorr=50, Ntau=200, NLegMax=40, NLegOrder=40, Niw=niw, Nftau=501,
+               TaudiffMax=p.qmc["TaudiffMax"] if taudiffmax == "fixed" else -1.0,   # -1 (the default): ctqmc_calibrate path
+               AccumGtau=2 if taudiffmax == "fixed" else 1)                           # 2: autocorrelation accumulator -> "gtau-blocks"
+    return p, qmc, niw
+
+
+@pytest.mark.parametrize("taudiffmax", ["fixed", "calibrate"])
+def test_restated_sequence_equals_plugin(built, taudiffmax):
+    """tests/_plugin_sequence.py (what the `-m gpu` boundary tests drive the CUDA library with, /root/reference being absent on the
+    GPU box) issues exactly the calls of the real, unmodified CtHybSolver: same subroutines, same order, same argument values,
+    same module-variable reads and writes."""
+    import _plugin_sequence as ps
+    p, qmc, niw = _c1_inputs(taudiffmax)
+    nb, beta = 1, p.beta
+    # --- the real plugin against a recording proxy
+    rec = ps.Recorder(_engine())
+    _install_stubs(rec)
+    import w2dyn.dmft.cthyb_solver as cs
+    import w2dyn.dmft.impurity as imp
+    import w2dyn.dmft.interaction as inter
+    ftau5 = np.zeros((501, nb, 2, nb, 2))
+    muimp = np.zeros((nb, 2, nb, 2))
+    for s in range(2):
+        ftau5[:, 0, s, 0, s] = p.ftau[0, s, 0, s]
+        muimp[0, s, 0, s] = p.mu
+    screening = np.zeros((501, nb, 2, nb, 2))
+    interaction = inter.Density(nb, 2.0, 0.0, 0.0)
+    interaction.quantum_numbers = ("auto",) + interaction.auto_quantum_numbers
+    problem = imp.ImpurityProblem(beta, np.zeros((niw, nb, 2, nb, 2), complex), np.zeros((niw, nb, 2, nb, 2), complex), screening, ftau5, muimp, interaction)
+    config = {"QMC": qmc, "General": {"FTType": "legendre", "beta": beta}, "Atoms": {"1": {"Nd": nb}}}
+    solver = cs.CtHybSolver(config, 43890, 0, 0, 0, interactive=False, mpi_comm=_Comm())
+    solver.set_problem(problem)
+    cfg_a = []
+    res_a = solver.solve(0, cfg_a)
+    # --- the restatement against a recording proxy around a fresh engine
+    rec2 = ps.Recorder(_engine())
+    seq = ps.PluginSequence(rec2, qmc, 43890, interactive=False)
+    seq.set_problem("Density", beta, nb, " ".join(interaction.auto_quantum_numbers), interaction.u_matrix, ftau5, muimp, screening)
+    cfg_b = []
+    res_b = seq.solve(0, cfg_b)
+    a = [e for e in rec.log if e[1] != "shape"]
+    b = [e for e in rec2.log if e[1] != "shape"]
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert x == y, "call %d differs:\n  plugin      %r\n  restatement %r" % (i, x, y)
+    assert len(a) == len(b)
+    # same engine, same seed, same calls -> same numbers
+    assert np.array_equal(res_a.other["gtau"].mean(), res_b["gtau"]) and np.array_equal(res_a.other["occ"].mean(), res_b["occ"])
+    assert np.array_equal(cfg_a[0].taus, cfg_b[0].taus)
+    for k in ("w2dyn.auxiliaries.CTQMC", "w2dyn.dmft.cthyb_solver"):
+        sys.modules.pop(k, None)
+
+
+@pytest.mark.parametrize("taudiffmax", ["fixed", "calibrate"])
+def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
+    from w2dynamics_b200 import problems
+    eng = _engine()
     _install_stubs(eng)
     import w2dyn.dmft.cthyb_solver as cs
     import w2dyn.dmft.impurity as imp
     import w2dyn.dmft.interaction as inter
     import w2dyn.auxiliaries.transform as tf
 
-    p = problems.make_problem("C1", nftau=501)
-    nb, beta, niw = 1, p.beta, 200
-    qmc = _qmc_defaults()                              # every [QMC] key of the reference, at its default
-    assert qmc["NCorr"] == 100 and qmc["Nftau"] == 5000 and "real_ham_tolerance" in qmc
-    qmc.update(Nwarmups=2000, Nmeas=150, NCorr=50, Ntau=200, NLegMax=40, NLegOrder=40, Niw=niw, Nftau=501,
-               TaudiffMax=p.qmc["TaudiffMax"] if taudiffmax == "fixed" else -1.0,   # -1 (the default): ctqmc_calibrate path
-               AccumGtau=2 if taudiffmax == "fixed" else 1)                           # 2: autocorrelation accumulator -> "gtau-blocks"
+    p, qmc, niw = _c1_inputs(taudiffmax)
+    nb, beta = 1, p.beta
     config = {"QMC": qmc, "General": {"FTType": "legendre", "beta": beta}, "Atoms": {"1": {"Nd": nb}}}
     iw = tf.matfreq(beta, "fermi", niw)
     tau = np.linspace(0, beta, 501)
