@@ -75,7 +75,7 @@ constexpr int MAX_CTA_THREADS = 1024;
 #if W2B_DEVICE
 __host__ __device__
 #endif
-inline int mat_doubles(const Chains& C, bool second) { return C.dmax > 1 ? C.xdoubles + 4 * C.dmax + (second ? C.mstride : 0) : 0; }
+inline int mat_doubles(const Chains& C, bool second) { return C.dmax > 1 ? C.xdoubles + 3 * mat_cols(C.dmax) + MAT_DMAX + (second ? C.mstride : 0) : 0; }
 
 #if W2B_DEVICE
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_init(Tables T, Run R, Chains C) {
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T_, Run R_
         phase_rare(T, R, C, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
 }
 // trace phase of one round (blocked traces): operator products of every surviving proposal on the FP64 tensor pipe
-__global__ void __launch_bounds__(TRACE_WARPS * 32, TRACE_NT == 1 ? 8 : 6) k_trace(Tables T, Chains C, int tdoubles, int parity) {
+__global__ void __launch_bounds__(TRACE_WARPS * 32, 6) k_trace(Tables T, Chains C, int tdoubles, int parity) {
     extern __shared__ double smem[];
     double* ws = smem + (size_t)(threadIdx.x >> 5) * tdoubles;
     int* sc = C.sched + parity * SC_STRIDE;
@@ -206,12 +206,12 @@ __global__ void __launch_bounds__(256) k_autocorr_add(const double* acc, long lo
     autocorr_add_one(val, n, nlevels, dat + (size_t)bin * nlevels * 3 * ncomp, ncomp, comp);
 }
 // measurement pre-pass (blocked traces): extend every chain's cache frontiers to tau = beta/2, one job per 8 outer states
-__global__ void __launch_bounds__(TRACE_WARPS * 32, TRACE_NT == 1 ? 8 : 6) k_meas_extend(Tables T, Chains C, int tdoubles) {
+__global__ void __launch_bounds__(TRACE_WARPS * 32, 6) k_meas_extend(Tables T, Chains C, int tdoubles) {
     extern __shared__ double smem[];
     double* ws = smem + (size_t)(threadIdx.x >> 5) * tdoubles;
     const int njobs = C.nchains * 4;
     for (int t = blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5); t < njobs; t += gridDim.x * TRACE_WARPS)
-        trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws, ws + C.ldx * TRACE_COLS, ws + C.ldx * TRACE_COLS + TRACE_COLS);
+        trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws);
 }
 // measurement: grid = nbins x nsub CTAs; CTA (bin, sub) serves every nsub-th chain of its bin and keeps the Legendre
 // accumulator of the bin in shared memory (one flush per CTA instead of nf * NLegMax same-address atomics per chain)
@@ -372,7 +372,7 @@ public:
         C.rng_ctr = keep(dev_alloc<unsigned long long>(nc)); C.counters = keep(dev_alloc<unsigned long long>((size_t)nc * C_NCNT));
         C.dmax = at.dmax; C.mstride = at.dmax > 1 ? at.dmax * at.dmax : 0;
         if (at.dmax > MAT_DMAX) throw std::runtime_error("quantum-number blocks larger than 32 are not supported by the tensor trace path (add quantum numbers)");
-        C.ldx = mat_ld(at.dmax); C.xdoubles = at.dmax > 1 ? C.ldx * at.dmax : 0;
+        C.ldx = mat_ld(at.dmax); C.xdoubles = at.dmax > 1 ? C.ldx * mat_cols(at.dmax) : 0;
         if (at.dmax > 1) {
             C.op_slot = keep(dev_alloc<unsigned short>((size_t)nc * ops_cap)); C.free_slot = keep(dev_alloc<unsigned short>((size_t)nc * ops_cap));
             C.ket = keep(dev_alloc<double>((size_t)nc * ops_cap * C.mstride)); C.bra = keep(dev_alloc<double>((size_t)nc * ops_cap * C.mstride));
@@ -611,7 +611,7 @@ public:
         W2B_CUDA_CHECK(cudaFuncSetAttribute(k_rare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem));
         rp_grid = std::max(1, std::min(nsm, C.nchains / (8 * DECIDE_WARPS) + 1));
         if (C.dmax > 1) {
-            tr_doubles = C.ldx * TRACE_COLS + TRACE_COLS + MAT_DMAX;
+            tr_doubles = trace_ws_doubles(C.ldx);
             tr_smem = (size_t)TRACE_WARPS * tr_doubles * sizeof(double);
             W2B_CUDA_CHECK(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
             W2B_CUDA_CHECK(cudaFuncSetAttribute(k_meas_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
@@ -724,7 +724,7 @@ public:
 #else
         std::vector<double> ws(wdoubles + 8);
         if (C.dmax > 1 && R.meas_dm) {
-            for (int t = 0; t < C.nchains * 4; ++t) trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws.data(), ws.data() + C.ldx * TRACE_COLS, ws.data() + C.ldx * TRACE_COLS + TRACE_COLS);
+            for (int t = 0; t < C.nchains * 4; ++t) trace_job(T, C, (t >> 2) | ((t & 3) << Q_NTSHIFT) | Q_MEAS, ws.data());
             C.meas_pre = 1;
         }
         for (int c = 0; c < C.nchains; ++c) measure_chain(T, R, C, A, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);

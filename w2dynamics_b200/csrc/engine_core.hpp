@@ -96,11 +96,7 @@ enum { ST_RUN = 0, ST_RARE_NEW = 1, ST_RARE_TRACE = 3, ST_RARE_QUEUED = 4, ST_RA
 constexpr int Q_MEAS = 1 << 28;      // trace-queue entry of a measurement: extend both cache frontiers to tau = beta/2, no trace
 constexpr int Q_RARE = 1 << 29;      // trace-queue entry of a global move / tau shift (whole sequence, no caches)
 constexpr int Q_REM = 1 << 30;       // decide-queue entry = chain id | Q_REM for a removal
-#ifndef W2B_TRACE_NT
-#define W2B_TRACE_NT 1
-#endif
-constexpr int TRACE_NT = W2B_TRACE_NT;   // DMMA column tiles per trace job
-constexpr int TRACE_COLS = 8 * TRACE_NT; // outer states (columns) per trace job
+constexpr int TRACE_COLS = TILE_COLS;    // outer states (columns) per trace job = one DMMA column tile
 constexpr int Q_NTSHIFT = 26;         // trace-queue entry: + column tile << Q_NTSHIFT
 constexpr int Q_IDMASK = (1 << 26) - 1;
 
@@ -349,7 +345,7 @@ W2B_HDN bool extend_kets(const Tables& T, const Chains& C, Ctx& x, int upto) {
     else {
         sst = (int)x.sst[i - 1]; tprev = x.tau[i - 1];
         const int d = ldg(&T.dim[sst]);
-        mat_move(X, ld, ket_slot(C, x, i - 1), d, d, m);
+        mat_load_padded(X, ld, ket_slot(C, x, i - 1), d, m);
         mat_copy(x.mlg, x.ketlg + (size_t)x.slot[i - 1] * C.dmax, m);
         wsync();
     }
@@ -375,7 +371,7 @@ W2B_HDN void extend_bras(const Tables& T, const Chains& C, Ctx& x, int downto) {
     else {
         tnext = x.tau[i];
         const int d = ldg(&T.dim[sst_before(x, i)]);
-        mat_move(X, ld, bra_slot(C, x, i), d, d, m);
+        mat_load_padded(X, ld, bra_slot(C, x, i), d, m);
         mat_copy(x.mlg, x.bralg + (size_t)x.slot[i] * C.dmax, m);
         wsync();
     }
@@ -409,49 +405,76 @@ W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsign
 // operator product is the only code in the loop and the per-step global-memory latency is paid once per 32 steps.
 // Writes the per-outer-state parts (log, sign) of the proposed configuration to C.ptc; the decide kernel sums them and
 // moves the frontiers (kv = max(kv, s), bv = min(bv, e)).
-W2B_HDN void load_tile(const Tables& T, const Chains& C, double* X, double* lg, const double* slot_mat, const double* slot_lg, int sst, int j0, int mw) {
-    if (slot_mat) {
-        const int d = ldg(&T.dim[sst]);
-        mat_move(X, C.ldx, slot_mat + j0 * d, d, d, mw);
-        for (int j = lane_id(); j < mw; j += W2B_WARP) lg[j] = slot_lg[j0 + j];
-    } else {                                                    // identity: columns j0 .. j0+mw-1 of I_m (m = dim of sst)
-        const int m = ldg(&T.dim[sst]);
-        for (int j = 0; j < mw; ++j) for (int r = lane_id(); r < m; r += W2B_WARP) X[r + j * C.ldx] = (r == j0 + j) ? 1.0 : 0.0;
-        for (int j = lane_id(); j < mw; j += W2B_WARP) lg[j] = 0.0;
-    }
-    wsync();
+// per-warp work space of a trace job in doubles: tile (ldx x 8) + 8 log scales + 32 propagation factors
+#if W2B_DEVICE
+__host__ __device__
+#endif
+inline int trace_ws_doubles(int ldx) { return ldx * TILE_COLS + TILE_COLS + MAT_DMAX; }
+#if !W2B_DEVICE
+struct Tile { double* X; double* lg; double* pw; int ld; };                                // host emulation: same interface on plain loops
+template <class TablesT> inline int tile_apply(const TablesT& T, int sst_in, int opc, double dt, const Tile& w, int mw, double* slot, double* slot_lg, int j0, int* work) {
+    return mat_apply_slot(T, sst_in, opc, dt, w.X, w.ld, w.lg, w.pw, mw, slot, slot_lg, j0, work);
 }
-W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, double* lg, double* pw) {
+inline void tile_load(const Tile& w, const double* src, const double* src_lg, int d, int j0, int mw) {
+    for (int j = 0; j < mw; ++j) for (int r = 0; r < d; ++r) w.X[r + j * w.ld] = src ? src[r + j * d] : (r == j0 + j ? 1.0 : 0.0);
+    for (int j = 0; j < mw; ++j) w.lg[j] = src ? src_lg[j] : 0.0;
+}
+template <class TablesT> inline void tile_close(const TablesT& T, int sst, double dt, const Tile& w, const double* B, const double* blg, int mw, int j0, double* pt) {
+    mat_close_parts(T, sst, dt, w.X, w.ld, w.lg, B, blg, w.pw, mw, j0, pt);
+}
+#endif
+// frontier tile of a chain: columns j0.. of KET_{i} (i >= 0) / BRA_{i} (i < n) or of the identity at the chain's ends
+struct JobView {
+    const double* tau; const unsigned char* code; const short* sst; const unsigned short* slot;
+    double* ket; double* bra; double* ketlg; double* bralg;
+    int n, outer, mstride, dmax;
+};
+W2B_HD void job_load_ket(const Tables& T, const JobView& V, const Tile& w, int i, int j0, int mw) {      // KET_i, i = -1: identity
+    if (i < 0) { tile_load(w, nullptr, nullptr, ldg(&T.dim[V.outer]), j0, mw); return; }
+    const int d = ldg(&T.dim[(int)V.sst[i]]);
+    const size_t sl = V.slot[i];
+    tile_load(w, V.ket + sl * V.mstride + j0 * d, V.ketlg + sl * V.dmax + j0, d, j0, mw);
+}
+W2B_HD void job_load_bra(const Tables& T, const JobView& V, const Tile& w, int i, int j0, int mw) {      // BRA_i, i = n: identity
+    if (i >= V.n) { tile_load(w, nullptr, nullptr, ldg(&T.dim[V.outer]), j0, mw); return; }
+    const int d = ldg(&T.dim[i == 0 ? V.outer : (int)V.sst[i - 1]]);
+    const size_t sl = V.slot[i];
+    tile_load(w, V.bra + sl * V.mstride + j0 * d, V.bralg + sl * V.dmax + j0, d, j0, mw);
+}
+W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* ws) {
     const int lane = lane_id();
+    const Tile w{ws, ws + C.ldx * TILE_COLS, ws + C.ldx * TILE_COLS + TILE_COLS, C.ldx};
     const int chain = entry & Q_IDMASK, nt = (entry >> Q_NTSHIFT) & 3;
-    const bool rem = (entry & Q_REM) != 0;
+    const bool rem = (entry & Q_REM) != 0, rare = (entry & Q_RARE) != 0, meas = (entry & Q_MEAS) != 0;
     const int* ih = C.ih + (size_t)chain * IH_STRIDE;
-    const double* tau = C.op_tau + (size_t)chain * C.ops_cap; const unsigned char* code = C.op_code + (size_t)chain * C.ops_cap;
-    const short* sst = C.op_sst + (size_t)chain * C.ops_cap; const unsigned short* slot = C.op_slot + (size_t)chain * C.ops_cap;
-    double* ket = C.ket + (size_t)chain * C.ops_cap * C.mstride; double* bra = C.bra + (size_t)chain * C.ops_cap * C.mstride;
-    double* ketlg = C.ketlg + (size_t)chain * C.ops_cap * C.dmax; double* bralg = C.bralg + (size_t)chain * C.ops_cap * C.dmax;
-    const bool rare = (entry & Q_RARE) != 0, meas = (entry & Q_MEAS) != 0;
-    const int n = ih[IH_NOPS];
-    int outer = ih[IH_OUTER], kv = ih[IH_KV], bv = ih[IH_BV];
+    const size_t cb = (size_t)chain * C.ops_cap;
+    JobView V;
+    V.tau = C.op_tau + cb; V.code = C.op_code + cb; V.sst = C.op_sst + cb; V.slot = C.op_slot + cb;
+    V.ket = C.ket + cb * C.mstride; V.bra = C.bra + cb * C.mstride; V.ketlg = C.ketlg + cb * C.dmax; V.bralg = C.bralg + cb * C.dmax;
+    V.n = ih[IH_NOPS]; V.outer = ih[IH_OUTER]; V.mstride = C.mstride; V.dmax = C.dmax;
+    const int n = V.n;
+    int kv = ih[IH_KV], bv = ih[IH_BV];
     const Prop& P = C.prop[chain];
     int i1 = P.i1, i2 = P.i2;
     bool store_seg = false;
     if (meas) {                                                   // kets of the operators with tau <= beta/2, bras of the others (update_b2_states_eb)
-        if (n == 0 || nt * TRACE_COLS >= ldg(&T.dim[outer])) return;
-        i1 = i2 = count_le(tau, n, T.beta / 2.0);
+        if (n == 0 || nt * TILE_COLS >= ldg(&T.dim[V.outer])) return;
+        i1 = i2 = count_le(V.tau, n, T.beta / 2.0);
     }
     if (rare) {                                                   // whole (relabelled / shifted) sequence from the identity, no caches used
         const RareJob& J = C.rjob[chain];
-        outer = J.new_outer; kv = 0; bv = n; i1 = 0; i2 = n;
-        code = C.sc_code + (size_t)chain * C.ops_cap;
-        if (J.kind == 4) tau = C.sc_tau + (size_t)chain * C.ops_cap;
+        V.outer = J.new_outer; kv = 0; bv = n; i1 = 0; i2 = n;
+        V.code = C.sc_code + cb;
+        if (J.kind == 4) V.tau = C.sc_tau + cb;
         store_seg = J.stored != 0;
     }
+    const double* tau = V.tau; const unsigned char* code = V.code; const short* sst = V.sst; const unsigned short* slot = V.slot;
+    const int outer = V.outer;
     const int s = i1, e = (rem && !rare) ? i2 + 1 : i2, lo = (rem && !rare) ? i1 + 1 : i1, hi = i2, nA = (rem || rare || meas) ? 0 : 1;
     const double tA = P.t1, tB = P.t2;
     const int codeA = P.f * 2 + P.type1, codeB = P.f * 2 + (1 - P.type1);
-    const int m = ldg(&T.dim[outer]), ld = C.ldx;
-    const int j0 = nt * TRACE_COLS, mw = m - j0 < TRACE_COLS ? m - j0 : TRACE_COLS;        // this job's columns
+    const int m = ldg(&T.dim[outer]);
+    const int j0 = nt * TILE_COLS, mw = m - j0 < TILE_COLS ? m - j0 : TILE_COLS;          // this job's columns
     const int nb = bv > e ? bv - e : 0, nk = kv <= s - 1 ? s - kv : 0, ns = nA + (hi - lo) + nA;
     const int total = nb + nk + ns;
     int cur = -1;                        // block of the work matrix (rows)
@@ -485,40 +508,27 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* X, do
         const int opc = wbcast(r_opc, src), sin = wbcast(r_sst, src), sl = wbcast(r_slot, src);
         const double dt = wbcast(r_dt, src);
         // phase starts: load the frontier tile (or identity columns) into the work matrix
-        if (j == 0 && nb > 0) {
-            if (bv == n) load_tile(T, C, X, lg, nullptr, nullptr, outer, j0, mw);
-            else load_tile(T, C, X, lg, bra + (size_t)slot[bv] * C.mstride, bralg + (size_t)slot[bv] * C.dmax, (int)sst[bv - 1], j0, mw);
-        } else if (j == nb && nk > 0) {
-            cur = kv == 0 ? outer : (int)sst[kv - 1];
-            if (kv == 0) load_tile(T, C, X, lg, nullptr, nullptr, outer, j0, mw);
-            else load_tile(T, C, X, lg, ket + (size_t)slot[kv - 1] * C.mstride, ketlg + (size_t)slot[kv - 1] * C.dmax, cur, j0, mw);
-        } else if (j == nb + nk && nk == 0) {
-            cur = s == 0 ? outer : (int)sst[s - 1];
-            if (s == 0) load_tile(T, C, X, lg, nullptr, nullptr, outer, j0, mw);
-            else load_tile(T, C, X, lg, ket + (size_t)slot[s - 1] * C.mstride, ketlg + (size_t)slot[s - 1] * C.dmax, cur, j0, mw);
-        }
+        if (j == 0 && nb > 0) job_load_bra(T, V, w, bv, j0, mw);
+        else if (j == nb && nk > 0) { cur = kv == 0 ? outer : (int)sst[kv - 1]; job_load_ket(T, V, w, kv - 1, j0, mw); }
+        else if (j == nb + nk && nk == 0) { cur = s == 0 ? outer : (int)sst[s - 1]; job_load_ket(T, V, w, s - 1, j0, mw); }
         const int in = sin >= 0 ? sin : cur;
         double* dst = nullptr; double* dlg = nullptr;
         if (sl >= 0) {                                          // this job's columns of the operator's cache slot are filled by the product's epilogue
-            dst = ((sl >> 16) == 1 ? ket : bra) + (size_t)(sl & 0xffff) * C.mstride;
-            dlg = ((sl >> 16) == 1 ? ketlg : bralg) + (size_t)(sl & 0xffff) * C.dmax + j0;
+            dst = ((sl >> 16) == 1 ? V.ket : V.bra) + (size_t)(sl & 0xffff) * C.mstride;
+            dlg = ((sl >> 16) == 1 ? V.ketlg : V.bralg) + (size_t)(sl & 0xffff) * C.dmax + j0;
         }
-        cur = mat_apply_inl<TRACE_NT>(T, in, opc, dt, X, ld, lg, pw, mw, dst, dlg, j0, &work);
+        cur = tile_apply(T, in, opc, dt, w, mw, dst, dlg, j0, &work);
     }
     if (meas) return;
-    if (ns == 0 && nk == 0) {                                   // nothing applied after the ket frontier: work matrix = KET_{s-1}
-        cur = s == 0 ? outer : (int)sst[s - 1];
-        if (s == 0) load_tile(T, C, X, lg, nullptr, nullptr, outer, j0, mw);
-        else load_tile(T, C, X, lg, ket + (size_t)slot[s - 1] * C.mstride, ketlg + (size_t)slot[s - 1] * C.dmax, cur, j0, mw);
-    }
+    if (ns == 0 && nk == 0) { cur = s == 0 ? outer : (int)sst[s - 1]; job_load_ket(T, V, w, s - 1, j0, mw); }   // nothing applied after the ket frontier: tile = KET_{s-1}
     const double tlast = ns > 0 ? (nA ? tB : tau[hi - 1]) : (s == 0 ? 0.0 : tau[s - 1]);
     double* pt = C.ptc + (size_t)chain * 2 * C.dmax + 2 * j0;
     const double* B = nullptr; const double* blg = nullptr; double tend = T.beta;         // e == n: unit bras at tau = beta
     if (e != n) {
         const int d = ldg(&T.dim[cur]);
-        B = bra + (size_t)slot[e] * C.mstride + j0 * d; blg = bralg + (size_t)slot[e] * C.dmax + j0; tend = tau[e];
+        B = V.bra + (size_t)slot[e] * C.mstride + j0 * d; blg = V.bralg + (size_t)slot[e] * C.dmax + j0; tend = tau[e];
     }
-    mat_close_parts(T, cur, tend - tlast, X, ld, lg, B, blg, pw, mw, j0, pt);
+    tile_close(T, cur, tend - tlast, w, B, blg, mw, j0, pt);
     if (lane == 0 && work) atomic_add(&C.counters[(size_t)chain * C_NCNT + C_TRFLOPS], 2ull * (unsigned long long)work * (unsigned long long)mw);   // per-chain counter: no hot address
 }
 
@@ -1223,7 +1233,7 @@ W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain,
         x.ket = C.ket + (size_t)chain * C.ops_cap * C.mstride; x.bra = C.bra + (size_t)chain * C.ops_cap * C.mstride;
         x.ketlg = C.ketlg + (size_t)chain * C.ops_cap * C.dmax; x.bralg = C.bralg + (size_t)chain * C.ops_cap * C.dmax;
         x.pt = C.pt + (size_t)chain * 2 * C.dmax;
-        x.ldx = C.ldx; x.mX = mscratch; x.mlg = mscratch + C.xdoubles; x.mpt = x.mlg + C.dmax; x.mpw = x.mpt + 2 * C.dmax; x.mY = x.mpw + C.dmax;
+        x.ldx = C.ldx; x.mX = mscratch; x.mlg = mscratch + C.xdoubles; x.mpt = x.mlg + mat_cols(C.dmax); x.mpw = x.mpt + 2 * mat_cols(C.dmax); x.mY = x.mpw + MAT_DMAX;
         x.kv = x.ih[IH_KV]; x.bv = x.ih[IH_BV]; x.nfree = x.ih[IH_NFREE];
     }
     x.n = x.ih[IH_NOPS]; x.outer = x.ih[IH_OUTER]; x.wpos = x.ih[IH_WPOS]; x.npairs = x.ih[IH_NPAIRS];
@@ -1523,7 +1533,7 @@ W2B_HD void phase_trace(const Tables& T, const Chains& C, int ticket, int parity
     const size_t qo = (size_t)parity * 4 * C.nchains;
     const int n0 = sc[SC_NT0], n1 = sc[SC_NT1];
     const int entry = ticket < n0 ? C.q_tr0[qo + ticket] : (ticket < n0 + n1 ? C.q_tr1[qo + ticket - n0] : C.q_tr2[qo + ticket - n0 - n1]);
-    trace_job(T, C, entry, mscratch, mscratch + C.ldx * TRACE_COLS, mscratch + C.ldx * TRACE_COLS + TRACE_COLS);
+    trace_job(T, C, entry, mscratch);
 }
 
 // Global moves / tau shifts (1 % of the moves, 10-1000x the cost of a pair move) run on their own stream beside the round
@@ -1660,9 +1670,9 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     const double e0 = ldg(&ev[0]);
     const double tauR = ih == 0 ? 0.0 : x.tau[ih - 1], tauL = ih == x.n ? T.beta : x.tau[ih];
     double* K = x.mX; double* B = x.mY; double* klg = x.mlg; double* blg = x.mpt; double* fac = x.mpt + C.dmax;
-    if (ih == 0) mat_identity(K, m, klg, m);
+    if (ih == 0) mat_identity_compact(K, klg, m);
     else { mat_copy(K, ket_slot(C, x, ih - 1), d * m); mat_copy(klg, x.ketlg + (size_t)x.slot[ih - 1] * C.dmax, m); }
-    if (ih == x.n) mat_identity(B, m, blg, m);
+    if (ih == x.n) mat_identity_compact(B, blg, m);
     else { mat_copy(B, bra_slot(C, x, ih), d * m); mat_copy(blg, x.bralg + (size_t)x.slot[ih] * C.dmax, m); }
     wsync();
     for (int e = lane_id(); e < d * m; e += W2B_WARP) {
