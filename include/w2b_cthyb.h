@@ -62,13 +62,29 @@ int w2b_set_empty_mc_config(int chain, int outer_sst, int outer_state);
  * gtau_blocks (Nb,2,Ntau,levels) when AccumGtau = 2 (autocorracc, Accumulators.F90:214-364; CTQMC.F90:8733-8739) ;
  * additionally per-bin samples gtau_bins gleg_bins occ_bins sign_bins (leading extents as the quantity, last = bin). */
 int w2b_get_array(const char* name, double* out, size_t cap, size_t* n);
-/* scalars: mean_sign accglob accshift accadd4 accrem4 accflavc time_warmup time_sim time_sim_steps aborted
+/* scalars: mean_sign accglob accshift accadd4 accrem4 accflavc time_warmup time_sim time_sim_steps
+ * aborted (0, or after SIGTERM / SIGINT / SIGUSR1 during sampling: 1 = stopped with some measurements, 2 = with none; the traps are armed by
+ *          init_solver and restored by dest_ctqmc -- register_trap CTQMC.F90:8076-8078, polls 8214 / 8430, truncation 8648-8658)
  * and engine diagnostics nchains nbins nsst nstates nstatesmax kcap max_k max_ops moves_per_chain gpu_launches */
 int w2b_get_scalar(const char* name, double* out);
 
+/* ---- rank combination: replaces the per-quantity mpi4py Allreduce of DistributedSample (w2dyn/auxiliaries/statistics.py:95-132)
+ * and the one-chain-per-MPI-rank layout (cthyb:144, cthyb_solver.py:319-320).  One process per GPU; chains shard over ranks by
+ * global chain id; ctqmc_measure ends with ONE ncclAllReduce(sum, f64) of the raw accumulator slab over NVLink / NVSwitch (plus a
+ * 2-int max of error / abort flags), after which every rank normalises and holds the population result.
+ * Protocol: rank 0 calls w2b_comm_unique_id (128 bytes), the HOST broadcasts those bytes by its own means (MPI_Bcast from a Fortran
+ * or mpi4py host; torch.distributed in bench.py), every rank calls w2b_comm_init(id, 128, rank, nranks) before w2b_init_solver. */
+int w2b_comm_unique_id(void* out, size_t cap, size_t* n);
+int w2b_comm_init(const void* unique_id, size_t nbytes, int rank, int nranks);
+int w2b_comm_destroy(void);
+/* the all-reduce by itself (w2b_ctqmc_measure calls it; exposed for the split form w2b_sample / w2b_finalize below) */
+int w2b_allreduce_accum(void);
+
 /* ---- engine controls without a reference counterpart ---- */
 /* keys: nchains nbins kcap ops_cap chain_base device nmeas_override propose_run scheduler (1x1 blocks: 0/1 = persistent CTA
- * scheduler kernel, 2 = round kernels) ; must be set before w2b_init_solver.  time_kernels (0/1: CUDA events around the round
+ * scheduler kernel, 2 = round kernels) reuse_population (1: dest_ctqmc parks the chain population and the static tables; the next
+ * init_solver of a bit-identical local problem revives them, uploads the new F(tau) and rebuilds every chain's inverse matrices /
+ * trace / signs on the device -- ReuseMCConfig (cthyb_solver.py:328-345) for the whole population) ; must be set before w2b_init_solver.  time_kernels (0/1: CUDA events around the round
  * kernels, read back through w2b_get_scalar ms_propose / ms_trace / ms_decide) may be switched at any time. */
 int w2b_set_option(const char* key, double value);
 /* split form of ctqmc_measure for multi-GPU runs: sample, all-reduce the raw accumulators yourself
@@ -76,6 +92,8 @@ int w2b_set_option(const char* key, double value);
 int w2b_sample(long long nmeas, int reset_accumulators);
 int w2b_accum_device(void** dev_ptr, size_t* n_doubles);
 int w2b_finalize(void);
+/* the signal handler itself: a host that owns the process's signal handling forwards SIGTERM / SIGINT / SIGUSR1 here */
+void w2b_trap_notify(int sig);
 /* one accumulation block: `nsweep` moves per chain followed by one measurement (bench / profiling hook) */
 int w2b_block(long long nsweep, int do_measure);
 int w2b_sync(void);

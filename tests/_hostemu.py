@@ -21,6 +21,32 @@ def build():
     return LIB
 
 
+_HOOKS = []          # keep the ctypes callbacks alive
+
+
 def make():
+    """An MCTQMC object on the host-emulation library.  The product class knows nothing about it: the collective the CUDA library
+    performs with NCCL is replaced here, through the test-only symbol w2b_test_set_allreduce_hook, by a torch.distributed (gloo)
+    all-reduce of the host accumulator slab."""
+    import ctypes as C
+    import numpy as np
     from w2dynamics_b200.CTQMC import MCTQMC
-    return MCTQMC(libpath=build(), device_kind="host-emu")
+
+    class HostEmuMCTQMC(MCTQMC):
+        def enable_distributed(self, group=None):
+            import torch
+            import torch.distributed as dist
+            rank, size = dist.get_rank(group), dist.get_world_size(group)
+
+            def hook(buf, n, flags):
+                t = torch.from_numpy(np.ctypeslib.as_array(buf, shape=(n,)))
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                f = torch.tensor([flags[0], flags[1]], dtype=torch.int32)
+                dist.all_reduce(f, op=dist.ReduceOp.MAX, group=group)
+                flags[0], flags[1] = int(f[0]), int(f[1])
+            cb = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_int))(hook)
+            _HOOKS.append(cb)
+            self._load().w2b_test_set_allreduce_hook(cb)
+            self.comm_init(b"\0" * 128, rank, size)
+
+    return HostEmuMCTQMC(libpath=build())

@@ -1,0 +1,215 @@
+"""Boundary behaviour of the mctqmc surface beyond the happy path, on the host-emulation build (CPU) and -- same bodies, `-m gpu` --
+on the CUDA library through the C ABI:
+  * successive init_solver calls after ONE init_rnd draw fresh random numbers (the reference seeds once in CtHybSolver.__init__ and
+    lets the generator run on, cthyb_solver.py:113), a new init_rnd reproduces the first solve;
+  * `aborted` (register_trap CTQMC.F90:8076-8078, polls 8214 / 8430, truncation 8648-8658): 2 = signal before the first
+    measurement, 1 = some measurements done, results normalised over those;
+  * reuse_population: dest_ctqmc parks the population, the next init_solver revives it and rebuilds every chain from its operator
+    list with the NEW hybridisation function (ReuseMCConfig for all chains, cthyb_solver.py:328-345 / Trace.F90:6872-7000);
+  * index / range validation of the configuration entry points."""
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from w2dynamics_b200 import problems
+
+
+def _hostemu_engine():
+    import _hostemu
+    return _hostemu.make()
+
+
+def _cuda_engine():
+    from w2dynamics_b200.CTQMC import MCTQMC
+    e = MCTQMC()
+    e.set_option("device", 0)
+    return e
+
+
+def _start(eng, p, nchains=8, nbins=4, seed=43890, init_rnd=True, **opts):
+    eng.set_option("nchains", nchains)
+    eng.set_option("nbins", nbins)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    if init_rnd:
+        eng.init_rnd(seed)
+    eng.init_paras(p.pstring())
+    eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)
+    eng.set_taudiffmax(p.qmc["TaudiffMax"])
+    return eng
+
+
+def body_fresh_streams(make):
+    p = problems.make_problem("C1", nftau=501, Nmeas=20, Ntau=50, NLegMax=10)
+    eng = make()
+    res = []
+    for i, rnd in enumerate([True, False, False, True]):
+        _start(eng, p, init_rnd=rnd)
+        eng.ctqmc_warmup(300)
+        eng.ctqmc_measure(1, 1)
+        res.append(eng.gtau.copy())
+        eng.dest_ctqmc()
+    assert not np.array_equal(res[0], res[1]) and not np.array_equal(res[1], res[2]) and not np.array_equal(res[0], res[2])
+    assert np.array_equal(res[0], res[3])                       # init_rnd restarts the streams: replay tests stay reproducible
+
+
+def body_aborted(make):
+    p = problems.make_problem("C1", nftau=501, Nmeas=100000, Ntau=50, NLegMax=10)
+    eng = _start(make(), p)
+    L = eng._load()
+    L.w2b_trap_notify.restype = None
+    eng.ctqmc_warmup(200)
+    assert int(eng.aborted) == 0
+    L.w2b_trap_notify(10)                                       # SIGUSR1 before the first measurement
+    eng.ctqmc_measure(1, 1)
+    assert int(eng.aborted) == 2                                # cthyb_solver.py:347: the plugin raises KeyboardInterrupt
+    eng.dest_ctqmc()
+    # signal while sampling: the run stops between two measurements, the measurements taken so far are normalised
+    eng = _start(make(), p)
+    L = eng._load()
+    eng.ctqmc_warmup(200)
+    t = threading.Timer(0.5, lambda: L.w2b_trap_notify(15))
+    t.start()
+    t0 = time.time()
+    eng.ctqmc_measure(1, 1)                                     # Nmeas = 100000 would take far longer than the timer
+    t.join()
+    assert int(eng.aborted) == 1 and 0 < eng.scalar("nmeas_done") < 100000 and time.time() - t0 < 120
+    assert np.all(np.isfinite(eng.gtau)) and abs(eng.occ[0, 0, 0, 0] - 0.5) < 0.2 and float(eng.mean_sign) == -1.0
+    eng.dest_ctqmc()
+    # a real signal takes the same route: the traps are armed between init_solver and dest_ctqmc
+    import os, signal
+    eng = _start(make(), p)
+    os.kill(os.getpid(), signal.SIGUSR1)
+    eng.ctqmc_measure(1, 1)
+    assert int(eng.aborted) == 2
+    eng.dest_ctqmc()
+    eng = _start(make(), problems.make_problem("C1", nftau=501, Nmeas=3, Ntau=50, NLegMax=10))
+    eng.ctqmc_measure(1, 1)
+    assert int(eng.aborted) == 0                                # the flag does not outlive the solve
+    eng.dest_ctqmc()
+
+
+def body_reuse_population(make, cfg):
+    p = problems.make_problem(cfg, nftau=501, Nmeas=5, Ntau=50, NLegMax=10)
+    eng = _start(make(), p, reuse_population=1)
+    eng.ctqmc_warmup(1500)
+    eng.ctqmc_measure(1, 1)
+    before = [eng.get_mc_config(eng.get_mc_config_scalars(c)[0], c) if eng.get_mc_config_scalars(c)[0] else None for c in range(8)]
+    assert any(b is not None for b in before)
+    eng.dest_ctqmc()
+    # next "DMFT iteration": same local problem, new hybridisation function
+    p2 = problems.make_problem(cfg, nftau=501, Nmeas=5, Ntau=50, NLegMax=10)
+    p2.ftau = p.ftau * 1.07
+    _start(eng, p2, init_rnd=False, reuse_population=1)
+    for c in range(8):
+        n, osst, _ = eng.get_mc_config_scalars(c)
+        if before[c] is None:
+            assert n == 0
+            continue
+        now = eng.get_mc_config(n, c)
+        assert n == before[c][0].size and np.array_equal(now[0], before[c][0]) and np.array_equal(now[1], before[c][1])
+        # revived state == a from-scratch set_mc_config with the new F(tau)
+        s = eng.debug_chain_scalars(c)
+        eng.set_mc_config(n, *now[:5], osst, 1, chain=c)
+        s2 = eng.debug_chain_scalars(c)
+        assert s["error"] == 0 and s2["error"] == 0 and s["cfgsign"] == s2["cfgsign"]
+        assert abs(s["det_log"] - s2["det_log"]) < 1e-9 and abs(s["trace_log"] - s2["trace_log"]) < 1e-9
+    eng.ctqmc_warmup(0)
+    eng.ctqmc_measure(1, 1)
+    assert np.all(np.isfinite(eng.gtau)) and eng.scalar("error_flags") == 0
+    eng.dest_ctqmc()
+    # a different local problem is never revived
+    p3 = problems.make_problem(cfg, nftau=501, Nmeas=5, Ntau=50, NLegMax=10)
+    p3.muimp = p.muimp * 1.01
+    _start(eng, p3, init_rnd=False, reuse_population=1)
+    assert all(eng.get_mc_config_scalars(c)[0] == 0 for c in range(8))
+    eng.set_option("reuse_population", 0)
+    eng.dest_ctqmc()
+
+
+def body_validation(make):
+    p = problems.make_problem("C2", nftau=501)
+    eng = _start(make(), p)
+    with pytest.raises(RuntimeError, match="chain index"):
+        eng.get_mc_config_scalars(8)
+    with pytest.raises(RuntimeError, match="chain index"):
+        eng.debug_chain_scalars(-1)
+    t, o, s, ca, h = np.array([0.5, 1.0]), np.array([1, 1]), np.array([1, 1]), np.array([1, 2]), np.array([-1, -1])
+    with pytest.raises(RuntimeError, match="outer superstate"):
+        eng.set_mc_config(2, t, o, s, ca, h, 99, 1)
+    with pytest.raises(RuntimeError, match="orbital"):
+        eng.set_mc_config(2, t, np.array([3, 1]), s, ca, h, 0, 1)
+    with pytest.raises(RuntimeError, match="tau outside"):
+        eng.set_mc_config(2, np.array([0.5, 50.0]), o, s, ca, h, 0, 1)
+    with pytest.raises(RuntimeError, match="ascending"):
+        eng.set_mc_config(2, t[::-1].copy(), o, s, ca, h, 0, 1)
+    eng.dest_ctqmc()
+
+
+def body_calibrate_list(make):
+    """ctqmc_calibrate phase 1 (CTQMC.F90:8118-8163, 3583-3586): `accpairtau` lists the tau distance of each of the first
+    phase1pairnum accepted pair moves -- actual distances, not histogram bin edges."""
+    p = problems.make_problem("C1", nftau=501, Ntau=50)
+    eng = _start(make(), p)
+    eng.set_taudiffmax(-1.0)
+    eng.init_counters()
+    eng.ctqmc_calibrate(True, 1000, 100, 1000, 100000)
+    lst = eng.accpairtau
+    assert lst.shape == (1000,) and np.all(lst > 0.0) and np.all(lst < p.beta)
+    frac = np.abs(lst / (p.beta / 50) - np.rint(lst / (p.beta / 50)))
+    assert (frac > 1e-6).mean() > 0.99 and len(np.unique(lst)) > 500          # a removal of a pair listed at its insertion repeats the distance
+    q = np.sort(lst)[995]
+    assert 0.2 * p.beta < q <= p.beta                             # the caller's 99.5 % quantile (cthyb_solver.py:906-909)
+    eng.dest_ctqmc()
+
+
+# ------------------------------------------------------------------ CPU (host-emulation build of the same sources)
+def test_calibrate_phase1_list(built):
+    body_calibrate_list(_hostemu_engine)
+
+
+
+def test_fresh_streams_per_solve(built):
+    body_fresh_streams(_hostemu_engine)
+
+
+def test_aborted_flag(built):
+    body_aborted(_hostemu_engine)
+
+
+@pytest.mark.parametrize("cfg", ["C2", "C3"])
+def test_reuse_population(built, cfg):
+    body_reuse_population(_hostemu_engine, cfg)
+
+
+def test_argument_validation(built):
+    body_validation(_hostemu_engine)
+
+
+# ------------------------------------------------------------------ GPU (CUDA library through the C ABI)
+@pytest.mark.gpu
+def test_gpu_fresh_streams_per_solve(built):
+    body_fresh_streams(_cuda_engine)
+
+
+@pytest.mark.gpu
+def test_gpu_aborted_flag(built):
+    body_aborted(_cuda_engine)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["C2", "C4"])
+def test_gpu_reuse_population(built, cfg):
+    body_reuse_population(_cuda_engine, cfg)
+
+
+@pytest.mark.gpu
+def test_gpu_calibrate_phase1_list(built):
+    body_calibrate_list(_cuda_engine)
+
+
+@pytest.mark.gpu
+def test_gpu_argument_validation(built):
+    body_validation(_cuda_engine)

@@ -196,14 +196,16 @@ def test_round_scheduler_on_scalar_blocks(built, cfg, nsteps, chain):
 
 
 def test_capacity_overflow_is_loud(built):
-    """A chain that outgrows its operator capacity raises a flag (never silent truncation) and ctqmc_measure refuses to hand
-    out results -- the counterpart of the reference's hard `stop`s."""
+    """A chain that outgrows its operator capacity raises a flag (never silent truncation); the warm-up that hit the limit fails
+    right away (not after the whole run) and ctqmc_measure refuses to hand out results -- the counterpart of the reference's hard
+    `stop`s."""
     p = problems.make_problem("C2", nftau=2001, Nmeas=5)
     eng = _hostemu.make()
     eng.set_option("nchains", 2); eng.set_option("nbins", 1); eng.set_option("ops_cap", 32)
     eng.init_rnd(43890); eng.init_paras(p.pstring()); eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)
     eng.set_taudiffmax(p.qmc["TaudiffMax"]); eng.init_counters()
-    eng.ctqmc_warmup(20000)
+    with pytest.raises(RuntimeError, match="capacity exceeded during warm-up"):
+        eng.ctqmc_warmup(20000)
     assert int(eng.scalar("error_flags")) & 1
     with pytest.raises(RuntimeError, match="capacity"):
         eng.ctqmc_measure(1, 1)

@@ -14,9 +14,11 @@ routes the Z-space CT-HYB hot path (everything between ``ctqmc.init_solver`` and
 (Fortran order) as the f2py module; where the reference ``stop``s, this raises RuntimeError.
 
 One process drives one GPU and a population of ``nchains`` Markov chains (the reference:
-one chain per MPI rank).  Under ``torch.distributed`` (one process per GPU, NCCL) call
-``mctqmc.enable_distributed()`` once: chains are sharded over ranks and the raw
-accumulators are combined with a single all-reduce per ``ctqmc_measure``.
+one chain per MPI rank).  With one process per GPU call ``mctqmc.enable_distributed()``
+once (under ``torch.distributed``), or ``mctqmc.comm_init(unique_id, rank, nranks)`` with
+an id obtained from ``mctqmc.comm_unique_id()`` on rank 0 and broadcast by any means
+(mpi4py ``bcast``): chains are sharded over ranks and the raw accumulators are combined
+inside the library with a single ``ncclAllReduce`` per ``ctqmc_measure``.
 
 There is no CPU fallback: the CUDA library must be present and a GPU visible.
 """
@@ -29,13 +31,6 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIB = os.path.join(_HERE, "libw2b_cthyb.so")
-
-
-class _CudaArrayView:
-    """Minimal __cuda_array_interface__ holder so torch can alias the engine's accumulator slab."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
 
 class MCTQMC:
@@ -70,9 +65,8 @@ class MCTQMC:
                 "time_warmup", "time_sim", "time_sim_steps", "aborted")
     _INT_ARRAYS = ("statessuperstates", "occbasismapping", "accpair")
 
-    def __init__(self, libpath=CUDA_LIB, device_kind="cuda"):
+    def __init__(self, libpath=CUDA_LIB):
         self._libpath = libpath
-        self._kind = device_kind
         self._lib = None
         self._dims = None
         self._dist = None
@@ -111,13 +105,31 @@ class MCTQMC:
         if key == "nbins":
             self._nbins = int(value)
 
+    def comm_unique_id(self):
+        """Rank 0: the NCCL unique id (bytes) every rank must pass to comm_init."""
+        n = C.c_size_t()
+        buf = C.create_string_buffer(256)
+        self._ck(self._load().w2b_comm_unique_id(buf, C.c_size_t(256), C.byref(n)))
+        return buf.raw[:n.value]
+
+    def comm_init(self, unique_id, rank, nranks):
+        """Collective: join the library's communicator (before init_solver).  Chains shard over ranks by global chain id and every
+        ctqmc_measure ends with one all-reduce of the raw accumulators inside the library."""
+        if "device" in self._options:
+            self._ck(self._load().w2b_set_option(b"device", C.c_double(float(self._options["device"]))))
+        self._ck(self._load().w2b_comm_init(unique_id, C.c_size_t(len(unique_id)), C.c_int(int(rank)), C.c_int(int(nranks))))
+        self._dist = (int(rank), int(nranks))
+        self.simid = int(rank)
+
     def enable_distributed(self, group=None):
-        """Shard chains over torch.distributed ranks; accumulators are all-reduced once per ctqmc_measure."""
+        """torch.distributed convenience: broadcast rank 0's unique id over the process group, then comm_init."""
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
-        self._dist = (dist, group)
-        self.simid = dist.get_rank(group)
+        rank, size = dist.get_rank(group), dist.get_world_size(group)
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.comm_init(box[0], rank, size)
 
     # ------------------------------------------------------------------ the mctqmc subroutines
     def init_rnd(self, nseed):
@@ -139,13 +151,10 @@ class MCTQMC:
         # the library is a process-wide singleton like the reference's module: every engine states ALL its options, so that
         # nothing set through another MCTQMC object lingers
         opts = {"kcap": 0, "ops_cap": 0, "cta_warps": 0, "batch_chains": 0, "scheduler": 0, "chain_base": 0, "propose_run": 4,
-                "prefetch": 1, "debug_same_key": 0, "time_kernels": 0}
+                "prefetch": 1, "debug_same_key": 0, "time_kernels": 0, "reuse_population": 0}
         opts.update(self._options)
         opts.setdefault("nchains", self._nchains)
         opts.setdefault("nbins", self._nbins)
-        if self._dist is not None:
-            dist, group = self._dist
-            opts["chain_base"] = dist.get_rank(group) * int(opts["nchains"])
         for k, v in opts.items():
             self._ck(L.w2b_set_option(k.encode(), C.c_double(float(v))))
         dp = C.POINTER(C.c_double)
@@ -173,29 +182,11 @@ class MCTQMC:
         self._cache = {}
         if isector != 1:
             raise RuntimeError("w2b_cthyb: only the partition-function sector (isector = 1) is implemented")
-        if self._dist is None:
-            self._ck(L.w2b_ctqmc_measure(C.c_int(isector), C.c_int(icomponent)))
-            return
-        nmeas = int(self._param("Nmeas"))
-        self._ck(L.w2b_sample(C.c_longlong(nmeas), C.c_int(1)))
-        self.allreduce_accumulators()
-        self._ck(L.w2b_finalize())
+        self._ck(L.w2b_ctqmc_measure(C.c_int(isector), C.c_int(icomponent)))      # ends with the library's own all-reduce when a communicator exists
 
     def allreduce_accumulators(self):
-        """One all-reduce(sum) of the raw accumulator slab over all ranks (NCCL over NVLink on the GPU box)."""
-        import torch
-        dist, group = self._dist
-        ptr, n = C.c_void_p(), C.c_size_t()
-        self._ck(self._load().w2b_accum_device(C.byref(ptr), C.byref(n)))
-        self._ck(self._load().w2b_sync())
-        if self._kind == "cuda":
-            t = torch.as_tensor(_CudaArrayView(ptr.value, n.value), device="cuda")
-        else:  # host-emulation library used by the CPU logic tests (gloo)
-            buf = (C.c_double * n.value).from_address(ptr.value)
-            t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        if self._kind == "cuda":
-            torch.cuda.synchronize()
+        """The all-reduce by itself (split form w2b_sample / w2b_allreduce_accum / w2b_finalize; bench.py)."""
+        self._ck(self._load().w2b_allreduce_accum())
 
     def dest_ctqmc(self):
         self._ck(self._load().w2b_dest_ctqmc())

@@ -194,6 +194,18 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, 6) k_trace(Tables T, Chains 
     for (int t0 = wgrab_n(&sc[SC_TTICKET], TICKET_BATCH); t0 < total; t0 = wgrab_n(&sc[SC_TTICKET], TICKET_BATCH))
         for (int t = t0; t < t0 + TICKET_BATCH && t < total; ++t) phase_trace(T, C, t, parity, ws);
 }
+// population health in three integers: OR of the chains' error flags, largest operator count, largest flavour order
+__global__ void __launch_bounds__(256) k_flags(Chains C, int nf, int* out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int e = 0, mo = 0, mk = 0;
+    if (c < C.nchains) {
+        const int* ih = C.ih + (size_t)c * IH_STRIDE;
+        e = ih[IH_ERR]; mo = ih[IH_NOPS];
+        for (int f = 0; f < nf; ++f) mk = max(mk, ih[IH_KF + f]);
+    }
+    for (int o = 16; o > 0; o >>= 1) { e |= __shfl_xor_sync(W2B_FULL, e, o); mo = max(mo, __shfl_xor_sync(W2B_FULL, mo, o)); mk = max(mk, __shfl_xor_sync(W2B_FULL, mk, o)); }
+    if ((threadIdx.x & 31) == 0) { if (e) atomicOr(&out[0], e); atomicMax(&out[1], mo); atomicMax(&out[2], mk); }
+}
 // autocorrelation accumulator: one thread per (bin, component)
 __global__ void __launch_bounds__(256) k_autocorr_add(const double* acc, long long stride, int o_gtau, int ncomp, int nbins, int nlevels, long long n,
                                                      const double* inv_group, double* prev, double* dat) {
@@ -284,6 +296,7 @@ public:
 #endif
         }
         owned.clear();
+        d_flags = nullptr; ac_prev = ac_dat = ac_invg = nullptr; ac_levels = 0;
         release_host();
     }
     template <class T_> T_* keep(T_* p) { owned.push_back((void*)p); return p; }
@@ -404,6 +417,8 @@ public:
         accpair_cap = std::max(R.ntau, 1024);
         A.accpair = keep(dev_alloc<unsigned long long>((size_t)nf * accpair_cap));
         R.naccpair = R.ntau; R.accpair_max = beta; R.freeze_window = 0;
+        pairlist_alloc = 4096;
+        A.pairlist = keep(dev_alloc<double>(pairlist_alloc)); A.pairlist_cnt = keep(dev_alloc<int>(1)); A.pairlist_cap = 0;
         init_chains();
     }
 
@@ -443,6 +458,14 @@ public:
         if (n > accpair_cap) throw std::runtime_error("accepted-pair histogram: too many bins");
         R.naccpair = n; R.accpair_max = range; dev_zero(A.accpair, (size_t)T.nf * accpair_cap);
     }
+    // list of the tau distances of the first `n` accepted pair moves (ctqmc_calibrate phase 1); n = 0 switches it off
+    int pairlist_alloc = 0;
+    void pairlist_begin(int n) {
+        if (n > pairlist_alloc) { A.pairlist = keep(dev_alloc<double>(n)); pairlist_alloc = n; }
+        dev_zero(A.pairlist_cnt, 1); A.pairlist_cap = n;
+    }
+    int pairlist_count() { sync(); int c = 0; d2h(&c, A.pairlist_cnt, 1); return c; }
+    void pairlist_get(std::vector<double>& out, int n) { sync(); out.resize(n); d2h(out.data(), A.pairlist, n); }
     void get_accpair(std::vector<unsigned long long>& out) { sync(); out.resize((size_t)T.nf * R.naccpair); d2h(out.data(), A.accpair, out.size()); }
     void zero_accum() { dev_zero(A.base, (size_t)R.nbins * accum_doubles); autocorr_reset(); }
 
@@ -569,6 +592,7 @@ public:
 #if W2B_DEVICE
     cudaStream_t rare_stream = nullptr; cudaEvent_t ev_prop[2] = {nullptr, nullptr}, ev_rare[2] = {nullptr, nullptr};
 #endif
+    size_t smem_cfg_measure = 0, smem_cfg_rebuild = 0;    // dynamic shared memory the measure / rebuild kernels are opted in for (this engine's device)
     int tr_doubles = 0, tr_grid = 1, rp_grid = 1; size_t tr_smem = 0;   // trace kernel: per-warp work space, grid, shared memory
     long long rounds = 0;              // rounds launched so far (bench accounting)
     bool time_kernels = false;         // bench: CUDA events around every round kernel (on the launching stream)
@@ -588,7 +612,7 @@ public:
 #else
         if (h_sched) { std::free(h_sched); h_sched = nullptr; }
 #endif
-        sw_ready = false; ct_ready = false;
+        sw_ready = false; ct_ready = false; smem_cfg_measure = smem_cfg_rebuild = 0;      // the opt-in is per device: redo after a device change
     }
     void plan_sweep() {
 #if W2B_DEVICE
@@ -706,8 +730,7 @@ public:
     void measure() {
 #if W2B_DEVICE
         size_t sm = smem_bytes() + (size_t)WARPS_PER_CTA * T.nf * R.nlegmax * sizeof(double);
-        static size_t configured = 0;
-        if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_measure, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+        if (sm > 48 * 1024 && sm > smem_cfg_measure) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_measure, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); smem_cfg_measure = sm; }
         int dev = 0, nsm = 1;
         W2B_CUDA_CHECK(cudaGetDevice(&dev));
         W2B_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -735,8 +758,7 @@ public:
     void rebuild(int only_chain = -1) {
 #if W2B_DEVICE
         size_t sm = smem_bytes();
-        static size_t configured = 0;
-        if (sm > 48 * 1024 && sm > configured) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+        if (sm > 48 * 1024 && sm > smem_cfg_rebuild) { W2B_CUDA_CHECK(cudaFuncSetAttribute(k_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); smem_cfg_rebuild = sm; }
         k_rebuild<<<grid(), WARPS_PER_CTA * 32, sm>>>(T, R, C, wdoubles, mat_doubles(C, true), only_chain); ++launches;
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
@@ -786,7 +808,20 @@ public:
         out.assign(C_NCNT, 0ull);
         for (int c = 0; c < C.nchains; ++c) for (int i = 0; i < C_NCNT; ++i) out[i] += all[(size_t)c * C_NCNT + i];
     }
+    int* d_flags = nullptr;
+    int forced_err = 0;                        // error flags of other ranks (w2b_allreduce_accum)
+    void force_error(int e) { forced_err |= e; }
+    int* flag_scratch() { if (!d_flags) d_flags = keep(dev_alloc<int>(4)); return d_flags; }
     int error_flags(int* max_k = nullptr, int* max_ops = nullptr) {
+#if W2B_DEVICE
+        if (!d_flags) d_flags = keep(dev_alloc<int>(4));
+        dev_zero(d_flags, 4);
+        k_flags<<<(C.nchains + 255) / 256, 256>>>(C, T.nf, d_flags); ++launches;
+        int h[4]; d2h(h, d_flags, 4);                         // synchronises
+        if (max_k) *max_k = h[2];
+        if (max_ops) *max_ops = h[1];
+        return h[0] | forced_err;
+#endif
         sync();
         std::vector<int> ih((size_t)C.nchains * IH_STRIDE);
         d2h(ih.data(), C.ih, ih.size());
@@ -798,7 +833,7 @@ public:
         }
         if (max_k) *max_k = mk;
         if (max_ops) *max_ops = mo;
-        return e;
+        return e | forced_err;
     }
     double mean_order() {                       // <k_f> averaged over chains and flavours
         sync();

@@ -74,7 +74,9 @@ struct Run {
     int propose_run;             // consecutive early-exit moves one chain may take inside one propose phase
     int prefetch;                // software prefetch of the next work item's records (0 = off)
     int same_key;                // diagnostics only: every chain uses chain 0's RNG key (identical control flow across warps)
+    unsigned stream;             // solves since init_rnd: every init_solver draws from a fresh section of each chain's Philox stream
 };
+constexpr int STREAM_SHIFT = 44;     // draws per chain and solve before two solves could overlap: 2^44
 
 // a proposal that survived the quantum-number check travels from the propose kernel to the decide kernel in this record
 struct Prop {
@@ -130,6 +132,7 @@ struct Accum {
     int o_gtau, o_gleg, o_histo, o_dens, o_outer, o_signsst, o_contribsst, o_outerst, o_signst, o_contribst, o_sign, o_cnt;
     unsigned long long* accpair;     // [nf][ntau]
     int ndens;
+    double* pairlist; int* pairlist_cnt; int pairlist_cap;      // AccPairTau of ctqmc_calibrate phase 1 (CTQMC.F90:3583-3586, 4123-4126): tau distances of the first accepted pair moves
 };
 
 struct Ctx {
@@ -763,6 +766,7 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     if (lane_id() == 0) {
         int bin = (int)floor((t2 - t1) / R.accpair_max * (double)R.naccpair) + 1; if (bin > R.naccpair) bin = R.naccpair;   // CTQMC.F90:3579-3582
         atomic_add(&A.accpair[(size_t)f * R.naccpair + bin - 1], 1ull);
+        if (A.pairlist_cap > 0) { const int i = atomic_add_int(A.pairlist_cnt, 1); if (i < A.pairlist_cap) A.pairlist[i] = t2 - t1; }
     }
     log_end(x, 1);
 }
@@ -891,6 +895,7 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     if (lane_id() == 0) {
         int bin = (int)floor((t2 - t1) / R.accpair_max * (double)R.naccpair) + 1; if (bin > R.naccpair) bin = R.naccpair;   // CTQMC.F90:3579-3582
         atomic_add(&A.accpair[(size_t)f * R.naccpair + bin - 1], 1ull);
+        if (A.pairlist_cap > 0) { const int i = atomic_add_int(A.pairlist_cnt, 1); if (i < A.pairlist_cap) A.pairlist[i] = t2 - t1; }
     }
     log_end(x, 1);
 }
@@ -1617,7 +1622,9 @@ W2B_HD void autocorr_add_one(double val, long long n, int nlevels, double* dat, 
 W2B_HD void init_chain(const Tables& T, const Run& R, const Chains& C, int chain) {
     if (lane_id() != 0) return;
     int* ih = C.ih + (size_t)chain * IH_STRIDE; double* dh = C.dh + (size_t)chain * DH_STRIDE;
-    Philox rng; rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, 0ull);
+    // the reference seeds once (CtHybSolver.__init__ -> init_rnd -> sgrnd) and lets the generator run on across init_solver calls:
+    // solve number `stream` since init_rnd starts at counter stream << 44 of the chain's stream (0 for the first solve)
+    Philox rng; rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, (unsigned long long)R.stream << STREAM_SHIFT);
     const double rand = rng.next();
     double acc = 0.0; int pick = T.nsst - 1;
     for (int i = 0; i < T.nsst; ++i) { double w = T.empty_w[i]; acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
