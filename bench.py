@@ -11,8 +11,11 @@ accepted or not (CTQMC.F90:8428-8434).  value = chains * NCorr * K * N / time.
 
 Timed region of `value`: chain state resident in HBM, K steps, (N > 1: plus the single all-reduce of the raw
 accumulators that ends an accumulation), CUDA events on the launching stream, max over ranks.
-`e2e`: same steps through the C ABI with HOST buffers: every step uploads the hybridisation function from pinned
-host memory (what a DMFT iteration hands to init_solver) and copies the accumulator slab back to the host.
+`e2e`: the same K accumulation blocks through the reference plugin's call sequence (w2dynamics_b200/solver_sequence.py) with
+HOST arrays: every step is one full solve -- init_paras, init_solver(u, F(tau), mu from host memory), set_taudiffmax,
+ctqmc_warmup(0), ctqmc_measure(1,1) with Nmeas = 1, every get_resultset array read back to the host, dest_ctqmc.  The chain
+population is kept thermalised across solves (option reuse_population = ReuseMCConfig for all chains): a revived population is
+rebuilt on the device from its operator lists with the new F(tau).
 `roofline`: dominant kernel k_sweep, algorithmic bytes counted in-kernel per move (DESIGN.md "Roofline accounting")
 divided by the kernel's summed event time.  `cpu_baseline`: the oracle (CPU restatement of the reference algorithm;
 the Fortran reference cannot be built in this image) on all host cores, bounded sample.
@@ -115,10 +118,10 @@ class OraclePopulation:
     Chains differ ~30x in cost per move on C4 (outer block of 1 vs 28 states), so each host thread owns several chains, times
     each one on its own for a slice, and the figure is  threads x chains / sum_i(seconds per move of chain i)  -- the
     equal-moves throughput of the population, not a time-weighted average that favours the cheap chains.
-    The chains run the oracle's windowed trace evaluation (cached edge states outside the sliding window, oracle/chain.cpp
-    `trace_windowed`): the reference's cost structure rather than the checker's from-scratch trace."""
+    The chains run the oracle's per-operator ket / bra caches (oracle/chain.cpp `trace_cached`: the reference's cost structure,
+    Trace.F90:47-49, 5384-5470, 6109-6209); the library is compiled on this host with -O3 -march=native."""
 
-    def __init__(self, cfg, nthreads, chains_per_thread=4):
+    def __init__(self, cfg, nthreads, chains_per_thread=8):
         from w2dynamics_b200 import problems
         from oracle.oracle import OracleChain
         from oracle import oracle as orc
@@ -126,7 +129,7 @@ class OraclePopulation:
         self.p = problems.make_problem(cfg)
         self.ncorr = int(self.p.qmc.get("NCorr", 100))
         self.nthreads, self.cpt, self.therm = nthreads, chains_per_thread, THERMALISE[cfg]
-        self.chains = [OracleChain(self.p, rng="philox", seed=43890, chain=1000 + i, fast_trace=True) for i in range(nthreads * chains_per_thread)]
+        self.chains = [OracleChain(self.p, rng="philox", seed=43890, chain=1000 + i, fast_trace=2) for i in range(nthreads * chains_per_thread)]
         self._threads(lambda t: [self.chains[t * self.cpt + j].warmup(self.therm) for j in range(self.cpt)])
         self.reset()
 
@@ -137,6 +140,9 @@ class OraclePopulation:
     def reset(self):
         self.moves = [0] * len(self.chains)
         self.busy = [0.0] * len(self.chains)
+        self.wall = 0.0
+        for c in self.chains:
+            c.measure(0, reset=True)
 
     def run(self, seconds):
         """Every thread gives each of its chains seconds / chains_per_thread of sweeps + measurements."""
@@ -151,34 +157,60 @@ class OraclePopulation:
                     if now >= stop:
                         break
                 self.busy[i] += now - t0
+        t0 = time.perf_counter()
         self._threads(work)
+        self.wall += time.perf_counter() - t0
 
     def rate(self):
-        per_move = [b / m for b, m in zip(self.busy, self.moves) if m > 0]
-        return self.nthreads * len(per_move) / sum(per_move)
+        """(equal-moves moves/s of the population, its standard error from the chain-to-chain scatter of the cost per move)"""
+        import numpy as np
+        c = np.array([b / m for b, m in zip(self.busy, self.moves) if m > 0])
+        r = self.nthreads / c.mean()
+        return r, r * c.std(ddof=1) / np.sqrt(len(c)) / c.mean()
+
+    def time_to_error(self):
+        """CPU counterpart of the engine's time_to_error: SEM of G(tau) over the chains of this run -> wall seconds to 1e-3."""
+        import numpy as np
+        g = np.array([c.results()["gtau"] for c, m in zip(self.chains, self.moves) if m > 0])
+        mid = g.shape[-1] // 2
+        gm, sem = np.abs(g.mean(0)[..., mid]).mean(), (g.std(0, ddof=1)[..., mid] / np.sqrt(g.shape[0])).mean()
+        gma, sema = np.abs(g.mean(0)).mean(), (g.std(0, ddof=1) / np.sqrt(g.shape[0])).mean()
+        if not (gm > 0 and sem > 0):
+            return None
+        return {"seconds_to_1e-3_relative": self.wall * (sem / (1e-3 * gm)) ** 2, "seconds_to_1e-3_relative_tau_average": self.wall * (sema / (1e-3 * gma)) ** 2,
+                "sample_seconds": self.wall, "chains": int(g.shape[0]), "moves": int(sum(self.moves))}
 
     def sample(self):
         tw = sum(self.moves) / (sum(self.busy) / self.nthreads)
-        return ("%d chains on %d host threads, %.1f s each of NCorr=%d sweeps + measurements (%d moves), thermalised %d moves; equal-moves "
-                "throughput (time-weighted average would be %.3g moves/s)" % (len(self.chains), self.nthreads, sum(self.busy) / len(self.chains),
-                                                                            self.ncorr, sum(self.moves), self.therm, tw))
+        return ("%d chains on %d host threads (%d per thread), %.1f s each of NCorr=%d sweeps + measurements (%d moves), thermalised %d moves; "
+                "per-operator trace caches, g++ -O3 -march=native on this host; equal-moves throughput (time-weighted average would be %.3g moves/s)"
+                % (len(self.chains), self.nthreads, self.cpt, sum(self.busy) / len(self.chains), self.ncorr, sum(self.moves), self.therm, tw))
 
 
-def cpu_oracle_rate(cfg, seconds, nthreads):
-    """Oracle (CPU restatement) on `nthreads` host threads; returns moves/s and a note."""
+def host_cores():
+    """(physical cores, hardware threads) of this host"""
+    try:
+        import psutil
+        return psutil.cpu_count(logical=False) or os.cpu_count() or 1, os.cpu_count() or 1
+    except Exception:
+        return os.cpu_count() or 1, os.cpu_count() or 1
+
+
+def cpu_baseline(cfg, seconds):
+    cores, nthreads = host_cores()
     pop = OraclePopulation(cfg, nthreads)
     pop.run(seconds)
-    return pop.rate(), pop.sample()
+    v, se = pop.rate()
+    return {"value": v, "stderr": se, "unit": UNIT, "cores": cores, "threads": nthreads, "kind": "port", "sample": pop.sample(), "time_to_error": pop.time_to_error()}
 
 
-def run_reference(args):
+def run_reference(args, cfg):
     """Reference arm: the reference's own CPU algorithm for the path.  The Fortran module cannot be built in this
     image (no Fortran compiler), so this is the oracle port on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = args.config
-    nthreads = os.cpu_count() or 1
+    cores, nthreads = host_cores()
     pop = OraclePopulation(cfg, nthreads)
     slice_s = args.slice_seconds if args.slice_seconds > 0 else min(60.0 / max(1, args.steps + args.warmup), 10.0)     # one step = one slice; whole run ~ a minute
     for _ in range(args.warmup):
@@ -188,20 +220,23 @@ def run_reference(args):
     for _ in range(args.steps):
         pop.run(slice_s)
     dt = time.time() - t0
-    val = pop.rate()
+    val, se = pop.rate()
     sample = pop.sample()
     ncorr = pop.ncorr
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[cfg], "ncorr": ncorr, "note": "oracle port of the reference algorithm (Fortran reference not buildable here); the port keeps cached edge states outside the sliding window and re-evaluates the window per proposal (the reference's cost structure; its per-operator caches inside the window are not restated)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOADS[cfg], "ncorr": ncorr, "note": "oracle port of the reference algorithm (Fortran reference not buildable here), compiled -O3 -march=native on this host; per-operator ket / bra caches with two frontiers = the reference's cost structure (Trace.F90:47-49, 5384-5470, 6109-6209)"},
+        "cpu_baseline": {"value": val, "stderr": se, "unit": UNIT, "cores": cores, "threads": nthreads, "kind": "port", "sample": sample, "time_to_error": pop.time_to_error()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
-def run_engine(args):
+_DIST = {}
+
+
+def run_engine(args, cfg):
     import ctypes as C
     import numpy as np
     import torch
@@ -213,7 +248,7 @@ def run_engine(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     import torch.distributed as dist
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         g.build()
@@ -221,30 +256,41 @@ def run_engine(args):
         dist.barrier()
     from w2dynamics_b200 import problems
     from w2dynamics_b200.CTQMC import MCTQMC
+    from w2dynamics_b200.solver_sequence import PluginSequence, qmc_defaults
 
-    cfg = args.config
     p = problems.make_problem(cfg)
     ncorr = int(p.qmc.get("NCorr", 100))
     nchains = args.chains or DEFAULT_CHAINS[cfg]
+    therm = args.thermalise if args.thermalise >= 0 else THERMALISE[cfg]
     eng = MCTQMC()
     eng.set_option("nchains", nchains); eng.set_option("nbins", 32); eng.set_option("device", local)
-    if os.environ.get("W2B_CTA_WARPS"):
-        eng.set_option("cta_warps", int(os.environ["W2B_CTA_WARPS"]))
-    if os.environ.get("W2B_OPS_CAP"):
-        eng.set_option("ops_cap", int(os.environ["W2B_OPS_CAP"]))
-    if os.environ.get("W2B_SCHEDULER"):
-        eng.set_option("scheduler", int(os.environ["W2B_SCHEDULER"]))
-    if os.environ.get("W2B_BATCH_CHAINS"):
-        eng.set_option("batch_chains", int(os.environ["W2B_BATCH_CHAINS"]))
-    if world > 1:
-        eng.enable_distributed()
-    eng.init_rnd(43890)
-    eng.init_paras(p.pstring())
-    eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)
-    eng.set_taudiffmax(p.qmc["TaudiffMax"])
+    eng.set_option("reuse_population", 1)      # dest_ctqmc parks the thermalised population; the next init_solver revives it (ReuseMCConfig for all chains)
+    for key in ("cta_warps", "ops_cap", "scheduler", "batch_chains"):
+        if os.environ.get("W2B_" + key.upper()):
+            eng.set_option(key, int(os.environ["W2B_" + key.upper()]))
+    if world > 1 and not _DIST.get("on"):
+        eng.enable_distributed()               # NCCL communicator inside the library (w2b_comm_init); ctqmc_measure ends with its all-reduce
+        _DIST["on"] = True
+    elif world > 1:
+        eng._dist = (rank, world)
     L = eng._load()
-    L.w2b_pinned_alloc.restype = C.c_void_p
-    eng.ctqmc_warmup(args.thermalise if args.thermalise >= 0 else THERMALISE[cfg])      # thermalisation, untimed
+
+    # ---- the reference plugin's call sequence (w2dynamics_b200/solver_sequence.py = CtHybSolver.set_problem / solve, proved
+    # call-identical to the unmodified plugin by tests/test_reference_plugin.py): host arrays in, host arrays out
+    qmc = qmc_defaults(); qmc.update(p.qmc)
+    ftau5 = np.ascontiguousarray(p.ftau.transpose(4, 0, 1, 2, 3))
+    screening = np.zeros_like(ftau5)
+
+    def plugin(nwarm, nmeas):
+        q = dict(qmc); q.update(Nwarmups=nwarm, Nmeas=nmeas)
+        seq = PluginSequence(eng, q, 43890 + 0)
+        seq.set_problem(p.hamiltonian, p.beta, p.nbands, p.quantum_numbers, p.u_matrix, ftau5, -p.muimp, screening)
+        return seq
+    plugin(therm, 1).solve(0)                                  # thermalisation, untimed: one solve; dest_ctqmc parks the population
+
+    # ---- `value`: chain state resident in HBM, K accumulation blocks timed on the device
+    eng.init_paras(p.pstring()); eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)      # revives the parked population
+    eng.set_taudiffmax(p.qmc["TaudiffMax"])
     eng.init_counters()
     ms = (C.c_double * 3)()
 
@@ -258,7 +304,6 @@ def run_engine(args):
 
     blocks(args.warmup)                                        # W untimed warm-up steps
     allreduce_accum()
-    eng._ck(L.w2b_read_accum(None, C.c_size_t(0), C.byref(C.c_size_t())))
     torch.cuda.synchronize()
     blocked = eng.scalar("blocked") > 0 or os.environ.get("W2B_SCHEDULER") == "2"
     bytes0, launches0 = eng.scalar("cnt_alg_bytes"), eng.scalar("gpu_launches")
@@ -289,38 +334,9 @@ def run_engine(args):
     if blocked:
         eng.set_option("time_kernels", 0)
     mean_k = eng.scalar("mean_order")
+    kcap = eng.scalar("kcap")
     moves = float(nchains) * ncorr * args.steps * world
     value = moves / (elapsed_ms * 1e-3)
-
-    # ---- e2e: host buffers in, host buffers out, every step
-    nacc = C.c_size_t()
-    eng._ck(L.w2b_read_accum(None, C.c_size_t(0), C.byref(nacc)))
-    nft = p.ftau.size
-    h_ft = L.w2b_pinned_alloc(C.c_size_t(nft * 8)); h_acc = L.w2b_pinned_alloc(C.c_size_t(nacc.value * 8))
-    C.memmove(h_ft, np.asfortranarray(p.ftau).ctypes.data, nft * 8)
-    dp = C.POINTER(C.c_double)
-
-    def e2e_step():
-        eng._ck(L.w2b_upload_ftau(C.cast(h_ft, dp), C.c_int(p.ftau.shape[-1])))
-        eng._ck(L.w2b_block(C.c_longlong(ncorr), C.c_int(1)))
-        eng._ck(L.w2b_read_accum(C.cast(h_acc, dp), C.c_size_t(nacc.value), C.byref(nacc)))
-    for _ in range(min(args.warmup, 3)):
-        e2e_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_val = moves / (e2e_ms * 1e-3)
     err = int(eng.scalar("error_flags"))
 
     # ---- wall time to a fixed G(tau) error (second half of BASELINE.json's metric): sample K fresh accumulation
@@ -346,61 +362,86 @@ def run_engine(args):
                    "sem_g_tau_average": float(sem_all), "g_tau_average": float(gm_all), "bins": int(gb.shape[0]), "moves": moves}
     except Exception as exc:                                    # diagnostic only: never lose the throughput line
         tte = {"error": str(exc)[:200]}
+    eng.dest_ctqmc()                                            # parks the population again
 
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        alg_bytes = bytes1 - bytes0
-        achieved = alg_bytes / (t_sweep * 1e-3) / 1e9 if t_sweep > 0 else 0.0
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg)
-        except Exception:
-            pass
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            nthreads = os.cpu_count() or 1
-            v, sample = cpu_oracle_rate(cfg, args.cpu_seconds, nthreads)
-            cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample}
-        state_gb = nchains * (2 * p.nbands + 1) * eng.scalar("kcap") ** 2 * 8 / 1e9
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[cfg], "chains_per_gpu": nchains, "ncorr": ncorr, "moves_per_step": nchains * ncorr * world,
-                       "mean_order_per_flavour": mean_k, "parallelism": "chains sharded over %d GPU(s), no data-path collective; one all-reduce of the accumulators per accumulation" % world,
-                       "l2": "inverse-matrix state %.1f GB per GPU > 126 MB L2 (inputs larger than L2, no flush needed)" % state_gb,
-                       "error_flags": err},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(nft * 8), "d2h_bytes_per_step": int(nacc.value * 8),
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches1 - launches0),
-            "kernel_ms": {"k_sweep": t_sweep / args.steps, "k_measure": t_meas / args.steps},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_sweep", "algorithmic_bytes_per_launch": alg_bytes / args.steps, "launch_ms": t_sweep / args.steps,
-                         "peak_source": peak_src},
-            "clocks": clocks,
-        }
-        if blocked:
-            # blocked traces: the sweep is rounds of k_propose / k_trace / k_decide (+ k_rare on a second stream); the dominant
-            # kernel is k_trace, bound by the FP64 tensor pipe (DMMA): algorithmic flops = 2 d_out d_in columns per operator
-            # product, counted in the kernel, over the summed CUDA-event durations of its launches in the timed region
-            nround = max(1.0, rounds1 - rounds0)
-            fpk, fsrc = fp64_peak()
-            tfl = (flops1 - flops0) / (kms["trace"] * 1e-3) / 1e12 if kms["trace"] > 0 else 0.0
-            line["kernel_ms"] = {"sweep": t_sweep / args.steps, "k_propose": kms["propose"] / args.steps, "k_trace": kms["trace"] / args.steps,
-                                 "k_decide": kms["decide"] / args.steps, "k_measure": t_meas / args.steps, "rounds_per_step": nround / args.steps}
-            line["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": fpk, "unit": "TFLOP/s", "frac": tfl / fpk, "traffic": traffic,
-                                "kernel": "k_trace", "dtype": "f64 (DMMA.8x8x4)", "algorithmic_flops_per_launch": (flops1 - flops0) / nround,
-                                "launch_ms": kms["trace"] / nround, "peak_source": fsrc,
-                                "hbm_view": {"achieved_gbs": achieved, "peak_gbs": peak, "note": "determinant-path algorithmic bytes over the whole sweep"}}
-        if tte:
-            line["time_to_error"] = tte
-        if cpu:
-            line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
-    eng.dest_ctqmc()
+    # ---- e2e: K plugin solves, each = init_paras + init_solver(host u, F(tau), mu) + set_taudiffmax + ctqmc_warmup(0) +
+    # ctqmc_measure(1 accumulation block; N > 1: + the library's all-reduce) + every result array of get_resultset read back to
+    # host memory + dest_ctqmc / dest_paras.  The population is the one thermalised above (reuse_population).
+    seq = plugin(0, 1)
+    for it in range(min(args.warmup, 3)):
+        seq.solve(1 + it)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    torch.cuda.synchronize()
+    hb0, db0 = eng.scalar("h2d_bytes"), eng.scalar("d2h_bytes")
+    t0 = time.perf_counter()
+    e0.record()
+    res = None
+    for it in range(args.steps):
+        res = seq.solve(10 + it)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    hb1, db1 = eng.scalar("h2d_bytes"), eng.scalar("d2h_bytes")
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = moves / (e2e_ms * 1e-3)
+    res_bytes = int(sum(np.asarray(v).nbytes for v in res.values()))
+    eng.set_option("reuse_population", 0)
+    eng.init_paras(p.pstring()); eng.dest_ctqmc(); eng.dest_paras()    # drop the parked population (frees the device memory for the next config)
+
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    alg_bytes = bytes1 - bytes0
+    achieved = alg_bytes / (t_sweep * 1e-3) / 1e9 if t_sweep > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg)
+    except Exception:
+        pass
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(cfg, args.cpu_seconds)
+    state_gb = nchains * (2 * p.nbands + 1) * kcap ** 2 * 8 / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[cfg], "chains_per_gpu": nchains, "ncorr": ncorr, "moves_per_step": nchains * ncorr * world,
+                   "mean_order_per_flavour": mean_k, "parallelism": "chains sharded over %d GPU(s), no data-path collective; one ncclAllReduce of the accumulators per accumulation (inside the library)" % world,
+                   "l2": "inverse-matrix state %.1f GB per GPU > 126 MB L2 (inputs larger than L2, no flush needed)" % state_gb,
+                   "error_flags": err},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int((hb1 - hb0) / args.steps), "d2h_bytes_per_step": int((db1 - db0) / args.steps),
+                "ms_per_step": e2e_ms / args.steps, "result_bytes_per_step": res_bytes,
+                "path": "per step one full plugin solve through the C ABI: init_paras, init_solver(host arrays), set_taudiffmax, ctqmc_warmup(0), ctqmc_measure(1,1) with Nmeas=1, all get_resultset arrays, dest_ctqmc"},
+        "gpu_launches": int(launches1 - launches0),
+        "kernel_ms": {"k_sweep": t_sweep / args.steps, "k_measure": t_meas / args.steps},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "k_sweep", "algorithmic_bytes_per_launch": alg_bytes / args.steps, "launch_ms": t_sweep / args.steps,
+                     "peak_source": peak_src},
+        "clocks": clocks,
+    }
+    if blocked:
+        # blocked traces: the sweep is rounds of k_propose / k_trace / k_decide (+ k_rare on a second stream); the dominant
+        # kernel is k_trace, bound by the FP64 tensor pipe (DMMA): algorithmic flops = 2 d_out d_in columns per operator
+        # product, counted in the kernel, over the summed CUDA-event durations of its launches in the timed region
+        nround = max(1.0, rounds1 - rounds0)
+        fpk, fsrc = fp64_peak()
+        tfl = (flops1 - flops0) / (kms["trace"] * 1e-3) / 1e12 if kms["trace"] > 0 else 0.0
+        line["kernel_ms"] = {"sweep": t_sweep / args.steps, "k_propose": kms["propose"] / args.steps, "k_trace": kms["trace"] / args.steps,
+                             "k_decide": kms["decide"] / args.steps, "k_measure": t_meas / args.steps, "rounds_per_step": nround / args.steps}
+        line["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": fpk, "unit": "TFLOP/s", "frac": tfl / fpk, "traffic": traffic,
+                            "kernel": "k_trace", "dtype": "f64 (DMMA.8x8x4)", "algorithmic_flops_per_launch": (flops1 - flops0) / nround,
+                            "launch_ms": kms["trace"] / nround, "peak_source": fsrc,
+                            "hbm_view": {"achieved_gbs": achieved, "peak_gbs": peak, "note": "determinant-path algorithmic bytes over the whole sweep"}}
+    if tte:
+        line["time_to_error"] = tte
+    if cpu:
+        line["cpu_baseline"] = cpu
+    return line
 
 
 def main():
@@ -409,7 +450,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default=os.environ.get("W2B_BENCH_CONFIG", "C4"), choices=sorted(WORKLOADS))
+    ap.add_argument("--config", default=os.environ.get("W2B_BENCH_CONFIG", "C4"), choices=sorted(WORKLOADS) + ["all"],
+                    help="workload (default C4 = the configuration BASELINE.json's metric is quoted on); `all`: one JSON line per config")
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default per config)")
     ap.add_argument("--thermalise", type=int, default=-1, help="untimed thermalisation moves per chain")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -417,10 +459,17 @@ def main():
     ap.add_argument("--slice-seconds", type=float, default=0.0, help="reference arm: wall time of one step (default: sized for a one-minute run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_engine(args)
+    for cfg in (sorted(WORKLOADS) if args.config == "all" else [args.config]):
+        if args.impl == "reference":
+            run_reference(args, cfg)
+        else:
+            line = run_engine(args, cfg)
+            if line is not None:
+                print(json.dumps(line), flush=True)
+    if args.impl != "reference" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -153,7 +153,7 @@ struct Chain {
         }
     }
     void init_window(double tdm) {
-        ec.valid = false;
+        ec.valid = false; fc.valid = false;
         window_position = 0;
         if (tdm > 0.0) {
             taudiff_max = tdm;
@@ -165,7 +165,7 @@ struct Chain {
         }
     }
     void shift_window() {                         // Trace.F90:1652-1678
-        ec.valid = false;
+        ec.valid = false;                            // (the per-operator caches do not depend on the window)
         if (num_windows > 1) {
             window_position += 1;
             if (window_position == num_windows) window_position = 0;
@@ -273,7 +273,7 @@ struct Chain {
     // chain of the operators right of it are cached per outer state and rebuilt when the window moves or a global move /
     // tau shift is accepted; a pair move (always inside the window) multiplies through the window only.  Same products as
     // trace_full in a different association order; the checker keeps using trace_full (fast_trace = false).
-    bool fast_trace = false;
+    int fast_trace = 0;                              // 0 from scratch (checker), 1 cached window edges, 2 per-operator caches (reference cost structure)
     struct EdgeCache {
         bool valid = false; int wpos = -1, outer = -1, nL = 0, nR = 0, sstL = 0, sstR = 0; double tauL = 0, tauR = 0;
         std::vector<double> KL, lgL, BR, lgR;
@@ -379,9 +379,138 @@ struct Chain {
         }
         return tot;
     }
-    // trace of a pair-move proposal (operators changed inside the window only)
-    LogVal trace_pair(const std::vector<Op>& o, int outer, std::vector<LogVal>* parts) {
-        if (fast_trace && T.dmax > 1 && num_windows > 1) return trace_windowed(o, outer, parts);
+    // ---------------------------------------------------------- per-operator state caches (opt-in, fast_trace = 2; CPU baseline)
+    // The reference stores one ket or bra per operator (TOper%state / %cache, Trace.F90:47-49) and, for a proposal, restarts
+    // from the innermost operators whose stored states are still valid (get_Trace_EB: StartR / StartL walk inward while
+    // `.not. calc_new`, Trace.F90:5384-5470), calculates kets up to the changed operators and bras behind them, and swaps state
+    // and cache on acceptance (update_trace_EB, Trace.F90:6109-6209).  Restated on the time-sorted array: KET_i (state after
+    // operator i, one vector per outer state) is valid for i < kv, BRA_i (state before operator i, propagated down from beta)
+    // for i >= bv; a proposal that changes the operators between old indices s and e extends the two frontiers to s-1 / e,
+    // multiplies through the changed sub-string and closes with BRA_e.  Work per proposal ~ operators between the previous and
+    // the current change, as in the reference; same products as trace_full in a different association order.
+    struct Slot { std::vector<double> ket, bra, klg, blg; };
+    struct FrontierCache { bool valid = false; int outer = -1, kv = 0, bv = 0; std::vector<Slot> slots; } fc;
+    // v <- O_op exp(-(E-E0) dt) v for one outer state; returns false when the operator annihilates the block
+    bool apply_ket(std::vector<double>& kt, std::vector<double>& ktp, int& sst, int& ns_sst, double& lg, const Op& e, double dt) const {
+        int ns = T.conn(sst, e.b, e.s, e.ca);
+        if (ns < 0) return false;
+        int nn = T.dim[ns];
+        const double* ev = &T.evals[T.offset[sst]];
+        const double* A = T.op(sst, e.b, e.s, e.ca);
+        if (ns_sst > 1) {
+            for (int c = 0; c < ns_sst; ++c) ktp[c] = std::exp(-(ev[c] - ev[0]) * dt) * kt[c];
+            lg += -(ev[0] - T.egs) * dt;
+            split_log(ktp.data(), ns_sst, lg);
+            for (int r = 0; r < nn; ++r) kt[r] = 0.0;
+            for (int c = 0; c < ns_sst; ++c) { double x = ktp[c]; const double* col = A + (size_t)c * nn; for (int r = 0; r < nn; ++r) kt[r] += col[r] * x; }
+            split_log(kt.data(), nn, lg);
+        } else {
+            lg += -(ev[0] - T.egs) * dt;
+            double x = kt[0];
+            for (int r = 0; r < nn; ++r) kt[r] = x * A[r];
+        }
+        sst = ns; ns_sst = nn;
+        return true;
+    }
+    // b <- O_op^T exp(-(E-E0) dt) b : bra living after the operator (block `sst`) pulled in front of it (block `before`)
+    void apply_bra(std::vector<double>& kt, std::vector<double>& ktp, int& sst, int& ns_sst, double& lg, const Op& e, int before, double dt) const {
+        const int nb_ = T.dim[before];
+        const double* ev = &T.evals[T.offset[sst]];
+        const double* A = T.op(before, e.b, e.s, e.ca);                         // (ns_sst x nb_) column-major
+        for (int c = 0; c < ns_sst; ++c) ktp[c] = std::exp(-(ev[c] - ev[0]) * dt) * kt[c];
+        lg += -(ev[0] - T.egs) * dt;
+        split_log(ktp.data(), ns_sst, lg);
+        for (int c = 0; c < nb_; ++c) { const double* col = A + (size_t)c * ns_sst; double acc = 0; for (int r = 0; r < ns_sst; ++r) acc += col[r] * ktp[r]; kt[c] = acc; }
+        split_log(kt.data(), nb_, lg);
+        sst = before; ns_sst = nb_;
+    }
+    void fc_reset(int outer) {
+        fc.valid = true; fc.outer = outer; fc.kv = 0; fc.bv = (int)ops.size();
+        fc.slots.assign(ops.size(), Slot());
+    }
+    // local trace of the proposed configuration `nw` that differs from `ops` only between old indices s (first changed) and
+    // e (first unchanged again); s == e for an insertion into one interval is allowed
+    LogVal trace_cached(const std::vector<Op>& nw, int outer, int s, int e, std::vector<LogVal>* parts) {
+        const int n = (int)ops.size(), m = T.dim[outer], dm = T.dmax, e_new = e + (int)nw.size() - n;
+        if (!fc.valid || fc.outer != outer || (int)fc.slots.size() != n) fc_reset(outer);
+        std::vector<int> after; sst_sequence(ops, outer, after);
+        std::vector<double> kt(dm), ktp(dm);
+        auto need = [&](std::vector<double>& v, size_t sz) { if (v.size() != sz) v.assign(sz, 0.0); };
+        // kets of the unchanged head: KET_i for i in [kv, s)
+        for (int i = fc.kv; i < s; ++i) {
+            Slot& cur = fc.slots[i];
+            need(cur.ket, (size_t)m * dm); need(cur.klg, m);
+            const int sb = i == 0 ? outer : after[i - 1], db = T.dim[sb];
+            const double tprev = i == 0 ? 0.0 : ops[i - 1].tau;
+            for (int j = 0; j < m; ++j) {
+                double lg; int sst = sb, ns_sst = db;
+                if (i == 0) { std::fill(kt.begin(), kt.end(), 0.0); kt[j] = 1.0; lg = 0.0; }
+                else { const Slot& pv = fc.slots[i - 1]; for (int c = 0; c < db; ++c) kt[c] = pv.ket[(size_t)j * dm + c]; lg = pv.klg[j]; }
+                apply_ket(kt, ktp, sst, ns_sst, lg, ops[i], ops[i].tau - tprev);
+                for (int c = 0; c < ns_sst; ++c) cur.ket[(size_t)j * dm + c] = kt[c];
+                cur.klg[j] = lg;
+            }
+        }
+        if (fc.kv < s) fc.kv = s;
+        // bras of the unchanged tail: BRA_i for i in [e, bv), descending
+        for (int i = fc.bv - 1; i >= e; --i) {
+            Slot& cur = fc.slots[i];
+            need(cur.bra, (size_t)m * dm); need(cur.blg, m);
+            const int sa = after[i], da = T.dim[sa], before = i == 0 ? outer : after[i - 1];
+            const double tnext = i + 1 == n ? beta : ops[i + 1].tau;
+            for (int j = 0; j < m; ++j) {
+                double lg; int sst = sa, ns_sst = da;
+                if (i + 1 == n) { std::fill(kt.begin(), kt.end(), 0.0); kt[j] = 1.0; lg = 0.0; }
+                else { const Slot& nx = fc.slots[i + 1]; for (int c = 0; c < da; ++c) kt[c] = nx.bra[(size_t)j * dm + c]; lg = nx.blg[j]; }
+                apply_bra(kt, ktp, sst, ns_sst, lg, ops[i], before, tnext - ops[i].tau);
+                for (int c = 0; c < ns_sst; ++c) cur.bra[(size_t)j * dm + c] = kt[c];
+                cur.blg[j] = lg;
+            }
+        }
+        if (fc.bv > e) fc.bv = e;
+        // changed sub-string of the proposed configuration, closed with BRA_e
+        LogVal tot{-HUGE_D, 0.0};
+        if (parts) parts->assign(m, LogVal{-HUGE_D, 0.0});
+        const int s_sst = s == 0 ? outer : after[s - 1];
+        const double s_tau = s == 0 ? 0.0 : ops[s - 1].tau;
+        const int e_sst = e == n ? outer : (e == 0 ? outer : after[e - 1]);
+        const double e_tau = e == n ? beta : ops[e].tau;
+        for (int j = 0; j < m; ++j) {
+            int sst = s_sst, ns_sst = T.dim[s_sst]; double lg, tauR_ = s_tau;
+            if (s == 0) { std::fill(kt.begin(), kt.end(), 0.0); kt[j] = 1.0; lg = 0.0; }
+            else { const Slot& pv = fc.slots[s - 1]; for (int c = 0; c < ns_sst; ++c) kt[c] = pv.ket[(size_t)j * dm + c]; lg = pv.klg[j]; }
+            bool dead = false;
+            for (int i = s; i < e_new; ++i) {
+                if (!apply_ket(kt, ktp, sst, ns_sst, lg, nw[i], nw[i].tau - tauR_)) { dead = true; break; }
+                tauR_ = nw[i].tau;
+            }
+            if (dead || sst != e_sst) continue;
+            const double* ev = &T.evals[T.offset[sst]];
+            double bl = -(ev[0] - T.egs) * (e_tau - tauR_), braket = 0.0, blg = 0.0;
+            if (e == n) braket = std::exp(-(ev[j] - ev[0]) * (e_tau - tauR_)) * kt[j];
+            else { const Slot& nx = fc.slots[e]; blg = nx.blg[j];
+                   for (int c = 0; c < ns_sst; ++c) braket += nx.bra[(size_t)j * dm + c] * std::exp(-(ev[c] - ev[0]) * (e_tau - tauR_)) * kt[c]; }
+            LogVal pt{lg + bl + blg + std::log(std::fabs(braket)), sgn(braket)};
+            if (braket == 0.0) pt = LogVal{-HUGE_D, 0.0};
+            if (parts) (*parts)[j] = pt;
+            if (pt.sign != 0.0) tot = (tot.sign == 0.0) ? pt : ladd(tot, pt);
+        }
+        return tot;
+    }
+    // an accepted pair move replaced old operators [s, e) by `nmid` new ones: hand the caches over (update_trace_EB)
+    void fc_accept(int s, int e, int nmid) {
+        if (!fc.valid) return;
+        std::vector<Slot> ns; ns.reserve(fc.slots.size() + 2);
+        for (int i = 0; i < s; ++i) ns.push_back(std::move(fc.slots[i]));
+        for (int i = 0; i < nmid; ++i) ns.emplace_back();
+        for (size_t i = e; i < fc.slots.size(); ++i) ns.push_back(std::move(fc.slots[i]));
+        fc.slots.swap(ns);
+        fc.kv = std::min(fc.kv, s); fc.bv = std::max(fc.bv, e) + (s + nmid - e);
+    }
+    // trace of a pair-move proposal: old operators [s, e) replaced (operators changed inside the window only)
+    LogVal trace_pair(const std::vector<Op>& o, int outer, std::vector<LogVal>* parts, int s, int e) {
+        if (fast_trace == 2 && T.dmax > 1) return trace_cached(o, outer, s, e, parts);
+        if (fast_trace == 1 && T.dmax > 1 && num_windows > 1) return trace_windowed(o, outer, parts);
         return trace_full(o, outer, parts);
     }
 
@@ -540,7 +669,7 @@ struct Chain {
         LogVal DetRat{std::log(std::fabs(S)), sgn(S) * sig};
         LogVal DetNew = lmul(DetRat, Det);
         std::vector<LogVal> parts;
-        LogVal TraceNew = trace_pair(nw, outer_sst, &parts);
+        LogVal TraceNew = trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2);
         double rand = grnd();
         int NPairs = count_pairs(nw);
         LogVal trr = ldiv(TraceNew, Trace);
@@ -560,6 +689,7 @@ struct Chain {
                     N[in + (size_t)jn * kn] = Mf[i + (size_t)j * k] + S * N[in + (size_t)p2 * kn] * N[p1 + (size_t)jn * kn]; } }
             M[f].swap(N); kf[f] = kn;
             ops.swap(nw);
+            if (fast_trace == 2) fc_accept((int)i1, (int)i2, (int)(i2 - i1) + 2);
             Det = DetNew; Trace = TraceNew; parttrace = parts;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccAdd += 1;
@@ -617,7 +747,7 @@ struct Chain {
         LogVal DetRat{std::log(std::fabs(S)), sgn(S) * sig};
         LogVal DetNew = lmul(DetRat, Det);
         std::vector<LogVal> parts;
-        LogVal TraceNew = trace_pair(nw, outer_sst, &parts);
+        LogVal TraceNew = trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2 + 1);
         LogVal trr = ldiv(TraceNew, Trace);
         double prob = std::fabs(factor / (double)(2 * nb) * std::exp(trr.log + DetRat.log));
         double rand = grnd();
@@ -632,6 +762,7 @@ struct Chain {
                     N[i + (size_t)j * kn] = Mf[io + (size_t)jo * k] - Mf[io + (size_t)p2 * k] * Mf[p1 + (size_t)jo * k] / Mf[p1 + (size_t)p2 * k]; } }
             M[f].swap(N); kf[f] = kn;
             ops.swap(nw);
+            if (fast_trace == 2) fc_accept((int)i1, (int)i2 + 1, (int)(i2 - i1) - 1);
             Det = DetNew; Trace = TraceNew; parttrace = parts;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccRem += 1;
@@ -701,7 +832,7 @@ struct Chain {
         rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[17] = rand;
         if (rand < prob) {
             ops.swap(nw); M.swap(Mn); kf = kn; outer_sst = new_outer;
-            Det = DetNew; Trace = TraceNew; parttrace = parts; ec.valid = false;
+            Det = DetNew; Trace = TraceNew; parttrace = parts; ec.valid = false; fc.valid = false;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccGlob += 1; log_end(1);
         } else log_end(0);
@@ -715,7 +846,7 @@ struct Chain {
         double rand = grnd(), acc = 0; int pick = T.nsst - 1;
         for (int i = 0; i < T.nsst; ++i) { acc += w[i]; pick = i; if (acc >= rand && w[i] != 0.0) break; }
         outer_sst = pick;
-        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false;
+        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false; fc.valid = false;
         cfgsign = -get_sign(ops, Trace, Det);
         rec[17] = rand;
     }
@@ -767,7 +898,7 @@ struct Chain {
                 if ((k % 2) != 0 && ((w1 + w2) % 2) != 0) detrat = -detrat;
             }
             ops.swap(nw); outer_sst = new_outer;
-            Trace = TraceNew; parttrace = parts; Det.sign *= detrat; ec.valid = false;
+            Trace = TraceNew; parttrace = parts; Det.sign *= detrat; ec.valid = false; fc.valid = false;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccShift += 1; log_end(1);
         } else {
@@ -890,7 +1021,7 @@ struct Chain {
         double rand = grnd(), acc = 0; int pick = T.nsst - 1;
         for (int i = 0; i < T.nsst; ++i) { acc += w[i]; pick = i; if (acc >= rand && w[i] != 0.0) break; }
         outer_sst = pick;
-        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false;
+        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false; fc.valid = false;
         cfgsign = -1.0;                              // TTrace default (Trace.F90:129), first computed on the first accepted move
     }
     void set_config(int n, const double* taus, const int* orbs, const int* spins, const int* cas, int osst) {
@@ -898,7 +1029,7 @@ struct Chain {
         ops.clear();
         for (int i = 0; i < n; ++i) ops.push_back(Op{taus[i], orbs[i] - 1, spins[i] - 1, cas[i]});
         outer_sst = osst; window_position = 0; set_window_edges();
-        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false;
+        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false; fc.valid = false;
         Det = build_inverse_all(ops, M, kf);
         cfgsign = -get_sign(ops, Trace, Det);
     }
@@ -976,7 +1107,7 @@ unsigned long long orc_rng_counter(void* h) { return ((Chain*)h)->ph.ctr; }
 
 void orc_init_trace(void* h) { ((Chain*)h)->init_trace(); }
 void orc_set_taudiffmax(void* h, double t) { ((Chain*)h)->init_window(t); }
-void orc_set_fast_trace(void* h, int on) { Chain* c = (Chain*)h; c->fast_trace = on != 0; c->ec.valid = false; }
+void orc_set_fast_trace(void* h, int on) { Chain* c = (Chain*)h; c->fast_trace = on; c->ec.valid = false; c->fc.valid = false; }
 void orc_init_counters(void* h) { ((Chain*)h)->reset_counters(); }
 void orc_set_log(void* h, double* buf, long long cap) { Chain* c = (Chain*)h; c->logp = buf; c->log_cap = cap; c->log_n = 0; }
 long long orc_log_count(void* h) { return ((Chain*)h)->log_n; }

@@ -98,7 +98,7 @@ class MCTQMC:
     def set_option(self, key, value):
         """Engine knobs without a reference counterpart (nchains, nbins, kcap, ops_cap, device, chain_base)."""
         self._options[key] = value
-        if self._lib is not None and key in ("time_kernels",):       # run-time switches take effect immediately
+        if self._lib is not None and key in ("time_kernels", "reuse_population"):       # run-time switches take effect immediately
             self._ck(self._lib.w2b_set_option(key.encode(), C.c_double(float(value))))
         if key == "nchains":
             self._nchains = int(value)

@@ -40,6 +40,7 @@ struct Solver {
     std::vector<std::vector<double>> bin_gtau, bin_gleg, bin_occ; std::vector<double> bin_sign;
     std::vector<double> raw_acc; bool bins_ready = false;      // raw accumulator slabs of the last finalize; per-bin results are normalised on first request
     double time_warmup = 0, time_sim = 0, time_sim_steps = 0;
+    Rho2Cache rho2cache; bool rho2_ready = false;
     unsigned nsolve = 0;            // init_solver calls since init_rnd (selects the section of every chain's RNG stream)
     int aborted = 0;                // 0 / 1 (some measurements done) / 2 (none): CTQMC.F90:8648-8658
     long long nmeas_done = 0;
@@ -151,7 +152,8 @@ void finalize_results() {
         }
     }
     S.res = ResultSet();
-    normalise_slab(E.at, E.A, E.R, S.beta, tot.data(), S.dens_off, true, S.res);
+    if (!S.rho2_ready) { S.rho2cache.build(E.at); S.rho2_ready = true; }
+    normalise_slab(E.at, E.A, E.R, S.beta, tot.data(), S.dens_off, true, S.res, &S.rho2cache);
     // per-bin samples (for error bars across chain groups) are normalised on first request (w2b_get_array "*_bins")
     S.raw_acc.swap(acc); S.bins_ready = false;
     S.bin_gtau.clear(); S.bin_gleg.clear(); S.bin_occ.clear(); S.bin_sign.clear();
@@ -361,6 +363,7 @@ int w2b_init_solver(const double* u_matrix, const double* ftau_full, const doubl
             AtomicTables at = build_atomic(nb, p.str("QuantumNumbers"), u_matrix, muimp_full, p.real("EPSBLOCK"), p.real("EPSEVEC"));
             S.eng.reset(new Engine());
             S.eng->setup(at, fd, nftau, S.beta, R, opt);
+            S.rho2_ready = false;
             S.key_u.assign(u_matrix, u_matrix + nu); S.key_mu.assign(muimp_full, muimp_full + nmu); S.key_par = key_of(p); S.key_opt = opt; S.key_nftau = nftau; S.key_nmeas = S.nmeas;
         }
         S.dens_off = S.eng->dens_off;                                        // block k: d x d column-major slab
@@ -697,6 +700,8 @@ int w2b_get_scalar(const char* name, double* out) {
         if (k == "time_sim") { *out = S.time_sim; return; }
         if (k == "time_sim_steps") { *out = S.time_sim_steps; return; }
         if (k == "aborted") { *out = S.aborted; return; }
+        if (k == "h2d_bytes") { *out = (double)h2d_bytes(); return; }
+        if (k == "d2h_bytes") { *out = (double)d2h_bytes(); return; }
         if (k == "nmeas_done") { *out = (double)S.nmeas_done; return; }
         if (k == "comm_rank") { *out = G.rank; return; }
         if (k == "comm_size") { *out = G.nranks; return; }

@@ -42,8 +42,12 @@ template <class T_> void dev_free(T_*& p) {
 #endif
     p = nullptr;
 }
+// bytes moved between host and device through these helpers (bench.py reports them per end-to-end step)
+inline unsigned long long& h2d_bytes() { static unsigned long long v = 0; return v; }
+inline unsigned long long& d2h_bytes() { static unsigned long long v = 0; return v; }
 template <class T_> void h2d(T_* d, const T_* h, size_t n) {
     if (!n) return;
+    h2d_bytes() += n * sizeof(T_);
 #if W2B_DEVICE
     W2B_CUDA_CHECK(cudaMemcpy((void*)d, h, n * sizeof(T_), cudaMemcpyHostToDevice));
 #else
@@ -52,6 +56,7 @@ template <class T_> void h2d(T_* d, const T_* h, size_t n) {
 }
 template <class T_> void d2h(T_* h, const T_* d, size_t n) {
     if (!n) return;
+    d2h_bytes() += n * sizeof(T_);
 #if W2B_DEVICE
     W2B_CUDA_CHECK(cudaMemcpy(h, d, n * sizeof(T_), cudaMemcpyDeviceToHost));
 #else

@@ -33,9 +33,31 @@ inline std::vector<double> mm(const double* A, int m, int k, const double* B, in
 }
 }  // namespace detail
 
+// Configuration-independent half of Meas_rho2_from_Densitymatrix (CTQMC.F90:2945-3017): for every block k and every pair of
+// annihilators (f1 first, then f2) with k -c1-> n1 -c2-> n2 the product  P21 = c2(n1 -> n2) c1(k -> n1)  (d_n2 x d_k).
+// rho2(f4,f3,f2,f1) = sum_k Tr[rho_k c4^+ c3^+ P21] then costs one dot product per element instead of two more matrix products.
+// Built once per solve (a few MB for the 5-orbital problem).
+struct Rho2Cache {
+    struct Entry { int f1, f2, n2; std::vector<double> p21; };
+    std::vector<std::vector<Entry>> by_block;
+    void build(const AtomicTables& at) {
+        const int nf = at.nf;
+        by_block.assign(at.nsst, {});
+        for (int k = 0; k < at.nsst; ++k) for (int f1 = 0; f1 < nf; ++f1) {
+            const int n1 = at.conn(k, f1 * 2 + 1);
+            if (n1 < 0) continue;
+            for (int f2 = 0; f2 < nf; ++f2) {
+                const int n2 = at.conn(n1, f2 * 2 + 1);
+                if (n2 < 0) continue;
+                by_block[k].push_back(Entry{f1, f2, n2, detail::mm(at.op(n1, f2 * 2 + 1), at.dim[n2], at.dim[n1], at.op(k, f1 * 2 + 1), at.dim[k])});
+            }
+        }
+    }
+};
+
 // Normalise one slab.  dens_eb: block-diagonal eigenbasis density matrix, block k column-major at dens_off[k].
 inline void normalise_slab(const AtomicTables& at, const Accum& A, const Run& R, double beta, const double* slab,
-                           const std::vector<int>& dens_off, bool want_rho2, ResultSet& out) {
+                           const std::vector<int>& dens_off, bool want_rho2, ResultSet& out, const Rho2Cache* r2c = nullptr) {
     const int nb = at.nb, nf = at.nf, ntau = R.ntau, nleg = R.nlegmax, nh = R.maxhisto + 1, ns = at.nstates, nsst = at.nsst;
     const double cnt = slab[A.o_cnt];
     const double mean_sign = slab[A.o_sign] / cnt;                           // CTQMC.F90:8670
@@ -101,7 +123,15 @@ inline void normalise_slab(const AtomicTables& at, const Accum& A, const Run& R,
                 int n2 = at.conn(n3, opc(b3, s3, 2));              // Connect(n2, 3, c^dag) == n3  <=> Connect(n3, 3, c) == n2
                 if (n2 < 0) continue;
                 int d2 = at.dim[n2];
-                std::vector<double> u2 = detail::mm(t1.data(), d, d3, at.op(n2, opc(b3, s3, 1)), d2);     // d x d2
+                std::vector<double> u2 = detail::mm(t1.data(), d, d3, at.op(n2, opc(b3, s3, 1)), d2);     // rho c4^+ c3^+ : d x d2
+                if (r2c) {                                         // Tr[u2 (c2 c1)] = sum_{i,p} u2(i,p) P21(p,i)
+                    for (const Rho2Cache::Entry& en : r2c->by_block[k]) {
+                        if (en.n2 != n2) continue;
+                        size_t idx = (2 * b4 + s4) + (size_t)nf * ((2 * b3 + s3) + (size_t)nf * (en.f2 + (size_t)nf * en.f1));
+                        rho2[idx] += trace_with(u2, d, d2, en.p21.data());
+                    }
+                    continue;
+                }
                 for (int b2 = 0; b2 < nb; ++b2) for (int s2 = 0; s2 < 2; ++s2) {
                     int n1 = at.conn(n2, opc(b2, s2, 1));          // Connect(n1, 2, c) == n2  <=> Connect(n2, 2, c^dag) == n1
                     if (n1 < 0) continue;
