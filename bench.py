@@ -281,11 +281,14 @@ def run_engine(args, cfg):
     ftau5 = np.ascontiguousarray(p.ftau.transpose(4, 0, 1, 2, 3))
     screening = np.zeros_like(ftau5)
 
-    def plugin(nwarm, nmeas):
-        q = dict(qmc); q.update(Nwarmups=nwarm, Nmeas=nmeas)
-        seq = PluginSequence(eng, q, 43890 + 0)
-        seq.set_problem(p.hamiltonian, p.beta, p.nbands, p.quantum_numbers, p.u_matrix, ftau5, -p.muimp, screening)
-        return seq
+    class plugin:                                              # one DMFT-style iteration = set_problem + solve (cthyb: 305, 314)
+        def __init__(self, nwarm, nmeas):
+            q = dict(qmc); q.update(Nwarmups=nwarm, Nmeas=nmeas)
+            self.seq = PluginSequence(eng, q, 43890)
+
+        def solve(self, it):
+            self.seq.set_problem(p.hamiltonian, p.beta, p.nbands, p.quantum_numbers, p.u_matrix, ftau5, -p.muimp, screening)
+            return self.seq.solve(it)
     plugin(therm, 1).solve(0)                                  # thermalisation, untimed: one solve; dest_ctqmc parks the population
 
     # ---- `value`: chain state resident in HBM, K accumulation blocks timed on the device

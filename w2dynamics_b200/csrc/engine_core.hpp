@@ -176,6 +176,7 @@ W2B_HD double* Mbuf(const Chains& C, Ctx& x, int f) { return x.Mbase + (size_t)x
 // number of sorted entries < t ; eq is set when an entry equals t
 W2B_HDN int count_lt(const double* a, int n, double t, bool& eq) {
     int c = 0; bool e = false;
+#pragma unroll 1
     for (int i = lane_id(); i < n; i += W2B_WARP) { double v = a[i]; c += (v < t); e |= (v == t); }
     eq = wany(e);
     return wsum(c);
@@ -184,6 +185,7 @@ W2B_HD int count_lt(const double* a, int n, double t) { bool e; return count_lt(
 // both insertion positions in one pass over the operator times (t1 < t2); eq: some entry equals t1 or t2
 W2B_HDN void count_lt2(const double* a, int n, double t1, double t2, int& c1, int& c2, bool& eq) {
     int x1 = 0, x2 = 0; bool e = false;
+#pragma unroll 1
     for (int i = lane_id(); i < n; i += W2B_WARP) { double v = a[i]; x1 += (v < t1); x2 += (v < t2); e |= (v == t1) | (v == t2); }
     eq = wany(e);
     const int packed = wsum(x1 | (x2 << 16));                 // n <= 4096 operators: both counts fit 16 bits
@@ -191,12 +193,14 @@ W2B_HDN void count_lt2(const double* a, int n, double t1, double t2, int& c1, in
 }
 W2B_HDN int count_le(const double* a, int n, double t) {
     int c = 0;
+#pragma unroll 1
     for (int i = lane_id(); i < n; i += W2B_WARP) c += (a[i] <= t);
     return wsum(c);
 }
 
 // array shifts by whole-warp chunks (read chunk, sync, write)
 template <class T_> W2B_HDN void shift_up(T_* a, int from, int n, int by) {       // [from,n) -> [from+by, n+by)
+#pragma unroll 1
     for (int top = n; top > from; top -= W2B_WARP) {
         int idx = top - 1 - lane_id();
         T_ v = T_(); bool act = idx >= from;
@@ -207,6 +211,7 @@ template <class T_> W2B_HDN void shift_up(T_* a, int from, int n, int by) {     
     }
 }
 template <class T_> W2B_HDN void shift_down(T_* a, int from, int n, int by) {     // [from+by, n) -> [from, n-by)
+#pragma unroll 1
     for (int base = from; base < n - by; base += W2B_WARP) {
         int idx = base + lane_id();
         T_ v = T_(); bool act = idx < n - by;
@@ -221,11 +226,13 @@ template <class T_> W2B_HDN void shift_down(T_* a, int from, int n, int by) {   
 // superstate `cur`; stores the superstate after each operator into out[i0out + j].  Returns the final superstate
 // (-1 if annihilated on the way).
 W2B_HDN int walk_store(const Tables& T, const unsigned char* code, int i0, int m, int cur, short* out, int i0out) {
+#pragma unroll 1
     for (int base = 0; base < m; base += W2B_WARP) {
         int j = base + lane_id(); bool act = j < m;
         int cj = act ? (int)code[i0 + j] : 0;
         int cnt = m - base < W2B_WARP ? m - base : W2B_WARP;
         int mine = -1;
+#pragma unroll 1
         for (int q = 0; q < cnt; ++q) {
             int cq = wbcast(cj, q);
             cur = cur >= 0 ? conn(T, cur, cq) : -1;
@@ -246,11 +253,13 @@ W2B_HDN void walk_delta(const Tables& T, const Ctx& x, int i0, int m, int f, int
                        double& dlog, double& dsign, int& nother) {
     double acc = 0.0; int neg = 0, oth = 0;
     int old_before0 = old_after; double tl0 = tl;
+#pragma unroll 1
     for (int base = 0; base < m; base += W2B_WARP) {
         int j = base + lane_id(); bool act = j < m;
         int cj = act ? (int)x.code[i0 + j] : 0;
         int cnt = m - base < W2B_WARP ? m - base : W2B_WARP;
         int nb4 = -1;
+#pragma unroll 1
         for (int q = 0; q < cnt; ++q) {
             int cq = wbcast(cj, q);
             if (lane_id() == q) nb4 = cur;
@@ -279,17 +288,21 @@ W2B_HD bool pairable(const Run& R, const Ctx& x, double a, double b) {
 }
 W2B_HDN int pairs_with(const Run& R, const Ctx& x, const double* opp, int k, double t) {
     int c = 0;
+#pragma unroll 1
     for (int i = lane_id(); i < k; i += W2B_WARP) c += pairable(R, x, opp[i], t);
     return wsum(c);
 }
 W2B_HDN int count_pairs_full(const Tables& T, const Run& R, const Chains& C, const Ctx& x) {
     int c = 0;
+#pragma unroll 1
     for (int f = 0; f < T.nf; ++f) {
         int k = x.ih[IH_KF + f];
         const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+#pragma unroll 1
         for (int i = lane_id(); i < k; i += W2B_WARP) {
             double t = tc[i];
             if (t < x.wmin || t > x.wmax) continue;
+#pragma unroll 1
             for (int a = 0; a < k; ++a) c += pairable(R, x, ta[a], t);
         }
     }
@@ -301,8 +314,10 @@ W2B_HDN int palt_flavour(const Chains& C, const Ctx& x, int f) {
     int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     int c = 0;
+#pragma unroll 1
     for (int i = lane_id(); i < k; i += W2B_WARP) {
         double t = tc[i]; int pos = i;
+#pragma unroll 1
         for (int a = 0; a < k; ++a) pos += (ta[a] < t);
         c += ((pos & 1) == 0);
     }
@@ -311,14 +326,17 @@ W2B_HDN int palt_flavour(const Chains& C, const Ctx& x, int f) {
 // inversion parity of the flavour sequence in time order (== get_BlockSign, Trace.F90:3594-3618)
 W2B_HDN int perm_full(const unsigned char* code, int n) {
     int c = 0;
+#pragma unroll 1
     for (int i = lane_id(); i < n; i += W2B_WARP) {
         int fi = code[i] >> 1;
+#pragma unroll 1
         for (int j = i + 1; j < n; ++j) c += ((code[j] >> 1) < fi);
     }
     return wsum(c) & 1;
 }
 W2B_HDN void update_cfgsign(const Tables& T, Ctx& x) {
     int pal = 0;
+#pragma unroll 1
     for (int f = 0; f < T.nf; ++f) pal ^= (x.palt >> f) & 1;
     if ((x.n / 2) & 1) pal ^= 1;
     double s = x.tr_sign * x.det_sign * ((x.perm & 1) ? -1.0 : 1.0) * (pal ? -1.0 : 1.0);
@@ -333,6 +351,7 @@ W2B_HD double* bra_slot(const Chains& C, const Ctx& x, int i) { return x.bra + (
 
 // all cache slots back to "operator i owns slot i", nothing valid
 W2B_HD void slots_reset(const Chains& C, Ctx& x) {
+#pragma unroll 1
     for (int i = lane_id(); i < C.ops_cap; i += W2B_WARP) { x.slot[i] = (unsigned short)i; x.freel[i] = (unsigned short)(C.ops_cap - 1 - i); }
     x.nfree = C.ops_cap - x.n; x.kv = 0; x.bv = x.n;
     wsync();
@@ -352,6 +371,7 @@ W2B_HDN bool extend_kets(const Tables& T, const Chains& C, Ctx& x, int upto) {
         mat_copy(x.mlg, x.ketlg + (size_t)x.slot[i - 1] * C.dmax, m);
         wsync();
     }
+#pragma unroll 1
     for (; i <= upto; ++i) {
         sst = mat_apply(T, sst, (int)x.code[i], x.tau[i] - tprev, X, ld, x.mlg, x.mpw, m);
         const int d = ldg(&T.dim[sst]);
@@ -378,6 +398,7 @@ W2B_HDN void extend_bras(const Tables& T, const Chains& C, Ctx& x, int downto) {
         mat_copy(x.mlg, x.bralg + (size_t)x.slot[i] * C.dmax, m);
         wsync();
     }
+#pragma unroll 1
     for (i = x.bv - 1; i >= downto; --i) {          // BRA_i = O_i^T P(tau_{i+1} - tau_i) BRA_{i+1}
         const int sb = mat_apply(T, (int)x.sst[i], (int)x.code[i] ^ 1, tnext - x.tau[i], X, ld, x.mlg, x.mpw, m);
         const int d = ldg(&T.dim[sb]);
@@ -395,6 +416,7 @@ W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsign
     double* X = x.mX;
     mat_identity(X, ld, x.mlg, m);
     int sst = outer; double tprev = 0.0;
+#pragma unroll 1
     for (int i = 0; i < n; ++i) { sst = mat_apply(T, sst, (int)code[i], tau[i] - tprev, X, ld, x.mlg, x.mpw, m); tprev = tau[i]; }
     mat_close(T, sst, T.beta - tprev, X, ld, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
 }
@@ -419,7 +441,9 @@ template <class TablesT> inline int tile_apply(const TablesT& T, int sst_in, int
     return mat_apply_slot(T, sst_in, opc, dt, w.X, w.ld, w.lg, w.pw, mw, slot, slot_lg, j0, work);
 }
 inline void tile_load(const Tile& w, const double* src, const double* src_lg, int d, int j0, int mw) {
+#pragma unroll 1
     for (int j = 0; j < mw; ++j) for (int r = 0; r < d; ++r) w.X[r + j * w.ld] = src ? src[r + j * d] : (r == j0 + j ? 1.0 : 0.0);
+#pragma unroll 1
     for (int j = 0; j < mw; ++j) w.lg[j] = src ? src_lg[j] : 0.0;
 }
 template <class TablesT> inline void tile_close(const TablesT& T, int sst, double dt, const Tile& w, const double* B, const double* blg, int mw, int j0, double* pt) {
@@ -483,6 +507,7 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* ws) {
     int cur = -1;                        // block of the work matrix (rows)
     int work = 0;                        // sum of d_out * d_in over the operator products of this job
     int r_opc = 0, r_sst = 0, r_slot = 0; double r_dt = 0.0;
+#pragma unroll 1
     for (int j = 0; j < total; ++j) {
         if ((j & (W2B_WARP - 1)) == 0) {                       // next 32 step records, one per lane
             const int q = j + lane;
@@ -539,21 +564,25 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* ws) {
 W2B_HD void empty_parts(const Tables& T, Ctx& x, int outer) {
     const int m = ldg(&T.dim[outer]);
     const double* ev = T.evals + ldg(&T.offset[outer]);
+#pragma unroll 1
     for (int j = lane_id(); j < m; j += W2B_WARP) { x.pt[2 * j] = -(ldg(&ev[j]) - T.egs) * T.beta; x.pt[2 * j + 1] = 1.0; }
     wsync();
 }
 W2B_HDN void commit_parts(const Tables& T, Ctx& x) {
     const int m = ldg(&T.dim[x.outer]);
+#pragma unroll 1
     for (int j = lane_id(); j < 2 * m; j += W2B_WARP) x.pt[j] = x.mpt[j];
 }
 
 // integer superstate walk over the old operators [i0, i0+mcount) starting from `cur`; counts operators of another flavour
 W2B_HDN int walk_check(const Tables& T, const Ctx& x, int i0, int mcount, int f, int cur, int& nother) {
     int oth = 0;
+#pragma unroll 1
     for (int base = 0; base < mcount; base += W2B_WARP) {
         int j = base + lane_id(); bool act = j < mcount;
         int cj = act ? (int)x.code[i0 + j] : 0;
         int cnt = mcount - base < W2B_WARP ? mcount - base : W2B_WARP;
+#pragma unroll 1
         for (int q = 0; q < cnt; ++q) { int cq = wbcast(cj, q); cur = cur >= 0 ? conn(T, cur, cq) : -1; }
         if (act) oth += ((cj >> 1) != f);
     }
@@ -566,6 +595,7 @@ W2B_HDN int walk_check(const Tables& T, const Ctx& x, int i0, int mcount, int f,
 W2B_HDN double det_ratio_add(const Tables& T, const Chains& C, Ctx& x, int f, double tau_c, double tau_a) {
     int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+#pragma unroll 1
     for (int j = lane_id(); j < k; j += W2B_WARP) {
         x.wQ[j] = hybrF(T, ta[j] - tau_c, f);              // Q_j = F(tau_a_j - tau_c,new)
         x.wR[j] = hybrF(T, tau_a - tc[j], f);              // R_i = F(tau_a,new - tau_c_i)
@@ -574,15 +604,18 @@ W2B_HDN double det_ratio_add(const Tables& T, const Chains& C, Ctx& x, int f, do
     const double* M = Mbuf(C, x, f);
     const int ld = C.ld;
     double part = 0.0;
+#pragma unroll 1
     for (int j = lane_id(); j < k; j += W2B_WARP) {
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         int i = 0;
+#pragma unroll 1
         for (; i + 3 < k; i += 4) {
             a0 += x.wR[i] * M[(size_t)i * ld + j];
             a1 += x.wR[i + 1] * M[(size_t)(i + 1) * ld + j];
             a2 += x.wR[i + 2] * M[(size_t)(i + 2) * ld + j];
             a3 += x.wR[i + 3] * M[(size_t)(i + 3) * ld + j];
         }
+#pragma unroll 1
         for (; i < k; ++i) a0 += x.wR[i] * M[(size_t)i * ld + j];
         double v = (a0 + a1) + (a2 + a3);
         x.wV[j] = v;
@@ -598,15 +631,19 @@ W2B_HDN void mat_add(const Chains& C, Ctx& x, int f, int nf, int p1, int p2, dou
     int k = x.ih[IH_KF + f];
     const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, nf);
     const int ld = C.ld; const double inv = 1.0 / S;
+#pragma unroll 1
     for (int in = 0; in <= k; ++in) {
         if (in == p1) {
+#pragma unroll 1
             for (int jn = lane_id(); jn <= k; jn += W2B_WARP)
                 dst[(size_t)in * ld + jn] = (jn == p2) ? inv : -x.wV[jn - (jn > p2)] * inv;
         } else {
             int i = in - (in > p1);
             double part = 0.0;
+#pragma unroll 1
             for (int j = lane_id(); j < k; j += W2B_WARP) part += src[(size_t)i * ld + j] * x.wQ[j];
             double u = wsum(part);
+#pragma unroll 1
             for (int jn = lane_id(); jn <= k; jn += W2B_WARP) {
                 if (jn == p2) dst[(size_t)in * ld + jn] = -u * inv;
                 else { int j = jn - (jn > p2); dst[(size_t)in * ld + jn] = src[(size_t)i * ld + j] + u * x.wV[j] * inv; }
@@ -623,12 +660,15 @@ W2B_HDN void mat_rem(const Chains& C, Ctx& x, int f, int nf, int p1, int p2) {
     int k = x.ih[IH_KF + f];
     const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, nf);
     const int ld = C.ld;
+#pragma unroll 1
     for (int j = lane_id(); j < k; j += W2B_WARP) { x.wV[j] = src[(size_t)p1 * ld + j]; x.wQ[j] = src[(size_t)j * ld + p2]; }
     wsync();
     const double ipiv = 1.0 / src[(size_t)p1 * ld + p2];
+#pragma unroll 1
     for (int i = 0; i < k - 1; ++i) {
         int io = i + (i >= p1);
         double c = x.wQ[io];
+#pragma unroll 1
         for (int j = lane_id(); j < k - 1; j += W2B_WARP) {
             int jo = j + (j >= p2);
             dst[(size_t)i * ld + j] = src[(size_t)io * ld + jo] - c * x.wV[jo] * ipiv;
@@ -784,6 +824,7 @@ W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     // same-flavour operators of opposite type with tau <= wmax and tau <= tau_El + taudiff_max
     int i1 = -1, f = 0, type1 = 0, midx = 0; double t1 = 0.0;
     int cum = 0;
+#pragma unroll 1
     for (int base = ia; base < ib; base += W2B_WARP) {
         int i = base + lane_id(); bool act = i < ib;
         int c = 0, lb = 0, fi = 0, ty = 0; double ti = 0.0;
@@ -791,6 +832,7 @@ W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
             int cd = x.code[i]; fi = cd >> 1; ty = cd & 1; ti = x.tau[i];
             int k = x.ih[IH_KF + fi];
             const double* opp = (ty == 0 ? x.ta : x.tc) + (size_t)fi * C.kcap;
+#pragma unroll 1
             for (int a = 0; a < k; ++a) {
                 double v = opp[a];
                 if (v <= ti) ++lb;
@@ -905,6 +947,7 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
 W2B_HDN void trace_full_scalar(const Tables& T, const double* tau, const unsigned char* code, const short* sst, int n, int outer,
                               double& lg, double& sg) {
     double acc = 0.0; int neg = 0;
+#pragma unroll 1
     for (int i = lane_id(); i < n; i += W2B_WARP) {
         int before = i == 0 ? outer : (int)sst[i - 1];
         double tp = i == 0 ? 0.0 : tau[i - 1];
@@ -927,14 +970,17 @@ W2B_HDN void trace_full_scalar(const Tables& T, const double* tau, const unsigne
 W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, double* colv, double* rowv, bool want_inverse, double& lg, double& sg) {
     lg = 0.0; sg = 1.0;
     const int lane = lane_id();
+#pragma unroll 1
     for (int c = 0; c < k; ++c) {
         // pivot search in column c among rows that have not been used as pivot rows (rows >= c after swapping)
         double best = 0.0; int bi = c;
+#pragma unroll 1
         for (int r = c + lane; r < k; r += W2B_WARP) { double v = fabs(a[(size_t)r * ld + c]); if (v > best) { best = v; bi = r; } }
         double bv; int p = wargmax_abs(best, bi, bv);
         if (!(bv > 0.0)) { sg = 0.0; lg = -1.7976931348623157e308; return; }
         if (lane == 0) wI[c] = p;
         if (p != c) {
+#pragma unroll 1
             for (int j = lane; j < k; j += W2B_WARP) { double t = a[(size_t)c * ld + j]; a[(size_t)c * ld + j] = a[(size_t)p * ld + j]; a[(size_t)p * ld + j] = t; }
             sg = -sg;
         }
@@ -945,22 +991,30 @@ W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, double* colv, dou
         wsync();
         if (want_inverse) {
             // Gauss-Jordan step: row c scaled, eliminated from every other row; column c becomes the inverse column
+#pragma unroll 1
             for (int j = lane; j < k; j += W2B_WARP) { const double v = (j == c) ? ipiv : a[(size_t)c * ld + j] * ipiv; a[(size_t)c * ld + j] = v; rowv[j] = v; }
+#pragma unroll 1
             for (int r = lane; r < k; r += W2B_WARP) colv[r] = a[(size_t)r * ld + c];
             wsync();
+#pragma unroll 1
             for (int r = 0; r < k; ++r) {
                 if (r == c) continue;
                 const double fct = colv[r];
+#pragma unroll 1
                 for (int j = lane; j < k; j += W2B_WARP)
                     a[(size_t)r * ld + j] = (j == c) ? -fct * ipiv : a[(size_t)r * ld + j] - fct * rowv[j];
             }
             wsync();
         } else {
+#pragma unroll 1
             for (int j = c + 1 + lane; j < k; j += W2B_WARP) rowv[j] = a[(size_t)c * ld + j];
+#pragma unroll 1
             for (int r = c + 1 + lane; r < k; r += W2B_WARP) colv[r] = a[(size_t)r * ld + c] * ipiv;
             wsync();
+#pragma unroll 1
             for (int r = c + 1; r < k; ++r) {
                 const double fct = colv[r];
+#pragma unroll 1
                 for (int j = c + 1 + lane; j < k; j += W2B_WARP) a[(size_t)r * ld + j] -= fct * rowv[j];
             }
             wsync();
@@ -968,6 +1022,7 @@ W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, double* colv, dou
     }
     if (want_inverse) {
         // undo the row swaps as column swaps in reverse order: inv(P A) = inv(A) P^T
+#pragma unroll 1
         for (int c = k - 1; c >= 0; --c) {
             int p = wI[c];
             if (p != c) for (int r = lane; r < k; r += W2B_WARP) { double t = a[(size_t)r * ld + c]; a[(size_t)r * ld + c] = a[(size_t)r * ld + p]; a[(size_t)r * ld + p] = t; }
@@ -982,13 +1037,16 @@ W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, double* colv, dou
 W2B_HDN void rebuild_inverses(const Tables& T, const Chains& C, Ctx& x, const double* tcs, const double* tas, const int* kfs,
                               bool want_inverse, double& lg, double& sg) {
     lg = 0.0; sg = 1.0;
+#pragma unroll 1
     for (int f = 0; f < T.nf; ++f) {
         int k = kfs[f];
         if (k == 0) continue;
         double* a = Mbuf(C, x, want_inverse ? f : T.nf);
         const double* tc = tcs + (size_t)f * C.kcap; const double* ta = tas + (size_t)f * C.kcap;
         // a[ia][ic] = Delta(ia, ic); its inverse inv[ic][ia] is what M stores at [creator ic][annihilator ia]
+#pragma unroll 1
         for (int ia = 0; ia < k; ++ia)
+#pragma unroll 1
             for (int ic = lane_id(); ic < k; ic += W2B_WARP) a[(size_t)ia * C.ld + ic] = hybrF(T, ta[ia] - tc[ic], f);
         wsync();
         double l, s;
@@ -1019,6 +1077,7 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
         type = 1;
         if (lane_id() == 0) for (int i = 1; i <= nf; ++i) gu[i] = i;
         wsync();
+#pragma unroll 1
         for (int j = 1; j <= nf; ++j) { int i = x.rng.randint(j, nf); if (lane_id() == 0) { int t = gu[j]; gu[j] = gu[i]; gu[i] = t; } wsync(); }
         int flip = x.rng.randint(0, 1);
         if (lane_id() == 0) gu[0] = flip;
@@ -1027,6 +1086,7 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
     log_set(x, 4, type);
     const int flip = gu[0];
     // relabelled operator codes (globalUpdate Trace.F90:2126-2188); flavour f=2b+s <-> gu index b+nb*s+1
+#pragma unroll 1
     for (int i = lane_id(); i < x.n; i += W2B_WARP) {
         int cd = x.code[i], f = cd >> 1, ty = cd & 1, b = f >> 1, s = f & 1;
         int g = gu[b + nb * s + 1] - 1;
@@ -1044,9 +1104,11 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
     } else {                               // perform_global_check_qn Trace.F90:1345-1394
         int pold = 0, pnew = 0;
         // each lane walks one candidate outer superstate through the old and the new sequence
+#pragma unroll 1
         for (int base = 0; base < T.nsst; base += W2B_WARP) {
             int k0 = base + lane_id(); bool act = k0 < T.nsst;
             int co = act ? k0 : -1, cn = act ? k0 : -1;
+#pragma unroll 1
             for (int i = 0; i < x.n; ++i) {
                 int a = x.code[i], b2 = x.sc_code[i];
                 co = co >= 0 ? conn(T, co, a) : -1;
@@ -1061,6 +1123,7 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
         if (pnew > 0) {
             factor = (double)pnew / (double)pold;
             int kk = x.rng.randint(1, pnew);
+#pragma unroll 1
             for (int i = 0; i < T.nsst; ++i) if (x.wI[C.kcap + 32 + i]) { if (--kk <= 0) { new_outer = i; break; } }
             walk_store(T, x.sc_code, 0, x.n, new_outer, x.sc_sst, 0);
         }
@@ -1069,12 +1132,14 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
     long long sumk2 = 0; for (int f = 0; f < nf; ++f) sumk2 += (long long)x.ih[IH_KF + f] * x.ih[IH_KF + f];
     bump_bytes(x, 8ll * sumk2);                   // build Delta_new (write)
     // relabelled flavour tau arrays and orders
+#pragma unroll 1
     for (int f = 0; f < nf; ++f) {
         int b = f >> 1, s = f & 1, g = gu[b + nb * s + 1] - 1, f2 = (g % nb) * 2 + g / nb;
         int k = x.ih[IH_KF + f];
         if (lane_id() == 0) J.knew[f2] = k;
         const double* oc = x.tc + (size_t)f * C.kcap; const double* oa = x.ta + (size_t)f * C.kcap;
         double* nc = x.sc_tc + (size_t)f2 * C.kcap; double* na = x.sc_ta + (size_t)f2 * C.kcap;
+#pragma unroll 1
         for (int i = lane_id(); i < k; i += W2B_WARP) { nc[i] = flip ? oa[i] : oc[i]; na[i] = flip ? oc[i] : oa[i]; }
     }
     wsync();
@@ -1099,9 +1164,12 @@ W2B_HDN void step_glob_finish(const Tables& T, const Run& R, const Chains& C, Ct
     // ---- accept
     long long sumk2 = 0; for (int f = 0; f < nf; ++f) sumk2 += (long long)x.ih[IH_KF + f] * x.ih[IH_KF + f];
     bump_bytes(x, 8ll * sumk2);
+#pragma unroll 1
     for (int i = lane_id(); i < x.n; i += W2B_WARP) { x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
+#pragma unroll 1
     for (int f = 0; f < nf; ++f) {
         int k = J.knew[f];
+#pragma unroll 1
         for (int i = lane_id(); i < k; i += W2B_WARP) { x.tc[(size_t)f * C.kcap + i] = x.sc_tc[(size_t)f * C.kcap + i]; x.ta[(size_t)f * C.kcap + i] = x.sc_ta[(size_t)f * C.kcap + i]; }
     }
     wsync();
@@ -1125,6 +1193,7 @@ W2B_HDN bool step_shift_prepare(const Tables& T, const Run& R, const Chains& C, 
     if (x.n == 0) {                        // StepChangeOuter CTQMC.F90:4570-4638
         const double rand = x.rng.next();
         double acc = 0.0; int pick = T.nsst - 1;
+#pragma unroll 1
         for (int i = 0; i < T.nsst; ++i) { double w = ldg(&T.empty_w[i]); acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
         x.outer = pick; x.tr_log = ldg(&T.empty_log[pick]); x.tr_sign = 1.0;
         if (T.dmax > 1) empty_parts(T, x, pick);
@@ -1140,6 +1209,7 @@ W2B_HDN bool step_shift_prepare(const Tables& T, const Run& R, const Chains& C, 
     const int nwrap = count_lt(x.tau, n, dt);                     // operators passing through tau = 0
     const int first = nwrap == n ? 0 : nwrap;
     const int new_outer = first == 0 ? x.outer : (int)x.sst[first - 1];
+#pragma unroll 1
     for (int i = lane_id(); i < n; i += W2B_WARP) {
         int src = first + i; if (src >= n) src -= n;
         double t = x.tau[src] - dt; if (t < 0.0) t += T.beta;     // modulo(tau - dt, beta)
@@ -1167,6 +1237,7 @@ W2B_HDN void step_shift_finish(const Tables& T, const Run& R, const Chains& C, C
     }
     // ---- accept: update_InvFullHybrShiftTau_diag Trace.F90:2355-2457 (cyclic roll + negation of wrapped rows/columns)
     double detrat = 1.0;
+#pragma unroll 1
     for (int f = 0; f < T.nf; ++f) {
         const int k = x.ih[IH_KF + f];
         if (k == 0) continue;
@@ -1175,8 +1246,10 @@ W2B_HDN void step_shift_finish(const Tables& T, const Run& R, const Chains& C, C
         if (!((w1 == 0 && w2 == 0) || (w1 == k && w2 == k))) {
             const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, T.nf);
             bump_bytes(x, 16ll * k * k);
+#pragma unroll 1
             for (int i = 0; i < k; ++i) {
                 int in = i - w1; double si = 1.0; if (in < 0) { in += k; si = -1.0; }
+#pragma unroll 1
                 for (int j = lane_id(); j < k; j += W2B_WARP) {
                     int jn = j - w2; double sj = si; if (jn < 0) { jn += k; sj = -si; }
                     dst[(size_t)in * C.ld + jn] = sj * src[(size_t)i * C.ld + j];
@@ -1189,6 +1262,7 @@ W2B_HDN void step_shift_finish(const Tables& T, const Run& R, const Chains& C, C
         if ((k & 1) && ((w1 + w2) & 1)) detrat = -detrat;
         // rotate the flavour tau arrays
         double* scc = x.sc_tc + (size_t)f * C.kcap; double* sca = x.sc_ta + (size_t)f * C.kcap;
+#pragma unroll 1
         for (int i = lane_id(); i < k; i += W2B_WARP) {
             int s1 = i + w1; if (s1 >= k) s1 -= k;
             int s2 = i + w2; if (s2 >= k) s2 -= k;
@@ -1197,9 +1271,11 @@ W2B_HDN void step_shift_finish(const Tables& T, const Run& R, const Chains& C, C
             scc[i] = v1; sca[i] = v2;
         }
         wsync();
+#pragma unroll 1
         for (int i = lane_id(); i < k; i += W2B_WARP) { tc[i] = scc[i]; ta[i] = sca[i]; }
         wsync();
     }
+#pragma unroll 1
     for (int i = lane_id(); i < n; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
     wsync();
     x.outer = new_outer;
@@ -1301,6 +1377,7 @@ W2B_HD void prefetch_minv(const Tables& T, const Chains& C, int chain, int f) {
     const int* ih = C.ih + (size_t)chain * IH_STRIDE;
     const int k = ih[IH_KF + f];
     const char* m = (const char*)(C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld));
+#pragma unroll 1
     for (int r = lane_id(); r < k; r += W2B_WARP) asm volatile("prefetch.global.L1 [%0];" ::"l"(m + (size_t)r * C.ld * 8));
 #endif
 }
@@ -1324,15 +1401,18 @@ W2B_HDN void post_move_cta(const Tables& T, const Run& R, Ctx& x, CtaShared& S, 
 W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain_lo, int nloc, long long nsteps,
                       CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf, Ctx& x) {
     const int W = cta_nwarps(), lane = lane_id();
+#pragma unroll 1
     for (int c = cta_tid(); c < nloc; c += cta_nthreads()) { S.left[c] = (int)nsteps; S.parked[c] = 0; }
     if (cta_tid() == 0) { S.nG = 0; S.cG = 0; }
     cta_sync();
     const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
+#pragma unroll 1
     for (;;) {
         if (cta_tid() == 0) { S.nA = 0; S.nA2 = S.nR2 = 0; S.cA = S.cA2 = S.cR2 = S.cA2h = S.cR2h = 0; }
         cta_sync();
         // ---- propose phase: every runnable chain draws move types (reference thresholds CTQMC.F90:8437-8488, plus the two
         //      draws spent on 4-operator / outer moves) and proposes until one proposal survives the quantum-number check
+#pragma unroll 1
         for (int c = wgrab(&S.cA), cnext; c < nloc; c = cnext) {
             cnext = wgrab(&S.cA);
             if (S.left[c] <= 0 || S.parked[c]) continue;
@@ -1340,6 +1420,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
             const int chain = chain_lo + c;
             ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
             if (lane == 0) wgrab_one(&S.nA);                              // S.nA counts the chains that were runnable this round
+#pragma unroll 1
             for (int run = 0; run < R.propose_run && S.left[c] > 0; ++run) {
                 const double r = x.rng.next();
                 if (!(r <= thr_rem)) {                                    // global move / tau shift: park for the rare phase
@@ -1367,8 +1448,10 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
             const int na2 = S.nA2, nr2 = S.nR2;
             // blocked traces: chains whose outer block is larger than 1x1 cost 10-100x more -> serve them first (longest
             // processing time first keeps the tail of the phase short); pass 0 = heavy, pass 1 = the rest
+#pragma unroll 1
             for (int pass = (T.dmax > 1 ? 0 : 1); pass < 2; ++pass) {
                 int* curA = pass == 0 ? &S.cA2h : &S.cA2; int* curR = pass == 0 ? &S.cR2h : &S.cR2;
+#pragma unroll 1
                 for (int i = wgrab(curA); i < na2; i = wgrab(curA)) {
                     const int c = S.lA2[i], chain = chain_lo + c;
                     if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
@@ -1378,6 +1461,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                     post_move_cta(T, R, x, S, c);
                     ctx_store(C, chain, x);
                 }
+#pragma unroll 1
                 for (int i = wgrab(curR); i < nr2; i = wgrab(curR)) {
                     const int c = S.lR2[i], chain = chain_lo + c;
                     if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
@@ -1394,6 +1478,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
         if (rare) {
             // ---- rare phase: global moves and tau shifts of all parked chains
             const int ng = S.nG;
+#pragma unroll 1
             for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {
                 const int c = S.lG[i], chain = chain_lo + c;
                 ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
@@ -1465,6 +1550,7 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
     }
     const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
     ctx_bind(T, R, C, chain, x, nullptr, nullptr, nullptr);
+#pragma unroll 1
     for (int run = 0; run < R.propose_run && left > 0; ++run) {
         const double r = x.rng.next();
         if (!(r <= thr_rem)) {                                    // global move / tau shift: rare stream
@@ -1498,12 +1584,14 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
 W2B_HD void propose_flush(const Chains& C, int parity, const ProposeOut* outs, int count) {
     int* sc = C.sched + parity * SC_STRIDE;
     const int lane = lane_id();
+#pragma unroll 1
     for (int base = 0; base < count; base += W2B_WARP) {
         const int i = base + lane;
         ProposeOut o = {0, 0, -1, 0, -1, 0, 0, 0};
         if (i < count) o = outs[i];
         const int nrun = wsum(o.run), ml = wmax(o.run ? o.left : 0);
         if (lane == 0 && nrun) { atomic_add_int(&sc[SC_NRUN], nrun); atomic_max_int(&sc[SC_MAXLEFT], ml); }
+#pragma unroll 1
         for (int c = 0; c < 3; ++c) {
             {   // decide queue c
                 const int mine = o.dq == c ? 1 : 0, incl = wscan_incl(mine), tot = wbcast(incl, W2B_WARP - 1);
@@ -1519,6 +1607,7 @@ W2B_HD void propose_flush(const Chains& C, int parity, const ProposeOut* outs, i
                     int b = 0; if (lane == 0) b = atomic_add_int(&sc[SC_NT0 + c], tot);
                     b = wbcast(b, 0);
                     int* q = (c == 0 ? C.q_tr0 : (c == 1 ? C.q_tr1 : C.q_tr2)) + (size_t)parity * 4 * C.nchains;
+#pragma unroll 1
                     for (int t = 0; t < cnt; ++t) q[b + incl - cnt + t] = o.tentry | (t << Q_NTSHIFT);
                 }
             }
@@ -1627,17 +1716,23 @@ W2B_HD void init_chain(const Tables& T, const Run& R, const Chains& C, int chain
     Philox rng; rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, (unsigned long long)R.stream << STREAM_SHIFT);
     const double rand = rng.next();
     double acc = 0.0; int pick = T.nsst - 1;
+#pragma unroll 1
     for (int i = 0; i < T.nsst; ++i) { double w = T.empty_w[i]; acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
+#pragma unroll 1
     for (int i = 0; i < IH_STRIDE; ++i) ih[i] = 0;
     ih[IH_OUTER] = pick; ih[IH_NPAIRS] = 0;
+#pragma unroll 1
     for (int f = 0; f <= T.nf; ++f) ih[IH_MSLOT + f] = f;
     dh[DH_DETLOG] = 0.0; dh[DH_DETSIGN] = 1.0; dh[DH_TRLOG] = T.empty_log[pick]; dh[DH_TRSIGN] = 1.0; dh[DH_CFGSIGN] = -1.0;
     C.rng_ctr[chain] = rng.ctr;
+#pragma unroll 1
     for (int i = 0; i < C_NCNT; ++i) C.counters[(size_t)chain * C_NCNT + i] = 0ull;
     if (C.dmax > 1) {
         ih[IH_KV] = 0; ih[IH_BV] = 0; ih[IH_NFREE] = C.ops_cap;
+#pragma unroll 1
         for (int i = 0; i < C.ops_cap; ++i) { C.op_slot[(size_t)chain * C.ops_cap + i] = (unsigned short)i; C.free_slot[(size_t)chain * C.ops_cap + i] = (unsigned short)(C.ops_cap - 1 - i); }
         const double* ev = T.evals + T.offset[pick];
+#pragma unroll 1
         for (int j = 0; j < T.dim[pick]; ++j) { C.pt[(size_t)chain * 2 * C.dmax + 2 * j] = -(ev[j] - T.egs) * T.beta; C.pt[(size_t)chain * 2 * C.dmax + 2 * j + 1] = 1.0; }
     }
 }
@@ -1650,6 +1745,7 @@ constexpr int LEG_CHUNK_BIG = 50;
 W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, double* acc) {
     const int m = ldg(&T.dim[x.outer]), off = ldg(&T.offset[x.outer]);
     double csum = 0.0;
+#pragma unroll 1
     for (int j = lane_id(); j < m; j += W2B_WARP) {
         const double e = x.pt[2 * j + 1] != 0.0 ? w_exp(x.pt[2 * j]) : 0.0;
         atomic_add(&acc[A.o_outerst + off + j], 1.0);
@@ -1662,6 +1758,7 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     if (!R.meas_dm) return;
     if (x.n == 0) {
         const int doff = ldg(&T.dens_off[x.outer]);
+#pragma unroll 1
         for (int j = lane_id(); j < m; j += W2B_WARP)
             atomic_add(&acc[A.o_dens + doff + j + j * m], -x.cfgsign * x.pt[2 * j + 1] * x.tr_sign * w_exp(x.pt[2 * j] - x.tr_log));
         return;
@@ -1682,19 +1779,23 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     if (ih == x.n) mat_identity_compact(B, blg, m);
     else { mat_copy(B, bra_slot(C, x, ih), d * m); mat_copy(blg, x.bralg + (size_t)x.slot[ih] * C.dmax, m); }
     wsync();
+#pragma unroll 1
     for (int e = lane_id(); e < d * m; e += W2B_WARP) {
         const int c = e % d; const double de = ldg(&ev[c]) - e0;
         K[e] *= w_exp(-de * (bh - tauR)); B[e] *= w_exp(-de * (tauL - bh));
     }
+#pragma unroll 1
     for (int j = lane_id(); j < m; j += W2B_WARP) {
         const double kl = klg[j] - (e0 - T.egs) * (bh - tauR), bl = blg[j] - (e0 - T.egs) * (tauL - bh);
         fac[j] = x.tr_sign * (-x.cfgsign) * w_exp(kl + bl - x.tr_log);      // 1 / trval(Trace / TLogTr(kl + bl, -cfgsign))
     }
     wsync();
     const int doff = ldg(&T.dens_off[sst]);
+#pragma unroll 1
     for (int e = lane_id(); e < d * d; e += W2B_WARP) {
         const int a = e % d, c = e / d;
         double v = 0.0;
+#pragma unroll 1
         for (int j = 0; j < m; ++j) v += B[a + (size_t)j * d] * K[c + (size_t)j * d] * fac[j];
         atomic_add(&acc[A.o_dens + doff + a + c * d], v);
     }
@@ -1720,6 +1821,7 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
             atomic_add(&acc[A.o_outerst + off], 1.0); atomic_add(&acc[A.o_signst + off], cfgsign);  // Trace.sign*parttrace.sign = 1 for a 1x1 block
             atomic_add(&acc[A.o_contribst + off], w_exp(dh[DH_TRLOG]));
         }
+#pragma unroll 1
         for (int f = 0; f < T.nf; ++f) {                                                       // MeasExpOrder 3264-3282
             int k = ih[IH_KF + f]; if (k > R.maxhisto) k = R.maxhisto;
             atomic_add(&acc[A.o_histo + f * (R.maxhisto + 1) + k], 1.0);
@@ -1747,16 +1849,19 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
         // warp-reduced first when the whole warp works on one flavour (large orders)
         // flavours with more than one warp-load of pairs: all lanes work on the same flavour anyway -- keep 50 partial sums per
         // lane in registers over all pairs and reduce once per l (two passes over the pairs, the second restarts the recurrence)
+#pragma unroll 1
         for (int f = 0; f < T.nf; ++f) {
             const int k = ih[IH_KF + f];
             if (k * k <= W2B_WARP) continue;
             const double* tc = C.tau_c + ((size_t)chain * T.nf + f) * C.kcap; const double* ta = C.tau_a + ((size_t)chain * T.nf + f) * C.kcap;
             const double* M = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
             double* g = gleg_sh + f * R.nlegmax;
+#pragma unroll 1
             for (int lbase = 0; lbase < R.nlegmax; lbase += LEG_CHUNK_BIG) {
                 double part[LEG_CHUNK_BIG];
 #pragma unroll
                 for (int q = 0; q < LEG_CHUNK_BIG; ++q) part[q] = 0.0;
+#pragma unroll 1
                 for (int p = lane; p < k * k; p += W2B_WARP) {
                     const int ic = p / k, ia = p - ic * k;
                     double Mv = M[(size_t)ic * C.ld + ia];
@@ -1793,8 +1898,10 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
         }
         // small flavours: one lane per pair across all of them
         int offs[NF_MAX + 1]; offs[0] = 0;
+#pragma unroll 1
         for (int f = 0; f < T.nf; ++f) { const int k2 = ih[IH_KF + f] * ih[IH_KF + f]; offs[f + 1] = offs[f] + (k2 <= W2B_WARP ? k2 : 0); }
         const int total = offs[T.nf];
+#pragma unroll 1
         for (int base = 0; base < total; base += W2B_WARP) {
             const int p = base + lane; const bool act = p < total;
             int f = 0;
@@ -1834,15 +1941,18 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
         }
         return;
     }
+#pragma unroll 1
     for (int f = 0; f < T.nf; ++f) {
         const int k = ih[IH_KF + f];
         if (k == 0) continue;
         const double* tc = C.tau_c + ((size_t)chain * T.nf + f) * C.kcap; const double* ta = C.tau_a + ((size_t)chain * T.nf + f) * C.kcap;
         const double* M = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
+#pragma unroll 1
         for (int lbase = 0; lbase < R.nlegmax; lbase += LEG_CHUNK) {
             double part[LEG_CHUNK];                       // statically indexed below -> registers
 #pragma unroll
             for (int q = 0; q < LEG_CHUNK; ++q) part[q] = 0.0;
+#pragma unroll 1
             for (int p = lane; p < k * k; p += W2B_WARP) {
                 int ic = p / k, ia = p - ic * k;
                 double Mv = M[(size_t)ic * C.ld + ia];
@@ -1886,9 +1996,11 @@ W2B_HD void rebuild_chain(const Tables& T, const Run& R, const Chains& C, int ch
     x.wpos = 0; set_window_edges(T, R, x);
     if (lane == 0) for (int f = 0; f <= T.nf; ++f) x.ih[IH_MSLOT + f] = f;
     // flavour arrays
+#pragma unroll 1
     for (int f = 0; f < T.nf; ++f) {
         int kc = 0, ka = 0;
         if (lane == 0) {
+#pragma unroll 1
             for (int i = 0; i < x.n; ++i) {
                 int cd = x.code[i];
                 if ((cd >> 1) != f) continue;

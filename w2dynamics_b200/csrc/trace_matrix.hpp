@@ -348,10 +348,12 @@ W2B_HD void mat_close_parts(const TablesT& T, int sst, double dt, double* K, int
 W2B_HDN void parts_sum(const double* pt, int m, double& tlog, double& tsign) {
     if (m == 1) { tlog = pt[0]; tsign = pt[1]; return; }
     double mx = NEG_HUGE;
+#pragma unroll 1
     for (int j = lane_id(); j < m; j += W2B_WARP) if (pt[2 * j + 1] != 0.0) mx = fmax(mx, pt[2 * j]);
     mx = wmaxd(mx);
     if (mx == NEG_HUGE) { tlog = NEG_HUGE; tsign = 0.0; return; }
     double sum = 0.0;
+#pragma unroll 1
     for (int j = lane_id(); j < m; j += W2B_WARP) if (pt[2 * j + 1] != 0.0) sum += pt[2 * j + 1] * w_exp(pt[2 * j] - mx);
     sum = wsumd(sum);
     if (sum == 0.0) { tlog = NEG_HUGE; tsign = 0.0; return; }
