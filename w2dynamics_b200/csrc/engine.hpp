@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T_, Run R_,
 #endif
 // ---- round kernels (blocked traces)
 constexpr int PROPOSE_WARPS = 2;      // warps per CTA of the propose kernel (its queue pushes are aggregated per CTA)
+#ifndef W2B_TRACE_OCC
+#define W2B_TRACE_OCC 6
+#endif
 constexpr int TRACE_WARPS = 4;        // warps per CTA of the trace kernel (one work matrix per warp in shared memory)
 constexpr int TICKET_BATCH = 1;       // tickets a warp takes per atomic on the round's ticket counter
 constexpr int DECIDE_WARPS = 4;       // warps per CTA of the decide kernel (one work matrix per warp in shared memory)
@@ -172,9 +175,14 @@ __global__ void __launch_bounds__(DECIDE_WARPS * 32, 8) k_decide(Tables T_, Run 
     int* sc = C.sched + parity * SC_STRIDE;
     __shared__ Ctx ctxs[DECIDE_WARPS];
     const int total = sc[SC_NRFIN] + sc[SC_NQ0] + sc[SC_NQ1] + sc[SC_NQ2];
+#ifdef W2B_STATIC_TICKETS
+    for (int t = blockIdx.x * DECIDE_WARPS + warp; t < total; t += gridDim.x * DECIDE_WARPS)
+        phase_decide(T, R, C, A, t, parity, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
+#else
     for (int t0 = wgrab_n(&sc[SC_TICKET], TICKET_BATCH); t0 < total; t0 = wgrab_n(&sc[SC_TICKET], TICKET_BATCH))
       for (int t = t0; t < t0 + TICKET_BATCH && t < total; ++t)
         phase_decide(T, R, C, A, t, parity, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
+#endif
 }
 // global moves / tau shifts, on their own stream beside the round pipeline: scan the chain states, serve ST_RARE_NEW
 __global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T_, Run R_, Chains C_, long long nsteps, int wdoubles, int mdoubles,
@@ -191,13 +199,17 @@ __global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T_, Run R_
         phase_rare(T, R, C, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
 }
 // trace phase of one round (blocked traces): operator products of every surviving proposal on the FP64 tensor pipe
-__global__ void __launch_bounds__(TRACE_WARPS * 32, 6) k_trace(Tables T, Chains C, int tdoubles, int parity) {
+__global__ void __launch_bounds__(TRACE_WARPS * 32, W2B_TRACE_OCC) k_trace(Tables T, Chains C, int tdoubles, int parity) {
     extern __shared__ double smem[];
     double* ws = smem + (size_t)(threadIdx.x >> 5) * tdoubles;
     int* sc = C.sched + parity * SC_STRIDE;
     const int total = sc[SC_NT0] + sc[SC_NT1] + sc[SC_NT2];
+#ifdef W2B_STATIC_TICKETS
+    for (int t = blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5); t < total; t += gridDim.x * TRACE_WARPS) phase_trace(T, C, t, parity, ws);
+#else
     for (int t0 = wgrab_n(&sc[SC_TTICKET], TICKET_BATCH); t0 < total; t0 = wgrab_n(&sc[SC_TTICKET], TICKET_BATCH))
         for (int t = t0; t < t0 + TICKET_BATCH && t < total; ++t) phase_trace(T, C, t, parity, ws);
+#endif
 }
 // population health in three integers: OR of the chains' error flags, largest operator count, largest flavour order
 __global__ void __launch_bounds__(256) k_flags(Chains C, int nf, int* out) {

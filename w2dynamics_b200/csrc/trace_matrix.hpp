@@ -22,8 +22,9 @@
 //   mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 -- sm_100a lowers every f64 mma shape to it, tools/probes/dmma_probe.cu; tcgen05
 //   has no FP64 kind).  What the profile of round 1 showed (profiles/r2b_*): 99 issued instructions per DMMA, two thirds of
 //   them integer / address / control, 76 per k-step.  Hence the shape of the code below:
-//     * the kernel is specialised on the number of 8-row output tiles (1..4): no predicated DMMA, all accumulators and the
-//       A fragments of the current and the next k-step in registers, 10-14 instructions per k-step;
+//     * two instances of the product (up to 16 / up to 32 output rows): no predicated DMMA, all accumulators and the A
+//       fragments of the current and the next k-step in registers; the whole kernel is kept near 2 k SASS instructions because
+//       the warps of an SM sit at unrelated program counters and share a 32 KB instruction cache;
 //     * A fragments come from a host-prepared array in fragment order (one coalesced 16-byte load per lane and tile pair);
 //     * propagation factors are zero-padded to the k range, the tile is zero-padded to the tile shape: no bounds tests in
 //       the loop;
@@ -129,24 +130,23 @@ W2B_HD void tile_scale(int e, double& sc, double& la) {
 }
 
 // acc(8 MT x 8) = O(8 MT x 4 ksteps) * (pw o X): the k-loop.  xb / pwb point at this lane's first B element / factor.
+// acc(8 MT x 8) = O(8 MT x 4 ksteps) * (pw o X): the k-loop.  xb / pwb point at this lane's first B element / factor; np = row-tile
+// pairs the fragment array holds per k-step (1 or 2).  Two instances only (MT = 2: blocks up to 16 rows, MT = 4: up to 32): the
+// kernel's hot code has to stay inside the 32 KB instruction cache of the SM -- with one instance per row-tile count (1..4) and
+// a two-fold unrolled loop the kernel was 3960 SASS instructions and 25 % slower than this 2270-instruction version although
+// it executed fewer instructions (profiles/r2g_*).
 template <int MT>
-W2B_HD void tile_mma(const double2* __restrict__ F, int ksteps, const double* xb, const double* pwb, double (&acc)[MT][2]) {
-    constexpr int NP = (MT + 1) / 2;
-    double2 a[NP], n[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) { a[p] = __ldg(F + p * 32); n[p] = a[p]; }
-#pragma unroll 2
+W2B_HD void tile_mma(const double2* __restrict__ F, int ksteps, const double* xb, const double* pwb, double (&acc)[MT][2], int np) {
+    double2 a0 = __ldg(F), a1 = make_double2(0.0, 0.0), n0 = a0, n1 = a1;
+    if (MT > 2 && np > 1) { a1 = __ldg(F + 32); n1 = a1; }
+#pragma unroll 1
     for (int ks = 0; ks < ksteps; ++ks) {
-        F += NP * 32;
-        if (ks + 1 < ksteps) {                                   // A fragments of the next k-step
-#pragma unroll
-            for (int p = 0; p < NP; ++p) n[p] = __ldg(F + p * 32);
-        }
+        F += np * 32;
+        if (ks + 1 < ksteps) { n0 = __ldg(F); if (MT > 2 && np > 1) n1 = __ldg(F + 32); }      // A fragments of the next k-step
         const double b = xb[4 * ks] * pwb[4 * ks];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][0], acc[mt][1], (mt & 1) ? a[mt >> 1].y : a[mt >> 1].x, b);
-#pragma unroll
-        for (int p = 0; p < NP; ++p) a[p] = n[p];
+        dmma884(acc[0][0], acc[0][1], a0.x, b); dmma884(acc[1][0], acc[1][1], a0.y, b);
+        if (MT > 2) { dmma884(acc[2][0], acc[2][1], a1.x, b); dmma884(acc[3][0], acc[3][1], a1.y, b); }
+        a0 = n0; a1 = n1;
     }
 }
 
@@ -156,7 +156,7 @@ W2B_HD void tile_apply_mt(const double2* __restrict__ F, int ksteps, int d_out, 
     double acc[MT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) { acc[mt][0] = 0.0; acc[mt][1] = 0.0; }
-    tile_mma<MT>(F + lane, ksteps, w.X + g * w.ld + t, w.pw + t, acc);
+    tile_mma<MT>(F + lane, ksteps, w.X + g * w.ld + t, w.pw + t, acc, (((d_out + 7) >> 3) + 1) >> 1);
     int e = 0;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) e = max(e, max(expfield(acc[mt][0]), expfield(acc[mt][1])));
@@ -210,26 +210,22 @@ W2B_HD int tile_apply(const TablesT& T, int sst_in, int opc, double dt, const Ti
     }
     {   // propagation factors, zero beyond d_in (k padding)
         double p = 0.0;
-        if (lane < d_in) p = lane ? exp(-(__ldg(T.evals + q0.w + lane) - e0) * dt) : 1.0;
+        if (lane < d_in) p = lane ? w_exp(-(__ldg(T.evals + q0.w + lane) - e0) * dt) : 1.0;
         w.pw[lane] = p;
     }
     wsync();
     const double2* F = (const double2*)(T.opfrag + q1.y);
     const int ksteps = (d_in + 3) >> 2;
-    switch ((d_out + 7) >> 3) {
-        case 1: tile_apply_mt<1>(F, ksteps, d_out, shift, w, mw, slot, slot_lg); break;
-        case 2: tile_apply_mt<2>(F, ksteps, d_out, shift, w, mw, slot, slot_lg); break;
-        case 3: tile_apply_mt<3>(F, ksteps, d_out, shift, w, mw, slot, slot_lg); break;
-        default: tile_apply_mt<4>(F, ksteps, d_out, shift, w, mw, slot, slot_lg); break;
-    }
+    if (d_out <= 16) tile_apply_mt<2>(F, ksteps, d_out, shift, w, mw, slot, slot_lg);
+    else tile_apply_mt<4>(F, ksteps, d_out, shift, w, mw, slot, slot_lg);
     return sst_out;
 }
 
 // tile <- columns j0 .. j0+mw-1 of a cached d x m block (src points at column j0, src_lg at its scale) or, src == nullptr,
 // of the identity I_m; padding rows / columns of the tile are zeroed
-W2B_HD void tile_load(const Tile& w, const double* src, const double* src_lg, int d, int j0, int mw) {
+W2B_HDN void tile_load(const Tile& w, const double* src, const double* src_lg, int d, int j0, int mw) {
     const int lane = lane_id(), R = mat_cols(d);
-#pragma unroll
+#pragma unroll 1
     for (int col = 0; col < TILE_COLS; ++col) {
         double v = 0.0;
         if (src) { if (lane < d && col < mw) v = src[col * d + lane]; }
@@ -251,7 +247,7 @@ W2B_HD void tile_close(const TablesT& T, int sst, double dt, const Tile& w, cons
     const double e0 = __hiloint2double(q1.w, q1.z);
     {
         double p = 0.0;
-        if (lane < d) p = lane ? exp(-(__ldg(T.evals + q0.w + lane) - e0) * dt) : 1.0;
+        if (lane < d) p = lane ? w_exp(-(__ldg(T.evals + q0.w + lane) - e0) * dt) : 1.0;
         w.pw[lane] = p;
     }
     wsync();
@@ -261,7 +257,7 @@ W2B_HD void tile_close(const TablesT& T, int sst, double dt, const Tile& w, cons
         s += __shfl_xor_sync(W2B_FULL, s, 1); s += __shfl_xor_sync(W2B_FULL, s, 2);
     } else if (g < mw) s = w.pw[j0 + g] * w.X[g * w.ld + j0 + g];
     if (t == 0 && g < mw) {
-        if (s != 0.0) { pt[2 * g] = w.lg[g] + (B ? blg[g] : 0.0) - (e0 - T.egs) * dt + log(fabs(s)); pt[2 * g + 1] = s < 0.0 ? -1.0 : 1.0; }
+        if (s != 0.0) { pt[2 * g] = w.lg[g] + (B ? blg[g] : 0.0) - (e0 - T.egs) * dt + w_log(fabs(s)); pt[2 * g + 1] = s < 0.0 ? -1.0 : 1.0; }
         else { pt[2 * g] = NEG_HUGE; pt[2 * g + 1] = 0.0; }
     }
     wsync();
