@@ -20,6 +20,18 @@ def ratio_close(le, lo):
         return (np.abs(le - lo) <= RTOL) | (np.abs(re_ - ro) <= RTOL * np.abs(ro) + AFLOOR)
 
 
+def floor_usage(log, ref):
+    """How many replayed moves pass only through the absolute floor (their relative deviation exceeds RTOL): (det, trace, moves)."""
+    out = []
+    for col in (7, 9):
+        le, lo = log[:, col], ref[:, col]
+        with np.errstate(over="ignore", invalid="ignore"):
+            re_, ro = np.exp(np.minimum(le, 700.0)), np.exp(np.minimum(lo, 700.0))
+            rel_ok = (np.abs(le - lo) <= RTOL) | (np.abs(re_ - ro) <= RTOL * np.abs(ro))
+        out.append(int((~rel_ok).sum()))
+    return out[0], out[1], int(log.shape[0])
+
+
 def assert_replay(log, ref):
     assert log.shape == ref.shape
     bad = np.nonzero((log[:, INTS] != ref[:, INTS]).any(1))[0]

@@ -11,7 +11,7 @@ import pytest
 from oracle.oracle import OracleChain
 from w2dynamics_b200 import problems
 
-from _parity import assert_replay
+from _parity import assert_replay, floor_usage
 
 pytestmark = pytest.mark.gpu
 
@@ -22,6 +22,14 @@ def replay(eng, p, chain, nsteps):
     orc.init_counters()
     ref = orc.steps(nsteps, log=True)
     assert_replay(log, ref)
+    fd, ft, n = floor_usage(log, ref)
+    # the absolute floor 1e-14 of tests/_parity.py is only allowed to matter for ratios that are numerical zeros (|r| < 1e-4)
+    print("replay %s: %d moves, %d determinant ratios and %d trace ratios outside 1e-10 relative (inside the 1e-14 absolute floor)" % (p.name, n, fd, ft))
+    small = np.exp(np.minimum(ref[:, 9], 0.0)) < 1e-4
+    with np.errstate(over="ignore", invalid="ignore"):
+        rel_bad = np.abs(np.exp(np.minimum(log[:, 9], 700.0)) - np.exp(np.minimum(ref[:, 9], 700.0))) > 1e-10 * np.exp(np.minimum(ref[:, 9], 700.0))
+    assert not np.any(rel_bad & ~small & (np.abs(log[:, 9] - ref[:, 9]) > 1e-10)), "trace ratio of O(1) magnitude outside 1e-10 relative"
+    assert fd + ft <= 0.002 * n
     return log, orc
 
 
