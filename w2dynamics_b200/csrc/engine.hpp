@@ -211,6 +211,11 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32, W2B_TRACE_OCC) k_trace(Table
         for (int t = t0; t < t0 + TICKET_BATCH && t < total; ++t) phase_trace(T, C, t, parity, ws);
 #endif
 }
+// set_taudiffmax -> init_window for every chain: window_position = 0, NPairs invalid (Trace.F90:1608-1648)
+__global__ void __launch_bounds__(256) k_reset_window(Chains C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C.nchains) { C.ih[(size_t)c * IH_STRIDE + IH_WPOS] = 0; C.ih[(size_t)c * IH_STRIDE + IH_NPAIRS] = -1; }
+}
 // population health in three integers: OR of the chains' error flags, largest operator count, largest flavour order
 __global__ void __launch_bounds__(256) k_flags(Chains C, int nf, int* out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,6 +466,11 @@ public:
         if (tdm > 0.0) { R.taudiff_max = tdm; R.num_windows = std::max((int)std::floor(T.beta / tdm) - 1, 1); }
         else { R.taudiff_max = T.beta; R.num_windows = 1; }
         // window_position = 0, NPairs invalid for every chain
+#if W2B_DEVICE
+        k_reset_window<<<(C.nchains + 255) / 256, 256>>>(C); ++launches;
+        W2B_CUDA_CHECK(cudaGetLastError());
+        return;
+#endif
         std::vector<int> ih((size_t)C.nchains * IH_STRIDE);
         d2h(ih.data(), C.ih, ih.size());
         for (int c = 0; c < C.nchains; ++c) { ih[(size_t)c * IH_STRIDE + IH_WPOS] = 0; ih[(size_t)c * IH_STRIDE + IH_NPAIRS] = -1; }

@@ -8,6 +8,7 @@
 #include <limits>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "atomic.hpp"
@@ -86,13 +87,20 @@ inline void normalise_slab(const AtomicTables& at, const Accum& A, const Run& R,
     // ---- density matrix estimators (8701-8717)
     std::vector<std::vector<double>> rho(nsst);
     for (int k = 0; k < nsst; ++k) { int d = at.dim[k]; rho[k].resize((size_t)d * d); for (int i = 0; i < d * d; ++i) rho[k][i] = slab[A.o_dens + dens_off[k] + i] * zs; }
-    auto& occ = out.arr["occ"]; occ.assign((size_t)nf * nf, 0.0);
-    auto& rho1 = out.arr["rho1"]; rho1.assign((size_t)nf * nf, 0.0);
-    auto& rho2 = out.arr["rho2"]; rho2.assign((size_t)nf * nf * nf * nf, 0.0);
+    auto& occ_out = out.arr["occ"]; occ_out.assign((size_t)nf * nf, 0.0);
+    auto& rho1_out = out.arr["rho1"]; rho1_out.assign((size_t)nf * nf, 0.0);
+    auto& rho2_out = out.arr["rho2"]; rho2_out.assign((size_t)nf * nf * nf * nf, 0.0);
     auto opc = [&](int b, int s, int ca) { return (b * 2 + s) * 2 + (ca - 1); };
     auto trace_with = [&](const std::vector<double>& X, int rows, int cols, const double* B) {   // trace(X(rows x cols) * B(cols x rows))
         double t = 0; for (int i = 0; i < rows; ++i) for (int p = 0; p < cols; ++p) t += X[i + (size_t)p * rows] * B[p + (size_t)i * cols]; return t; };
-    for (int k = 0; k < nsst; ++k) {
+    // the blocks are independent: host threads take blocks round-robin and sum into private copies (a few hundred small matrix
+    // products per block for the 5-orbital problem; single-threaded this was half of an end-to-end solve of one accumulation block)
+    int nthr = (int)std::thread::hardware_concurrency(); if (nthr < 1) nthr = 1; if (nthr > 8) nthr = 8; if (nthr > nsst) nthr = nsst;
+    std::vector<std::vector<double>> p_occ(nthr, std::vector<double>(occ_out.size(), 0.0)), p_rho1(nthr, std::vector<double>(rho1_out.size(), 0.0)),
+                                     p_rho2(nthr, std::vector<double>(want_rho2 ? rho2_out.size() : 0, 0.0));
+    auto work = [&](int tid) {
+    std::vector<double>& occ = p_occ[tid]; std::vector<double>& rho1 = p_rho1[tid]; std::vector<double>& rho2 = p_rho2[tid];
+    for (int k = tid; k < nsst; k += nthr) {
         const int d = at.dim[k];
         for (int b4 = 0; b4 < nb; ++b4) for (int s4 = 0; s4 < 2; ++s4) {
             // t1 = rho * c4^+ (from n3 -> k)  ; requires some n3 with Connect(n3, 4, c^dag) == k  <=> Connect(k, 4, c) == n3
@@ -146,6 +154,14 @@ inline void normalise_slab(const AtomicTables& at, const Accum& A, const Run& R,
                 }
             }
         }
+    }
+    };
+    if (nthr == 1) work(0);
+    else { std::vector<std::thread> th; for (int t = 0; t < nthr; ++t) th.emplace_back(work, t); for (auto& t : th) t.join(); }
+    for (int t = 0; t < nthr; ++t) {
+        for (size_t i = 0; i < occ_out.size(); ++i) occ_out[i] += p_occ[t][i];
+        for (size_t i = 0; i < rho1_out.size(); ++i) rho1_out[i] += p_rho1[t][i];
+        for (size_t i = 0; i < p_rho2[t].size(); ++i) rho2_out[i] += p_rho2[t][i];
     }
     // densitymatrix in the occupation basis (3163-3179), stored (NStates x NStates) in block order
     auto& dm = out.arr["densitymatrix"]; dm.assign((size_t)ns * ns, 0.0);
