@@ -379,6 +379,10 @@ public:
             std::vector<double> la(std::max(R.nlegmax, 2), 0.0), lb(std::max(R.nlegmax, 2), 0.0);
             for (int l = 2; l < R.nlegmax; ++l) { const int ll = l - 1; la[l] = (2.0 * ll + 1.0) / (double)(ll + 1); lb[l] = (double)ll / (double)(ll + 1); }
             T.leg_a = keep(dev_upload(la)); T.leg_b = keep(dev_upload(lb));
+            std::vector<double> lg(la.size(), 0.0), lc(la.size(), 1.0);
+            for (int l = 1; l < (int)lc.size(); ++l) lc[l] = lc[l - 1] * (2.0 * l - 1.0) / (double)l;       // c_l = (2l)! / (2^l l!^2)
+            for (int l = 2; l < (int)lg.size(); ++l) lg[l] = ((double)(l - 1) * (l - 1)) / ((2.0 * l - 1.0) * (2.0 * l - 3.0));
+            T.leg_g = keep(dev_upload(lg)); T.leg_c = keep(dev_upload(lc));
         }
         T.op_off = keep(dev_upload(at.op_off)); T.opdata = keep(dev_upload(at.opdata)); T.evals = keep(dev_upload(at.evals));
 

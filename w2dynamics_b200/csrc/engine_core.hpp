@@ -58,6 +58,7 @@ struct Tables {
     const double* empty_w;       // [nsst] normalised empty-trace weights (init_Trace / StepChangeOuter)
     const double* empty_log;     // [nsst] log of the empty trace of each outer superstate
     const double* leg_a; const double* leg_b;   // Legendre recurrence coefficients (2l-1)/l and (l-1)/l, [NLegMax]
+    const double* leg_g; const double* leg_c;   // monic recurrence g_l = (l-1)^2/((2l-1)(2l-3)) and leading coefficients c_l: P_l = c_l Q_l
     const OpDesc* desc;          // [nsst*nops] packed operator records of the blocked trace
     const long long* op_off;     // matrix path
     const double* opdata;
@@ -1847,51 +1848,56 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
         // pairs per flavour: a lane-per-pair loop inside one flavour leaves 3/4 of the warp idle); each lane runs the whole
         // three-term recurrence (CTQMC.F90:2407-2420, coefficients tabulated) and adds into the CTA's shared accumulator --
         // warp-reduced first when the whole warp works on one flavour (large orders)
-        // flavours with more than one warp-load of pairs: all lanes work on the same flavour anyway -- keep 50 partial sums per
-        // lane in registers over all pairs and reduce once per l (two passes over the pairs, the second restarts the recurrence)
-#pragma unroll 1
+        // flavours with more than one warp-load of pairs: all lanes work on the same flavour anyway -- one pair per lane, 50 partial
+        // sums per lane in registers over all pairs, one warp reduction per l at the end (two passes over the pairs, the second
+        // restarts the recurrence without accumulating).  The recurrence runs on MONIC Legendre polynomials,
+        //     Q_l = x Q_{l-1} - g_l Q_{l-2},  g_l = (l-1)^2 / ((2l-1)(2l-3)),  P_l = c_l Q_l,
+        // two FP64 operations per step instead of three (CTQMC.F90:2407-2420 divides by l in every step); the leading coefficients
+        // c_l multiply the reduced sums once.  At beta = 200 (5600 pairs per flavour) this loop was a third of the whole step.
         for (int f = 0; f < T.nf; ++f) {
             const int k = ih[IH_KF + f];
             if (k * k <= W2B_WARP) continue;
             const double* tc = C.tau_c + ((size_t)chain * T.nf + f) * C.kcap; const double* ta = C.tau_a + ((size_t)chain * T.nf + f) * C.kcap;
             const double* M = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
             double* g = gleg_sh + f * R.nlegmax;
+            const double* gam = T.leg_g;
 #pragma unroll 1
             for (int lbase = 0; lbase < R.nlegmax; lbase += LEG_CHUNK_BIG) {
                 double part[LEG_CHUNK_BIG];
 #pragma unroll
                 for (int q = 0; q < LEG_CHUNK_BIG; ++q) part[q] = 0.0;
+                int ic = 0, ia = lane;                                  // pair p = ic * k + ia, advanced without divisions
+                while (ia >= k) { ia -= k; ++ic; }
 #pragma unroll 1
                 for (int p = lane; p < k * k; p += W2B_WARP) {
-                    const int ic = p / k, ia = p - ic * k;
                     double Mv = M[(size_t)ic * C.ld + ia];
                     const double dtau = ta[ia] - tc[ic]; double xx; int idt;
                     if (dtau > 0.0) { idt = (int)(dtau / beta * (double)R.ntau) + 1; xx = 2.0 / beta * dtau - 1.0; }
                     else { idt = (int)((beta + dtau) / beta * (double)R.ntau) + 1; xx = 2.0 / beta * (beta + dtau) - 1.0; Mv = -Mv; }
                     Mv *= cfgsign;
                     if (lbase == 0) { if (idt > R.ntau) idt = R.ntau; atomic_add(&acc[A.o_gtau + f * R.ntau + idt - 1], Mv); }
-                    double Plx = 0.0, Plm1 = 0.0, Pl = 0.0;
-#pragma unroll 1
-                    for (int l = 0; l < lbase; ++l) {
-                        if (l == 0) Pl = 1.0; else if (l == 1) Pl = xx;
-                        else Pl = ldg(&T.leg_a[l]) * xx * Plx - ldg(&T.leg_b[l]) * Plm1;
-                        Plm1 = Plx; Plx = Pl;
+                    double qm1 = 1.0, q0 = xx;                          // Q_0, Q_1
+                    int l0 = 2;
+                    if (lbase == 0) { part[0] += Mv; part[1] += Mv * xx; }
+                    else {
+#pragma unroll 4
+                        for (int l = 2; l < lbase; ++l) { const double qn = fma(xx, q0, -ldg(&gam[l]) * qm1); qm1 = q0; q0 = qn; }
+                        l0 = 0;
                     }
 #pragma unroll
                     for (int q = 0; q < LEG_CHUNK_BIG; ++q) {
-                        const int l = lbase + q;
-                        if (l < R.nlegmax) {
-                            if (l == 0) Pl = 1.0; else if (l == 1) Pl = xx;
-                            else Pl = ldg(&T.leg_a[l]) * xx * Plx - ldg(&T.leg_b[l]) * Plm1;
-                            part[q] += Mv * Pl;
-                            Plm1 = Plx; Plx = Pl;
+                        if (q >= l0 && lbase + q < R.nlegmax) {
+                            const double qn = fma(xx, q0, -ldg(&gam[lbase + q]) * qm1);
+                            part[q] += Mv * qn;
+                            qm1 = q0; q0 = qn;
                         }
                     }
+                    ia += W2B_WARP; while (ia >= k) { ia -= k; ++ic; }
                 }
 #pragma unroll
                 for (int q = 0; q < LEG_CHUNK_BIG; ++q) {
                     const double sum = wsum(part[q]);
-                    if (lane == 0 && lbase + q < R.nlegmax) g[lbase + q] += sum;
+                    if (lane == 0 && lbase + q < R.nlegmax) g[lbase + q] += sum * ldg(&T.leg_c[lbase + q]);
                 }
             }
             wsync();
