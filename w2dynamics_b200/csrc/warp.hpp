@@ -7,7 +7,7 @@
 // The same source also compiles with W2B_HOST_EMU (g++, W2B_WARP == 1) into a
 // test-only library so that the *logic* of the kernels can be checked against the
 // oracle on machines without a GPU (tests/test_engine_logic.py).  That build is not
-// reachable from the product API (w2dynamics_b200/mctqmc.py loads the CUDA library only
+// reachable from the product API (w2dynamics_b200/CTQMC.py loads the CUDA library only
 // and fails loudly without it).
 #pragma once
 #include <cstdint>

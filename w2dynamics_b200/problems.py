@@ -11,9 +11,9 @@ route with ``General.DOS = EDcheck`` (reference ``cthyb:170-198``):
   (``w2dyn/dmft/interaction.py:171-273, 275-425``),
 * ``muimp`` handed to the engine already negated (``cthyb_solver.py:255``).
 
-The U-matrix builders are our own implementations; ``tests/test_problems.py``
+The U-matrix builders are our own implementations; ``tests/test_oracle_pins.py``
 pins them against vectors generated from the reference's ``interaction.py``
-(``tests/golden/umatrix_*.npz``, generator ``tools/gen_golden.py``).
+(``tests/golden/umatrix.npz``, generator ``tools/gen_golden.py``).
 """
 from __future__ import annotations
 
