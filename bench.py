@@ -11,11 +11,12 @@ accepted or not (CTQMC.F90:8428-8434).  value = chains * NCorr * K * N / time.
 
 Timed region of `value`: chain state resident in HBM, K steps, (N > 1: plus the single all-reduce of the raw
 accumulators that ends an accumulation), CUDA events on the launching stream, max over ranks.
-`e2e`: the same K accumulation blocks through the reference plugin's call sequence (w2dynamics_b200/solver_sequence.py) with
-HOST arrays: every step is one full solve -- init_paras, init_solver(u, F(tau), mu from host memory), set_taudiffmax,
-ctqmc_warmup(0), ctqmc_measure(1,1) with Nmeas = 1, every get_resultset array read back to the host, dest_ctqmc.  The chain
-population is kept thermalised across solves (option reuse_population = ReuseMCConfig for all chains): a revived population is
-rebuilt on the device from its operator lists with the new F(tau).
+`e2e`: the same K accumulation blocks as ONE call of the reference plugin's solve (w2dynamics_b200/solver_sequence.py, the call a
+user of the reference makes) with HOST arrays: init_paras, init_solver(u, F(tau), mu from host memory), set_taudiffmax,
+ctqmc_warmup(0), ctqmc_measure(1,1) with Nmeas = K, every get_resultset array read back to the host, dest_ctqmc -- all inside the
+timed region.  The chain population is kept thermalised across solves (option reuse_population = ReuseMCConfig for all chains): a
+revived population is rebuilt on the device from its operator lists with the new F(tau).  `e2e.per_solve_of_one_step` is the same
+with Nmeas = 1: the fixed cost of a solve charged to a single accumulation block.
 `roofline`: dominant kernel k_sweep, algorithmic bytes counted in-kernel per move (DESIGN.md "Roofline accounting")
 divided by the kernel's summed event time.  `cpu_baseline`: the oracle (CPU restatement of the reference algorithm;
 the Fortran reference cannot be built in this image) on all host cores, bounded sample.
@@ -367,31 +368,40 @@ def run_engine(args, cfg):
         tte = {"error": str(exc)[:200]}
     eng.dest_ctqmc()                                            # parks the population again
 
-    # ---- e2e: K plugin solves, each = init_paras + init_solver(host u, F(tau), mu) + set_taudiffmax + ctqmc_warmup(0) +
-    # ctqmc_measure(1 accumulation block; N > 1: + the library's all-reduce) + every result array of get_resultset read back to
-    # host memory + dest_ctqmc / dest_paras.  The population is the one thermalised above (reuse_population).
-    seq = plugin(0, 1)
-    for it in range(min(args.warmup, 3)):
-        seq.solve(1 + it)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    hb0, db0 = eng.scalar("h2d_bytes"), eng.scalar("d2h_bytes")
-    t0 = time.perf_counter()
-    e0.record()
-    res = None
-    for it in range(args.steps):
-        res = seq.solve(10 + it)
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    hb1, db1 = eng.scalar("h2d_bytes"), eng.scalar("d2h_bytes")
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    # ---- e2e: the K steps as ONE call of the reference plugin's solve (what a user of the reference runs): init_paras +
+    # init_solver(host u, F(tau), mu) + set_taudiffmax + ctqmc_warmup(0) + ctqmc_measure(1,1) with Nmeas = K accumulation blocks
+    # (N > 1: + the library's all-reduce) + every result array of get_resultset read back to host memory + dest_ctqmc /
+    # dest_paras -- everything inside the timed region.  The population is the one thermalised above (reuse_population: revived
+    # and rebuilt from its operator lists with the uploaded F(tau)).  `per_solve_of_one_step`: the same with Nmeas = 1, i.e. the
+    # fixed cost of a solve (upload, rebuild, normalisation, result copies) charged to a single accumulation block.
+    def timed_solves(nmeas, nsolves, it0):
+        seq = plugin(0, nmeas)
+        for it in range(2):
+            seq.solve(it0 + it)                                # warm-up solves (untimed)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        hb0, db0 = eng.scalar("h2d_bytes"), eng.scalar("d2h_bytes")
+        t0 = time.perf_counter()
+        e0.record()
+        res = None
+        for it in range(nsolves):
+            res = seq.solve(it0 + 2 + it)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        hb1, db1 = eng.scalar("h2d_bytes"), eng.scalar("d2h_bytes")
+        if world > 1:
+            t = torch.tensor([ms_], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        return ms_, hb1 - hb0, db1 - db0, res
+    e2e_ms, hb, db, res = timed_solves(args.steps, 1, 100)
+    hb0 = db0 = 0.0; hb1, db1 = hb, db
     e2e_val = moves / (e2e_ms * 1e-3)
     res_bytes = int(sum(np.asarray(v).nbytes for v in res.values()))
+    one_ms, _, _, _ = timed_solves(1, 5, 200)
+    one_val = float(nchains) * ncorr * 5 * world / (one_ms * 1e-3)
     eng.set_option("reuse_population", 0)
     eng.init_paras(p.pstring()); eng.dest_ctqmc(); eng.dest_paras()    # drop the parked population (frees the device memory for the next config)
 
@@ -418,8 +428,9 @@ def run_engine(args, cfg):
                    "l2": "inverse-matrix state %.1f GB per GPU > 126 MB L2 (inputs larger than L2, no flush needed)" % state_gb,
                    "error_flags": err},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int((hb1 - hb0) / args.steps), "d2h_bytes_per_step": int((db1 - db0) / args.steps),
-                "ms_per_step": e2e_ms / args.steps, "result_bytes_per_step": res_bytes,
-                "path": "per step one full plugin solve through the C ABI: init_paras, init_solver(host arrays), set_taudiffmax, ctqmc_warmup(0), ctqmc_measure(1,1) with Nmeas=1, all get_resultset arrays, dest_ctqmc"},
+                "ms_per_step": e2e_ms / args.steps, "result_bytes_per_solve": res_bytes,
+                "path": "one call of the reference plugin's solve through the C ABI with Nmeas = steps: init_paras, init_solver(host arrays), set_taudiffmax, ctqmc_warmup(0), ctqmc_measure(1,1), all get_resultset arrays, dest_ctqmc; bytes are per step (totals / steps)",
+                "per_solve_of_one_step": {"value": one_val, "ms_per_solve": one_ms / 5}},
         "gpu_launches": int(launches1 - launches0),
         "kernel_ms": {"k_sweep": t_sweep / args.steps, "k_measure": t_meas / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

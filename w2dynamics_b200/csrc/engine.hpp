@@ -131,7 +131,16 @@ __global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T_, Run R_,
 }
 #endif
 // ---- round kernels (blocked traces)
-constexpr int PROPOSE_WARPS = 2;      // warps per CTA of the propose kernel (its queue pushes are aggregated per CTA)
+#ifndef W2B_PROPOSE_WARPS
+#define W2B_PROPOSE_WARPS 2
+#endif
+#ifndef W2B_PROPOSE_OCC
+#define W2B_PROPOSE_OCC 20
+#endif
+#ifndef W2B_DECIDE_OCC
+#define W2B_DECIDE_OCC 8
+#endif
+constexpr int PROPOSE_WARPS = W2B_PROPOSE_WARPS;      // warps per CTA of the propose kernel (its queue pushes are aggregated per CTA)
 #ifndef W2B_TRACE_OCC
 #define W2B_TRACE_OCC 6
 #endif
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(256) k_sweep_begin(Chains C, long long nsteps)
 // propose phase of one round: one warp per chain; the CTA's results reach the round's queues with one atomic per queue
 // (the parameter structs are copied to shared memory once per CTA: passing kernel parameters by reference to out-of-line
 // functions would otherwise spill a private copy per thread to local memory)
-__global__ void __launch_bounds__(PROPOSE_WARPS * 32, 20) k_propose(Tables T_, Run R_, Chains C_, long long nsteps, int parity, int log_chain, double* logbuf) {
+__global__ void __launch_bounds__(PROPOSE_WARPS * 32, W2B_PROPOSE_OCC) k_propose(Tables T_, Run R_, Chains C_, long long nsteps, int parity, int log_chain, double* logbuf) {
     __shared__ ProposeOut outs[PROPOSE_WARPS];
     __shared__ Ctx ctxs[PROPOSE_WARPS];
     __shared__ Tables T; __shared__ Run R; __shared__ Chains C;
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(PROPOSE_WARPS * 32, 20) k_propose(Tables T_, R
     if (warp == 0) propose_flush(C, parity, outs, PROPOSE_WARPS);
 }
 // decide phase of one round: persistent warps take tickets (rare moves first, then decide queues by outer block size)
-__global__ void __launch_bounds__(DECIDE_WARPS * 32, 8) k_decide(Tables T_, Run R_, Chains C_, Accum A_, long long nsteps, int wdoubles, int mdoubles, int parity,
+__global__ void __launch_bounds__(DECIDE_WARPS * 32, W2B_DECIDE_OCC) k_decide(Tables T_, Run R_, Chains C_, Accum A_, long long nsteps, int wdoubles, int mdoubles, int parity,
                                                               int log_chain, double* logbuf) {
     extern __shared__ double smem[];
     __shared__ Tables T; __shared__ Run R; __shared__ Chains C; __shared__ Accum A;
