@@ -469,6 +469,9 @@ W2B_HD void job_load_bra(const Tables& T, const JobView& V, const Tile& w, int i
     const size_t sl = V.slot[i];
     tile_load(w, V.bra + sl * V.mstride + j0 * d, V.bralg + sl * V.dmax + j0, d, j0, mw);
 }
+// Measured alternative (round 2): ONE job per proposal over all column tiles of the outer block, sharing step records, operator
+// descriptors and exp() factors: 15 % fewer instructions, but 57.9 instead of 39.7 ms per C4 step -- the kernel is bound by the
+// latency of its longest jobs (a warp issues one instruction every ~16 cycles), so four short jobs on four warps beat one long one.
 W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* ws) {
     const int lane = lane_id();
     const Tile w{ws, ws + C.ldx * TILE_COLS, ws + C.ldx * TILE_COLS + TILE_COLS, C.ldx};
