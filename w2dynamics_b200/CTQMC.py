@@ -151,7 +151,7 @@ class MCTQMC:
         # the library is a process-wide singleton like the reference's module: every engine states ALL its options, so that
         # nothing set through another MCTQMC object lingers
         opts = {"kcap": 0, "ops_cap": 0, "cta_warps": 0, "batch_chains": 0, "scheduler": 0, "chain_base": 0, "propose_run": 4,
-                "prefetch": 1, "debug_same_key": 0, "time_kernels": 0, "reuse_population": 0}
+                "prefetch": 1, "debug_same_key": 0, "time_kernels": 0, "reuse_population": 0, "lu_groups": 0}
         opts.update(self._options)
         opts.setdefault("nchains", self._nchains)
         opts.setdefault("nbins", self._nbins)

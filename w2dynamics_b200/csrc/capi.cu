@@ -204,7 +204,7 @@ std::string key_of(const Params& p) {
 }
 bool same_opt(const EngineOptions& a, const EngineOptions& b) {
     return a.nchains == b.nchains && a.nbins == b.nbins && a.kcap == b.kcap && a.ops_cap == b.ops_cap && a.cta_warps == b.cta_warps &&
-           a.batch_chains == b.batch_chains && a.scheduler == b.scheduler && a.seed == b.seed && a.chain_base == b.chain_base;
+           a.batch_chains == b.batch_chains && a.scheduler == b.scheduler && a.lu_groups == b.lu_groups && a.seed == b.seed && a.chain_base == b.chain_base;
 }
 
 void bins_materialise() {
@@ -288,6 +288,7 @@ int w2b_set_option(const char* key, double value) {
     else if (k == "cta_warps") S.opt.cta_warps = (int)value;
     else if (k == "batch_chains") S.opt.batch_chains = (int)value;
     else if (k == "scheduler") S.opt.scheduler = (int)value;
+    else if (k == "lu_groups") S.opt.lu_groups = (int)value;
     else if (k == "device") S.device = (int)value;
     else if (k == "nmeas_override") S.nmeas_override = (long long)value;
     else if (k == "debug_same_key") S.same_key = (int)value;

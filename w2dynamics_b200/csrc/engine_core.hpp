@@ -90,6 +90,7 @@ struct RareJob {
     double dt, factor, dn_log, dn_sign;
     int kind, new_outer, type, stored;       // kind 3 = global move, 4 = tau shift; stored: the trace kernel filled the ket caches of the new configuration
     int knew[NF_MAX];
+    double tn_log, tn_sign;                  // staged global moves of the CTA scheduler: local trace of the proposed configuration
 };
 
 // round scheduler counters (device memory, two sets used in alternation by consecutive rounds)
@@ -317,10 +318,11 @@ W2B_HDN int palt_flavour(const Chains& C, const Ctx& x, int f) {
     int c = 0;
 #pragma unroll 1
     for (int i = lane_id(); i < k; i += W2B_WARP) {
-        double t = tc[i]; int pos = i;
+        const double t = tc[i];
+        int lo = 0, hi = k;                                   // annihilators before this creator: lower bound in the sorted times
 #pragma unroll 1
-        for (int a = 0; a < k; ++a) pos += (ta[a] < t);
-        c += ((pos & 1) == 0);
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ta[mid] < t) lo = mid + 1; else hi = mid; }
+        c += (((i + lo) & 1) == 0);
     }
     return wsum(c) & 1;
 }
@@ -1063,7 +1065,7 @@ W2B_HDN void rebuild_inverses(const Tables& T, const Chains& C, Ctx& x, const do
 // Split in two halves around the local trace of the proposed configuration so that blocked traces can run in the trace
 // kernel: prepare (update choice, relabelling, quantum numbers, determinant from scratch) returns true when a trace is
 // needed; finish takes (log, sign) of that trace, draws the Metropolis number and applies the update.
-W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J) {
+W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, bool with_lu = true) {
     log_begin(x, 3);
     bump(x, C_TRYGLOB);
     if (x.n == 0) { log_end(x, 2); return false; }
@@ -1147,26 +1149,33 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
         for (int i = lane_id(); i < k; i += W2B_WARP) { nc[i] = flip ? oa[i] : oc[i]; na[i] = flip ? oc[i] : oa[i]; }
     }
     wsync();
+    if (lane_id() == 0) { J.kind = 3; J.new_outer = new_outer; J.type = type; J.factor = factor; J.stored = 0; }
+    wsync();
+    if (!with_lu) return true;               // staged form (CTA scheduler): the determinants come from the group LU in shared memory
     // determinant of the new configuration from scratch (LU in the spare buffer).  The reference obtains the old determinant
     // from an LU of the stored inverses (get_FullLogDet, Trace.F90:2665-2685); the tracked Det is the same number up to the
     // rounding of the fast updates (pinned by the from-scratch tests), so the second LU is not repeated here.
     double dn_log, dn_sign;
     rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, J.knew, false, dn_log, dn_sign);
-    if (lane_id() == 0) { J.kind = 3; J.new_outer = new_outer; J.type = type; J.factor = factor; J.dn_log = dn_log; J.dn_sign = dn_sign; J.stored = 0; }
+    if (lane_id() == 0) { J.dn_log = dn_log; J.dn_sign = dn_sign; }
     wsync();
     return true;
 }
-W2B_HDN void step_glob_finish(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, double tn_log, double tn_sign) {
-    const int nf = T.nf, new_outer = J.new_outer;
+// finish, part a: Metropolis decision; on acceptance the relabelled configuration replaces the old one (the inverse matrices still
+// have to be rebuilt: part b).  Returns true when accepted.
+W2B_HDN bool step_glob_finish_a(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, double tn_log, double tn_sign) {
+    const int nf = T.nf;
     const double dn_log = J.dn_log, dn_sign = J.dn_sign;
     const double dr_log = dn_log - x.det_log, dr_sign = dn_sign * x.det_sign;
     const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
     const double prob = fabs(w_exp(trr_log + dr_log) * J.factor);
     const double rand = x.rng.next();
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 17, rand);
-    if (!(rand < prob)) { log_end(x, 0); return; }
+    if (!(rand < prob)) { log_end(x, 0); return false; }
     // ---- accept
-    long long sumk2 = 0; for (int f = 0; f < nf; ++f) sumk2 += (long long)x.ih[IH_KF + f] * x.ih[IH_KF + f];
+    long long sumk2 = 0;
+#pragma unroll 1
+    for (int f = 0; f < nf; ++f) sumk2 += (long long)x.ih[IH_KF + f] * x.ih[IH_KF + f];
     bump_bytes(x, 8ll * sumk2);
 #pragma unroll 1
     for (int i = lane_id(); i < x.n; i += W2B_WARP) { x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
@@ -1179,16 +1188,27 @@ W2B_HDN void step_glob_finish(const Tables& T, const Run& R, const Chains& C, Ct
     wsync();
     if (lane_id() == 0) for (int f = 0; f < nf; ++f) x.ih[IH_KF + f] = J.knew[f];
     wsync();
-    double l2, s2;
-    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
-    x.outer = new_outer;
-    x.det_log = dn_log; x.det_sign = dn_sign; x.tr_log = tn_log; x.tr_sign = tn_sign;
+    return true;
+}
+// finish, part b (the inverse matrices of the new configuration are in place): outer superstate, determinant, trace, signs
+W2B_HDN void step_glob_finish_b(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, double tn_log, double tn_sign) {
+    const int nf = T.nf;
+    x.outer = J.new_outer;
+    x.det_log = J.dn_log; x.det_sign = J.dn_sign; x.tr_log = tn_log; x.tr_sign = tn_sign;
     if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); }
     x.perm = perm_full(x.code, x.n);
-    x.palt = 0; for (int f = 0; f < nf; ++f) x.palt |= palt_flavour(C, x, f) << f;
+    x.palt = 0;
+#pragma unroll 1
+    for (int f = 0; f < nf; ++f) x.palt |= palt_flavour(C, x, f) << f;
     update_cfgsign(T, x);
     bump(x, C_ACCGLOB);
     log_end(x, 1);
+}
+W2B_HDN void step_glob_finish(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, double tn_log, double tn_sign) {
+    if (!step_glob_finish_a(T, R, C, x, J, tn_log, tn_sign)) return;
+    double l2, s2;
+    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
+    step_glob_finish_b(T, R, C, x, J, tn_log, tn_sign);
 }
 
 // ------------------------------------------------------------------ StepShiftTau (CTQMC.F90:4557-4835), same two halves
@@ -1340,6 +1360,104 @@ W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
 }
 
+// ------------------------------------------------------------------ group LU in shared memory (global moves of the CTA scheduler)
+// A global move needs the determinant of every flavour's hybridisation matrix from scratch and, when accepted, its inverse
+// (get_InvFullHybr / get_MatLogDetFull, Trace.F90:2279-2333, MatrixUpdate.F90:41-99).  One warp eliminating a 75 x 75 matrix in
+// global memory re-reads and re-writes the matrix for every pivot: at beta = 200 that was 40 % of the sweep kernel's instructions
+// and seven times the algorithmic DRAM traffic (profiles/r2h_*).  Here a GROUP of warps of the CTA (named barrier) builds the
+// matrix in shared memory, eliminates it there -- same pivots and the same arithmetic per element as invert_inplace -- and
+// writes only the inverse back.
+constexpr int LU_GROUP_MIN = 40;       // flavour orders from which a global move goes through the staged group path
+struct LuGroup { double* buf; int cap, gid, gwarps, gw; };           // buffer (doubles), group id, warps per group, this warp's index in it
+W2B_HD void grp_sync(const LuGroup& G) {
+#if W2B_DEVICE
+    asm volatile("bar.sync %0, %1;" ::"r"(G.gid + 1), "r"(G.gwarps * 32) : "memory");
+#endif
+}
+#if W2B_DEVICE
+__host__ __device__
+#endif
+inline int lu_need(int k) { return k * (k | 1) + 2 * k + (k + 1) / 2 + 4; }
+// log|det| and sign of flavour f's matrix Delta(ia, ic) = F(ta[ia] - tc[ic]) (every thread of the group returns them); with Mdst the
+// inverse is written to Mdst[creator][annihilator] (leading dimension ldm).  Singular -> sign 0.
+W2B_HDN void group_lu(const Tables& T, const LuGroup& G, const double* tc, const double* ta, int k, int f, double* Mdst, int ldm, double& lg, double& sg) {
+    const int lds = k | 1, lane = lane_id();
+    double* A = G.buf; double* colv = A + k * lds; double* rowv = colv + k; int* piv = (int*)(rowv + k); int* flag = piv + k + (k & 1);
+    lg = 0.0; sg = 1.0;
+#pragma unroll 1
+    for (int ia = G.gw; ia < k; ia += G.gwarps) {
+        const double t = ta[ia];
+#pragma unroll 1
+        for (int ic = lane; ic < k; ic += W2B_WARP) A[ia * lds + ic] = hybrF(T, t - tc[ic], f);
+    }
+    grp_sync(G);
+#pragma unroll 1
+    for (int c = 0; c < k; ++c) {
+        if (G.gw == 0) {                                           // pivot search (rows >= c of column c) by the group's first warp
+            double best = 0.0; int bi = c;
+#pragma unroll 1
+            for (int r = c + lane; r < k; r += W2B_WARP) { const double v = fabs(A[r * lds + c]); if (v > best) { best = v; bi = r; } }
+            double bv; const int p = wargmax_abs(best, bi, bv);
+            if (lane == 0) { flag[0] = p; flag[1] = bv > 0.0 ? 0 : 1; }
+        }
+        grp_sync(G);
+        const int p = flag[0];
+        if (flag[1]) { sg = 0.0; lg = -1.7976931348623157e308; return; }
+        if (p != c) {
+            if (G.gw == 0) {
+#pragma unroll 1
+                for (int j = lane; j < k; j += W2B_WARP) { const double t = A[c * lds + j]; A[c * lds + j] = A[p * lds + j]; A[p * lds + j] = t; }
+            }
+            sg = -sg;
+        }
+        if (G.gw == 0 && lane == 0) piv[c] = p;
+        grp_sync(G);
+        const double pv = A[c * lds + c];
+        lg += w_log(fabs(pv)); if (pv < 0) sg = -sg;
+        const double ipiv = 1.0 / pv;
+        if (Mdst) {                                                 // Gauss-Jordan step (same element arithmetic as invert_inplace)
+            if (G.gw == 0) {
+#pragma unroll 1
+                for (int j = lane; j < k; j += W2B_WARP) { rowv[j] = (j == c) ? ipiv : A[c * lds + j] * ipiv; colv[j] = A[j * lds + c]; }
+            }
+            grp_sync(G);
+#pragma unroll 1
+            for (int r = G.gw; r < k; r += G.gwarps) {
+                const double fct = colv[r];
+#pragma unroll 1
+                for (int j = lane; j < k; j += W2B_WARP)
+                    A[r * lds + j] = (r == c) ? rowv[j] : ((j == c) ? -fct * ipiv : A[r * lds + j] - fct * rowv[j]);
+            }
+        } else {                                                    // plain elimination below the pivot: determinant only
+#pragma unroll 1
+            for (int r = c + 1 + G.gw; r < k; r += G.gwarps) {
+                const double fct = A[r * lds + c] * ipiv;
+#pragma unroll 1
+                for (int j = c + 1 + lane; j < k; j += W2B_WARP) A[r * lds + j] -= fct * A[c * lds + j];
+            }
+        }
+        grp_sync(G);
+    }
+    if (!Mdst) return;
+#pragma unroll 1
+    for (int c = k - 1; c >= 0; --c) {                              // undo the row swaps as column swaps in reverse order: inv(P A) = inv(A) P^T
+        const int p = piv[c];
+        if (p != c) {
+            if (G.gw == 0) {
+#pragma unroll 1
+                for (int r = lane; r < k; r += W2B_WARP) { const double t = A[r * lds + c]; A[r * lds + c] = A[r * lds + p]; A[r * lds + p] = t; }
+            }
+            grp_sync(G);
+        }
+    }
+#pragma unroll 1
+    for (int r = G.gw; r < k; r += G.gwarps) {
+#pragma unroll 1
+        for (int j = lane; j < k; j += W2B_WARP) Mdst[(size_t)r * ldm + j] = A[r * lds + j];
+    }
+    grp_sync(G);
+}
+
 // ------------------------------------------------------------------ phase scheduler of one CTA (CTQMC.F90:8213-8258, 8428-8533)
 // Used for 1x1 quantum-number blocks (C1, C2, C5), where a move is short and a global move (LU of every flavour's matrix)
 // costs 100-1000 moves: one persistent kernel, no launch per round.  Blocked traces use the round kernels further down.
@@ -1354,6 +1472,7 @@ W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
 // Within a chain the sequence of moves and RNG draws is exactly the reference's.
 struct CtaShared {
     int nA, nR, nA2, nR2, nG, cA, cR, cA2, cR2, cG, cA2h, cR2h;
+    int nLU, nINV, cS;                     // staged global moves: chains waiting for the group LU / for the inverse (lists lA / lR), stage cursor
     int* left; unsigned char* parked; unsigned char* kind;
     short* lA; short* lR; short* lA2; short* lR2; short* lG;
     Prop* prop;
@@ -1403,7 +1522,7 @@ W2B_HDN void post_move_cta(const Tables& T, const Run& R, Ctx& x, CtaShared& S, 
 
 
 W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain_lo, int nloc, long long nsteps,
-                      CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf, Ctx& x) {
+                      CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf, Ctx& x, const LuGroup& LG) {
     const int W = cta_nwarps(), lane = lane_id();
 #pragma unroll 1
     for (int c = cta_tid(); c < nloc; c += cta_nthreads()) { S.left[c] = (int)nsteps; S.parked[c] = 0; }
@@ -1480,14 +1599,109 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
             rare = S.nG >= W || (S.nG > 0 && nrun < W);
         }
         if (rare) {
-            // ---- rare phase: global moves and tau shifts of all parked chains
+            // ---- rare phase: global moves and tau shifts of all parked chains.  Tau shifts run whole on one warp.  Global moves run
+            // in stages, the dense linear algebra by warp GROUPS in shared memory (group_lu):
+            //   A (warp per chain)  update choice, relabelling, quantum numbers            -> list LU
+            //   B (group per chain) determinant of every flavour's new matrix              -> J.dn_log / dn_sign
+            //   C (warp per chain)  local trace, Metropolis, configuration hand-over       -> list INV (accepted)
+            //   D (group per chain) inverse matrices of the accepted configurations       -> M
+            //   E (warp per chain)  outer superstate, determinant, signs, counters
             const int ng = S.nG;
+            if (cta_tid() == 0) { S.nLU = 0; S.nINV = 0; S.cS = 0; }
+            cta_sync();
 #pragma unroll 1
-            for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {
+            for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {                     // ---- A
                 const int c = S.lG[i], chain = chain_lo + c;
                 ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                step_rare(T, R, C, x, C.rjob[chain], (int)S.kind[c]);
+                bool staged = false;
+                int kmax = 0;
+#pragma unroll 1
+                for (int f = 0; f < T.nf; ++f) kmax = kmax > x.ih[IH_KF + f] ? kmax : x.ih[IH_KF + f];
+                // small matrices: 32 warps each eliminating their own are faster than groups taking turns (measured: C2, k ~ 12, +17 % sweep time staged)
+                if ((int)S.kind[c] == 3 && LG.cap > 0 && kmax >= LU_GROUP_MIN) {
+                    staged = step_glob_prepare(T, R, C, x, C.rjob[chain], false);
+                    if (staged && lane == 0) S.lA[wgrab_one(&S.nLU)] = (short)c;
+                } else step_rare(T, R, C, x, C.rjob[chain], (int)S.kind[c]);
+                if (!staged) post_move_cta(T, R, x, S, c);
+                ctx_store(C, chain, x);
+                if (!staged && lane == 0) S.parked[c] = 0;
+            }
+            cta_sync();
+            const int nlu = S.nLU, ngroups = cta_nwarps() / LG.gwarps;
+#pragma unroll 1
+            for (int i = LG.gid; i < nlu; i += ngroups) {                               // ---- B
+                const int chain = chain_lo + S.lA[i];
+                RareJob& J = C.rjob[chain];
+                bool fits = true;
+#pragma unroll 1
+                for (int f = 0; f < T.nf; ++f) fits = fits && lu_need(J.knew[f]) <= LG.cap;
+                double lgt = 0.0, sgt = 1.0;
+                if (fits) {
+#pragma unroll 1
+                    for (int f = 0; f < T.nf; ++f) {
+                        const int k = J.knew[f];
+                        if (k == 0) continue;
+                        double l, sg_;
+                        group_lu(T, LG, C.sc_tc + ((size_t)chain * T.nf + f) * C.kcap, C.sc_ta + ((size_t)chain * T.nf + f) * C.kcap, k, f, nullptr, 0, l, sg_);
+                        lgt += l; sgt *= sg_;
+                    }
+                } else if (LG.gw == 0) {                                                // too large for the group buffer: one warp, global memory
+                    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                    rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, J.knew, false, lgt, sgt);
+                }
+                if (LG.gw == 0 && lane == 0) { J.dn_log = lgt; J.dn_sign = sgt; }
+                grp_sync(LG);
+            }
+            cta_sync();
+#pragma unroll 1
+            for (int i = wgrab(&S.cS); i < nlu; i = wgrab(&S.cS)) {                     // ---- C
+                const int c = S.lA[i], chain = chain_lo + c;
+                ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                RareJob& J = C.rjob[chain];
+                double tn_log, tn_sign;
+                trace_full_scalar(T, x.tau, x.sc_code, x.sc_sst, x.n, J.new_outer, tn_log, tn_sign);
+                const bool acc = step_glob_finish_a(T, R, C, x, J, tn_log, tn_sign);
+                if (acc) { if (lane == 0) { J.tn_log = tn_log; J.tn_sign = tn_sign; S.lR[wgrab_one(&S.nINV)] = (short)c; } }
+                else post_move_cta(T, R, x, S, c);
+                ctx_store(C, chain, x);
+                if (!acc && lane == 0) S.parked[c] = 0;
+            }
+            cta_sync();
+            if (cta_tid() == 0) S.cS = 0;
+            const int ninv = S.nINV;
+#pragma unroll 1
+            for (int i = LG.gid; i < ninv; i += ngroups) {                              // ---- D
+                const int chain = chain_lo + S.lR[i];
+                const int* ih = C.ih + (size_t)chain * IH_STRIDE;
+                bool fits = true;
+#pragma unroll 1
+                for (int f = 0; f < T.nf; ++f) fits = fits && lu_need(ih[IH_KF + f]) <= LG.cap;
+                if (fits) {
+#pragma unroll 1
+                    for (int f = 0; f < T.nf; ++f) {
+                        const int k = ih[IH_KF + f];
+                        if (k == 0) continue;
+                        double l, sg_;
+                        double* Md = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
+                        group_lu(T, LG, C.tau_c + ((size_t)chain * T.nf + f) * C.kcap, C.tau_a + ((size_t)chain * T.nf + f) * C.kcap, k, f, Md, C.ld, l, sg_);
+                    }
+                } else if (LG.gw == 0) {
+                    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                    double l2, s2;
+                    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
+                }
+                grp_sync(LG);
+            }
+            cta_sync();
+#pragma unroll 1
+            for (int i = wgrab(&S.cS); i < ninv; i = wgrab(&S.cS)) {                    // ---- E
+                const int c = S.lR[i], chain = chain_lo + c;
+                ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
+                RareJob& J = C.rjob[chain];
+                step_glob_finish_b(T, R, C, x, J, J.tn_log, J.tn_sign);
                 post_move_cta(T, R, x, S, c);
                 ctx_store(C, chain, x);
                 if (lane == 0) S.parked[c] = 0;
