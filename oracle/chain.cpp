@@ -102,6 +102,7 @@ struct Chain {
     double beta = 1, taudiff_max = 1, pglob = 0.005, pshift = 0.005, p4op = 0, pouter = 0;
     int nb = 1, nf = 2, nftau = 0, ntau = 1000, nlegmax = 100, maxhisto = 500, ncorr = 100, nslide = 1;
     bool has_szt = true; int meas_dm = 1;
+    int nsym = 0; std::vector<int> symmoves;       // user symmetry moves and their inverses: SymMoves(2 NSymMove, 2 NBands), Trace.F90:403-404, 471-478
     std::vector<double> ftau;                      // (nb,2,nftau)  [ (b*2+s)*nftau + i ]
     // rng
     int rng_kind = 1; Philox ph; MtLib mt;
@@ -790,7 +791,11 @@ struct Chain {
             type = 3; for (int i = 1; i <= nb; ++i) gu[i] = i + nb; for (int i = nb + 1; i <= 2 * nb; ++i) gu[i] = i - nb;
         } else if (r < 0.6) {                        // gen_CAFlip 1186-1198
             type = 4; gu[0] = 1; for (int i = 1; i <= nf; ++i) gu[i] = i;
-        } else {                                     // gen_GlobalUpdate_new 1103-1123 (no user symmetry moves)
+        } else if (r < 0.8 && nsym > 0) {            // gen_SymUpdate 1170-1182 (CTQMC.F90:4463-4465)
+            type = 2;
+            int isym = randint(1, 2 * nsym);
+            for (int i = 1; i <= nf; ++i) gu[i] = symmoves[(size_t)(isym - 1) * nf + i - 1];
+        } else {                                     // gen_GlobalUpdate_new 1103-1123
             type = 1; for (int i = 1; i <= nf; ++i) gu[i] = i;
             for (int j = 1; j <= nf; ++j) { int i = randint(j, nf); std::swap(gu[j], gu[i]); }
             gu[0] = randint(0, 1);
@@ -1107,6 +1112,16 @@ unsigned long long orc_rng_counter(void* h) { return ((Chain*)h)->ph.ctr; }
 
 void orc_init_trace(void* h) { ((Chain*)h)->init_trace(); }
 void orc_set_taudiffmax(void* h, double t) { ((Chain*)h)->init_window(t); }
+// SymMoveNN lists (1-based target indices b + nb s + 1); the inverses are appended as init_Trace does (Trace.F90:471-478)
+void orc_set_symmoves(void* h, int nsym, const int* moves) {
+    Chain* c = (Chain*)h; const int nf = c->nf;
+    c->nsym = nsym; c->symmoves.assign((size_t)2 * nsym * nf, 0);
+    for (int i = 0; i < nsym; ++i) for (int j = 0; j < nf; ++j) {
+        const int v = moves[i * nf + j];
+        c->symmoves[(size_t)i * nf + j] = v;
+        c->symmoves[(size_t)(nsym + i) * nf + v - 1] = j + 1;
+    }
+}
 void orc_set_fast_trace(void* h, int on) { Chain* c = (Chain*)h; c->fast_trace = on; c->ec.valid = false; c->fc.valid = false; }
 void orc_init_counters(void* h) { ((Chain*)h)->reset_counters(); }
 void orc_set_log(void* h, double* buf, long long cap) { Chain* c = (Chain*)h; c->logp = buf; c->log_cap = cap; c->log_n = 0; }

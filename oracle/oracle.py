@@ -122,6 +122,10 @@ class OracleChain:
         L.orc_init_trace(self.h)
         if q["TaudiffMax"] > 0:
             L.orc_set_taudiffmax(self.h, C.c_double(q["TaudiffMax"]))
+        sym = getattr(problem, "symmetry_moves", None)
+        if sym:
+            mv = np.ascontiguousarray(np.asarray(sym, dtype=np.int32) + 1)          # the plugin sends vals + 1 (symm_to_pstring)
+            L.orc_set_symmoves(self.h, C.c_int(len(sym)), _p(mv, C.c_int))
         if fast_trace:
             L.orc_set_fast_trace(self.h, C.c_int(int(fast_trace)))
         self._log = None

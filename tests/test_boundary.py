@@ -165,7 +165,40 @@ def body_calibrate_list(make):
     eng.dest_ctqmc()
 
 
+def body_symmetry_moves(make, cfg, nsteps):
+    """User symmetry moves (NSymMove / SymMoveNN, symm_to_pstring cthyb_solver.py:769-774; gen_SymUpdate Trace.F90:1170-1182, the
+    20 % branch of StepGlob CTQMC.F90:4463-4465): replay parity against the oracle with two declared orbital symmetries."""
+    from oracle.oracle import OracleChain
+    from _parity import assert_replay
+    p = problems.make_problem(cfg, nftau=2001, PercentageGlobalMove=0.05)
+    nb = p.nbands
+    swap01 = list(range(2 * nb)); swap01[0], swap01[1] = 1, 0; swap01[nb], swap01[nb + 1] = nb + 1, nb      # orbitals 0 <-> 1, both spins
+    cyc = [(b + 1) % nb + nb * s for s in range(2) for b in range(nb)]                                          # cyclic orbital shift
+    p.symmetry_moves = [swap01, cyc]
+    assert "NSymMove = 2" in p.pstring() and "SymMove02" in p.pstring()
+    eng = _start(make(), p, nchains=8)
+    eng.init_counters()
+    log = eng.debug_steps(3, nsteps)
+    orc = OracleChain(p, rng="philox", seed=43890, chain=3)
+    orc.init_counters()
+    ref = orc.steps(nsteps, log=True)
+    assert_replay(log, ref)
+    sym = log[(log[:, 0] == 3) & (log[:, 4] == 2)]
+    assert sym.shape[0] > 5 and (sym[:, 1] == 1).any()            # symmetry moves were proposed, some accepted
+    assert eng.scalar("error_flags") == 0
+    eng.dest_ctqmc()
+    with pytest.raises(RuntimeError, match="permutation"):
+        q = problems.make_problem(cfg, nftau=501)
+        q.symmetry_moves = [[0] * (2 * nb)]
+        _start(make(), q)
+
+
 # ------------------------------------------------------------------ CPU (host-emulation build of the same sources)
+@pytest.mark.parametrize("cfg,nsteps", [("C2", 12000), ("C3", 6000)])
+def test_symmetry_moves(built, cfg, nsteps):
+    body_symmetry_moves(_hostemu_engine, cfg, nsteps)
+
+
 def test_calibrate_phase1_list(built):
     body_calibrate_list(_hostemu_engine)
 
@@ -203,6 +236,12 @@ def test_gpu_aborted_flag(built):
 @pytest.mark.parametrize("cfg", ["C2", "C4"])
 def test_gpu_reuse_population(built, cfg):
     body_reuse_population(_cuda_engine, cfg)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,nsteps", [("C2", 20000), ("C4", 12000)])
+def test_gpu_symmetry_moves(built, cfg, nsteps):
+    body_symmetry_moves(_cuda_engine, cfg, nsteps)
 
 
 @pytest.mark.gpu

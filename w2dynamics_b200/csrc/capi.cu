@@ -119,7 +119,7 @@ void check_chain(int chain) {
 void check_supported(const Params& p) {
     auto zero_i = [&](const char* k) { if (p.has(k) && p.integer(k) != 0) throw std::runtime_error(std::string(k) + " != 0 is outside the implemented hot path"); };
     auto zero_r = [&](const char* k) { if (p.has(k) && p.real(k) != 0.0) throw std::runtime_error(std::string(k) + " != 0 is outside the implemented hot path"); };
-    zero_i("segment"); zero_i("offdiag"); zero_i("statesampling"); zero_i("Uw"); zero_i("Phonon"); zero_i("NSymMove");
+    zero_i("segment"); zero_i("offdiag"); zero_i("statesampling"); zero_i("Uw"); zero_i("Phonon");
     zero_i("MeasGiw"); zero_i("MeasG2iw"); zero_i("MeasSusz"); zero_i("MeasExpResDensityMatrix"); zero_i("FourPnt");
     zero_i("MeasSsquare"); zero_i("MeasGtauDetRat"); zero_i("flavourchange_moves"); zero_i("Gtau_mean_step"); zero_i("Gtau_mid_step"); zero_i("sign_step");
     zero_r("PercentageOuterMove"); zero_r("Percentage4OperatorMove");
@@ -335,6 +335,23 @@ int w2b_init_solver(const double* u_matrix, const double* ftau_full, const doubl
         if (G.nranks > 1) opt.chain_base += (unsigned)G.rank * (unsigned)opt.nchains;      // chains shard over ranks by global chain id
         R.seed = (unsigned)S.seed; R.chain_base = opt.chain_base; R.same_key = S.same_key; R.prefetch = S.prefetch; R.propose_run = S.propose_run > 0 ? S.propose_run : 1;
         R.stream = S.nsolve++;
+        // user symmetry moves (symm_to_pstring cthyb_solver.py:769-774; init_Trace Trace.F90:403-404, 471-478): NSymMove lists of 2 Nb
+        // target indices (b + Nb s + 1), followed by their inverses
+        std::vector<int> symmoves;
+        R.nsym = (int)p.integer_or("NSymMove", 0);
+        if (R.nsym > 0) {
+            symmoves.assign((size_t)2 * R.nsym * nf, 0);
+            for (int i = 0; i < R.nsym; ++i) {
+                char id[16]; std::snprintf(id, sizeof id, "SymMove%02d", i + 1);
+                const std::vector<int> v = p.integer_list(id, nf);
+                std::vector<int> seen(nf + 1, 0);
+                for (int j = 0; j < nf; ++j) {
+                    if (v[j] < 1 || v[j] > nf || seen[v[j]]++) throw std::runtime_error(std::string(id) + " is not a permutation of 1.." + std::to_string(nf));
+                    symmoves[(size_t)i * nf + j] = v[j];
+                    symmoves[(size_t)(R.nsym + i) * nf + v[j] - 1] = j + 1;
+                }
+            }
+        }
         // init_window with the configured TaudiffMax, NSlide fixed here (CTQMC.F90:8068-8069)
         if (S.cfg_taudiffmax > 0.0) { R.taudiff_max = S.cfg_taudiffmax; R.num_windows = std::max((int)std::floor(S.beta / S.cfg_taudiffmax) - 1, 1); }
         else { R.taudiff_max = S.beta; R.num_windows = 1; }
@@ -363,6 +380,7 @@ int w2b_init_solver(const double* u_matrix, const double* ftau_full, const doubl
             S.parked.reset();
             AtomicTables at = build_atomic(nb, p.str("QuantumNumbers"), u_matrix, muimp_full, p.real("EPSBLOCK"), p.real("EPSEVEC"));
             S.eng.reset(new Engine());
+            S.eng->symmoves = symmoves;
             S.eng->setup(at, fd, nftau, S.beta, R, opt);
             S.rho2_ready = false;
             S.key_u.assign(u_matrix, u_matrix + nu); S.key_mu.assign(muimp_full, muimp_full + nmu); S.key_par = key_of(p); S.key_opt = opt; S.key_nftau = nftau; S.key_nmeas = S.nmeas;

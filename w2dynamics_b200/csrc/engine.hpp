@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T_, Run R_,
 #endif
 constexpr int PROPOSE_WARPS = W2B_PROPOSE_WARPS;      // warps per CTA of the propose kernel (its queue pushes are aggregated per CTA)
 #ifndef W2B_TRACE_OCC
-#define W2B_TRACE_OCC 6
+#define W2B_TRACE_OCC 8
 #endif
 constexpr int TRACE_WARPS = 4;        // warps per CTA of the trace kernel (one work matrix per warp in shared memory)
 constexpr int TICKET_BATCH = 1;       // tickets a warp takes per atomic on the round's ticket counter
@@ -209,8 +209,15 @@ __global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T_, Run R_
     double* ws = smem + (size_t)warp * wdoubles;
     int* is = (int*)(ws + 3 * C.kcap + mdoubles);
     __shared__ Ctx ctxs[DECIDE_WARPS];
-    for (int c = blockIdx.x * DECIDE_WARPS + warp; c < C.nchains; c += gridDim.x * DECIDE_WARPS)
-        phase_rare(T, R, C, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
+    // every warp scans 32 chain states per load (1 % of the chains have a rare move pending) and serves the flagged ones
+    for (int base = (blockIdx.x * DECIDE_WARPS + warp) * 32; base < C.nchains; base += gridDim.x * DECIDE_WARPS * 32) {
+        const int c0 = base + (threadIdx.x & 31);
+        unsigned m = __ballot_sync(0xffffffffu, c0 < C.nchains && vload_u8(&C.parked[c0]) == ST_RARE_NEW);
+        while (m) {
+            const int c = base + __ffs(m) - 1; m &= m - 1;
+            phase_rare(T, R, C, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
+        }
+    }
 }
 // trace phase of one round (blocked traces): operator products of every surviving proposal on the FP64 tensor pipe
 __global__ void __launch_bounds__(TRACE_WARPS * 32, W2B_TRACE_OCC) k_trace(Tables T, Chains C, int tdoubles, int parity) {
@@ -339,6 +346,7 @@ public:
     template <class T_> T_* keep(T_* p) { owned.push_back((void*)p); return p; }
 
     // ftau_diag: [nf][nftau] with flavour f = 2*band+spin
+    std::vector<int> symmoves;         // [2 NSymMove][nf], set before setup()
     void setup(const AtomicTables& tables, const std::vector<double>& ftau_diag, int nftau, double beta, const Run& run,
                const EngineOptions& options) {
         release();
@@ -399,6 +407,7 @@ public:
             for (int l = 2; l < (int)lg.size(); ++l) lg[l] = ((double)(l - 1) * (l - 1)) / ((2.0 * l - 1.0) * (2.0 * l - 3.0));
             T.leg_g = keep(dev_upload(lg)); T.leg_c = keep(dev_upload(lc));
         }
+        { std::vector<int> sm = symmoves; if (sm.empty()) sm.push_back(0); T.symmoves = keep(dev_upload(sm)); }
         T.op_off = keep(dev_upload(at.op_off)); T.opdata = keep(dev_upload(at.opdata)); T.evals = keep(dev_upload(at.evals));
 
         // capacities

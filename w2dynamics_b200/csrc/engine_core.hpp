@@ -58,6 +58,7 @@ struct Tables {
     const double* empty_w;       // [nsst] normalised empty-trace weights (init_Trace / StepChangeOuter)
     const double* empty_log;     // [nsst] log of the empty trace of each outer superstate
     const double* leg_a; const double* leg_b;   // Legendre recurrence coefficients (2l-1)/l and (l-1)/l, [NLegMax]
+    const int* symmoves;         // [2 NSymMove][nf] flavour permutations (target index b + nb s + 1) and their inverses (Trace.F90:471-478)
     const double* leg_g; const double* leg_c;   // monic recurrence g_l = (l-1)^2/((2l-1)(2l-3)) and leading coefficients c_l: P_l = c_l Q_l
     const OpDesc* desc;          // [nsst*nops] packed operator records of the blocked trace
     const long long* op_off;     // matrix path
@@ -75,6 +76,7 @@ struct Run {
     int propose_run;             // consecutive early-exit moves one chain may take inside one propose phase
     int prefetch;                // software prefetch of the next work item's records (0 = off)
     int same_key;                // diagnostics only: every chain uses chain 0's RNG key (identical control flow across warps)
+    int nsym;                    // user symmetry moves (NSymMove); the table Tables::symmoves holds them and their inverses
     unsigned stream;             // solves since init_rnd: every init_solver draws from a fresh section of each chain's Philox stream
 };
 constexpr int STREAM_SHIFT = 44;     // draws per chain and solve before two solves could overlap: 2^44
@@ -1079,7 +1081,11 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
     } else if (r < 0.6) {                  // gen_CAFlip 1186-1198
         type = 4;
         if (lane_id() == 0) { gu[0] = 1; for (int i = 1; i <= nf; ++i) gu[i] = i; }
-    } else {                               // gen_GlobalUpdate_new 1103-1123 (NSymMove = 0)
+    } else if (r < 0.8 && R.nsym > 0) {    // gen_SymUpdate 1170-1182: one of the user's symmetry moves or its inverse (CTQMC.F90:4463-4465)
+        type = 2;
+        const int isym = x.rng.randint(1, 2 * R.nsym) - 1;
+        if (lane_id() == 0) { gu[0] = 0; for (int i = 1; i <= nf; ++i) gu[i] = ldg(&T.symmoves[isym * nf + i - 1]); }
+    } else {                               // gen_GlobalUpdate_new 1103-1123
         type = 1;
         if (lane_id() == 0) for (int i = 1; i <= nf; ++i) gu[i] = i;
         wsync();

@@ -72,6 +72,12 @@ struct Params {
         return (long long)x;
     }
     long long integer_or(const std::string& id, long long d) const { return has(id) ? integer(id) : d; }
+    std::vector<int> integer_list(const std::string& id, size_t n) const {      // get_Integer_List (Parameters.F90:185-203): list-directed read of n integers
+        std::istringstream in(raw(id));
+        std::vector<int> v(n);
+        for (size_t i = 0; i < n; ++i) if (!(in >> v[i])) throw std::runtime_error(id + " holds fewer than " + std::to_string(n) + " integers");
+        return v;
+    }
 };
 
 }  // namespace w2b

@@ -195,6 +195,7 @@ class Problem:
     eps_bath: np.ndarray | None = None
     v_bath: np.ndarray | None = None
     mu: float = 0.0
+    symmetry_moves: list = field(default_factory=list)   # 0-based flavour permutations (index band + nbands * spin), as ImpurityProblem.symmetry_moves
 
     @property
     def nflavours(self):
@@ -214,7 +215,8 @@ class Problem:
             "g_phonon": "", "omega0": "", "Screening": 0, "Uw": 0,
         }
         s += "".join("%s = %s #\n" % (k, v) for k, v in sorted(prob.items()))
-        s += "NSymMove = 0 #\n"
+        s += "NSymMove = %d #\n" % len(self.symmetry_moves)                       # symm_to_pstring, cthyb_solver.py:769-774
+        s += "".join("SymMove%02d = %s #\n" % (i + 1, " ".join(str(int(v) + 1) for v in vals)) for i, vals in enumerate(self.symmetry_moves))
         return s
 
 
