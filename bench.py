@@ -262,6 +262,8 @@ def run_engine(args, cfg):
     p = problems.make_problem(cfg)
     ncorr = int(p.qmc.get("NCorr", 100))
     nchains = args.chains or DEFAULT_CHAINS[cfg]
+    if args.strong:
+        nchains = max(1024, nchains // world)      # strong scaling: the population of one GPU is split over the ranks
     therm = args.thermalise if args.thermalise >= 0 else THERMALISE[cfg]
     eng = MCTQMC()
     eng.set_option("nchains", nchains); eng.set_option("nbins", 32); eng.set_option("device", local)
@@ -421,7 +423,7 @@ def run_engine(args, cfg):
     state_gb = nchains * (2 * p.nbands + 1) * kcap ** 2 * 8 / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[cfg], "chains_per_gpu": nchains, "ncorr": ncorr, "moves_per_step": nchains * ncorr * world,
                    "mean_order_per_flavour": mean_k, "parallelism": "chains sharded over %d GPU(s), no data-path collective; one ncclAllReduce of the accumulators per accumulation (inside the library)" % world,
@@ -470,6 +472,7 @@ def main():
     ap.add_argument("--thermalise", type=int, default=-1, help="untimed thermalisation moves per chain")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: split the one-GPU chain population over the ranks (default: weak, fixed chains per GPU)")
     ap.add_argument("--slice-seconds", type=float, default=0.0, help="reference arm: wall time of one step (default: sized for a one-minute run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
