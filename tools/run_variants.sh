@@ -1,4 +1,4 @@
-for v in vA vB; do
+for v in vA; do
   cp w2dynamics_b200/libw2b_cthyb.so /tmp/base.so
   cp w2dynamics_b200/libw2b_$v.so w2dynamics_b200/libw2b_cthyb.so
   touch w2dynamics_b200/libw2b_cthyb.so
