@@ -198,3 +198,47 @@ def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
     assert len(mc_cfg) == 1 and mc_cfg[0].taus.shape == mc_cfg[0].orbs.shape
     for k in ("w2dyn.auxiliaries.CTQMC", "w2dyn.dmft.cthyb_solver"):
         sys.modules.pop(k, None)
+
+
+def test_chain_group_bins_feed_distributedsample(built):
+    """the reference's OWN `DistributedSample` (statistics.py:36-63, 99-132, 180-209) accepts n samples per
+    rank.  The engine hands back `nbins` chain-group means (`mctqmc.bins(name)`), so `mean()` reproduces the population result and
+    `stderr()` is the standard error over chain groups -- what the 3-line change at cthyb_solver.py:366,389-390 documented in
+    INTEGRATION.md passes on.  Checked here with the unmodified class on gtau, gleg, occ and sign."""
+    from w2dynamics_b200 import problems
+    eng = _engine()
+    eng.set_option("nchains", 32)
+    eng.set_option("nbins", 8)
+    _install_stubs(eng)
+    sys.modules.pop("w2dyn.auxiliaries.statistics", None)
+    import w2dyn.auxiliaries.statistics as st
+    p = problems.make_problem("C1", nftau=501, Nmeas=40, Nwarmups=2000)
+    eng.init_rnd(43890)
+    eng.init_paras(p.pstring())
+    eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)
+    eng.set_taudiffmax(p.qmc["TaudiffMax"])
+    eng.ctqmc_warmup(2000)
+    eng.init_counters()
+    eng.ctqmc_measure(1, 1)
+    comm = _Comm()
+    for name in ("gtau", "gleg", "occ"):
+        pop = np.array(getattr(eng, name))
+        bins = eng.bins(name)
+        assert bins.shape == (8,) + pop.shape
+        ds = st.DistributedSample(bins, comm)
+        assert ds.ntotal == 8
+        # every bin holds the same number of chains and the sign is -1 in every bin (no sign problem): mean of bins = population
+        assert np.allclose(ds.mean(), pop, rtol=1e-12, atol=1e-14)
+        sem = ds.stderr()
+        ref = bins.std(axis=0, ddof=1) / np.sqrt(8.0)
+        assert np.allclose(sem, ref, rtol=1e-12, atol=1e-300)
+        if name == "gtau":
+            assert np.all(sem > 0) and np.all(sem < np.abs(pop).max())           # genuine scatter between chain groups
+    sign = st.DistributedSample(eng.bins("sign"), comm)
+    assert float(sign.mean()) == float(eng.mean_sign) == -1.0 and float(sign.stderr()) == 0.0
+    # what the unmodified plugin does instead (one sample per rank): SEM over ranks only -- a single rank has none
+    one = st.DistributedSample([np.array(eng.gtau)], comm)
+    assert one.ntotal == 1
+    eng.dest_ctqmc()
+    for k in ("w2dyn.auxiliaries.CTQMC", "w2dyn.auxiliaries.statistics"):
+        sys.modules.pop(k, None)
