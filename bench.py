@@ -43,7 +43,11 @@ WORKLOADS = {
 DEFAULT_CHAINS = {"C1": 65536, "C2": 65536, "C3": 32768, "C4": 32768, "C5": 32768}     # per GPU
 # (C5: the CTA scheduler serves global moves a warp-load at a time -- with 28 chains per CTA (4096 chains) 91 % of the warp
 #  samples waited at the CTA barrier for single global moves; 222 chains per CTA keep all warps busy: 2.2 -> 7.9 M moves/s)
-THERMALISE = {"C1": 2000, "C2": 6000, "C3": 6000, "C4": 6000, "C5": 8000}
+# moves per chain from the empty configuration before anything is timed, BOTH arms.  Round 2, late: 6000 / 8000 moves left C4 at
+# <k_f> = 2.65 (equilibrium 2.9, oracle chains: flat from 50 000 moves on) and C5 at 61 (equilibrium 74, flat from 10 000 on the CPU but
+# the 65-window sweep of a 32 768-chain population needs longer), so the timed steps still grew and the later legs (time-to-error, e2e)
+# ran on more expensive configurations than `value`: C5 104 -> 165 -> 199 ms per step within one bench run.
+THERMALISE = {"C1": 4000, "C2": 12000, "C3": 12000, "C4": 40000, "C5": 24000}
 METRIC = "QMC moves/sec (box)"
 UNIT = "moves/s"
 
@@ -284,10 +288,13 @@ def run_engine(args, cfg):
     ftau5 = np.ascontiguousarray(p.ftau.transpose(4, 0, 1, 2, 3))
     screening = np.zeros_like(ftau5)
 
+    solver = PluginSequence(eng, dict(qmc), 43890)             # ONE CtHybSolver for the whole run: init_rnd once, the random streams run on
+
     class plugin:                                              # one DMFT-style iteration = set_problem + solve (cthyb: 305, 314)
         def __init__(self, nwarm, nmeas):
-            q = dict(qmc); q.update(Nwarmups=nwarm, Nmeas=nmeas)
-            self.seq = PluginSequence(eng, q, 43890)
+            solver.qmc.update(Nwarmups=nwarm, Nmeas=nmeas)
+            solver.param_string = "".join("%s = %s #\n" % (k, v) for k, v in sorted(solver.qmc.items()))
+            self.seq = solver
 
         def solve(self, it):
             self.seq.set_problem(p.hamiltonian, p.beta, p.nbands, p.quantum_numbers, p.u_matrix, ftau5, -p.muimp, screening)
@@ -295,7 +302,18 @@ def run_engine(args, cfg):
     plugin(therm, 1).solve(0)                                  # thermalisation, untimed: one solve; dest_ctqmc parks the population
 
     # ---- `value`: chain state resident in HBM, K accumulation blocks timed on the device
-    eng.init_paras(p.pstring()); eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)      # revives the parked population
+    # (the parameter string and arrays are the plugin's own: the parked population is revived only for a bit-identical local problem.
+    #  Until late in round 2 this leg passed problems.pstring(), whose key set differs, silently got a FRESH, empty population and
+    #  timed it 300 moves after its creation -- C5 at <k> = 61 and growing instead of 74.  Now checked: see `revived` below.)
+    def revive():
+        seq = plugin(0, args.steps)
+        seq.seq.set_problem(p.hamiltonian, p.beta, p.nbands, p.quantum_numbers, p.u_matrix, ftau5, -p.muimp, screening)
+        eng.init_solver(seq.seq.umatrix, seq.seq.ftau, seq.seq.muimp, seq.seq.screening, 1)
+        k = eng.scalar("mean_order")
+        if therm > 0 and not k > 0.0:
+            raise SystemExit("bench.py: the thermalised population was not revived (empty chains after init_solver)")
+        return k
+    mean_k_start = revive()
     eng.set_taudiffmax(p.qmc["TaudiffMax"])
     eng.init_counters()
     ms = (C.c_double * 3)()
@@ -404,8 +422,10 @@ def run_engine(args, cfg):
     res_bytes = int(sum(np.asarray(v).nbytes for v in res.values()))
     one_ms, _, _, _ = timed_solves(1, 5, 200)
     one_val = float(nchains) * ncorr * 5 * world / (one_ms * 1e-3)
+    # stationarity check: mean expansion order after every leg (the population was revived once more) next to the one before `value`
+    mean_k_end = revive()
     eng.set_option("reuse_population", 0)
-    eng.init_paras(p.pstring()); eng.dest_ctqmc(); eng.dest_paras()    # drop the parked population (frees the device memory for the next config)
+    eng.dest_ctqmc(); eng.dest_paras()                         # drop the population (frees the device memory for the next config)
 
     if rank != 0:
         return None
@@ -426,7 +446,7 @@ def run_engine(args, cfg):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[cfg], "chains_per_gpu": nchains, "ncorr": ncorr, "moves_per_step": nchains * ncorr * world,
-                   "mean_order_per_flavour": mean_k, "parallelism": "chains sharded over %d GPU(s), no data-path collective; one ncclAllReduce of the accumulators per accumulation (inside the library)" % world,
+                   "mean_order_per_flavour": mean_k, "mean_order_before_timed_steps": mean_k_start, "mean_order_after_all_legs": mean_k_end, "thermalisation_moves": therm, "parallelism": "chains sharded over %d GPU(s), no data-path collective; one ncclAllReduce of the accumulators per accumulation (inside the library)" % world,
                    "l2": "inverse-matrix state %.1f GB per GPU > 126 MB L2 (inputs larger than L2, no flush needed)" % state_gb,
                    "error_flags": err},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int((hb1 - hb0) / args.steps), "d2h_bytes_per_step": int((db1 - db0) / args.steps),

@@ -615,8 +615,12 @@ struct Chain {
         int r = 0; for (const Op& e : o) if (e.b == b && e.s == s && e.ca == ca && e.tau < tau) ++r; return r + 1;
     }
 
-    void StepAdd() {                                 // CTQMC.F90:3353-3612 (change_outer = .false.)
-        log_begin(1);
+    // change_outer (PercentageOuterMove, CTQMC.F90:3422-3449 / 3934-3961): the superstates BETWEEN the two operators are kept and
+    // the part of the sequence that runs from the later operator over beta to the earlier one is re-walked; the superstate it
+    // passes tau = beta with becomes the outer superstate (check_sst_sequence Trace.F90:1278-1295), and the local trace is
+    // evaluated from scratch because the outer superstate changed (CalcNew, Trace.F90:5381).
+    void StepAdd(bool outer = false) {               // CTQMC.F90:3353-3612
+        log_begin(outer ? 5 : 1);
         C.TryAdd += 1;
         // pair_OperAdd Trace.F90:3657-3698
         double W = tauwin_max - tauwin_min;
@@ -646,7 +650,8 @@ struct Chain {
         FPos[2] = rank_of(nw, b, s, 2, tau_a);
         rec[5] = FPos[1]; rec[6] = FPos[2];
         // quantum-number check of the changed sub-string: check_sst_sequence Trace.F90:1243-1302
-        {   // begin = Oper(1)%prev, end = Oper(2)%next (CTQMC.F90:3435-3438), ssts from the stored sequence
+        int new_outer = outer_sst;
+        if (!outer) {   // begin = Oper(1)%prev, end = Oper(2)%next (CTQMC.F90:3435-3438), ssts from the stored sequence
             std::vector<int> after; sst_sequence(ops, outer_sst, after);
             int begin_sst = (i1 == 0) ? outer_sst : after[i1 - 1];
             int end_sst = (i2 == ops.size() || i2 == 0) ? outer_sst : after[i2 - 1];
@@ -654,6 +659,16 @@ struct Chain {
             for (size_t i = i1; i < i2 && cur >= 0; ++i) cur = T.conn(cur, ops[i].b, ops[i].s, ops[i].ca);
             if (cur >= 0) cur = T.conn(cur, o2.b, o2.s, o2.ca);
             if (cur < 0 || cur != end_sst) { C.AccQNAdd += 1; log_end(2); return; }
+        } else {        // begin = Oper(2)%prev, end = Oper(1)%next (CTQMC.F90:3422-3449; adjacent insertions: both are the "inner" sst)
+            std::vector<int> after; sst_sequence(ops, outer_sst, after);
+            int s_b = (i2 == 0) ? outer_sst : after[i2 - 1];          // superstate the later operator acts on (kept inner part ends here)
+            int s_a = (i1 == 0) ? outer_sst : after[i1 - 1];          // superstate the earlier operator has to produce
+            int cur = T.conn(s_b, o2.b, o2.s, o2.ca);
+            for (size_t i = i2; i < ops.size() && cur >= 0; ++i) cur = T.conn(cur, ops[i].b, ops[i].s, ops[i].ca);
+            new_outer = cur;                                          // passes tau = beta: the new outer superstate
+            for (size_t i = 0; i < i1 && cur >= 0; ++i) cur = T.conn(cur, ops[i].b, ops[i].s, ops[i].ca);
+            if (cur >= 0) cur = T.conn(cur, o1.b, o1.s, o1.ca);
+            if (cur < 0 || cur != s_a) { C.AccQNAdd += 1; log_end(2); return; }
         }
         // get_LogDetRatPairAdd Trace.F90:2775-2832 + get_DetRatAdd MatrixUpdate.F90:392-407
         int f = b * 2 + s, k = kf[f];
@@ -670,7 +685,7 @@ struct Chain {
         LogVal DetRat{std::log(std::fabs(S)), sgn(S) * sig};
         LogVal DetNew = lmul(DetRat, Det);
         std::vector<LogVal> parts;
-        LogVal TraceNew = trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2);
+        LogVal TraceNew = outer ? trace_full(nw, new_outer, &parts) : trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2);
         double rand = grnd();
         int NPairs = count_pairs(nw);
         LogVal trr = ldiv(TraceNew, Trace);
@@ -690,7 +705,8 @@ struct Chain {
                     N[in + (size_t)jn * kn] = Mf[i + (size_t)j * k] + S * N[in + (size_t)p2 * kn] * N[p1 + (size_t)jn * kn]; } }
             M[f].swap(N); kf[f] = kn;
             ops.swap(nw);
-            if (fast_trace == 2) fc_accept((int)i1, (int)i2, (int)(i2 - i1) + 2);
+            if (outer) { outer_sst = new_outer; ec.valid = false; fc.valid = false; }
+            else if (fast_trace == 2) fc_accept((int)i1, (int)i2, (int)(i2 - i1) + 2);
             Det = DetNew; Trace = TraceNew; parttrace = parts;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccAdd += 1;
@@ -700,8 +716,8 @@ struct Chain {
         } else log_end(0);
     }
 
-    void StepRem() {                                 // CTQMC.F90:3892-4150 (change_outer = .false.)
-        log_begin(2);
+    void StepRem(bool outer = false) {               // CTQMC.F90:3892-4150
+        log_begin(outer ? 6 : 2);
         C.TryRem += 1;
         // gen_OperRemove Trace.F90:4851-4950
         int NPairs = count_pairs(ops);
@@ -731,13 +747,21 @@ struct Chain {
                         * (std::min(tau_an + taudiff_max, tauwin_max) - std::max(tau_an - taudiff_max, tauwin_min)));
         std::vector<Op> nw; nw.reserve(ops.size());
         for (size_t i = 0; i < ops.size(); ++i) if (i != i1 && i != i2) nw.push_back(ops[i]);
-        {   // begin = Oper(1)%prev, end = Oper(2)%next (CTQMC.F90:3947-3950)
+        int new_outer = outer_sst;
+        if (!outer) {   // begin = Oper(1)%prev, end = Oper(2)%next (CTQMC.F90:3947-3950)
             std::vector<int> after; sst_sequence(ops, outer_sst, after);
             int begin_sst = (i1 == 0) ? outer_sst : after[i1 - 1];
             int end_sst = (i2 + 1 == ops.size()) ? outer_sst : after[i2];
             int cur = begin_sst;
             for (size_t i = i1 + 1; i < i2 && cur >= 0; ++i) cur = T.conn(cur, ops[i].b, ops[i].s, ops[i].ca);
             if (cur < 0 || cur != end_sst) { C.AccQNRem += 1; log_end(2); return; }
+        } else {        // begin = Oper(2)%prev, end = Oper(1)%next (CTQMC.F90:3934-3961): the inner part keeps its superstates
+            std::vector<int> after; sst_sequence(ops, outer_sst, after);
+            int cur = after[i2 - 1];                                  // superstate before the later operator (i2 > i1 >= 0)
+            for (size_t i = i2 + 1; i < ops.size() && cur >= 0; ++i) cur = T.conn(cur, ops[i].b, ops[i].s, ops[i].ca);
+            new_outer = cur;
+            for (size_t i = 0; i < i1 && cur >= 0; ++i) cur = T.conn(cur, ops[i].b, ops[i].s, ops[i].ca);
+            if (cur < 0 || cur != after[i1]) { C.AccQNRem += 1; log_end(2); return; }
         }
         // get_LogDetRatPairRem Trace.F90:2937-2963, get_DetRatRem MatrixUpdate.F90:445-452
         int k = kf[f];
@@ -748,7 +772,7 @@ struct Chain {
         LogVal DetRat{std::log(std::fabs(S)), sgn(S) * sig};
         LogVal DetNew = lmul(DetRat, Det);
         std::vector<LogVal> parts;
-        LogVal TraceNew = trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2 + 1);
+        LogVal TraceNew = outer ? trace_full(nw, new_outer, &parts) : trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2 + 1);
         LogVal trr = ldiv(TraceNew, Trace);
         double prob = std::fabs(factor / (double)(2 * nb) * std::exp(trr.log + DetRat.log));
         double rand = grnd();
@@ -763,7 +787,8 @@ struct Chain {
                     N[i + (size_t)j * kn] = Mf[io + (size_t)jo * k] - Mf[io + (size_t)p2 * k] * Mf[p1 + (size_t)jo * k] / Mf[p1 + (size_t)p2 * k]; } }
             M[f].swap(N); kf[f] = kn;
             ops.swap(nw);
-            if (fast_trace == 2) fc_accept((int)i1, (int)i2 + 1, (int)(i2 - i1) - 1);
+            if (outer) { outer_sst = new_outer; ec.valid = false; fc.valid = false; }
+            else if (fast_trace == 2) fc_accept((int)i1, (int)i2 + 1, (int)(i2 - i1) - 1);
             Det = DetNew; Trace = TraceNew; parttrace = parts;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccRem += 1;
@@ -915,11 +940,11 @@ struct Chain {
     void step() {                                    // CTQMC.F90:8213-8258 / 8428-8533
         double r = grnd();
         if (r < (1.0 - pshift - pglob) / 2.0) {
-            (void)(grnd() >= p4op); (void)(grnd() < pouter);
-            StepAdd();
+            (void)(grnd() >= p4op);
+            StepAdd(grnd() < pouter);
         } else if (r <= 1.0 - pshift - pglob) {
-            (void)(grnd() >= p4op); (void)(grnd() < pouter);
-            StepRem();
+            (void)(grnd() >= p4op);
+            StepRem(grnd() < pouter);
         } else if (r <= 1.0 - pshift) StepGlob();
         else StepShiftTau();
         long long att = (long long)(C.TryAdd + C.TryRem);

@@ -193,7 +193,41 @@ def body_symmetry_moves(make, cfg, nsteps):
         _start(make(), q)
 
 
+def body_outer_moves(make, cfg, nsteps, beta=None, **opts):
+    """Outer pair moves (`PercentageOuterMove > 0`: StepAdd / StepRem with change_outer, CTQMC.F90:3422-3449,
+    3934-3961, 8441-8457): the superstates between the two operators are kept, the rest of the sequence is re-walked over
+    tau = beta and the outer superstate changes.  Replay parity against the oracle (move types 5 / 6 in the log).  At the named
+    configurations' temperatures these moves survive the quantum-number walk but are practically never accepted (a different outer
+    superstate over a long beta); the high-temperature variants (`beta`) exercise the acceptance paths."""
+    from oracle.oracle import OracleChain
+    from _parity import assert_replay
+    p = problems.make_problem(cfg, nftau=2001, beta=beta, PercentageOuterMove=0.25)
+    assert "PercentageOuterMove = 0.25" in p.pstring()
+    eng = _start(make(), p, nchains=8, **opts)
+    eng.init_counters()
+    log = eng.debug_steps(5, nsteps)
+    orc = OracleChain(p, rng="philox", seed=43890, chain=5)
+    orc.init_counters()
+    ref = orc.steps(nsteps, log=True)
+    assert_replay(log, ref)
+    for kind in (5, 6):
+        mv = log[log[:, 0] == kind]
+        assert mv.shape[0] > 0.08 * nsteps and (mv[:, 1] == 2).any()
+        if beta is not None:
+            assert (mv[:, 1] == 1).sum() >= 10 and (mv[:, 1] == 0).sum() >= 10
+    idx = np.nonzero((log[:, 0] >= 5) & (log[:, 1] == 1) & (np.arange(log.shape[0]) > 0))[0]
+    assert (log[idx, 13] != log[idx - 1, 13]).all()                # an accepted outer move always changes the outer superstate
+    assert eng.scalar("error_flags") == 0
+    eng.dest_ctqmc()
+
+
 # ------------------------------------------------------------------ CPU (host-emulation build of the same sources)
+@pytest.mark.parametrize("cfg,nsteps,beta,opts", [("C2", 6000, None, {}), ("C2", 6000, 4.0, {}), ("C3", 5000, 3.0, {}), ("C4", 2500, 2.0, {}),
+                                                  ("C2", 4000, 4.0, {"scheduler": 2})])
+def test_outer_moves(built, cfg, nsteps, beta, opts):
+    body_outer_moves(_hostemu_engine, cfg, nsteps, beta, **opts)
+
+
 @pytest.mark.parametrize("cfg,nsteps", [("C2", 12000), ("C3", 6000)])
 def test_symmetry_moves(built, cfg, nsteps):
     body_symmetry_moves(_hostemu_engine, cfg, nsteps)
@@ -242,6 +276,13 @@ def test_gpu_reuse_population(built, cfg):
 @pytest.mark.parametrize("cfg,nsteps", [("C2", 20000), ("C4", 12000)])
 def test_gpu_symmetry_moves(built, cfg, nsteps):
     body_symmetry_moves(_cuda_engine, cfg, nsteps)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,nsteps,beta,opts", [("C2", 20000, None, {}), ("C4", 8000, None, {}), ("C5", 5000, None, {}), ("C1", 20000, None, {}),
+                                                  ("C2", 20000, 4.0, {}), ("C3", 12000, 3.0, {}), ("C4", 8000, 2.0, {}), ("C2", 8000, 4.0, {"scheduler": 2})])
+def test_gpu_outer_moves(built, cfg, nsteps, beta, opts):
+    body_outer_moves(_cuda_engine, cfg, nsteps, beta, **opts)
 
 
 @pytest.mark.gpu

@@ -122,7 +122,8 @@ void check_supported(const Params& p) {
     zero_i("segment"); zero_i("offdiag"); zero_i("statesampling"); zero_i("Uw"); zero_i("Phonon");
     zero_i("MeasGiw"); zero_i("MeasG2iw"); zero_i("MeasSusz"); zero_i("MeasExpResDensityMatrix"); zero_i("FourPnt");
     zero_i("MeasSsquare"); zero_i("MeasGtauDetRat"); zero_i("flavourchange_moves"); zero_i("Gtau_mean_step"); zero_i("Gtau_mid_step"); zero_i("sign_step");
-    zero_r("PercentageOuterMove"); zero_r("Percentage4OperatorMove");
+    zero_r("Percentage4OperatorMove");                          // PercentageOuterMove (outer pair moves, CTQMC.F90:3422-3449, 3934-3961) is implemented
+    if (p.has("PercentageOuterMove") && (p.real("PercentageOuterMove") < 0.0 || p.real("PercentageOuterMove") > 1.0)) throw std::runtime_error("PercentageOuterMove must lie in [0, 1]");
     if (p.has("Eigenbasis") && p.integer("Eigenbasis") == 0) throw std::runtime_error("You requested Krylov, but this no longer supported.");
     if (p.has("EnableOuterTruncation") && p.str("EnableOuterTruncation") == "YES") throw std::runtime_error("EnableOuterTruncation is outside the implemented hot path");
     if (p.has("AccumGtau") && p.integer("AccumGtau") != 1 && p.integer("AccumGtau") != 2) throw std::runtime_error("AccumGtau must be 1 (mean) or 2 (mean + autocorrelation blocks)");

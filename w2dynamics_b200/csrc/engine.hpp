@@ -199,11 +199,11 @@ __global__ void __launch_bounds__(DECIDE_WARPS * 32, W2B_DECIDE_OCC) k_decide(Ta
 #endif
 }
 // global moves / tau shifts, on their own stream beside the round pipeline: scan the chain states, serve ST_RARE_NEW
-__global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T_, Run R_, Chains C_, long long nsteps, int wdoubles, int mdoubles,
+__global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T_, Run R_, Chains C_, Accum A_, long long nsteps, int wdoubles, int mdoubles,
                                                               int log_chain, double* logbuf) {
     extern __shared__ double smem[];
-    __shared__ Tables T; __shared__ Run R; __shared__ Chains C;
-    if (threadIdx.x == 0) { T = T_; R = R_; C = C_; }
+    __shared__ Tables T; __shared__ Run R; __shared__ Chains C; __shared__ Accum A;
+    if (threadIdx.x == 0) { T = T_; R = R_; C = C_; A = A_; }
     __syncthreads();
     const int warp = threadIdx.x >> 5;
     double* ws = smem + (size_t)warp * wdoubles;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(DECIDE_WARPS * 32, 4) k_rare(Tables T_, Run R_
         unsigned m = __ballot_sync(0xffffffffu, c0 < C.nchains && vload_u8(&C.parked[c0]) == ST_RARE_NEW);
         while (m) {
             const int c = base + __ffs(m) - 1; m &= m - 1;
-            phase_rare(T, R, C, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
+            phase_rare(T, R, C, A, c, nsteps, log_chain, logbuf, ws, is, ws + 3 * C.kcap, ctxs[warp]);
         }
     }
 }
@@ -749,7 +749,7 @@ public:
                 // global moves / tau shifts drawn in this round: served on the rare stream, never waited for by the rounds
                 W2B_CUDA_CHECK(cudaEventRecord(ev_prop[parity], 0));
                 W2B_CUDA_CHECK(cudaStreamWaitEvent(rare_stream, ev_prop[parity], 0));
-                k_rare<<<rp_grid, DECIDE_WARPS * 32, sw_smem, rare_stream>>>(T, R, C, nsteps, wdoubles_sweep, md, log_chain, dlog);
+                k_rare<<<rp_grid, DECIDE_WARPS * 32, sw_smem, rare_stream>>>(T, R, C, A, nsteps, wdoubles_sweep, md, log_chain, dlog);
                 ++launches;
                 if (C.dmax > 1) { k_trace<<<tr_grid, TRACE_WARPS * 32, tr_smem>>>(T, C, tr_doubles, parity); ++launches; }
                 if (time_kernels) W2B_CUDA_CHECK(cudaEventRecord(tev[4 * i + 2], 0));
@@ -761,7 +761,7 @@ public:
                 for (int c = 0; c < nc; ++c) { ProposeOut o{0, 0, -1, 0, -1, 0, 0, 0}; Ctx x; phase_propose(T, R, C, c, nsteps, parity, log_chain, dlog, &o, x); propose_flush(C, parity, &o, 1); }
                 int* sc = C.sched + parity * SC_STRIDE;
                 for (int c = 0; c < nc; ++c)
-                    { Ctx x; phase_rare(T, R, C, c, nsteps, log_chain, dlog, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, x); }
+                    { Ctx x; phase_rare(T, R, C, A, c, nsteps, log_chain, dlog, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, x); }
                 if (C.dmax > 1) for (int t = 0; t < sc[SC_NT0] + sc[SC_NT1] + sc[SC_NT2]; ++t) phase_trace(T, C, t, parity, ws.data() + 3 * C.kcap);
                 const int total = sc[SC_NRFIN] + sc[SC_NQ0] + sc[SC_NQ1] + sc[SC_NQ2];
                 for (int t = 0; t < total; ++t)

@@ -93,6 +93,7 @@ struct RareJob {
     int kind, new_outer, type, stored;       // kind 3 = global move, 4 = tau shift; stored: the trace kernel filled the ket caches of the new configuration
     int knew[NF_MAX];
     double tn_log, tn_sign;                  // staged global moves of the CTA scheduler: local trace of the proposed configuration
+    int nnew;                                // kinds 5 / 6 (outer pair moves): number of operators of the proposed sequence in the scratch arrays
 };
 
 // round scheduler counters (device memory, two sets used in alternation by consecutive rounds)
@@ -491,6 +492,7 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* ws) {
     V.tau = C.op_tau + cb; V.code = C.op_code + cb; V.sst = C.op_sst + cb; V.slot = C.op_slot + cb;
     V.ket = C.ket + cb * C.mstride; V.bra = C.bra + cb * C.mstride; V.ketlg = C.ketlg + cb * C.dmax; V.bralg = C.bralg + cb * C.dmax;
     V.n = ih[IH_NOPS]; V.outer = ih[IH_OUTER]; V.mstride = C.mstride; V.dmax = C.dmax;
+    if (rare && C.rjob[chain].kind >= 5) V.n = C.rjob[chain].nnew;       // outer pair move: the staged sequence has two operators more / less
     const int n = V.n;
     int kv = ih[IH_KV], bv = ih[IH_BV];
     const Prop& P = C.prop[chain];
@@ -504,7 +506,7 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* ws) {
         const RareJob& J = C.rjob[chain];
         V.outer = J.new_outer; kv = 0; bv = n; i1 = 0; i2 = n;
         V.code = C.sc_code + cb;
-        if (J.kind == 4) V.tau = C.sc_tau + cb;
+        if (J.kind >= 4) V.tau = C.sc_tau + cb;
         store_seg = J.stored != 0;
     }
     const double* tau = V.tau; const unsigned char* code = V.code; const short* sst = V.sst; const unsigned short* slot = V.slot;
@@ -710,8 +712,13 @@ W2B_HD void bump_bytes(Ctx& x, long long b) { if (lane_id() == 0) x.cnt[C_ALGBYT
 // -> decide (determinant ratio, blocked trace, Metropolis draw, rank-1 update).  The proposal travels in a Prop record.
 
 // StepAdd part 1 (CTQMC.F90:3353-3469): pair_OperAdd, process_OperAdd, check_sst_sequence.  Returns false on an early exit.
+// OUTER = change_outer (PercentageOuterMove, CTQMC.F90:3422-3449): the superstates BETWEEN the two new operators are kept, the part of
+// the sequence from the later operator over tau = beta to the earlier one is re-walked, and the superstate it passes beta with
+// becomes the outer superstate (check_sst_sequence, Trace.F90:1278-1295); it is left in P.begin_sst.  These moves are served like
+// global moves (whole-sequence trace from scratch: CalcNew, Trace.F90:5381), never by the hot propose kernel.
+template <bool OUTER>
 W2B_HDN bool add_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x, Prop& P) {
-    log_begin(x, 1);
+    log_begin(x, OUTER ? 5 : 1);
     bump(x, C_TRYADD);
     const double W = x.wmax - x.wmin;
     const double tau_a = add_rn(x.wmin, mul_rn(W, x.rng.next()));                    // pair_OperAdd Trace.F90:3672-3695
@@ -734,12 +741,22 @@ W2B_HDN bool add_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     log_set(x, 5, p1 + 1); log_set(x, 6, p2 + 1);
     bump_bytes(x, 64ll * k);
     // quantum-number check of the changed sub-string (+ scalar trace ratio when every block is 1x1)
-    const int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
+    int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
     double dlog = 0.0, dsign = 1.0;
     int cur = conn(T, begin_sst, code1), old_after = begin_sst, nother = 0;
     double tl = t1;
     int new_end = -1;
-    if (T.dmax == 1) {
+    if (OUTER) {
+        const int s_b = i2 == 0 ? x.outer : (int)x.sst[i2 - 1];     // superstate the later operator acts on; begin_sst = the one the earlier has to produce
+        int dummy;
+        cur = conn(T, s_b, code2);
+        if (cur >= 0) cur = walk_check(T, x, i2, x.n - i2, f, cur, dummy);
+        const int new_outer = cur;
+        if (cur >= 0) cur = walk_check(T, x, 0, i1, f, cur, dummy);
+        if (cur >= 0) cur = conn(T, cur, code1);
+        walk_check(T, x, i1, i2 - i1, f, 0, nother);                // operators of other flavours between the two (permutation sign)
+        new_end = cur; old_after = begin_sst; begin_sst = new_outer;
+    } else if (T.dmax == 1) {
         if (cur >= 0) {
             double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog += ldg(&T.lelem[begin_sst * T.nops + code1]); if (e < 0) dsign = -dsign;
             walk_delta(T, x, i1, i2 - i1, f, cur, old_after, tl, dlog, dsign, nother);
@@ -765,6 +782,9 @@ W2B_HDN bool add_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
 }
 
 // StepAdd part 2 (CTQMC.F90:3470-3612): determinant ratio, local trace, Metropolis, get_MatAdd + list insertion
+// OUTER: the proposed sequence (times, codes, superstates from the new outer superstate P.begin_sst) is staged in the scratch arrays
+// (outer_stage) and its local trace was evaluated from scratch: parts in x.mpt (blocked) / ratio in P.dlog, P.dsign (1x1 blocks).
+template <bool OUTER>
 W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, const Prop& P) {
     const int f = P.f, i1 = P.i1, i2 = P.i2, p1 = P.p1, p2 = P.p2, begin_sst = P.begin_sst, nother = P.nother;
     const double t1 = P.t1, t2 = P.t2, tau_a = P.tau_a, tau_c = P.tau_c;
@@ -778,7 +798,8 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     double tn_log = 0.0, tn_sign = 1.0;
     if (blocked) {                                                     // get_trace_EB of the proposed configuration
         // the trace kernel has left the per-outer-state parts of the proposed configuration in C.ptc and extended the cache frontiers
-        parts_sum(x.mpt, ldg(&T.dim[x.outer]), tn_log, tn_sign); if (x.kv < i1) x.kv = i1; if (x.bv > i2) x.bv = i2;
+        parts_sum(x.mpt, ldg(&T.dim[OUTER ? begin_sst : x.outer]), tn_log, tn_sign);
+        if (!OUTER) { if (x.kv < i1) x.kv = i1; if (x.bv > i2) x.bv = i2; }
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
@@ -797,6 +818,13 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     mat_add(C, x, f, T.nf, p1, p2, S);
     shift_up(x.tc + (size_t)f * C.kcap, p1, k, 1); shift_up(x.ta + (size_t)f * C.kcap, p2, k, 1);
     if (lane_id() == 0) { x.tc[(size_t)f * C.kcap + p1] = tau_c; x.ta[(size_t)f * C.kcap + p2] = tau_a; }
+    if (OUTER) {                                                       // the staged sequence replaces the old one; every cached product is void
+#pragma unroll 1
+        for (int i = lane_id(); i < x.n + 2; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
+        wsync();
+        x.n += 2; x.outer = begin_sst;
+        if (blocked) { commit_parts(T, x); slots_reset(C, x); }
+    } else {
     shift_up(x.tau, i2, x.n, 2); shift_up(x.code, i2, x.n, 2); shift_up(x.sst, i2, x.n, 2);
     shift_up(x.tau, i1, i2, 1); shift_up(x.code, i1, i2, 1); shift_up(x.sst, i1, i2, 1);
     if (lane_id() == 0) { x.tau[i1] = t1; x.code[i1] = (unsigned char)code1; x.tau[i2 + 1] = t2; x.code[i2 + 1] = (unsigned char)code2; }
@@ -809,6 +837,7 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     wsync();
     x.n += 2;
     walk_store(T, x.code, i1, i2 - i1 + 2, begin_sst, x.sst, i1);
+    }
     x.det_log += dr_log; x.det_sign *= dr_sign;
     if (blocked) { x.tr_log = tn_log; x.tr_sign = tn_sign; } else { x.tr_log += dlog; x.tr_sign *= dsign; }
     x.perm ^= (nother & 1);
@@ -825,8 +854,10 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
 }
 
 // StepRem part 1 (CTQMC.F90:3892-3977): gen_OperRemove (pair choice in the reference's enumeration order), quantum numbers
+// OUTER = change_outer (CTQMC.F90:3934-3961), see add_propose: the new outer superstate is left in P.begin_sst.
+template <bool OUTER>
 W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x, Prop& P) {
-    log_begin(x, 2);
+    log_begin(x, OUTER ? 6 : 2);
     bump(x, C_TRYREM);
     if (x.npairs < 0) x.npairs = count_pairs_full(T, R, C, x);        // gen_OperRemove Trace.F90:4868-4877
     log_set(x, 14, x.npairs);
@@ -880,12 +911,20 @@ W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     const double factor = (double)x.npairs / ((x.wmax - x.wmin) * (fmin(tau_an + R.taudiff_max, x.wmax) - fmax(tau_an - R.taudiff_max, x.wmin)));
     // quantum numbers (+ scalar trace ratio) of the configuration without the pair
     const int code1 = f * 2 + type1, code2 = f * 2 + (1 - type1);
-    const int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
+    int begin_sst = i1 == 0 ? x.outer : (int)x.sst[i1 - 1];
     double dlog = 0.0, dsign = 1.0;
     int cur = begin_sst, old_after = (int)x.sst[i1], nother = 0;
     double tl = t1;
     const int end_sst = (int)x.sst[i2];
-    if (T.dmax == 1) {
+    if (OUTER) {
+        int dummy;
+        cur = walk_check(T, x, i2 + 1, x.n - i2 - 1, f, (int)x.sst[i2 - 1], dummy);      // from the superstate before the later operator over beta ...
+        const int new_outer = cur;
+        if (cur >= 0) cur = walk_check(T, x, 0, i1, f, cur, dummy);                       // ... to the superstate after the earlier one
+        if (cur < 0 || cur != old_after) { bump(x, C_QNREM); log_end(x, 2); return false; }
+        walk_check(T, x, i1 + 1, i2 - i1 - 1, f, 0, nother);
+        begin_sst = new_outer;
+    } else if (T.dmax == 1) {
         { double e = ldg(&T.elem[begin_sst * T.nops + code1]); dlog -= ldg(&T.lelem[begin_sst * T.nops + code1]); if (e < 0) dsign = -dsign; }
         walk_delta(T, x, i1 + 1, i2 - i1 - 1, f, cur, old_after, tl, dlog, dsign, nother);
         if (cur < 0 || cur != end_sst) { bump(x, C_QNREM); log_end(x, 2); return false; }
@@ -904,6 +943,7 @@ W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
 }
 
 // StepRem part 2 (CTQMC.F90:3978-4150): ratio = M(p1,p2), local trace, Metropolis, get_MatRem + list removal
+template <bool OUTER>
 W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, const Prop& P) {
     const int f = P.f, i1 = P.i1, i2 = P.i2, p1 = P.p1, p2 = P.p2, begin_sst = P.begin_sst, nother = P.nother, type1 = P.type1;
     const double t1 = P.t1, t2 = P.t2;
@@ -912,7 +952,8 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     double dlog = P.dlog, dsign = P.dsign, tn_log = 0.0, tn_sign = 1.0;
     if (blocked) {
-        parts_sum(x.mpt, ldg(&T.dim[x.outer]), tn_log, tn_sign); if (x.kv < i1) x.kv = i1; if (x.bv > i2 + 1) x.bv = i2 + 1;
+        parts_sum(x.mpt, ldg(&T.dim[OUTER ? begin_sst : x.outer]), tn_log, tn_sign);
+        if (!OUTER) { if (x.kv < i1) x.kv = i1; if (x.bv > i2 + 1) x.bv = i2 + 1; }
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
     // determinant ratio = M(p1,p2)  (MatrixUpdate.F90:445-452)
@@ -929,6 +970,13 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     bump_bytes(x, 8ll * (k * k + (k - 1) * (k - 1)));
     mat_rem(C, x, f, T.nf, p1, p2);
     shift_down(x.tc + (size_t)f * C.kcap, p1, k, 1); shift_down(x.ta + (size_t)f * C.kcap, p2, k, 1);
+    if (OUTER) {
+#pragma unroll 1
+        for (int i = lane_id(); i < x.n - 2; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
+        wsync();
+        x.n -= 2; x.outer = begin_sst;
+        if (blocked) { commit_parts(T, x); slots_reset(C, x); }
+    } else {
     if (blocked) {                                                     // give the two cache slots back; kets valid below i1, bras from i2-1 on
         if (lane_id() == 0) { x.freel[x.nfree] = x.slot[i1]; x.freel[x.nfree + 1] = x.slot[i2]; }
         wsync();
@@ -940,6 +988,7 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     shift_down(x.tau, i2 - 1, x.n, 2); shift_down(x.code, i2 - 1, x.n, 2); shift_down(x.sst, i2 - 1, x.n, 2);
     x.n -= 2;
     walk_store(T, x.code, i1, i2 - i1 - 1, begin_sst, x.sst, i1);
+    }
     x.det_log += dr_log; x.det_sign *= dr_sign;
     if (blocked) { x.tr_log = tn_log; x.tr_sign = tn_sign; } else { x.tr_log += dlog; x.tr_sign *= dsign; }
     x.perm ^= (nother & 1);
@@ -1334,6 +1383,45 @@ W2B_HD void step_rare(const Tables& T, const Run& R, const Chains& C, Ctx& x, Ra
     if (kind == 3) step_glob_finish(T, R, C, x, J, tn_log, tn_sign); else step_shift_finish(T, R, C, x, J, tn_log, tn_sign);
 }
 
+// ------------------------------------------------------------------ StepAdd / StepRem with change_outer (PercentageOuterMove)
+// Served like global moves: the proposed sequence is staged in the scratch arrays and its local trace evaluated from scratch.
+// Stages the proposed sequence of an outer pair move: times and codes with the pair inserted / taken out, superstates walked from
+// the new outer superstate P.begin_sst; 1x1 blocks: also the trace ratio (P.dlog, P.dsign).  Returns false when it does not fit.
+W2B_HDN bool outer_stage(const Tables& T, const Chains& C, Ctx& x, Prop& P, RareJob& J, bool add) {
+    const int n = x.n, i1 = P.i1, i2 = P.i2, nn = add ? n + 2 : n - 2, new_outer = P.begin_sst;
+    if (nn > C.ops_cap) { x.err |= ERR_CAPACITY; log_end(x, 0); return false; }
+    const int codeA = P.f * 2 + P.type1, codeB = P.f * 2 + (1 - P.type1);
+#pragma unroll 1
+    for (int i = lane_id(); i < nn; i += W2B_WARP) {
+        int src;                                                     // >= 0: old operator; -1 / -2: the new pair
+        if (add) src = i < i1 ? i : (i == i1 ? -1 : (i <= i2 ? i - 1 : (i == i2 + 1 ? -2 : i - 2)));
+        else src = i < i1 ? i : (i < i2 - 1 ? i + 1 : i + 2);
+        x.sc_tau[i] = src >= 0 ? x.tau[src] : (src == -1 ? P.t1 : P.t2);
+        x.sc_code[i] = src >= 0 ? x.code[src] : (unsigned char)(src == -1 ? codeA : codeB);
+    }
+    wsync();
+    walk_store(T, x.sc_code, 0, nn, new_outer, x.sc_sst, 0);
+    if (T.dmax == 1) {
+        double tl, ts;
+        trace_full_scalar(T, x.sc_tau, x.sc_code, x.sc_sst, nn, new_outer, tl, ts);
+        if (lane_id() == 0) { P.dlog = tl - x.tr_log; P.dsign = ts * x.tr_sign; }
+    }
+    if (lane_id() == 0) { J.kind = add ? 5 : 6; J.new_outer = new_outer; J.nnew = nn; J.stored = 0; }
+    wsync();
+    return true;
+}
+// first half (kinds 5 / 6); returns true when the proposal survived and is staged
+W2B_HDN bool outer_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x, Prop& P, RareJob& J, int kind) {
+    const bool go = kind == 5 ? add_propose<true>(T, R, C, x, P) : rem_propose<true>(T, R, C, x, P);
+    return go && outer_stage(T, C, x, P, J, kind == 5);
+}
+// the whole move on one warp (1x1 blocks; host paths that do not use the trace kernel)
+W2B_HDN void step_outer(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, Prop& P, RareJob& J, int kind) {
+    if (!outer_prepare(T, R, C, x, P, J, kind)) return;
+    if (T.dmax > 1) { double tl, ts; full_trace(T, x, x.sc_tau, x.sc_code, J.nnew, J.new_outer, tl, ts); }     // parts in x.mpt
+    if (kind == 5) add_decide<true>(T, R, C, A, x, P); else rem_decide<true>(T, R, C, A, x, P);
+}
+
 // ------------------------------------------------------------------ chain load / store
 W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, double* wscratch, int* iscratch, double* mscratch) {
     x.tau = C.op_tau + (size_t)chain * C.ops_cap; x.code = C.op_code + (size_t)chain * C.ops_cap; x.sst = C.op_sst + (size_t)chain * C.ops_cap;
@@ -1561,11 +1649,17 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                     if (lane == 0) { S.kind[c] = (unsigned char)(r <= thr_glob ? 3 : 4); S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
                     break;
                 }
-                x.rng.skip(2);                                            // Percentage4OperatorMove / PercentageOuterMove draws (both 0)
+                if (R.pouter > 0.0) {                                     // Percentage4OperatorMove draw (0), then `grnd() < PercentageOuterMove` (CTQMC.F90:8441-8442)
+                    x.rng.skip(1);
+                    if (x.rng.next() < R.pouter) {                        // outer pair move: parked, served like a global move
+                        if (lane == 0) { S.kind[c] = (unsigned char)(r < thr_add ? 5 : 6); S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
+                        break;
+                    }
+                } else x.rng.skip(2);
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
                 bool go;
-                if (r < thr_add) { go = add_propose(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lA2[wgrab_one(&S.nA2)] = (short)c; }
-                else { go = rem_propose(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lR2[wgrab_one(&S.nR2)] = (short)c; }
+                if (r < thr_add) { go = add_propose<false>(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lA2[wgrab_one(&S.nA2)] = (short)c; }
+                else { go = rem_propose<false>(T, R, C, x, S.prop[c]); if (go && lane == 0) S.lR2[wgrab_one(&S.nR2)] = (short)c; }
                 if (go) break;
                 post_move_cta(T, R, x, S, c);
             }
@@ -1591,7 +1685,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                     if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
                     ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                     if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                    add_decide(T, R, C, A, x, S.prop[c]);
+                    add_decide<false>(T, R, C, A, x, S.prop[c]);
                     post_move_cta(T, R, x, S, c);
                     ctx_store(C, chain, x);
                 }
@@ -1601,7 +1695,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                     if (T.dmax > 1 && (ldg(&T.dim[C.ih[(size_t)chain * IH_STRIDE + IH_OUTER]]) > 1) != (pass == 0)) continue;
                     ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                     if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                    rem_decide(T, R, C, A, x, S.prop[c]);
+                    rem_decide<false>(T, R, C, A, x, S.prop[c]);
                     post_move_cta(T, R, x, S, c);
                     ctx_store(C, chain, x);
                 }
@@ -1633,7 +1727,8 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                 if ((int)S.kind[c] == 3 && LG.cap > 0 && kmax >= LU_GROUP_MIN) {
                     staged = step_glob_prepare(T, R, C, x, C.rjob[chain], false);
                     if (staged && lane == 0) S.lA[wgrab_one(&S.nLU)] = (short)c;
-                } else step_rare(T, R, C, x, C.rjob[chain], (int)S.kind[c]);
+                } else if ((int)S.kind[c] >= 5) step_outer(T, R, C, A, x, S.prop[c], C.rjob[chain], (int)S.kind[c]);
+                else step_rare(T, R, C, x, C.rjob[chain], (int)S.kind[c]);
                 if (!staged) post_move_cta(T, R, x, S, c);
                 ctx_store(C, chain, x);
                 if (!staged && lane == 0) S.parked[c] = 0;
@@ -1786,11 +1881,17 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
             if (lane == 0) { C.kind[chain] = (unsigned char)(r <= thr_glob ? 3 : 4); C.parked[chain] = ST_RARE_NEW; }
             break;
         }
-        x.rng.skip(2);                                            // Percentage4OperatorMove / PercentageOuterMove draws (both 0)
+        if (R.pouter > 0.0) {                                     // Percentage4OperatorMove draw (0), then `grnd() < PercentageOuterMove` (CTQMC.F90:8441-8442)
+            x.rng.skip(1);
+            if (x.rng.next() < R.pouter) {                        // outer pair move: rare stream
+                if (lane == 0) { C.kind[chain] = (unsigned char)(r < thr_add ? 5 : 6); C.parked[chain] = ST_RARE_NEW; }
+                break;
+            }
+        } else x.rng.skip(2);
         if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - left) * LOGW;
         bool go; int entry = chain;
-        if (r < thr_add) go = add_propose(T, R, C, x, C.prop[chain]);
-        else { go = rem_propose(T, R, C, x, C.prop[chain]); entry |= Q_REM; }
+        if (r < thr_add) go = add_propose<false>(T, R, C, x, C.prop[chain]);
+        else { go = rem_propose<false>(T, R, C, x, C.prop[chain]); entry |= Q_REM; }
         if (go) {
             if (lane == 0) {
                 const int m = T.dmax > 1 ? ldg(&T.dim[x.outer]) : 1;
@@ -1865,7 +1966,7 @@ W2B_HD void phase_trace(const Tables& T, const Chains& C, int ticket, int parity
 //   blocked traces: the first half (everything up to the local trace), then ST_RARE_TRACE: the next propose kernel queues the
 //                   trace jobs and the second half for its round (trace kernel / decide kernel).
 // The round pipeline never waits for this stream; a chain whose rare move is in flight simply sits out a few rounds.
-W2B_HD void phase_rare(const Tables& T, const Run& R, const Chains& C, int chain, long long nsteps,
+W2B_HD void phase_rare(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain, long long nsteps,
                        int log_chain, double* logbuf, double* wscratch, int* iscratch, double* mscratch, Ctx& x) {
     if (vload_u8(&C.parked[chain]) != ST_RARE_NEW) return;
     ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
@@ -1873,7 +1974,10 @@ W2B_HD void phase_rare(const Tables& T, const Run& R, const Chains& C, int chain
     RareJob& J = C.rjob[chain];
     const int kind = C.kind[chain];
     bool pending = false;
-    if (T.dmax > 1) {
+    if (kind >= 5) {                                                 // outer pair moves (PercentageOuterMove)
+        if (T.dmax > 1) pending = outer_prepare(T, R, C, x, C.prop[chain], J, kind);
+        else step_outer(T, R, C, A, x, C.prop[chain], J, kind);
+    } else if (T.dmax > 1) {
         pending = kind == 3 ? step_glob_prepare(T, R, C, x, J) : step_shift_prepare(T, R, C, x, J);
         if (pending && kind == 4 && lane_id() == 0) J.stored = 1;    // tau shifts are accepted with probability ~1: cache the kets of the new sequence
     } else step_rare(T, R, C, x, J, kind);
@@ -1903,10 +2007,14 @@ W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const A
         double tn_log, tn_sign;
         x.mpt = C.ptc + (size_t)chain * 2 * C.dmax;
         parts_sum(x.mpt, ldg(&T.dim[J.new_outer]), tn_log, tn_sign);
-        if (C.kind[chain] == 3) step_glob_finish(T, R, C, x, J, tn_log, tn_sign); else step_shift_finish(T, R, C, x, J, tn_log, tn_sign);
+        const int kind = C.kind[chain];
+        if (kind == 3) step_glob_finish(T, R, C, x, J, tn_log, tn_sign);
+        else if (kind == 4) step_shift_finish(T, R, C, x, J, tn_log, tn_sign);
+        else if (kind == 5) add_decide<true>(T, R, C, A, x, C.prop[chain]);
+        else rem_decide<true>(T, R, C, A, x, C.prop[chain]);
     }
-    else if (entry & Q_REM) rem_decide(T, R, C, A, x, C.prop[chain]);
-    else add_decide(T, R, C, A, x, C.prop[chain]);
+    else if (entry & Q_REM) rem_decide<false>(T, R, C, A, x, C.prop[chain]);
+    else add_decide<false>(T, R, C, A, x, C.prop[chain]);
     post_move(T, R, C, x, chain);
     ctx_store(C, chain, x);
     if (rare && lane == 0) C.parked[chain] = ST_RUN;

@@ -238,36 +238,39 @@ def _assemble(name, nb, beta, ham, qns, um8, mu, n_bath, qmc, nftau=5000):
                    muimp, ftau, q, eps, v, mu)
 
 
-def make_problem(cfg: str, nftau: int = 5000, **qmc_over) -> Problem:
-    """The five named configurations of BASELINE.json (table in SURVEY.md §8(d))."""
+def make_problem(cfg: str, nftau: int = 5000, beta: float = None, **qmc_over) -> Problem:
+    """The five named configurations of BASELINE.json (table in SURVEY.md §8(d)).  `beta` overrides the inverse temperature (tests
+    of moves that are only accepted at high temperature); TaudiffMax is then capped at beta."""
     cfg = cfg.upper()
     if cfg == "C1":
         um = u_density(1, 2.0, 0.0, 0.0)
-        p = _assemble("C1", 1, 10.0, "Density", "Nt Szt Azt", um, 1.0, 8,
+        p = _assemble("C1", 1, beta or 10.0, "Density", "Nt Szt Azt", um, 1.0, 8,
                       {"Nwarmups": 100000, "Nmeas": 10000, "NCorr": 100, "TaudiffMax": 10.0}, nftau)
     elif cfg == "C2":
         u, jj, v = 4.0, 0.75, 2.5
         um = u_density(2, u, v, jj)
         mu = 0.5 * (u + (2 - 1) * (2 * v - jj))
-        p = _assemble("C2", 2, 50.0, "Density", "Nt Szt Azt", um, mu, 8,
+        p = _assemble("C2", 2, beta or 50.0, "Density", "Nt Szt Azt", um, mu, 8,
                       {"TaudiffMax": 5.0}, nftau)
     elif cfg == "C3":
         u, jj, v = 4.0, 0.6, 2.8
         um = u_kanamori(3, u, v, jj)
         mu = 0.5 * (u + (3 - 1) * (2 * v - jj))
-        p = _assemble("C3", 3, 40.0, "Kanamori", "Nt Szt Qzt", um, mu, 6,
+        p = _assemble("C3", 3, beta or 40.0, "Kanamori", "Nt Szt Qzt", um, mu, 6,
                       {"TaudiffMax": 4.0}, nftau)
     elif cfg == "C4":
         um, cub = u_coulomb(5, 4.0, 8.615, 5.385)
         ud = udens_from_ufull(cub)
         mu = 0.5 * ud[0, 0].sum()
-        p = _assemble("C4", 5, 20.0, "Coulomb", "Nt Szt All", um, mu, 6,
+        p = _assemble("C4", 5, beta or 20.0, "Coulomb", "Nt Szt All", um, mu, 6,
                       {"TaudiffMax": 2.0, "Nmeas": 2000}, nftau)
     elif cfg == "C5":
         um = u_density(1, 2.0, 0.0, 0.0)
-        p = _assemble("C5", 1, 200.0, "Density", "Nt Szt Azt", um, 1.0, 8,
+        p = _assemble("C5", 1, beta or 200.0, "Density", "Nt Szt Azt", um, 1.0, 8,
                       {"TaudiffMax": 3.0}, nftau)
     else:
         raise ValueError("unknown config %r" % cfg)
+    if beta is not None:
+        p.qmc["TaudiffMax"] = min(p.qmc["TaudiffMax"], float(beta))
     p.qmc.update(qmc_over)
     return p
