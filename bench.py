@@ -272,7 +272,7 @@ def run_engine(args, cfg):
     eng = MCTQMC()
     eng.set_option("nchains", nchains); eng.set_option("nbins", 32); eng.set_option("device", local)
     eng.set_option("reuse_population", 1)      # dest_ctqmc parks the thermalised population; the next init_solver revives it (ReuseMCConfig for all chains)
-    for key in ("cta_warps", "ops_cap", "scheduler", "batch_chains"):
+    for key in ("cta_warps", "ops_cap", "scheduler", "batch_chains", "lu_groups"):
         if os.environ.get("W2B_" + key.upper()):
             eng.set_option(key, int(os.environ["W2B_" + key.upper()]))
     if world > 1 and not _DIST.get("on"):

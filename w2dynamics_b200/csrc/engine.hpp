@@ -109,7 +109,7 @@ W2B_HOSTDEV inline void sched_carve(CtaShared& S, char* base, int ncb) {
 #if W2B_DEVICE
 // persistent sweep kernel: every CTA serves batches of ncb chains (batch b -> chains [b*ncb, (b+1)*ncb))
 __global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T_, Run R_, Chains C_, Accum A_, long long nsteps, int wdoubles, int ncb, int nbatch,
-                                                             int log_chain, double* logbuf, int lu_groups) {
+                                                             int log_chain, double* logbuf) {
     extern __shared__ double smem[];
     __shared__ CtaShared S;
     // one chain context per warp and one copy of the parameter structs per CTA in shared memory (not one per thread in local memory)
@@ -123,14 +123,9 @@ __global__ void __launch_bounds__(MAX_CTA_THREADS, 1) k_sweep(Tables T_, Run R_,
     if (threadIdx.x == 0) { CtaShared tmp; sched_carve(tmp, (char*)(smem + (size_t)W * wdoubles), ncb);
         S.prop = tmp.prop; S.left = tmp.left; S.lA = tmp.lA; S.lR = tmp.lR; S.lA2 = tmp.lA2; S.lR2 = tmp.lR2; S.lG = tmp.lG; S.parked = tmp.parked; S.kind = tmp.kind; }
     __syncthreads();
-    // global moves: groups of W / lu_groups warps share one matrix buffer = the scratch of the group's warps except its first
-    // (idle while the group works on a matrix; the first warp keeps its scratch for the moves that do not fit)
-    LuGroup LG;
-    LG.gwarps = lu_groups > 0 ? W / lu_groups : 1; LG.gid = lu_groups > 0 ? warp / LG.gwarps : 0; LG.gw = lu_groups > 0 ? warp % LG.gwarps : 0;
-    LG.buf = smem + (size_t)(LG.gid * LG.gwarps + 1) * wdoubles; LG.cap = lu_groups > 0 ? (LG.gwarps - 1) * wdoubles : 0;
     for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
         const int lo = b * ncb, nloc = min(ncb, C.nchains - lo);
-        cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws, is, ws + 3 * C.kcap, log_chain, logbuf, ctxs[warp], LG);
+        cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws, is, ws + 3 * C.kcap, log_chain, logbuf, ctxs[warp]);
         __syncthreads();
     }
 }
@@ -309,7 +304,7 @@ struct EngineOptions {
     int nchains = 1024, nbins = 16, kcap = 0, ops_cap = 0;
     int cta_warps = 0, batch_chains = 0;      // sweep kernel geometry (0 = automatic)
     int scheduler = 0;                        // 1x1 blocks: 0 / 1 = persistent CTA-scheduler kernel, 2 = round kernels (blocked traces always use rounds)
-    int lu_groups = 0;                        // CTA scheduler: warp groups of the shared-memory LU of global moves (0 = automatic, -1 = off)
+    int lu_groups = 0;                        // (accepted and ignored: the shared-memory group LU of round 2 was replaced by invert_blocked)
     unsigned seed = 0, chain_base = 0;
 };
 
@@ -586,7 +581,7 @@ public:
     }
 
     // ---- 1x1 blocks: persistent CTA-scheduler kernel; geometry: W warps per CTA, batches of ncb chains, persistent grid
-    int ct_warps = 1, ct_ncb = 1, ct_nbatch = 1, ct_grid = 1, ct_lu_groups = 0; size_t ct_smem = 0; bool ct_ready = false;
+    int ct_warps = 1, ct_ncb = 1, ct_nbatch = 1, ct_grid = 1; size_t ct_smem = 0; bool ct_ready = false;
     void plan_cta() {
         const int nc = C.nchains;
 #if W2B_DEVICE
@@ -613,14 +608,6 @@ public:
         if (ncb > target) ncb = target;
         ct_warps = W; ct_ncb = ncb; ct_nbatch = (nc + ncb - 1) / ncb; ct_grid = std::min(ct_nbatch, slots);
         ct_smem = W * per_warp + sched_bytes(ncb);
-        // warp groups of the shared-memory LU: as many groups as still hold the largest matrix, at least 16 warps per group otherwise
-        // (larger matrices take the one-warp path in global memory); option lu_groups: -1 = off
-        ct_lu_groups = 0;
-        if (opt.lu_groups >= 0 && W >= 4) {
-            ct_lu_groups = W >= 32 ? 2 : 1;
-            for (int g = 4; g >= 1; g >>= 1) if (W % g == 0 && W / g >= 2 && lu_need(C.kcap) <= (W / g - 1) * wdoubles_sweep) { ct_lu_groups = g; break; }
-            if (opt.lu_groups > 0 && W % opt.lu_groups == 0 && W / opt.lu_groups >= 2) ct_lu_groups = opt.lu_groups;
-        }
 #else
         ct_warps = 1; ct_ncb = opt.batch_chains > 0 ? opt.batch_chains : 4; ct_nbatch = (nc + ct_ncb - 1) / ct_ncb; ct_grid = 1;
 #endif
@@ -633,17 +620,16 @@ public:
         double* dlog = nullptr;
         if (log_chain >= 0) dlog = dev_alloc<double>((size_t)nsteps * LOGW);
 #if W2B_DEVICE
-        k_sweep<<<ct_grid, ct_warps * 32, ct_smem>>>(T, R, C, A, nsteps, wdoubles_sweep, ct_ncb, ct_nbatch, log_chain, dlog, ct_lu_groups); ++launches;
+        k_sweep<<<ct_grid, ct_warps * 32, ct_smem>>>(T, R, C, A, nsteps, wdoubles_sweep, ct_ncb, ct_nbatch, log_chain, dlog); ++launches;
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
         std::vector<double> ws(wdoubles + 8);
-        std::vector<double> lubuf(opt.lu_groups < 0 ? 0 : lu_need(C.kcap));       // host emulation: the "group" is one thread with a buffer of its own
         std::vector<char> sb(sched_bytes(ct_ncb));
         CtaShared S{}; sched_carve(S, sb.data(), ct_ncb);
         for (int b = 0; b < ct_nbatch; ++b) {
             const int lo = b * ct_ncb, nloc = std::min(ct_ncb, C.nchains - lo);
-            { Ctx x; LuGroup LG{lubuf.data(), (int)lubuf.size(), 0, 1, 0};
-              cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, log_chain, dlog, x, LG); }
+            { Ctx x;
+              cta_sweep(T, R, C, A, lo, nloc, nsteps, S, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, log_chain, dlog, x); }
         }
 #endif
         if (log_chain >= 0) { sync(); d2h(log_host, dlog, (size_t)nsteps * LOGW); dev_free(dlog); }

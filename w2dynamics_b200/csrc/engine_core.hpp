@@ -1093,6 +1093,131 @@ W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, double* colv, dou
     }
 }
 
+// Blocked Gauss-Jordan with partial pivoting on the FP64 tensor pipe: the same job as invert_inplace (in-place inverse, or only
+// log|det| / sign, of the k x k row-major matrix a) for the large matrices of global moves at large beta, where the k^3 work of
+// DGETRF / DGETRI (MatrixUpdate.F90:41-99) is most of the arithmetic of the whole run (C5: every global move is accepted, so each
+// needs 2 determinants and 2 inverses of 74 x 74 matrices -- 70 % of all flops; the unblocked warp version re-read and re-wrote
+// the matrix once per pivot, a warp GROUP eliminating it in shared memory spent 47 % of the sweep kernel's instructions there and
+// served two matrices per SM at a time).  Here ONE warp owns a matrix, in global memory (L1 / L2), no CTA barriers:
+//   panel  4 pivots at a time: unblocked Gauss-Jordan steps restricted to the panel's 4 columns (pivot search, row swap, lanes over
+//          rows).  Afterwards the panel holds P = [ A_BB^-1 ; -A_OB A_BB^-1 ] (B = the 4 pivot rows, O = the other rows).
+//   update every other column at once: rows O  A_OO += P_OB R,  rows B  A_BO = P_BB R  with R = the 4 pivot rows before the update --
+//          one DMMA.8x8x4 per 8 x 8 tile (K = 4 = the panel width), 16 tiles' worth of data touched once per panel instead of once
+//          per pivot.
+// Determinant only (want_inverse = false): panel and update are restricted to the trailing rows / columns (an LU in disguise).
+// In exact arithmetic the pivots are those of the unblocked elimination; the determinant is accumulated as a product with the
+// exponent split off (one logarithm per matrix instead of one per pivot).
+constexpr int LU_BLOCKED_MIN = 24;     // orders from which rebuild_inverses uses the blocked routine
+W2B_HDN void invert_blocked(double* a, int k, int ld, int* wI, bool want_inverse, double& lg, double& sg) {
+    const int lane = lane_id();
+    double prod = 1.0; int esum = 0;
+    sg = 1.0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < k; c0 += 4) {
+        const int pw = k - c0 < 4 ? k - c0 : 4;
+        const int rlo = want_inverse ? 0 : c0;
+        // ---- panel
+#pragma unroll 1
+        for (int q = 0; q < pw; ++q) {
+            const int c = c0 + q;
+            double best = 0.0; int bi = c;
+#pragma unroll 1
+            for (int r = c + lane; r < k; r += W2B_WARP) { const double v = fabs(a[(size_t)r * ld + c]); if (v > best) { best = v; bi = r; } }
+            double bv; const int p = wargmax_abs(best, bi, bv);
+            if (!(bv > 0.0)) { sg = 0.0; lg = -1.7976931348623157e308; return; }
+            if (lane == 0) wI[c] = p;
+            if (p != c) {
+#pragma unroll 1
+                for (int j = lane; j < k; j += W2B_WARP) { const double t = a[(size_t)c * ld + j]; a[(size_t)c * ld + j] = a[(size_t)p * ld + j]; a[(size_t)p * ld + j] = t; }
+                sg = -sg;
+            }
+            wsync();
+            double pr[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) pr[t] = t < pw ? a[(size_t)c * ld + c0 + t] : 0.0;
+            const double piv = q == 0 ? pr[0] : (q == 1 ? pr[1] : (q == 2 ? pr[2] : pr[3]));
+            const double ipiv = 1.0 / piv;
+            prod *= piv;
+            {   // split the exponent off the running product (exact scaling)
+#if W2B_DEVICE
+                const int hi = __double2hiint(prod), e = ((hi >> 20) & 0x7ff) - 1023;
+                prod = __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(prod));
+#else
+                int e; prod = std::frexp(prod, &e) * 2.0; e -= 1;
+#endif
+                esum += e;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) pr[t] = (t == q) ? ipiv : pr[t] * ipiv;      // scaled pivot row; its own column becomes the inverse column
+            wsync();
+#pragma unroll 1
+            for (int r = rlo + lane; r < k; r += W2B_WARP) {
+                double* row = a + (size_t)r * ld + c0;
+                if (r == c) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) if (t < pw) row[t] = pr[t];
+                } else {
+                    const double f = row[q];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) if (t < pw) row[t] = (t == q) ? -f * ipiv : row[t] - f * pr[t];
+                }
+            }
+            wsync();
+        }
+        // ---- every other column: one rank-4 update
+        const int jlo = want_inverse ? 0 : (c0 + pw) & ~7;
+        const int ilo = want_inverse ? 0 : (c0 + pw) & ~7;
+#if W2B_DEVICE
+        const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll 1
+        for (int j0 = jlo; j0 < k; j0 += 8) {
+            const int jb = j0 + g;                                                                  // B fragment: R[t4][j0 + g]
+            const bool jb_ok = jb < k && t4 < pw && !(jb >= c0 && jb < c0 + pw);
+            const double b = jb_ok ? a[(size_t)(c0 + t4) * ld + jb] : 0.0;
+            const int jc = j0 + 2 * t4;                                                             // C fragment: rows i0 + g, columns jc, jc + 1
+            const bool c0_ok = jc < k && !(jc >= c0 && jc < c0 + pw), c1_ok = jc + 1 < k && !(jc + 1 >= c0 && jc + 1 < c0 + pw);
+            wsync();                                                                                // R is read before any row of this tile column is rewritten
+#pragma unroll 2
+            for (int i0 = ilo; i0 < k; i0 += 8) {
+                const int ia = i0 + g;
+                const bool in_b = ia >= c0 && ia < c0 + pw;
+                const bool row_ok = ia < k && (want_inverse || ia >= c0 + pw);
+                const double af = (ia < k && t4 < pw) ? a[(size_t)ia * ld + c0 + t4] : 0.0;        // A fragment: P[i0 + g][t4]
+                double* cp = a + (size_t)ia * ld + jc;
+                double d0 = (row_ok && c0_ok && !in_b) ? cp[0] : 0.0, d1 = (row_ok && c1_ok && !in_b) ? cp[1] : 0.0;
+                dmma884(d0, d1, af, b);
+                if (row_ok && c0_ok) cp[0] = d0;
+                if (row_ok && c1_ok) cp[1] = d1;
+            }
+        }
+        wsync();
+#else
+        for (int j = jlo; j < k; ++j) {
+            if (j >= c0 && j < c0 + pw) continue;
+            double rr[4];
+            for (int t = 0; t < pw; ++t) rr[t] = a[(size_t)(c0 + t) * ld + j];
+            for (int i = ilo; i < k; ++i) {
+                if (!want_inverse && i < c0 + pw) continue;
+                double v = (i >= c0 && i < c0 + pw) ? 0.0 : a[(size_t)i * ld + j];
+                for (int t = 0; t < pw; ++t) v += a[(size_t)i * ld + c0 + t] * rr[t];
+                a[(size_t)i * ld + j] = v;
+            }
+        }
+#endif
+    }
+    lg = w_log(fabs(prod)) + (double)esum * 0.6931471805599453;
+    if (prod < 0.0) sg = -sg;
+    if (want_inverse) {
+        // undo the row swaps as column swaps in reverse order: inv(P A) = inv(A) P^T
+#pragma unroll 1
+        for (int c = k - 1; c >= 0; --c) {
+            const int p = wI[c];
+            if (p != c) for (int r = lane; r < k; r += W2B_WARP) { const double t = a[(size_t)r * ld + c]; a[(size_t)r * ld + c] = a[(size_t)r * ld + p]; a[(size_t)r * ld + p] = t; }
+            wsync();
+        }
+    }
+}
+
 // Rebuild every inverse hybridisation matrix from the flavour tau arrays (get_InvFullHybr Trace.F90:2279-2333):
 // Delta(ia, ic) = F(tau_a[ia] - tau_c[ic]) ; M = Delta^{-1} is indexed (creator, annihilator).
 // Builds directly the transposed system so that the in-place inverse lands in M's [creator][annihilator] layout.
@@ -1112,7 +1237,8 @@ W2B_HDN void rebuild_inverses(const Tables& T, const Chains& C, Ctx& x, const do
             for (int ic = lane_id(); ic < k; ic += W2B_WARP) a[(size_t)ia * C.ld + ic] = hybrF(T, ta[ia] - tc[ic], f);
         wsync();
         double l, s;
-        invert_inplace(a, k, C.ld, x.wI, x.wQ, x.wR, want_inverse, l, s);
+        if (k >= LU_BLOCKED_MIN) invert_blocked(a, k, C.ld, x.wI, want_inverse, l, s);
+        else invert_inplace(a, k, C.ld, x.wI, x.wQ, x.wR, want_inverse, l, s);
         lg += l; sg *= s;
     }
 }
@@ -1211,7 +1337,7 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
     wsync();
     if (lane_id() == 0) { J.kind = 3; J.new_outer = new_outer; J.type = type; J.factor = factor; J.stored = 0; }
     wsync();
-    if (!with_lu) return true;               // staged form (CTA scheduler): the determinants come from the group LU in shared memory
+    if (!with_lu) return true;               // (callers that obtain the determinants elsewhere)
     // determinant of the new configuration from scratch (LU in the spare buffer).  The reference obtains the old determinant
     // from an LU of the stored inverses (get_FullLogDet, Trace.F90:2665-2685); the tracked Det is the same number up to the
     // rounding of the fast updates (pinned by the from-scratch tests), so the second LU is not repeated here.
@@ -1459,104 +1585,6 @@ W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
 }
 
-// ------------------------------------------------------------------ group LU in shared memory (global moves of the CTA scheduler)
-// A global move needs the determinant of every flavour's hybridisation matrix from scratch and, when accepted, its inverse
-// (get_InvFullHybr / get_MatLogDetFull, Trace.F90:2279-2333, MatrixUpdate.F90:41-99).  One warp eliminating a 75 x 75 matrix in
-// global memory re-reads and re-writes the matrix for every pivot: at beta = 200 that was 40 % of the sweep kernel's instructions
-// and seven times the algorithmic DRAM traffic (profiles/r2h_*).  Here a GROUP of warps of the CTA (named barrier) builds the
-// matrix in shared memory, eliminates it there -- same pivots and the same arithmetic per element as invert_inplace -- and
-// writes only the inverse back.
-constexpr int LU_GROUP_MIN = 40;       // flavour orders from which a global move goes through the staged group path
-struct LuGroup { double* buf; int cap, gid, gwarps, gw; };           // buffer (doubles), group id, warps per group, this warp's index in it
-W2B_HD void grp_sync(const LuGroup& G) {
-#if W2B_DEVICE
-    asm volatile("bar.sync %0, %1;" ::"r"(G.gid + 1), "r"(G.gwarps * 32) : "memory");
-#endif
-}
-#if W2B_DEVICE
-__host__ __device__
-#endif
-inline int lu_need(int k) { return k * (k | 1) + 2 * k + (k + 1) / 2 + 4; }
-// log|det| and sign of flavour f's matrix Delta(ia, ic) = F(ta[ia] - tc[ic]) (every thread of the group returns them); with Mdst the
-// inverse is written to Mdst[creator][annihilator] (leading dimension ldm).  Singular -> sign 0.
-W2B_HDN void group_lu(const Tables& T, const LuGroup& G, const double* tc, const double* ta, int k, int f, double* Mdst, int ldm, double& lg, double& sg) {
-    const int lds = k | 1, lane = lane_id();
-    double* A = G.buf; double* colv = A + k * lds; double* rowv = colv + k; int* piv = (int*)(rowv + k); int* flag = piv + k + (k & 1);
-    lg = 0.0; sg = 1.0;
-#pragma unroll 1
-    for (int ia = G.gw; ia < k; ia += G.gwarps) {
-        const double t = ta[ia];
-#pragma unroll 1
-        for (int ic = lane; ic < k; ic += W2B_WARP) A[ia * lds + ic] = hybrF(T, t - tc[ic], f);
-    }
-    grp_sync(G);
-#pragma unroll 1
-    for (int c = 0; c < k; ++c) {
-        if (G.gw == 0) {                                           // pivot search (rows >= c of column c) by the group's first warp
-            double best = 0.0; int bi = c;
-#pragma unroll 1
-            for (int r = c + lane; r < k; r += W2B_WARP) { const double v = fabs(A[r * lds + c]); if (v > best) { best = v; bi = r; } }
-            double bv; const int p = wargmax_abs(best, bi, bv);
-            if (lane == 0) { flag[0] = p; flag[1] = bv > 0.0 ? 0 : 1; }
-        }
-        grp_sync(G);
-        const int p = flag[0];
-        if (flag[1]) { sg = 0.0; lg = -1.7976931348623157e308; return; }
-        if (p != c) {
-            if (G.gw == 0) {
-#pragma unroll 1
-                for (int j = lane; j < k; j += W2B_WARP) { const double t = A[c * lds + j]; A[c * lds + j] = A[p * lds + j]; A[p * lds + j] = t; }
-            }
-            sg = -sg;
-        }
-        if (G.gw == 0 && lane == 0) piv[c] = p;
-        grp_sync(G);
-        const double pv = A[c * lds + c];
-        lg += w_log(fabs(pv)); if (pv < 0) sg = -sg;
-        const double ipiv = 1.0 / pv;
-        if (Mdst) {                                                 // Gauss-Jordan step (same element arithmetic as invert_inplace)
-            if (G.gw == 0) {
-#pragma unroll 1
-                for (int j = lane; j < k; j += W2B_WARP) { rowv[j] = (j == c) ? ipiv : A[c * lds + j] * ipiv; colv[j] = A[j * lds + c]; }
-            }
-            grp_sync(G);
-#pragma unroll 1
-            for (int r = G.gw; r < k; r += G.gwarps) {
-                const double fct = colv[r];
-#pragma unroll 1
-                for (int j = lane; j < k; j += W2B_WARP)
-                    A[r * lds + j] = (r == c) ? rowv[j] : ((j == c) ? -fct * ipiv : A[r * lds + j] - fct * rowv[j]);
-            }
-        } else {                                                    // plain elimination below the pivot: determinant only
-#pragma unroll 1
-            for (int r = c + 1 + G.gw; r < k; r += G.gwarps) {
-                const double fct = A[r * lds + c] * ipiv;
-#pragma unroll 1
-                for (int j = c + 1 + lane; j < k; j += W2B_WARP) A[r * lds + j] -= fct * A[c * lds + j];
-            }
-        }
-        grp_sync(G);
-    }
-    if (!Mdst) return;
-#pragma unroll 1
-    for (int c = k - 1; c >= 0; --c) {                              // undo the row swaps as column swaps in reverse order: inv(P A) = inv(A) P^T
-        const int p = piv[c];
-        if (p != c) {
-            if (G.gw == 0) {
-#pragma unroll 1
-                for (int r = lane; r < k; r += W2B_WARP) { const double t = A[r * lds + c]; A[r * lds + c] = A[r * lds + p]; A[r * lds + p] = t; }
-            }
-            grp_sync(G);
-        }
-    }
-#pragma unroll 1
-    for (int r = G.gw; r < k; r += G.gwarps) {
-#pragma unroll 1
-        for (int j = lane; j < k; j += W2B_WARP) Mdst[(size_t)r * ldm + j] = A[r * lds + j];
-    }
-    grp_sync(G);
-}
-
 // ------------------------------------------------------------------ phase scheduler of one CTA (CTQMC.F90:8213-8258, 8428-8533)
 // Used for 1x1 quantum-number blocks (C1, C2, C5), where a move is short and a global move (LU of every flavour's matrix)
 // costs 100-1000 moves: one persistent kernel, no launch per round.  Blocked traces use the round kernels further down.
@@ -1571,7 +1599,6 @@ W2B_HDN void group_lu(const Tables& T, const LuGroup& G, const double* tc, const
 // Within a chain the sequence of moves and RNG draws is exactly the reference's.
 struct CtaShared {
     int nA, nR, nA2, nR2, nG, cA, cR, cA2, cR2, cG, cA2h, cR2h;
-    int nLU, nINV, cS;                     // staged global moves: chains waiting for the group LU / for the inverse (lists lA / lR), stage cursor
     int* left; unsigned char* parked; unsigned char* kind;
     short* lA; short* lR; short* lA2; short* lR2; short* lG;
     Prop* prop;
@@ -1621,7 +1648,7 @@ W2B_HDN void post_move_cta(const Tables& T, const Run& R, Ctx& x, CtaShared& S, 
 
 
 W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain_lo, int nloc, long long nsteps,
-                      CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf, Ctx& x, const LuGroup& LG) {
+                      CtaShared& S, double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf, Ctx& x) {
     const int W = cta_nwarps(), lane = lane_id();
 #pragma unroll 1
     for (int c = cta_tid(); c < nloc; c += cta_nthreads()) { S.left[c] = (int)nsteps; S.parked[c] = 0; }
@@ -1704,110 +1731,19 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
             rare = S.nG >= W || (S.nG > 0 && nrun < W);
         }
         if (rare) {
-            // ---- rare phase: global moves and tau shifts of all parked chains.  Tau shifts run whole on one warp.  Global moves run
-            // in stages, the dense linear algebra by warp GROUPS in shared memory (group_lu):
-            //   A (warp per chain)  update choice, relabelling, quantum numbers            -> list LU
-            //   B (group per chain) determinant of every flavour's new matrix              -> J.dn_log / dn_sign
-            //   C (warp per chain)  local trace, Metropolis, configuration hand-over       -> list INV (accepted)
-            //   D (group per chain) inverse matrices of the accepted configurations       -> M
-            //   E (warp per chain)  outer superstate, determinant, signs, counters
+            // ---- rare phase: global moves, tau shifts and outer pair moves of all parked chains, each whole on one warp.  (Round 2
+            // staged the dense linear algebra of large global moves through warp GROUPS eliminating in shared memory; the blocked
+            // tensor-pipe routine invert_blocked made one warp per matrix 1.5x faster for the whole sweep at C5 -- 190 -> 128 ms --
+            // because 32 matrices are in flight per SM instead of two, and the five stages and their barriers are gone.)
             const int ng = S.nG;
-            if (cta_tid() == 0) { S.nLU = 0; S.nINV = 0; S.cS = 0; }
             cta_sync();
 #pragma unroll 1
-            for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {                     // ---- A
+            for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {
                 const int c = S.lG[i], chain = chain_lo + c;
                 ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                bool staged = false;
-                int kmax = 0;
-#pragma unroll 1
-                for (int f = 0; f < T.nf; ++f) kmax = kmax > x.ih[IH_KF + f] ? kmax : x.ih[IH_KF + f];
-                // small matrices: 32 warps each eliminating their own are faster than groups taking turns (measured: C2, k ~ 12, +17 % sweep time staged)
-                if ((int)S.kind[c] == 3 && LG.cap > 0 && kmax >= LU_GROUP_MIN) {
-                    staged = step_glob_prepare(T, R, C, x, C.rjob[chain], false);
-                    if (staged && lane == 0) S.lA[wgrab_one(&S.nLU)] = (short)c;
-                } else if ((int)S.kind[c] >= 5) step_outer(T, R, C, A, x, S.prop[c], C.rjob[chain], (int)S.kind[c]);
+                if ((int)S.kind[c] >= 5) step_outer(T, R, C, A, x, S.prop[c], C.rjob[chain], (int)S.kind[c]);
                 else step_rare(T, R, C, x, C.rjob[chain], (int)S.kind[c]);
-                if (!staged) post_move_cta(T, R, x, S, c);
-                ctx_store(C, chain, x);
-                if (!staged && lane == 0) S.parked[c] = 0;
-            }
-            cta_sync();
-            const int nlu = S.nLU, ngroups = cta_nwarps() / LG.gwarps;
-#pragma unroll 1
-            for (int i = LG.gid; i < nlu; i += ngroups) {                               // ---- B
-                const int chain = chain_lo + S.lA[i];
-                RareJob& J = C.rjob[chain];
-                bool fits = true;
-#pragma unroll 1
-                for (int f = 0; f < T.nf; ++f) fits = fits && lu_need(J.knew[f]) <= LG.cap;
-                double lgt = 0.0, sgt = 1.0;
-                if (fits) {
-#pragma unroll 1
-                    for (int f = 0; f < T.nf; ++f) {
-                        const int k = J.knew[f];
-                        if (k == 0) continue;
-                        double l, sg_;
-                        group_lu(T, LG, C.sc_tc + ((size_t)chain * T.nf + f) * C.kcap, C.sc_ta + ((size_t)chain * T.nf + f) * C.kcap, k, f, nullptr, 0, l, sg_);
-                        lgt += l; sgt *= sg_;
-                    }
-                } else if (LG.gw == 0) {                                                // too large for the group buffer: one warp, global memory
-                    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                    rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, J.knew, false, lgt, sgt);
-                }
-                if (LG.gw == 0 && lane == 0) { J.dn_log = lgt; J.dn_sign = sgt; }
-                grp_sync(LG);
-            }
-            cta_sync();
-#pragma unroll 1
-            for (int i = wgrab(&S.cS); i < nlu; i = wgrab(&S.cS)) {                     // ---- C
-                const int c = S.lA[i], chain = chain_lo + c;
-                ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                RareJob& J = C.rjob[chain];
-                double tn_log, tn_sign;
-                trace_full_scalar(T, x.tau, x.sc_code, x.sc_sst, x.n, J.new_outer, tn_log, tn_sign);
-                const bool acc = step_glob_finish_a(T, R, C, x, J, tn_log, tn_sign);
-                if (acc) { if (lane == 0) { J.tn_log = tn_log; J.tn_sign = tn_sign; S.lR[wgrab_one(&S.nINV)] = (short)c; } }
-                else post_move_cta(T, R, x, S, c);
-                ctx_store(C, chain, x);
-                if (!acc && lane == 0) S.parked[c] = 0;
-            }
-            cta_sync();
-            if (cta_tid() == 0) S.cS = 0;
-            const int ninv = S.nINV;
-#pragma unroll 1
-            for (int i = LG.gid; i < ninv; i += ngroups) {                              // ---- D
-                const int chain = chain_lo + S.lR[i];
-                const int* ih = C.ih + (size_t)chain * IH_STRIDE;
-                bool fits = true;
-#pragma unroll 1
-                for (int f = 0; f < T.nf; ++f) fits = fits && lu_need(ih[IH_KF + f]) <= LG.cap;
-                if (fits) {
-#pragma unroll 1
-                    for (int f = 0; f < T.nf; ++f) {
-                        const int k = ih[IH_KF + f];
-                        if (k == 0) continue;
-                        double l, sg_;
-                        double* Md = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
-                        group_lu(T, LG, C.tau_c + ((size_t)chain * T.nf + f) * C.kcap, C.tau_a + ((size_t)chain * T.nf + f) * C.kcap, k, f, Md, C.ld, l, sg_);
-                    }
-                } else if (LG.gw == 0) {
-                    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                    double l2, s2;
-                    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
-                }
-                grp_sync(LG);
-            }
-            cta_sync();
-#pragma unroll 1
-            for (int i = wgrab(&S.cS); i < ninv; i = wgrab(&S.cS)) {                    // ---- E
-                const int c = S.lR[i], chain = chain_lo + c;
-                ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
-                if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                RareJob& J = C.rjob[chain];
-                step_glob_finish_b(T, R, C, x, J, J.tn_log, J.tn_sign);
                 post_move_cta(T, R, x, S, c);
                 ctx_store(C, chain, x);
                 if (lane == 0) S.parked[c] = 0;
