@@ -301,8 +301,13 @@ W2B_HDN int pairs_with(const Run& R, const Ctx& x, const double* opp, int k, dou
     for (int i = lane_id(); i < k; i += W2B_WARP) c += pairable(R, x, opp[i], t);
     return wsum(c);
 }
+// The annihilator times are sorted: only those within taudiff_max of the creator can pair, so the exact predicate is evaluated on
+// the candidates between two binary searches (bounds widened by a relative 1e-12: NPairs is integer state, the predicate decides).
+// With 65 windows (C5) the window moves every second attempt and every move recounts: the full k x k scan was 14 % of the sweep
+// kernel's instructions.
 W2B_HDN int count_pairs_full(const Tables& T, const Run& R, const Chains& C, const Ctx& x) {
     int c = 0;
+    const double slack = 1e-12 * T.beta;
 #pragma unroll 1
     for (int f = 0; f < T.nf; ++f) {
         int k = x.ih[IH_KF + f];
@@ -311,8 +316,12 @@ W2B_HDN int count_pairs_full(const Tables& T, const Run& R, const Chains& C, con
         for (int i = lane_id(); i < k; i += W2B_WARP) {
             double t = tc[i];
             if (t < x.wmin || t > x.wmax) continue;
+            const double lo_t = t - R.taudiff_max - slack, hi_t = t + R.taudiff_max + slack;
+            int lo = 0, hi = k;
 #pragma unroll 1
-            for (int a = 0; a < k; ++a) c += pairable(R, x, ta[a], t);
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ta[mid] < lo_t) lo = mid + 1; else hi = mid; }
+#pragma unroll 1
+            for (int a = lo; a < k; ++a) { const double v = ta[a]; if (v > hi_t) break; c += pairable(R, x, v, t); }
         }
     }
     return wsum(c);
@@ -640,27 +649,43 @@ W2B_HDN double det_ratio_add(const Tables& T, const Chains& C, Ctx& x, int f, do
     return S;
 }
 
-// get_MatAdd MatrixUpdate.F90:410-442, fused with the row/column shift, written into the spare buffer
+// get_MatAdd MatrixUpdate.F90:410-442, fused with the row/column shift, written into the spare buffer.
+// Two passes (profiles/r2q_*: the row-at-a-time form -- load a row, reduce, store it -- spent 70-80 % of its samples waiting for
+// one row's loads at a time): u = M Q for four rows per iteration (twelve loads in flight per lane), then the rank-1 update
+// streams two rows at a time with nothing but independent loads and stores.  Same operations per element as before.
 W2B_HDN void mat_add(const Chains& C, Ctx& x, int f, int nf, int p1, int p2, double S) {
     int k = x.ih[IH_KF + f];
     const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, nf);
     const int ld = C.ld; const double inv = 1.0 / S;
+    double* wU = x.wR;                                                 // R is spent once V = R^T M exists
 #pragma unroll 1
-    for (int in = 0; in <= k; ++in) {
-        if (in == p1) {
+    for (int i0 = 0; i0 < k; i0 += 4) {
+        const double* r0 = src + (size_t)i0 * ld;
+        const double* r1 = i0 + 1 < k ? r0 + ld : r0; const double* r2 = i0 + 2 < k ? r0 + 2 * (size_t)ld : r0; const double* r3 = i0 + 3 < k ? r0 + 3 * (size_t)ld : r0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll 1
-            for (int jn = lane_id(); jn <= k; jn += W2B_WARP)
-                dst[(size_t)in * ld + jn] = (jn == p2) ? inv : -x.wV[jn - (jn > p2)] * inv;
-        } else {
-            int i = in - (in > p1);
-            double part = 0.0;
+        for (int j = lane_id(); j < k; j += W2B_WARP) { const double q = x.wQ[j]; s0 += r0[j] * q; s1 += r1[j] * q; s2 += r2[j] * q; s3 += r3[j] * q; }
+        s0 = wsum(s0); s1 = wsum(s1); s2 = wsum(s2); s3 = wsum(s3);
+        if (lane_id() == 0) { wU[i0] = s0; if (i0 + 1 < k) wU[i0 + 1] = s1; if (i0 + 2 < k) wU[i0 + 2] = s2; if (i0 + 3 < k) wU[i0 + 3] = s3; }
+    }
+    wsync();
 #pragma unroll 1
-            for (int j = lane_id(); j < k; j += W2B_WARP) part += src[(size_t)i * ld + j] * x.wQ[j];
-            double u = wsum(part);
+    for (int jn = lane_id(); jn <= k; jn += W2B_WARP)
+        dst[(size_t)p1 * ld + jn] = (jn == p2) ? inv : -x.wV[jn - (jn > p2)] * inv;
 #pragma unroll 1
-            for (int jn = lane_id(); jn <= k; jn += W2B_WARP) {
-                if (jn == p2) dst[(size_t)in * ld + jn] = -u * inv;
-                else { int j = jn - (jn > p2); dst[(size_t)in * ld + jn] = src[(size_t)i * ld + j] + u * x.wV[j] * inv; }
+    for (int i = 0; i < k; i += 2) {
+        const bool two = i + 1 < k;
+        const double* ra = src + (size_t)i * ld; const double* rb = two ? ra + ld : ra;
+        double* da = dst + (size_t)(i + (i >= p1)) * ld; double* db = dst + (size_t)(i + 1 + (i + 1 >= p1)) * ld;
+        const double ua = wU[i], ub = two ? wU[i + 1] : 0.0;
+#pragma unroll 1
+        for (int jn = lane_id(); jn <= k; jn += W2B_WARP) {
+            if (jn == p2) { da[jn] = -ua * inv; if (two) db[jn] = -ub * inv; }
+            else {
+                const int j = jn - (jn > p2);
+                const double v = x.wV[j], a = ra[j], b = rb[j];
+                da[jn] = a + ua * v * inv;
+                if (two) db[jn] = b + ub * v * inv;
             }
         }
     }
@@ -669,7 +694,7 @@ W2B_HDN void mat_add(const Chains& C, Ctx& x, int f, int nf, int p1, int p2, dou
     wsync();
 }
 
-// get_MatRem MatrixUpdate.F90:455-482
+// get_MatRem MatrixUpdate.F90:455-482 (two rows per iteration: independent loads in flight)
 W2B_HDN void mat_rem(const Chains& C, Ctx& x, int f, int nf, int p1, int p2) {
     int k = x.ih[IH_KF + f];
     const double* src = Mbuf(C, x, f); double* dst = Mbuf(C, x, nf);
@@ -679,13 +704,18 @@ W2B_HDN void mat_rem(const Chains& C, Ctx& x, int f, int nf, int p1, int p2) {
     wsync();
     const double ipiv = 1.0 / src[(size_t)p1 * ld + p2];
 #pragma unroll 1
-    for (int i = 0; i < k - 1; ++i) {
-        int io = i + (i >= p1);
-        double c = x.wQ[io];
+    for (int i = 0; i < k - 1; i += 2) {
+        const bool two = i + 1 < k - 1;
+        const int ia = i + (i >= p1), ib = i + 1 + (i + 1 >= p1);
+        const double ca = x.wQ[ia], cb = two ? x.wQ[ib] : 0.0;
+        const double* ra = src + (size_t)ia * ld; const double* rb = two ? src + (size_t)ib * ld : ra;
+        double* da = dst + (size_t)i * ld; double* db = da + ld;
 #pragma unroll 1
         for (int j = lane_id(); j < k - 1; j += W2B_WARP) {
-            int jo = j + (j >= p2);
-            dst[(size_t)i * ld + j] = src[(size_t)io * ld + jo] - c * x.wV[jo] * ipiv;
+            const int jo = j + (j >= p2);
+            const double v = x.wV[jo], a = ra[jo], b = rb[jo];
+            da[j] = a - ca * v * ipiv;
+            if (two) db[j] = b - cb * v * ipiv;
         }
     }
     wsync();
@@ -876,11 +906,16 @@ W2B_HDN bool rem_propose(const Tables& T, const Run& R, const Chains& C, Ctx& x,
             int cd = x.code[i]; fi = cd >> 1; ty = cd & 1; ti = x.tau[i];
             int k = x.ih[IH_KF + fi];
             const double* opp = (ty == 0 ? x.ta : x.tc) + (size_t)fi * C.kcap;
+            {                                                     // lb = number of opposite-type times <= ti (sorted): binary search
+                int lo = 0, hi = k;
 #pragma unroll 1
-            for (int a = 0; a < k; ++a) {
-                double v = opp[a];
-                if (v <= ti) ++lb;
-                else if (v <= x.wmax && !(v > ti + R.taudiff_max)) ++c;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (opp[mid] <= ti) lo = mid + 1; else hi = mid; }
+                lb = lo;
+            }
+#pragma unroll 1
+            for (int a = lb; a < k; ++a) {
+                const double v = opp[a];
+                if (v <= x.wmax && !(v > ti + R.taudiff_max)) ++c;
                 else break;
             }
         }
@@ -1728,7 +1763,7 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                 }
             }
             cta_sync();
-            rare = S.nG >= W || (S.nG > 0 && nrun < W);
+            rare = S.nG >= 2 * W || (S.nG > 0 && nrun < W);          // two warp-loads: the cheap tau shifts fill the tail behind the global moves
         }
         if (rare) {
             // ---- rare phase: global moves, tau shifts and outer pair moves of all parked chains, each whole on one warp.  (Round 2
@@ -1737,9 +1772,12 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
             // because 32 matrices are in flight per SM instead of two, and the five stages and their barriers are gone.)
             const int ng = S.nG;
             cta_sync();
+            // longest first: global moves (two determinants + two inverses), then everything else; tickets [0, ng) = first pass, [ng, 2 ng) = second
 #pragma unroll 1
-            for (int i = wgrab(&S.cG); i < ng; i = wgrab(&S.cG)) {
+            for (int t = wgrab(&S.cG); t < 2 * ng; t = wgrab(&S.cG)) {
+                const int i = t < ng ? t : t - ng;
                 const int c = S.lG[i], chain = chain_lo + c;
+                if (((int)S.kind[c] == 3) != (t < ng)) continue;
                 ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
                 if ((int)S.kind[c] >= 5) step_outer(T, R, C, A, x, S.prop[c], C.rjob[chain], (int)S.kind[c]);
@@ -2140,28 +2178,47 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
                 for (int q = 0; q < LEG_CHUNK_BIG; ++q) part[q] = 0.0;
                 int ic = 0, ia = lane;                                  // pair p = ic * k + ia, advanced without divisions
                 while (ia >= k) { ia -= k; ++ic; }
+                // TWO pairs per lane and iteration (p and p + 32): the recurrence is one dependent DMUL -> DFMA chain per pair and the
+                // kernel runs 2 warps per scheduler (238 registers), so a second independent chain per lane doubles what the FP64
+                // pipe has in flight
 #pragma unroll 1
-                for (int p = lane; p < k * k; p += W2B_WARP) {
-                    double Mv = M[(size_t)ic * C.ld + ia];
-                    const double dtau = ta[ia] - tc[ic]; double xx; int idt;
-                    if (dtau > 0.0) { idt = (int)(dtau / beta * (double)R.ntau) + 1; xx = 2.0 / beta * dtau - 1.0; }
-                    else { idt = (int)((beta + dtau) / beta * (double)R.ntau) + 1; xx = 2.0 / beta * (beta + dtau) - 1.0; Mv = -Mv; }
-                    Mv *= cfgsign;
-                    if (lbase == 0) { if (idt > R.ntau) idt = R.ntau; atomic_add(&acc[A.o_gtau + f * R.ntau + idt - 1], Mv); }
-                    double qm1 = 1.0, q0 = xx;                          // Q_0, Q_1
+                for (int p = lane; p < k * k; p += 2 * W2B_WARP) {
+                    double MvA = M[(size_t)ic * C.ld + ia], xxA, MvB = 0.0, xxB = 0.0;
+                    {
+                        const double dtau = ta[ia] - tc[ic]; int idt;
+                        if (dtau > 0.0) { idt = (int)(dtau / beta * (double)R.ntau) + 1; xxA = 2.0 / beta * dtau - 1.0; }
+                        else { idt = (int)((beta + dtau) / beta * (double)R.ntau) + 1; xxA = 2.0 / beta * (beta + dtau) - 1.0; MvA = -MvA; }
+                        MvA *= cfgsign;
+                        if (lbase == 0) { if (idt > R.ntau) idt = R.ntau; atomic_add(&acc[A.o_gtau + f * R.ntau + idt - 1], MvA); }
+                    }
+                    ia += W2B_WARP; while (ia >= k) { ia -= k; ++ic; }
+                    if (p + W2B_WARP < k * k) {
+                        MvB = M[(size_t)ic * C.ld + ia];
+                        const double dtau = ta[ia] - tc[ic]; int idt;
+                        if (dtau > 0.0) { idt = (int)(dtau / beta * (double)R.ntau) + 1; xxB = 2.0 / beta * dtau - 1.0; }
+                        else { idt = (int)((beta + dtau) / beta * (double)R.ntau) + 1; xxB = 2.0 / beta * (beta + dtau) - 1.0; MvB = -MvB; }
+                        MvB *= cfgsign;
+                        if (lbase == 0) { if (idt > R.ntau) idt = R.ntau; atomic_add(&acc[A.o_gtau + f * R.ntau + idt - 1], MvB); }
+                    }
+                    double qm1A = 1.0, q0A = xxA, qm1B = 1.0, q0B = xxB;   // Q_0, Q_1
                     int l0 = 2;
-                    if (lbase == 0) { part[0] += Mv; part[1] += Mv * xx; }
+                    if (lbase == 0) { part[0] += MvA + MvB; part[1] += MvA * xxA + MvB * xxB; }
                     else {
 #pragma unroll 4
-                        for (int l = 2; l < lbase; ++l) { const double qn = fma(xx, q0, -ldg(&gam[l]) * qm1); qm1 = q0; q0 = qn; }
+                        for (int l = 2; l < lbase; ++l) {
+                            const double gl = -ldg(&gam[l]);
+                            const double qnA = fma(xxA, q0A, gl * qm1A), qnB = fma(xxB, q0B, gl * qm1B);
+                            qm1A = q0A; q0A = qnA; qm1B = q0B; q0B = qnB;
+                        }
                         l0 = 0;
                     }
 #pragma unroll
                     for (int q = 0; q < LEG_CHUNK_BIG; ++q) {
                         if (q >= l0 && lbase + q < R.nlegmax) {
-                            const double qn = fma(xx, q0, -ldg(&gam[lbase + q]) * qm1);
-                            part[q] += Mv * qn;
-                            qm1 = q0; q0 = qn;
+                            const double gl = -ldg(&gam[lbase + q]);
+                            const double qnA = fma(xxA, q0A, gl * qm1A), qnB = fma(xxB, q0B, gl * qm1B);
+                            part[q] = fma(MvB, qnB, fma(MvA, qnA, part[q]));
+                            qm1A = q0A; q0A = qnA; qm1B = q0B; q0B = qnB;
                         }
                     }
                     ia += W2B_WARP; while (ia >= k) { ia -= k; ++ic; }
