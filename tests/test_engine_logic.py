@@ -195,6 +195,23 @@ def test_round_scheduler_on_scalar_blocks(built, cfg, nsteps, chain):
     eng.dest_ctqmc()
 
 
+@pytest.mark.parametrize("cfg,nsteps,chain,pouter", [("C5", 5000, 1, 0.0), ("C2", 8000, 3, 0.0), ("C1", 6000, 0, 0.2)])
+def test_autonomous_scheduler(built, cfg, nsteps, chain, pouter):
+    """Scheduler 3 (large orders with 1x1 blocks: one warp takes a chain through all its moves, no CTA phases; engine_core.hpp
+    `chain_sweep`): the same per-chain move sequence, so the same replay parity against the oracle, outer pair moves included."""
+    p = problems.make_problem(cfg, nftau=2001, PercentageOuterMove=pouter)
+    eng = _hostemu.make()
+    eng.set_option("nchains", 4); eng.set_option("nbins", 2); eng.set_option("scheduler", 3)
+    eng.init_rnd(43890); eng.init_paras(p.pstring()); eng.init_solver(p.u_matrix, p.ftau, p.muimp, None, 1)
+    eng.set_taudiffmax(p.qmc["TaudiffMax"]); eng.init_counters()
+    log = eng.debug_steps(chain, nsteps)
+    orc = OracleChain(p, rng="philox", seed=43890, chain=chain)
+    orc.init_counters()
+    assert_replay(log, orc.steps(nsteps, log=True))
+    assert eng.scalar("error_flags") == 0
+    eng.dest_ctqmc()
+
+
 def test_capacity_overflow_is_loud(built):
     """A chain that outgrows its operator capacity raises a flag (never silent truncation); the warm-up that hit the limit fails
     right away (not after the whole run) and ctqmc_measure refuses to hand out results -- the counterpart of the reference's hard

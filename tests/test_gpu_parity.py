@@ -55,6 +55,25 @@ def test_replay_parity(cuda_engine_factory, cfg, nsteps, chain):
     eng.dest_ctqmc()
 
 
+@pytest.mark.parametrize("cfg,nsteps,chain", [("C5", 12000, 9), ("C2", 20000, 21)])
+def test_replay_parity_autonomous_scheduler(cuda_engine_factory, cfg, nsteps, chain):
+    """Scheduler 3 (one warp takes a chain through all its moves; the default at large orders): same replay parity, and the same
+    from-scratch checks of the inverse matrices afterwards (the blocked tensor-pipe Gauss-Jordan serves its global moves)."""
+    p = problems.make_problem(cfg)
+    eng = cuda_engine_factory(p, nchains=64, nbins=4, scheduler=3)
+    log, orc = replay(eng, p, chain, nsteps)
+    assert set(np.unique(log[:, 0])) == {1.0, 2.0, 3.0, 4.0}
+    s, o = eng.debug_chain_scalars(chain), orc.scalars()
+    assert s["error"] == 0 and orc.error == 0
+    assert abs(s["trace_log"] - o["trace_log"]) < 1e-8 and abs(s["det_log"] - o["det_log"]) < 1e-8
+    assert (s["trace_sign"], s["det_sign"], s["cfgsign"]) == (o["trace_sign"], o["det_sign"], o["cfgsign"])
+    for f in range(2 * p.nbands):
+        a, b, c = eng.debug_minv(chain, f // 2 + 1, f % 2 + 1), orc.minv(f), orc.minv(f, scratch=True)
+        assert a.shape == b.shape and np.abs(a - b).max() < 1e-9 * max(1.0, np.abs(b).max()) and np.abs(a - c).max() < 1e-7 * max(1.0, np.abs(c).max())
+    assert eng.scalar("error_flags") == 0
+    eng.dest_ctqmc()
+
+
 def test_measurement_parity(cuda_engine_factory):
     p = problems.make_problem("C2", Ntau=200, NLegMax=40)
     eng = cuda_engine_factory(p, nchains=1, nbins=1)

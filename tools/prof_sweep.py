@@ -12,7 +12,7 @@ nwarm = int(sys.argv[3]) if len(sys.argv) > 3 else 3000
 p = problems.make_problem(cfg)
 eng = MCTQMC()
 eng.set_option("nchains", nc); eng.set_option("nbins", 32)
-for k in ("cta_warps", "batch_chains", "propose_run", "prefetch", "lu_groups"):
+for k in ("cta_warps", "batch_chains", "propose_run", "prefetch", "lu_groups", "scheduler"):
     if os.environ.get("W2B_" + k.upper()):
         eng.set_option(k, int(os.environ["W2B_" + k.upper()]))
 eng.init_rnd(43890); eng.init_paras(p.pstring())

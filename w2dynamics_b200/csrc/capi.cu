@@ -757,6 +757,9 @@ int w2b_get_scalar(const char* name, double* out) {
                 for (int i = 0; i < C_NCNT; ++i) if (k.substr(4) == names[i]) { *out = (double)cnt[i]; return; }
             }
             if (k == "mean_order") { *out = E.mean_order(); return; }
+            if (k.rfind("tick", 0) == 0 && k.size() == 5) {             // W2B_TIMING builds: clock cycles per move category of the autonomous sweep (diagnostics)
+                unsigned long long v[8] = {0}; E.sync(); d2h((int*)v, E.C.sched + SC_STRIDE, 16); *out = (double)v[k[4] - '0']; return;
+            }
             if (k == "max_k" || k == "max_ops" || k == "error_flags") { int mk, mo; int e = E.error_flags(&mk, &mo); *out = k == "max_k" ? mk : k == "max_ops" ? mo : e; return; }
         }
         if (S.have_res) { auto it = S.res.scal.find(k); if (it != S.res.scal.end()) { *out = it->second; return; } }

@@ -153,6 +153,23 @@ __global__ void __launch_bounds__(256) k_sweep_begin(Chains C, long long nsteps)
     if (c < C.nchains) { C.left[c] = (int)nsteps; C.parked[c] = 0; }
     if (c < 2 * SC_STRIDE) C.sched[c] = 0;
 }
+// ---- autonomous sweep kernel (1x1 blocks, large orders): warps take chains from one ticket counter and run them start to finish
+constexpr int AUTO_WARPS = 8;
+#ifndef W2B_AUTO_OCC
+#define W2B_AUTO_OCC 4
+#endif
+__global__ void __launch_bounds__(AUTO_WARPS * 32, W2B_AUTO_OCC) k_sweep_auto(Tables T_, Run R_, Chains C_, Accum A_, long long nsteps, int wdoubles, int log_chain, double* logbuf) {
+    extern __shared__ double smem[];
+    __shared__ Ctx ctxs[AUTO_WARPS]; __shared__ Prop props[AUTO_WARPS];
+    __shared__ Tables T; __shared__ Run R; __shared__ Chains C; __shared__ Accum A;
+    if (threadIdx.x == 0) { T = T_; R = R_; C = C_; A = A_; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    double* ws = smem + (size_t)warp * wdoubles;
+    int* is = (int*)(ws + 3 * C.kcap);
+    for (int chain = wgrab(&C.sched[SC_TICKET]); chain < C.nchains; chain = wgrab(&C.sched[SC_TICKET]))
+        chain_sweep(T, R, C, A, chain, nsteps, props[warp], ws, is, ws + 3 * C.kcap, log_chain, logbuf, ctxs[warp]);
+}
 // propose phase of one round: one warp per chain; the CTA's results reach the round's queues with one atomic per queue
 // (the parameter structs are copied to shared memory once per CTA: passing kernel parameters by reference to out-of-line
 // functions would otherwise spill a private copy per thread to local memory)
@@ -614,6 +631,35 @@ public:
         ct_ready = true;
     }
 
+    // autonomous form (scheduler 3; automatic for 1x1 blocks when the capacity says the orders are large): one warp per chain, no phases
+    int au_grid = 1; size_t au_smem = 0; bool au_ready = false;
+    void sweep_auto(long long nsteps, int log_chain, double* log_host) {
+        double* dlog = nullptr;
+        if (log_chain >= 0) dlog = dev_alloc<double>((size_t)nsteps * LOGW);
+#if W2B_DEVICE
+        if (!au_ready) {
+            int dev = 0, nsm = 1;
+            W2B_CUDA_CHECK(cudaGetDevice(&dev));
+            W2B_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+            au_smem = (size_t)AUTO_WARPS * wdoubles_sweep * sizeof(double);
+            W2B_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_auto, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)au_smem));
+            int occ = 1;
+            W2B_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_auto, AUTO_WARPS * 32, au_smem));
+            occ = std::min(occ, W2B_AUTO_OCC);
+            au_grid = std::max(1, std::min(nsm * std::max(1, occ), (C.nchains + AUTO_WARPS - 1) / AUTO_WARPS));
+            au_ready = true;
+        }
+        k_sweep_begin<<<(std::max(C.nchains, 2 * SC_STRIDE) + 255) / 256, 256>>>(C, nsteps); ++launches;        // zeroes the ticket counter
+        k_sweep_auto<<<au_grid, AUTO_WARPS * 32, au_smem>>>(T, R, C, A, nsteps, wdoubles_sweep, log_chain, dlog); ++launches;
+        W2B_CUDA_CHECK(cudaGetLastError());
+#else
+        std::vector<double> ws(wdoubles + 8);
+        for (int c = 0; c < C.nchains; ++c) { Ctx x; Prop P;
+            chain_sweep(T, R, C, A, c, nsteps, P, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap, log_chain, dlog, x); }
+#endif
+        if (log_chain >= 0) { sync(); d2h(log_host, dlog, (size_t)nsteps * LOGW); dev_free(dlog); }
+    }
+
     // advance every chain by nsteps moves; optionally record the replay log of one chain
     void sweep_cta(long long nsteps, int log_chain, double* log_host) {
         if (!ct_ready) plan_cta();
@@ -663,7 +709,7 @@ public:
 #else
         if (h_sched) { std::free(h_sched); h_sched = nullptr; }
 #endif
-        sw_ready = false; ct_ready = false; smem_cfg_measure = smem_cfg_rebuild = 0;      // the opt-in is per device: redo after a device change
+        sw_ready = false; ct_ready = false; au_ready = false; smem_cfg_measure = smem_cfg_rebuild = 0;      // the opt-in is per device: redo after a device change
     }
     void plan_sweep() {
 #if W2B_DEVICE
@@ -704,6 +750,7 @@ public:
     // advance every chain by nsteps moves; optionally record the replay log of one chain
     void sweep(long long nsteps, int log_chain = -1, double* log_host = nullptr) {
         if (nsteps <= 0) return;
+        if (C.dmax == 1 && opt.scheduler == 3) { sweep_auto(nsteps, log_chain, log_host); return; }
         if (C.dmax == 1 && opt.scheduler != 2) { sweep_cta(nsteps, log_chain, log_host); return; }
         if (!sw_ready) plan_sweep();
         double* dlog = nullptr;

@@ -613,6 +613,24 @@ W2B_HDN int walk_check(const Tables& T, const Ctx& x, int i0, int mcount, int f,
     return cur;
 }
 
+// Every line of the k x k matrix a requested from HBM into L2 at once.  The rank-1 routines below walk the matrix in dependent
+// steps of a few loads (a warp has ~4 loads in flight, one memory round trip per step: 50-100 round trips per 74 x 74 matrix);
+// with the lines already on their way the same loops run at L2 latency.  Used where the matrix is about to be read whole.
+W2B_HD void prefetch_matrix(const double* a, int k, int ld) {
+#if W2B_DEVICE
+    if (k < 16) return;
+    const int nl = (k * 8 + 127) / 128 + 1;
+#pragma unroll 1
+    for (int c = 0; c < nl; ++c) {
+#pragma unroll 1
+        for (int r = lane_id(); r < k; r += W2B_WARP) {
+            const char* q = (const char*)(a + (size_t)r * ld) + c * 128;
+            if (q < (const char*)(a + (size_t)r * ld + k)) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+    }
+#endif
+}
+
 // ------------------------------------------------------------------ determinant ratio + rank-1 updates
 // S - R^T M Q (MatrixUpdate.F90:392-407); leaves Q, R, V = R^T M in the warp scratch for the update
 W2B_HDN double det_ratio_add(const Tables& T, const Chains& C, Ctx& x, int f, double tau_c, double tau_a) {
@@ -823,6 +841,7 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     const int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     double dlog = P.dlog, dsign = P.dsign;
+    prefetch_matrix(Mbuf(C, x, f), k, C.ld);
     const double S = det_ratio_add(T, C, x, f, tau_c, tau_a);
     bump_bytes(x, 8ll * k * k);
     double tn_log = 0.0, tn_sign = 1.0;
@@ -986,6 +1005,7 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     const int k = x.ih[IH_KF + f];
     const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
     double dlog = P.dlog, dsign = P.dsign, tn_log = 0.0, tn_sign = 1.0;
+    prefetch_matrix(Mbuf(C, x, f), k, C.ld);                            // read whole if the removal is accepted (1 in 5 at C5; HBM has the headroom)
     if (blocked) {
         parts_sum(x.mpt, ldg(&T.dim[OUTER ? begin_sst : x.outer]), tn_log, tn_sign);
         if (!OUTER) { if (x.kv < i1) x.kv = i1; if (x.bv > i2 + 1) x.bv = i2 + 1; }
@@ -1144,6 +1164,9 @@ W2B_HDN void invert_inplace(double* a, int k, int ld, int* wI, double* colv, dou
 // exponent split off (one logarithm per matrix instead of one per pivot).
 constexpr int LU_BLOCKED_MIN = 24;     // orders from which rebuild_inverses uses the blocked routine
 W2B_HDN void invert_blocked(double* a, int k, int ld, int* wI, bool want_inverse, double& lg, double& sg) {
+    // (Measured and rejected: the panel held in registers, lane l owning rows l, l + 32, l + 64, with the A fragments shuffled out of
+    //  them -- no memory traffic inside the panel, yet 60 % slower per global move: the selects and shuffles that stand in for
+    //  dynamic register indexing cost more than the L1 hits they replace.)
     const int lane = lane_id();
     double prod = 1.0; int esum = 0;
     sg = 1.0;
@@ -1808,6 +1831,41 @@ W2B_HDN void post_move(const Tables& T, const Run& R, const Chains& C, Ctx& x, i
     }
     if (lane_id() == 0) { if (x.log) x.log[16] = x.wpos; x.cnt[C_STEPS] += 1ull; C.left[chain] -= 1; }
     wsync();
+}
+
+// ------------------------------------------------------------------ autonomous sweep (1x1 blocks, large orders)
+// One warp takes one chain through ALL its moves: context bound once, no CTA phases, no barriers.  The phase scheduler above exists
+// because short moves are bound by instruction delivery (every warp at its own place in 10 k instructions of code); at large
+// expansion orders (C5, k = 74) a move is a handful of long loops over a 44 kB matrix, the code between them matters little, and
+// what the phases cost -- every chain's records re-read per phase, the whole CTA waiting at three barriers per round behind its
+// longest item, global moves (5 ms on one warp) served in CTA-wide rare phases -- is most of the step (profiles/r2q_*: 40 % of the
+// warp samples at the CTA barrier, and the sweep time did not move when 14 % of its instructions were removed).
+W2B_HD void chain_sweep(const Tables& T, const Run& R, const Chains& C, const Accum& A, int chain, long long nsteps, Prop& P,
+                        double* wscratch, int* iscratch, double* mscratch, int log_chain, double* logbuf, Ctx& x) {
+    const double thr_add = (1.0 - R.pshift - R.pglob) / 2.0, thr_rem = 1.0 - R.pshift - R.pglob, thr_glob = 1.0 - R.pshift;
+    ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
+#if defined(W2B_TIMING) && W2B_DEVICE
+#define W2B_TICK(slot) { const long long t1_ = clock64(); if (lane_id() == 0) atomicAdd((unsigned long long*)&C.sched[16 + 2 * (slot)], (unsigned long long)(t1_ - t0_)); t0_ = t1_; }
+    long long t0_ = clock64();
+#else
+#define W2B_TICK(slot)
+#endif
+#pragma unroll 1
+    for (long long s = 0; s < nsteps; ++s) {
+        if (chain == log_chain) x.log = logbuf + (size_t)s * LOGW;
+        const double r = x.rng.next();                                // move type: reference thresholds CTQMC.F90:8437-8488
+        if (!(r <= thr_rem)) { const int kind = r <= thr_glob ? 3 : 4; step_rare(T, R, C, x, C.rjob[chain], kind); W2B_TICK(kind == 3 ? 4 : 5) }
+        else {
+            bool outer = false;
+            if (R.pouter > 0.0) { x.rng.skip(1); outer = x.rng.next() < R.pouter; } else x.rng.skip(2);
+            if (outer) step_outer(T, R, C, A, x, P, C.rjob[chain], r < thr_add ? 5 : 6);
+            else if (r < thr_add) { const bool go = add_propose<false>(T, R, C, x, P); W2B_TICK(0) if (go) { add_decide<false>(T, R, C, A, x, P); W2B_TICK(1) } }
+            else { const bool go = rem_propose<false>(T, R, C, x, P); W2B_TICK(2) if (go) { rem_decide<false>(T, R, C, A, x, P); W2B_TICK(3) } }
+        }
+        post_move(T, R, C, x, chain);
+        W2B_TICK(6)
+    }
+    ctx_store(C, chain, x);
 }
 
 // ------------------------------------------------------------------ round scheduler (CTQMC.F90:8213-8258, 8428-8533)
