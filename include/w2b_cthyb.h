@@ -82,7 +82,7 @@ int w2b_allreduce_accum(void);
 
 /* ---- engine controls without a reference counterpart ---- */
 /* keys: nchains nbins kcap ops_cap chain_base device nmeas_override propose_run scheduler (1x1 blocks: 0/1 = persistent CTA
- * scheduler kernel, 2 = round kernels) reuse_population (1: dest_ctqmc parks the chain population and the static tables; the next
+ * scheduler kernel, 2 = round kernels, 3 = autonomous kernel: one warp takes a chain through all its moves) reuse_population (1: dest_ctqmc parks the chain population and the static tables; the next
  * init_solver of a bit-identical local problem revives them, uploads the new F(tau) and rebuilds every chain's inverse matrices /
  * trace / signs on the device -- ReuseMCConfig (cthyb_solver.py:328-345) for the whole population) ; must be set before w2b_init_solver.  time_kernels (0/1: CUDA events around the round
  * kernels, read back through w2b_get_scalar ms_propose / ms_trace / ms_decide) may be switched at any time. */
@@ -110,7 +110,7 @@ void w2b_pinned_free(void* p);
 
 /* ---- replay / parity hooks ---- */
 /* advance all chains by nsteps moves and record chain `chain`'s per-move records (20 doubles each):
- * [0] move 1=add 2=rem 3=glob 4=shift  [1] status 0=rejected 1=accepted 2=early exit  [2],[3] tau1,tau2
+ * [0] move 1=add 2=rem 3=glob 4=shift 5=outer add 6=outer rem  [1] status 0=rejected 1=accepted 2=early exit  [2],[3] tau1,tau2
  * [4] flavour  [5],[6] FPos(c^dag),FPos(c)  [7],[8] log|det ratio|, sign  [9],[10] log|trace ratio|, sign
  * [11] acceptance probability  [12] #operators after  [13] outer superstate after  [14] NPairs used
  * [15] configuration sign after  [16] window position after  [17] accept random number */

@@ -64,6 +64,22 @@ CASES = {
 def test_statistical_agreement_with_cpu_population(cuda_engine_factory, cfg):
     gch, gwarm, gmeas, cch, cwarm, cmeas, fast = CASES[cfg]
     p = problems.make_problem(cfg, Nmeas=gmeas, Ntau=500, NLegMax=40)
+    _compare(cuda_engine_factory, cfg, p, p, CASES[cfg])
+
+
+@pytest.mark.parametrize("cfg,beta", [("C3", 3.0), ("C2", 4.0)])
+def test_outer_moves_leave_the_distribution_invariant(cuda_engine_factory, cfg, beta):
+    """Outer pair moves (PercentageOuterMove) only add a way to move through configuration space: the GPU population
+    sampled WITH 30 % outer moves must agree with a CPU oracle population sampled WITHOUT them, inside the same error bars (high
+    temperature, where a tenth of these moves is accepted)."""
+    case = (2048, 6000, 100, 32, 8000, 3000, 0)
+    p_gpu = problems.make_problem(cfg, beta=beta, Nmeas=case[2], Ntau=500, NLegMax=40, PercentageOuterMove=0.3)
+    p_cpu = problems.make_problem(cfg, beta=beta, Nmeas=case[2], Ntau=500, NLegMax=40)
+    _compare(cuda_engine_factory, "%s beta=%g with outer moves" % (cfg, beta), p_gpu, p_cpu, case)
+
+
+def _compare(cuda_engine_factory, cfg, p, p_cpu, case):
+    gch, gwarm, gmeas, cch, cwarm, cmeas, fast = case
     eng = cuda_engine_factory(p, nchains=gch, nbins=32)
     eng.ctqmc_warmup(gwarm)
     eng.ctqmc_measure(1, 1)
@@ -78,7 +94,7 @@ def test_statistical_agreement_with_cpu_population(cuda_engine_factory, cfg):
     sign_gerr = sb.std(ddof=1) / np.sqrt(sb.size)
     eng.dest_ctqmc()
     # ---- CPU: independent oracle chains, one sample each (DistributedSample semantics)
-    res = oracle_population(p, cch, cwarm, cmeas, fast)
+    res = oracle_population(p_cpu, cch, cwarm, cmeas, fast)
     g_cpu, g_cerr = stats([coarse(r["gtau"]) for r in res])
     occ_cpu, occ_cerr = stats([r["occ"] for r in res])
     k_cpu, k_cerr = stats([order(r["hist"]) for r in res])
