@@ -92,6 +92,7 @@ struct Counters {
     double TryAdd = 0, TryRem = 0, TryGlob = 0, TryShift = 0;
     double AccAdd = 0, AccRem = 0, AccGlob = 0, AccShift = 0;
     double AccQNAdd = 0, AccQNRem = 0, AccQNGlob = 0;
+    double TryAdd4 = 0, AccAdd4 = 0, TryRem4 = 0, AccRem4 = 0;
 };
 
 const int LOGW = 20;   // doubles per replay-log record
@@ -798,6 +799,132 @@ struct Chain {
         } else log_end(0);
     }
 
+    // ---------------------------------------------------------- 4-operator moves (diagonal hybridisation): CTQMC.F90:3615-3889, 4153-4430
+    // Two pairs are inserted / removed at once (Percentage4OperatorMove); the determinant of the proposed configuration is
+    // rebuilt from scratch (get_InvFullHybr, CTQMC.F90:3816-3817) and the proposal ratio sums over the orders in which the
+    // inverse move could take the four operators out (rempair_factor).
+    bool is_rempair(const Op& a, const Op& b) const {            // is_rempair_diag Trace.F90:2005-2030
+        return a.b == b.b && a.s == b.s && a.ca != b.ca && a.tau >= tauwin_min && a.tau <= tauwin_max && b.tau >= tauwin_min && b.tau <= tauwin_max
+               && std::fabs(a.tau - b.tau) <= taudiff_max;
+    }
+    static std::vector<Op> merged(const std::vector<Op>& base, const std::vector<Op>& add) {
+        std::vector<Op> r = base; r.insert(r.end(), add.begin(), add.end());
+        std::stable_sort(r.begin(), r.end(), [](const Op& x, const Op& y) { return x.tau < y.tau; });
+        return r;
+    }
+    static std::vector<Op> without(const std::vector<Op>& base, const std::vector<Op>& drop) {
+        std::vector<Op> r;
+        for (const Op& e : base) { bool d = false; for (const Op& x : drop) if (x.tau == e.tau && x.b == e.b && x.s == e.s && x.ca == e.ca) d = true; if (!d) r.push_back(e); }
+        return r;
+    }
+    // gen_OperRemove's pair #NPair in the reference's enumeration order (Trace.F90:4886-4914)
+    bool pick_pair(const std::vector<Op>& o, int NPair, size_t& i1, size_t& i2) const {
+        for (size_t i = 0; i < o.size(); ++i) {
+            if (o[i].tau < tauwin_min) continue;
+            for (size_t j = i + 1; j < o.size(); ++j) {
+                if (o[j].b != o[i].b || o[j].s != o[i].s) continue;
+                if (o[j].tau > tauwin_max) break;
+                if (o[j].tau > o[i].tau + taudiff_max) break;
+                if (o[j].ca != o[i].ca) { if (--NPair <= 0) { i1 = i; i2 = j; return true; } }
+            }
+        }
+        return false;
+    }
+    double remfactor(int NPairs, const Op& a, const Op& b) const {   // hybpairremfactor Trace.F90:4939-4948 (around the annihilator)
+        double tau_an = (a.ca == 2) ? a.tau : b.tau;
+        return (double)NPairs / ((tauwin_max - tauwin_min) * (std::min(tau_an + taudiff_max, tauwin_max) - std::max(tau_an - taudiff_max, tauwin_min)));
+    }
+    void finish4(const std::vector<Op>& nw, double factor, int np_new, double& acc_counter) {
+        std::vector<std::vector<double>> Mn; std::vector<int> kn;
+        LogVal DetNew = build_inverse_all(nw, Mn, kn);
+        LogVal DetOld{0, 1};                         // get_FullLogDet: LU of the stored inverses (CTQMC.F90:3817, 4345)
+        for (int f = 0; f < nf; ++f) if (kf[f] > 0) DetOld = lmul(mat_logdet(M[f], kf[f]), DetOld);
+        LogVal DetRat = lmul(DetNew, DetOld);
+        std::vector<LogVal> parts;
+        LogVal TraceNew = trace_full(nw, outer_sst, &parts);
+        LogVal trr = ldiv(TraceNew, Trace);
+        double rand = grnd();
+        double prob = std::fabs(factor * std::exp(trr.log + DetRat.log));
+        rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[14] = np_new; rec[17] = rand;
+        if (rand < prob) {
+            ops = nw; M.swap(Mn); kf = kn; Det = DetNew; Trace = TraceNew; parttrace = parts; ec.valid = false; fc.valid = false;
+            cfgsign = -get_sign(ops, Trace, Det);
+            acc_counter += 1; log_end(1);
+        } else log_end(0);
+    }
+    void StepAdd4() {                                // CTQMC.F90:3615-3889 (b_offdiag = .false.)
+        log_begin(7);
+        C.TryAdd4 += 1;
+        double W = tauwin_max - tauwin_min, fac = 1.0, tau_ref = 0; Op o[4];
+        for (int i = 0; i < 4; ++i) {                // pair_OperAdd with N = 4, force_diagonal (Trace.F90:3657-3698)
+            o[i].ca = (i % 2 == 0) ? 2 : 1;
+            if (i % 2 == 0) {
+                tau_ref = tauwin_min + W * grnd(); o[i].tau = tau_ref; fac *= W;
+                o[i].b = randint(1, nb) - 1; o[i].s = randint(1, 2) - 1;
+            } else {
+                double tmin = std::max(tau_ref - taudiff_max, tauwin_min), w2 = std::min(tau_ref + taudiff_max, tauwin_max) - tmin;
+                o[i].tau = tmin + w2 * grnd(); fac *= w2; o[i].b = o[i - 1].b; o[i].s = o[i - 1].s;
+            }
+        }
+        const int old_N = count_pairs(ops);          // ensure_valid_NPairs 3651
+        bool equal = false;
+        for (int i = 0; i < 4; ++i) { for (const Op& e : ops) if (e.tau == o[i].tau) equal = true; for (int j = 0; j < i; ++j) if (o[j].tau == o[i].tau) equal = true; }
+        Op O1 = o[0].tau < o[1].tau ? o[0] : o[1], O2 = o[0].tau < o[1].tau ? o[1] : o[0];
+        Op O3 = o[2].tau < o[3].tau ? o[2] : o[3], O4 = o[2].tau < o[3].tau ? o[3] : o[2];
+        std::vector<Op> all = merged(ops, {O1, O2, O3, O4});
+        rec[2] = all.front().tau; rec[3] = all.back().tau;
+        { double tmn = std::min(O1.tau, O3.tau), tmx = std::max(O2.tau, O4.tau); rec[2] = tmn; rec[3] = tmx; }
+        rec[4] = (O1.b * 2 + O1.s) * nf + (O3.b * 2 + O3.s);
+        if (equal) { log_end(2); return; }
+        const int N12 = count_pairs(merged(ops, {O1, O2})), N34 = count_pairs(merged(ops, {O3, O4})), Nall = count_pairs(all);
+        double rf;
+        if (is_rempair(O1, O4) && is_rempair(O2, O3)) {
+            const int N23 = count_pairs(merged(ops, {O2, O3})), N14 = count_pairs(merged(ops, {O1, O4}));
+            rf = (1.0 / Nall) * (1.0 / N12 + 1.0 / N34 + 1.0 / N14 + 1.0 / N23); fac /= 4.0;
+        } else if (is_rempair(O1, O3) && is_rempair(O2, O4)) {
+            const int N23 = count_pairs(merged(ops, {O2, O4})), N14 = count_pairs(merged(ops, {O1, O3}));
+            rf = (1.0 / Nall) * (1.0 / N12 + 1.0 / N34 + 1.0 / N14 + 1.0 / N23); fac /= 4.0;
+        } else { rf = (1.0 / Nall) * (1.0 / N12 + 1.0 / N34); fac /= 2.0; }
+        (void)old_N;
+        std::vector<int> after;
+        if (!sst_sequence(all, outer_sst, after)) { log_end(2); return; }   // check_sst_sequence over the changed sub-string (the rest is unchanged)
+        finish4(all, fac * (double)((2 * nb) * (2 * nb)) * rf, Nall, C.AccAdd4);
+    }
+    void StepRem4() {                                // CTQMC.F90:4153-4430 (b_offdiag = .false.)
+        log_begin(8);
+        C.TryRem4 += 1;
+        const int old_N = count_pairs(ops);
+        rec[14] = old_N;
+        if (old_N <= 0) { log_end(2); return; }
+        size_t i1, i2;
+        if (!pick_pair(ops, randint(1, old_N), i1, i2)) { error = 2; log_end(2); return; }
+        const Op O1 = ops[i1], O2 = ops[i2];
+        const double f1 = remfactor(old_N, O1, O2);
+        const std::vector<Op> c34 = without(ops, {O1, O2});
+        const int N34 = count_pairs(c34);
+        if (N34 <= 0) { log_end(2); return; }
+        size_t j1, j2;
+        if (!pick_pair(c34, randint(1, N34), j1, j2)) { error = 2; log_end(2); return; }
+        const Op O3 = c34[j1], O4 = c34[j2];
+        const double f2 = remfactor(N34, O3, O4);
+        double taudiff = (double)old_N * (double)N34 / f1 / f2;
+        const int N12 = count_pairs(without(ops, {O3, O4}));
+        double rf;
+        if (is_rempair(O1, O4) && is_rempair(O2, O3)) {
+            const int N23 = count_pairs(without(ops, {O1, O4})), N14 = count_pairs(without(ops, {O2, O3}));
+            rf = (1.0 / old_N) * (1.0 / N12 + 1.0 / N34 + 1.0 / N14 + 1.0 / N23); taudiff /= 4.0;
+        } else if (is_rempair(O1, O3) && is_rempair(O2, O4)) {
+            const int N23 = count_pairs(without(ops, {O1, O3})), N14 = count_pairs(without(ops, {O2, O4}));
+            rf = (1.0 / old_N) * (1.0 / N12 + 1.0 / N34 + 1.0 / N14 + 1.0 / N23); taudiff /= 4.0;
+        } else { rf = (1.0 / old_N) * (1.0 / N12 + 1.0 / N34); taudiff /= 2.0; }
+        const std::vector<Op> none = without(ops, {O1, O2, O3, O4});
+        rec[2] = std::min(O1.tau, O3.tau); rec[3] = std::max(O2.tau, O4.tau);
+        rec[4] = (O1.b * 2 + O1.s) * nf + (O3.b * 2 + O3.s);
+        std::vector<int> after;
+        if (!sst_sequence(none, outer_sst, after)) { log_end(2); return; }
+        finish4(none, 1.0 / (double)((2 * nb) * (2 * nb)) / taudiff / rf, count_pairs(none), C.AccRem4);
+    }
+
     // count compatible outer superstates: check_qn_all_ssts Trace.F90:1402-1433
     int compatible_ssts(const std::vector<Op>& o, std::vector<int>& ssts) const {
         ssts.resize(T.nsst); int cnt = 0; std::vector<int> after;
@@ -940,11 +1067,9 @@ struct Chain {
     void step() {                                    // CTQMC.F90:8213-8258 / 8428-8533
         double r = grnd();
         if (r < (1.0 - pshift - pglob) / 2.0) {
-            (void)(grnd() >= p4op);
-            StepAdd(grnd() < pouter);
+            if (grnd() >= p4op) StepAdd(grnd() < pouter); else StepAdd4();
         } else if (r <= 1.0 - pshift - pglob) {
-            (void)(grnd() >= p4op);
-            StepRem(grnd() < pouter);
+            if (grnd() >= p4op) StepRem(grnd() < pouter); else StepRem4();
         } else if (r <= 1.0 - pshift) StepGlob();
         else StepShiftTau();
         long long att = (long long)(C.TryAdd + C.TryRem);
@@ -1184,7 +1309,8 @@ void orc_get_scalars(void* h, double* out) {   // trace log/sign, det log/sign, 
 }
 void orc_get_counters(void* h, double* out) {
     Counters& C = ((Chain*)h)->C;
-    double v[11] = {C.TryAdd, C.TryRem, C.TryGlob, C.TryShift, C.AccAdd, C.AccRem, C.AccGlob, C.AccShift, C.AccQNAdd, C.AccQNRem, C.AccQNGlob};
+    double v[15] = {C.TryAdd, C.TryRem, C.TryGlob, C.TryShift, C.AccAdd, C.AccRem, C.AccGlob, C.AccShift, C.AccQNAdd, C.AccQNRem, C.AccQNGlob,
+                    C.TryAdd4, C.AccAdd4, C.TryRem4, C.AccRem4};
     std::memcpy(out, v, sizeof(v));
 }
 int orc_kf(void* h, int f) { return ((Chain*)h)->kf[f]; }

@@ -196,10 +196,10 @@ class OracleChain:
                     meas_sign=out[5], cnt_meas=int(out[6]), cnt_steps=int(out[7]))
 
     def counters(self):
-        out = np.zeros(11)
+        out = np.zeros(15)
         lib().orc_get_counters(self.h, _p(out, C.c_double))
         names = ["TryAdd", "TryRem", "TryGlob", "TryShift", "AccAdd", "AccRem", "AccGlob", "AccShift",
-                 "AccQNAdd", "AccQNRem", "AccQNGlob"]
+                 "AccQNAdd", "AccQNRem", "AccQNGlob", "TryAdd4", "AccAdd4", "TryRem4", "AccRem4"]
         return dict(zip(names, out))
 
     def kf(self):

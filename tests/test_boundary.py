@@ -221,7 +221,44 @@ def body_outer_moves(make, cfg, nsteps, beta=None, **opts):
     eng.dest_ctqmc()
 
 
+def body_four_operator_moves(make, cfg, nsteps, beta=None, **opts):
+    """4-operator moves with diagonal hybridisation (`Percentage4OperatorMove > 0`: StepAdd4 / StepRem4, CTQMC.F90:3615-3889,
+    4153-4430, scheduler branch 8441-8457; the move half of SURVEY.md 8 f3): two pairs inserted / removed at once, determinant from
+    scratch, proposal ratio summed over the orders of the inverse move.  Replay parity against the oracle (move types 7 / 8)."""
+    from oracle.oracle import OracleChain
+    from _parity import assert_replay
+    p = problems.make_problem(cfg, nftau=2001, beta=beta, Percentage4OperatorMove=0.3)
+    assert "Percentage4OperatorMove = 0.3" in p.pstring()
+    eng = _start(make(), p, nchains=8, **opts)
+    eng.init_counters()
+    log = eng.debug_steps(5, nsteps)
+    orc = OracleChain(p, rng="philox", seed=43890, chain=5)
+    orc.init_counters()
+    ref = orc.steps(nsteps, log=True)
+    assert_replay(log, ref)
+    for kind in (7, 8):
+        mv = log[log[:, 0] == kind]
+        assert mv.shape[0] > 0.1 * nsteps and (mv[:, 1] == 2).any() and (mv[:, 1] == 0).any()
+        if beta is not None:
+            assert (mv[:, 1] == 1).sum() >= 10
+    acc = log[(log[:, 0] >= 7) & (log[:, 1] == 1)]
+    idx = np.nonzero((log[:, 0] >= 7) & (log[:, 1] == 1) & (np.arange(log.shape[0]) > 0))[0]
+    assert (np.abs(log[idx, 12] - log[idx - 1, 12]) == 4).all()     # an accepted 4-operator move changes the number of operators by four
+    assert eng.scalar("error_flags") == 0
+    # state after thousands of mixed moves: inverse matrices against the oracle's (fast updates + from-scratch rebuilds on both sides)
+    for f in range(2 * p.nbands):
+        a, b = eng.debug_minv(5, f // 2 + 1, f % 2 + 1), orc.minv(f)
+        assert a.shape == b.shape and (a.size == 0 or np.abs(a - b).max() < 1e-8 * max(1.0, np.abs(b).max()))
+    eng.dest_ctqmc()
+
+
 # ------------------------------------------------------------------ CPU (host-emulation build of the same sources)
+@pytest.mark.parametrize("cfg,nsteps,beta,opts", [("C2", 5000, None, {}), ("C3", 4000, None, {}), ("C3", 4000, 3.0, {}), ("C4", 2000, 2.0, {}),
+                                                  ("C2", 4000, 4.0, {"scheduler": 2}), ("C2", 4000, 4.0, {"scheduler": 3})])
+def test_four_operator_moves(built, cfg, nsteps, beta, opts):
+    body_four_operator_moves(_hostemu_engine, cfg, nsteps, beta, **opts)
+
+
 @pytest.mark.parametrize("cfg,nsteps,beta,opts", [("C2", 6000, None, {}), ("C2", 6000, 4.0, {}), ("C3", 5000, 3.0, {}), ("C4", 2500, 2.0, {}),
                                                   ("C2", 4000, 4.0, {"scheduler": 2})])
 def test_outer_moves(built, cfg, nsteps, beta, opts):
@@ -283,6 +320,13 @@ def test_gpu_symmetry_moves(built, cfg, nsteps):
                                                   ("C2", 20000, 4.0, {}), ("C3", 12000, 3.0, {}), ("C4", 8000, 2.0, {}), ("C2", 8000, 4.0, {"scheduler": 2})])
 def test_gpu_outer_moves(built, cfg, nsteps, beta, opts):
     body_outer_moves(_cuda_engine, cfg, nsteps, beta, **opts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,nsteps,beta,opts", [("C2", 20000, None, {}), ("C3", 12000, None, {}), ("C4", 6000, None, {}), ("C5", 4000, None, {}),
+                                                  ("C3", 12000, 3.0, {}), ("C4", 6000, 2.0, {}), ("C2", 8000, 4.0, {"scheduler": 2}), ("C2", 8000, 4.0, {"scheduler": 3})])
+def test_gpu_four_operator_moves(built, cfg, nsteps, beta, opts):
+    body_four_operator_moves(_cuda_engine, cfg, nsteps, beta, **opts)
 
 
 @pytest.mark.gpu

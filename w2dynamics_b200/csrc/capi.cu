@@ -122,7 +122,9 @@ void check_supported(const Params& p) {
     zero_i("segment"); zero_i("offdiag"); zero_i("statesampling"); zero_i("Uw"); zero_i("Phonon");
     zero_i("MeasGiw"); zero_i("MeasG2iw"); zero_i("MeasSusz"); zero_i("MeasExpResDensityMatrix"); zero_i("FourPnt");
     zero_i("MeasSsquare"); zero_i("MeasGtauDetRat"); zero_i("flavourchange_moves"); zero_i("Gtau_mean_step"); zero_i("Gtau_mid_step"); zero_i("sign_step");
-    zero_r("Percentage4OperatorMove");                          // PercentageOuterMove (outer pair moves, CTQMC.F90:3422-3449, 3934-3961) is implemented
+    // PercentageOuterMove (outer pair moves, CTQMC.F90:3422-3449, 3934-3961) and Percentage4OperatorMove (StepAdd4 / StepRem4 with
+    // diagonal hybridisation, CTQMC.F90:3615-3889, 4153-4430) are implemented
+    if (p.has("Percentage4OperatorMove") && (p.real("Percentage4OperatorMove") < 0.0 || p.real("Percentage4OperatorMove") > 1.0)) throw std::runtime_error("Percentage4OperatorMove must lie in [0, 1]");
     if (p.has("PercentageOuterMove") && (p.real("PercentageOuterMove") < 0.0 || p.real("PercentageOuterMove") > 1.0)) throw std::runtime_error("PercentageOuterMove must lie in [0, 1]");
     if (p.has("Eigenbasis") && p.integer("Eigenbasis") == 0) throw std::runtime_error("You requested Krylov, but this no longer supported.");
     if (p.has("EnableOuterTruncation") && p.str("EnableOuterTruncation") == "YES") throw std::runtime_error("EnableOuterTruncation is outside the implemented hot path");
@@ -165,7 +167,7 @@ void finalize_results() {
     accadd[0] = ratio(cnt[C_ACCADD], cnt[C_TRYADD]); accrem[0] = ratio(cnt[C_ACCREM], cnt[C_TRYREM]);
     S.res.arr["accadd"] = accadd; S.res.arr["accrem"] = accrem;
     S.res.scal["accglob"] = ratio(cnt[C_ACCGLOB], cnt[C_TRYGLOB]); S.res.scal["accshift"] = ratio(cnt[C_ACCSHIFT], cnt[C_TRYSHIFT]);
-    S.res.scal["accadd4"] = std::numeric_limits<double>::quiet_NaN(); S.res.scal["accrem4"] = std::numeric_limits<double>::quiet_NaN();
+    S.res.scal["accadd4"] = ratio(cnt[C_ACCADD4], cnt[C_TRYADD4]); S.res.scal["accrem4"] = ratio(cnt[C_ACCREM4], cnt[C_TRYREM4]);   // AccAdd4 / TryAdd4: NaN without 4-operator moves, as in the reference
     S.res.scal["accflavc"] = std::numeric_limits<double>::quiet_NaN();
     S.res.scal["steps"] = (double)cnt[C_STEPS];
     if (E.ac_levels) {                                                       // gtau_blocks(NBands, 2, NGtau, levels), raw as in the reference (CTQMC.F90:8733-8739)
@@ -752,7 +754,7 @@ int w2b_get_scalar(const char* name, double* out) {
             if (k == "blocked") { *out = E.C.dmax > 1 ? 1.0 : 0.0; return; }
             if (k.rfind("cnt_", 0) == 0) {
                 static const char* names[C_NCNT] = {"try_add", "try_rem", "try_glob", "try_shift", "acc_add", "acc_rem", "acc_glob", "acc_shift",
-                                                    "qn_add", "qn_rem", "qn_glob", "steps", "alg_bytes", "trace_flops"};
+                                                    "qn_add", "qn_rem", "qn_glob", "steps", "alg_bytes", "trace_flops", "try_add4", "acc_add4", "try_rem4", "acc_rem4"};
                 std::vector<unsigned long long> cnt; E.get_counters(cnt);
                 for (int i = 0; i < C_NCNT; ++i) if (k.substr(4) == names[i]) { *out = (double)cnt[i]; return; }
             }

@@ -36,7 +36,7 @@ namespace w2b {
 
 constexpr int LOGW = 20;      // doubles per replay-log record (same layout as oracle/chain.cpp)
 constexpr int NF_MAX = 14;
-enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_ALGBYTES, C_TRFLOPS, C_NCNT };
+enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_ALGBYTES, C_TRFLOPS, C_TRYADD4, C_ACCADD4, C_TRYREM4, C_ACCREM4, C_NCNT };
 enum { IH_NOPS = 0, IH_OUTER, IH_WPOS, IH_NPAIRS, IH_PERM, IH_PALT, IH_ERR, IH_KV, IH_KF = 8, IH_MSLOT = IH_KF + NF_MAX, IH_BV = IH_MSLOT + NF_MAX + 1, IH_NFREE, IH_STRIDE };
 enum { DH_DETLOG = 0, DH_DETSIGN, DH_TRLOG, DH_TRSIGN, DH_CFGSIGN, DH_STRIDE = 8 };
 enum { ERR_CAPACITY = 1, ERR_DETRAT_SMALL = 2, ERR_PAIR_LOGIC = 4, ERR_GLOBAL_QN = 8, ERR_SINGULAR = 16 };
@@ -93,7 +93,8 @@ struct RareJob {
     int kind, new_outer, type, stored;       // kind 3 = global move, 4 = tau shift; stored: the trace kernel filled the ket caches of the new configuration
     int knew[NF_MAX];
     double tn_log, tn_sign;                  // staged global moves of the CTA scheduler: local trace of the proposed configuration
-    int nnew;                                // kinds 5 / 6 (outer pair moves): number of operators of the proposed sequence in the scratch arrays
+    int nnew;                                // kinds 5 - 8 (outer pair moves, 4-operator moves): number of operators of the proposed sequence in the scratch arrays
+    int np_new;                              // kinds 7 / 8: NPairs of the proposed configuration
 };
 
 // round scheduler counters (device memory, two sets used in alternation by consecutive rounds)
@@ -1606,6 +1607,232 @@ W2B_HDN void step_outer(const Tables& T, const Run& R, const Chains& C, const Ac
     if (kind == 5) add_decide<true>(T, R, C, A, x, P); else rem_decide<true>(T, R, C, A, x, P);
 }
 
+// ------------------------------------------------------------------ 4-operator moves (Percentage4OperatorMove, diagonal hybridisation)
+// StepAdd4 / StepRem4 (CTQMC.F90:3615-3889, 4153-4430): two pairs are inserted / removed at once.  As in the reference the determinant
+// of the proposed configuration comes from scratch (get_InvFullHybr, CTQMC.F90:3816) -- here the blocked tensor-pipe elimination --
+// and the inverse matrices are rebuilt on acceptance; the proposal ratio sums over the orders in which the inverse move could take
+// the four operators out (rempair_factor).  Served like global moves (kinds 7 / 8 of the rare machinery): proposed sequence staged
+// in the scratch arrays, whole-sequence local trace.  All pair counts are taken over ONE time-sorted list U (the stored
+// configuration, for insertions with the four new operators merged in) with some of the four "special" operators masked out.
+W2B_HD bool four_masked(int i, const int* sp, int mask) {
+    return ((mask & 1) && i == sp[0]) || ((mask & 2) && i == sp[1]) || ((mask & 4) && i == sp[2]) || ((mask & 8) && i == sp[3]);
+}
+// partners of operator i in gen_OperRemove's enumeration (Trace.F90:4886-4914): later operators of the same flavour and opposite type
+// with tau <= wmax and tau <= tau_i + taudiff_max; `want` > 0: returns the index of the want-th partner instead of the count
+W2B_HDN int four_partners(const Run& R, const Ctx& x, const double* tau, const unsigned char* code, int n, const int* sp, int mask, int i, int want) {
+    const int cd = code[i]; const double ti = tau[i];
+    int c = 0;
+#pragma unroll 1
+    for (int m = i + 1; m < n; ++m) {
+        const int cm = code[m];
+        if ((cm >> 1) != (cd >> 1) || four_masked(m, sp, mask)) continue;
+        const double v = tau[m];
+        if (v > x.wmax || v > ti + R.taudiff_max) break;
+        if ((cm ^ cd) & 1) { ++c; if (c == want) return m; }
+    }
+    return want > 0 ? -1 : c;
+}
+// NPairs of U minus the masked specials (ensure_valid_NPairs_diag Trace.F90:1770-1815); r > 0: the r-th pair in enumeration order -> (i1, i2)
+W2B_HDN int four_pairs(const Run& R, const Ctx& x, const double* tau, const unsigned char* code, int n, const int* sp, int mask, int r, int& i1, int& i2) {
+    const int ia = count_lt(tau, n, x.wmin), ib = count_le(tau, n, x.wmax);
+    int cum = 0;
+#pragma unroll 1
+    for (int base = ia; base < ib; base += W2B_WARP) {
+        const int i = base + lane_id();
+        const int c = (i < ib && !four_masked(i, sp, mask)) ? four_partners(R, x, tau, code, n, sp, mask, i, 0) : 0;
+        const int incl = wscan_incl(c), total = wbcast(incl, W2B_WARP - 1);
+        if (r > 0 && cum + total >= r) {
+            const unsigned hit = wballot(cum + incl >= r);
+            int src = 0;
+#if W2B_DEVICE
+            src = __ffs(hit) - 1;
+#endif
+            i1 = base + src;
+            i2 = four_partners(R, x, tau, code, n, sp, mask, i1, r - (cum + wbcast(incl - c, src)));
+            return cum + total;
+        }
+        cum += total;
+    }
+    return cum;
+}
+W2B_HD bool is_rempair(const Run& R, const Ctx& x, double t1, int c1, double t2, int c2) {      // is_rempair_diag Trace.F90:2005-2030
+    return (c1 >> 1) == (c2 >> 1) && ((c1 ^ c2) & 1) && t1 >= x.wmin && t1 <= x.wmax && t2 >= x.wmin && t2 <= x.wmax && fabs(t1 - t2) <= R.taudiff_max;
+}
+// first half; returns true when a proposal is staged: sequence, flavour time arrays and orders in the scratch arrays, determinant in
+// J.dn_*, proposal factor in J.factor, new pair count in J.np_new
+W2B_HDN bool four_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, int kind) {
+    const bool add = kind == 7;
+    const int n = x.n, nf = T.nf;
+    log_begin(x, kind);
+    bump(x, add ? C_TRYADD4 : C_TRYREM4);
+    if (x.npairs < 0) x.npairs = count_pairs_full(T, R, C, x);        // ensure_valid_NPairs CTQMC.F90:3651 / gen_OperRemove
+    const int N0 = x.npairs;
+    const double W = x.wmax - x.wmin;
+    double t[4]; int code[4]; int* sp = x.wI;                         // sp[0..3]: list indices of the four special operators in U
+    const double* Ut; const unsigned char* Uc; int nU, nn;
+    double fac, rf; int np_new, N12, N34, dummy1, dummy2;
+    if (add) {
+        nn = n + 4; nU = nn;
+        if (nn > C.ops_cap) { x.err |= ERR_CAPACITY; log_end(x, 0); return false; }
+        fac = 1.0;                                                    // pair_OperAdd with N = 4, force_diagonal (Trace.F90:3657-3698)
+#pragma unroll 1
+        for (int pr = 0; pr < 2; ++pr) {
+            const double tau_a = add_rn(x.wmin, mul_rn(W, x.rng.next()));
+            const int b = x.rng.randint(1, T.nb) - 1, sp_ = x.rng.randint(1, 2) - 1;
+            const double tmin = fmax(tau_a - R.taudiff_max, x.wmin), w2 = fmin(tau_a + R.taudiff_max, x.wmax) - tmin;
+            const double tau_c = add_rn(tmin, mul_rn(w2, x.rng.next()));
+            fac = mul_rn(mul_rn(fac, W), w2);
+            const int f = b * 2 + sp_, lo = 2 * pr, hi = 2 * pr + 1;    // each pair in time order (process_OperAdd)
+            if (tau_a < tau_c) { t[lo] = tau_a; code[lo] = f * 2 + 1; t[hi] = tau_c; code[hi] = f * 2; }
+            else { t[lo] = tau_c; code[lo] = f * 2; t[hi] = tau_a; code[hi] = f * 2 + 1; }
+        }
+        log_set(x, 2, fmin(t[0], t[2])); log_set(x, 3, fmax(t[1], t[3])); log_set(x, 4, (code[0] >> 1) * nf + (code[2] >> 1));
+        bool equal = false;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) { bool e; count_lt(x.tau, n, t[j], e); equal |= e; for (int j2 = 0; j2 < j; ++j2) equal |= t[j2] == t[j]; }
+        if (equal) { log_end(x, 2); return false; }
+        // U = the proposed sequence: stored operators shifted by the number of new ones before them, new ones at their ranks
+#pragma unroll 1
+        for (int i = lane_id(); i < n; i += W2B_WARP) {
+            const double v = x.tau[i]; const int sh = (t[0] < v) + (t[1] < v) + (t[2] < v) + (t[3] < v);
+            x.sc_tau[i + sh] = v; x.sc_code[i + sh] = x.code[i];
+        }
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            int pos = count_lt(x.tau, n, t[j]);
+#pragma unroll 1
+            for (int j2 = 0; j2 < 4; ++j2) pos += (j2 != j && t[j2] < t[j]) ? 1 : 0;
+            if (lane_id() == 0) { x.sc_tau[pos] = t[j]; x.sc_code[pos] = (unsigned char)code[j]; sp[j] = pos; }
+        }
+        wsync();
+        Ut = x.sc_tau; Uc = x.sc_code;
+        N12 = four_pairs(R, x, Ut, Uc, nU, sp, 4 | 8, 0, dummy1, dummy2);
+        N34 = four_pairs(R, x, Ut, Uc, nU, sp, 1 | 2, 0, dummy1, dummy2);
+        np_new = four_pairs(R, x, Ut, Uc, nU, sp, 0, 0, dummy1, dummy2);
+    } else {
+        nn = n - 4; nU = n; Ut = x.tau; Uc = x.code;
+        log_set(x, 14, N0);
+        if (N0 <= 0) { log_end(x, 2); return false; }
+        // gen_OperRemove twice: the second pair is drawn from the configuration without the first
+        int i1 = -1, i2 = -1;
+        if (lane_id() == 0) { sp[0] = sp[1] = sp[2] = sp[3] = -1; }
+        wsync();
+        four_pairs(R, x, Ut, Uc, nU, sp, 0, x.rng.randint(1, N0), i1, i2);
+        if (i1 < 0 || i2 < 0) { x.err |= ERR_PAIR_LOGIC; log_end(x, 2); return false; }
+        if (lane_id() == 0) { sp[0] = i1; sp[1] = i2; }
+        wsync();
+        N34 = four_pairs(R, x, Ut, Uc, nU, sp, 1 | 2, 0, dummy1, dummy2);
+        if (N34 <= 0) { log_end(x, 2); return false; }
+        int i3 = -1, i4 = -1;
+        four_pairs(R, x, Ut, Uc, nU, sp, 1 | 2, x.rng.randint(1, N34), i3, i4);
+        if (i3 < 0 || i4 < 0) { x.err |= ERR_PAIR_LOGIC; log_end(x, 2); return false; }
+        if (lane_id() == 0) { sp[2] = i3; sp[3] = i4; }
+        wsync();
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) { t[j] = Ut[sp[j]]; code[j] = Uc[sp[j]]; }
+        // inverse tau-choice probability of the insertion: (W w2(annihilator 1)) (W w2(annihilator 2))   (CTQMC.F90:4194-4195)
+        fac = 1.0;
+#pragma unroll 1
+        for (int pr = 0; pr < 2; ++pr) {
+            const double tan = (code[2 * pr] & 1) ? t[2 * pr] : t[2 * pr + 1];
+            fac *= W * (fmin(tan + R.taudiff_max, x.wmax) - fmax(tan - R.taudiff_max, x.wmin));
+        }
+        N12 = four_pairs(R, x, Ut, Uc, nU, sp, 4 | 8, 0, dummy1, dummy2);
+        np_new = four_pairs(R, x, Ut, Uc, nU, sp, 15, 0, dummy1, dummy2);
+        log_set(x, 2, fmin(t[0], t[2])); log_set(x, 3, fmax(t[1], t[3])); log_set(x, 4, (code[0] >> 1) * nf + (code[2] >> 1));
+    }
+    {   // rempair_factor: the four operators can leave in two or in four orders (CTQMC.F90:3677-3766, 4204-4290)
+        const double Nref = add ? (double)np_new : (double)N0;
+        int N14 = 0, N23 = 0; bool four_ways = false;
+        if (is_rempair(R, x, t[0], code[0], t[3], code[3]) && is_rempair(R, x, t[1], code[1], t[2], code[2])) {
+            four_ways = true;
+            N23 = four_pairs(R, x, Ut, Uc, nU, sp, 1 | 8, 0, dummy1, dummy2); N14 = four_pairs(R, x, Ut, Uc, nU, sp, 2 | 4, 0, dummy1, dummy2);
+        } else if (is_rempair(R, x, t[0], code[0], t[2], code[2]) && is_rempair(R, x, t[1], code[1], t[3], code[3])) {
+            four_ways = true;
+            N23 = four_pairs(R, x, Ut, Uc, nU, sp, 1 | 4, 0, dummy1, dummy2); N14 = four_pairs(R, x, Ut, Uc, nU, sp, 2 | 8, 0, dummy1, dummy2);
+        }
+        if (four_ways) { rf = (1.0 / Nref) * (1.0 / (double)N12 + 1.0 / (double)N34 + 1.0 / (double)N14 + 1.0 / (double)N23); fac /= 4.0; }
+        else { rf = (1.0 / Nref) * (1.0 / (double)N12 + 1.0 / (double)N34); fac /= 2.0; }
+    }
+    const double nb2 = (double)((2 * T.nb) * (2 * T.nb));
+    const double factor = add ? fac * nb2 * rf : 1.0 / nb2 / fac / rf;
+    if (!add) {                                                       // proposed sequence = U without the four
+#pragma unroll 1
+        for (int i = lane_id(); i < n; i += W2B_WARP) {
+            if (four_masked(i, sp, 15)) continue;
+            const int sh = (sp[0] < i) + (sp[1] < i) + (sp[2] < i) + (sp[3] < i);
+            x.sc_tau[i - sh] = x.tau[i]; x.sc_code[i - sh] = x.code[i];
+        }
+        wsync();
+    }
+    // quantum numbers: the proposed sequence has to close on the unchanged outer superstate (check_sst_sequence over the changed
+    // sub-string, CTQMC.F90:3769-3796; outside it nothing changes and the superstate maps are injective)
+    if (walk_store(T, x.sc_code, 0, nn, x.outer, x.sc_sst, 0) != x.outer) { log_end(x, 2); return false; }
+    // flavour time arrays of the proposed sequence: rank among the operators of the same code
+#pragma unroll 1
+    for (int c = 0; c < 2 * nf; ++c) {
+        double* dst = ((c & 1) ? x.sc_ta : x.sc_tc) + (size_t)(c >> 1) * C.kcap;
+        int run = 0;
+#pragma unroll 1
+        for (int base = 0; base < nn; base += W2B_WARP) {
+            const int i = base + lane_id(); const bool mine = i < nn && (int)x.sc_code[i] == c;
+            const int incl = wscan_incl(mine ? 1 : 0);
+            if (mine) { if (run + incl - 1 < C.kcap) dst[run + incl - 1] = x.sc_tau[i]; }
+            run += wbcast(incl, W2B_WARP - 1);
+        }
+        if (run > C.kcap) { x.err |= ERR_CAPACITY; log_end(x, 0); return false; }
+        if (!(c & 1) && lane_id() == 0) J.knew[c >> 1] = run;
+    }
+    wsync();
+    double dn_log, dn_sign;
+    rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, J.knew, false, dn_log, dn_sign);
+    if (lane_id() == 0) { J.kind = kind; J.new_outer = x.outer; J.nnew = nn; J.stored = 0; J.factor = factor; J.np_new = np_new; J.dn_log = dn_log; J.dn_sign = dn_sign; }
+    wsync();
+    return true;
+}
+// second half: Metropolis; on acceptance the staged configuration replaces the stored one and the inverse matrices are rebuilt
+W2B_HDN void four_finish(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, double tn_log, double tn_sign) {
+    const int nf = T.nf, nn = J.nnew;
+    const double dr_log = J.dn_log - x.det_log, dr_sign = J.dn_sign * x.det_sign;
+    const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
+    const double rand = x.rng.next();
+    const double prob = fabs(J.factor * w_exp(trr_log + dr_log));
+    log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 14, J.np_new); log_set(x, 17, rand);
+    if (!(rand < prob)) { log_end(x, 0); return; }
+#pragma unroll 1
+    for (int i = lane_id(); i < nn; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
+#pragma unroll 1
+    for (int f = 0; f < nf; ++f) {
+        const int k = J.knew[f];
+#pragma unroll 1
+        for (int i = lane_id(); i < k; i += W2B_WARP) { x.tc[(size_t)f * C.kcap + i] = x.sc_tc[(size_t)f * C.kcap + i]; x.ta[(size_t)f * C.kcap + i] = x.sc_ta[(size_t)f * C.kcap + i]; }
+    }
+    wsync();
+    if (lane_id() == 0) for (int f = 0; f < nf; ++f) x.ih[IH_KF + f] = J.knew[f];
+    wsync();
+    x.n = nn;
+    double l2, s2;
+    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
+    x.det_log = J.dn_log; x.det_sign = J.dn_sign; x.tr_log = tn_log; x.tr_sign = tn_sign;
+    if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); }
+    x.npairs = J.np_new;
+    x.perm = perm_full(x.code, x.n);
+    x.palt = 0;
+#pragma unroll 1
+    for (int f = 0; f < nf; ++f) x.palt |= palt_flavour(C, x, f) << f;
+    update_cfgsign(T, x);
+    bump(x, J.kind == 7 ? C_ACCADD4 : C_ACCREM4);
+    log_end(x, 1);
+}
+// the whole move on one warp (1x1 blocks; host paths that do not use the trace kernel)
+W2B_HDN void step_four(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, int kind) {
+    if (!four_prepare(T, R, C, x, J, kind)) return;
+    double tn_log, tn_sign;
+    if (T.dmax > 1) full_trace(T, x, x.sc_tau, x.sc_code, J.nnew, x.outer, tn_log, tn_sign);
+    else trace_full_scalar(T, x.sc_tau, x.sc_code, x.sc_sst, J.nnew, x.outer, tn_log, tn_sign);
+    four_finish(T, R, C, x, J, tn_log, tn_sign);
+}
+
 // ------------------------------------------------------------------ chain load / store
 W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain, Ctx& x, double* wscratch, int* iscratch, double* mscratch) {
     x.tau = C.op_tau + (size_t)chain * C.ops_cap; x.code = C.op_code + (size_t)chain * C.ops_cap; x.sst = C.op_sst + (size_t)chain * C.ops_cap;
@@ -1734,10 +1961,12 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                     if (lane == 0) { S.kind[c] = (unsigned char)(r <= thr_glob ? 3 : 4); S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
                     break;
                 }
-                if (R.pouter > 0.0) {                                     // Percentage4OperatorMove draw (0), then `grnd() < PercentageOuterMove` (CTQMC.F90:8441-8442)
-                    x.rng.skip(1);
-                    if (x.rng.next() < R.pouter) {                        // outer pair move: parked, served like a global move
-                        if (lane == 0) { S.kind[c] = (unsigned char)(r < thr_add ? 5 : 6); S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
+                if (R.pouter > 0.0 || R.p4op > 0.0) {                     // `if (grnd() >= Percentage4OperatorMove) StepAdd(grnd() < PercentageOuterMove) else StepAdd4` (CTQMC.F90:8441-8449)
+                    int special = 0;
+                    if (!(x.rng.next() >= R.p4op)) special = r < thr_add ? 7 : 8;
+                    else if (x.rng.next() < R.pouter) special = r < thr_add ? 5 : 6;
+                    if (special) {                                        // 4-operator / outer pair move: parked, served like a global move
+                        if (lane == 0) { S.kind[c] = (unsigned char)special; S.parked[c] = 1; S.lG[wgrab_one(&S.nG)] = (short)c; }
                         break;
                     }
                 } else x.rng.skip(2);
@@ -1803,7 +2032,8 @@ W2B_HD void cta_sweep(const Tables& T, const Run& R, const Chains& C, const Accu
                 if (((int)S.kind[c] == 3) != (t < ng)) continue;
                 ctx_bind(T, R, C, chain, x, wscratch, iscratch, mscratch);
                 if (chain == log_chain) x.log = logbuf + (size_t)(nsteps - S.left[c]) * LOGW;
-                if ((int)S.kind[c] >= 5) step_outer(T, R, C, A, x, S.prop[c], C.rjob[chain], (int)S.kind[c]);
+                if ((int)S.kind[c] >= 7) step_four(T, R, C, x, C.rjob[chain], (int)S.kind[c]);
+                else if ((int)S.kind[c] >= 5) step_outer(T, R, C, A, x, S.prop[c], C.rjob[chain], (int)S.kind[c]);
                 else step_rare(T, R, C, x, C.rjob[chain], (int)S.kind[c]);
                 post_move_cta(T, R, x, S, c);
                 ctx_store(C, chain, x);
@@ -1856,9 +2086,10 @@ W2B_HD void chain_sweep(const Tables& T, const Run& R, const Chains& C, const Ac
         const double r = x.rng.next();                                // move type: reference thresholds CTQMC.F90:8437-8488
         if (!(r <= thr_rem)) { const int kind = r <= thr_glob ? 3 : 4; step_rare(T, R, C, x, C.rjob[chain], kind); W2B_TICK(kind == 3 ? 4 : 5) }
         else {
-            bool outer = false;
-            if (R.pouter > 0.0) { x.rng.skip(1); outer = x.rng.next() < R.pouter; } else x.rng.skip(2);
-            if (outer) step_outer(T, R, C, A, x, P, C.rjob[chain], r < thr_add ? 5 : 6);
+            bool outer = false, four = false;
+            if (R.pouter > 0.0 || R.p4op > 0.0) { four = !(x.rng.next() >= R.p4op); if (!four) outer = x.rng.next() < R.pouter; } else x.rng.skip(2);
+            if (four) step_four(T, R, C, x, C.rjob[chain], r < thr_add ? 7 : 8);
+            else if (outer) step_outer(T, R, C, A, x, P, C.rjob[chain], r < thr_add ? 5 : 6);
             else if (r < thr_add) { const bool go = add_propose<false>(T, R, C, x, P); W2B_TICK(0) if (go) { add_decide<false>(T, R, C, A, x, P); W2B_TICK(1) } }
             else { const bool go = rem_propose<false>(T, R, C, x, P); W2B_TICK(2) if (go) { rem_decide<false>(T, R, C, A, x, P); W2B_TICK(3) } }
         }
@@ -1913,10 +2144,12 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
             if (lane == 0) { C.kind[chain] = (unsigned char)(r <= thr_glob ? 3 : 4); C.parked[chain] = ST_RARE_NEW; }
             break;
         }
-        if (R.pouter > 0.0) {                                     // Percentage4OperatorMove draw (0), then `grnd() < PercentageOuterMove` (CTQMC.F90:8441-8442)
-            x.rng.skip(1);
-            if (x.rng.next() < R.pouter) {                        // outer pair move: rare stream
-                if (lane == 0) { C.kind[chain] = (unsigned char)(r < thr_add ? 5 : 6); C.parked[chain] = ST_RARE_NEW; }
+        if (R.pouter > 0.0 || R.p4op > 0.0) {                     // `if (grnd() >= Percentage4OperatorMove) StepAdd(grnd() < PercentageOuterMove) else StepAdd4` (CTQMC.F90:8441-8449)
+            int special = 0;
+            if (!(x.rng.next() >= R.p4op)) special = r < thr_add ? 7 : 8;
+            else if (x.rng.next() < R.pouter) special = r < thr_add ? 5 : 6;
+            if (special) {                                        // 4-operator / outer pair move: rare stream
+                if (lane == 0) { C.kind[chain] = (unsigned char)special; C.parked[chain] = ST_RARE_NEW; }
                 break;
             }
         } else x.rng.skip(2);
@@ -2006,7 +2239,10 @@ W2B_HD void phase_rare(const Tables& T, const Run& R, const Chains& C, const Acc
     RareJob& J = C.rjob[chain];
     const int kind = C.kind[chain];
     bool pending = false;
-    if (kind >= 5) {                                                 // outer pair moves (PercentageOuterMove)
+    if (kind >= 7) {                                                 // 4-operator moves (Percentage4OperatorMove)
+        if (T.dmax > 1) pending = four_prepare(T, R, C, x, J, kind);
+        else step_four(T, R, C, x, J, kind);
+    } else if (kind >= 5) {                                          // outer pair moves (PercentageOuterMove)
         if (T.dmax > 1) pending = outer_prepare(T, R, C, x, C.prop[chain], J, kind);
         else step_outer(T, R, C, A, x, C.prop[chain], J, kind);
     } else if (T.dmax > 1) {
@@ -2043,7 +2279,8 @@ W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const A
         if (kind == 3) step_glob_finish(T, R, C, x, J, tn_log, tn_sign);
         else if (kind == 4) step_shift_finish(T, R, C, x, J, tn_log, tn_sign);
         else if (kind == 5) add_decide<true>(T, R, C, A, x, C.prop[chain]);
-        else rem_decide<true>(T, R, C, A, x, C.prop[chain]);
+        else if (kind == 6) rem_decide<true>(T, R, C, A, x, C.prop[chain]);
+        else four_finish(T, R, C, x, J, tn_log, tn_sign);
     }
     else if (entry & Q_REM) rem_decide<false>(T, R, C, A, x, C.prop[chain]);
     else add_decide<false>(T, R, C, A, x, C.prop[chain]);
