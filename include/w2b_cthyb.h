@@ -110,7 +110,8 @@ void w2b_pinned_free(void* p);
 
 /* ---- replay / parity hooks ---- */
 /* advance all chains by nsteps moves and record chain `chain`'s per-move records (20 doubles each):
- * [0] move 1=add 2=rem 3=glob 4=shift 5=outer add 6=outer rem  [1] status 0=rejected 1=accepted 2=early exit  [2],[3] tau1,tau2
+ * [0] move 1=add 2=rem 3=glob 4=shift 5=outer add 6=outer rem 7=add4 8=rem4 ([2],[3]: earliest / latest of the four times,
+ *     [4] = flavour(pair 1) * nf + flavour(pair 2))  [1] status 0=rejected 1=accepted 2=early exit  [2],[3] tau1,tau2
  * [4] flavour  [5],[6] FPos(c^dag),FPos(c)  [7],[8] log|det ratio|, sign  [9],[10] log|trace ratio|, sign
  * [11] acceptance probability  [12] #operators after  [13] outer superstate after  [14] NPairs used
  * [15] configuration sign after  [16] window position after  [17] accept random number */

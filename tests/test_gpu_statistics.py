@@ -78,6 +78,17 @@ def test_outer_moves_leave_the_distribution_invariant(cuda_engine_factory, cfg, 
     _compare(cuda_engine_factory, "%s beta=%g with outer moves" % (cfg, beta), p_gpu, p_cpu, case)
 
 
+@pytest.mark.parametrize("cfg,beta", [("C3", None), ("C3", 3.0), ("C2", 4.0)])
+def test_four_operator_moves_leave_the_distribution_invariant(cuda_engine_factory, cfg, beta):
+    """4-operator moves (Percentage4OperatorMove, the move half of SURVEY.md 8 f3): the GPU population sampled WITH 30 % of the pair
+    moves replaced by two-pair moves must agree with a CPU oracle population sampled WITHOUT them (C3 as named: 4 % of them are
+    accepted; high temperature: 10 %)."""
+    case = (2048, 12000, 100, 32, 15000, 1500, 2) if beta is None else (2048, 6000, 100, 32, 8000, 3000, 0)
+    p_gpu = problems.make_problem(cfg, beta=beta, Nmeas=case[2], Ntau=500, NLegMax=40, Percentage4OperatorMove=0.3)
+    p_cpu = problems.make_problem(cfg, beta=beta, Nmeas=case[2], Ntau=500, NLegMax=40)
+    _compare(cuda_engine_factory, "%s beta=%s with 4-operator moves" % (cfg, beta), p_gpu, p_cpu, case)
+
+
 def _compare(cuda_engine_factory, cfg, p, p_cpu, case):
     gch, gwarm, gmeas, cch, cwarm, cmeas, fast = case
     eng = cuda_engine_factory(p, nchains=gch, nbins=32)
