@@ -146,6 +146,21 @@ def body_validation(make):
     with pytest.raises(RuntimeError, match="ascending"):
         eng.set_mc_config(2, t[::-1].copy(), o, s, ca, h, 0, 1)
     eng.dest_ctqmc()
+    # what is outside the implemented path is refused by name, never approximated
+    for key, val in (("statesampling", 1), ("offdiag", 1), ("segment", 1), ("flavourchange_moves", 1), ("Percentage4OperatorMove", 1.5), ("PercentageOuterMove", -0.1)):
+        q = problems.make_problem("C2", nftau=501, **{key: val})
+        with pytest.raises(RuntimeError, match=key):
+            make().init_paras(q.pstring())
+    # 4-operator moves through the result surface: AccAdd4 / TryAdd4 (CTQMC.F90:8680-8695) -- NaN without them, as in the reference
+    q = problems.make_problem("C2", nftau=501, beta=4.0, Nmeas=20, Percentage4OperatorMove=0.3)
+    eng = _start(make(), q)
+    eng.ctqmc_warmup(500); eng.ctqmc_measure(1, 1)
+    assert 0.0 < float(eng.accadd4) < 1.0 and 0.0 < float(eng.accrem4) < 1.0 and np.isnan(float(eng.accflavc))
+    eng.dest_ctqmc()
+    eng = _start(make(), problems.make_problem("C2", nftau=501, Nmeas=5))
+    eng.ctqmc_warmup(200); eng.ctqmc_measure(1, 1)
+    assert np.isnan(float(eng.accadd4)) and np.isnan(float(eng.accrem4))
+    eng.dest_ctqmc()
 
 
 def body_calibrate_list(make):
