@@ -1608,10 +1608,10 @@ W2B_HDN void step_outer(const Tables& T, const Run& R, const Chains& C, const Ac
 }
 
 // ------------------------------------------------------------------ 4-operator moves (Percentage4OperatorMove, diagonal hybridisation)
-// StepAdd4 / StepRem4 (CTQMC.F90:3615-3889, 4153-4430): two pairs are inserted / removed at once.  As in the reference the determinant
-// of the proposed configuration comes from scratch (get_InvFullHybr, CTQMC.F90:3816) -- here the blocked tensor-pipe elimination --
-// and the inverse matrices are rebuilt on acceptance; the proposal ratio sums over the orders in which the inverse move could take
-// the four operators out (rempair_factor).  Served like global moves (kinds 7 / 8 of the rare machinery): proposed sequence staged
+// StepAdd4 / StepRem4 (CTQMC.F90:3615-3889, 4153-4430): two pairs are inserted / removed at once.  The reference takes the determinant
+// of every proposed configuration from scratch (get_InvFullHybr, CTQMC.F90:3816); here the RATIO is a rank-2 form on the stored
+// inverses (four_det_ratio) and only accepted moves rebuild the inverse matrices (blocked tensor-pipe elimination); the proposal
+// ratio sums over the orders in which the inverse move could take the four operators out (rempair_factor).  Served like global moves (kinds 7 / 8 of the rare machinery): proposed sequence staged
 // in the scratch arrays, whole-sequence local trace.  All pair counts are taken over ONE time-sorted list U (the stored
 // configuration, for insertions with the four new operators merged in) with some of the four "special" operators masked out.
 W2B_HD bool four_masked(int i, const int* sp, int mask) {
@@ -1658,6 +1658,61 @@ W2B_HDN int four_pairs(const Run& R, const Ctx& x, const double* tau, const unsi
 W2B_HD bool is_rempair(const Run& R, const Ctx& x, double t1, int c1, double t2, int c2) {      // is_rempair_diag Trace.F90:2005-2030
     return (c1 >> 1) == (c2 >> 1) && ((c1 ^ c2) & 1) && t1 >= x.wmin && t1 <= x.wmax && t2 >= x.wmin && t2 <= x.wmax && fabs(t1 - t2) <= R.taudiff_max;
 }
+// Determinant ratio of a 4-operator move WITHOUT an elimination: Woodbury / Jacobi rank-2 forms on the stored inverse matrices.
+//   two pairs of different flavours: the product of the two rank-1 ratios (S = F - R M Q, resp. the element M(c, a));
+//   insertion into ONE flavour:  det Delta' / det Delta = (-1)^(i1+i2+j1+j2) det S,  S_uv = F(a_u - c_v) - R_u M Q_v  (2 x 2 Schur complement;
+//     rows u = the new annihilators, columns v = the new creators, both in time order; i, j their positions in the new matrix);
+//   removal from ONE flavour:    det Delta' / det Delta = (-1)^(i1+i2+j1+j2) det [ M(c_v, a_u) ]   (Jacobi's complementary-minor identity).
+// O(k^2) per proposal instead of the reference's from-scratch determinant of every flavour (CTQMC.F90:3816-3817); accepted moves still
+// rebuild the inverse matrices from scratch as the reference does, which also resets the rounding of the fast updates.
+// t / code: the four operators; returns (log|ratio|, sign); sign 0 = singular.
+W2B_HDN void four_det_ratio(const Tables& T, const Chains& C, Ctx& x, bool add, const double* t, const int* code, double& rlog, double& rsign) {
+    double ratio = 1.0; int par = 0;
+    const int fA = code[0] >> 1, fB = code[2] >> 1;
+    // creator / annihilator time of each pair (each pair holds one of either)
+    double tc2[2], ta2[2];
+#pragma unroll 1
+    for (int pr = 0; pr < 2; ++pr) { const bool first_is_a = code[2 * pr] & 1; ta2[pr] = first_is_a ? t[2 * pr] : t[2 * pr + 1]; tc2[pr] = first_is_a ? t[2 * pr + 1] : t[2 * pr]; }
+    if (fA != fB) {
+#pragma unroll 1
+        for (int pr = 0; pr < 2; ++pr) {
+            const int f = pr == 0 ? fA : fB, k = x.ih[IH_KF + f];
+            const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+            const int p1 = count_lt(tc, k, tc2[pr]), p2 = count_lt(ta, k, ta2[pr]);
+            ratio *= add ? det_ratio_add(T, C, x, f, tc2[pr], ta2[pr]) : Mbuf(C, x, f)[(size_t)p1 * C.ld + p2];
+            par ^= (p1 - p2) & 1;
+        }
+    } else {
+        const int f = fA, k = x.ih[IH_KF + f];
+        const double* tc = x.tc + (size_t)f * C.kcap; const double* ta = x.ta + (size_t)f * C.kcap;
+        const double c0 = fmin(tc2[0], tc2[1]), c1 = fmax(tc2[0], tc2[1]), a0 = fmin(ta2[0], ta2[1]), a1 = fmax(ta2[0], ta2[1]);
+        const int jc0 = count_lt(tc, k, c0), jc1 = count_lt(tc, k, c1), ia0 = count_lt(ta, k, a0), ia1 = count_lt(ta, k, a1);
+        if (add) {
+            // positions in the NEW arrays: jc0, jc1 + 1, ia0, ia1 + 1 -> the two +1 cancel in the parity
+            par = (jc0 + jc1 + ia0 + ia1) & 1;
+            const double S00 = det_ratio_add(T, C, x, f, c0, a0);               // leaves V0 = R(a0)^T M in wV
+            double part = 0.0;
+#pragma unroll 1
+            for (int j = lane_id(); j < k; j += W2B_WARP) part += x.wV[j] * hybrF(T, ta[j] - c1, f);
+            const double S01 = hybrF(T, a0 - c1, f) - wsum(part);
+            wsync();
+            const double S11 = det_ratio_add(T, C, x, f, c1, a1);               // V1 = R(a1)^T M
+            part = 0.0;
+#pragma unroll 1
+            for (int j = lane_id(); j < k; j += W2B_WARP) part += x.wV[j] * hybrF(T, ta[j] - c0, f);
+            const double S10 = hybrF(T, a1 - c0, f) - wsum(part);
+            wsync();
+            ratio = S00 * S11 - S01 * S10;
+        } else {
+            par = (jc0 + jc1 + ia0 + ia1) & 1;
+            const double* M = Mbuf(C, x, f); const int ld = C.ld;
+            ratio = M[(size_t)jc0 * ld + ia0] * M[(size_t)jc1 * ld + ia1] - M[(size_t)jc0 * ld + ia1] * M[(size_t)jc1 * ld + ia0];
+        }
+    }
+    if (ratio == 0.0) { rlog = -1.7976931348623157e308; rsign = 0.0; return; }
+    rlog = w_log(fabs(ratio)); rsign = sgn1(ratio) * (par ? -1.0 : 1.0);
+}
+
 // first half; returns true when a proposal is staged: sequence, flavour time arrays and orders in the scratch arrays, determinant in
 // J.dn_*, proposal factor in J.factor, new pair count in J.np_new
 W2B_HDN bool four_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, int kind) {
@@ -1785,7 +1840,11 @@ W2B_HDN bool four_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x
     }
     wsync();
     double dn_log, dn_sign;
-    rebuild_inverses(T, C, x, x.sc_tc, x.sc_ta, J.knew, false, dn_log, dn_sign);
+    {   // determinant of the proposed configuration = stored determinant x rank-2 ratio (no elimination per proposal)
+        double rl, rs;
+        four_det_ratio(T, C, x, add, t, code, rl, rs);
+        dn_log = rs == 0.0 ? rl : x.det_log + rl; dn_sign = x.det_sign * rs;
+    }
     if (lane_id() == 0) { J.kind = kind; J.new_outer = x.outer; J.nnew = nn; J.stored = 0; J.factor = factor; J.np_new = np_new; J.dn_log = dn_log; J.dn_sign = dn_sign; }
     wsync();
     return true;
@@ -1812,8 +1871,8 @@ W2B_HDN void four_finish(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     wsync();
     x.n = nn;
     double l2, s2;
-    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);
-    x.det_log = J.dn_log; x.det_sign = J.dn_sign; x.tr_log = tn_log; x.tr_sign = tn_sign;
+    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);       // get_InvFullHybr: inverse matrices AND determinant from scratch (CTQMC.F90:3856-3866)
+    x.det_log = l2; x.det_sign = s2; x.tr_log = tn_log; x.tr_sign = tn_sign;
     if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); }
     x.npairs = J.np_new;
     x.perm = perm_full(x.code, x.n);
