@@ -100,6 +100,36 @@ def test_measurement_parity(cuda_engine_factory):
     eng.dest_ctqmc()
 
 
+@pytest.mark.parametrize("extra", [{}, {"PercentageOuterMove": 0.3}, {"Percentage4OperatorMove": 0.3}, {"PercentageOuterMove": 0.2, "Percentage4OperatorMove": 0.2}],
+                         ids=["pair-moves", "outer-moves", "4-operator-moves", "both"])
+@pytest.mark.parametrize("scheduler", [0, 3])
+def test_noninteracting_exact(cuda_engine_factory, extra, scheduler):
+    """U = 0: the CUDA engine's G(tau) against the EXACT impurity Green's function of the discrete bath (no oracle involved), with
+    every optional move type switched on in turn -- the z-scores use the engine's own chain-group error bars."""
+    p = problems.make_problem("C1", nftau=2000, Nmeas=60, **extra)
+    p.u_matrix[...] = 0.0
+    p.muimp[...] = 0.0
+    eng = cuda_engine_factory(p, nchains=4096, nbins=32, scheduler=scheduler)
+    eng.ctqmc_warmup(6000)
+    eng.ctqmc_measure(1, 1)
+    assert eng.scalar("error_flags") == 0
+    eps, v, beta = p.eps_bath, p.v_bath, p.beta
+    n = len(eps) + 1
+    h = np.zeros((n, n)); h[0, 1:] = v; h[1:, 0] = v; h[np.arange(1, n), np.arange(1, n)] = eps
+    w, u = np.linalg.eigh(h)
+    tau = (np.arange(1000) + 0.5) * beta / 1000
+    gex = ((u[0] ** 2)[None, :] * np.exp(-tau[:, None] * w[None, :]) / (1.0 + np.exp(-beta * w[None, :]))).sum(1).reshape(50, 20).mean(1)
+    bins = eng.bins("gtau").reshape(32, 2, 50, 20).mean(3)
+    g, err = bins.mean(0), bins.std(0, ddof=1) / np.sqrt(32.0)
+    z = (g - gex[None, :]) / np.sqrt(err ** 2 + (2e-4) ** 2)
+    print("U=0 %s scheduler %d: max |z| %.2f, mean z^2 %.2f, relative error bar %.1e" % (extra, scheduler, np.abs(z).max(), (z ** 2).mean(), (err / g).mean()))
+    assert np.abs(z).max() < 5.0 and (z ** 2).mean() < 2.5
+    assert (err / g).mean() < 1e-2                                   # the comparison has teeth: better than one per cent
+    if "Percentage4OperatorMove" in extra:
+        assert 0.0 < float(eng.accadd4) < 0.2 and abs(float(eng.accadd4) - float(eng.accrem4)) < 0.01     # balance of the two directions
+    eng.dest_ctqmc()
+
+
 def test_statistical_agreement(cuda_engine_factory):
     """C1 at BASELINE parameters: 2048 chains on the GPU vs one long oracle chain."""
     p = problems.make_problem("C1", Nmeas=200)
