@@ -130,6 +130,64 @@ def test_noninteracting_exact(cuda_engine_factory, extra, scheduler):
     eng.dest_ctqmc()
 
 
+def _fock_operators(nf):
+    """c_i as dense matrices on the 2^nf-dimensional Fock space (bit i = flavour i occupied; sign = parity of the occupied bits below)."""
+    dim = 1 << nf
+    ops = []
+    for i in range(nf):
+        c = np.zeros((dim, dim))
+        for st in range(dim):
+            if st >> i & 1:
+                c[st & ~(1 << i), st] = (-1.0) ** bin(st & ((1 << i) - 1)).count("1")
+        ops.append(c)
+    return ops
+
+
+@pytest.mark.parametrize("cfg", ["C3", "C4"])
+def test_atomic_limit_exact(cuda_engine_factory, cfg):
+    """F -> 0 (no hybridisation): the expansion order stays 0 and <n_i n_j> must equal the thermal expectation values of the atomic
+    Hamiltonian  H = sum_ij muimp_ij c+_i c_j + 1/2 sum U_ijkl c+_i c+_j c_l c_k  -- computed here by exact diagonalisation in the
+    full Fock space (64 / 1024 states) with nothing but numpy, no oracle: pins the engine's own eigen-decomposition and block
+    structure (atomic.hpp), the empty-trace weights, the beta/2 density-matrix estimator and the occupation post-processing."""
+    p = problems.make_problem(cfg, nftau=100, Nmeas=20)
+    p.ftau[...] = 1e-300                                              # strictly positive but negligible: no pair is ever accepted
+    nb, nf = p.nbands, 2 * p.nbands
+    eng = cuda_engine_factory(p, nchains=16384, nbins=32)
+    eng.ctqmc_warmup(1000)
+    eng.ctqmc_measure(1, 1)
+    assert eng.scalar("error_flags") == 0 and eng.scalar("mean_order") == 0.0
+    # flavour index of (band b, spin s): 2 b + s  (Operator.F90:1042-1168; the u_matrix and muimp index convention)
+    c = _fock_operators(nf)
+    cd = [m.T for m in c]
+    u = np.asarray(p.u_matrix).reshape((nf,) * 4)
+    mu = np.asarray(p.muimp).reshape(nf, nf)
+    h = np.zeros((1 << nf, 1 << nf))
+    for i in range(nf):
+        for j in range(nf):
+            if mu[i, j] != 0.0:
+                h += mu[i, j] * cd[i] @ c[j]
+    nz = np.argwhere(np.abs(u) > 1e-14)
+    pair = {}
+    for i, j, k, l in nz:
+        key = (k, l)
+        if key not in pair:
+            pair[key] = c[l] @ c[k]
+        h += 0.5 * u[i, j, k, l] * (cd[i] @ cd[j] @ pair[key])
+    assert np.abs(h - h.T).max() < 1e-12
+    w, v = np.linalg.eigh(h)
+    bw = np.exp(-(w - w.min()) * p.beta); bw /= bw.sum()
+    rho = (v * bw[None, :]) @ v.T
+    n = [cd[i] @ c[i] for i in range(nf)]
+    occ_exact = np.array([[np.trace(rho @ n[i] @ n[j]) for j in range(nf)] for i in range(nf)]).reshape(nb, 2, nb, 2)
+    bins = eng.bins("occ")
+    occ, err = eng.occ, bins.std(0, ddof=1) / np.sqrt(bins.shape[0])
+    z = (occ - occ_exact) / np.sqrt(err ** 2 + (1e-4) ** 2)
+    print("%s atomic limit: max |z| %.2f, mean z^2 %.2f over %d occupation correlators, error bar %.1e" % (cfg, np.abs(z).max(), (z ** 2).mean(), z.size, err.mean()))
+    assert np.abs(z).max() < 5.0 and (z ** 2).mean() < 2.5
+    assert err.mean() < 0.01
+    eng.dest_ctqmc()
+
+
 def test_statistical_agreement(cuda_engine_factory):
     """C1 at BASELINE parameters: 2048 chains on the GPU vs one long oracle chain."""
     p = problems.make_problem("C1", Nmeas=200)
