@@ -1,0 +1,118 @@
+"""Exact reference for small Anderson impurity models (test infrastructure; numpy / scipy only, no oracle, no engine code):
+the impurity of one of the named configurations coupled to a bath of n_bath levels per flavour, diagonalised densely in the full
+Fock space of impurity + bath.  Gives G(tau) = <c_f(tau) c_f^+(0)> and <n_i n_j> at inverse temperature beta -- the answer a CT-HYB
+run of the same model has to reproduce inside its error bars, for ANY interaction (Kanamori spin-flip / pair-hopping included)."""
+import numpy as np
+import scipy.sparse as sp
+
+from w2dynamics_b200 import problems
+
+
+def small_bath_problem(cfg, n_bath, beta, nftau=2001, **qmc):
+    """The named configuration's impurity (same U-matrix, mu, quantum numbers) with a Bethe bath of n_bath levels per flavour."""
+    p = problems.make_problem(cfg, nftau=nftau, beta=beta, **qmc)
+    eps, v = problems.bethe_bath(n_bath)
+    f = problems.hybr_tau(eps, v, beta, nftau)
+    p.ftau[...] = 0.0
+    for b in range(p.nbands):
+        for s in range(2):
+            p.ftau[b, s, b, s, :] = f
+    p.eps_bath, p.v_bath = eps, v
+    return p
+
+
+def kanamori2_problem(n_bath, beta, jj=0.6, nftau=2001, **qmc):
+    """Two orbitals with the full Kanamori interaction (spin flip and pair hopping, 2 x 2 blocks -> the blocked trace path) at half
+    filling.  NOTE on the bath: with ONE level per flavour the bath can hold one electron per flavour, so every configuration whose
+    flavour-f operators do not alternate has zero weight although its local trace is finite for J != 0 -- the pair / 4-operator
+    moves are then NOT ergodic (measured: G(tau -> 0) 1.6 % low at J = 0.6, 2.5 % at J = 1.2, with <k> and all occupations exact);
+    two levels per flavour remove that and the same chains agree with the exact result.  Use n_bath >= 2 for J != 0."""
+    u, v = 4.0, 2.8
+    mu = 0.5 * (u + (2 * v - jj))
+    q = {"TaudiffMax": min(4.0, beta)}
+    q.update(qmc)
+    p = problems._assemble("K2", 2, beta, "Kanamori", "Nt Szt Qzt", problems.u_kanamori(2, u, v, jj), mu, n_bath, q, nftau)
+    eps, vb = problems.bethe_bath(n_bath)
+    f = problems.hybr_tau(eps, vb, beta, nftau)
+    p.ftau[...] = 0.0
+    for b in range(2):
+        for s in range(2):
+            p.ftau[b, s, b, s, :] = f
+    p.eps_bath, p.v_bath = eps, vb
+    return p
+
+
+_CACHE = {}
+
+
+def solve_cached(key, p, **kw):
+    if key not in _CACHE:
+        _CACHE[key] = solve(p, **kw)
+    return _CACHE[key]
+
+
+def _annihilators(nmodes):
+    dim = 1 << nmodes
+    st = np.arange(dim)
+    ops = []
+    for i in range(nmodes):
+        occ = (st >> i) & 1
+        src = st[occ == 1]
+        par = np.zeros(src.size, dtype=np.int64)
+        for j in range(i):
+            par += (src >> j) & 1
+        ops.append(sp.csr_matrix(((-1.0) ** par, (src & ~(1 << i), src)), shape=(dim, dim)))
+    return ops
+
+
+def solve(p, nbins=50, flavours=(0,)):
+    """Returns (gbin[len(flavours), nbins] = EXACT averages of G(tau) over nbins equal tau bins, occ[nb,2,nb,2]).  Mode index: impurity
+    flavour i = 2 b + s -> i; bath level q of flavour i -> nf + i * n_bath + q."""
+    nb, nf, beta = p.nbands, 2 * p.nbands, p.beta
+    eps, v = np.asarray(p.eps_bath), np.asarray(p.v_bath)
+    nbath = eps.size
+    nm = nf * (1 + nbath)
+    c = _annihilators(nm)
+    cd = [m.T.tocsr() for m in c]
+    u = np.asarray(p.u_matrix).reshape((nf,) * 4)
+    mu = np.asarray(p.muimp).reshape(nf, nf)
+    h = sp.csr_matrix((1 << nm, 1 << nm))
+    for i in range(nf):
+        for j in range(nf):
+            if mu[i, j] != 0.0:
+                h = h + mu[i, j] * (cd[i] @ c[j])
+    pair = {}
+    for i, j, k, l in np.argwhere(np.abs(u) > 1e-14):
+        if (k, l) not in pair:
+            pair[(k, l)] = c[l] @ c[k]
+        h = h + 0.5 * u[i, j, k, l] * (cd[i] @ cd[j] @ pair[(k, l)])
+    for i in range(nf):
+        for q in range(nbath):
+            m = nf + i * nbath + q
+            h = h + eps[q] * (cd[m] @ c[m]) + v[q] * (cd[i] @ c[m] + cd[m] @ c[i])
+    hd = h.toarray()
+    assert np.abs(hd - hd.T).max() < 1e-12
+    w, vec = np.linalg.eigh(hd)
+    w -= w.min()
+    bw = np.exp(-beta * w)
+    z = bw.sum()
+    edges = np.linspace(0.0, beta, nbins + 1)
+    g = np.zeros((len(flavours), nbins))
+    for a, f in enumerate(flavours):
+        m2 = (vec.T @ (cd[f] @ vec)) ** 2                             # |<m| c_f^+ |n>|^2
+        # G(tau) = 1/Z sum_nm |<m|c+|n>|^2 exp(-(beta - tau) E_n - tau E_m): at tau -> beta the FINAL state's thermal weight counts
+        im, in_ = np.nonzero((m2 > 1e-15) & (np.maximum(bw[:, None], bw[None, :]) / z > 1e-13))
+        mm, em, en = m2[im, in_], w[im], w[in_]
+        de = em - en
+        small = np.abs(de) < 1e-9
+        for ib in range(nbins):                                       # exact bin average; every exponent is <= 0
+            t1, t2 = edges[ib], edges[ib + 1]
+            e1, e2 = np.exp(-(beta - t1) * en - t1 * em), np.exp(-(beta - t2) * en - t2 * em)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                avg = np.where(small, e1, (e1 - e2) / (de * (t2 - t1)))
+            g[a, ib] = (mm * avg).sum() / z
+    keep = bw / z > 1e-14
+    rho_diag = ((vec[:, keep] ** 2) @ bw[keep]) / z                   # thermal weight of every occupation-number state
+    st = np.arange(1 << nm)
+    occ = np.array([[(rho_diag * ((st >> i) & 1) * ((st >> j) & 1)).sum() for j in range(nf)] for i in range(nf)])
+    return g, occ.reshape(nb, 2, nb, 2)
