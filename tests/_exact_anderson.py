@@ -65,9 +65,11 @@ def _annihilators(nmodes):
     return ops
 
 
-def solve(p, nbins=50, flavours=(0,)):
-    """Returns (gbin[len(flavours), nbins] = EXACT averages of G(tau) over nbins equal tau bins, occ[nb,2,nb,2]).  Mode index: impurity
+def solve(p, nbins=50, flavours=(0,), nleg=12):
+    """Returns (gbin[len(flavours), nbins] = EXACT averages of G(tau) over nbins equal tau bins, occ[nb,2,nb,2],
+    gleg[len(flavours), nleg] = sqrt(2l+1) int_0^beta P_l(2 tau / beta - 1) G(tau) dtau in closed form).  Mode index: impurity
     flavour i = 2 b + s -> i; bath level q of flavour i -> nf + i * n_bath + q."""
+    from scipy.special import ive
     nb, nf, beta = p.nbands, 2 * p.nbands, p.beta
     eps, v = np.asarray(p.eps_bath), np.asarray(p.v_bath)
     nbath = eps.size
@@ -98,6 +100,7 @@ def solve(p, nbins=50, flavours=(0,)):
     z = bw.sum()
     edges = np.linspace(0.0, beta, nbins + 1)
     g = np.zeros((len(flavours), nbins))
+    gleg = np.zeros((len(flavours), nleg))
     for a, f in enumerate(flavours):
         m2 = (vec.T @ (cd[f] @ vec)) ** 2                             # |<m| c_f^+ |n>|^2
         # G(tau) = 1/Z sum_nm |<m|c+|n>|^2 exp(-(beta - tau) E_n - tau E_m): at tau -> beta the FINAL state's thermal weight counts
@@ -111,8 +114,16 @@ def solve(p, nbins=50, flavours=(0,)):
             with np.errstate(divide="ignore", invalid="ignore"):
                 avg = np.where(small, e1, (e1 - e2) / (de * (t2 - t1)))
             g[a, ib] = (mm * avg).sum() / z
+        # Legendre coefficients: int_0^beta P_l(x) exp(-(beta - tau) E_n - tau E_m) dtau = beta (-1)^l i_l(a) exp(-beta (E_n + E_m) / 2),
+        # a = beta (E_m - E_n) / 2, i_l = modified spherical Bessel function of the first kind (exponentially scaled for stability)
+        aa = 0.5 * beta * de
+        pref = mm * np.exp(-0.5 * beta * (en + em) + np.abs(aa)) / z          # exp(-beta min(E_n, E_m)) <= 1
+        for l in range(nleg):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                il = np.where(np.abs(aa) < 1e-12, 1.0 if l == 0 else 0.0, np.sqrt(np.pi / (2.0 * np.abs(aa))) * ive(l + 0.5, np.abs(aa)) * np.sign(aa) ** l)
+            gleg[a, l] = np.sqrt(2 * l + 1.0) * beta * (-1.0) ** l * (pref * il).sum()
     keep = bw / z > 1e-14
     rho_diag = ((vec[:, keep] ** 2) @ bw[keep]) / z                   # thermal weight of every occupation-number state
     st = np.arange(1 << nm)
     occ = np.array([[(rho_diag * ((st >> i) & 1) * ((st >> j) & 1)).sum() for j in range(nf)] for i in range(nf)])
-    return g, occ.reshape(nb, 2, nb, 2)
+    return g, occ.reshape(nb, 2, nb, 2), gleg

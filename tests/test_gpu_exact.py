@@ -1,6 +1,7 @@
 """The CUDA engine against EXACT results of interacting Anderson impurity models (no oracle involved): the impurity of a named
 configuration coupled to one to three bath levels per flavour is diagonalised densely in the full Fock space of impurity + bath
-(tests/_exact_anderson.py, numpy only); G(tau) in 50 tau bins (exact bin averages) and all <n_i n_j> must lie inside the engine's own
+(tests/_exact_anderson.py, numpy only); G(tau) in 50 tau bins (exact bin averages), the Legendre coefficients l < 12 (closed form) and
+all <n_i n_j> must lie inside the engine's own
 chain-group error bars.  This pins the whole hot path -- proposals, window, quantum-number walk, determinant fast updates, local
 trace (1x1 blocks AND the blocked DMMA path: two-orbital Kanamori model with spin-flip / pair-hopping terms), signs, G(tau) and density-matrix
 estimators, normalisation -- to something that is not a restatement of the reference by the same author.  The optional move types
@@ -27,7 +28,7 @@ def test_engine_against_exact_diagonalisation(cuda_engine_factory, cfg, nbath, b
         p = ea.kanamori2_problem(nbath, beta, Nmeas=100, Ntau=1000, **extra)
     else:
         p = ea.small_bath_problem(cfg, nbath, beta, Nmeas=100, Ntau=1000, **extra)
-    gex, occ_ex = ea.solve_cached((cfg, nbath, beta), p)             # flavour 0; all flavours are equivalent in these models
+    gex, occ_ex, gl_ex = ea.solve_cached((cfg, nbath, beta), p)      # flavour 0; all flavours are equivalent in these models
     eng = cuda_engine_factory(p, nchains=4096, nbins=32, scheduler=scheduler)
     eng.ctqmc_warmup(6000)
     eng.ctqmc_measure(1, 1)
@@ -37,9 +38,12 @@ def test_engine_against_exact_diagonalisation(cuda_engine_factory, cfg, nbath, b
     g, gerr = gb.mean(0), gb.std(0, ddof=1) / np.sqrt(32.0)
     ob = eng.bins("occ")
     occ, oerr = ob.mean(0), ob.std(0, ddof=1) / np.sqrt(32.0)
+    lb = eng.bins("gleg").reshape(32, 2 * nb, -1).mean(1)[:, :12]                # Legendre coefficients l < 12, flavour average
+    gl, glerr = lb.mean(0), lb.std(0, ddof=1) / np.sqrt(32.0)
     zg = (g - gex[0]) / np.sqrt(gerr ** 2 + (1e-4) ** 2)
     zo = ((occ - occ_ex) / np.sqrt(oerr ** 2 + (1e-4) ** 2)).ravel()
-    z = np.concatenate([zg, zo])
+    zl = (gl - gl_ex[0]) / np.sqrt(glerr ** 2 + (1e-4) ** 2)
+    z = np.concatenate([zg, zo, zl])
     print("%s + %d bath levels, beta = %g, %s: %d values, max |z| %.2f, mean z^2 %.2f; relative G error bar %.1e; <k> %.2f; sign %.4f"
           % (cfg, nbath, beta, extra or "pair moves", z.size, np.abs(z).max(), (z ** 2).mean(), (gerr / g).mean(), eng.scalar("mean_order"), float(eng.mean_sign)))
     assert np.abs(z).max() < 5.0 and (z ** 2).mean() < 2.5
