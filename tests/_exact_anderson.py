@@ -65,7 +65,7 @@ def _annihilators(nmodes):
     return ops
 
 
-def solve(p, nbins=50, flavours=(0,), nleg=12):
+def solve(p, nbins=50, flavours=(0,), nleg=12, want_rho=False):
     """Returns (gbin[len(flavours), nbins] = EXACT averages of G(tau) over nbins equal tau bins, occ[nb,2,nb,2],
     gleg[len(flavours), nleg] = sqrt(2l+1) int_0^beta P_l(2 tau / beta - 1) G(tau) dtau in closed form).  Mode index: impurity
     flavour i = 2 b + s -> i; bath level q of flavour i -> nf + i * n_bath + q."""
@@ -126,4 +126,23 @@ def solve(p, nbins=50, flavours=(0,), nleg=12):
     rho_diag = ((vec[:, keep] ** 2) @ bw[keep]) / z                   # thermal weight of every occupation-number state
     st = np.arange(1 << nm)
     occ = np.array([[(rho_diag * ((st >> i) & 1) * ((st >> j) & 1)).sum() for j in range(nf)] for i in range(nf)])
-    return g, occ.reshape(nb, 2, nb, 2), gleg
+    if not want_rho:
+        return g, occ.reshape(nb, 2, nb, 2), gleg
+    # one- and two-particle reduced density matrices of the impurity: rho1[i, j] = <c+_i c_j>,
+    # rho2[i, j, k, l] = <c+_i c+_j c_k c_l>  (Meas_rho1 / rho2_from_Densitymatrix, CTQMC.F90:2884-3017: rho2(f4, f3, f2, f1) = Tr[rho c+_4 c+_3 c_2 c_1])
+    vk, wk = vec[:, keep], bw[keep] / z
+
+    def expect(op):
+        return float((((op @ vk) * vk).sum(0) * wk).sum())
+    rho1 = np.array([[expect(cd[i] @ c[j]) for j in range(nf)] for i in range(nf)])
+    rho2 = np.zeros((nf,) * 4)
+    for k in range(nf):
+        for l in range(nf):
+            if k == l:
+                continue
+            ckl = c[k] @ c[l]
+            for i in range(nf):
+                for j in range(nf):
+                    if i != j:
+                        rho2[i, j, k, l] = expect(cd[i] @ cd[j] @ ckl)
+    return g, occ.reshape(nb, 2, nb, 2), gleg, rho1, rho2

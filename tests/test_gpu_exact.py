@@ -48,4 +48,15 @@ def test_engine_against_exact_diagonalisation(cuda_engine_factory, cfg, nbath, b
           % (cfg, nbath, beta, extra or "pair moves", z.size, np.abs(z).max(), (z ** 2).mean(), (gerr / g).mean(), eng.scalar("mean_order"), float(eng.mean_sign)))
     assert np.abs(z).max() < 5.0 and (z ** 2).mean() < 2.5
     assert (gerr / g).mean() < 0.02                                  # the comparison has teeth
+    if cfg == "K2":
+        # reduced density matrices incl. the spin-flip / pair-hopping elements of rho2 (index convention of Meas_rho2_from_Densitymatrix,
+        # CTQMC.F90:2945-3017).  The library keeps no per-group samples of rho2; its elements are linear in the same density matrix
+        # as occ, so the largest occ error bar sets the scale.
+        _, _, _, r1_ex, r2_ex = ea.solve_cached((cfg, nbath, beta, "rho"), p, want_rho=True)
+        nf = 2 * nb
+        d1 = np.abs(np.asarray(eng.rho1).reshape(nf, nf) - r1_ex).max()
+        d2 = np.abs(np.asarray(eng.rho2).reshape((nf,) * 4) - r2_ex).max()
+        tol = 6.0 * oerr.max() + 2e-4
+        print("  rho1 max deviation %.2e, rho2 max deviation %.2e over %d non-zero elements (tolerance %.2e)" % (d1, d2, (np.abs(r2_ex) > 1e-3).sum(), tol))
+        assert d1 < tol and d2 < tol
     eng.dest_ctqmc()
