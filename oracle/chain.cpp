@@ -112,6 +112,7 @@ struct Chain {
     std::vector<std::vector<double>> M;            // per flavour f=b*2+s: k x k, column-major M(i,j)=M[i+j*k], i=creator idx
     std::vector<int> kf;
     int outer_sst = 0, window_position = 0, num_windows = 1;
+    bool statesampling = false; int outer_state = 0;   // statesampling = 1: ONE outer eigenstate (0-based inside outer_sst) instead of the sum over the superstate
     double tauwin_min = 0, tauwin_max = 1;
     LogVal Trace{0, 1}, Det{0, 1};
     double cfgsign = -1;
@@ -211,7 +212,8 @@ struct Chain {
         if (mv > 0) for (int i = 0; i < n; ++i) v[i] /= mv;
         lf += std::log(mv);
     }
-    LogVal trace_full(const std::vector<Op>& o, int outer, std::vector<LogVal>* parts) const {
+    // only >= 0 (state sampling, louter_sst_size = 1 Trace.F90:5759-5764): the contribution of that single outer eigenstate
+    LogVal trace_full(const std::vector<Op>& o, int outer, std::vector<LogVal>* parts, int only = -1) const {
         LogVal tot{-HUGE_D, 0.0};
         int m = T.dim[outer];
         if (parts) parts->assign(m, LogVal{-HUGE_D, 0.0});
@@ -231,7 +233,7 @@ struct Chain {
             return tot;
         }
         std::vector<double> kt(T.dmax), ktp(T.dmax);
-        for (int j = 0; j < m; ++j) {                           // StateLoop 5765
+        for (int j = (only >= 0 ? only : 0); j < (only >= 0 ? only + 1 : m); ++j) {                           // StateLoop 5765
             int sst = outer, ns_sst = m; double lg = 0, tauR = 0;
             std::fill(kt.begin(), kt.end(), 0.0); kt[j] = 1.0;
             bool dead = false;
@@ -511,6 +513,7 @@ struct Chain {
     }
     // trace of a pair-move proposal: old operators [s, e) replaced (operators changed inside the window only)
     LogVal trace_pair(const std::vector<Op>& o, int outer, std::vector<LogVal>* parts, int s, int e) {
+        if (statesampling) return trace_full(o, outer, parts, outer_state);
         if (fast_trace == 2 && T.dmax > 1) return trace_cached(o, outer, s, e, parts);
         if (fast_trace == 1 && T.dmax > 1 && num_windows > 1) return trace_windowed(o, outer, parts);
         return trace_full(o, outer, parts);
@@ -616,6 +619,28 @@ struct Chain {
         int r = 0; for (const Op& e : o) if (e.b == b && e.s == s && e.ca == ca && e.tau < tau) ++r; return r + 1;
     }
 
+    // WeightedOuterStateChoice Trace.F90:1477-1604 (state sampling; no outer truncation: every superstate keeps all its states).
+    // Picks the new outer (superstate, eigenstate) among the superstates of `news` with probability ~ exp(-tau_new (E - Egs)) and
+    // returns p_prop(new -> old) / p_prop(old -> new); entries < 0 are skipped; one random number, none when nothing can be chosen.
+    double outer_tau(const std::vector<Op>& o) const { return o.empty() ? beta : beta - o.back().tau + o.front().tau; }
+    double wosc(double tau_old, double tau_new, int sst_old, int state_old, const std::vector<int>& olds, const std::vector<int>& news,
+                int& sst_new, int& state_new) {
+        double tw = 0;
+        for (int q : olds) if (q >= 0) for (int j = 0; j < T.dim[q]; ++j) tw += std::exp(-tau_old * (T.evals[T.offset[q] + j] - T.egs));
+        double res = std::exp(-tau_old * (T.evals[T.offset[sst_old] + state_old] - T.egs)) / tw;
+        sst_new = sst_old; state_new = state_old;
+        double tot = 0; bool any = false;
+        for (int q : news) if (q >= 0) for (int j = 0; j < T.dim[q]; ++j) { tot += std::exp(-tau_new * (T.evals[T.offset[q] + j] - T.egs)); any = true; }
+        if (!any || tot <= 0.0) return 0.0;
+        double rand = grnd() * tot, acc = 0;
+        for (int q : news) if (q >= 0) for (int j = 0; j < T.dim[q]; ++j) {
+            double w = std::exp(-tau_new * (T.evals[T.offset[q] + j] - T.egs));
+            acc += w;
+            if (rand <= acc && w != 0.0) { sst_new = q; state_new = j; return res * (tot / w); }
+        }
+        return 0.0;
+    }
+
     // change_outer (PercentageOuterMove, CTQMC.F90:3422-3449 / 3934-3961): the superstates BETWEEN the two operators are kept and
     // the part of the sequence that runs from the later operator over beta to the earlier one is re-walked; the superstate it
     // passes tau = beta with becomes the outer superstate (check_sst_sequence Trace.F90:1278-1295), and the local trace is
@@ -671,6 +696,9 @@ struct Chain {
             if (cur >= 0) cur = T.conn(cur, o1.b, o1.s, o1.ca);
             if (cur < 0 || cur != s_a) { C.AccQNAdd += 1; log_end(2); return; }
         }
+        // state sampling: the new outer eigenstate is drawn inside the new outer superstate (CTQMC.F90:3471-3480)
+        double osf = 1.0; int new_state = outer_state;
+        if (statesampling && outer) osf = wosc(outer_tau(ops), outer_tau(nw), outer_sst, outer_state, {outer_sst}, {new_outer}, new_outer, new_state);
         // get_LogDetRatPairAdd Trace.F90:2775-2832 + get_DetRatAdd MatrixUpdate.F90:392-407
         int f = b * 2 + s, k = kf[f];
         std::vector<double> Q(k), R(k);
@@ -686,11 +714,12 @@ struct Chain {
         LogVal DetRat{std::log(std::fabs(S)), sgn(S) * sig};
         LogVal DetNew = lmul(DetRat, Det);
         std::vector<LogVal> parts;
-        LogVal TraceNew = outer ? trace_full(nw, new_outer, &parts) : trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2);
+        LogVal TraceNew = outer ? trace_full(nw, new_outer, &parts, statesampling ? new_state : -1) : trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2);
         double rand = grnd();
         int NPairs = count_pairs(nw);
         LogVal trr = ldiv(TraceNew, Trace);
-        double prob = std::fabs(taudiff_factor * (double)(2 * nb) / (double)NPairs * std::exp(trr.log + DetRat.log));
+        double prob = std::fabs(osf * taudiff_factor * (double)(2 * nb) / (double)NPairs * std::exp(trr.log + DetRat.log));
+        if (osf == 0.0) { trr = LogVal{0.0, 0.0}; prob = 0.0; }      // no outer state could be chosen: rejected whatever the trace
         rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[14] = NPairs; rec[17] = rand;
         if (rand < prob) {
             // get_MatAdd MatrixUpdate.F90:410-442
@@ -706,7 +735,7 @@ struct Chain {
                     N[in + (size_t)jn * kn] = Mf[i + (size_t)j * k] + S * N[in + (size_t)p2 * kn] * N[p1 + (size_t)jn * kn]; } }
             M[f].swap(N); kf[f] = kn;
             ops.swap(nw);
-            if (outer) { outer_sst = new_outer; ec.valid = false; fc.valid = false; }
+            if (outer) { outer_sst = new_outer; outer_state = new_state; ec.valid = false; fc.valid = false; }
             else if (fast_trace == 2) fc_accept((int)i1, (int)i2, (int)(i2 - i1) + 2);
             Det = DetNew; Trace = TraceNew; parttrace = parts;
             cfgsign = -get_sign(ops, Trace, Det);
@@ -764,6 +793,8 @@ struct Chain {
             for (size_t i = 0; i < i1 && cur >= 0; ++i) cur = T.conn(cur, ops[i].b, ops[i].s, ops[i].ca);
             if (cur < 0 || cur != after[i1]) { C.AccQNRem += 1; log_end(2); return; }
         }
+        double osf = 1.0; int new_state = outer_state;                  // state sampling, CTQMC.F90:3979-3988
+        if (statesampling && outer) osf = wosc(outer_tau(ops), outer_tau(nw), outer_sst, outer_state, {outer_sst}, {new_outer}, new_outer, new_state);
         // get_LogDetRatPairRem Trace.F90:2937-2963, get_DetRatRem MatrixUpdate.F90:445-452
         int k = kf[f];
         const std::vector<double>& Mf = M[f];
@@ -773,9 +804,10 @@ struct Chain {
         LogVal DetRat{std::log(std::fabs(S)), sgn(S) * sig};
         LogVal DetNew = lmul(DetRat, Det);
         std::vector<LogVal> parts;
-        LogVal TraceNew = outer ? trace_full(nw, new_outer, &parts) : trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2 + 1);
+        LogVal TraceNew = outer ? trace_full(nw, new_outer, &parts, statesampling ? new_state : -1) : trace_pair(nw, outer_sst, &parts, (int)i1, (int)i2 + 1);
         LogVal trr = ldiv(TraceNew, Trace);
-        double prob = std::fabs(factor / (double)(2 * nb) * std::exp(trr.log + DetRat.log));
+        double prob = std::fabs(osf * factor / (double)(2 * nb) * std::exp(trr.log + DetRat.log));
+        if (osf == 0.0) { trr = LogVal{0.0, 0.0}; prob = 0.0; }
         double rand = grnd();
         rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[17] = rand;
         if (rand < prob) {
@@ -788,7 +820,7 @@ struct Chain {
                     N[i + (size_t)j * kn] = Mf[io + (size_t)jo * k] - Mf[io + (size_t)p2 * k] * Mf[p1 + (size_t)jo * k] / Mf[p1 + (size_t)p2 * k]; } }
             M[f].swap(N); kf[f] = kn;
             ops.swap(nw);
-            if (outer) { outer_sst = new_outer; ec.valid = false; fc.valid = false; }
+            if (outer) { outer_sst = new_outer; outer_state = new_state; ec.valid = false; fc.valid = false; }
             else if (fast_trace == 2) fc_accept((int)i1, (int)i2 + 1, (int)(i2 - i1) - 1);
             Det = DetNew; Trace = TraceNew; parttrace = parts;
             cfgsign = -get_sign(ops, Trace, Det);
@@ -841,7 +873,7 @@ struct Chain {
         for (int f = 0; f < nf; ++f) if (kf[f] > 0) DetOld = lmul(mat_logdet(M[f], kf[f]), DetOld);
         LogVal DetRat = lmul(DetNew, DetOld);
         std::vector<LogVal> parts;
-        LogVal TraceNew = trace_full(nw, outer_sst, &parts);
+        LogVal TraceNew = trace_full(nw, outer_sst, &parts, statesampling ? outer_state : -1);
         LogVal trr = ldiv(TraceNew, Trace);
         double rand = grnd();
         double prob = std::fabs(factor * std::exp(trr.log + DetRat.log));
@@ -956,7 +988,7 @@ struct Chain {
         // globalUpdate Trace.F90:2126-2188: flavour index i-1 = b + nb*s
         std::vector<Op> nw = ops;
         for (Op& e : nw) { int i = e.b + nb * e.s + 1; int g = gu[i]; e.b = (g - 1) % nb; e.s = (g - 1) / nb; if (gu[0] != 0) e.ca = 3 - e.ca; }
-        double factor = 0; int new_outer = outer_sst;
+        double factor = 0; int new_outer = outer_sst, new_state = outer_state;
         std::vector<int> after;
         if (type == 3 && has_szt) {                  // perform_spinflip_check_qn 1306-1339
             int st = T.first_state[outer_sst];
@@ -964,12 +996,17 @@ struct Chain {
             int ns = up | (dn << nb);
             new_outer = T.state2sst[ns];
             factor = sst_sequence(nw, new_outer, after) ? 1.0 : 0.0;
+            if (factor != 0.0 && statesampling) {    // Trace.F90:1325-1332
+                const int cand = new_outer;
+                factor = wosc(outer_tau(ops), outer_tau(ops), outer_sst, outer_state, {outer_sst}, {cand}, new_outer, new_state);
+            }
         } else {                                     // perform_global_check_qn 1345-1394
             std::vector<int> so, sn;
             int pold = compatible_ssts(ops, so);
             if (pold <= 0) { error = 3; log_end(2); return; }
             int pnew = compatible_ssts(nw, sn);
-            if (pnew > 0) {
+            if (pnew > 0 && statesampling) factor = wosc(outer_tau(ops), outer_tau(ops), outer_sst, outer_state, so, sn, new_outer, new_state);   // Trace.F90:1372-1379
+            else if (pnew > 0) {
                 factor = (double)pnew / (double)pold;
                 int kk = randint(1, pnew);
                 for (int i = 0; i < T.nsst; ++i) if (sn[i] != -1) { if (--kk <= 0) { new_outer = sn[i]; break; } }
@@ -982,20 +1019,38 @@ struct Chain {
         for (int f = 0; f < nf; ++f) if (kf[f] > 0) DetOld = lmul(mat_logdet(M[f], kf[f]), DetOld);
         LogVal DetRat = lmul(DetNew, DetOld);
         std::vector<LogVal> parts;
-        LogVal TraceNew = trace_full(nw, new_outer, &parts);
+        LogVal TraceNew = trace_full(nw, new_outer, &parts, statesampling ? new_state : -1);
         LogVal trr = ldiv(TraceNew, Trace);
         double prob = std::fabs(std::exp(trr.log + DetRat.log) * factor);
         double rand = grnd();
         rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[17] = rand;
         if (rand < prob) {
-            ops.swap(nw); M.swap(Mn); kf = kn; outer_sst = new_outer;
+            ops.swap(nw); M.swap(Mn); kf = kn; outer_sst = new_outer; outer_state = new_state;
             Det = DetNew; Trace = TraceNew; parttrace = parts; ec.valid = false; fc.valid = false;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccGlob += 1; log_end(1);
         } else log_end(0);
     }
 
-    void StepChangeOuter() {                         // CTQMC.F90:4570-4638 (no state sampling)
+    // empty-trace choice of the outer (superstate, eigenstate) with state sampling: CTQMC.F90:4580-4608 / Trace.F90:612-643
+    void choose_outer_state(double rand) {
+        std::vector<double> w; double sum = 0;
+        for (int i = 0; i < T.nsst; ++i) for (int j = 0; j < T.dim[i]; ++j) { w.push_back(lval(trace_full(ops, i, nullptr, j))); sum += w.back(); }
+        double acc = 0; size_t q = 0;
+        for (int i = 0; i < T.nsst; ++i) for (int j = 0; j < T.dim[i]; ++j, ++q) {
+            outer_sst = i; outer_state = j; acc += w[q] / sum;
+            if (acc >= rand && w[q] != 0.0) return;
+        }
+    }
+    void StepChangeOuter() {                         // CTQMC.F90:4570-4638
+        if (statesampling) {
+            double rand = grnd();
+            choose_outer_state(rand);
+            Trace = trace_full(ops, outer_sst, &parttrace, outer_state); ec.valid = false; fc.valid = false;
+            cfgsign = -get_sign(ops, Trace, Det);
+            rec[17] = rand;
+            return;
+        }
         std::vector<double> w(T.nsst);
         double sum = 0;
         for (int i = 0; i < T.nsst; ++i) { w[i] = lval(trace_full(ops, i, nullptr)); sum += w[i]; }
@@ -1025,14 +1080,16 @@ struct Chain {
         int new_outer = (first == 0) ? outer_sst : after[first - 1];
         std::vector<Op> nw; nw.reserve(n);
         for (size_t i = 0; i < n; ++i) { Op e = ops[(first + i) % n]; e.tau = std::fmod(e.tau - dt, beta); if (e.tau < 0) e.tau += beta; nw.push_back(e); }
+        double osf = 1.0; int new_state = outer_state;                  // CTQMC.F90:4702-4710
+        if (statesampling) { const int cand = new_outer; osf = wosc(outer_tau(ops), outer_tau(nw), outer_sst, outer_state, {outer_sst}, {cand}, new_outer, new_state); }
         int wp_old = window_position; double wmin_old = tauwin_min, wmax_old = tauwin_max;
         int sh = (int)std::floor((dt / beta) * (double)(num_windows + 1)) % num_windows;
         window_position = ((wp_old - sh) % num_windows + num_windows) % num_windows;
         set_window_edges();
         std::vector<LogVal> parts;
-        LogVal TraceNew = trace_full(nw, new_outer, &parts);
-        LogVal trr = ldiv(TraceNew, Trace);
-        double prob = std::fabs(lval(trr));
+        LogVal TraceNew = osf > 0.0 ? trace_full(nw, new_outer, &parts, statesampling ? new_state : -1) : LogVal{-HUGE_D, 0.0};
+        LogVal trr = osf > 0.0 ? ldiv(TraceNew, Trace) : LogVal{0.0, 0.0};
+        double prob = osf > 0.0 ? std::fabs(osf * lval(trr)) : 0.0;
         double rand = grnd();
         rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[17] = rand;
         if (rand < prob) {
@@ -1054,7 +1111,7 @@ struct Chain {
                 }
                 if ((k % 2) != 0 && ((w1 + w2) % 2) != 0) detrat = -detrat;
             }
-            ops.swap(nw); outer_sst = new_outer;
+            ops.swap(nw); outer_sst = new_outer; outer_state = new_state;
             Trace = TraceNew; parttrace = parts; Det.sign *= detrat; ec.valid = false; fc.valid = false;
             cfgsign = -get_sign(ops, Trace, Det);
             C.AccShift += 1; log_end(1);
@@ -1085,6 +1142,9 @@ struct Chain {
         meas_sign += cfgsign;                                                  // MeasSign 3343
         // MeasOuterHistograms 3285-3339
         outer_hist[outer_sst] += 1.0; sign_hist[outer_sst] += cfgsign;
+        if (statesampling) { int q = T.offset[outer_sst] + outer_state; double e = std::exp(parttrace[outer_state].log);
+          outerstate_hist[q] += 1.0; signstate_hist[q] += cfgsign; contrib_state[q] += e; contrib_sst[outer_sst] += e; }
+        else
         { int off = T.offset[outer_sst], m = T.dim[outer_sst]; double c = 0;
           for (int i = 0; i < m; ++i) { outerstate_hist[off + i] += 1.0;
               signstate_hist[off + i] += Trace.sign * parttrace[i].sign * cfgsign;
@@ -1121,12 +1181,12 @@ struct Chain {
         int m = T.dim[outer_sst];
         if (ops.empty()) {
             int off = T.offset[outer_sst];
-            for (int j = 0; j < m; ++j) dens[(size_t)(off + j) * ns + off + j] += -cfgsign * lval(ldiv(parttrace[j], Trace));
+            for (int j = (statesampling ? outer_state : 0); j < (statesampling ? outer_state + 1 : m); ++j) dens[(size_t)(off + j) * ns + off + j] += -cfgsign * lval(ldiv(parttrace[j], Trace));
             return;
         }
         double bh = beta / 2.0;
         std::vector<double> kt(T.dmax), bt(T.dmax), tmp(T.dmax);
-        for (int j = 0; j < m; ++j) {
+        for (int j = (statesampling ? outer_state : 0); j < (statesampling ? outer_state + 1 : m); ++j) {
             // ket: apply operators with tau <= beta/2
             int sst = outer_sst, nst = m; double kl = 0, tauR = 0;
             std::fill(kt.begin(), kt.end(), 0.0); kt[j] = 1.0;
@@ -1170,6 +1230,13 @@ struct Chain {
     void init_trace() {
         ops.clear(); M.assign(nf, {}); kf.assign(nf, 0);
         Det = {0, 1};
+        if (statesampling) {
+            choose_outer_state(grnd());
+            Trace = trace_full(ops, outer_sst, &parttrace, outer_state); ec.valid = false; fc.valid = false;
+            cfgsign = -1.0;
+            return;
+        }
+        outer_state = 0;
         std::vector<double> w(T.nsst); double sum = 0;
         for (int i = 0; i < T.nsst; ++i) { w[i] = lval(trace_full(ops, i, nullptr)); sum += w[i]; }
         for (double& x : w) x /= sum;
@@ -1179,12 +1246,12 @@ struct Chain {
         Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false; fc.valid = false;
         cfgsign = -1.0;                              // TTrace default (Trace.F90:129), first computed on the first accepted move
     }
-    void set_config(int n, const double* taus, const int* orbs, const int* spins, const int* cas, int osst) {
+    void set_config(int n, const double* taus, const int* orbs, const int* spins, const int* cas, int osst, int ostate = 0) {
         // set_mc_config_from_arrays Trace.F90:6872-7000
         ops.clear();
         for (int i = 0; i < n; ++i) ops.push_back(Op{taus[i], orbs[i] - 1, spins[i] - 1, cas[i]});
-        outer_sst = osst; window_position = 0; set_window_edges();
-        Trace = trace_full(ops, outer_sst, &parttrace); ec.valid = false; fc.valid = false;
+        outer_sst = osst; outer_state = statesampling ? ostate : 0; window_position = 0; set_window_edges();
+        Trace = trace_full(ops, outer_sst, &parttrace, statesampling ? outer_state : -1); ec.valid = false; fc.valid = false;
         Det = build_inverse_all(ops, M, kf);
         cfgsign = -get_sign(ops, Trace, Det);
     }
@@ -1261,6 +1328,8 @@ int orc_randint(void* h, int lo, int hi) { return ((Chain*)h)->randint(lo, hi); 
 unsigned long long orc_rng_counter(void* h) { return ((Chain*)h)->ph.ctr; }
 
 void orc_init_trace(void* h) { ((Chain*)h)->init_trace(); }
+void orc_set_statesampling(void* h, int on) { ((Chain*)h)->statesampling = on != 0; }     // before orc_init_trace
+int orc_outer_state(void* h) { return ((Chain*)h)->outer_state; }
 void orc_set_taudiffmax(void* h, double t) { ((Chain*)h)->init_window(t); }
 // SymMoveNN lists (1-based target indices b + nb s + 1); the inverses are appended as init_Trace does (Trace.F90:471-478)
 void orc_set_symmoves(void* h, int nsym, const int* moves) {
@@ -1299,8 +1368,8 @@ void orc_get_config(void* h, double* taus, int* orbs, int* spins, int* cas) {
     Chain* c = (Chain*)h;
     for (size_t i = 0; i < c->ops.size(); ++i) { taus[i] = c->ops[i].tau; orbs[i] = c->ops[i].b + 1; spins[i] = c->ops[i].s + 1; cas[i] = c->ops[i].ca; }
 }
-void orc_set_config(void* h, int n, const double* taus, const int* orbs, const int* spins, const int* cas, int outer_sst) {
-    ((Chain*)h)->set_config(n, taus, orbs, spins, cas, outer_sst);
+void orc_set_config(void* h, int n, const double* taus, const int* orbs, const int* spins, const int* cas, int outer_sst, int outer_state) {
+    ((Chain*)h)->set_config(n, taus, orbs, spins, cas, outer_sst, outer_state);
 }
 void orc_get_scalars(void* h, double* out) {   // trace log/sign, det log/sign, cfgsign, meas_sign, cnt_meas, cnt_steps
     Chain* c = (Chain*)h;

@@ -119,6 +119,7 @@ class OracleChain:
         rc = L.orc_init_rnd(self.h, C.c_int(kind), C.c_uint(seed), C.c_uint(chain), MTLIB.encode())
         if rc != 0:
             raise RuntimeError("oracle RNG init failed (%d); libmtrng.so missing?" % rc)
+        L.orc_set_statesampling(self.h, C.c_int(int(q.get("statesampling", 0))))        # before the first outer-state choice
         L.orc_init_trace(self.h)
         if q["TaudiffMax"] > 0:
             L.orc_set_taudiffmax(self.h, C.c_double(q["TaudiffMax"]))
@@ -178,16 +179,16 @@ class OracleChain:
         cas = np.zeros(n, dtype=np.int32)
         if n:
             L.orc_get_config(self.h, _p(taus, C.c_double), _p(orbs, C.c_int), _p(spins, C.c_int), _p(cas, C.c_int))
-        return dict(taus=taus, orbs=orbs, spins=spins, cas=cas, outer_sst=L.orc_outer_sst(self.h),
+        return dict(taus=taus, orbs=orbs, spins=spins, cas=cas, outer_sst=L.orc_outer_sst(self.h), outer_state=L.orc_outer_state(self.h) + 1,
                     window_position=L.orc_window_position(self.h))
 
-    def set_config(self, taus, orbs, spins, cas, outer_sst):
+    def set_config(self, taus, orbs, spins, cas, outer_sst, outer_state=1):
         taus = np.ascontiguousarray(taus, dtype=np.float64)
         orbs = np.ascontiguousarray(orbs, dtype=np.int32)
         spins = np.ascontiguousarray(spins, dtype=np.int32)
         cas = np.ascontiguousarray(cas, dtype=np.int32)
         lib().orc_set_config(self.h, C.c_int(len(taus)), _p(taus, C.c_double), _p(orbs, C.c_int),
-                             _p(spins, C.c_int), _p(cas, C.c_int), C.c_int(outer_sst))
+                             _p(spins, C.c_int), _p(cas, C.c_int), C.c_int(outer_sst), C.c_int(int(outer_state) - 1))
 
     def scalars(self):
         out = np.zeros(8)
