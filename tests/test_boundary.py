@@ -147,7 +147,7 @@ def body_validation(make):
         eng.set_mc_config(2, t[::-1].copy(), o, s, ca, h, 0, 1)
     eng.dest_ctqmc()
     # what is outside the implemented path is refused by name, never approximated
-    for key, val in (("statesampling", 1), ("offdiag", 1), ("segment", 1), ("flavourchange_moves", 1), ("Percentage4OperatorMove", 1.5), ("PercentageOuterMove", -0.1)):
+    for key, val in (("offdiag", 1), ("segment", 1), ("flavourchange_moves", 1), ("Percentage4OperatorMove", 1.5), ("PercentageOuterMove", -0.1)):
         q = problems.make_problem("C2", nftau=501, **{key: val})
         with pytest.raises(RuntimeError, match=key):
             make().init_paras(q.pstring())

@@ -19,10 +19,13 @@ CASES = [  # cfg (K2 = two-orbital full Kanamori, 2 x 2 blocks), bath levels per
     ("C2", 1, 8.0, {}, 0),
     ("K2", 2, 6.0, {}, 0),
     ("K2", 2, 6.0, {"PercentageOuterMove": 0.2, "Percentage4OperatorMove": 0.2}, 0),
+    # state sampling (one outer eigenstate, WeightedOuterStateChoice): degenerate multiplets included -- statistically exact in any eigenbasis
+    ("K2", 2, 6.0, {"statesampling": 1, "PercentageOuterMove": 0.2, "Percentage4OperatorMove": 0.2}, 0),
+    ("C2", 1, 8.0, {"statesampling": 1, "PercentageOuterMove": 0.2}, 3),
 ]
 
 
-@pytest.mark.parametrize("cfg,nbath,beta,extra,scheduler", CASES, ids=["C1", "C1-all-moves-autonomous", "C2", "Kanamori2", "Kanamori2-all-moves"])
+@pytest.mark.parametrize("cfg,nbath,beta,extra,scheduler", CASES, ids=["C1", "C1-all-moves-autonomous", "C2", "Kanamori2", "Kanamori2-all-moves", "Kanamori2-state-sampling-all-moves", "C2-state-sampling-autonomous"])
 def test_engine_against_exact_diagonalisation(cuda_engine_factory, cfg, nbath, beta, extra, scheduler):
     if cfg == "K2":
         p = ea.kanamori2_problem(nbath, beta, Nmeas=100, Ntau=1000, **extra)

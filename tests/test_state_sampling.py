@@ -1,0 +1,149 @@
+"""State sampling (`statesampling = 1`, the second half of SURVEY.md 8 a21): the local trace runs over ONE outer eigenstate instead of
+the sum over the outer superstate, and every move that changes the outer superstate draws the new eigenstate with
+WeightedOuterStateChoice (Trace.F90:1477-1604; StepAdd / StepRem with change_outer CTQMC.F90:3471-3480, 3979-3996; global moves
+Trace.F90:1325-1332, 1372-1379; tau shifts CTQMC.F90:4702-4710; empty configurations CTQMC.F90:4580-4608, Trace.F90:612-643; the
+beta/2 density matrix and the outer histograms of the single state CTQMC.F90:3106-3110, 3294-3339).
+
+Replay parity engine <-> oracle, CPU (host-emulation build of the kernel sources) and `-m gpu` (CUDA library through the C ABI).
+NOTE on degenerate spectra: the contribution of ONE eigenstate of a degenerate multiplet depends on the basis chosen inside the
+multiplet (the engine diagonalises with Jacobi rotations, the oracle with LAPACK; only sums over a multiplet are basis independent),
+so per-move parity needs a non-degenerate spectrum inside every block: the blocked configurations get a crystal field and
+orbital-pair dependent interaction strengths here.  The statistical correctness of state sampling on the degenerate models is
+pinned against exact diagonalisation (tests/test_gpu_exact.py, tests/test_oracle_pins.py)."""
+import numpy as np
+import pytest
+
+from w2dynamics_b200 import problems
+from test_boundary import _cuda_engine, _hostemu_engine, _start
+
+
+def lift_degeneracies(p):
+    """Orbital-dependent level shifts and two-orbital interaction strengths: no two eigenvalues inside a quantum-number block coincide
+    (the block structure itself -- Nt, Szt, Qzt -- is untouched: every element keeps its operator structure)."""
+    nb = p.nbands
+    uu = p.u_matrix.reshape(nb, 2, nb, 2, nb, 2, nb, 2)
+    for idx in np.argwhere(np.abs(uu) > 1e-14):
+        orbs = sorted({int(idx[0]), int(idx[2]), int(idx[4]), int(idx[6])})
+        if len(orbs) == 2:
+            a, b = orbs
+            uu[tuple(idx)] *= 1.0 + 0.05 * (a + 1) - 0.03 * (b + 1) * (b - a)
+    for b in range(nb):
+        for s in range(2):
+            p.muimp[b, s, b, s] += 0.13 * b * b + 0.07 * b
+    return p
+
+
+def body_replay(make, cfg, nsteps, beta, extra, **opts):
+    from oracle.oracle import OracleChain
+    from _parity import assert_replay
+    p = problems.make_problem(cfg, nftau=2001, beta=beta, statesampling=1, PercentageGlobalMove=0.05, PercentageTauShiftMove=0.05, **extra)
+    assert "statesampling = 1" in p.pstring()
+    if cfg in ("C3", "C4"):
+        lift_degeneracies(p)
+    eng = _start(make(), p, nchains=8, **opts)
+    eng.init_counters()
+    log = eng.debug_steps(5, nsteps)
+    orc = OracleChain(p, rng="philox", seed=43890, chain=5)
+    orc.init_counters()
+    if cfg in ("C3", "C4"):
+        assert min(np.diff(np.sort(e)).min() for e in orc.at.eval if len(e) > 1) > 5e-5
+    ref = orc.steps(nsteps, log=True)
+    # a single-state trace that vanishes by symmetry is a pure rounding residue (|ratio| < 1e-11: rejected with certainty in both)
+    zero = (log[:, 9] < -25.0) & (ref[:, 9] < -25.0) & (log[:, 1] == 0) & (ref[:, 1] == 0)
+    assert zero.sum() < 0.05 * nsteps                  # C4: 2 % (multiplet symmetries the quantum-number blocks do not resolve)
+    log[zero, 9] = ref[zero, 9]; log[zero, 10] = ref[zero, 10]; log[zero, 11] = ref[zero, 11]
+    assert_replay(log, ref)
+    acc = {k: int(((log[:, 0] == k) & (log[:, 1] == 1)).sum()) for k in range(1, 9)}
+    assert acc[1] > 20 and acc[2] > 20 and acc[3] >= 5 and acc[4] >= 5          # pair moves, global moves and tau shifts were accepted
+    if extra.get("PercentageOuterMove"):
+        assert acc[5] + acc[6] >= 5
+    if extra.get("Percentage4OperatorMove"):
+        assert acc[7] + acc[8] >= 5
+    # the configuration interface carries the outer eigenstate (1-based, get_mc_config_scalars CTQMC.F90:9358-9365)
+    c = orc.config()
+    n, osst, ostate = eng.get_mc_config_scalars(5)
+    assert (n, osst, ostate) == (len(c["taus"]), c["outer_sst"], c["outer_state"])
+    assert eng.scalar("error_flags") == 0
+    if n > 0:                                          # set_mc_config round trip on another chain: same trace, same state
+        cfgd = eng.get_mc_config(n, 5)
+        eng.set_mc_config(n, *cfgd[:5], osst, ostate, chain=2)
+        assert eng.get_mc_config_scalars(2) == (n, osst, ostate)
+        a, b = eng.debug_chain_scalars(5), eng.debug_chain_scalars(2)
+        assert abs(a["trace_log"] - b["trace_log"]) < 1e-9 and a["trace_sign"] == b["trace_sign"]
+        with pytest.raises(RuntimeError, match="outer state"):
+            eng.set_mc_config(n, *cfgd[:5], osst, 99, chain=2)
+    eng.dest_ctqmc()
+
+
+CPU_CASES = [("C2", 6000, 4.0, {}, {}), ("C2", 4000, 4.0, {"PercentageOuterMove": 0.25}, {"scheduler": 2}),
+             ("C2", 4000, 4.0, {"PercentageOuterMove": 0.25, "Percentage4OperatorMove": 0.2}, {"scheduler": 3}),
+             ("C3", 5000, 3.0, {}, {}), ("C3", 5000, 3.0, {"PercentageOuterMove": 0.25, "Percentage4OperatorMove": 0.2}, {}),
+             ("C3", 4000, None, {}, {}), ("C4", 2000, 2.0, {"PercentageOuterMove": 0.25}, {})]
+GPU_CASES = [("C2", 20000, 4.0, {"PercentageOuterMove": 0.25, "Percentage4OperatorMove": 0.2}, {}),
+             ("C2", 8000, 4.0, {"PercentageOuterMove": 0.25}, {"scheduler": 2}), ("C2", 8000, 4.0, {"PercentageOuterMove": 0.25}, {"scheduler": 3}),
+             ("C1", 10000, None, {}, {}), ("C5", 3000, None, {}, {}),
+             ("C3", 12000, 3.0, {"PercentageOuterMove": 0.25, "Percentage4OperatorMove": 0.2}, {}), ("C3", 8000, None, {}, {}),
+             ("C4", 6000, 2.0, {"PercentageOuterMove": 0.25}, {}), ("C4", 4000, None, {}, {})]
+
+
+def _ids(cases):
+    return ["%s-beta%s%s%s" % (c[0], c[2], "-outer" if c[3].get("PercentageOuterMove") else "", "-sched%d" % c[4]["scheduler"] if c[4] else "") +
+            ("-4op" if c[3].get("Percentage4OperatorMove") else "") for c in cases]
+
+
+@pytest.mark.parametrize("cfg,nsteps,beta,extra,opts", CPU_CASES, ids=_ids(CPU_CASES))
+def test_state_sampling_replay(built, cfg, nsteps, beta, extra, opts):
+    body_replay(_hostemu_engine, cfg, nsteps, beta, extra, **opts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,nsteps,beta,extra,opts", GPU_CASES, ids=_ids(GPU_CASES))
+def test_gpu_state_sampling_replay(built, cfg, nsteps, beta, extra, opts):
+    body_replay(_cuda_engine, cfg, nsteps, beta, extra, **opts)
+
+
+def body_measurement(make, cfg, beta):
+    """Measurements of identical configurations (the engine's configuration, outer eigenstate included, is handed to the oracle): local
+    trace of the single state, its beta/2 density matrix, occ, rho1, the outer-state histograms, G(tau)."""
+    from oracle.oracle import OracleChain
+    p = problems.make_problem(cfg, nftau=2001, beta=beta, statesampling=1, PercentageGlobalMove=0.05, PercentageTauShiftMove=0.05, Ntau=100, NLegMax=20,
+                              PercentageOuterMove=0.2)
+    if cfg in ("C3", "C4"):
+        lift_degeneracies(p)
+    eng = _start(make(), p, nchains=1, nbins=1)
+    eng.init_counters()
+    orc = OracleChain(p, seed=1, Ntau=100, NLegMax=20)
+    orc.measure(0, reset=True)
+    states = set()
+    for _ in range(25):
+        eng.ctqmc_warmup(300)
+        n, osst, ostate = eng.get_mc_config_scalars(0)
+        taus, orbs, spins, cas, hyb, _, _ = eng.get_mc_config(n, 0)
+        orc.set_config(taus, orbs, spins, cas, osst, ostate)
+        s, o = eng.debug_chain_scalars(0), orc.scalars()
+        assert abs(s["trace_log"] - o["trace_log"]) < 1e-9 and s["trace_sign"] == o["trace_sign"] and s["cfgsign"] == o["cfgsign"]
+        states.add((osst, ostate))
+        eng.block(0, True)
+        orc.measure_once()
+    assert len(states) > 3
+    eng._ck(eng._load().w2b_finalize())
+    r = orc.results(want_rho2=True)
+    for a, b in ((eng.gtau, r["gtau"]), (eng.occ, r["occ"]), (eng.rho1, r["rho1"]), (eng.rho2, r["rho2"]),
+                 (eng.densitymatrix, r["densitymatrix"]), (eng.outerstatehisto, r["hist-state"]),
+                 (eng.tracecontribstates, r["contrib-state"]), (eng.tracecontribsuperstates, r["contrib-sst"])):
+        assert np.abs(a - b).max() < 1e-9 * max(1e-3, np.abs(b).max())
+    assert abs(np.asarray(eng.outerstatehisto).sum() - 1.0) < 1e-12   # one state per measurement (normalised by the number of measurements), not one per state of the superstate
+    assert np.array_equal(eng.histo, r["hist"]) and eng.mean_sign == r["sign"]
+    assert eng.scalar("error_flags") == 0
+    eng.dest_ctqmc()
+
+
+@pytest.mark.parametrize("cfg,beta", [("C2", 4.0), ("C3", 3.0)])
+def test_state_sampling_measurement(built, cfg, beta):
+    body_measurement(_hostemu_engine, cfg, beta)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,beta", [("C2", 4.0), ("C3", 3.0), ("C4", 2.0)])
+def test_gpu_state_sampling_measurement(built, cfg, beta):
+    body_measurement(_cuda_engine, cfg, beta)

@@ -119,7 +119,7 @@ void check_chain(int chain) {
 void check_supported(const Params& p) {
     auto zero_i = [&](const char* k) { if (p.has(k) && p.integer(k) != 0) throw std::runtime_error(std::string(k) + " != 0 is outside the implemented hot path"); };
     auto zero_r = [&](const char* k) { if (p.has(k) && p.real(k) != 0.0) throw std::runtime_error(std::string(k) + " != 0 is outside the implemented hot path"); };
-    zero_i("segment"); zero_i("offdiag"); zero_i("statesampling"); zero_i("Uw"); zero_i("Phonon");
+    zero_i("segment"); zero_i("offdiag"); zero_i("Uw"); zero_i("Phonon");
     zero_i("MeasGiw"); zero_i("MeasG2iw"); zero_i("MeasSusz"); zero_i("MeasExpResDensityMatrix"); zero_i("FourPnt");
     zero_i("MeasSsquare"); zero_i("MeasGtauDetRat"); zero_i("flavourchange_moves"); zero_i("Gtau_mean_step"); zero_i("Gtau_mid_step"); zero_i("sign_step");
     // PercentageOuterMove (outer pair moves, CTQMC.F90:3422-3449, 3934-3961) and Percentage4OperatorMove (StepAdd4 / StepRem4 with
@@ -330,6 +330,7 @@ int w2b_init_solver(const double* u_matrix, const double* ftau_full, const doubl
         Run R{};
         R.pglob = p.real("PercentageGlobalMove"); R.pshift = p.real("PercentageTauShiftMove");
         R.p4op = p.real_or("Percentage4OperatorMove", 0.0); R.pouter = p.real_or("PercentageOuterMove", 0.0);
+        R.statesampling = (p.has("statesampling") && p.integer("statesampling") != 0) ? 1 : 0;
         R.ntau = (int)p.integer("Ntau"); R.nlegmax = (int)p.integer("NLegMax"); R.maxhisto = (int)p.integer("MaxHisto");
         R.has_szt = p.str("QuantumNumbers").find("Szt") != std::string::npos;
         R.meas_dm = p.integer("MeasDensityMatrix") != 0;
@@ -659,7 +660,7 @@ int w2b_get_mc_config_scalars(int chain, int* noper, int* outer_sst, int* outer_
     return guarded([&] {
         check_chain(chain);
         std::vector<int> ih; std::vector<double> dh; S.eng->get_header(chain, ih, dh);
-        *noper = ih[IH_NOPS]; *outer_sst = ih[IH_OUTER]; *outer_state = 1;
+        *noper = ih[IH_NOPS]; *outer_sst = ih[IH_OUTER]; *outer_state = ih[IH_OSTATE] + 1;
     });
 }
 int w2b_get_mc_config(int chain, int n, double* taus, int* orbs, int* spins, int* cas, int* hashybs, int* outer_sst, int* outer_state) {
@@ -670,16 +671,17 @@ int w2b_get_mc_config(int chain, int n, double* taus, int* orbs, int* spins, int
         if ((int)tau.size() != n) throw std::runtime_error("get_mc_config: size mismatch");
         for (int i = 0; i < n; ++i) { int f = code[i] >> 1; taus[i] = tau[i]; orbs[i] = f / 2 + 1; spins[i] = f % 2 + 1; cas[i] = (code[i] & 1) + 1; hashybs[i] = -1; }
         std::vector<int> ih; std::vector<double> dh; S.eng->get_header(chain, ih, dh);
-        *outer_sst = ih[IH_OUTER]; *outer_state = 1;
+        *outer_sst = ih[IH_OUTER]; *outer_state = ih[IH_OSTATE] + 1;
     });
 }
 int w2b_set_mc_config(int chain, int n, const double* taus, const int* orbs, const int* spins, const int* cas, const int* hashybs, int outer_sst, int outer_state) {
-    (void)outer_state;
     return guarded([&] {
         check_chain(chain);
         const Engine& E = *S.eng;
         if (n < 0 || n > E.C.ops_cap) throw std::runtime_error("set_mc_config: " + std::to_string(n) + " operators exceed the capacity " + std::to_string(E.C.ops_cap) + " (option ops_cap)");
         if (outer_sst < 0 || outer_sst >= E.at.nsst) throw std::runtime_error("set_mc_config: outer superstate " + std::to_string(outer_sst) + " outside [0, " + std::to_string(E.at.nsst) + ")");
+        // outer eigenstate (1-based like the reference, Trace.F90:6918): meaningful with state sampling only, else always the whole superstate
+        if (E.R.statesampling && (outer_state < 1 || outer_state > E.at.dim[outer_sst])) throw std::runtime_error("set_mc_config: outer state " + std::to_string(outer_state) + " outside 1.." + std::to_string(E.at.dim[outer_sst]));
         std::vector<int> kf(E.at.nf, 0);
         std::vector<unsigned char> code(n);
         for (int i = 0; i < n; ++i) {
@@ -690,7 +692,7 @@ int w2b_set_mc_config(int chain, int n, const double* taus, const int* orbs, con
             code[i] = (unsigned char)((((orbs[i] - 1) * 2 + (spins[i] - 1)) << 1) | (cas[i] - 1));
             if (i && !(taus[i] > taus[i - 1])) throw std::runtime_error("set_mc_config: operators must be in ascending tau");
         }
-        S.eng->set_ops(chain, n, taus, code.data(), outer_sst);
+        S.eng->set_ops(chain, n, taus, code.data(), outer_sst, E.R.statesampling ? outer_state - 1 : 0);
     });
 }
 int w2b_set_empty_mc_config(int chain, int outer_sst, int outer_state) { return w2b_set_mc_config(chain, 0, nullptr, nullptr, nullptr, nullptr, nullptr, outer_sst, outer_state); }

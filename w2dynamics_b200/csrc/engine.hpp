@@ -378,6 +378,7 @@ public:
             ew[k] = w; el[k] = std::log(w); wsum_ += w;
         }
         for (double& w : ew) w /= wsum_;
+        T.empty_norm = wsum_;
         std::vector<double> lelem(elem.size(), 0.0);
         for (size_t i = 0; i < elem.size(); ++i) if (elem[i] != 0.0) lelem[i] = std::log(std::fabs(elem[i]));
         T.connect = keep(dev_upload(conn)); T.e0 = keep(dev_upload(e0)); T.elem = keep(dev_upload(elem)); T.lelem = keep(dev_upload(lelem));
@@ -463,7 +464,7 @@ public:
             C.ptc = keep(dev_alloc<double>((size_t)nc * 2 * at.dmax));
             C.q_tr0 = keep(dev_alloc<int>((size_t)nc * 8)); C.q_tr1 = keep(dev_alloc<int>((size_t)nc * 8)); C.q_tr2 = keep(dev_alloc<int>((size_t)nc * 8));
         }
-        int wints = kcap + 32 + nsst;
+        int wints = kcap + 32 + 2 * nsst;      // + candidate outer superstates of a global move: new [nsst], old [nsst]
         wdoubles = 3 * kcap + mat_doubles(C, true) + (wints + 1) / 2;
         wdoubles_sweep = 3 * kcap + (wints + 1) / 2;   // sweep kernels hold no work matrix: blocked traces run in the trace kernel
 
@@ -888,12 +889,12 @@ public:
         out.assign((size_t)k * k, 0.0);                // column-major (creator, annihilator) like the reference
         for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) out[i + (size_t)j * k] = buf[(size_t)i * C.ld + j];
     }
-    void set_ops(int chain, int n, const double* tau, const unsigned char* code, int outer_sst) {
+    void set_ops(int chain, int n, const double* tau, const unsigned char* code, int outer_sst, int outer_state = 0) {
         if (n > C.ops_cap) throw std::runtime_error("configuration exceeds operator capacity");
         sync();
         std::vector<int> ih(IH_STRIDE);
         d2h(ih.data(), C.ih + (size_t)chain * IH_STRIDE, IH_STRIDE);
-        ih[IH_NOPS] = n; ih[IH_OUTER] = outer_sst; ih[IH_ERR] = 0;
+        ih[IH_NOPS] = n; ih[IH_OUTER] = outer_sst; ih[IH_OSTATE] = outer_state; ih[IH_ERR] = 0;
         h2d(C.ih + (size_t)chain * IH_STRIDE, ih.data(), IH_STRIDE);
         h2d(C.op_tau + (size_t)chain * C.ops_cap, tau, n);
         h2d(C.op_code + (size_t)chain * C.ops_cap, code, n);

@@ -37,7 +37,7 @@ namespace w2b {
 constexpr int LOGW = 20;      // doubles per replay-log record (same layout as oracle/chain.cpp)
 constexpr int NF_MAX = 14;
 enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_ALGBYTES, C_TRFLOPS, C_TRYADD4, C_ACCADD4, C_TRYREM4, C_ACCREM4, C_NCNT };
-enum { IH_NOPS = 0, IH_OUTER, IH_WPOS, IH_NPAIRS, IH_PERM, IH_PALT, IH_ERR, IH_KV, IH_KF = 8, IH_MSLOT = IH_KF + NF_MAX, IH_BV = IH_MSLOT + NF_MAX + 1, IH_NFREE, IH_STRIDE };
+enum { IH_NOPS = 0, IH_OUTER, IH_WPOS, IH_NPAIRS, IH_PERM, IH_PALT, IH_ERR, IH_KV, IH_KF = 8, IH_MSLOT = IH_KF + NF_MAX, IH_BV = IH_MSLOT + NF_MAX + 1, IH_NFREE, IH_OSTATE, IH_STRIDE };   // IH_OSTATE: outer eigenstate inside the outer superstate (state sampling; else 0)
 enum { DH_DETLOG = 0, DH_DETSIGN, DH_TRLOG, DH_TRSIGN, DH_CFGSIGN, DH_STRIDE = 8 };
 enum { ERR_CAPACITY = 1, ERR_DETRAT_SMALL = 2, ERR_PAIR_LOGIC = 4, ERR_GLOBAL_QN = 8, ERR_SINGULAR = 16 };
 
@@ -57,6 +57,7 @@ struct Tables {
     const int* dens_off;         // [nsst] offset of the block's d x d slab inside the density-matrix accumulator
     const double* empty_w;       // [nsst] normalised empty-trace weights (init_Trace / StepChangeOuter)
     const double* empty_log;     // [nsst] log of the empty trace of each outer superstate
+    double empty_norm;           // sum over ALL states of exp(-(E - Egs) beta): normalisation of the per-state empty-trace weights (state sampling)
     const double* leg_a; const double* leg_b;   // Legendre recurrence coefficients (2l-1)/l and (l-1)/l, [NLegMax]
     const int* symmoves;         // [2 NSymMove][nf] flavour permutations (target index b + nb s + 1) and their inverses (Trace.F90:471-478)
     const double* leg_g; const double* leg_c;   // monic recurrence g_l = (l-1)^2/((2l-1)(2l-3)) and leading coefficients c_l: P_l = c_l Q_l
@@ -77,6 +78,7 @@ struct Run {
     int prefetch;                // software prefetch of the next work item's records (0 = off)
     int same_key;                // diagnostics only: every chain uses chain 0's RNG key (identical control flow across warps)
     int nsym;                    // user symmetry moves (NSymMove); the table Tables::symmoves holds them and their inverses
+    int statesampling;           // statesampling = 1: the local trace runs over ONE outer eigenstate (Trace.F90:203, 1477-1604)
     unsigned stream;             // solves since init_rnd: every init_solver draws from a fresh section of each chain's Philox stream
 };
 constexpr int STREAM_SHIFT = 44;     // draws per chain and solve before two solves could overlap: 2^44
@@ -85,6 +87,7 @@ constexpr int STREAM_SHIFT = 44;     // draws per chain and solve before two sol
 struct Prop {
     double t1, t2, tau_a, tau_c, factor, dlog, dsign;
     int f, i1, i2, p1, p2, begin_sst, nother, type1;
+    int new_state; double osf;               // outer pair moves with state sampling: chosen outer eigenstate and WeightedOuterStateChoice factor
 };
 
 // a global move / tau shift between its two halves (prepare -> trace kernel -> finish)
@@ -95,6 +98,7 @@ struct RareJob {
     double tn_log, tn_sign;                  // staged global moves of the CTA scheduler: local trace of the proposed configuration
     int nnew;                                // kinds 5 - 8 (outer pair moves, 4-operator moves): number of operators of the proposed sequence in the scratch arrays
     int np_new;                              // kinds 7 / 8: NPairs of the proposed configuration
+    int new_state;                           // state sampling: outer eigenstate of the proposed configuration (-1: sum over the superstate)
 };
 
 // round scheduler counters (device memory, two sets used in alternation by consecutive rounds)
@@ -151,6 +155,7 @@ struct Ctx {
     int ldx;
     int kv, bv, nfree;
     int n, outer, wpos, npairs, perm, palt, err;
+    int ostate, only;      // outer eigenstate (0 without state sampling); only = ostate with state sampling, else -1 (argument of parts_sum)
     double det_log, det_sign, tr_log, tr_sign, cfgsign, wmin, wmax;
     Philox rng;
     double* log;           // replay record for the current step (or nullptr)
@@ -431,14 +436,14 @@ W2B_HDN void extend_bras(const Tables& T, const Chains& C, Ctx& x, int downto) {
 }
 
 // from-scratch trace of an arbitrary sequence (global moves, tau shifts, set_mc_config); no caches touched
-W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsigned char* code, int n, int outer, double& tlog, double& tsign) {
+W2B_HDN void full_trace(const Tables& T, Ctx& x, const double* tau, const unsigned char* code, int n, int outer, double& tlog, double& tsign, int only = -1) {
     const int m = ldg(&T.dim[outer]), ld = x.ldx;
     double* X = x.mX;
     mat_identity(X, ld, x.mlg, m);
     int sst = outer; double tprev = 0.0;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) { sst = mat_apply(T, sst, (int)code[i], tau[i] - tprev, X, ld, x.mlg, x.mpw, m); tprev = tau[i]; }
-    mat_close(T, sst, T.beta - tprev, X, ld, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign);
+    mat_close(T, sst, T.beta - tprev, X, ld, x.mlg, (const double*)nullptr, (const double*)nullptr, x.mpw, m, x.mpt, tlog, tsign, only);
 }
 // ------------------------------------------------------------------ trace kernel (blocked traces, pair moves)
 // One job = 8 columns (outer states) of the local trace of one proposed pair insertion / removal.  Columns never mix
@@ -592,6 +597,46 @@ W2B_HD void empty_parts(const Tables& T, Ctx& x, int outer) {
     for (int j = lane_id(); j < m; j += W2B_WARP) { x.pt[2 * j] = -(ldg(&ev[j]) - T.egs) * T.beta; x.pt[2 * j + 1] = 1.0; }
     wsync();
 }
+// WeightedOuterStateChoice (Trace.F90:1477-1604, state sampling; no outer truncation: every superstate keeps all its states).  Picks
+// the new outer (superstate, eigenstate) among the candidate superstates with probability ~ exp(-tau_new (E - Egs)) and returns
+// p_prop(new -> old) / p_prop(old -> new).  Candidates: the single superstates one_old / one_new, or (flags != nullptr) every superstate
+// k with flags[k] (new) / flags[nsst + k] (old).  One random number; none, and 0 returned, when nothing can be chosen.  Warp-uniform.
+W2B_HDN double wosc(const Tables& T, Ctx& x, double tau_old, double tau_new, int one_old, int one_new, const int* flags, int& sst_new, int& state_new) {
+    const int sst_old = x.outer, state_old = x.ostate;
+    double tw = 0.0, tot = 0.0; bool any = false;
+#pragma unroll 1
+    for (int q = flags ? 0 : one_old; q < (flags ? T.nsst : one_old + 1); ++q) {
+        if (flags && !flags[T.nsst + q]) continue;
+        const double* ev = T.evals + ldg(&T.offset[q]); const int d = ldg(&T.dim[q]);
+#pragma unroll 1
+        for (int j = 0; j < d; ++j) tw += w_exp(-tau_old * (ldg(&ev[j]) - T.egs));
+    }
+    const double res = w_exp(-tau_old * (ldg(&T.evals[ldg(&T.offset[sst_old]) + state_old]) - T.egs)) / tw;
+    sst_new = sst_old; state_new = state_old;
+#pragma unroll 1
+    for (int q = flags ? 0 : one_new; q < (flags ? T.nsst : one_new + 1); ++q) {
+        if (flags && !flags[q]) continue;
+        const double* ev = T.evals + ldg(&T.offset[q]); const int d = ldg(&T.dim[q]);
+#pragma unroll 1
+        for (int j = 0; j < d; ++j) { tot += w_exp(-tau_new * (ldg(&ev[j]) - T.egs)); any = true; }
+    }
+    if (!any || !(tot > 0.0)) return 0.0;
+    const double rand = x.rng.next() * tot;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int q = flags ? 0 : one_new; q < (flags ? T.nsst : one_new + 1); ++q) {
+        if (flags && !flags[q]) continue;
+        const double* ev = T.evals + ldg(&T.offset[q]); const int d = ldg(&T.dim[q]);
+#pragma unroll 1
+        for (int j = 0; j < d; ++j) {
+            const double w = w_exp(-tau_new * (ldg(&ev[j]) - T.egs));
+            acc += w;
+            if (rand <= acc && w != 0.0) { sst_new = q; state_new = j; return res * (tot / w); }
+        }
+    }
+    return 0.0;
+}
+W2B_HD double outer_tau(const Tables& T, const double* tau, int n) { return n == 0 ? T.beta : T.beta - tau[n - 1] + tau[0]; }
 W2B_HDN void commit_parts(const Tables& T, Ctx& x) {
     const int m = ldg(&T.dim[x.outer]);
 #pragma unroll 1
@@ -848,7 +893,7 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     double tn_log = 0.0, tn_sign = 1.0;
     if (blocked) {                                                     // get_trace_EB of the proposed configuration
         // the trace kernel has left the per-outer-state parts of the proposed configuration in C.ptc and extended the cache frontiers
-        parts_sum(x.mpt, ldg(&T.dim[OUTER ? begin_sst : x.outer]), tn_log, tn_sign);
+        parts_sum(x.mpt, ldg(&T.dim[OUTER ? begin_sst : x.outer]), tn_log, tn_sign, OUTER ? (R.statesampling ? P.new_state : -1) : x.only);
         if (!OUTER) { if (x.kv < i1) x.kv = i1; if (x.bv > i2) x.bv = i2; }
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
@@ -858,7 +903,9 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     // NPairs after insertion (CTQMC.F90:3510-3515)
     if (x.npairs < 0) x.npairs = count_pairs_full(T, R, C, x);
     const int np_new = x.npairs + pairs_with(R, x, ta, k, tau_c) + pairs_with(R, x, tc, k, tau_a) + (pairable(R, x, tau_a, tau_c) ? 1 : 0);
-    const double prob = fabs(P.factor * (double)(2 * T.nb) / (double)np_new * w_exp(dlog + dr_log));
+    const double osf = (OUTER && R.statesampling) ? P.osf : 1.0;                // WeightedOuterStateChoice factor (CTQMC.F90:3471-3480, 3527)
+    if (osf == 0.0) { dlog = 0.0; dsign = 0.0; }                                // no outer state could be chosen: rejected whatever the trace
+    const double prob = osf == 0.0 ? 0.0 : fabs(osf * P.factor * (double)(2 * T.nb) / (double)np_new * w_exp(dlog + dr_log));
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, dlog); log_set(x, 10, dsign); log_set(x, 11, prob);
     log_set(x, 14, np_new); log_set(x, 17, rand);
     if (!(rand < prob)) { log_end(x, 0); return; }
@@ -873,6 +920,7 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
         for (int i = lane_id(); i < x.n + 2; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
         wsync();
         x.n += 2; x.outer = begin_sst;
+        if (R.statesampling) { x.ostate = P.new_state; x.only = x.ostate; }
         if (blocked) { commit_parts(T, x); slots_reset(C, x); }
     } else {
     shift_up(x.tau, i2, x.n, 2); shift_up(x.code, i2, x.n, 2); shift_up(x.sst, i2, x.n, 2);
@@ -1008,7 +1056,7 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     double dlog = P.dlog, dsign = P.dsign, tn_log = 0.0, tn_sign = 1.0;
     prefetch_matrix(Mbuf(C, x, f), k, C.ld);                            // read whole if the removal is accepted (1 in 5 at C5; HBM has the headroom)
     if (blocked) {
-        parts_sum(x.mpt, ldg(&T.dim[OUTER ? begin_sst : x.outer]), tn_log, tn_sign);
+        parts_sum(x.mpt, ldg(&T.dim[OUTER ? begin_sst : x.outer]), tn_log, tn_sign, OUTER ? (R.statesampling ? P.new_state : -1) : x.only);
         if (!OUTER) { if (x.kv < i1) x.kv = i1; if (x.bv > i2 + 1) x.bv = i2 + 1; }
         dlog = tn_log - x.tr_log; dsign = tn_sign * x.tr_sign;
     }
@@ -1016,7 +1064,9 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     const double S = Mbuf(C, x, f)[(size_t)p1 * C.ld + p2];
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
     const double dr_log = w_log(fabs(S)), dr_sign = sgn1(S) * sig;
-    const double prob = fabs(P.factor / (double)(2 * T.nb) * w_exp(dlog + dr_log));
+    const double osf = (OUTER && R.statesampling) ? P.osf : 1.0;                // CTQMC.F90:3979-3996
+    if (osf == 0.0) { dlog = 0.0; dsign = 0.0; }
+    const double prob = osf == 0.0 ? 0.0 : fabs(osf * P.factor / (double)(2 * T.nb) * w_exp(dlog + dr_log));
     const double rand = x.rng.next();
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, dlog); log_set(x, 10, dsign); log_set(x, 11, prob); log_set(x, 17, rand);
     if (!(rand < prob)) { log_end(x, 0); return; }
@@ -1031,6 +1081,7 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
         for (int i = lane_id(); i < x.n - 2; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
         wsync();
         x.n -= 2; x.outer = begin_sst;
+        if (R.statesampling) { x.ostate = P.new_state; x.only = x.ostate; }
         if (blocked) { commit_parts(T, x); slots_reset(C, x); }
     } else {
     if (blocked) {                                                     // give the two cache slots back; kets valid below i1, bras from i2-1 on
@@ -1345,13 +1396,17 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
         x.sc_code[i] = (unsigned char)(f2 * 2 + (flip ? 1 - ty : ty));
     }
     wsync();
-    double factor = 0.0; int new_outer = x.outer;
+    double factor = 0.0; int new_outer = x.outer, new_state = R.statesampling ? x.ostate : -1;
     if (type == 3 && R.has_szt) {          // perform_spinflip_check_qn Trace.F90:1306-1339
         int st = ldg(&T.first_state[x.outer]);
         int dn = st & ((1 << nb) - 1), up = (st >> nb) & ((1 << nb) - 1);
         new_outer = ldg(&T.state2sst[up | (dn << nb)]);
         int fin = walk_store(T, x.sc_code, 0, x.n, new_outer, x.sc_sst, 0);
         factor = (fin == new_outer) ? 1.0 : 0.0;
+        if (factor != 0.0 && R.statesampling) {                        // Trace.F90:1325-1332
+            const int cand = new_outer; const double ot = outer_tau(T, x.tau, x.n);
+            factor = wosc(T, x, ot, ot, x.outer, cand, nullptr, new_outer, new_state);
+        }
     } else {                               // perform_global_check_qn Trace.F90:1345-1394
         int pold = 0, pnew = 0;
         // each lane walks one candidate outer superstate through the old and the new sequence
@@ -1366,12 +1421,16 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
                 cn = cn >= 0 ? conn(T, cn, b2) : -1;
             }
             bool oko = act && co == k0, okn = act && cn == k0;
-            if (act) x.wI[C.kcap + 32 + k0] = okn ? 1 : 0;
+            if (act) { x.wI[C.kcap + 32 + k0] = okn ? 1 : 0; x.wI[C.kcap + 32 + T.nsst + k0] = oko ? 1 : 0; }
             pold += wsum(oko ? 1 : 0); pnew += wsum(okn ? 1 : 0);
         }
         wsync();
         if (pold <= 0) { x.err |= ERR_GLOBAL_QN; log_end(x, 2); return false; }
-        if (pnew > 0) {
+        if (pnew > 0 && R.statesampling) {                             // Trace.F90:1372-1379: weighted choice among all states of the compatible superstates
+            const double ot = outer_tau(T, x.tau, x.n);
+            factor = wosc(T, x, ot, ot, -1, -1, x.wI + C.kcap + 32, new_outer, new_state);
+            if (factor != 0.0) walk_store(T, x.sc_code, 0, x.n, new_outer, x.sc_sst, 0);
+        } else if (pnew > 0) {
             factor = (double)pnew / (double)pold;
             int kk = x.rng.randint(1, pnew);
 #pragma unroll 1
@@ -1394,7 +1453,7 @@ W2B_HDN bool step_glob_prepare(const Tables& T, const Run& R, const Chains& C, C
         for (int i = lane_id(); i < k; i += W2B_WARP) { nc[i] = flip ? oa[i] : oc[i]; na[i] = flip ? oc[i] : oa[i]; }
     }
     wsync();
-    if (lane_id() == 0) { J.kind = 3; J.new_outer = new_outer; J.type = type; J.factor = factor; J.stored = 0; }
+    if (lane_id() == 0) { J.kind = 3; J.new_outer = new_outer; J.new_state = new_state; J.type = type; J.factor = factor; J.stored = 0; }
     wsync();
     if (!with_lu) return true;               // (callers that obtain the determinants elsewhere)
     // determinant of the new configuration from scratch (LU in the spare buffer).  The reference obtains the old determinant
@@ -1439,6 +1498,7 @@ W2B_HDN bool step_glob_finish_a(const Tables& T, const Run& R, const Chains& C, 
 W2B_HDN void step_glob_finish_b(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, double tn_log, double tn_sign) {
     const int nf = T.nf;
     x.outer = J.new_outer;
+    if (R.statesampling) { x.ostate = J.new_state; x.only = x.ostate; }
     x.det_log = J.dn_log; x.det_sign = J.dn_sign; x.tr_log = tn_log; x.tr_sign = tn_sign;
     if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); }
     x.perm = perm_full(x.code, x.n);
@@ -1462,6 +1522,25 @@ W2B_HDN bool step_shift_prepare(const Tables& T, const Run& R, const Chains& C, 
     if (x.n == 0) {                        // StepChangeOuter CTQMC.F90:4570-4638
         const double rand = x.rng.next();
         double acc = 0.0; int pick = T.nsst - 1;
+        if (R.statesampling) {             // outer (superstate, eigenstate) ~ empty-trace value of the state (CTQMC.F90:4580-4608)
+            int pstate = 0; bool done = false;
+#pragma unroll 1
+            for (int i = 0; i < T.nsst && !done; ++i) {
+                const double* ev = T.evals + ldg(&T.offset[i]); const int d = ldg(&T.dim[i]);
+#pragma unroll 1
+                for (int j = 0; j < d; ++j) {
+                    const double w = w_exp(-(ldg(&ev[j]) - T.egs) * T.beta) / T.empty_norm;
+                    acc += w; pick = i; pstate = j;
+                    if (acc >= rand && w != 0.0) { done = true; break; }
+                }
+            }
+            x.outer = pick; x.ostate = pstate; x.only = pstate;
+            x.tr_log = -(ldg(&T.evals[ldg(&T.offset[pick]) + pstate]) - T.egs) * T.beta; x.tr_sign = 1.0;
+            if (T.dmax > 1) empty_parts(T, x, pick);
+            update_cfgsign(T, x);
+            log_set(x, 17, rand); log_end(x, 1);
+            return false;
+        }
 #pragma unroll 1
         for (int i = 0; i < T.nsst; ++i) { double w = ldg(&T.empty_w[i]); acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
         x.outer = pick; x.tr_log = ldg(&T.empty_log[pick]); x.tr_sign = 1.0;
@@ -1484,7 +1563,10 @@ W2B_HDN bool step_shift_prepare(const Tables& T, const Run& R, const Chains& C, 
         double t = x.tau[src] - dt; if (t < 0.0) t += T.beta;     // modulo(tau - dt, beta)
         x.sc_tau[i] = t; x.sc_code[i] = x.code[src]; x.sc_sst[i] = x.sst[src];
     }
-    if (lane_id() == 0) { J.kind = 4; J.dt = dt; J.new_outer = new_outer; J.stored = 0; }
+    wsync();
+    int sst_new = new_outer, new_state = -1; double osf = 1.0;
+    if (R.statesampling) osf = wosc(T, x, outer_tau(T, x.tau, n), outer_tau(T, x.sc_tau, n), x.outer, new_outer, nullptr, sst_new, new_state);   // CTQMC.F90:4702-4710
+    if (lane_id() == 0) { J.kind = 4; J.dt = dt; J.new_outer = new_outer; J.new_state = new_state; J.factor = osf; J.stored = 0; }
     wsync();
     return true;
 }
@@ -1495,8 +1577,9 @@ W2B_HDN void step_shift_finish(const Tables& T, const Run& R, const Chains& C, C
     const int sh = ((int)floor((dt / T.beta) * (double)(R.num_windows + 1))) % R.num_windows;
     x.wpos = ((wp_old - sh) % R.num_windows + R.num_windows) % R.num_windows;
     set_window_edges(T, R, x);
-    const double trr_log = tn_log - x.tr_log, trr_sign = tn_sign * x.tr_sign;
-    const double prob = fabs(trr_sign * w_exp(trr_log));
+    const double osf = R.statesampling ? J.factor : 1.0;
+    const double trr_log = osf == 0.0 ? 0.0 : tn_log - x.tr_log, trr_sign = osf == 0.0 ? 0.0 : tn_sign * x.tr_sign;
+    const double prob = osf == 0.0 ? 0.0 : fabs(osf * (trr_sign * w_exp(trr_log)));
     const double rand = x.rng.next();
     log_set(x, 9, trr_log); log_set(x, 10, trr_sign); log_set(x, 11, prob); log_set(x, 17, rand);
     if (!(rand < prob)) {
@@ -1548,6 +1631,7 @@ W2B_HDN void step_shift_finish(const Tables& T, const Run& R, const Chains& C, C
     for (int i = lane_id(); i < n; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
     wsync();
     x.outer = new_outer;
+    if (R.statesampling) { x.ostate = J.new_state; x.only = x.ostate; }
     x.tr_log = tn_log; x.tr_sign = tn_sign; x.det_sign *= detrat;
     if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); if (J.stored) x.kv = n; }   // kets of the shifted sequence are already cached
     x.npairs = -1;
@@ -1563,7 +1647,7 @@ W2B_HD void step_rare(const Tables& T, const Run& R, const Chains& C, Ctx& x, Ra
     if (!go) return;
     const double* tau = kind == 3 ? x.tau : x.sc_tau;
     double tn_log, tn_sign;
-    if (T.dmax > 1) full_trace(T, x, tau, x.sc_code, x.n, J.new_outer, tn_log, tn_sign);
+    if (T.dmax > 1) full_trace(T, x, tau, x.sc_code, x.n, J.new_outer, tn_log, tn_sign, J.new_state);
     else trace_full_scalar(T, tau, x.sc_code, x.sc_sst, x.n, J.new_outer, tn_log, tn_sign);
     if (kind == 3) step_glob_finish(T, R, C, x, J, tn_log, tn_sign); else step_shift_finish(T, R, C, x, J, tn_log, tn_sign);
 }
@@ -1572,7 +1656,7 @@ W2B_HD void step_rare(const Tables& T, const Run& R, const Chains& C, Ctx& x, Ra
 // Served like global moves: the proposed sequence is staged in the scratch arrays and its local trace evaluated from scratch.
 // Stages the proposed sequence of an outer pair move: times and codes with the pair inserted / taken out, superstates walked from
 // the new outer superstate P.begin_sst; 1x1 blocks: also the trace ratio (P.dlog, P.dsign).  Returns false when it does not fit.
-W2B_HDN bool outer_stage(const Tables& T, const Chains& C, Ctx& x, Prop& P, RareJob& J, bool add) {
+W2B_HDN bool outer_stage(const Tables& T, const Run& R, const Chains& C, Ctx& x, Prop& P, RareJob& J, bool add) {
     const int n = x.n, i1 = P.i1, i2 = P.i2, nn = add ? n + 2 : n - 2, new_outer = P.begin_sst;
     if (nn > C.ops_cap) { x.err |= ERR_CAPACITY; log_end(x, 0); return false; }
     const int codeA = P.f * 2 + P.type1, codeB = P.f * 2 + (1 - P.type1);
@@ -1586,24 +1670,29 @@ W2B_HDN bool outer_stage(const Tables& T, const Chains& C, Ctx& x, Prop& P, Rare
     }
     wsync();
     walk_store(T, x.sc_code, 0, nn, new_outer, x.sc_sst, 0);
+    int new_state = -1;
+    if (R.statesampling) {                 // the new outer eigenstate is drawn inside the new outer superstate (CTQMC.F90:3471-3480, 3979-3996)
+        int sn; double osf = wosc(T, x, outer_tau(T, x.tau, n), outer_tau(T, x.sc_tau, nn), x.outer, new_outer, nullptr, sn, new_state);
+        if (lane_id() == 0) { P.osf = osf; P.new_state = new_state; }
+    }
     if (T.dmax == 1) {
         double tl, ts;
         trace_full_scalar(T, x.sc_tau, x.sc_code, x.sc_sst, nn, new_outer, tl, ts);
         if (lane_id() == 0) { P.dlog = tl - x.tr_log; P.dsign = ts * x.tr_sign; }
     }
-    if (lane_id() == 0) { J.kind = add ? 5 : 6; J.new_outer = new_outer; J.nnew = nn; J.stored = 0; }
+    if (lane_id() == 0) { J.kind = add ? 5 : 6; J.new_outer = new_outer; J.new_state = new_state; J.nnew = nn; J.stored = 0; }
     wsync();
     return true;
 }
 // first half (kinds 5 / 6); returns true when the proposal survived and is staged
 W2B_HDN bool outer_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x, Prop& P, RareJob& J, int kind) {
     const bool go = kind == 5 ? add_propose<true>(T, R, C, x, P) : rem_propose<true>(T, R, C, x, P);
-    return go && outer_stage(T, C, x, P, J, kind == 5);
+    return go && outer_stage(T, R, C, x, P, J, kind == 5);
 }
 // the whole move on one warp (1x1 blocks; host paths that do not use the trace kernel)
 W2B_HDN void step_outer(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, Prop& P, RareJob& J, int kind) {
     if (!outer_prepare(T, R, C, x, P, J, kind)) return;
-    if (T.dmax > 1) { double tl, ts; full_trace(T, x, x.sc_tau, x.sc_code, J.nnew, J.new_outer, tl, ts); }     // parts in x.mpt
+    if (T.dmax > 1) { double tl, ts; full_trace(T, x, x.sc_tau, x.sc_code, J.nnew, J.new_outer, tl, ts, J.new_state); }     // parts in x.mpt
     if (kind == 5) add_decide<true>(T, R, C, A, x, P); else rem_decide<true>(T, R, C, A, x, P);
 }
 
@@ -1845,7 +1934,7 @@ W2B_HDN bool four_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x
         four_det_ratio(T, C, x, add, t, code, rl, rs);
         dn_log = rs == 0.0 ? rl : x.det_log + rl; dn_sign = x.det_sign * rs;
     }
-    if (lane_id() == 0) { J.kind = kind; J.new_outer = x.outer; J.nnew = nn; J.stored = 0; J.factor = factor; J.np_new = np_new; J.dn_log = dn_log; J.dn_sign = dn_sign; }
+    if (lane_id() == 0) { J.kind = kind; J.new_outer = x.outer; J.new_state = x.only; J.nnew = nn; J.stored = 0; J.factor = factor; J.np_new = np_new; J.dn_log = dn_log; J.dn_sign = dn_sign; }
     wsync();
     return true;
 }
@@ -1887,7 +1976,7 @@ W2B_HDN void four_finish(const Tables& T, const Run& R, const Chains& C, Ctx& x,
 W2B_HDN void step_four(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, int kind) {
     if (!four_prepare(T, R, C, x, J, kind)) return;
     double tn_log, tn_sign;
-    if (T.dmax > 1) full_trace(T, x, x.sc_tau, x.sc_code, J.nnew, x.outer, tn_log, tn_sign);
+    if (T.dmax > 1) full_trace(T, x, x.sc_tau, x.sc_code, J.nnew, x.outer, tn_log, tn_sign, x.only);
     else trace_full_scalar(T, x.sc_tau, x.sc_code, x.sc_sst, J.nnew, x.outer, tn_log, tn_sign);
     four_finish(T, R, C, x, J, tn_log, tn_sign);
 }
@@ -1912,6 +2001,7 @@ W2B_HDN void ctx_bind(const Tables& T, const Run& R, const Chains& C, int chain,
     }
     x.n = x.ih[IH_NOPS]; x.outer = x.ih[IH_OUTER]; x.wpos = x.ih[IH_WPOS]; x.npairs = x.ih[IH_NPAIRS];
     x.perm = x.ih[IH_PERM]; x.palt = x.ih[IH_PALT]; x.err = x.ih[IH_ERR];
+    x.ostate = x.ih[IH_OSTATE]; x.only = R.statesampling ? x.ostate : -1;
     x.det_log = x.dh[DH_DETLOG]; x.det_sign = x.dh[DH_DETSIGN]; x.tr_log = x.dh[DH_TRLOG]; x.tr_sign = x.dh[DH_TRSIGN]; x.cfgsign = x.dh[DH_CFGSIGN];
     x.rng.init(R.seed, R.same_key ? 0u : R.chain_base + (unsigned)chain, C.rng_ctr[chain]);
     set_window_edges(T, R, x);
@@ -1921,7 +2011,7 @@ W2B_HDN void ctx_store(const Chains& C, int chain, Ctx& x) {
     wsync();
     if (lane_id() == 0) {
         x.ih[IH_NOPS] = x.n; x.ih[IH_OUTER] = x.outer; x.ih[IH_WPOS] = x.wpos; x.ih[IH_NPAIRS] = x.npairs;
-        x.ih[IH_PERM] = x.perm; x.ih[IH_PALT] = x.palt; x.ih[IH_ERR] = x.err;
+        x.ih[IH_PERM] = x.perm; x.ih[IH_PALT] = x.palt; x.ih[IH_ERR] = x.err; x.ih[IH_OSTATE] = x.ostate;
         if (C.dmax > 1) { x.ih[IH_KV] = x.kv; x.ih[IH_BV] = x.bv; x.ih[IH_NFREE] = x.nfree; }
         x.dh[DH_DETLOG] = x.det_log; x.dh[DH_DETSIGN] = x.det_sign; x.dh[DH_TRLOG] = x.tr_log; x.dh[DH_TRSIGN] = x.tr_sign; x.dh[DH_CFGSIGN] = x.cfgsign;
         C.rng_ctr[chain] = x.rng.ctr;
@@ -2333,7 +2423,7 @@ W2B_HD void phase_decide(const Tables& T, const Run& R, const Chains& C, const A
         RareJob& J = C.rjob[chain];
         double tn_log, tn_sign;
         x.mpt = C.ptc + (size_t)chain * 2 * C.dmax;
-        parts_sum(x.mpt, ldg(&T.dim[J.new_outer]), tn_log, tn_sign);
+        parts_sum(x.mpt, ldg(&T.dim[J.new_outer]), tn_log, tn_sign, R.statesampling ? J.new_state : -1);
         const int kind = C.kind[chain];
         if (kind == 3) step_glob_finish(T, R, C, x, J, tn_log, tn_sign);
         else if (kind == 4) step_shift_finish(T, R, C, x, J, tn_log, tn_sign);
@@ -2382,13 +2472,26 @@ W2B_HD void init_chain(const Tables& T, const Run& R, const Chains& C, int chain
     const double rand = rng.next();
     double acc = 0.0; int pick = T.nsst - 1;
 #pragma unroll 1
-    for (int i = 0; i < T.nsst; ++i) { double w = T.empty_w[i]; acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
+    for (int i = 0; i < T.nsst && !R.statesampling; ++i) { double w = T.empty_w[i]; acc += w; pick = i; if (acc >= rand && w != 0.0) break; }
+    int pstate = 0;
+    if (R.statesampling) {                 // initial outer (superstate, eigenstate) ~ empty-trace value of the state (Trace.F90:612-643)
+        bool done = false;
+#pragma unroll 1
+        for (int i = 0; i < T.nsst && !done; ++i) {
+#pragma unroll 1
+            for (int j = 0; j < T.dim[i]; ++j) {
+                const double w = w_exp(-(T.evals[T.offset[i] + j] - T.egs) * T.beta) / T.empty_norm;
+                acc += w; pick = i; pstate = j;
+                if (acc >= rand && w != 0.0) { done = true; break; }
+            }
+        }
+    }
 #pragma unroll 1
     for (int i = 0; i < IH_STRIDE; ++i) ih[i] = 0;
-    ih[IH_OUTER] = pick; ih[IH_NPAIRS] = 0;
+    ih[IH_OUTER] = pick; ih[IH_NPAIRS] = 0; ih[IH_OSTATE] = pstate;
 #pragma unroll 1
     for (int f = 0; f <= T.nf; ++f) ih[IH_MSLOT + f] = f;
-    dh[DH_DETLOG] = 0.0; dh[DH_DETSIGN] = 1.0; dh[DH_TRLOG] = T.empty_log[pick]; dh[DH_TRSIGN] = 1.0; dh[DH_CFGSIGN] = -1.0;
+    dh[DH_DETLOG] = 0.0; dh[DH_DETSIGN] = 1.0; dh[DH_TRLOG] = R.statesampling ? -(T.evals[T.offset[pick] + pstate] - T.egs) * T.beta : T.empty_log[pick]; dh[DH_TRSIGN] = 1.0; dh[DH_CFGSIGN] = -1.0;
     C.rng_ctr[chain] = rng.ctr;
 #pragma unroll 1
     for (int i = 0; i < C_NCNT; ++i) C.counters[(size_t)chain * C_NCNT + i] = 0ull;
@@ -2410,8 +2513,10 @@ constexpr int LEG_CHUNK_BIG = 50;
 W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, const Accum& A, Ctx& x, double* acc) {
     const int m = ldg(&T.dim[x.outer]), off = ldg(&T.offset[x.outer]);
     double csum = 0.0;
+    const int only = x.only;                // state sampling: the one outer eigenstate of the configuration (CTQMC.F90:3294-3339, 3106-3110)
 #pragma unroll 1
     for (int j = lane_id(); j < m; j += W2B_WARP) {
+        if (only >= 0 && j != only) continue;
         const double e = x.pt[2 * j + 1] != 0.0 ? w_exp(x.pt[2 * j]) : 0.0;
         atomic_add(&acc[A.o_outerst + off + j], 1.0);
         atomic_add(&acc[A.o_signst + off + j], x.tr_sign * x.pt[2 * j + 1] * x.cfgsign);
@@ -2424,7 +2529,7 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
     if (x.n == 0) {
         const int doff = ldg(&T.dens_off[x.outer]);
 #pragma unroll 1
-        for (int j = lane_id(); j < m; j += W2B_WARP)
+        for (int j = lane_id(); j < m; j += W2B_WARP) if (only < 0 || j == only)
             atomic_add(&acc[A.o_dens + doff + j + j * m], -x.cfgsign * x.pt[2 * j + 1] * x.tr_sign * w_exp(x.pt[2 * j] - x.tr_log));
         return;
     }
@@ -2452,7 +2557,7 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
 #pragma unroll 1
     for (int j = lane_id(); j < m; j += W2B_WARP) {
         const double kl = klg[j] - (e0 - T.egs) * (bh - tauR), bl = blg[j] - (e0 - T.egs) * (tauL - bh);
-        fac[j] = x.tr_sign * (-x.cfgsign) * w_exp(kl + bl - x.tr_log);      // 1 / trval(Trace / TLogTr(kl + bl, -cfgsign))
+        fac[j] = (only >= 0 && j != only) ? 0.0 : x.tr_sign * (-x.cfgsign) * w_exp(kl + bl - x.tr_log);      // 1 / trval(Trace / TLogTr(kl + bl, -cfgsign))
     }
     wsync();
     const int doff = ldg(&T.dens_off[sst]);
@@ -2710,8 +2815,8 @@ W2B_HD void rebuild_chain(const Tables& T, const Run& R, const Chains& C, int ch
     if (sg == 0.0) x.err |= ERR_SINGULAR;
     if (!(x.err & ERR_GLOBAL_QN)) {
         if (T.dmax > 1) {
-            if (x.n > 0) { full_trace(T, x, x.tau, x.code, x.n, x.outer, x.tr_log, x.tr_sign); commit_parts(T, x); }
-            else { x.tr_log = T.empty_log[x.outer]; x.tr_sign = 1.0; empty_parts(T, x, x.outer); }
+            if (x.n > 0) { full_trace(T, x, x.tau, x.code, x.n, x.outer, x.tr_log, x.tr_sign, x.only); commit_parts(T, x); }
+            else { x.tr_log = R.statesampling ? -(T.evals[T.offset[x.outer] + x.ostate] - T.egs) * T.beta : T.empty_log[x.outer]; x.tr_sign = 1.0; empty_parts(T, x, x.outer); }
             slots_reset(C, x);
         } else trace_full_scalar(T, x.tau, x.code, x.sst, x.n, x.outer, x.tr_log, x.tr_sign);
     }

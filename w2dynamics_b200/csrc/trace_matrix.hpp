@@ -341,7 +341,9 @@ W2B_HD void mat_close_parts(const TablesT& T, int sst, double dt, double* K, int
 #endif
 }
 // signed log-sum of the per-outer-state parts (addLogTr, Trace.F90:298-309), lane-parallel
-W2B_HDN void parts_sum(const double* pt, int m, double& tlog, double& tsign) {
+// only >= 0 (state sampling, Trace.F90:5759-5764): the contribution of that single outer state is the trace
+W2B_HDN void parts_sum(const double* pt, int m, double& tlog, double& tsign, int only = -1) {
+    if (only >= 0) { tsign = pt[2 * only + 1]; tlog = tsign != 0.0 ? pt[2 * only] : NEG_HUGE; return; }
     if (m == 1) { tlog = pt[0]; tsign = pt[1]; return; }
     double mx = NEG_HUGE;
 #pragma unroll 1
@@ -357,9 +359,9 @@ W2B_HDN void parts_sum(const double* pt, int m, double& tlog, double& tsign) {
 }
 template <class TablesT>
 W2B_HDN void mat_close(const TablesT& T, int sst, double dt, double* K, int ld, double* klg, const double* B, const double* blg,
-                      double* pw, int m, double* pt, double& tlog, double& tsign) {
+                      double* pw, int m, double* pt, double& tlog, double& tsign, int only = -1) {
     mat_close_parts(T, sst, dt, K, ld, klg, B, blg, pw, m, 0, pt);
-    parts_sum(pt, m, tlog, tsign);
+    parts_sum(pt, m, tlog, tsign, only);
 }
 
 }  // namespace w2b
