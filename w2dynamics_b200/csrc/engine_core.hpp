@@ -87,7 +87,7 @@ constexpr int STREAM_SHIFT = 44;     // draws per chain and solve before two sol
 struct Prop {
     double t1, t2, tau_a, tau_c, factor, dlog, dsign;
     int f, i1, i2, p1, p2, begin_sst, nother, type1;
-    int new_state; double osf;               // outer pair moves with state sampling: chosen outer eigenstate and WeightedOuterStateChoice factor
+    int new_state;                           // outer pair moves with state sampling: chosen outer eigenstate (its WeightedOuterStateChoice factor is folded into `factor`)
 };
 
 // a global move / tau shift between its two halves (prepare -> trace kernel -> finish)
@@ -903,9 +903,11 @@ W2B_HDN void add_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     // NPairs after insertion (CTQMC.F90:3510-3515)
     if (x.npairs < 0) x.npairs = count_pairs_full(T, R, C, x);
     const int np_new = x.npairs + pairs_with(R, x, ta, k, tau_c) + pairs_with(R, x, tc, k, tau_a) + (pairable(R, x, tau_a, tau_c) ? 1 : 0);
-    const double osf = (OUTER && R.statesampling) ? P.osf : 1.0;                // WeightedOuterStateChoice factor (CTQMC.F90:3471-3480, 3527)
-    if (osf == 0.0) { dlog = 0.0; dsign = 0.0; }                                // no outer state could be chosen: rejected whatever the trace
-    const double prob = osf == 0.0 ? 0.0 : fabs(osf * P.factor * (double)(2 * T.nb) / (double)np_new * w_exp(dlog + dr_log));
+    // state sampling, outer moves: P.factor carries the WeightedOuterStateChoice factor (CTQMC.F90:3471-3480, 3527); 0 = no outer state
+    // could be chosen: rejected whatever the trace
+    const bool dead = OUTER && R.statesampling && P.factor == 0.0;
+    if (dead) { dlog = 0.0; dsign = 0.0; }
+    const double prob = dead ? 0.0 : fabs(P.factor * (double)(2 * T.nb) / (double)np_new * w_exp(dlog + dr_log));
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, dlog); log_set(x, 10, dsign); log_set(x, 11, prob);
     log_set(x, 14, np_new); log_set(x, 17, rand);
     if (!(rand < prob)) { log_end(x, 0); return; }
@@ -1064,9 +1066,9 @@ W2B_HDN void rem_decide(const Tables& T, const Run& R, const Chains& C, const Ac
     const double S = Mbuf(C, x, f)[(size_t)p1 * C.ld + p2];
     const double sig = ((p1 - p2) & 1) ? -1.0 : 1.0;
     const double dr_log = w_log(fabs(S)), dr_sign = sgn1(S) * sig;
-    const double osf = (OUTER && R.statesampling) ? P.osf : 1.0;                // CTQMC.F90:3979-3996
-    if (osf == 0.0) { dlog = 0.0; dsign = 0.0; }
-    const double prob = osf == 0.0 ? 0.0 : fabs(osf * P.factor / (double)(2 * T.nb) * w_exp(dlog + dr_log));
+    const bool dead = OUTER && R.statesampling && P.factor == 0.0;              // CTQMC.F90:3979-3996, see add_decide
+    if (dead) { dlog = 0.0; dsign = 0.0; }
+    const double prob = dead ? 0.0 : fabs(P.factor / (double)(2 * T.nb) * w_exp(dlog + dr_log));
     const double rand = x.rng.next();
     log_set(x, 7, dr_log); log_set(x, 8, dr_sign); log_set(x, 9, dlog); log_set(x, 10, dsign); log_set(x, 11, prob); log_set(x, 17, rand);
     if (!(rand < prob)) { log_end(x, 0); return; }
@@ -1673,7 +1675,7 @@ W2B_HDN bool outer_stage(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     int new_state = -1;
     if (R.statesampling) {                 // the new outer eigenstate is drawn inside the new outer superstate (CTQMC.F90:3471-3480, 3979-3996)
         int sn; double osf = wosc(T, x, outer_tau(T, x.tau, n), outer_tau(T, x.sc_tau, nn), x.outer, new_outer, nullptr, sn, new_state);
-        if (lane_id() == 0) { P.osf = osf; P.new_state = new_state; }
+        if (lane_id() == 0) { P.factor = mul_rn(osf, P.factor); P.new_state = new_state; }
     }
     if (T.dmax == 1) {
         double tl, ts;
