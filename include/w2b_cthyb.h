@@ -47,6 +47,8 @@ int w2b_dest_ctqmc(void);
 int w2b_dest_paras(void);
 
 /* ---- Monte-Carlo configurations (CTQMC.F90:9358-9400; per chain, the reference's single chain = chain 0) */
+/* outer_sst: 0-based superstate; outer_state: 1-based eigenstate inside it (Trace.F90:6854, 6918) -- the sampled state with
+   statesampling = 1, otherwise always 1 (the whole superstate is summed). */
 int w2b_get_mc_config_scalars(int chain, int* noper, int* outer_sst, int* outer_state);
 int w2b_get_mc_config(int chain, int n, double* taus, int* orbs, int* spins, int* cas, int* hashybs,
                       int* outer_sst, int* outer_state);
