@@ -122,6 +122,7 @@ struct Chain {
     // accumulators
     std::vector<double> gtau, gleg, histo, dens, outer_hist, sign_hist, contrib_sst, outerstate_hist, signstate_hist, contrib_state;
     std::vector<long long> accpair;
+    int ngiw = 0; std::vector<double> giw;         // MeasGiw: [nf][2 ngiw] complex sums (re, im), frequencies n = -ngiw .. ngiw - 1
     double meas_sign = 0; long long cnt_meas = 0, cnt_steps = 0;
     // replay log
     double* logp = nullptr; long long log_n = 0, log_cap = 0;
@@ -1157,6 +1158,15 @@ struct Chain {
             int k = kf[f]; if (k == 0) continue;
             std::vector<double> tc, ta;
             for (const Op& e : ops) if (e.b * 2 + e.s == f) (e.ca == 1 ? tc : ta).push_back(e.tau);
+            // Matsubara estimator, lookup branch of MeasGtauRem (CTQMC.F90:2400-2414; the non-lookup measure_giw_nfft 1015-1056 sums the same
+            // terms): Giw(n) += -cfgsign M(c, a) exp(i w_n (tau_a - tau_c)), w_n = (2n + 1) pi / beta -- summed directly instead of by NFFT
+            if (ngiw > 0) for (int ia = 0; ia < k; ++ia) for (int ic = 0; ic < k; ++ic) {
+                const double mv = -cfgsign * M[f][ic + (size_t)ia * k], x = (ta[ia] - tc[ic]) / beta;
+                for (int m = 0; m < 2 * ngiw; ++m) {
+                    const double ph = M_PI * (double)(2 * (m - ngiw) + 1) * x;
+                    giw[2 * ((size_t)f * 2 * ngiw + m)] += mv * std::cos(ph); giw[2 * ((size_t)f * 2 * ngiw + m) + 1] += mv * std::sin(ph);
+                }
+            }
             for (int ia = 0; ia < k; ++ia) for (int ic = 0; ic < k; ++ic) {
                 double Mv = M[f][ic + (size_t)ia * k];
                 double dtau = ta[ia] - tc[ic], x; int idt;
@@ -1262,6 +1272,7 @@ struct Chain {
         outer_hist.assign(T.nsst, 0); sign_hist.assign(T.nsst, 0); contrib_sst.assign(T.nsst, 0);
         outerstate_hist.assign(T.nstates, 0); signstate_hist.assign(T.nstates, 0); contrib_state.assign(T.nstates, 0);
         accpair.assign((size_t)nf * ntau, 0);
+        giw.assign((size_t)2 * nf * 2 * ngiw, 0.0);
         meas_sign = 0; cnt_meas = 0;
     }
 };
@@ -1328,6 +1339,8 @@ int orc_randint(void* h, int lo, int hi) { return ((Chain*)h)->randint(lo, hi); 
 unsigned long long orc_rng_counter(void* h) { return ((Chain*)h)->ph.ctr; }
 
 void orc_init_trace(void* h) { ((Chain*)h)->init_trace(); }
+void orc_set_meas_giw(void* h, int ngiw) { Chain* c = (Chain*)h; c->ngiw = ngiw; c->giw.assign((size_t)2 * c->nf * 2 * ngiw, 0.0); }
+void orc_get_giw(void* h, double* out) { Chain* c = (Chain*)h; std::memcpy(out, c->giw.data(), c->giw.size() * sizeof(double)); }
 void orc_set_statesampling(void* h, int on) { ((Chain*)h)->statesampling = on != 0; }     // before orc_init_trace
 int orc_outer_state(void* h) { return ((Chain*)h)->outer_state; }
 void orc_set_taudiffmax(void* h, double t) { ((Chain*)h)->init_window(t); }

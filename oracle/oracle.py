@@ -119,6 +119,9 @@ class OracleChain:
         rc = L.orc_init_rnd(self.h, C.c_int(kind), C.c_uint(seed), C.c_uint(chain), MTLIB.encode())
         if rc != 0:
             raise RuntimeError("oracle RNG init failed (%d); libmtrng.so missing?" % rc)
+        self.ngiw = int(q.get("Niw", 0)) if int(q.get("MeasGiw", 0)) else 0
+        if self.ngiw:
+            L.orc_set_meas_giw(self.h, C.c_int(self.ngiw))
         L.orc_set_statesampling(self.h, C.c_int(int(q.get("statesampling", 0))))        # before the first outer-state choice
         L.orc_init_trace(self.h)
         if q["TaudiffMax"] > 0:
@@ -239,6 +242,10 @@ class OracleChain:
                                       ("gtau", "gleg", "histo", "dens", "outer_hist", "sign_hist", "contrib_sst",
                                        "outerstate_hist", "signstate_hist", "contrib_state")],
                             _p(r["accpair"], C.c_longlong))
+        if self.ngiw:
+            g = np.zeros(2 * nf * 2 * self.ngiw)
+            lib().orc_get_giw(self.h, _p(g, C.c_double))
+            r["giw"] = (g[0::2] + 1j * g[1::2]).reshape(nf, 2 * self.ngiw)
         r.update(self.scalars())
         r.update(self.counters())
         return r
@@ -326,6 +333,8 @@ def normalise(raw, at, beta, want_rho2=False):
     leg = raw["gleg"] * np.sqrt(2.0 * np.arange(nleg) + 1.0)[None, :] / beta
     out["gleg"] = (-leg * zs).reshape(nb, 2, nleg)
     out["hist"] = (raw["histo"] / n).reshape(nb, 2, -1)
+    if "giw" in raw:                                                # Giw *= zScaling / beta, CTQMC.F90:8815-8817
+        out["giw"] = (raw["giw"] * zs / beta).reshape(nb, 2, -1)
     dm = raw["dens"] * zs
     occ, rho1, dm_occ = density_estimators(dm, at)
     out["occ"], out["rho1"], out["densitymatrix"] = occ, rho1, dm_occ

@@ -65,7 +65,7 @@ def _annihilators(nmodes):
     return ops
 
 
-def solve(p, nbins=50, flavours=(0,), nleg=12, want_rho=False):
+def solve(p, nbins=50, flavours=(0,), nleg=12, want_rho=False, niw=0):
     """Returns (gbin[len(flavours), nbins] = EXACT averages of G(tau) over nbins equal tau bins, occ[nb,2,nb,2],
     gleg[len(flavours), nleg] = sqrt(2l+1) int_0^beta P_l(2 tau / beta - 1) G(tau) dtau in closed form).  Mode index: impurity
     flavour i = 2 b + s -> i; bath level q of flavour i -> nf + i * n_bath + q."""
@@ -101,6 +101,7 @@ def solve(p, nbins=50, flavours=(0,), nleg=12, want_rho=False):
     edges = np.linspace(0.0, beta, nbins + 1)
     g = np.zeros((len(flavours), nbins))
     gleg = np.zeros((len(flavours), nleg))
+    giw = np.zeros((len(flavours), 2 * niw), dtype=complex)
     for a, f in enumerate(flavours):
         m2 = (vec.T @ (cd[f] @ vec)) ** 2                             # |<m| c_f^+ |n>|^2
         # G(tau) = 1/Z sum_nm |<m|c+|n>|^2 exp(-(beta - tau) E_n - tau E_m): at tau -> beta the FINAL state's thermal weight counts
@@ -122,10 +123,18 @@ def solve(p, nbins=50, flavours=(0,), nleg=12, want_rho=False):
             with np.errstate(divide="ignore", invalid="ignore"):
                 il = np.where(np.abs(aa) < 1e-12, 1.0 if l == 0 else 0.0, np.sqrt(np.pi / (2.0 * np.abs(aa))) * ive(l + 0.5, np.abs(aa)) * np.sign(aa) ** l)
             gleg[a, l] = np.sqrt(2 * l + 1.0) * beta * (-1.0) ** l * (pref * il).sum()
+        if niw:
+            # int_0^beta exp(i w_n tau) G(tau) dtau = -1/Z sum |<m|c+|n>|^2 (exp(-beta E_m) + exp(-beta E_n)) / (i w_n - (E_m - E_n)):
+            # what MeasGiw accumulates ("giw-meas"; the physical G(i w) is its negative, cthyb_solver.py:814)
+            wn = (2.0 * np.arange(-niw, niw) + 1.0) * np.pi / beta
+            wt = mm * (bw[im] + bw[in_]) / z
+            giw[a] = -(wt[None, :] / (1j * wn[:, None] - de[None, :])).sum(1)
     keep = bw / z > 1e-14
     rho_diag = ((vec[:, keep] ** 2) @ bw[keep]) / z                   # thermal weight of every occupation-number state
     st = np.arange(1 << nm)
     occ = np.array([[(rho_diag * ((st >> i) & 1) * ((st >> j) & 1)).sum() for j in range(nf)] for i in range(nf)])
+    if niw:
+        return g, occ.reshape(nb, 2, nb, 2), gleg, giw
     if not want_rho:
         return g, occ.reshape(nb, 2, nb, 2), gleg
     # one- and two-particle reduced density matrices of the impurity: rho1[i, j] = <c+_i c_j>,

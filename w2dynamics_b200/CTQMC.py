@@ -257,6 +257,11 @@ class MCTQMC:
         d = self._get_dims()
         if name == "sign":
             return self.array("sign_bins")
+        if name == "giw":
+            flat = self.array("giw_bins")
+            nbins = d["nbins"]
+            flat = (flat[0::2] + 1j * flat[1::2]).reshape(nbins, -1)
+            return np.stack([flat[i].reshape((self._nb, 2, -1), order="F") for i in range(nbins)])
         shp = self._ARRAYS[name](d)
         flat = self.array(name + "_bins")
         nb = flat.size // int(np.prod(shp))
@@ -267,6 +272,13 @@ class MCTQMC:
             raise AttributeError(name)
         if name == "accpairtau":
             return self.array("accpairtau")
+        if name == "giw":
+            # MeasGiw != 0: Giw(NBands, 2, -Niw:Niw-1), complex (CTQMC.F90:573, 8815-8817; read at cthyb_solver.py:990); the C ABI hands
+            # complex numbers over as (re, im) pairs
+            if "giw" not in self._cache:
+                raw = self.array("giw")
+                self._cache["giw"] = np.asfortranarray((raw[0::2] + 1j * raw[1::2]).reshape((self._nb, 2, -1), order="F"))
+            return self._cache["giw"]
         if name == "accpair" and int(self.scalar("naccpair")) != self._get_dims()["ntau"]:
             # calibration phase 2 (cthyb_solver.py:914-921): AccPair(Nb, 2, phase2taugrid)
             return np.asfortranarray(np.rint(self.array("accpair", (self._nb, 2, int(self.scalar("naccpair"))))).astype(np.int64))

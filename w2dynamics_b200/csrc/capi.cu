@@ -37,7 +37,7 @@ struct Solver {
     double cfg_taudiffmax = -1;
     std::vector<int> dens_off;
     ResultSet res; bool have_res = false;
-    std::vector<std::vector<double>> bin_gtau, bin_gleg, bin_occ; std::vector<double> bin_sign;
+    std::vector<std::vector<double>> bin_gtau, bin_gleg, bin_occ, bin_giw; std::vector<double> bin_sign;
     std::vector<double> raw_acc; bool bins_ready = false;      // raw accumulator slabs of the last finalize; per-bin results are normalised on first request
     double time_warmup = 0, time_sim = 0, time_sim_steps = 0;
     Rho2Cache rho2cache; bool rho2_ready = false;
@@ -120,7 +120,7 @@ void check_supported(const Params& p) {
     auto zero_i = [&](const char* k) { if (p.has(k) && p.integer(k) != 0) throw std::runtime_error(std::string(k) + " != 0 is outside the implemented hot path"); };
     auto zero_r = [&](const char* k) { if (p.has(k) && p.real(k) != 0.0) throw std::runtime_error(std::string(k) + " != 0 is outside the implemented hot path"); };
     zero_i("segment"); zero_i("offdiag"); zero_i("Uw"); zero_i("Phonon");
-    zero_i("MeasGiw"); zero_i("MeasG2iw"); zero_i("MeasSusz"); zero_i("MeasExpResDensityMatrix"); zero_i("FourPnt");
+    zero_i("MeasG2iw"); zero_i("MeasSusz"); zero_i("MeasExpResDensityMatrix"); zero_i("FourPnt");
     zero_i("MeasSsquare"); zero_i("MeasGtauDetRat"); zero_i("flavourchange_moves"); zero_i("Gtau_mean_step"); zero_i("Gtau_mid_step"); zero_i("sign_step");
     // PercentageOuterMove (outer pair moves, CTQMC.F90:3422-3449, 3934-3961) and Percentage4OperatorMove (StepAdd4 / StepRem4 with
     // diagonal hybridisation, CTQMC.F90:3615-3889, 4153-4430) are implemented
@@ -159,7 +159,7 @@ void finalize_results() {
     normalise_slab(E.at, E.A, E.R, S.beta, tot.data(), S.dens_off, true, S.res, &S.rho2cache);
     // per-bin samples (for error bars across chain groups) are normalised on first request (w2b_get_array "*_bins")
     S.raw_acc.swap(acc); S.bins_ready = false;
-    S.bin_gtau.clear(); S.bin_gleg.clear(); S.bin_occ.clear(); S.bin_sign.clear();
+    S.bin_gtau.clear(); S.bin_gleg.clear(); S.bin_occ.clear(); S.bin_giw.clear(); S.bin_sign.clear();
     // move statistics (CTQMC.F90:8680-8695)
     std::vector<unsigned long long> cnt; E.get_counters(cnt);
     auto ratio = [](unsigned long long a, unsigned long long b) { return b ? (double)a / (double)b : std::numeric_limits<double>::quiet_NaN(); };
@@ -220,6 +220,7 @@ void bins_materialise() {
         if (slab[E.A.o_cnt] <= 0.0) continue;
         ResultSet r; normalise_slab(E.at, E.A, E.R, S.beta, slab, S.dens_off, false, r);
         S.bin_gtau.push_back(r.arr["gtau"]); S.bin_gleg.push_back(r.arr["gleg"]); S.bin_occ.push_back(r.arr["occ"]);
+        if (r.arr.count("giw")) S.bin_giw.push_back(r.arr["giw"]);
         S.bin_sign.push_back(r.scal["mean_sign"]);
     }
     S.bins_ready = true;
@@ -331,6 +332,7 @@ int w2b_init_solver(const double* u_matrix, const double* ftau_full, const doubl
         R.pglob = p.real("PercentageGlobalMove"); R.pshift = p.real("PercentageTauShiftMove");
         R.p4op = p.real_or("Percentage4OperatorMove", 0.0); R.pouter = p.real_or("PercentageOuterMove", 0.0);
         R.statesampling = (p.has("statesampling") && p.integer("statesampling") != 0) ? 1 : 0;
+        R.ngiw = (p.has("MeasGiw") && p.integer("MeasGiw") != 0) ? (int)p.integer("Niw") : 0;       // Giw(NBands, 2, -NGiw:NGiw-1), CTQMC.F90:300, 569-575
         R.ntau = (int)p.integer("Ntau"); R.nlegmax = (int)p.integer("NLegMax"); R.maxhisto = (int)p.integer("MaxHisto");
         R.has_szt = p.str("QuantumNumbers").find("Szt") != std::string::npos;
         R.meas_dm = p.integer("MeasDensityMatrix") != 0;
@@ -709,6 +711,7 @@ int w2b_get_array(const char* name, double* out, size_t cap, size_t* n) {
         if (k.size() > 5 && k.compare(k.size() - 5, 5, "_bins") == 0) bins_materialise();
         if (k == "gtau_bins") bins(S.bin_gtau);
         else if (k == "gleg_bins") bins(S.bin_gleg);
+        else if (k == "giw_bins") bins(S.bin_giw);
         else if (k == "occ_bins") bins(S.bin_occ);
         else if (k == "sign_bins") { tmp = S.bin_sign; src = &tmp; }
         else { auto it = S.res.arr.find(k); if (it == S.res.arr.end()) throw std::runtime_error("unknown result array " + k); src = &it->second; }

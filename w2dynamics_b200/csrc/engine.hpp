@@ -306,6 +306,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) k_measure(Tables T_, Ru
         if (v != 0.0) atomicAdd(&acc[i], v);
     }
 }
+// Matsubara estimator (MeasGiw): grid = (nbins * nsub, nf, frequency tiles of GIW_THREADS * GIW_F); CTA (bin, sub) sums every nsub-th
+// chain of its bin into register accumulators, one atomic per (thread, frequency) at the end
+constexpr int GIW_THREADS = 128;
+__global__ void __launch_bounds__(GIW_THREADS) k_meas_giw(Tables T, Run R, Chains C, Accum A, int nsub) {
+    const int bin = blockIdx.x % R.nbins, sub = blockIdx.x / R.nbins, f = blockIdx.y;
+    const int nfreq = 2 * R.ngiw, m0 = (blockIdx.z * GIW_THREADS + threadIdx.x) * GIW_F;
+    if (m0 >= nfreq) return;
+    double re[GIW_F], im[GIW_F];
+#pragma unroll
+    for (int q = 0; q < GIW_F; ++q) { re[q] = 0.0; im[q] = 0.0; }
+    const int c0 = (int)(((unsigned)bin + (unsigned)R.nbins - R.chain_base % (unsigned)R.nbins) % (unsigned)R.nbins);   // first chain of this bin
+    for (int chain = c0 + R.nbins * sub; chain < C.nchains; chain += R.nbins * nsub) giw_accumulate_chain(T, R, C, chain, f, m0, re, im);
+    double* acc = A.base + (size_t)bin * A.stride + A.o_giw + 2 * ((size_t)f * nfreq + m0);
+#pragma unroll
+    for (int q = 0; q < GIW_F; ++q) if (m0 + q < nfreq) { atomicAdd(&acc[2 * q], re[q]); atomicAdd(&acc[2 * q + 1], im[q]); }
+}
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rebuild(Tables T, Run R, Chains C, int wdoubles, int mdoubles, int only_chain) {
     extern __shared__ double smem[];
     int warp = threadIdx.x >> 5;
@@ -448,6 +464,7 @@ public:
         C.rng_ctr = keep(dev_alloc<unsigned long long>(nc)); C.counters = keep(dev_alloc<unsigned long long>((size_t)nc * C_NCNT));
         C.dmax = at.dmax; C.mstride = at.dmax > 1 ? at.dmax * at.dmax : 0;
         if (at.dmax > MAT_DMAX) throw std::runtime_error("quantum-number blocks larger than 32 are not supported by the tensor trace path (add quantum numbers)");
+        C.ss = R.statesampling;
         C.ldx = mat_ld(at.dmax); C.xdoubles = at.dmax > 1 ? C.ldx * mat_cols(at.dmax) : 0;
         if (at.dmax > 1) {
             C.op_slot = keep(dev_alloc<unsigned short>((size_t)nc * ops_cap)); C.free_slot = keep(dev_alloc<unsigned short>((size_t)nc * ops_cap));
@@ -475,6 +492,7 @@ public:
         A.o_outer = o; o += nsst; A.o_signsst = o; o += nsst; A.o_contribsst = o; o += nsst;
         A.o_outerst = o; o += at.nstates; A.o_signst = o; o += at.nstates; A.o_contribst = o; o += at.nstates;
         A.o_sign = o; o += 1; A.o_cnt = o; o += 1;
+        A.o_giw = o; o += 2 * nf * 2 * R.ngiw;
         accum_doubles = o; A.stride = o;
         A.base = keep(dev_alloc<double>((size_t)R.nbins * o));
         accpair_cap = std::max(R.ntau, 1024);
@@ -842,6 +860,11 @@ public:
         }
         k_measure<<<R.nbins * nsub, WARPS_PER_CTA * 32, sm>>>(T, R, C, A, wdoubles, mat_doubles(C, true), nsub); ++launches;
         C.meas_pre = 0;
+        if (R.ngiw > 0) {
+            const int per_cta = GIW_THREADS * GIW_F, ntile = (2 * R.ngiw + per_cta - 1) / per_cta;
+            const int gsub = std::max(1, std::min(per_bin, (nsm * 16) / std::max(1, R.nbins * T.nf * ntile)));
+            k_meas_giw<<<dim3(R.nbins * gsub, T.nf, ntile), GIW_THREADS>>>(T, R, C, A, gsub); ++launches;
+        }
         W2B_CUDA_CHECK(cudaGetLastError());
 #else
         std::vector<double> ws(wdoubles + 8);
@@ -851,6 +874,15 @@ public:
         }
         for (int c = 0; c < C.nchains; ++c) measure_chain(T, R, C, A, c, ws.data(), (int*)(ws.data() + 3 * C.kcap + mat_doubles(C, true)), ws.data() + 3 * C.kcap);
         C.meas_pre = 0;
+        if (R.ngiw > 0) {                               // same per-thread routine as k_meas_giw, one "thread" per GIW_F frequencies
+            const int nfreq = 2 * R.ngiw;
+            for (int c = 0; c < C.nchains; ++c) for (int f = 0; f < T.nf; ++f) for (int m0 = 0; m0 < nfreq; m0 += GIW_F) {
+                double re[GIW_F] = {0}, im[GIW_F] = {0};
+                giw_accumulate_chain(T, R, C, c, f, m0, re, im);
+                double* acc = A.base + (size_t)((R.chain_base + (unsigned)c) % (unsigned)R.nbins) * A.stride + A.o_giw + 2 * ((size_t)f * nfreq + m0);
+                for (int q = 0; q < GIW_F && m0 + q < nfreq; ++q) { acc[2 * q] += re[q]; acc[2 * q + 1] += im[q]; }
+            }
+        }
 #endif
     }
 

@@ -78,6 +78,7 @@ struct Run {
     int prefetch;                // software prefetch of the next work item's records (0 = off)
     int same_key;                // diagnostics only: every chain uses chain 0's RNG key (identical control flow across warps)
     int nsym;                    // user symmetry moves (NSymMove); the table Tables::symmoves holds them and their inverses
+    int ngiw;                    // MeasGiw != 0: Matsubara frequencies n = -ngiw .. ngiw - 1 of the G(iw) estimator (Niw); 0 = not measured
     int statesampling;           // statesampling = 1: the local trace runs over ONE outer eigenstate (Trace.F90:203, 1477-1604)
     unsigned stream;             // solves since init_rnd: every init_solver draws from a fresh section of each chain's Philox stream
 };
@@ -132,6 +133,7 @@ struct Chains {
     int* q_rfin; int* q_dec0; int* q_dec1; int* q_dec2; int* sched;      // q_rare, q_rfin and the trace queues: one buffer per counter set
     double* ptc;                                               // trace kernel results: per-outer-state parts (log, sign) of the proposed configuration [chain][2*dmax]
     int* q_tr0; int* q_tr1; int* q_tr2;                        // trace jobs (chain | column tile | removal flag) by number of steps: long, medium, short
+    int ss;                                                    // state sampling: trace jobs run for the column tile of the sampled outer eigenstate only
     int meas_pre;                                              // measurement kernel: the cache frontiers already reach beta/2 (extended by trace jobs)
     int ldx, xdoubles;                                         // work matrix: leading dimension (4 mod 16) and size ldx * dmax
 };
@@ -140,6 +142,7 @@ struct Chains {
 struct Accum {
     double* base; long long stride;
     int o_gtau, o_gleg, o_histo, o_dens, o_outer, o_signsst, o_contribsst, o_outerst, o_signst, o_contribst, o_sign, o_cnt;
+    int o_giw;                       // [nf][2 ngiw] complex (re, im) sums of the Matsubara estimator
     unsigned long long* accpair;     // [nf][ntau]
     int ndens;
     double* pairlist; int* pairlist_cnt; int pairlist_cap;      // AccPairTau of ctqmc_calibrate phase 1 (CTQMC.F90:3583-3586, 4123-4126): tau distances of the first accepted pair moves
@@ -515,6 +518,7 @@ W2B_HD void trace_job(const Tables& T, const Chains& C, int entry, double* ws) {
     bool store_seg = false;
     if (meas) {                                                   // kets of the operators with tau <= beta/2, bras of the others (update_b2_states_eb)
         if (n == 0 || nt * TILE_COLS >= ldg(&T.dim[V.outer])) return;
+        if (C.ss && nt != ih[IH_OSTATE] / TILE_COLS) return;     // state sampling: the caches hold the sampled state's column tile only
         i1 = i2 = count_le(V.tau, n, T.beta / 2.0);
     }
     if (rare) {                                                   // whole (relabelled / shifted) sequence from the identity, no caches used
@@ -2281,6 +2285,10 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
             if (state == ST_RARE_TRACE) {                         // first half done: this round's trace kernel runs its jobs, the decide kernel the second half
                 const int new_outer = *(const volatile int*)&C.rjob[chain].new_outer;
                 out->tq = 0; out->tentry = chain | Q_RARE; out->ntl = (ldg(&T.dim[new_outer]) + TRACE_COLS - 1) / TRACE_COLS; out->rfin = 1;
+                if (R.statesampling) {                            // only the column tile that holds the proposed outer eigenstate
+                    const int ns = *(const volatile int*)&C.rjob[chain].new_state;
+                    out->tentry |= ((ns < 0 ? 0 : ns) / TRACE_COLS) << Q_NTSHIFT; out->ntl = 1;
+                }
                 C.parked[chain] = ST_RARE_QUEUED;
             }
         }
@@ -2317,6 +2325,7 @@ W2B_HD void phase_propose(const Tables& T, const Run& R, const Chains& C, int ch
                     const int rem = (entry & Q_REM) ? 1 : 0, s = P.i1, e = P.i2 + rem;
                     const int steps = (x.bv > e ? x.bv - e : 0) + (x.kv <= s - 1 ? s - x.kv : 0) + (P.i2 - P.i1 - rem) + (rem ? 0 : 2);
                     out->tq = steps >= 24 ? 0 : (steps >= 8 ? 1 : 2); out->tentry = entry; out->ntl = (m + TRACE_COLS - 1) / TRACE_COLS;
+                    if (R.statesampling) { out->tentry |= (x.ostate / TRACE_COLS) << Q_NTSHIFT; out->ntl = 1; }       // the sampled state's column tile
                 }
             }
             break;
@@ -2568,7 +2577,7 @@ W2B_HDN void measure_blocked(const Tables& T, const Run& R, const Chains& C, con
         const int a = e % d, c = e / d;
         double v = 0.0;
 #pragma unroll 1
-        for (int j = 0; j < m; ++j) v += B[a + (size_t)j * d] * K[c + (size_t)j * d] * fac[j];
+        for (int j = (only >= 0 ? only : 0); j < (only >= 0 ? only + 1 : m); ++j) v += B[a + (size_t)j * d] * K[c + (size_t)j * d] * fac[j];
         atomic_add(&acc[A.o_dens + doff + a + c * d], v);
     }
     wsync();
@@ -2778,6 +2787,40 @@ W2B_HD void measure_chain(const Tables& T, const Run& R, const Chains& C, const 
             for (int q = 0; q < LEG_CHUNK; ++q) {
                 double s = wsum(part[q]);
                 if (lane == 0 && lbase + q < R.nlegmax) atomic_add(gleg_sh ? &gleg_sh[f * R.nlegmax + lbase + q] : &acc[A.o_gleg + f * R.nlegmax + lbase + q], s);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ Matsubara estimator (MeasGiw; CTQMC.F90:2400-2414, measure_giw_nfft 1015-1056)
+// Giw(b, s, n) += sum over (annihilator a, creator c) pairs of the flavour:  -cfgsign M(c, a) exp(i w_n (tau_a - tau_c)),  w_n = (2n + 1) pi / beta,
+// n = -Niw .. Niw - 1.  The reference evaluates these sums with NFFT (non-equispaced FFT, Nfft_z.F90:133-200, an approximation to ~1e-12);
+// here they are summed DIRECTLY: one thread owns GIW_F consecutive frequencies, starts each pair with one sincospi (exact argument
+// reduction) and steps through its frequencies with the pair's phase factor exp(2 pi i (tau_a - tau_c) / beta) -- 6 FP64 operations per
+// (pair, frequency).  A CTA serves chains of ONE bin and keeps its partial sums in registers over all of them: one atomic per
+// (thread, frequency) at the end instead of one per chain.
+constexpr int GIW_F = 8;
+W2B_HD void giw_accumulate_chain(const Tables& T, const Run& R, const Chains& C, int chain, int f, int m0, double* re, double* im) {
+    const int* ih = C.ih + (size_t)chain * IH_STRIDE;
+    const int k = ih[IH_KF + f];
+    if (k == 0) return;
+    const double ms = -C.dh[(size_t)chain * DH_STRIDE + DH_CFGSIGN];
+    const double* tc = C.tau_c + ((size_t)chain * T.nf + f) * C.kcap; const double* ta = C.tau_a + ((size_t)chain * T.nf + f) * C.kcap;
+    const double* M = C.M + ((size_t)chain * (T.nf + 1) + ih[IH_MSLOT + f]) * ((size_t)C.kcap * C.ld);
+    const double ib = 1.0 / T.beta, odd = (double)(2 * (m0 - R.ngiw) + 1);
+#pragma unroll 1
+    for (int ic = 0; ic < k; ++ic) {
+        const double t_c = tc[ic];
+#pragma unroll 1
+        for (int ia = 0; ia < k; ++ia) {
+            const double x = (ta[ia] - t_c) * ib, mv = ms * M[(size_t)ic * C.ld + ia];
+            double zs, zc, ss, sc;
+            w_sincospi(odd * x, zs, zc);                     // exp(i w_{m0} (tau_a - tau_c))
+            w_sincospi(2.0 * x, ss, sc);                     // step to the next frequency
+#pragma unroll
+            for (int q = 0; q < GIW_F; ++q) {
+                re[q] += mv * zc; im[q] += mv * zs;
+                const double nc = zc * sc - zs * ss; zs = zc * ss + zs * sc; zc = nc;
             }
         }
     }

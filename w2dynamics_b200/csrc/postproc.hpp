@@ -76,6 +76,14 @@ inline void normalise_slab(const AtomicTables& at, const Accum& A, const Run& R,
             gleg[bs + (size_t)nf * l] = -(slab[A.o_gleg + f * nleg + l] * std::sqrt(2.0 * l + 1.0) / beta) * zs;
         for (int k = 0; k < nh; ++k) histo[bs + (size_t)nf * k] = slab[A.o_histo + f * nh + k] / cnt;   // 8755
     }
+    if (R.ngiw > 0) {                                                          // Giw *= zScaling / beta (CTQMC.F90:8815-8817); (re, im) pairs, element (b, s, n) Fortran order
+        const int nfreq = 2 * R.ngiw;
+        auto& giw = out.arr["giw"]; giw.assign((size_t)2 * nf * nfreq, 0.0);
+        for (int b = 0; b < nb; ++b) for (int s = 0; s < 2; ++s) for (int m = 0; m < nfreq; ++m) {
+            const size_t e = (b + (size_t)nb * s) + (size_t)nf * m, src = (size_t)A.o_giw + 2 * ((size_t)(2 * b + s) * nfreq + m);
+            giw[2 * e] = slab[src] * zs / beta; giw[2 * e + 1] = slab[src + 1] * zs / beta;
+        }
+    }
     auto div = [](double a, double b) { return a / b; };
     auto& oh = out.arr["outersuperstatehisto"]; oh.resize(nsst); auto& sh = out.arr["signhistosuperstates"]; sh.resize(nsst);
     auto& ch = out.arr["tracecontribsuperstates"]; ch.resize(nsst);

@@ -151,6 +151,12 @@ W2B_HD long long ldg(const long long* p) { return *p; }
 W2B_HDN double w_log(double x) { return log(x); }
 W2B_HDN double w_exp(double x) { return exp(x); }
 W2B_HDN double wsumd(double x) { return wsum(x); }
+// sin(pi t), cos(pi t) with exact argument reduction
+#if W2B_DEVICE
+W2B_HD void w_sincospi(double t, double& s, double& c) { sincospi(t, &s, &c); }
+#else
+W2B_HD void w_sincospi(double t, double& s, double& c) { const double r = t - 2.0 * std::floor(0.5 * t); s = std::sin(M_PI * r); c = std::cos(M_PI * r); }
+#endif
 
 // Unfused multiply / add: proposal times must be bit-identical to a CPU evaluation of the reference formulas
 // (nvcc would contract a*b+c into one FMA; times feed exact comparisons and integer bookkeeping).
