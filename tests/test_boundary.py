@@ -260,7 +260,15 @@ def body_four_operator_moves(make, cfg, nsteps, beta=None, **opts):
     idx = np.nonzero((log[:, 0] >= 7) & (log[:, 1] == 1) & (np.arange(log.shape[0]) > 0))[0]
     assert (np.abs(log[idx, 12] - log[idx - 1, 12]) == 4).all()     # an accepted 4-operator move changes the number of operators by four
     assert eng.scalar("error_flags") == 0
-    # state after thousands of mixed moves: inverse matrices against the oracle's (fast updates + from-scratch rebuilds on both sides)
+    # accepted 4-operator moves update the stored inverses by the rank-2 (two-step bordering / Schur-complement) update; the from-scratch
+    # re-inversion of the reference (CTQMC.F90:3856-3866) only serves as the fall-back for a vanishing intermediate pivot
+    n4 = eng.scalar("cnt_acc_add4") + eng.scalar("cnt_acc_rem4")
+    if opts.get("four_rank2", 1):
+        assert eng.scalar("cnt_four_rank2") >= 0.9 * n4 and (n4 == 0 or eng.scalar("cnt_four_rank2") > 0)
+    else:
+        assert eng.scalar("cnt_four_rank2") == 0
+    # state after thousands of mixed moves: inverse matrices against the oracle's (fast updates on the engine's side, fast updates +
+    # from-scratch rebuilds on the oracle's)
     for f in range(2 * p.nbands):
         a, b = eng.debug_minv(5, f // 2 + 1, f % 2 + 1), orc.minv(f)
         assert a.shape == b.shape and (a.size == 0 or np.abs(a - b).max() < 1e-8 * max(1.0, np.abs(b).max()))
@@ -269,7 +277,7 @@ def body_four_operator_moves(make, cfg, nsteps, beta=None, **opts):
 
 # ------------------------------------------------------------------ CPU (host-emulation build of the same sources)
 @pytest.mark.parametrize("cfg,nsteps,beta,opts", [("C2", 5000, None, {}), ("C3", 4000, None, {}), ("C3", 4000, 3.0, {}), ("C4", 2000, 2.0, {}),
-                                                  ("C2", 4000, 4.0, {"scheduler": 2}), ("C2", 4000, 4.0, {"scheduler": 3})])
+                                                  ("C2", 4000, 4.0, {"scheduler": 2}), ("C2", 4000, 4.0, {"scheduler": 3}), ("C3", 4000, 3.0, {"four_rank2": 0})])
 def test_four_operator_moves(built, cfg, nsteps, beta, opts):
     body_four_operator_moves(_hostemu_engine, cfg, nsteps, beta, **opts)
 

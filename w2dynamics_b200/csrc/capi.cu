@@ -30,6 +30,7 @@ struct Solver {
     int device = -1;
     int same_key = 0;
     int prefetch = 1;
+    int four_rank2 = 1;
     int time_kernels = 0;
     int propose_run = 4;
     // derived
@@ -167,6 +168,7 @@ void finalize_results() {
     accadd[0] = ratio(cnt[C_ACCADD], cnt[C_TRYADD]); accrem[0] = ratio(cnt[C_ACCREM], cnt[C_TRYREM]);
     S.res.arr["accadd"] = accadd; S.res.arr["accrem"] = accrem;
     S.res.scal["accglob"] = ratio(cnt[C_ACCGLOB], cnt[C_TRYGLOB]); S.res.scal["accshift"] = ratio(cnt[C_ACCSHIFT], cnt[C_TRYSHIFT]);
+    S.res.scal["four_rank2_updates"] = (double)cnt[C_FOUR_RANK2];
     S.res.scal["accadd4"] = ratio(cnt[C_ACCADD4], cnt[C_TRYADD4]); S.res.scal["accrem4"] = ratio(cnt[C_ACCREM4], cnt[C_TRYREM4]);   // AccAdd4 / TryAdd4: NaN without 4-operator moves, as in the reference
     S.res.scal["accflavc"] = std::numeric_limits<double>::quiet_NaN();
     S.res.scal["steps"] = (double)cnt[C_STEPS];
@@ -297,6 +299,7 @@ int w2b_set_option(const char* key, double value) {
     else if (k == "nmeas_override") S.nmeas_override = (long long)value;
     else if (k == "debug_same_key") S.same_key = (int)value;
     else if (k == "prefetch") S.prefetch = (int)value;
+    else if (k == "four_rank2") S.four_rank2 = (int)value;
     else if (k == "time_kernels") { S.time_kernels = (int)value; if (S.eng) { S.eng->time_kernels = value != 0; S.eng->ms_propose = S.eng->ms_trace = S.eng->ms_decide = 0; } }
     else if (k == "propose_run") S.propose_run = (int)value;
     else if (k == "reuse_population") S.reuse_population = (int)value;
@@ -339,7 +342,7 @@ int w2b_init_solver(const double* u_matrix, const double* ftau_full, const doubl
         R.nbins = std::max(1, std::min(S.opt.nbins, S.opt.nchains));
         EngineOptions opt = S.opt;
         if (G.nranks > 1) opt.chain_base += (unsigned)G.rank * (unsigned)opt.nchains;      // chains shard over ranks by global chain id
-        R.seed = (unsigned)S.seed; R.chain_base = opt.chain_base; R.same_key = S.same_key; R.prefetch = S.prefetch; R.propose_run = S.propose_run > 0 ? S.propose_run : 1;
+        R.seed = (unsigned)S.seed; R.chain_base = opt.chain_base; R.same_key = S.same_key; R.prefetch = S.prefetch; R.four_rank2 = S.four_rank2; R.propose_run = S.propose_run > 0 ? S.propose_run : 1;
         R.stream = S.nsolve++;
         // user symmetry moves (symm_to_pstring cthyb_solver.py:769-774; init_Trace Trace.F90:403-404, 471-478): NSymMove lists of 2 Nb
         // target indices (b + Nb s + 1), followed by their inverses
@@ -759,7 +762,7 @@ int w2b_get_scalar(const char* name, double* out) {
             if (k == "blocked") { *out = E.C.dmax > 1 ? 1.0 : 0.0; return; }
             if (k.rfind("cnt_", 0) == 0) {
                 static const char* names[C_NCNT] = {"try_add", "try_rem", "try_glob", "try_shift", "acc_add", "acc_rem", "acc_glob", "acc_shift",
-                                                    "qn_add", "qn_rem", "qn_glob", "steps", "alg_bytes", "trace_flops", "try_add4", "acc_add4", "try_rem4", "acc_rem4"};
+                                                    "qn_add", "qn_rem", "qn_glob", "steps", "alg_bytes", "trace_flops", "try_add4", "acc_add4", "try_rem4", "acc_rem4", "four_rank2"};
                 std::vector<unsigned long long> cnt; E.get_counters(cnt);
                 for (int i = 0; i < C_NCNT; ++i) if (k.substr(4) == names[i]) { *out = (double)cnt[i]; return; }
             }

@@ -36,7 +36,7 @@ namespace w2b {
 
 constexpr int LOGW = 20;      // doubles per replay-log record (same layout as oracle/chain.cpp)
 constexpr int NF_MAX = 14;
-enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_ALGBYTES, C_TRFLOPS, C_TRYADD4, C_ACCADD4, C_TRYREM4, C_ACCREM4, C_NCNT };
+enum { C_TRYADD = 0, C_TRYREM, C_TRYGLOB, C_TRYSHIFT, C_ACCADD, C_ACCREM, C_ACCGLOB, C_ACCSHIFT, C_QNADD, C_QNREM, C_QNGLOB, C_STEPS, C_ALGBYTES, C_TRFLOPS, C_TRYADD4, C_ACCADD4, C_TRYREM4, C_ACCREM4, C_FOUR_RANK2, C_NCNT };
 enum { IH_NOPS = 0, IH_OUTER, IH_WPOS, IH_NPAIRS, IH_PERM, IH_PALT, IH_ERR, IH_KV, IH_KF = 8, IH_MSLOT = IH_KF + NF_MAX, IH_BV = IH_MSLOT + NF_MAX + 1, IH_NFREE, IH_OSTATE, IH_STRIDE };   // IH_OSTATE: outer eigenstate inside the outer superstate (state sampling; else 0)
 enum { DH_DETLOG = 0, DH_DETSIGN, DH_TRLOG, DH_TRSIGN, DH_CFGSIGN, DH_STRIDE = 8 };
 enum { ERR_CAPACITY = 1, ERR_DETRAT_SMALL = 2, ERR_PAIR_LOGIC = 4, ERR_GLOBAL_QN = 8, ERR_SINGULAR = 16 };
@@ -79,6 +79,7 @@ struct Run {
     int same_key;                // diagnostics only: every chain uses chain 0's RNG key (identical control flow across warps)
     int nsym;                    // user symmetry moves (NSymMove); the table Tables::symmoves holds them and their inverses
     int ngiw;                    // MeasGiw != 0: Matsubara frequencies n = -ngiw .. ngiw - 1 of the G(iw) estimator (Niw); 0 = not measured
+    int four_rank2;              // accepted 4-operator moves: rank-2 update of the stored inverses (1, default) or re-inversion from scratch as the reference does (0)
     int statesampling;           // statesampling = 1: the local trace runs over ONE outer eigenstate (Trace.F90:203, 1477-1604)
     unsigned stream;             // solves since init_rnd: every init_solver draws from a fresh section of each chain's Philox stream
 };
@@ -1945,6 +1946,50 @@ W2B_HDN bool four_prepare(const Tables& T, const Run& R, const Chains& C, Ctx& x
     return true;
 }
 // second half: Metropolis; on acceptance the staged configuration replaces the stored one and the inverse matrices are rebuilt
+// Rank-2 UPDATE of the inverse matrices for an accepted 4-operator move (the reference re-inverts every flavour from scratch,
+// CTQMC.F90:3856-3866): the block (Woodbury) update of a flavour that gains / loses two rows and columns is applied in factored form,
+// as two successive bordering / Schur-complement steps on the stored inverse (det_ratio_add + mat_add, or mat_rem on the pivot), O(k^2)
+// instead of O(nf k^3); a flavour that gains / loses one pair takes one step.  The pairs are taken in time order (earliest new creator
+// with earliest new annihilator).  Returns false -- the caller then re-inverts from scratch -- when an intermediate pivot is too small
+// for the factored form (|S| < 1e-6: the 2 x 2 Schur complement can be regular while its leading element vanishes).
+// On success x.tc / x.ta hold the proposed flavour arrays (x.sc_tc / x.sc_ta) and IH_KF the proposed orders.
+W2B_HDN bool four_update_rank2(const Tables& T, const Chains& C, Ctx& x, const RareJob& J) {
+#pragma unroll 1
+    for (int f = 0; f < T.nf; ++f) {
+        const int knew = J.knew[f];
+        double* tc = x.tc + (size_t)f * C.kcap; double* ta = x.ta + (size_t)f * C.kcap;
+        const double* nc = x.sc_tc + (size_t)f * C.kcap; const double* na = x.sc_ta + (size_t)f * C.kcap;
+#pragma unroll 1
+        while (x.ih[IH_KF + f] < knew) {                          // one bordering step: the earliest missing creator / annihilator
+            const int k = x.ih[IH_KF + f];
+            int p1 = 0, p2 = 0;
+            while (p1 < k && tc[p1] == nc[p1]) ++p1;
+            while (p2 < k && ta[p2] == na[p2]) ++p2;
+            const double tau_c = nc[p1], tau_a = na[p2];
+            const double S = det_ratio_add(T, C, x, f, tau_c, tau_a);
+            if (!(fabs(S) >= 1e-6)) return false;
+            bump_bytes(x, 8ll * (2 * k * k + (k + 1) * (k + 1)));
+            mat_add(C, x, f, T.nf, p1, p2, S);
+            shift_up(tc, p1, k, 1); shift_up(ta, p2, k, 1);
+            if (lane_id() == 0) { tc[p1] = tau_c; ta[p2] = tau_a; }
+            wsync();
+        }
+#pragma unroll 1
+        while (x.ih[IH_KF + f] > knew) {                          // one Schur-complement step: the earliest surplus creator / annihilator
+            const int k = x.ih[IH_KF + f];
+            int p1 = 0, p2 = 0;
+            while (p1 < k - 1 && tc[p1] == nc[p1]) ++p1;
+            while (p2 < k - 1 && ta[p2] == na[p2]) ++p2;
+            const double piv = Mbuf(C, x, f)[(size_t)p1 * C.ld + p2];
+            if (!(fabs(piv) >= 1e-6)) return false;
+            bump_bytes(x, 8ll * (k * k + (k - 1) * (k - 1)));
+            mat_rem(C, x, f, T.nf, p1, p2);
+            shift_down(tc, p1, k, 1); shift_down(ta, p2, k, 1);
+            wsync();
+        }
+    }
+    return true;
+}
 W2B_HDN void four_finish(const Tables& T, const Run& R, const Chains& C, Ctx& x, RareJob& J, double tn_log, double tn_sign) {
     const int nf = T.nf, nn = J.nnew;
     const double dr_log = J.dn_log - x.det_log, dr_sign = J.dn_sign * x.det_sign;
@@ -1955,19 +2000,26 @@ W2B_HDN void four_finish(const Tables& T, const Run& R, const Chains& C, Ctx& x,
     if (!(rand < prob)) { log_end(x, 0); return; }
 #pragma unroll 1
     for (int i = lane_id(); i < nn; i += W2B_WARP) { x.tau[i] = x.sc_tau[i]; x.code[i] = x.sc_code[i]; x.sst[i] = x.sc_sst[i]; }
-#pragma unroll 1
-    for (int f = 0; f < nf; ++f) {
-        const int k = J.knew[f];
-#pragma unroll 1
-        for (int i = lane_id(); i < k; i += W2B_WARP) { x.tc[(size_t)f * C.kcap + i] = x.sc_tc[(size_t)f * C.kcap + i]; x.ta[(size_t)f * C.kcap + i] = x.sc_ta[(size_t)f * C.kcap + i]; }
-    }
-    wsync();
-    if (lane_id() == 0) for (int f = 0; f < nf; ++f) x.ih[IH_KF + f] = J.knew[f];
     wsync();
     x.n = nn;
-    double l2, s2;
-    rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);       // get_InvFullHybr: inverse matrices AND determinant from scratch (CTQMC.F90:3856-3866)
-    x.det_log = l2; x.det_sign = s2; x.tr_log = tn_log; x.tr_sign = tn_sign;
+    if (R.four_rank2 && four_update_rank2(T, C, x, J)) {                     // rank-2 update of the stored inverses; the determinant follows the rank-2 ratio
+        x.det_log = J.dn_log; x.det_sign = J.dn_sign;
+        bump(x, C_FOUR_RANK2);
+    } else {
+#pragma unroll 1
+        for (int f = 0; f < nf; ++f) {
+            const int k = J.knew[f];
+#pragma unroll 1
+            for (int i = lane_id(); i < k; i += W2B_WARP) { x.tc[(size_t)f * C.kcap + i] = x.sc_tc[(size_t)f * C.kcap + i]; x.ta[(size_t)f * C.kcap + i] = x.sc_ta[(size_t)f * C.kcap + i]; }
+        }
+        wsync();
+        if (lane_id() == 0) for (int f = 0; f < nf; ++f) x.ih[IH_KF + f] = J.knew[f];
+        wsync();
+        double l2, s2;
+        rebuild_inverses(T, C, x, x.tc, x.ta, x.ih + IH_KF, true, l2, s2);   // get_InvFullHybr: inverse matrices AND determinant from scratch (CTQMC.F90:3856-3866)
+        x.det_log = l2; x.det_sign = s2;
+    }
+    x.tr_log = tn_log; x.tr_sign = tn_sign;
     if (T.dmax > 1) { commit_parts(T, x); slots_reset(C, x); }
     x.npairs = J.np_new;
     x.perm = perm_full(x.code, x.n);
