@@ -62,12 +62,13 @@ int w2b_set_empty_mc_config(int chain, int outer_sst, int outer_state);
  * eigenstatesenergies occbasismapping outersuperstatehisto outerstatehisto signhistosuperstates signhistostates
  * tracecontribsuperstates tracecontribstates accadd accrem accpair densitymatrix rho1 rho2 ;
  * gtau_blocks (Nb,2,Ntau,levels) when AccumGtau = 2 (autocorracc, Accumulators.F90:214-364; CTQMC.F90:8733-8739) ;
- * additionally per-bin samples gtau_bins gleg_bins occ_bins sign_bins (leading extents as the quantity, last = bin). */
+ * giw (MeasGiw != 0: Giw(NBands, 2, -Niw:Niw-1), CTQMC.F90:573, 8815-8817) as (re, im) pairs = the storage of a complex(8) array ;
+ * additionally per-bin samples gtau_bins gleg_bins occ_bins sign_bins giw_bins (leading extents as the quantity, last = bin). */
 int w2b_get_array(const char* name, double* out, size_t cap, size_t* n);
 /* scalars: mean_sign accglob accshift accadd4 accrem4 accflavc time_warmup time_sim time_sim_steps
  * aborted (0, or after SIGTERM / SIGINT / SIGUSR1 during sampling: 1 = stopped with some measurements, 2 = with none; the traps are armed by
  *          init_solver and restored by dest_ctqmc -- register_trap CTQMC.F90:8076-8078, polls 8214 / 8430, truncation 8648-8658)
- * and engine diagnostics nchains nbins nsst nstates nstatesmax kcap max_k max_ops moves_per_chain gpu_launches */
+ * and engine diagnostics nchains nbins nsst nstates nstatesmax kcap max_k max_ops moves_per_chain gpu_launches cnt_<counter> */
 int w2b_get_scalar(const char* name, double* out);
 
 /* ---- rank combination: replaces the per-quantity mpi4py Allreduce of DistributedSample (w2dyn/auxiliaries/statistics.py:95-132)

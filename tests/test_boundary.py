@@ -41,7 +41,7 @@ def _start(eng, p, nchains=8, nbins=4, seed=43890, init_rnd=True, **opts):
     return eng
 
 
-def body_fresh_streams(make):
+def body_fresh_streams(make, bit_exact=True):
     p = problems.make_problem("C1", nftau=501, Nmeas=20, Ntau=50, NLegMax=10)
     eng = make()
     res = []
@@ -52,7 +52,12 @@ def body_fresh_streams(make):
         res.append(eng.gtau.copy())
         eng.dest_ctqmc()
     assert not np.array_equal(res[0], res[1]) and not np.array_equal(res[1], res[2]) and not np.array_equal(res[0], res[2])
-    assert np.array_equal(res[0], res[3])                       # init_rnd restarts the streams: replay tests stay reproducible
+    # init_rnd restarts the streams: replay tests stay reproducible.  The chains walk bit-identical paths; on the GPU the G(tau) bins are
+    # summed with floating-point atomics from several warps, whose order is not fixed (seen once in 20 GPU runs: last-bit differences)
+    if bit_exact:
+        assert np.array_equal(res[0], res[3])
+    else:
+        assert np.abs(res[0] - res[3]).max() <= 1e-13 * np.abs(res[0]).max() and np.abs(res[0] - res[1]).max() > 1e-3 * np.abs(res[0]).max()
 
 
 def body_aborted(make):
@@ -318,7 +323,7 @@ def test_argument_validation(built):
 # ------------------------------------------------------------------ GPU (CUDA library through the C ABI)
 @pytest.mark.gpu
 def test_gpu_fresh_streams_per_solve(built):
-    body_fresh_streams(_cuda_engine)
+    body_fresh_streams(_cuda_engine, bit_exact=False)
 
 
 @pytest.mark.gpu
