@@ -88,10 +88,12 @@ def _c1_inputs(taudiffmax):
     qmc.update(Nwarmups=2000, Nmeas=150, NCorr=50, Ntau=200, NLegMax=40, NLegOrder=40, Niw=niw, Nftau=501,
                TaudiffMax=p.qmc["TaudiffMax"] if taudiffmax == "fixed" else -1.0,   # -1 (the default): ctqmc_calibrate path
                AccumGtau=2 if taudiffmax == "fixed" else 1)                           # 2: autocorrelation accumulator -> "gtau-blocks"
+    if taudiffmax == "giw":             # Z-space Matsubara estimator: Giw(NBands, 2, -Niw:Niw-1) has to match the problem's niw frequencies
+        qmc.update(TaudiffMax=p.qmc["TaudiffMax"], MeasGiw=1, Niw=niw // 2)
     return p, qmc, niw
 
 
-@pytest.mark.parametrize("taudiffmax", ["fixed", "calibrate"])
+@pytest.mark.parametrize("taudiffmax", ["fixed", "calibrate", "giw"])
 def test_restated_sequence_equals_plugin(built, taudiffmax):
     """tests/_plugin_sequence.py (what the `-m gpu` boundary tests drive the CUDA library with, /root/reference being absent on the
     GPU box) issues exactly the calls of the real, unmodified CtHybSolver: same subroutines, same order, same argument values,
@@ -114,7 +116,7 @@ def test_restated_sequence_equals_plugin(built, taudiffmax):
     interaction = inter.Density(nb, 2.0, 0.0, 0.0)
     interaction.quantum_numbers = ("auto",) + interaction.auto_quantum_numbers
     problem = imp.ImpurityProblem(beta, np.zeros((niw, nb, 2, nb, 2), complex), np.zeros((niw, nb, 2, nb, 2), complex), screening, ftau5, muimp, interaction)
-    config = {"QMC": qmc, "General": {"FTType": "legendre", "beta": beta}, "Atoms": {"1": {"Nd": nb}}}
+    config = {"QMC": qmc, "General": {"FTType": "none" if taudiffmax == "giw" else "legendre", "beta": beta}, "Atoms": {"1": {"Nd": nb}}}
     solver = cs.CtHybSolver(config, 43890, 0, 0, 0, interactive=False, mpi_comm=_Comm())
     solver.set_problem(problem)
     cfg_a = []
@@ -137,7 +139,7 @@ def test_restated_sequence_equals_plugin(built, taudiffmax):
         sys.modules.pop(k, None)
 
 
-@pytest.mark.parametrize("taudiffmax", ["fixed", "calibrate"])
+@pytest.mark.parametrize("taudiffmax", ["fixed", "calibrate", "giw"])
 def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
     from w2dynamics_b200 import problems
     eng = _engine()
@@ -149,7 +151,8 @@ def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
 
     p, qmc, niw = _c1_inputs(taudiffmax)
     nb, beta = 1, p.beta
-    config = {"QMC": qmc, "General": {"FTType": "legendre", "beta": beta}, "Atoms": {"1": {"Nd": nb}}}
+    # "giw": MeasGiw = 1 with FTType = none -- the plugin takes G(iw) = -ctqmc.giw (cthyb_solver.py:813-814, 989-990), no transform
+    config = {"QMC": qmc, "General": {"FTType": "none" if taudiffmax == "giw" else "legendre", "beta": beta}, "Atoms": {"1": {"Nd": nb}}}
     iw = tf.matfreq(beta, "fermi", niw)
     tau = np.linspace(0, beta, 501)
     fiw, ftau = tf.hybr_from_sites(p.eps_bath, p.v_bath[:, None], iw, tau, beta)       # (nb, nb, niw), (nb, nb, ntau)
@@ -188,6 +191,11 @@ def test_unmodified_cthybsolver_runs_on_engine(built, taudiffmax):
     # G(iw) from the Legendre coefficients: particle-hole symmetric problem -> purely imaginary, negative imaginary part
     g = giw[niw // 2:niw // 2 + 10, 0, 0, 0, 0]
     assert np.all(g.imag < 0) and np.abs(g.real).max() < 0.08
+    if taudiffmax == "giw":             # the measured G(iw) is the Fourier integral of the measured G(tau) (200 bins: 3 % at the lowest frequencies)
+        assert "giw-meas" in result.other and result.other["giw-meas"].mean().shape == (nb, 2, niw)
+        tmid = (np.arange(200) + 0.5) * beta / 200
+        ft = -(gtau[0, 0][None, :] * np.exp(1j * iw[niw // 2:niw // 2 + 5, None] * tmid[None, :])).sum(1) * beta / 200
+        assert np.abs(ft - g[:5]).max() < 0.03 * np.abs(g[:5]).max()
     if taudiffmax == "fixed":           # cthyb_solver.py:1024-1026 reads ctqmc.gtau_blocks; ilog2(150) = 7 binning levels
         blocks = result.other["gtau-blocks"].mean()
         assert blocks.shape == (nb, 2, 200, 7) and np.all(blocks[..., 0] >= 0) and np.all(np.isfinite(blocks[..., :5]))

@@ -140,6 +140,8 @@ class PluginSequence:
         result = {}
         for key, attr in RESULT_READS:
             result[key] = getattr(c, attr)
+        if q.get("MeasGiw", 0) != 0 and q["offdiag"] == 0:                   # 989-990
+            result["giw-meas"] = c.giw
         if q["MeasDensityMatrix"] != 0 and q["segment"] == 0:
             result["densitymatrix"] = c.densitymatrix
             result["rho2"] = c.rho2.reshape((norbitals, 2) * 4)
