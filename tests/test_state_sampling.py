@@ -158,3 +158,27 @@ def test_state_sampling_measurement(built, cfg, beta):
 @pytest.mark.parametrize("cfg,beta", [("C2", 4.0), ("C3", 3.0), ("C4", 2.0)])
 def test_gpu_state_sampling_measurement(built, cfg, beta):
     body_measurement(_cuda_engine, cfg, beta)
+
+
+def test_state_sampling_exact_diagonalisation_host_emulation(built):
+    """The kernel sources (host-emulation build) with state sampling and every optional move type on the DEGENERATE two-orbital Kanamori
+    model against exact diagonalisation (tests/_exact_anderson.py): per-move parity with the oracle is basis dependent there (module
+    docstring), the sampled distribution is not.  The same comparison runs on the GPU with 4096 chains (tests/test_gpu_exact.py)."""
+    import _exact_anderson as ea
+    p = ea.kanamori2_problem(2, 6.0, Nmeas=150, Ntau=1000, statesampling=1, PercentageOuterMove=0.2, Percentage4OperatorMove=0.2)
+    gex, occ_ex, _ = ea.solve_cached(("K2", 2, 6.0), p)
+    eng = _start(_hostemu_engine(), p, nchains=512, nbins=16)
+    eng.init_counters()
+    eng.ctqmc_warmup(4000)
+    eng.ctqmc_measure(1, 1)
+    assert eng.scalar("error_flags") == 0
+    gb = eng.bins("gtau").reshape(16, 4, 50, 20).mean(3).mean(1)
+    g, gerr = gb.mean(0), gb.std(0, ddof=1) / 4.0
+    ob = eng.bins("occ")
+    occ, oerr = ob.mean(0), ob.std(0, ddof=1) / 4.0
+    z = np.concatenate([(g - gex[0]) / np.sqrt(gerr ** 2 + 1e-8), ((occ - occ_ex) / np.sqrt(oerr ** 2 + 1e-8)).ravel()])
+    print("host emulation, state sampling vs exact: %d values, max |z| %.2f, mean z^2 %.2f, relative G error bar %.1e, %d outer states visited"
+          % (z.size, np.abs(z).max(), (z ** 2).mean(), (gerr / g).mean(), int((np.asarray(eng.outerstatehisto) > 0).sum())))
+    assert np.abs(z).max() < 5.0 and (z ** 2).mean() < 2.5 and (gerr / g).mean() < 0.04
+    assert (np.asarray(eng.outerstatehisto) > 0).sum() >= 12          # single eigenstates all over the 16-state impurity
+    eng.dest_ctqmc()
