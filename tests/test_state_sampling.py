@@ -182,3 +182,32 @@ def test_state_sampling_exact_diagonalisation_host_emulation(built):
     assert np.abs(z).max() < 5.0 and (z ** 2).mean() < 2.5 and (gerr / g).mean() < 0.04
     assert (np.asarray(eng.outerstatehisto) > 0).sum() >= 12          # single eigenstates all over the 16-state impurity
     eng.dest_ctqmc()
+
+
+@pytest.mark.parametrize("ss", [0, 1])
+def test_empty_configuration_round_trip(built, ss):
+    """`set_empty_mc_config(outer_sst, outer_state)` (CTQMC.F90:9391-9400; MCConfig.set_to_ctqmc of an empty configuration,
+    cthyb_solver.py:41-50): the trace of the empty configuration is the Boltzmann weight of the outer superstate -- of the ONE outer
+    eigenstate with state sampling -- and the chain runs on from there (edge case: no operators at all)."""
+    from oracle.oracle import OracleChain
+    p = lift_degeneracies(problems.make_problem("C3", nftau=1001, beta=3.0, statesampling=ss))
+    eng = _start(_hostemu_engine(), p, nchains=2, nbins=1)
+    orc = OracleChain(p, seed=1)
+    at = orc.at
+    wide = int(np.argmax(at.dim))                      # a 3 x 3 block
+    for state in (1, int(at.dim[wide])):
+        eng.set_empty_mc_config(wide, state, chain=1)
+        n, osst, ostate = eng.get_mc_config_scalars(1)
+        assert (n, osst) == (0, wide) and ostate == (state if ss else 1)
+        lw = -(np.asarray(at.eval[wide]) - at.egs) * p.beta
+        want = lw[state - 1] if ss else np.log(np.exp(lw).sum())
+        s = eng.debug_chain_scalars(1)
+        assert abs(s["trace_log"] - want) < 1e-12 and s["trace_sign"] == 1.0 and s["n_ops"] == 0
+        orc.set_config([], [], [], [], wide, state)
+        assert abs(orc.scalars()["trace_log"] - want) < 1e-12
+    if ss:
+        with pytest.raises(RuntimeError, match="outer state"):
+            eng.set_empty_mc_config(wide, int(at.dim[wide]) + 1, chain=1)
+    eng.ctqmc_warmup(500)                              # and the chains run on from the empty configuration
+    assert eng.scalar("error_flags") == 0 and eng.get_mc_config_scalars(1)[0] >= 0
+    eng.dest_ctqmc()
