@@ -122,6 +122,10 @@ struct Chain {
     // accumulators
     std::vector<double> gtau, gleg, histo, dens, outer_hist, sign_hist, contrib_sst, outerstate_hist, signstate_hist, contrib_state;
     std::vector<long long> accpair;
+    // offdiag = 1 (ORACLE ONLY so far): ONE matrix over all flavours, pair moves with independent flavours
+    bool offdiag = false; std::vector<double> ftau_full;   // F(f_a, f_c, i) = Ftau_full(b_a, s_a, b_c, s_c, i) at [(f_a * nf + f_c) * nftau + i]
+    std::vector<double> Mfull; int kfull = 0;             // inverse of the full hybridisation matrix, (creator idx, annihilator idx), flavour-major order
+    std::vector<double> gtau_full;                        // [f_a][f_c][ntau]
     int ngiw = 0; std::vector<double> giw;         // MeasGiw: [nf][2 ngiw] complex sums (re, im), frequencies n = -ngiw .. ngiw - 1
     double meas_sign = 0; long long cnt_meas = 0, cnt_steps = 0;
     // replay log
@@ -588,6 +592,175 @@ struct Chain {
         std::vector<double> lu = a; std::vector<int> piv;
         if (!lu_decomp(lu, k, piv)) return {-HUGE_D, 0.0};
         return lu_logdet(lu, k, piv);
+    }
+
+    // ---------------------------------------------------------- off-diagonal hybridisation (offdiag = 1)
+    double hybrF_full(double tau, int fa, int fc) const {        // get_HybrF_full Trace.F90:1038-1057
+        double sig = 1.0;
+        if (tau < 0.0) { tau += beta; sig = -1.0; }
+        const double* F = &ftau_full[((size_t)fa * nf + fc) * nftau];
+        double n = tau / beta * (double)(nftau - 1);
+        int i = (int)n;
+        if (i >= nftau - 1) return sig * F[nftau - 1];
+        return sig * (F[i] + (n - (double)i) * (F[i + 1] - F[i]));
+    }
+    // operators in the order of get_FullHybr_offdiag (Trace.F90:2690-2770): by flavour (band outer, spin inner), then by time
+    void flavour_major(const std::vector<Op>& o, std::vector<int>& cr, std::vector<int>& an) const {
+        cr.clear(); an.clear();
+        for (int f = 0; f < nf; ++f) for (size_t i = 0; i < o.size(); ++i) if (o[i].b * 2 + o[i].s == f) (o[i].ca == 1 ? cr : an).push_back((int)i);
+    }
+    // determinant of the full hybridisation matrix Hyb(annihilator, creator) and (optionally) its inverse (creator, annihilator)
+    LogVal full_det(const std::vector<Op>& o, std::vector<double>* inv, int* kout) const {
+        std::vector<int> cr, an; flavour_major(o, cr, an);
+        if (cr.size() != an.size()) return {-HUGE_D, 0.0};
+        int k = (int)cr.size();
+        if (kout) *kout = k;
+        if (k == 0) { if (inv) inv->clear(); return {0, 1}; }
+        std::vector<double> a((size_t)k * k);
+        for (int ic = 0; ic < k; ++ic) for (int ia = 0; ia < k; ++ia) {
+            const Op& A = o[an[ia]]; const Op& Cc = o[cr[ic]];
+            a[ia + (size_t)ic * k] = hybrF_full(A.tau - Cc.tau, A.b * 2 + A.s, Cc.b * 2 + Cc.s);
+        }
+        LogVal d = mat_logdet_inv(a, k);
+        if (inv) *inv = a;
+        return d;
+    }
+    // recalc_sign Trace.F90:3500-3546, literally: exchange "sort" of the keys with a swap count, plus sum_{i < n/2} i
+    double recalc_sign(const std::vector<Op>& o) const {
+        std::vector<double> key; key.reserve(o.size());
+        for (const Op& e : o) key.push_back((double)(3 - e.ca) * 100000.0 + (double)(e.b + 1) * 10000.0 + (double)(e.s + 1) * 1000.0 + e.tau);
+        long long perm = 0; const size_t n = key.size();
+        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) if (key[i] > key[j]) { std::swap(key[i], key[j]); ++perm; }
+        for (long long i = 1; i <= (long long)n / 2 - 1; ++i) perm += i;
+        return (perm % 2) ? -1.0 : 1.0;
+    }
+    double get_sign_offdiag(const std::vector<Op>& o, LogVal tr, LogVal det) const { return tr.sign * det.sign * recalc_sign(o); }   // Trace.F90:3483-3486
+    int count_pairs_offdiag(const std::vector<Op>& o) const {       // ensure_valid_NPairs_offdiag / is_rempair_offdiag Trace.F90:2018-2030
+        int np = 0;
+        for (size_t i = 0; i < o.size(); ++i) {
+            if (o[i].tau < tauwin_min) continue;
+            if (o[i].tau > tauwin_max) break;
+            for (size_t j = i + 1; j < o.size(); ++j) {
+                if (o[j].tau > tauwin_max) break;
+                if (o[j].tau > o[i].tau + taudiff_max) break;
+                if (o[j].ca != o[i].ca) ++np;
+            }
+        }
+        return np;
+    }
+    // StepAdd with b_offdiag (CTQMC.F90:3353-3612; pair_OperAdd force_diagonal = .false., Trace.F90:3657-3698): the creator draws its own
+    // flavour; determinant from scratch (the b_full_offdiag branch, 3482-3487); (2 NBands)^2 / NPairs
+    void StepAdd_offdiag() {
+        log_begin(1);
+        C.TryAdd += 1;
+        double W = tauwin_max - tauwin_min;
+        double tau_a = tauwin_min + W * grnd();
+        int ba = randint(1, nb) - 1, sa = randint(1, 2) - 1;
+        double tmin = std::max(tau_a - taudiff_max, tauwin_min);
+        double w2 = std::min(tau_a + taudiff_max, tauwin_max) - tmin;
+        double tau_c = tmin + w2 * grnd();
+        int bc = randint(1, nb) - 1, sc = randint(1, 2) - 1;
+        double taudiff_factor = W * w2;
+        Op oa{tau_a, ba, sa, 2}, oc{tau_c, bc, sc, 1};
+        rec[4] = (ba * 2 + sa) * nf + bc * 2 + sc;
+        bool equal = (tau_a == tau_c);
+        for (const Op& e : ops) if (e.tau == tau_a || e.tau == tau_c) equal = true;
+        Op o1 = (tau_a < tau_c) ? oa : oc, o2 = (tau_a < tau_c) ? oc : oa;
+        rec[2] = o1.tau; rec[3] = o2.tau;
+        if (equal) { C.AccQNAdd += 1; log_end(2); return; }
+        size_t i1 = 0; while (i1 < ops.size() && ops[i1].tau < o1.tau) ++i1;
+        size_t i2 = i1; while (i2 < ops.size() && ops[i2].tau < o2.tau) ++i2;
+        std::vector<Op> nw; nw.reserve(ops.size() + 2);
+        nw.insert(nw.end(), ops.begin(), ops.begin() + i1); nw.push_back(o1);
+        nw.insert(nw.end(), ops.begin() + i1, ops.begin() + i2); nw.push_back(o2);
+        nw.insert(nw.end(), ops.begin() + i2, ops.end());
+        {   // check_sst_sequence over the changed sub-string
+            std::vector<int> after; sst_sequence(ops, outer_sst, after);
+            int begin_sst = (i1 == 0) ? outer_sst : after[i1 - 1];
+            int end_sst = (i2 == ops.size() || i2 == 0) ? outer_sst : after[i2 - 1];
+            int cur = T.conn(begin_sst, o1.b, o1.s, o1.ca);
+            for (size_t i = i1; i < i2 && cur >= 0; ++i) cur = T.conn(cur, ops[i].b, ops[i].s, ops[i].ca);
+            if (cur >= 0) cur = T.conn(cur, o2.b, o2.s, o2.ca);
+            if (cur < 0 || cur != end_sst) { C.AccQNAdd += 1; log_end(2); return; }
+        }
+        std::vector<double> Mn; int kn = 0;
+        LogVal DetNew = full_det(nw, &Mn, &kn);
+        LogVal DetRat = ldiv(DetNew, Det);
+        std::vector<LogVal> parts;
+        LogVal TraceNew = trace_full(nw, outer_sst, &parts);
+        double rand = grnd();
+        int NPairs = count_pairs_offdiag(nw);
+        LogVal trr = ldiv(TraceNew, Trace);
+        double prob = (DetNew.sign == 0.0) ? 0.0 : std::fabs(taudiff_factor * (double)(2 * nb) * (double)(2 * nb) / (double)NPairs * std::exp(trr.log + DetRat.log));
+        rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[14] = NPairs; rec[17] = rand;
+        if (rand < prob) {
+            ops.swap(nw); Mfull.swap(Mn); kfull = kn;
+            Det = DetNew; Trace = TraceNew; parttrace = parts;
+            cfgsign = -get_sign_offdiag(ops, Trace, Det);
+            C.AccAdd += 1; log_end(1);
+        } else log_end(0);
+    }
+    // StepRem with b_offdiag (CTQMC.F90:3892-4150; gen_OperRemove walks `next` instead of `fnext`, Trace.F90:4885-4905)
+    void StepRem_offdiag() {
+        log_begin(2);
+        C.TryRem += 1;
+        int NPairs = count_pairs_offdiag(ops);
+        rec[14] = NPairs;
+        if (NPairs <= 0) { C.AccQNRem += 1; log_end(2); return; }
+        int NPair = randint(1, NPairs);
+        size_t i1 = 0, i2 = 0; bool found = false;
+        for (size_t i = 0; i < ops.size() && !found; ++i) {
+            if (ops[i].tau < tauwin_min) continue;
+            for (size_t j = i + 1; j < ops.size(); ++j) {
+                if (ops[j].tau > tauwin_max) break;
+                if (ops[j].tau > ops[i].tau + taudiff_max) break;
+                if (ops[j].ca != ops[i].ca) { if (--NPair <= 0) { i1 = i; i2 = j; found = true; break; } }
+            }
+        }
+        if (!found) { error = 2; log_end(2); return; }
+        Op o1 = ops[i1], o2 = ops[i2];
+        rec[2] = o1.tau; rec[3] = o2.tau;
+        double tau_an = (o1.ca == 2) ? o1.tau : o2.tau;
+        double factor = (double)NPairs / ((tauwin_max - tauwin_min)
+                        * (std::min(tau_an + taudiff_max, tauwin_max) - std::max(tau_an - taudiff_max, tauwin_min)));
+        std::vector<Op> nw; nw.reserve(ops.size());
+        for (size_t i = 0; i < ops.size(); ++i) if (i != i1 && i != i2) nw.push_back(ops[i]);
+        {
+            std::vector<int> after; sst_sequence(ops, outer_sst, after);
+            int begin_sst = (i1 == 0) ? outer_sst : after[i1 - 1];
+            int end_sst = (i2 + 1 == ops.size()) ? outer_sst : after[i2];
+            int cur = begin_sst;
+            for (size_t i = i1 + 1; i < i2 && cur >= 0; ++i) cur = T.conn(cur, ops[i].b, ops[i].s, ops[i].ca);
+            if (cur < 0 || cur != end_sst) { C.AccQNRem += 1; log_end(2); return; }
+        }
+        std::vector<double> Mn; int kn = 0;
+        LogVal DetNew = full_det(nw, &Mn, &kn);
+        LogVal DetRat = ldiv(DetNew, Det);
+        std::vector<LogVal> parts;
+        LogVal TraceNew = trace_full(nw, outer_sst, &parts);
+        LogVal trr = ldiv(TraceNew, Trace);
+        double prob = (DetNew.sign == 0.0) ? 0.0 : std::fabs(factor / ((double)(2 * nb) * (double)(2 * nb)) * std::exp(trr.log + DetRat.log));
+        double rand = grnd();
+        rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[17] = rand;
+        if (rand < prob) {
+            ops.swap(nw); Mfull.swap(Mn); kfull = kn;
+            Det = DetNew; Trace = TraceNew; parttrace = parts;
+            cfgsign = -get_sign_offdiag(ops, Trace, Det);
+            C.AccRem += 1; log_end(1);
+        } else log_end(0);
+    }
+    // MeasGtauRem_full CTQMC.F90:2475-2584: Gtau_full(f_a, f_c, bin) += +-M(c, a) cfgsign over ALL creator / annihilator pairs
+    void measure_gtau_full() {
+        std::vector<int> cr, an; flavour_major(ops, cr, an);
+        const int k = (int)cr.size();
+        for (int ic = 0; ic < k; ++ic) for (int ia = 0; ia < k; ++ia) {
+            const Op& A = ops[an[ia]]; const Op& Cc = ops[cr[ic]];
+            double Mv = Mfull[ic + (size_t)ia * k], dtau = A.tau - Cc.tau; int idt;
+            if (dtau > 0.0) idt = (int)(dtau / beta * (double)ntau) + 1;
+            else { idt = (int)((beta + dtau) / beta * (double)ntau) + 1; Mv = -Mv; }
+            if (idt > ntau) idt = ntau;
+            gtau_full[((size_t)(A.b * 2 + A.s) * nf + (Cc.b * 2 + Cc.s)) * ntau + idt - 1] += Mv * cfgsign;
+        }
     }
 
     // Delta matrices from scratch: get_InvFullHybr Trace.F90:2279-2333 -> Mat(annih idx, creator idx)
@@ -1093,6 +1266,14 @@ struct Chain {
         double prob = osf > 0.0 ? std::fabs(osf * lval(trr)) : 0.0;
         double rand = grnd();
         rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[17] = rand;
+        if (rand < prob && offdiag) {
+            // offdiag: the rolled matrix (update_InvFullHybrShiftTau, Trace.F90:2336-2352 / 2460-2560) is rebuilt from scratch here -- same
+            // matrix, same determinant (its modulus cannot change, its sign can)
+            ops.swap(nw); outer_sst = new_outer; outer_state = new_state;
+            Trace = TraceNew; parttrace = parts; Det = full_det(ops, &Mfull, &kfull); ec.valid = false; fc.valid = false;
+            cfgsign = -get_sign_offdiag(ops, Trace, Det);
+            C.AccShift += 1; log_end(1);
+        } else
         if (rand < prob) {
             // update_InvFullHybrShiftTau_diag Trace.F90:2355-2457
             double detrat = 1.0;
@@ -1124,6 +1305,12 @@ struct Chain {
 
     void step() {                                    // CTQMC.F90:8213-8258 / 8428-8533
         double r = grnd();
+        if (offdiag) {                               // ORACLE-ONLY groundwork for offdiag = 1: pair moves (global moves / tau shifts must be switched off)
+            if (r < (1.0 - pshift - pglob) / 2.0) { (void)grnd(); (void)grnd(); StepAdd_offdiag(); }     // the two draws of CTQMC.F90:8441-8442
+            else if (r <= 1.0 - pshift - pglob) { (void)grnd(); (void)grnd(); StepRem_offdiag(); }
+            else if (r <= 1.0 - pshift) { error = 5; }              // global moves are not restated for offdiag
+            else StepShiftTau();
+        } else
         if (r < (1.0 - pshift - pglob) / 2.0) {
             if (grnd() >= p4op) StepAdd(grnd() < pouter); else StepAdd4();
         } else if (r <= 1.0 - pshift - pglob) {
@@ -1151,6 +1338,13 @@ struct Chain {
               signstate_hist[off + i] += Trace.sign * parttrace[i].sign * cfgsign;
               double e = std::exp(parttrace[i].log); c += e; contrib_state[off + i] += e; }
           contrib_sst[outer_sst] += c; }
+        if (offdiag) {                                                         // NOSOper / 2 per flavour, MeasGtauRem_full instead of MeasGtauRem
+            std::vector<int> cnt(nf, 0); for (const Op& e : ops) cnt[e.b * 2 + e.s]++;
+            for (int f = 0; f < nf; ++f) histo[(size_t)f * (maxhisto + 1) + std::min(cnt[f] / 2, maxhisto)] += 1.0;
+            if (meas_dm) measure_density();
+            measure_gtau_full();
+            return;
+        }
         for (int f = 0; f < nf; ++f) histo[(size_t)f * (maxhisto + 1) + std::min(kf[f], maxhisto)] += 1.0;   // MeasExpOrder 3264
         if (meas_dm) measure_density();
         // MeasGtauRem 2252-2440 (isDetRat = .false.)
@@ -1273,6 +1467,7 @@ struct Chain {
         outerstate_hist.assign(T.nstates, 0); signstate_hist.assign(T.nstates, 0); contrib_state.assign(T.nstates, 0);
         accpair.assign((size_t)nf * ntau, 0);
         giw.assign((size_t)2 * nf * 2 * ngiw, 0.0);
+        gtau_full.assign(offdiag ? (size_t)nf * nf * ntau : 0, 0.0);
         meas_sign = 0; cnt_meas = 0;
     }
 };
@@ -1339,6 +1534,13 @@ int orc_randint(void* h, int lo, int hi) { return ((Chain*)h)->randint(lo, hi); 
 unsigned long long orc_rng_counter(void* h) { return ((Chain*)h)->ph.ctr; }
 
 void orc_init_trace(void* h) { ((Chain*)h)->init_trace(); }
+// offdiag = 1 (oracle-only groundwork): full hybridisation function F(f_a, f_c, i), flavour f = 2 b + s; before orc_init_trace
+void orc_set_offdiag(void* h, const double* ftau_full) {
+    Chain* c = (Chain*)h; c->offdiag = true;
+    c->ftau_full.assign(ftau_full, ftau_full + (size_t)c->nf * c->nf * c->nftau);
+    c->gtau_full.assign((size_t)c->nf * c->nf * c->ntau, 0.0);
+}
+void orc_get_gtau_full(void* h, double* out) { Chain* c = (Chain*)h; std::memcpy(out, c->gtau_full.data(), c->gtau_full.size() * sizeof(double)); }
 void orc_set_meas_giw(void* h, int ngiw) { Chain* c = (Chain*)h; c->ngiw = ngiw; c->giw.assign((size_t)2 * c->nf * 2 * ngiw, 0.0); }
 void orc_get_giw(void* h, double* out) { Chain* c = (Chain*)h; std::memcpy(out, c->giw.data(), c->giw.size() * sizeof(double)); }
 void orc_set_statesampling(void* h, int on) { ((Chain*)h)->statesampling = on != 0; }     // before orc_init_trace

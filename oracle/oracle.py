@@ -119,6 +119,14 @@ class OracleChain:
         rc = L.orc_init_rnd(self.h, C.c_int(kind), C.c_uint(seed), C.c_uint(chain), MTLIB.encode())
         if rc != 0:
             raise RuntimeError("oracle RNG init failed (%d); libmtrng.so missing?" % rc)
+        self.offdiag = int(q.get("offdiag", 0)) != 0
+        if self.offdiag:
+            # ORACLE-ONLY groundwork for SURVEY.md 8 f3: ONE matrix over all flavours, pair moves with independent flavours, determinant from
+            # scratch (b_full_offdiag), recalc_sign, tau shifts, MeasGtauRem_full.  Global, outer and 4-operator moves are not restated.
+            if q["PercentageGlobalMove"] != 0 or q["Percentage4OperatorMove"] != 0 or q["PercentageOuterMove"] != 0:
+                raise ValueError("oracle offdiag = 1: only pair moves and tau shifts are restated (set the other move percentages to 0)")
+            ff = np.ascontiguousarray(np.stack([[problem.ftau[b1, s1, b2, s2, :] for b2 in range(nb) for s2 in range(2)] for b1 in range(nb) for s1 in range(2)]))
+            L.orc_set_offdiag(self.h, _p(ff, C.c_double))
         self.ngiw = int(q.get("Niw", 0)) if int(q.get("MeasGiw", 0)) else 0
         if self.ngiw:
             L.orc_set_meas_giw(self.h, C.c_int(self.ngiw))
@@ -242,6 +250,10 @@ class OracleChain:
                                       ("gtau", "gleg", "histo", "dens", "outer_hist", "sign_hist", "contrib_sst",
                                        "outerstate_hist", "signstate_hist", "contrib_state")],
                             _p(r["accpair"], C.c_longlong))
+        if self.offdiag:
+            gf = np.zeros((nf, nf, self.ntau))
+            lib().orc_get_gtau_full(self.h, _p(gf, C.c_double))
+            r["gtau_full"] = gf
         if self.ngiw:
             g = np.zeros(2 * nf * 2 * self.ngiw)
             lib().orc_get_giw(self.h, _p(g, C.c_double))
@@ -333,6 +345,8 @@ def normalise(raw, at, beta, want_rho2=False):
     leg = raw["gleg"] * np.sqrt(2.0 * np.arange(nleg) + 1.0)[None, :] / beta
     out["gleg"] = (-leg * zs).reshape(nb, 2, nleg)
     out["hist"] = (raw["histo"] / n).reshape(nb, 2, -1)
+    if "gtau_full" in raw:                                          # Gtau_full = -Gtau_full * zScaling * Ntau / beta^2, CTQMC.F90:8752-8753
+        out["gtau-full"] = (-raw["gtau_full"] * zs * ntau / beta ** 2).reshape(nb, 2, nb, 2, ntau)
     if "giw" in raw:                                                # Giw *= zScaling / beta, CTQMC.F90:8815-8817
         out["giw"] = (raw["giw"] * zs / beta).reshape(nb, 2, -1)
     dm = raw["dens"] * zs

@@ -42,6 +42,91 @@ def kanamori2_problem(n_bath, beta, jj=0.6, nftau=2001, **qmc):
     return p
 
 
+def offdiag_two_orbital_problem(beta, nftau=2001, kanamori=False, **qmc):
+    """Two orbitals, density-density (or, `kanamori`, full Kanamori) interaction, and a bath whose levels couple to BOTH orbitals: three levels per spin, level q hops to
+    orbital 0 with V[0, q] and to orbital 1 with V[1, q] -> orbital-off-diagonal hybridisation F_{(0 s), (1 s)}(tau) != 0 (`offdiag = 1`).
+    F_ab(tau) = sum_q V_aq V_bq / (exp(-tau eps_q) + exp((beta - tau) eps_q)), the off-diagonal form of problems.hybr_tau.
+    NOTE on ergodicity: with spin-flip / pair-hopping terms H_loc does not conserve the particle number per flavour, configurations like
+    c+_{0 up} c+_{0 dn} c_{1 dn} c_{1 up} carry weight through F_01, and single pair insertions cannot reach them (the quantum-number check
+    rejects one flavour-changing pair): pair moves alone are then NOT ergodic (measured: G_01 comes out 3-5 x too large while the diagonal
+    G and all occupations agree) -- the reference's 4-operator / flavour-change moves exist for this.  Density-density interactions
+    conserve every flavour's particle number and pair moves are ergodic."""
+    u, v, jj = 4.0, 2.8, 0.6
+    mu = 0.5 * (u + (2 * v - jj))
+    q = {"TaudiffMax": min(4.0, beta), "offdiag": 1, "PercentageGlobalMove": 0.0}
+    q.update(qmc)
+    if kanamori:
+        p = problems._assemble("K2o", 2, beta, "Kanamori", "Nt Szt Qzt", problems.u_kanamori(2, u, v, jj), mu, 3, q, nftau)
+    else:
+        p = problems._assemble("D2o", 2, beta, "Density", "Nt Szt Azt", problems.u_density(2, u, v, jj), mu, 3, q, nftau)
+    eps = np.array([-0.8, 0.15, 1.1])
+    vq = np.array([[0.65, 0.5, 0.45], [0.4, -0.55, 0.6]])                 # [orbital, level]
+    tau = np.linspace(0.0, beta, nftau)
+    den = np.exp(-tau[:, None] * eps[None, :]) + np.exp((beta - tau[:, None]) * eps[None, :])
+    p.ftau[...] = 0.0
+    for s in range(2):
+        for b1 in range(2):
+            for b2 in range(2):
+                p.ftau[b1, s, b2, s, :] = ((vq[b1] * vq[b2])[None, :] / den).sum(-1)
+    # general bath for the exact solver: modes (spin, level); hopping matrix [impurity flavour 2 b + s, bath mode]
+    nmode = 2 * eps.size
+    p.bath_eps = np.concatenate([eps, eps])
+    p.bath_v = np.zeros((4, nmode))
+    for s in range(2):
+        for b in range(2):
+            p.bath_v[2 * b + s, s * eps.size:(s + 1) * eps.size] = vq[b]
+    return p
+
+
+def solve_general(p, pairs, nbins=50):
+    """Exact G_ab(tau) = <c_a(tau) c_b^+(0)> (bin averages) and <n_i n_j> for a GENERAL bath (p.bath_eps[m], p.bath_v[flavour, m])."""
+    nb, nf, beta = p.nbands, 2 * p.nbands, p.beta
+    eps, v = np.asarray(p.bath_eps), np.asarray(p.bath_v)
+    nm = nf + eps.size
+    c = _annihilators(nm)
+    cd = [m.T.tocsr() for m in c]
+    u = np.asarray(p.u_matrix).reshape((nf,) * 4)
+    mu = np.asarray(p.muimp).reshape(nf, nf)
+    h = sp.csr_matrix((1 << nm, 1 << nm))
+    for i in range(nf):
+        for j in range(nf):
+            if mu[i, j] != 0.0:
+                h = h + mu[i, j] * (cd[i] @ c[j])
+    for i, j, k, l in np.argwhere(np.abs(u) > 1e-14):
+        h = h + 0.5 * u[i, j, k, l] * (cd[i] @ cd[j] @ (c[l] @ c[k]))
+    for m in range(eps.size):
+        h = h + eps[m] * (cd[nf + m] @ c[nf + m])
+        for i in range(nf):
+            if v[i, m] != 0.0:
+                h = h + v[i, m] * (cd[i] @ c[nf + m] + cd[nf + m] @ c[i])
+    hd = h.toarray()
+    assert np.abs(hd - hd.T).max() < 1e-12
+    w, vec = np.linalg.eigh(hd)
+    w -= w.min()
+    bw = np.exp(-beta * w)
+    z = bw.sum()
+    edges = np.linspace(0.0, beta, nbins + 1)
+    cmat = {f: vec.T @ (cd[f] @ vec) for f in {x for pr in pairs for x in pr}}       # <m| c_f^+ |n>
+    g = np.zeros((len(pairs), nbins))
+    for a, (fa, fb) in enumerate(pairs):
+        m2 = cmat[fa] * cmat[fb]                                        # <n|c_a|m> <m|c_b^+|n> (real matrices)
+        im, in_ = np.nonzero((np.abs(m2) > 1e-15) & (np.maximum(bw[:, None], bw[None, :]) / z > 1e-13))
+        mm, em, en = m2[im, in_], w[im], w[in_]
+        de = em - en
+        small = np.abs(de) < 1e-9
+        for ib in range(nbins):
+            t1, t2 = edges[ib], edges[ib + 1]
+            e1, e2 = np.exp(-(beta - t1) * en - t1 * em), np.exp(-(beta - t2) * en - t2 * em)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                avg = np.where(small, e1, (e1 - e2) / (de * (t2 - t1)))
+            g[a, ib] = (mm * avg).sum() / z
+    keep = bw / z > 1e-14
+    rho_diag = ((vec[:, keep] ** 2) @ bw[keep]) / z
+    st = np.arange(1 << nm)
+    occ = np.array([[(rho_diag * ((st >> i) & 1) * ((st >> j) & 1)).sum() for j in range(nf)] for i in range(nf)])
+    return g, occ.reshape(nb, 2, nb, 2)
+
+
 _CACHE = {}
 
 
