@@ -1188,10 +1188,18 @@ struct Chain {
         }
         if (factor == 0.0) { C.AccQNGlob += 1; log_end(2); return; }
         std::vector<std::vector<double>> Mn; std::vector<int> kn;
-        LogVal DetNew = build_inverse_all(nw, Mn, kn);
+        std::vector<double> Mfn; int kfn = 0;
+        LogVal DetNew, DetRat;
+        if (offdiag) {                               // CTQMC.F90:4491-4494: the relabelled full matrix from scratch
+            DetNew = full_det(nw, &Mfn, &kfn);
+            if (DetNew.sign == 0.0) { (void)grnd(); log_end(0); return; }   // singular relabelled matrix: weight 0, rejected (the accept draw is still consumed)
+            DetRat = ldiv(DetNew, Det);
+        } else {
+        DetNew = build_inverse_all(nw, Mn, kn);
         LogVal DetOld{0, 1};                         // get_FullLogDet Trace.F90:2665-2685 (LU of the stored inverses)
         for (int f = 0; f < nf; ++f) if (kf[f] > 0) DetOld = lmul(mat_logdet(M[f], kf[f]), DetOld);
-        LogVal DetRat = lmul(DetNew, DetOld);
+        DetRat = lmul(DetNew, DetOld);
+        }
         std::vector<LogVal> parts;
         LogVal TraceNew = trace_full(nw, new_outer, &parts, statesampling ? new_state : -1);
         LogVal trr = ldiv(TraceNew, Trace);
@@ -1199,9 +1207,10 @@ struct Chain {
         double rand = grnd();
         rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[17] = rand;
         if (rand < prob) {
-            ops.swap(nw); M.swap(Mn); kf = kn; outer_sst = new_outer; outer_state = new_state;
+            ops.swap(nw); outer_sst = new_outer; outer_state = new_state;
+            if (offdiag) { Mfull.swap(Mfn); kfull = kfn; } else { M.swap(Mn); kf = kn; }
             Det = DetNew; Trace = TraceNew; parttrace = parts; ec.valid = false; fc.valid = false;
-            cfgsign = -get_sign(ops, Trace, Det);
+            cfgsign = offdiag ? -get_sign_offdiag(ops, Trace, Det) : -get_sign(ops, Trace, Det);
             C.AccGlob += 1; log_end(1);
         } else log_end(0);
     }
@@ -1305,10 +1314,10 @@ struct Chain {
 
     void step() {                                    // CTQMC.F90:8213-8258 / 8428-8533
         double r = grnd();
-        if (offdiag) {                               // ORACLE-ONLY groundwork for offdiag = 1: pair moves (global moves / tau shifts must be switched off)
+        if (offdiag) {                               // ORACLE-ONLY groundwork for offdiag = 1: pair moves, global moves, tau shifts
             if (r < (1.0 - pshift - pglob) / 2.0) { (void)grnd(); (void)grnd(); StepAdd_offdiag(); }     // the two draws of CTQMC.F90:8441-8442
             else if (r <= 1.0 - pshift - pglob) { (void)grnd(); (void)grnd(); StepRem_offdiag(); }
-            else if (r <= 1.0 - pshift) { error = 5; }              // global moves are not restated for offdiag
+            else if (r <= 1.0 - pshift) StepGlob();
             else StepShiftTau();
         } else
         if (r < (1.0 - pshift - pglob) / 2.0) {

@@ -1,7 +1,7 @@
 """ORACLE-ONLY groundwork for `offdiag = 1` (the open half of SURVEY.md 8 f3; the CUDA engine still refuses the key): one matrix over
 all flavours in the order of `get_FullHybr_offdiag` (Trace.F90:2690-2770), pair moves whose creator draws its own flavour
 (`pair_OperAdd` with force_diagonal = .false., Trace.F90:3657-3698; `(2 NBands)^2 / NPairs`, CTQMC.F90:3517-3519), the flavour-blind pair
-count (`is_rempair_offdiag`, Trace.F90:2018-2030), `recalc_sign` (Trace.F90:3500-3546), tau shifts, `MeasGtauRem_full`
+count (`is_rempair_offdiag`, Trace.F90:2018-2030), `recalc_sign` (Trace.F90:3500-3546), global moves (CTQMC.F90:4491-4494), tau shifts, `MeasGtauRem_full`
 (CTQMC.F90:2475-2584) with its normalisation (8752-8753); determinants from scratch (the reference's own `b_full_offdiag` branch,
 CTQMC.F90:3482-3487).  Pinned to EXACT results of a two-orbital impurity whose bath levels couple to both orbitals: the full G_ab(tau)
 matrix -- its orbital-off-diagonal elements change sign along tau -- and all <n_i n_j>."""
@@ -50,7 +50,7 @@ PAIRS = [(0, 0), (2, 2), (1, 1), (0, 2), (2, 0), (1, 3)]
 
 def test_offdiag_noninteracting_exact(built):
     """U = 0: the exact G_ab(tau) follows from the one-particle Hamiltonian of impurity + bath (checked against the Fock-space solver here)."""
-    p = ea.offdiag_two_orbital_problem(5.0, NCorr=20, PercentageTauShiftMove=0.02)
+    p = ea.offdiag_two_orbital_problem(5.0, NCorr=20, PercentageTauShiftMove=0.02, PercentageGlobalMove=0.02)
     p.u_matrix[...] = 0.0
     for b in range(2):
         for s in range(2):
@@ -72,13 +72,13 @@ def test_offdiag_noninteracting_exact(built):
 def test_offdiag_interacting_exact(built):
     """Density-density interaction (pair moves are ergodic: every flavour's particle number is conserved by H_loc; see the note in
     tests/_exact_anderson.py on Kanamori terms)."""
-    p = ea.offdiag_two_orbital_problem(5.0, NCorr=20, PercentageTauShiftMove=0.02)
+    p = ea.offdiag_two_orbital_problem(5.0, NCorr=20, PercentageTauShiftMove=0.02, PercentageGlobalMove=0.02)
     gex, occ_ex = ea.solve_general(p, PAIRS)
     _compare(_run(p, nchains=48, meas=12000), PAIRS, gex, occ_ex, "offdiag oracle, density-density U = 4")
 
 
 def test_offdiag_oracle_refuses_unrestated_moves(built):
     from oracle.oracle import OracleChain
-    p = ea.offdiag_two_orbital_problem(5.0, PercentageGlobalMove=0.005)
+    p = ea.offdiag_two_orbital_problem(5.0, Percentage4OperatorMove=0.1)
     with pytest.raises(ValueError, match="offdiag"):
         OracleChain(p, seed=1)
