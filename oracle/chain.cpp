@@ -183,6 +183,7 @@ struct Chain {
 
     // ---------------------------------------------------------- NPairs: ensure_valid_NPairs_diag Trace.F90:1770-1815
     int count_pairs(const std::vector<Op>& o) const {
+        if (offdiag) return count_pairs_offdiag(o);
         int np = 0;
         for (size_t i = 0; i < o.size(); ++i) {
             if (o[i].tau < tauwin_min) continue;
@@ -1010,7 +1011,7 @@ struct Chain {
     // rebuilt from scratch (get_InvFullHybr, CTQMC.F90:3816-3817) and the proposal ratio sums over the orders in which the
     // inverse move could take the four operators out (rempair_factor).
     bool is_rempair(const Op& a, const Op& b) const {            // is_rempair_diag Trace.F90:2005-2030
-        return a.b == b.b && a.s == b.s && a.ca != b.ca && a.tau >= tauwin_min && a.tau <= tauwin_max && b.tau >= tauwin_min && b.tau <= tauwin_max
+        return (offdiag || (a.b == b.b && a.s == b.s)) && a.ca != b.ca && a.tau >= tauwin_min && a.tau <= tauwin_max && b.tau >= tauwin_min && b.tau <= tauwin_max
                && std::fabs(a.tau - b.tau) <= taudiff_max;
     }
     static std::vector<Op> merged(const std::vector<Op>& base, const std::vector<Op>& add) {
@@ -1028,7 +1029,7 @@ struct Chain {
         for (size_t i = 0; i < o.size(); ++i) {
             if (o[i].tau < tauwin_min) continue;
             for (size_t j = i + 1; j < o.size(); ++j) {
-                if (o[j].b != o[i].b || o[j].s != o[i].s) continue;
+                if (!offdiag && (o[j].b != o[i].b || o[j].s != o[i].s)) continue;      // offdiag: `next` instead of `fnext` (Trace.F90:4885-4905)
                 if (o[j].tau > tauwin_max) break;
                 if (o[j].tau > o[i].tau + taudiff_max) break;
                 if (o[j].ca != o[i].ca) { if (--NPair <= 0) { i1 = i; i2 = j; return true; } }
@@ -1042,19 +1043,27 @@ struct Chain {
     }
     void finish4(const std::vector<Op>& nw, double factor, int np_new, double& acc_counter) {
         std::vector<std::vector<double>> Mn; std::vector<int> kn;
-        LogVal DetNew = build_inverse_all(nw, Mn, kn);
+        std::vector<double> Mfn; int kfn = 0;
+        LogVal DetNew, DetRat;
+        if (offdiag) {                               // get_FullHybr_offdiag + get_MatLogDetFull (CTQMC.F90:3809-3811, 4339-4341)
+            DetNew = full_det(nw, &Mfn, &kfn);
+            DetRat = DetNew.sign == 0.0 ? LogVal{0.0, 0.0} : ldiv(DetNew, Det);
+        } else {
+        DetNew = build_inverse_all(nw, Mn, kn);
         LogVal DetOld{0, 1};                         // get_FullLogDet: LU of the stored inverses (CTQMC.F90:3817, 4345)
         for (int f = 0; f < nf; ++f) if (kf[f] > 0) DetOld = lmul(mat_logdet(M[f], kf[f]), DetOld);
-        LogVal DetRat = lmul(DetNew, DetOld);
+        DetRat = lmul(DetNew, DetOld);
+        }
         std::vector<LogVal> parts;
         LogVal TraceNew = trace_full(nw, outer_sst, &parts, statesampling ? outer_state : -1);
         LogVal trr = ldiv(TraceNew, Trace);
         double rand = grnd();
-        double prob = std::fabs(factor * std::exp(trr.log + DetRat.log));
+        double prob = (offdiag && DetNew.sign == 0.0) ? 0.0 : std::fabs(factor * std::exp(trr.log + DetRat.log));
         rec[7] = DetRat.log; rec[8] = DetRat.sign; rec[9] = trr.log; rec[10] = trr.sign; rec[11] = prob; rec[14] = np_new; rec[17] = rand;
         if (rand < prob) {
-            ops = nw; M.swap(Mn); kf = kn; Det = DetNew; Trace = TraceNew; parttrace = parts; ec.valid = false; fc.valid = false;
-            cfgsign = -get_sign(ops, Trace, Det);
+            ops = nw; Det = DetNew; Trace = TraceNew; parttrace = parts; ec.valid = false; fc.valid = false;
+            if (offdiag) { Mfull.swap(Mfn); kfull = kfn; cfgsign = -get_sign_offdiag(ops, Trace, Det); }
+            else { M.swap(Mn); kf = kn; cfgsign = -get_sign(ops, Trace, Det); }
             acc_counter += 1; log_end(1);
         } else log_end(0);
     }
@@ -1069,7 +1078,9 @@ struct Chain {
                 o[i].b = randint(1, nb) - 1; o[i].s = randint(1, 2) - 1;
             } else {
                 double tmin = std::max(tau_ref - taudiff_max, tauwin_min), w2 = std::min(tau_ref + taudiff_max, tauwin_max) - tmin;
-                o[i].tau = tmin + w2 * grnd(); fac *= w2; o[i].b = o[i - 1].b; o[i].s = o[i - 1].s;
+                o[i].tau = tmin + w2 * grnd(); fac *= w2;
+                if (offdiag) { o[i].b = randint(1, nb) - 1; o[i].s = randint(1, 2) - 1; }    // force_diagonal = .false. (CTQMC.F90:3641-3642)
+                else { o[i].b = o[i - 1].b; o[i].s = o[i - 1].s; }
             }
         }
         const int old_N = count_pairs(ops);          // ensure_valid_NPairs 3651
@@ -1094,7 +1105,8 @@ struct Chain {
         (void)old_N;
         std::vector<int> after;
         if (!sst_sequence(all, outer_sst, after)) { log_end(2); return; }   // check_sst_sequence over the changed sub-string (the rest is unchanged)
-        finish4(all, fac * (double)((2 * nb) * (2 * nb)) * rf, Nall, C.AccAdd4);
+        const double nfl = (double)((2 * nb) * (2 * nb));                      // (2 NBands)^2, with offdiag (2 NBands)^4 (CTQMC.F90:3823-3826)
+        finish4(all, fac * (offdiag ? nfl * nfl : nfl) * rf, Nall, C.AccAdd4);
     }
     void StepRem4() {                                // CTQMC.F90:4153-4430 (b_offdiag = .false.)
         log_begin(8);
@@ -1128,7 +1140,8 @@ struct Chain {
         rec[4] = (O1.b * 2 + O1.s) * nf + (O3.b * 2 + O3.s);
         std::vector<int> after;
         if (!sst_sequence(none, outer_sst, after)) { log_end(2); return; }
-        finish4(none, 1.0 / (double)((2 * nb) * (2 * nb)) / taudiff / rf, count_pairs(none), C.AccRem4);
+        const double nfl = (double)((2 * nb) * (2 * nb));                      // CTQMC.F90:4353-4356
+        finish4(none, 1.0 / (offdiag ? nfl * nfl : nfl) / taudiff / rf, count_pairs(none), C.AccRem4);
     }
 
     // count compatible outer superstates: check_qn_all_ssts Trace.F90:1402-1433
@@ -1314,9 +1327,9 @@ struct Chain {
 
     void step() {                                    // CTQMC.F90:8213-8258 / 8428-8533
         double r = grnd();
-        if (offdiag) {                               // ORACLE-ONLY groundwork for offdiag = 1: pair moves, global moves, tau shifts
-            if (r < (1.0 - pshift - pglob) / 2.0) { (void)grnd(); (void)grnd(); StepAdd_offdiag(); }     // the two draws of CTQMC.F90:8441-8442
-            else if (r <= 1.0 - pshift - pglob) { (void)grnd(); (void)grnd(); StepRem_offdiag(); }
+        if (offdiag) {                               // ORACLE-ONLY groundwork for offdiag = 1: pair moves, 4-operator moves, global moves, tau shifts
+            if (r < (1.0 - pshift - pglob) / 2.0) { if (grnd() >= p4op) { (void)grnd(); StepAdd_offdiag(); } else StepAdd4(); }     // draws of CTQMC.F90:8441-8442
+            else if (r <= 1.0 - pshift - pglob) { if (grnd() >= p4op) { (void)grnd(); StepRem_offdiag(); } else StepRem4(); }
             else if (r <= 1.0 - pshift) StepGlob();
             else StepShiftTau();
         } else

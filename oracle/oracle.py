@@ -122,9 +122,9 @@ class OracleChain:
         self.offdiag = int(q.get("offdiag", 0)) != 0
         if self.offdiag:
             # ORACLE-ONLY groundwork for SURVEY.md 8 f3: ONE matrix over all flavours, pair moves with independent flavours, determinant from
-            # scratch (b_full_offdiag), recalc_sign, global moves, tau shifts, MeasGtauRem_full.  Outer and 4-operator moves are not restated.
-            if q["Percentage4OperatorMove"] != 0 or q["PercentageOuterMove"] != 0 or int(q.get("statesampling", 0)) != 0:
-                raise ValueError("oracle offdiag = 1: pair moves, global moves and tau shifts are restated; 4-operator / outer moves and state sampling are not")
+            # scratch (b_full_offdiag), recalc_sign, 4-operator moves, global moves, tau shifts, MeasGtauRem_full.  Outer moves are not restated.
+            if q["PercentageOuterMove"] != 0 or int(q.get("statesampling", 0)) != 0:
+                raise ValueError("oracle offdiag = 1: pair, 4-operator, global moves and tau shifts are restated; outer moves and state sampling are not")
             ff = np.ascontiguousarray(np.stack([[problem.ftau[b1, s1, b2, s2, :] for b2 in range(nb) for s2 in range(2)] for b1 in range(nb) for s1 in range(2)]))
             L.orc_set_offdiag(self.h, _p(ff, C.c_double))
         self.ngiw = int(q.get("Niw", 0)) if int(q.get("MeasGiw", 0)) else 0

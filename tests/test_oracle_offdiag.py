@@ -1,7 +1,7 @@
 """ORACLE-ONLY groundwork for `offdiag = 1` (the open half of SURVEY.md 8 f3; the CUDA engine still refuses the key): one matrix over
 all flavours in the order of `get_FullHybr_offdiag` (Trace.F90:2690-2770), pair moves whose creator draws its own flavour
 (`pair_OperAdd` with force_diagonal = .false., Trace.F90:3657-3698; `(2 NBands)^2 / NPairs`, CTQMC.F90:3517-3519), the flavour-blind pair
-count (`is_rempair_offdiag`, Trace.F90:2018-2030), `recalc_sign` (Trace.F90:3500-3546), global moves (CTQMC.F90:4491-4494), tau shifts, `MeasGtauRem_full`
+count (`is_rempair_offdiag`, Trace.F90:2018-2030), `recalc_sign` (Trace.F90:3500-3546), 4-operator moves, global moves (CTQMC.F90:4491-4494), tau shifts, `MeasGtauRem_full`
 (CTQMC.F90:2475-2584) with its normalisation (8752-8753); determinants from scratch (the reference's own `b_full_offdiag` branch,
 CTQMC.F90:3482-3487).  Pinned to EXACT results of a two-orbital impurity whose bath levels couple to both orbitals: the full G_ab(tau)
 matrix -- its orbital-off-diagonal elements change sign along tau -- and all <n_i n_j>."""
@@ -77,8 +77,32 @@ def test_offdiag_interacting_exact(built):
     _compare(_run(p, nchains=48, meas=12000), PAIRS, gex, occ_ex, "offdiag oracle, density-density U = 4")
 
 
+def test_offdiag_kanamori_with_four_operator_moves_exact(built):
+    """Full Kanamori interaction: H_loc does not conserve the particle number per flavour, flavour-unbalanced configurations carry weight
+    through F_01 and only the 4-operator moves (StepAdd4 / StepRem4 with `offdiag`: four independent flavours, (2 NBands)^4, CTQMC.F90:3641,
+    3823, 4353) reach them -- with them the whole G_ab(tau) matrix is exact, at a mean sign of -0.97 (recalc_sign at work); without them
+    G_01 comes out 3-5 x too large (note in tests/_exact_anderson.py)."""
+    p = ea.offdiag_two_orbital_problem(5.0, kanamori=True, NCorr=20, PercentageTauShiftMove=0.02, PercentageGlobalMove=0.02, Percentage4OperatorMove=0.3)
+    gex, occ_ex = ea.solve_general(p, PAIRS)
+    res = _run(p, nchains=48, warm=6000, meas=16000)
+    sign = np.mean([r["sign"] for r in res])
+    assert -0.995 < sign < -0.9                                    # a genuine, mild sign problem
+    n = len(res)
+    gf = np.array([r["gtau-full"].reshape(4, 4, 50, 20).mean(3) for r in res])
+    zs = []
+    for (a, b), ge in zip(PAIRS, gex):
+        g, e = gf[:, a, b].mean(0), gf[:, a, b].std(0, ddof=1) / np.sqrt(n)
+        zs.append((g - ge) / np.sqrt(e ** 2 + 1e-8))
+    z = np.concatenate(zs)
+    occ = np.array([r["occ"] for r in res])
+    zo = ((occ.mean(0) - occ_ex) / np.sqrt(occ.var(0, ddof=1) / n + 1e-8)).ravel()
+    print("offdiag oracle, Kanamori + 4-operator moves: G_ab %d values max |z| %.2f mean z^2 %.2f; occupations max |z| %.2f; sign %.3f"
+          % (z.size, np.abs(z).max(), (z ** 2).mean(), np.abs(zo).max(), sign))
+    assert np.abs(z).max() < 5.0 and (z ** 2).mean() < 2.0 and np.abs(zo).max() < 4.5
+
+
 def test_offdiag_oracle_refuses_unrestated_moves(built):
     from oracle.oracle import OracleChain
-    p = ea.offdiag_two_orbital_problem(5.0, Percentage4OperatorMove=0.1)
+    p = ea.offdiag_two_orbital_problem(5.0, PercentageOuterMove=0.1)
     with pytest.raises(ValueError, match="offdiag"):
         OracleChain(p, seed=1)
