@@ -687,6 +687,21 @@ struct Chain {
         std::vector<double> Mn; int kn = 0;
         LogVal DetNew = full_det(nw, &Mn, &kn);
         LogVal DetRat = ldiv(DetNew, Det);
+        {   // the same ratio by the rank-1 form on the stored inverse (get_LogDetRatPairAdd_full, Trace.F90:2835-2934): S = F_new - R M Q over ALL
+            // flavours, sign (-1)^(row + column) of the new pair in the flavour-major order -- what an engine kernel would compute; logged
+            // beside the from-scratch ratio (columns 18, 19) and compared by tests/test_oracle_offdiag.py
+            std::vector<int> cr, an; flavour_major(ops, cr, an);
+            const int k = (int)cr.size(), fa = ba * 2 + sa, fc = bc * 2 + sc;
+            double S = hybrF_full(tau_a - tau_c, fa, fc);
+            std::vector<double> Q(k), R(k);
+            for (int j = 0; j < k; ++j) { const Op& A = ops[an[j]]; Q[j] = hybrF_full(A.tau - tau_c, A.b * 2 + A.s, fc); }
+            for (int i = 0; i < k; ++i) { const Op& Cc = ops[cr[i]]; R[i] = hybrF_full(tau_a - Cc.tau, fa, Cc.b * 2 + Cc.s); }
+            for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) S -= R[i] * Mfull[i + (size_t)j * k] * Q[j];
+            int pc = 0, pa = 0;                                   // rank of the new creator / annihilator in the flavour-major order
+            for (int i = 0; i < k; ++i) { const Op& Cc = ops[cr[i]]; const int f = Cc.b * 2 + Cc.s; if (f < fc || (f == fc && Cc.tau < tau_c)) ++pc; }
+            for (int j = 0; j < k; ++j) { const Op& A = ops[an[j]]; const int f = A.b * 2 + A.s; if (f < fa || (f == fa && A.tau < tau_a)) ++pa; }
+            rec[18] = std::log(std::fabs(S)); rec[19] = sgn(S) * (((pc + pa) % 2) ? -1.0 : 1.0);
+        }
         std::vector<LogVal> parts;
         LogVal TraceNew = trace_full(nw, outer_sst, &parts);
         double rand = grnd();
@@ -737,6 +752,15 @@ struct Chain {
         std::vector<double> Mn; int kn = 0;
         LogVal DetNew = full_det(nw, &Mn, &kn);
         LogVal DetRat = ldiv(DetNew, Det);
+        {   // rank-1 form of the removal (get_LogDetRatPairRem_full, Trace.F90:2966-2997): the element of the stored inverse at (creator, annihilator)
+            std::vector<int> cr, an; flavour_major(ops, cr, an);
+            const int k = (int)cr.size();
+            const size_t ic_op = o1.ca == 1 ? i1 : i2, ia_op = o1.ca == 2 ? i1 : i2;
+            int pc = 0, pa = 0;
+            for (int i = 0; i < k; ++i) { if (cr[i] == (int)ic_op) pc = i; if (an[i] == (int)ia_op) pa = i; }
+            const double S = Mfull[pc + (size_t)pa * k];
+            rec[18] = std::log(std::fabs(S)); rec[19] = sgn(S) * (((pc + pa) % 2) ? -1.0 : 1.0);
+        }
         std::vector<LogVal> parts;
         LogVal TraceNew = trace_full(nw, outer_sst, &parts);
         LogVal trr = ldiv(TraceNew, Trace);

@@ -101,6 +101,21 @@ def test_offdiag_kanamori_with_four_operator_moves_exact(built):
     assert np.abs(z).max() < 5.0 and (z ** 2).mean() < 2.0 and np.abs(zo).max() < 4.5
 
 
+def test_offdiag_rank1_ratio_equals_from_scratch(built):
+    """The determinant ratio of every pair proposal by the rank-1 form on the stored single inverse (`get_LogDetRatPairAdd_full /
+    Rem_full`, Trace.F90:2835-2997: S = F_new - R M Q over all flavours resp. the inverse's element, sign (-1)^(row + column) in the
+    flavour-major order) equals the from-scratch determinant ratio the oracle walks with -- the formula the engine's flavour-agnostic
+    `det_ratio_add` has to reproduce for `offdiag = 1`."""
+    from oracle.oracle import OracleChain
+    p = ea.offdiag_two_orbital_problem(5.0, kanamori=True, NCorr=20, PercentageTauShiftMove=0.02, PercentageGlobalMove=0.02, Percentage4OperatorMove=0.2)
+    o = OracleChain(p, rng="philox", seed=3, chain=1)
+    log = o.steps(20000, log=True)
+    pm = log[((log[:, 0] == 1) | (log[:, 0] == 2)) & (log[:, 1] != 2) & np.isfinite(log[:, 7])]
+    assert pm.shape[0] > 2000 and (pm[:, 1] == 1).sum() > 300 and (pm[:, 8] < 0).sum() > 500       # many proposals, both signs
+    assert np.abs(pm[:, 7] - pm[:, 18]).max() < 1e-9 and np.array_equal(pm[:, 8], pm[:, 19])
+    assert o.error == 0
+
+
 def test_offdiag_oracle_refuses_unrestated_moves(built):
     from oracle.oracle import OracleChain
     p = ea.offdiag_two_orbital_problem(5.0, PercentageOuterMove=0.1)
