@@ -1,7 +1,8 @@
 // ORACLE -- test infrastructure, NOT product code.
 //
 // CPU restatement of the Z-space CT-HYB Markov chain of w2dynamics' matrix solver
-// (segment=0, offdiag=0, statesampling=0, PercentageOuterMove=0).  Each function
+// (segment=0; the four pair / global / tau-shift moves, user symmetry moves, outer pair moves, 4-operator moves, state sampling,
+// the Matsubara estimator; offdiag=1 is restated for pair, 4-operator, global and tau-shift moves as groundwork for the engine).  Each function
 // cites the reference lines (relative to /root/reference/src/ctqmc_fortran) it
 // follows.  Representation differs from the reference on purpose (time-sorted
 // arrays instead of linked lists, no ket/bra caches: as a checker the local trace is
@@ -17,7 +18,10 @@
 // unpinned" by the reference.  The pins are (i) analytic limits, (ii) from-scratch
 // LU vs fast updates, (iii) the reference's C++ RNG (src/mtrng/random.cc compiled
 // unchanged into oracle/_ref/libmtrng.so) whose stream this oracle can consume in
-// the reference's draw order.
+// the reference's draw order, (iv) EXACT results of interacting impurity + bath models
+// from dense diagonalisation (tests/_exact_anderson.py): G(tau), Legendre coefficients,
+// G(iw), <n_i n_j>, rho1 / rho2, with every optional move type, state sampling and
+// off-diagonal hybridisation (tests/test_oracle_pins.py, test_matsubara.py, test_oracle_offdiag.py).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm
 // may load this library.
